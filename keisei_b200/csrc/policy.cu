@@ -1,0 +1,443 @@
+// policy.cu — masked-policy kernels over the 11,259-action space (HBM-bound, one CTA per row).
+//
+//   kb_policy_sample     rollout:  mask -> softmax -> sample -> log-prob, + scalar value (K11, K12)
+//                        reference: keisei/training/katago_ppo.py:589-613, value_adapter.py:79-96
+//   kb_ppo_policy_fwd    update:   masked log-softmax, gather, entropy, clipped surrogate (K13, K14)
+//                        reference: keisei/training/katago_ppo.py:33-43, :858-888
+//   kb_ppo_policy_bwd    update:   d(loss)/d(logits), written once
+//   kb_value_losses_*    update:   W/D/L cross-entropy (ignore_index=-1) + score MSE (K15)
+//                        reference: keisei/training/katago_ppo.py:46-57, :910-912; value_adapter.py:98-126
+//
+// Each row is staged once into shared memory as fp32 masked logits (illegal -> -inf); every
+// reduction afterwards runs out of shared memory, so HBM sees one read of the logits and one of
+// the mask per pass. Logit rows may be padded (row_stride >= A); 16-byte vector loads are used
+// when the row base is 16-byte aligned, scalar loads otherwise.
+#include "kb_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T> struct Vec4;  // 4 consecutive logits
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&o)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  static constexpr int kAlign = 16;
+};
+template <> struct Vec4<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&o)[4]) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    o[0] = __uint_as_float(v.x << 16); o[1] = __uint_as_float(v.x & 0xffff0000u);
+    o[2] = __uint_as_float(v.y << 16); o[3] = __uint_as_float(v.y & 0xffff0000u);
+  }
+  static constexpr int kAlign = 8;
+};
+
+// Stage one row: s_row[i] = legal ? logit : -inf. Returns per-thread (legal count, any NaN in raw logits).
+template <typename T>
+__device__ __forceinline__ void stage_row(const T* __restrict__ lrow, const uint8_t* __restrict__ mrow,
+                                          int A, float* s_row, int& legal, int& has_nan) {
+  legal = 0; has_nan = 0;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(lrow) % Vec4<T>::kAlign) == 0);
+  const int A4 = vec_ok ? (A & ~3) : 0;
+  for (int i = threadIdx.x * 4; i < A4; i += kThreads * 4) {
+    float v[4];
+    Vec4<T>::load(lrow + i, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool ok = mrow[i + j] != 0;
+      has_nan |= (v[j] != v[j]);
+      legal += ok;
+      s_row[i + j] = ok ? v[j] : -INFINITY;
+    }
+  }
+  for (int i = A4 + threadIdx.x; i < A; i += kThreads) {
+    const float v = kb_to_float<T>(lrow[i]);
+    const bool ok = mrow[i] != 0;
+    has_nan |= (v != v);
+    legal += ok;
+    s_row[i] = ok ? v : -INFINITY;
+  }
+}
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ---------------------------------------------------------------------------------------------
+// Rollout: sample + log-prob + scalar value
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) policy_sample_kernel(
+    const T* __restrict__ logits, long long row_stride, const uint8_t* __restrict__ mask,
+    const float* __restrict__ value_logits, const float* __restrict__ score_lead, float alpha,
+    int A, unsigned long long seed, unsigned long long offset, int logprob_mode,
+    long long* __restrict__ actions, float* __restrict__ logp_out, float* __restrict__ value_out,
+    int* __restrict__ legal_count, int* __restrict__ flags) {
+  extern __shared__ float s_row[];
+  __shared__ float scratch[32];
+  __shared__ float s_best[kThreads / 32];
+  __shared__ int s_besti[kThreads / 32];
+  const int row = blockIdx.x;
+  const T* lrow = logits + (size_t)row * row_stride;
+  const uint8_t* mrow = mask + (size_t)row * A;
+  int legal, has_nan;
+  stage_row<T>(lrow, mrow, A, s_row, legal, has_nan);
+  __syncthreads();
+  const int n_legal = (int)(kb_block_sum((float)legal, scratch) + 0.5f);
+  if (threadIdx.x == 0) {
+    legal_count[row] = n_legal;
+    if (n_legal == 0) atomicAdd(&flags[0], 1);
+  }
+  // scalar value (K12): P(W) - P(L), optional score blend
+  if (threadIdx.x == 32 && value_out != nullptr) {
+    const float a = value_logits[row * 3 + 0], b = value_logits[row * 3 + 1], c = value_logits[row * 3 + 2];
+    const float m = fmaxf(a, fmaxf(b, c));
+    const float ea = expf(a - m), eb = expf(b - m), ec = expf(c - m);
+    const float inv = 1.f / (ea + eb + ec);
+    float v = ea * inv - ec * inv;
+    if (alpha != 0.f && score_lead != nullptr) {
+      const float s = fminf(fmaxf(score_lead[row], -1.f), 1.f);
+      v = (1.f - alpha) * v + alpha * s;
+    }
+    value_out[row] = v;
+  }
+  if (n_legal == 0) {  // reference raises; keep outputs defined
+    if (threadIdx.x == 0) { actions[row] = 0; logp_out[row] = __int_as_float(0x7fc00000); }
+    return;
+  }
+  // pass 1: max, and Gumbel-max argmax among legal entries
+  float m = -INFINITY, best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int i = threadIdx.x; i < A; i += kThreads) {
+    const float l = s_row[i];
+    if (l == -INFINITY) continue;  // illegal (or a legal -inf logit: probability exactly 0)
+    m = fmaxf(m, l);
+    const kb_philox4 r = kb_philox4x32_10(seed, (unsigned long long)row,
+                                          (offset << 32) | (unsigned long long)(unsigned)i);
+    const float u = kb_u32_to_unit(r.x);
+    const float g = -__logf(-__logf(u));
+    const float sc = l + g;
+    if (sc > best || (sc == best && i < besti)) { best = sc; besti = i; }
+  }
+  // NaN logits on a legal entry: propagate through max like torch (m becomes NaN-free here, the
+  // reference guard for NaN lives in update(); select_actions has none), keep going.
+  m = kb_block_max(m, scratch);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = best; s_besti[threadIdx.x >> 5] = besti; }
+  // pass 2: normaliser
+  float s = 0.f;
+  for (int i = threadIdx.x; i < A; i += kThreads) s += __expf(s_row[i] - m);  // exp(-inf)=0
+  const float S = kb_block_sum(s, scratch);  // includes the __syncthreads that publishes s_best
+  if (threadIdx.x < 32) {
+    float b = threadIdx.x < kThreads / 32 ? s_best[threadIdx.x] : -INFINITY;
+    int bi = threadIdx.x < kThreads / 32 ? s_besti[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, b, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > b || (ob == b && oi < bi)) { b = ob; bi = oi; }
+    }
+    if (threadIdx.x == 0) { s_besti[0] = bi; }
+  }
+  __syncthreads();
+  int a = s_besti[0];
+  if (a == 0x7fffffff) {  // every legal logit was -inf/NaN: fall back to the first legal index
+    int first = 0x7fffffff;
+    for (int i = threadIdx.x; i < A; i += kThreads) if (mrow[i] != 0) { first = min(first, i); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_besti[threadIdx.x >> 5] = first;
+    __syncthreads();
+    a = s_besti[0];
+    for (int w = 1; w < kThreads / 32; ++w) a = min(a, s_besti[w]);
+  }
+  const float la = s_row[a];
+  float lp;
+  if (logprob_mode == 0) {
+    // fp32 reference: Categorical(probs).log_prob = log(clamp(p, eps, 1-eps)), eps = finfo(float32).eps
+    const float eps = 1.1920928955078125e-07f;
+    const float p = expf(la - m) / S;
+    lp = logf(fminf(fmaxf(p, eps), 1.f - eps));
+  } else {
+    // bf16 reference (autocast logits -> bf16 probs): probs rounded to bf16, renormalised in bf16,
+    // clamped with eps = finfo(bfloat16).eps = 2^-7, log rounded to bf16.
+    float q = 0.f;
+    const float invS = 1.f / S;
+    for (int i = threadIdx.x; i < A; i += kThreads) q += bf16_round(__expf(s_row[i] - m) * invS);
+    const float Q = bf16_round(kb_block_sum(q, scratch));
+    const float eps = 0.0078125f;
+    const float p = bf16_round(bf16_round(expf(la - m) * invS) / Q);
+    lp = bf16_round(logf(fminf(fmaxf(p, eps), 1.f - eps)));
+  }
+  if (threadIdx.x == 0) { actions[row] = (long long)a; logp_out[row] = lp; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Update: forward (per row) + reduction + backward
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) ppo_policy_fwd_kernel(
+    const T* __restrict__ logits, long long row_stride, const uint8_t* __restrict__ mask,
+    const long long* __restrict__ actions, int A, float* __restrict__ new_logp,
+    float* __restrict__ row_entropy, float* __restrict__ row_lse, int* __restrict__ flags) {
+  extern __shared__ float s_row[];
+  __shared__ float scratch[32];
+  const int row = blockIdx.x;
+  const T* lrow = logits + (size_t)row * row_stride;
+  const uint8_t* mrow = mask + (size_t)row * A;
+  int legal, has_nan;
+  stage_row<T>(lrow, mrow, A, s_row, legal, has_nan);
+  __syncthreads();
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < A; i += kThreads) m = fmaxf(m, s_row[i]);
+  m = kb_block_max(m, scratch);
+  const int n_legal = (int)(kb_block_sum((float)legal, scratch) + 0.5f);
+  const int any_nan = (int)(kb_block_sum((float)has_nan, scratch) + 0.5f);
+  if (threadIdx.x == 0) {
+    if (n_legal == 0) atomicAdd(&flags[0], 1);
+    if (any_nan != 0) atomicAdd(&flags[1], 1);
+  }
+  if (n_legal == 0) {
+    if (threadIdx.x == 0) { new_logp[row] = 0.f; row_entropy[row] = 0.f; row_lse[row] = 0.f; }
+    return;
+  }
+  // S = sum exp(l-m);  U = sum exp(l-m)*(l-m)  (legal only; exp(-inf)=0 and the product is skipped)
+  float s = 0.f, u = 0.f;
+  for (int i = threadIdx.x; i < A; i += kThreads) {
+    const float d = s_row[i] - m;
+    if (d > -INFINITY) { const float e = __expf(d); s += e; u += e * d; }
+  }
+  const float S = kb_block_sum(s, scratch);
+  const float U = kb_block_sum(u, scratch);
+  if (threadIdx.x == 0) {
+    const float logS = logf(S);
+    const long long a = actions[row];
+    const float la = (a >= 0 && a < A) ? s_row[a] : -INFINITY;
+    new_logp[row] = (la - m) - logS;
+    row_entropy[row] = logS - U / S;  // -sum p*logp over legal
+    row_lse[row] = m + logS;
+  }
+}
+
+// Single CTA: clipped-surrogate mean, entropy mean, and the per-row d(policy_loss)/d(new_logp).
+__global__ void __launch_bounds__(1024) ppo_policy_reduce_kernel(
+    const float* __restrict__ new_logp, const float* __restrict__ old_logp,
+    const float* __restrict__ adv, const float* __restrict__ row_entropy, int B, float clip_eps,
+    float* __restrict__ out2 /* [policy_loss, entropy] */, float* __restrict__ dlogp /* (B,) */) {
+  __shared__ double scratch[32];
+  double ls = 0.0, es = 0.0;
+  const float lo = 1.f - clip_eps, hi = 1.f + clip_eps;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float ratio = expf(new_logp[i] - old_logp[i]);
+    const float a = adv[i];
+    const float s1 = ratio * a;
+    const float rc = fminf(fmaxf(ratio, lo), hi);
+    const float s2 = rc * a;
+    ls += (double)fminf(s1, s2);
+    es += (double)row_entropy[i];
+    // torch.min backward: ties split evenly; clamp passes gradient when lo <= ratio <= hi
+    const float inr = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+    float g;
+    if (s1 < s2) g = a; else if (s1 > s2) g = a * inr; else g = 0.5f * a + 0.5f * a * inr;
+    if (!(s1 == s1) || !(s2 == s2)) g = __int_as_float(0x7fc00000);
+    dlogp[i] = -(g * ratio) / (float)B;  // d(-mean(min))/d new_logp
+  }
+  const double L = kb_block_sum_d(ls, scratch);
+  const double E = kb_block_sum_d(es, scratch);
+  if (threadIdx.x == 0) { out2[0] = (float)(-L / (double)B); out2[1] = (float)(E / (double)B); }
+}
+
+// dlogits[i] = legal ? gP*dlogp[row]*(onehot - p_i) + gH/B * (-p_i*(logp_i + H_row)) : 0
+template <typename T>
+__global__ void __launch_bounds__(kThreads) ppo_policy_bwd_kernel(
+    const T* __restrict__ logits, long long row_stride, const uint8_t* __restrict__ mask,
+    const long long* __restrict__ actions, int A, int B, const float* __restrict__ row_lse,
+    const float* __restrict__ row_entropy, const float* __restrict__ dlogp,
+    const float* __restrict__ g_policy, const float* __restrict__ g_entropy,
+    T* __restrict__ dlogits, long long d_row_stride) {
+  const int row = blockIdx.x;
+  const T* lrow = logits + (size_t)row * row_stride;
+  const uint8_t* mrow = mask + (size_t)row * A;
+  T* drow = dlogits + (size_t)row * d_row_stride;
+  const float lse = row_lse[row], H = row_entropy[row];
+  const float gl = g_policy[0] * dlogp[row];
+  const float gh = g_entropy[0] / (float)B;
+  const int a = (int)actions[row];
+  for (int i = threadIdx.x; i < A; i += kThreads) {
+    float d = 0.f;
+    if (mrow[i] != 0) {
+      const float lp = kb_to_float<T>(lrow[i]) - lse;
+      const float p = __expf(lp);
+      d = gl * ((i == a ? 1.f : 0.f) - p);
+      if (p > 0.f) d -= gh * p * (lp + H);
+    }
+    drow[i] = kb_from_float<T>(d);
+  }
+  for (int i = A + threadIdx.x; i < d_row_stride; i += kThreads) drow[i] = kb_from_float<T>(0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// W/D/L cross-entropy (ignore_index = -1, mean over valid rows) + score MSE. Single CTA.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) value_losses_fwd_kernel(
+    const float* __restrict__ value_logits, const long long* __restrict__ cats,
+    const float* __restrict__ score_pred, const float* __restrict__ score_tgt, int B,
+    float* __restrict__ out3 /* [value_loss, score_loss, n_valid] */) {
+  __shared__ double scratch[32];
+  double ce = 0.0, nv = 0.0, se = 0.0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const long long c = cats[i];
+    if (c >= 0 && c < 3) {
+      const float a = value_logits[i * 3], b = value_logits[i * 3 + 1], d = value_logits[i * 3 + 2];
+      const float m = fmaxf(a, fmaxf(b, d));
+      const float lse = m + logf(expf(a - m) + expf(b - m) + expf(d - m));
+      ce += (double)(lse - value_logits[i * 3 + c]);
+      nv += 1.0;
+    }
+    const float e = score_pred[i] - score_tgt[i];
+    se += (double)(e * e);
+  }
+  const double CE = kb_block_sum_d(ce, scratch);
+  const double NV = kb_block_sum_d(nv, scratch);
+  const double SE = kb_block_sum_d(se, scratch);
+  if (threadIdx.x == 0) {
+    out3[0] = NV > 0.0 ? (float)(CE / NV) : 0.f;  // all-ignored -> graph-connected zero
+    out3[1] = (float)(SE / (double)B);
+    out3[2] = (float)NV;
+  }
+}
+
+__global__ void __launch_bounds__(256) value_losses_bwd_kernel(
+    const float* __restrict__ value_logits, const long long* __restrict__ cats,
+    const float* __restrict__ score_pred, const float* __restrict__ score_tgt, int B,
+    const float* __restrict__ out3, const float* __restrict__ g_value, const float* __restrict__ g_score,
+    float* __restrict__ dvalue_logits, float* __restrict__ dscore) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const float nvalid = out3[2];
+  const long long c = cats[i];
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+  if (c >= 0 && c < 3 && nvalid > 0.f) {
+    const float a = value_logits[i * 3], b = value_logits[i * 3 + 1], d = value_logits[i * 3 + 2];
+    const float m = fmaxf(a, fmaxf(b, d));
+    const float ea = expf(a - m), eb = expf(b - m), ed = expf(d - m);
+    const float inv = 1.f / (ea + eb + ed);
+    const float g = g_value[0] / nvalid;
+    d0 = g * (ea * inv - (c == 0 ? 1.f : 0.f));
+    d1 = g * (eb * inv - (c == 1 ? 1.f : 0.f));
+    d2 = g * (ed * inv - (c == 2 ? 1.f : 0.f));
+  }
+  dvalue_logits[i * 3] = d0; dvalue_logits[i * 3 + 1] = d1; dvalue_logits[i * 3 + 2] = d2;
+  dscore[i] = g_score[0] * 2.f * (score_pred[i] - score_tgt[i]) / (float)B;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { kb_set_error("cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e)); return KB_ERR_CUDA; }
+  }
+  return KB_OK;
+}
+
+}  // namespace
+
+extern "C" int kb_policy_sample(const void* logits, int logits_dtype, long long row_stride,
+                                const uint8_t* mask, const float* value_logits, const float* score_lead,
+                                float alpha, int B, int A, unsigned long long seed,
+                                unsigned long long offset, int logprob_mode, long long* actions,
+                                float* logp, float* values, int* legal_count, int* flags,
+                                cudaStream_t stream) {
+  KB_CHECK_ARG(B >= 0 && A > 0 && row_stride >= A, "kb_policy_sample: bad shape B=%d A=%d stride=%lld", B, A, row_stride);
+  KB_CHECK_ARG(logits_dtype == KB_F32 || logits_dtype == KB_BF16, "kb_policy_sample: bad dtype %d", logits_dtype);
+  if (B == 0) return KB_OK;
+  KB_CHECK_ARG(logits && mask && actions && logp && legal_count && flags, "kb_policy_sample: null pointer");
+  KB_CHECK_ARG(values == nullptr || value_logits != nullptr, "kb_policy_sample: values requested without value_logits");
+  const size_t smem = (size_t)A * sizeof(float);
+  KB_CHECK_ARG(smem <= 200 * 1024, "kb_policy_sample: action space %d too large for one CTA", A);
+  if (logits_dtype == KB_F32) {
+    if (int r = set_smem(policy_sample_kernel<float>, smem)) return r;
+    policy_sample_kernel<float><<<B, kThreads, smem, stream>>>((const float*)logits, row_stride, mask, value_logits,
+        score_lead, alpha, A, seed, offset, logprob_mode, actions, logp, values, legal_count, flags);
+  } else {
+    if (int r = set_smem(policy_sample_kernel<bf16>, smem)) return r;
+    policy_sample_kernel<bf16><<<B, kThreads, smem, stream>>>((const bf16*)logits, row_stride, mask, value_logits,
+        score_lead, alpha, A, seed, offset, logprob_mode, actions, logp, values, legal_count, flags);
+  }
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+extern "C" int kb_ppo_policy_fwd(const void* logits, int logits_dtype, long long row_stride,
+                                 const uint8_t* mask, const long long* actions,
+                                 const float* old_logp, const float* adv, int B, int A, float clip_eps,
+                                 float* new_logp, float* row_entropy, float* row_lse, float* dlogp,
+                                 float* out2, int* flags, cudaStream_t stream) {
+  KB_CHECK_ARG(B > 0 && A > 0 && row_stride >= A, "kb_ppo_policy_fwd: bad shape B=%d A=%d stride=%lld", B, A, row_stride);
+  KB_CHECK_ARG(logits_dtype == KB_F32 || logits_dtype == KB_BF16, "kb_ppo_policy_fwd: bad dtype %d", logits_dtype);
+  KB_CHECK_ARG(logits && mask && actions && old_logp && adv && new_logp && row_entropy && row_lse && dlogp && out2 && flags,
+               "kb_ppo_policy_fwd: null pointer");
+  const size_t smem = (size_t)A * sizeof(float);
+  KB_CHECK_ARG(smem <= 200 * 1024, "kb_ppo_policy_fwd: action space %d too large for one CTA", A);
+  if (logits_dtype == KB_F32) {
+    if (int r = set_smem(ppo_policy_fwd_kernel<float>, smem)) return r;
+    ppo_policy_fwd_kernel<float><<<B, kThreads, smem, stream>>>((const float*)logits, row_stride, mask, actions, A,
+                                                                  new_logp, row_entropy, row_lse, flags);
+  } else {
+    if (int r = set_smem(ppo_policy_fwd_kernel<bf16>, smem)) return r;
+    ppo_policy_fwd_kernel<bf16><<<B, kThreads, smem, stream>>>((const bf16*)logits, row_stride, mask, actions, A,
+                                                                 new_logp, row_entropy, row_lse, flags);
+  }
+  KB_CUDA_LAUNCH_CHECK();
+  ppo_policy_reduce_kernel<<<1, 1024, 0, stream>>>(new_logp, old_logp, adv, row_entropy, B, clip_eps, out2, dlogp);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+extern "C" int kb_ppo_policy_bwd(const void* logits, int logits_dtype, long long row_stride,
+                                 const uint8_t* mask, const long long* actions, int B, int A,
+                                 const float* row_lse, const float* row_entropy, const float* dlogp,
+                                 const float* g_policy, const float* g_entropy, void* dlogits,
+                                 long long d_row_stride, cudaStream_t stream) {
+  KB_CHECK_ARG(B > 0 && A > 0 && row_stride >= A && d_row_stride >= A, "kb_ppo_policy_bwd: bad shape");
+  KB_CHECK_ARG(logits_dtype == KB_F32 || logits_dtype == KB_BF16, "kb_ppo_policy_bwd: bad dtype %d", logits_dtype);
+  KB_CHECK_ARG(logits && mask && actions && row_lse && row_entropy && dlogp && g_policy && g_entropy && dlogits,
+               "kb_ppo_policy_bwd: null pointer");
+  if (logits_dtype == KB_F32)
+    ppo_policy_bwd_kernel<float><<<B, kThreads, 0, stream>>>((const float*)logits, row_stride, mask, actions, A, B, row_lse,
+        row_entropy, dlogp, g_policy, g_entropy, (float*)dlogits, d_row_stride);
+  else
+    ppo_policy_bwd_kernel<bf16><<<B, kThreads, 0, stream>>>((const bf16*)logits, row_stride, mask, actions, A, B, row_lse,
+        row_entropy, dlogp, g_policy, g_entropy, (bf16*)dlogits, d_row_stride);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+extern "C" int kb_value_losses_fwd(const float* value_logits, const long long* cats, const float* score_pred,
+                                   const float* score_tgt, int B, float* out3, cudaStream_t stream) {
+  KB_CHECK_ARG(B > 0, "kb_value_losses_fwd: B must be > 0");
+  KB_CHECK_ARG(value_logits && cats && score_pred && score_tgt && out3, "kb_value_losses_fwd: null pointer");
+  value_losses_fwd_kernel<<<1, 1024, 0, stream>>>(value_logits, cats, score_pred, score_tgt, B, out3);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+extern "C" int kb_value_losses_bwd(const float* value_logits, const long long* cats, const float* score_pred,
+                                   const float* score_tgt, int B, const float* out3, const float* g_value,
+                                   const float* g_score, float* dvalue_logits, float* dscore,
+                                   cudaStream_t stream) {
+  KB_CHECK_ARG(B > 0, "kb_value_losses_bwd: B must be > 0");
+  KB_CHECK_ARG(value_logits && cats && score_pred && score_tgt && out3 && g_value && g_score && dvalue_logits && dscore,
+               "kb_value_losses_bwd: null pointer");
+  value_losses_bwd_kernel<<<kb_ceil_div(B, 256), 256, 0, stream>>>(value_logits, cats, score_pred, score_tgt, B, out3,
+                                                                   g_value, g_score, dvalue_logits, dscore);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}

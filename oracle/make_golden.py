@@ -1,0 +1,226 @@
+"""Generate tests/golden/*.npz by running the REAL reference (imported read-only from
+/root/reference) on seeded inputs. Run in the build container only:
+
+    python oracle/make_golden.py
+
+The GPU box has no /root/reference; tests read the committed .npz files. TEST INFRASTRUCTURE.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+TINY = dict(num_blocks=2, channels=32, se_reduction=4, global_pool_channels=16, policy_channels=8,
+            value_fc_size=16, score_fc_size=16, obs_channels=50)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def make_inputs(B: int, seed: int, A: int = 11259):
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randn(B, 50, 9, 9, generator=g)
+    mask = torch.rand(B, A, generator=g) < 0.01
+    actions = torch.randint(0, A, (B,), generator=g)
+    mask[torch.arange(B), actions] = True
+    old_logp = -3.0 * torch.rand(B, generator=g)
+    adv = torch.randn(B, generator=g)
+    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+    cats = torch.randint(-1, 3, (B,), generator=g)
+    score_t = torch.randn(B, generator=g).clamp(-1.5, 1.5)
+    return obs, mask, actions, old_logp, adv, cats, score_t
+
+
+def golden_model():
+    from keisei.training.model_registry import build_model
+    from keisei.training.katago_ppo import ppo_clip_loss, wdl_cross_entropy_loss
+    import torch.nn.functional as F
+
+    torch.manual_seed(0)
+    model = build_model("se_resnet", dict(TINY))
+    # make BN affine/running stats non-trivial
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, buf in model.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(0.1 * torch.randn(buf.shape, generator=g))
+            elif name.endswith("running_var"):
+                buf.copy_(0.5 + torch.rand(buf.shape, generator=g))
+        for name, p in model.named_parameters():
+            if ".bn" in name or "_bn" in name:
+                if name.endswith("weight"):
+                    p.copy_(0.5 + torch.rand(p.shape, generator=g))
+                else:
+                    p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    B = 6
+    obs, mask, actions, old_logp, adv, cats, score_t = make_inputs(B, seed=2)
+
+    out = {f"sd/{k}": _np(v) for k, v in sd0.items()}
+    out.update(obs=_np(obs), mask=_np(mask), actions=_np(actions), old_logp=_np(old_logp), adv=_np(adv),
+               cats=_np(cats), score_t=_np(score_t))
+
+    model.eval()
+    with torch.no_grad():
+        o = model(obs)
+    out.update(eval_policy=_np(o.policy_logits.contiguous()), eval_value=_np(o.value_logits), eval_score=_np(o.score_lead))
+
+    model.train()
+    o = model(obs)
+    flat = o.policy_logits.reshape(B, -1)
+    masked = flat.masked_fill(~mask, float("-inf"))
+    logp_all = F.log_softmax(masked, dim=-1)
+    new_logp = logp_all.gather(1, actions.unsqueeze(1)).squeeze(1)
+    pl = ppo_clip_loss(new_logp, old_logp, adv, 0.2)
+    probs = logp_all.exp()
+    ent = -(probs * logp_all.masked_fill(~mask, 0.0)).sum(-1).mean()
+    vl = wdl_cross_entropy_loss(o.value_logits, cats)
+    sl = F.mse_loss(o.score_lead.squeeze(-1), score_t)
+    loss = 1.0 * pl + 1.5 * vl + 0.02 * sl - 0.01 * ent
+    loss.backward()
+    out.update(train_policy=_np(o.policy_logits.contiguous()), train_value=_np(o.value_logits), train_score=_np(o.score_lead),
+               loss=_np(loss), policy_loss=_np(pl), value_loss=_np(vl), score_loss=_np(sl), entropy=_np(ent),
+               new_logp=_np(new_logp))
+    for k, p in model.named_parameters():
+        out[f"grad/{k}"] = _np(p.grad)
+    for k, v in model.state_dict().items():
+        if "running_" in k or "num_batches" in k:
+            out[f"sd_after/{k}"] = _np(v)
+    np.savez_compressed(OUT / "seresnet_tiny.npz", **out)
+    print("seresnet_tiny.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB raw")
+
+
+def golden_gae():
+    from keisei.training.gae import compute_gae, compute_gae_gpu, compute_gae_padded, compute_gae_padded_gpu
+    g = torch.Generator().manual_seed(3)
+    T, N = 37, 7
+    r = torch.randn(T, N, generator=g)
+    v = 0.3 * torch.randn(T, N, generator=g)
+    term = torch.rand(T, N, generator=g) < 0.1
+    nv = torch.randn(N, generator=g)
+    ov = torch.full((T, N), float("nan"))
+    sel = torch.rand(T, N, generator=g) < 0.15
+    ov[sel] = torch.randn(int(sel.sum()), generator=g)
+    ov[-1, 0] = 0.77  # override at the last step too
+    out = dict(r=_np(r), v=_np(v), term=_np(term), nv=_np(nv), ov=_np(ov))
+    out["adv_plain"] = _np(compute_gae(r, v, term, nv, 0.99, 0.95))
+    out["adv_plain_gpufn"] = _np(compute_gae_gpu(r, v, term, nv, 0.99, 0.95))
+    out["adv_override"] = _np(compute_gae(r, v, term, nv, 0.99, 0.95, next_value_override=ov))
+    out["adv_override_gpufn"] = _np(compute_gae_gpu(r, v, term, nv, 0.99, 0.95, next_value_override=ov))
+    out["adv_termfloat"] = _np(compute_gae(r, v, term.float(), nv, 0.97, 0.9))
+    out["adv_1d"] = _np(compute_gae(r[:, 0], v[:, 0], term[:, 0], nv[0], 0.99, 0.95))
+    lengths = torch.tensor([37, 5, 1, 20, 36, 12, 37])
+    termp = term.float().clone()
+    for i, L in enumerate(lengths.tolist()):
+        termp[L:, i] = 1.0
+    out["lengths"] = _np(lengths)
+    out["termp"] = _np(termp)
+    out["adv_padded"] = _np(compute_gae_padded(r, v, termp, nv, lengths, 0.99, 0.95))
+    out["adv_padded_gpufn"] = _np(compute_gae_padded_gpu(r, v, termp, nv, lengths, 0.99, 0.95))
+    out["adv_padded_override"] = _np(compute_gae_padded(r, v, termp, nv, lengths, 0.99, 0.95, next_value_override=ov))
+    a = out["adv_override"].reshape(-1)
+    at = torch.from_numpy(a.copy())
+    out["adv_override_normalized"] = _np((at - at.mean()) / (at.std() + 1e-8))
+    # the reference's hand-computed known answers (tests/test_gae.py:10-40, test_katago_ppo.py:449-489)
+    out["known_adv_3step"] = _np(compute_gae(torch.tensor([1.0, 1.0, 1.0]), torch.tensor([0.5, 0.5, 0.5]),
+                                             torch.tensor([False, False, False]), torch.tensor(0.5), 0.99, 0.95))
+    np.savez_compressed(OUT / "gae.npz", **out)
+    print("gae.npz ok")
+
+
+def golden_rollout():
+    """select_actions log-prob semantics for given actions, fp32 and bf16 (katago_ppo.py:599-613)."""
+    from keisei.training.katago_ppo import KataGoPPOAlgorithm
+    from keisei.training.value_adapter import get_value_adapter
+    g = torch.Generator().manual_seed(4)
+    B, A = 8, 11259
+    logits = 2.0 * torch.randn(B, A, generator=g)
+    mask = torch.rand(B, A, generator=g) < 0.01
+    mask[0] = False
+    mask[0, 1234] = True  # single legal action -> log_prob ~ 0
+    logits[1, :] = -5.0
+    mask[1, 100] = True
+    logits[1, 100] = 12.0  # near-certain action (exercises the 1-eps clamp)
+    actions = torch.stack([torch.nonzero(mask[i])[torch.randint(0, int(mask[i].sum()), (1,), generator=g)][0, 0] for i in range(B)])
+    actions[1] = 100
+    out = dict(logits=_np(logits), mask=_np(mask), actions=_np(actions))
+    for name, lg in (("f32", logits), ("bf16", logits.to(torch.bfloat16))):
+        masked = lg.masked_fill(~mask, float("-inf"))
+        probs = torch.softmax(masked, dim=-1)
+        dist = torch.distributions.Categorical(probs, validate_args=False)
+        out[f"logp_{name}"] = _np(dist.log_prob(actions).float())
+        # low-probability action as well (exercises the eps clamp from below)
+        worst = torch.where(mask, lg.float(), torch.full_like(lg.float(), float("inf"))).argmin(dim=-1)
+        out[f"logp_worst_{name}"] = _np(dist.log_prob(worst).float())
+        out["worst"] = _np(worst)
+    vl = torch.randn(B, 3, generator=g)
+    sc = 2.0 * torch.randn(B, 1, generator=g)
+    out.update(value_logits=_np(vl), score_lead=_np(sc))
+    out["scalar_value"] = _np(KataGoPPOAlgorithm.scalar_value(vl))
+    ad = get_value_adapter("multi_head", 1.5, 0.02, 0.3)
+    out["scalar_value_blend03"] = _np(ad.scalar_value_blended(vl, sc))
+    np.savez_compressed(OUT / "rollout.npz", **out)
+    print("rollout.npz ok")
+
+
+def golden_update():
+    """One reference KataGoPPOAlgorithm.update() over a tiny (T,N) buffer, single minibatch."""
+    from keisei.training.model_registry import build_model
+    from keisei.training.katago_ppo import KataGoPPOAlgorithm, KataGoPPOParams, KataGoRolloutBuffer
+    torch.manual_seed(5)
+    model = build_model("se_resnet", dict(TINY))
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    T, N, A = 6, 4, 11259
+    g = torch.Generator().manual_seed(6)
+    buf = KataGoRolloutBuffer(N, (50, 9, 9), A)
+    steps = []
+    for t in range(T):
+        obs = torch.randn(N, 50, 9, 9, generator=g)
+        mask = torch.rand(N, A, generator=g) < 0.01
+        actions = torch.randint(0, A, (N,), generator=g)
+        mask[torch.arange(N), actions] = True
+        logp = -3.0 * torch.rand(N, generator=g)
+        values = 0.3 * torch.randn(N, generator=g)
+        term = torch.rand(N, generator=g) < 0.2
+        rewards = torch.where(term, torch.sign(torch.randn(N, generator=g)), torch.zeros(N))
+        cats = torch.where(term, torch.randint(0, 3, (N,), generator=g), torch.full((N,), -1))
+        score_t = torch.randn(N, generator=g).clamp(-1.5, 1.5)
+        ov = torch.full((N,), float("nan"))
+        if t == 2:
+            ov[1] = 0.25
+        steps.append(dict(obs=obs, actions=actions, logp=logp, values=values, rewards=rewards, term=term,
+                          mask=mask, cats=cats, score_t=score_t, ov=ov))
+        buf.add(obs, actions, logp, values, rewards, term, term, mask, cats, score_t, next_value_override=ov)
+    next_values = torch.randn(N, generator=g)
+    params = KataGoPPOParams(batch_size=T * N, epochs_per_batch=1, learning_rate=1e-3)
+    algo = KataGoPPOAlgorithm(params, model)
+    metrics = algo.update(buf, next_values)
+    out = {f"sd/{k}": _np(v) for k, v in sd0.items()}
+    for k in steps[0]:
+        out[f"steps/{k}"] = np.stack([_np(s[k]) for s in steps])
+    out["next_values"] = _np(next_values)
+    for k, v in metrics.items():
+        out[f"metrics/{k}"] = np.float64(v)
+    for k, v in model.state_dict().items():
+        out[f"sd_after/{k}"] = _np(v)
+    np.savez_compressed(OUT / "update_tiny.npz", **out)
+    print("update_tiny.npz ok", metrics)
+
+
+if __name__ == "__main__":
+    if not REF.exists():
+        sys.exit("needs /root/reference (build container only)")
+    sys.path.insert(0, str(REF))
+    torch.set_num_threads(4)
+    OUT.mkdir(parents=True, exist_ok=True)
+    golden_gae()
+    golden_rollout()
+    golden_model()
+    golden_update()
