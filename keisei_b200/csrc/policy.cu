@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(kThreads) policy_sample_kernel(
     const T* __restrict__ logits, long long row_stride, const uint8_t* __restrict__ mask,
     const float* __restrict__ value_logits, const float* __restrict__ score_lead, float alpha,
     int A, unsigned long long seed, unsigned long long offset, int logprob_mode,
+    const long long* __restrict__ forced_actions,
     long long* __restrict__ actions, float* __restrict__ logp_out, float* __restrict__ value_out,
     int* __restrict__ legal_count, int* __restrict__ flags) {
   extern __shared__ float s_row[];
@@ -147,6 +148,10 @@ __global__ void __launch_bounds__(kThreads) policy_sample_kernel(
   }
   __syncthreads();
   int a = s_besti[0];
+  if (forced_actions != nullptr) {  // evaluate the log-prob of a caller-chosen action instead
+    const long long fa = forced_actions[row];
+    a = (fa >= 0 && fa < A) ? (int)fa : 0;
+  }
   if (a == 0x7fffffff) {  // every legal logit was -inf/NaN: fall back to the first legal index
     int first = 0x7fffffff;
     for (int i = threadIdx.x; i < A; i += kThreads) if (mrow[i] != 0) { first = min(first, i); }
@@ -352,7 +357,8 @@ int set_smem(K kernel, size_t bytes) {
 extern "C" int kb_policy_sample(const void* logits, int logits_dtype, long long row_stride,
                                 const uint8_t* mask, const float* value_logits, const float* score_lead,
                                 float alpha, int B, int A, unsigned long long seed,
-                                unsigned long long offset, int logprob_mode, long long* actions,
+                                unsigned long long offset, int logprob_mode,
+                                const long long* forced_actions, long long* actions,
                                 float* logp, float* values, int* legal_count, int* flags,
                                 cudaStream_t stream) {
   KB_CHECK_ARG(B >= 0 && A > 0 && row_stride >= A, "kb_policy_sample: bad shape B=%d A=%d stride=%lld", B, A, row_stride);
@@ -365,11 +371,11 @@ extern "C" int kb_policy_sample(const void* logits, int logits_dtype, long long 
   if (logits_dtype == KB_F32) {
     if (int r = set_smem(policy_sample_kernel<float>, smem)) return r;
     policy_sample_kernel<float><<<B, kThreads, smem, stream>>>((const float*)logits, row_stride, mask, value_logits,
-        score_lead, alpha, A, seed, offset, logprob_mode, actions, logp, values, legal_count, flags);
+        score_lead, alpha, A, seed, offset, logprob_mode, forced_actions, actions, logp, values, legal_count, flags);
   } else {
     if (int r = set_smem(policy_sample_kernel<bf16>, smem)) return r;
     policy_sample_kernel<bf16><<<B, kThreads, smem, stream>>>((const bf16*)logits, row_stride, mask, value_logits,
-        score_lead, alpha, A, seed, offset, logprob_mode, actions, logp, values, legal_count, flags);
+        score_lead, alpha, A, seed, offset, logprob_mode, forced_actions, actions, logp, values, legal_count, flags);
   }
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
