@@ -1,0 +1,132 @@
+/* keisei_b200.h — C-ABI of libkeisei_b200.so: the B200 (sm_100a) kernels behind Keisei's
+ * data-parallel hot path (SE-ResNet forward/backward + KataGo-PPO update + GAE).
+ *
+ * The reference (tachyon-beep/keisei) has NO FFI on this path — every device op is a PyTorch
+ * library call from Python. Each entry point below therefore names the reference Python call
+ * site(s) it replaces (file:line relative to the reference root); INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer is a DEVICE pointer
+ * unless stated otherwise; the caller owns all memory including workspaces; nothing is allocated
+ * and no global mutable state is kept (thread-safe; kernels go to the caller's `stream`);
+ * return 0 on success or a negative code, never throw; kb_last_error() gives the message for the
+ * calling thread. dtype codes: 0 = float32, 1 = bfloat16.
+ */
+#ifndef KEISEI_B200_H
+#define KEISEI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* kb_stream_t;
+
+#define KB_DTYPE_F32 0
+#define KB_DTYPE_BF16 1
+
+/* ---- library ---- */
+int kb_abi_version(void);
+int kb_compiled_sm(void);                     /* 100 */
+const char* kb_last_error(void);              /* thread-local message of the last failing call */
+unsigned long long kb_launch_count(void);     /* kernels launched by this library so far */
+int kb_device_sm_count(int device);
+
+/* ---- GAE: keisei/training/gae.py:8-73 compute_gae, :76-148 compute_gae_padded,
+ *      :151-218 compute_gae_gpu, :221-296 compute_gae_padded_gpu  (one launch instead of 2*T) ----
+ * (T,N) row-major. terminated: term_kind 0 = uint8/bool, 1 = same float type as the values.
+ * override_nv: optional (T,N), NaN = "no override". lengths: optional (N,) int32 -> padded variant
+ * (bootstrap stamped at lengths[n]-1). dtype_is_f64: 0 = float32 tensors, 1 = float64. */
+int kb_gae_scan(const void* rewards, const void* values, const void* terminated, int term_kind,
+                const void* next_value, const void* override_nv, const int* lengths, void* adv,
+                int T, int N, double gamma, double lam, int dtype_is_f64, kb_stream_t stream);
+/* keisei/training/katago_ppo.py:797-798: (A - mean) / (std_unbiased + eps), in place, no-op for n <= 1 */
+int kb_advantage_normalize(float* adv, long long n, float eps, kb_stream_t stream);
+
+/* ---- rollout policy: keisei/training/katago_ppo.py:589-613 (also katago_loop.py:345-357, 407-418;
+ *      match_utils.py:211-224): legal-count guard, mask -> softmax -> sample -> log_prob, scalar
+ *      value P(W)-P(L) with optional score blend (value_adapter.py:79-96) ----
+ * logits: (B, A) with row stride `row_stride` elements; mask: (B, A) uint8 contiguous.
+ * logprob_mode 0 = float32 Categorical semantics, 1 = bfloat16-autocast semantics (eps = 2^-7).
+ * forced_actions (optional, (B,) int64): report the log-prob of these instead of sampling.
+ * flags[0] += rows with zero legal actions; legal_count (B,) int32. */
+int kb_policy_sample(const void* logits, int logits_dtype, long long row_stride, const uint8_t* mask,
+                     const float* value_logits, const float* score_lead, float alpha, int B, int A,
+                     unsigned long long seed, unsigned long long offset, int logprob_mode,
+                     const long long* forced_actions, long long* actions, float* logp, float* values,
+                     int* legal_count, int* flags, kb_stream_t stream);
+
+/* ---- update losses: keisei/training/katago_ppo.py:858-888 (NaN / zero-legal guards, masked
+ *      log_softmax, gather, entropy) and :33-43 ppo_clip_loss ----
+ * out2 = [policy_loss, entropy]; dlogp (B,) = d policy_loss / d new_logp; flags[0] zero-legal rows,
+ * flags[1] rows with NaN raw logits. */
+int kb_ppo_policy_fwd(const void* logits, int logits_dtype, long long row_stride, const uint8_t* mask,
+                      const long long* actions, const float* old_logp, const float* adv, int B, int A,
+                      float clip_eps, float* new_logp, float* row_entropy, float* row_lse, float* dlogp,
+                      float* out2, int* flags, kb_stream_t stream);
+/* dlogits = g_policy[0] * d policy_loss + g_entropy[0] * d entropy, written once (zeros on illegal) */
+int kb_ppo_policy_bwd(const void* logits, int logits_dtype, long long row_stride, const uint8_t* mask,
+                      const long long* actions, int B, int A, const float* row_lse,
+                      const float* row_entropy, const float* dlogp, const float* g_policy,
+                      const float* g_entropy, void* dlogits, long long d_row_stride, kb_stream_t stream);
+/* keisei/training/katago_ppo.py:46-57 wdl_cross_entropy_loss (ignore_index=-1, all-ignored -> 0),
+ * :910-912 score MSE; value_adapter.py:98-126. out3 = [value_loss, score_loss, n_valid] */
+int kb_value_losses_fwd(const float* value_logits, const long long* cats, const float* score_pred,
+                        const float* score_tgt, int B, float* out3, kb_stream_t stream);
+int kb_value_losses_bwd(const float* value_logits, const long long* cats, const float* score_pred,
+                        const float* score_tgt, int B, const float* out3, const float* g_value,
+                        const float* g_score, float* dvalue_logits, float* dscore, kb_stream_t stream);
+
+/* ---- SE-ResNet: keisei/training/models/se_resnet.py:132-159 SEResNetModel._forward_impl,
+ *      :68-90 GlobalPoolBiasBlock.forward, :93-98 _global_pool, and their autograd ----
+ * params / buffers / grads are HOST arrays of device pointers in the reference's registration
+ * order (see keisei_b200/csrc/model.cu header): params[16 + 14*num_blocks] float32,
+ * buffers[6 + 6*num_blocks] (running_mean, running_var float32; num_batches_tracked int64). */
+typedef struct {
+  int num_blocks, channels, se_hidden, gpool_channels, policy_channels, value_fc, score_fc, obs_channels;
+} kb_seresnet_desc;
+
+long long kb_seresnet_num_params(const kb_seresnet_desc* d);
+long long kb_seresnet_num_buffers(const kb_seresnet_desc* d);
+long long kb_seresnet_wpack_bytes(const kb_seresnet_desc* d, int dtype);
+long long kb_seresnet_workspace_bytes(const kb_seresnet_desc* d, int B, int training, int dtype);
+/* repack conv weights (activation dtype, forward + dgrad layouts) and fold eval-mode BatchNorm */
+int kb_seresnet_pack_weights(const kb_seresnet_desc* d, const void* const* params, const void* const* buffers,
+                             int dtype, void* wpack, long long wpack_bytes, kb_stream_t stream);
+/* obs: (B, obs_channels, 9, 9) float32 NCHW. policy_out: (B, policy_pitch >= 11259) rows of
+ * (9,9,139) logits in the activation dtype; value_out (B,3), score_out (B,1) float32.
+ * training != 0: batch-statistics BatchNorm, activations saved in `workspace` for
+ * kb_seresnet_backward; running stats (momentum 0.1, unbiased var) are updated in place in `buffers`
+ * (and num_batches_tracked incremented) when new_stats == NULL, else written to new_stats
+ * ([2*num_blocks+2][2][max(channels, policy_channels)] float32: mean row, var row per BN layer in
+ * registration order) leaving `buffers` untouched. use_tc: 1 = tcgen05 convolutions when shape/dtype allow. */
+int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const* params, void* const* buffers,
+                        float* new_stats, const void* wpack, const float* obs, int B, int training, int dtype, void* workspace,
+                        long long ws_bytes, void* policy_out, long long policy_pitch, float* value_out,
+                        float* score_out, int use_tc, int num_sms, kb_stream_t stream);
+/* grads: float32 buffers shaped like params, PRE-ZEROED by the caller */
+int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const* params, const void* wpack, int B,
+                         int dtype, void* workspace, long long ws_bytes, const void* dpolicy,
+                         long long policy_pitch, const float* dvalue, const float* dscore,
+                         void* const* grads, int use_tc, int num_sms, kb_stream_t stream);
+
+/* ---- single 3x3 convolution on NHWC 9x9 boards (unit-test / profiling entry points):
+ *      F.conv2d(padding=1, bias=False) at se_resnet.py:50,52,110 ----
+ * in (B,81,Cin), w (Cout,9,Cin) packed, out (B,81,Cout), all `dtype`. backend 0 = SIMT fp32-accumulate,
+ * 1 = tcgen05 (bf16 only). Optional fused epilogue pieces (null = off): per-channel scale/shift,
+ * relu, per-(board,channel) bias, channel sums (double[2*Cout]: sum, sum of squares),
+ * board_mean (B,Cout), pool (B,3*Cout: mean,max,std). */
+int kb_conv3x3_forward(const void* in, const void* w, void* out, int B, int Cin, int Cout, int dtype, int backend,
+                       const float* scale, const float* shift, int relu, const float* gbias, double* ch_sums,
+                       float* board_mean, float* pool, int num_sms, kb_stream_t stream);
+/* dw (Cout,Cin_true,3,3) float32 += sum over boards/pixels of dy (B,81,Cout) x shifted x (B,81,Cin) */
+int kb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true, int dtype,
+                     int backend, int num_sms, kb_stream_t stream);
+/* w (Cout,Cin,3,3) float32 -> wf (Cout,9,Cinp) and optional wd (Cinp,9,Cout) (flipped taps) in `dtype` */
+int kb_pack_conv_weight(const float* w, void* wf, void* wd, int Cout, int Cin, int Cinp, int dtype, kb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KEISEI_B200_H */

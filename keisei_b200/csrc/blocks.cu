@@ -1,0 +1,417 @@
+// blocks.cu — HBM-bound elementwise + reduction kernels of the SE-ResNet block, forward and
+// backward: BatchNorm finalize/apply, SE scale+shift, residual, ReLU, global-pool statistics and
+// their gradients (reference se_resnet.py:68-98 and the autograd of those lines).
+//
+// Layout: NHWC activations [B][81][C]; one CTA per board, one thread per channel, so every
+// per-(board, channel) reduction over the 81 pixels is a register loop with 2*C-byte coalesced rows.
+#include "kb_common.cuh"
+#include "kb_kernels.h"
+
+namespace {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+template <typename T>
+__global__ void apply_kernel(ApplyArgs g) {
+  const int b = blockIdx.x, c = threadIdx.x, C = g.C;
+  if (c >= C) return;
+  const float a_ = g.a ? g.a[c] : 1.f, b_ = g.a ? g.b[c] : 0.f;
+  const float sg = g.se ? sigmoidf_(g.se[(size_t)b * 2 * C + c]) : 1.f;
+  const float sf = g.se ? g.se[(size_t)b * 2 * C + C + c] : 0.f;
+  const float gb = g.gbias ? g.gbias[(size_t)b * C + c] : 0.f;
+  const T* z = (const T*)g.z + (size_t)b * 81 * C + c;
+  const T* res = g.res ? (const T*)g.res + (size_t)b * 81 * C + c : nullptr;
+  T* out = (T*)g.out + (size_t)b * 81 * C + c;
+  float s = 0.f, mx = -INFINITY, k0 = 0.f, ds = 0.f, dss = 0.f;
+#pragma unroll 9
+  for (int p = 0; p < 81; ++p) {
+    float v = fmaf(kb_to_float<T>(z[(size_t)p * C]), a_, b_);
+    v = fmaf(v, sg, sf);
+    if (res) v += kb_to_float<T>(res[(size_t)p * C]);
+    v = fmaxf(v, 0.f) + gb;
+    const T st = kb_from_float<T>(v);
+    out[(size_t)p * C] = st;
+    const float r = kb_to_float<T>(st);
+    if (p == 0) k0 = r;
+    const float d = r - k0;
+    s += r; mx = fmaxf(mx, r); ds += d; dss = fmaf(d, d, dss);
+  }
+  if (g.pool) {
+    const float dm = ds * (1.f / 81.f);
+    float* pr = g.pool + (size_t)b * 3 * C;
+    pr[c] = s * (1.f / 81.f);
+    pr[C + c] = mx;
+    pr[2 * C + c] = sqrtf(fmaxf(dss * (1.f / 81.f) - dm * dm, 0.f));
+  }
+}
+
+__global__ void bn_eval_affine_kernel(const float* w, const float* bias, const float* rm, const float* rv, float eps,
+                                      int C, float* a, float* b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float inv = 1.f / sqrtf(rv[c] + eps);
+  const float aa = w[c] * inv;
+  a[c] = aa;
+  b[c] = bias[c] - rm[c] * aa;
+}
+
+__global__ void affine_rows_kernel(const float* __restrict__ in, const float* __restrict__ a, const float* __restrict__ b,
+                                   float* __restrict__ out, long long n, int C) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % C);
+  out[i] = fmaf(in[i], a[c], b[c]);
+}
+
+__global__ void bn_finalize_kernel(double* sums, double count, const float* w, const float* bias, const float* rm,
+                                   const float* rv, float* rm_out, float* rv_out, long long* nbt, float momentum, float eps,
+                                   int C, float* a, float* b, float* mean_o, float* invstd_o) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt != nullptr) *nbt += 1;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  sums[c] = 0.0; sums[C + c] = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float aa = w[c] * invstd;
+  a[c] = aa;
+  b[c] = bias[c] - (float)mean * aa;
+  mean_o[c] = (float)mean;
+  invstd_o[c] = invstd;
+  if (rm != nullptr) {
+    const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+    rm_out[c] = (1.f - momentum) * rm[c] + momentum * (float)mean;
+    rv_out[c] = (1.f - momentum) * rv[c] + momentum * (float)unb;
+  }
+}
+
+// column sums / sums of squares of a [M][C] fp32 matrix -> double atomics. block (32, 8)
+__global__ void rows_stats_kernel(const float* __restrict__ x, long long M, int C, long long rows_per_block, double* sums) {
+  __shared__ float sh[2][8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cx;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  float s = 0.f, q = 0.f;
+  if (c < C)
+    for (long long r = r0 + ry; r < r1; r += 8) { const float v = x[r * C + c]; s += v; q = fmaf(v, v, q); }
+  sh[0][ry][cx] = s; sh[1][ry][cx] = q;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; ++i) { a += sh[0][i][cx]; b += sh[1][i][cx]; }
+    atomicAdd(&sums[c], a);
+    atomicAdd(&sums[C + c], b);
+  }
+}
+
+// ---------------- backward ----------------
+template <typename T>
+__global__ void block_bwd_reduce_kernel(BlockBwdArgs g) {
+  const int b = blockIdx.x, c = threadIdx.x, C = g.C;
+  if (c >= C) return;
+  const size_t base = (size_t)b * 81 * C + c;
+  const T* dxp = (const T*)g.dxp + base; const T* xp = (const T*)g.xp + base; const T* z2 = (const T*)g.z2 + base;
+  float s = 0.f, sz = 0.f;
+#pragma unroll 9
+  for (int p = 0; p < 81; ++p) {
+    const float du = kb_to_float<T>(xp[(size_t)p * C]) > 0.f ? kb_to_float<T>(dxp[(size_t)p * C]) : 0.f;
+    s += du;
+    sz = fmaf(du, kb_to_float<T>(z2[(size_t)p * C]), sz);
+  }
+  g.s_du[(size_t)b * C + c] = s;
+  g.s_duz[(size_t)b * C + c] = sz;
+}
+
+__global__ void se_bwd_prep_kernel(const float* s_du, const float* s_duz, const float* a2, const float* b2,
+                                   const float* se, float* dse, int B, int C) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * C) return;
+  const int c = (int)(i % C); const long long b = i / C;
+  const float sg = sigmoidf_(se[b * 2 * C + c]);
+  const float duzh = fmaf(a2[c], s_duz[i], b2[c] * s_du[i]);  // sum_p du * zhat2
+  dse[b * 2 * C + c] = duzh * sg * (1.f - sg);
+  dse[b * 2 * C + C + c] = s_du[i];
+}
+
+// block (32, 8): channel tile x board slice
+__global__ void bn2_bwd_sums_kernel(const float* s_du, const float* s_duz, const float* se, const float* dmean,
+                                    const float* bsum2, int B, int C, int boards_per_block, double* sums) {
+  __shared__ float sh[2][8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cx;
+  const int b0 = blockIdx.x * boards_per_block, b1 = min(B, b0 + boards_per_block);
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C)
+    for (int b = b0 + ry; b < b1; b += 8) {
+      const size_t i = (size_t)b * C + c;
+      const float sg = sigmoidf_(se[(size_t)b * 2 * C + c]);
+      const float dm = dmean[i];
+      s1 += fmaf(sg, s_du[i], dm);
+      s2 += fmaf(sg, s_duz[i], dm * bsum2[i]);  // bsum2 holds the board MEAN of z2
+    }
+  sh[0][ry][cx] = s1; sh[1][ry][cx] = s2;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    double a = 0.0, d = 0.0;
+    for (int i = 0; i < 8; ++i) { a += sh[0][i][cx]; d += sh[1][i][cx]; }
+    atomicAdd(&sums[c], a);
+    atomicAdd(&sums[C + c], d);
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(double* sums, double count, const float* w, const float* mean, const float* invstd,
+                                       float* k1, float* k2, float* k3, float* dgamma, float* dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double S1 = sums[c], S2 = sums[C + c];
+  sums[c] = 0.0; sums[C + c] = 0.0;
+  const double mu = mean[c], is = invstd[c];
+  const double dg = is * (S2 - mu * S1);
+  const double kk1 = (double)w[c] * is;
+  if (dgamma) dgamma[c] = (float)dg;
+  if (dbeta) dbeta[c] = (float)S1;
+  k1[c] = (float)kk1;
+  k2[c] = (float)(kk1 * is * dg / count);
+  k3[c] = (float)(kk1 * (S1 / count - mu * is * dg / count));
+}
+
+template <typename T>
+__global__ void block_bwd_dz2_kernel(PassBArgs g) {
+  const int b = blockIdx.x, c = threadIdx.x, C = g.C;
+  if (c >= C) return;
+  const size_t base = (size_t)b * 81 * C + c;
+  const T* dxp = (const T*)g.dxp + base; const T* xp = (const T*)g.xp + base; const T* z2 = (const T*)g.z2 + base;
+  T* dz2 = (T*)g.dz2 + base;
+  const float sg = sigmoidf_(g.se[(size_t)b * 2 * C + c]);
+  const float dm = g.dse_in[(size_t)b * C + c] * (1.f / 81.f);
+  const float k1 = g.k1[c], k2 = g.k2[c], k3 = g.k3[c];
+#pragma unroll 9
+  for (int p = 0; p < 81; ++p) {
+    const float du = kb_to_float<T>(xp[(size_t)p * C]) > 0.f ? kb_to_float<T>(dxp[(size_t)p * C]) : 0.f;
+    const float dzh = fmaf(du, sg, dm);
+    dz2[(size_t)p * C] = kb_from_float<T>(k1 * dzh - k2 * kb_to_float<T>(z2[(size_t)p * C]) - k3);
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(T* __restrict__ d, const T* __restrict__ z, const float* __restrict__ k1,
+                                    const float* __restrict__ k2, const float* __restrict__ k3, long long n, int C) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    d[i] = kb_from_float<T>(k1[c] * kb_to_float<T>(d[i]) - k2[c] * kb_to_float<T>(z[i]) - k3[c]);
+  }
+}
+
+template <typename T>
+__global__ void block_bwd_dx_kernel(PassDArgs g) {
+  const int b = blockIdx.x, c = threadIdx.x, C = g.C;
+  if (c >= C) return;
+  const size_t base = (size_t)b * 81 * C + c;
+  const T* x = (const T*)g.x + base;
+  const T* dxc = g.dxc ? (const T*)g.dxc + base : nullptr;
+  const T* dxp = g.dxp ? (const T*)g.dxp + base : nullptr;
+  const T* xp = g.xp ? (const T*)g.xp + base : nullptr;
+  T* dx = (T*)g.dx + base;
+  float gmean = 0.f, gmax = 0.f, gstd = 0.f, mean = 0.f, mx = 0.f;
+  if (g.dpool) {
+    const float* pr = g.pool + (size_t)b * 3 * C;
+    const float* dp = g.dpool + (size_t)b * 3 * C;
+    mean = pr[c]; mx = pr[C + c];
+    const float sd = pr[2 * C + c];
+    gmean = dp[c] * (1.f / 81.f);
+    gstd = sd > 0.f ? dp[2 * C + c] / (81.f * sd) : 0.f;  // torch: d std/dx = 0 where std == 0
+    int ties = 0;
+#pragma unroll 9
+    for (int p = 0; p < 81; ++p) ties += (kb_to_float<T>(x[(size_t)p * C]) == mx);
+    gmax = ties > 0 ? dp[C + c] / (float)ties : 0.f;  // amax backward splits evenly across ties
+  }
+#pragma unroll 9
+  for (int p = 0; p < 81; ++p) {
+    float v = dxc ? kb_to_float<T>(dxc[(size_t)p * C]) : 0.f;
+    if (dxp) {
+      const float up = kb_to_float<T>(dxp[(size_t)p * C]);
+      v += (xp == nullptr || kb_to_float<T>(xp[(size_t)p * C]) > 0.f) ? up : 0.f;
+    }
+    if (g.dpool) {
+      const float xv = kb_to_float<T>(x[(size_t)p * C]);
+      v += gmean + (xv == mx ? gmax : 0.f) + gstd * (xv - mean);
+    }
+    dx[(size_t)p * C] = kb_from_float<T>(v);
+  }
+}
+
+template <typename T>
+__global__ void relu_bwd_stats_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ z,
+                                      T* __restrict__ dzh, int C, double* sums) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c >= C) return;
+  const size_t base = (size_t)b * 81 * C + c;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 9
+  for (int p = 0; p < 81; ++p) {
+    const size_t i = base + (size_t)p * C;
+    const float d = kb_to_float<T>(y[i]) > 0.f ? kb_to_float<T>(dy[i]) : 0.f;
+    const T st = kb_from_float<T>(d);
+    dzh[i] = st;
+    const float r = kb_to_float<T>(st);
+    s1 += r;
+    s2 = fmaf(r, kb_to_float<T>(z[i]), s2);
+  }
+  atomicAdd(&sums[c], (double)s1);
+  atomicAdd(&sums[C + c], (double)s2);
+}
+
+__global__ void relu_bwd_stats_f32_kernel(float* __restrict__ d, const float* __restrict__ act, const float* __restrict__ z,
+                                          long long M, int C, long long rows_per_block, double* sums) {
+  __shared__ float sh[2][8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cx;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C)
+    for (long long r = r0 + ry; r < r1; r += 8) {
+      const long long i = r * C + c;
+      const float v = act[i] > 0.f ? d[i] : 0.f;
+      d[i] = v;
+      s1 += v;
+      s2 = fmaf(v, z[i], s2);
+    }
+  sh[0][ry][cx] = s1; sh[1][ry][cx] = s2;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    double a = 0.0, q = 0.0;
+    for (int i = 0; i < 8; ++i) { a += sh[0][i][cx]; q += sh[1][i][cx]; }
+    atomicAdd(&sums[c], a);
+    atomicAdd(&sums[C + c], q);
+  }
+}
+
+inline int ch_threads(int C) { return ((C + 31) / 32) * 32; }
+
+}  // namespace
+
+#define KB_DISPATCH_T(dtype, KERNEL, GRID, BLOCK, SMEM, ST, ...)                                  \
+  do {                                                                                            \
+    if ((dtype) == KB_F32) KERNEL<float><<<GRID, BLOCK, SMEM, ST>>>(__VA_ARGS__);                 \
+    else KERNEL<bf16><<<GRID, BLOCK, SMEM, ST>>>(__VA_ARGS__);                                    \
+    KB_CUDA_LAUNCH_CHECK();                                                                       \
+  } while (0)
+
+int kbk_apply(const ApplyArgs& a, cudaStream_t st) {
+  KB_CHECK_ARG(a.C >= 1 && a.C <= 1024, "apply: C=%d out of range", a.C);
+  if (a.B == 0) return KB_OK;
+  KB_DISPATCH_T(a.dtype, apply_kernel, a.B, ch_threads(a.C), 0, st, a);
+  return KB_OK;
+}
+
+int kbk_bn_eval_affine(const float* w, const float* bias, const float* rm, const float* rv, float eps, int C, float* a,
+                       float* b, cudaStream_t st) {
+  bn_eval_affine_kernel<<<kb_ceil_div(C, 128), 128, 0, st>>>(w, bias, rm, rv, eps, C, a, b);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kbk_bn_finalize(double* sums, double count, const float* w, const float* bias, const float* running_mean,
+                    const float* running_var, float* rm_out, float* rv_out, long long* nbt, float momentum, float eps,
+                    int C, float* a, float* b, float* mean, float* invstd, cudaStream_t st) {
+  bn_finalize_kernel<<<kb_ceil_div(C, 128), 128, 0, st>>>(sums, count, w, bias, running_mean, running_var, rm_out, rv_out,
+                                                          nbt, momentum, eps, C, a, b, mean, invstd);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kbk_affine_rows(const float* in, const float* a, const float* b, float* out, long long rows, int C, cudaStream_t st) {
+  const long long n = rows * C;
+  if (n == 0) return KB_OK;
+  affine_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, a, b, out, n, C);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kbk_rows_stats(const float* x, long long M, int C, double* sums, cudaStream_t st) {
+  if (M == 0) return KB_OK;
+  const long long rpb = 512;
+  rows_stats_kernel<<<dim3((unsigned)((M + rpb - 1) / rpb), kb_ceil_div(C, 32)), 256, 0, st>>>(x, M, C, rpb, sums);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kbk_block_bwd_reduce(const BlockBwdArgs& a, cudaStream_t st) {
+  KB_CHECK_ARG(a.C <= 1024, "block_bwd_reduce: C too large");
+  KB_DISPATCH_T(a.dtype, block_bwd_reduce_kernel, a.B, ch_threads(a.C), 0, st, a);
+  return KB_OK;
+}
+
+int kbk_se_bwd_prep(const float* s_du, const float* s_duz, const float* a2, const float* b2, const float* se, float* dse,
+                    int B, int C, cudaStream_t st) {
+  se_bwd_prep_kernel<<<kb_ceil_div((long long)B * C, 256), 256, 0, st>>>(s_du, s_duz, a2, b2, se, dse, B, C);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kbk_bn2_bwd_sums(const float* s_du, const float* s_duz, const float* se, const float* dmean,
+                     const float* bsum2, int B, int C, double* sums, cudaStream_t st) {
+  const int bpb = 64;
+  bn2_bwd_sums_kernel<<<dim3(kb_ceil_div(B, bpb), kb_ceil_div(C, 32)), 256, 0, st>>>(s_du, s_duz, se, dmean, bsum2, B, C,
+                                                                                     bpb, sums);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kbk_bn_bwd_finalize(double* sums, double count, const float* w, const float* mean, const float* invstd, float* k1,
+                        float* k2, float* k3, float* dgamma, float* dbeta, int C, cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<kb_ceil_div(C, 128), 128, 0, st>>>(sums, count, w, mean, invstd, k1, k2, k3, dgamma, dbeta, C);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kbk_block_bwd_dz2(const PassBArgs& a, cudaStream_t st) {
+  KB_CHECK_ARG(a.C <= 1024, "block_bwd_dz2: C too large");
+  KB_DISPATCH_T(a.dtype, block_bwd_dz2_kernel, a.B, ch_threads(a.C), 0, st, a);
+  return KB_OK;
+}
+
+int kbk_bn_bwd_apply(void* d, const void* z, const float* k1, const float* k2, const float* k3, long long rows, int C,
+                     int dtype, cudaStream_t st) {
+  const long long n = rows * C;
+  if (n == 0) return KB_OK;
+  const int grid = (int)min((long long)148 * 16, (n + 255) / 256);
+  if (dtype == KB_F32) bn_bwd_apply_kernel<float><<<grid, 256, 0, st>>>((float*)d, (const float*)z, k1, k2, k3, n, C);
+  else bn_bwd_apply_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)d, (const bf16*)z, k1, k2, k3, n, C);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kbk_block_bwd_dx(const PassDArgs& a, cudaStream_t st) {
+  KB_CHECK_ARG(a.C <= 1024, "block_bwd_dx: C too large");
+  KB_DISPATCH_T(a.dtype, block_bwd_dx_kernel, a.B, ch_threads(a.C), 0, st, a);
+  return KB_OK;
+}
+
+int kbk_relu_bwd_stats(const void* dy, const void* y, const void* z, void* dzh, long long rows, int C, int dtype,
+                       double* sums, cudaStream_t st) {
+  KB_CHECK_ARG(rows % 81 == 0 && C <= 1024, "relu_bwd_stats: bad shape");
+  const int B = (int)(rows / 81);
+  if (dtype == KB_F32)
+    relu_bwd_stats_kernel<float><<<B, ch_threads(C), 0, st>>>((const float*)dy, (const float*)y, (const float*)z, (float*)dzh, C, sums);
+  else
+    relu_bwd_stats_kernel<bf16><<<B, ch_threads(C), 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)z, (bf16*)dzh, C, sums);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kbk_relu_bwd_stats_f32(float* d, const float* act, const float* z, long long M, int C, double* sums, cudaStream_t st) {
+  if (M == 0) return KB_OK;
+  const long long rpb = 512;
+  relu_bwd_stats_f32_kernel<<<dim3((unsigned)((M + rpb - 1) / rpb), kb_ceil_div(C, 32)), 256, 0, st>>>(d, act, z, M, C, rpb, sums);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kbk_fill_zero(void* p, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return KB_OK;
+  KB_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, st));
+  return KB_OK;
+}

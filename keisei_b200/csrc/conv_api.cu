@@ -1,0 +1,38 @@
+// conv_api.cu — C-ABI entry points for a single 3x3 convolution (unit tests, profiling).
+#include "kb_common.cuh"
+#include "kb_kernels.h"
+#include "../../include/keisei_b200.h"
+
+extern "C" int kb_conv3x3_forward(const void* in, const void* w, void* out, int B, int Cin, int Cout, int dtype,
+                                  int backend, const float* scale, const float* shift, int relu, const float* gbias,
+                                  double* ch_sums, float* board_mean, float* pool, int num_sms, cudaStream_t stream) {
+  KB_CHECK_ARG(in && w && out, "kb_conv3x3_forward: null pointer");
+  KB_CHECK_ARG(B >= 0 && Cin > 0 && Cout > 0, "kb_conv3x3_forward: bad shape");
+  KB_CHECK_ARG(dtype == KB_F32 || dtype == KB_BF16, "kb_conv3x3_forward: bad dtype");
+  ConvEpi e; memset(&e, 0, sizeof(e));
+  e.scale = scale; e.shift = shift; e.relu = relu; e.gbias = gbias;
+  if (ch_sums) { e.ch_sum = ch_sums; e.ch_sumsq = ch_sums + Cout; }
+  e.board_sum = board_mean; e.board_scale = 1.f / 81.f; e.pool = pool;
+  if (backend == 1) {
+    KB_CHECK_ARG(kbk_conv3x3_tc_supported(Cin, Cout, dtype), "kb_conv3x3_forward: tcgen05 path needs bf16, Cin%%64==0, Cout%%128==0 (got %d,%d,dtype %d)", Cin, Cout, dtype);
+    return kbk_conv3x3_tc(in, w, out, B, Cin, Cout, e, num_sms, stream);
+  }
+  return kbk_conv3x3_simt(in, w, out, B, Cin, Cout, dtype, e, stream);
+}
+
+extern "C" int kb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true,
+                                int dtype, int backend, int num_sms, cudaStream_t stream) {
+  KB_CHECK_ARG(x && dy && dw, "kb_conv3x3_wgrad: null pointer");
+  KB_CHECK_ARG(dtype == KB_F32 || dtype == KB_BF16, "kb_conv3x3_wgrad: bad dtype");
+  if (backend == 1) {
+    KB_CHECK_ARG(kbk_conv3x3_tc_supported(Cin, Cout, dtype), "kb_conv3x3_wgrad: tcgen05 path unsupported for this shape/dtype");
+    return kbk_conv3x3_wgrad_tc(x, dy, dw, B, Cin, Cout, Cin_true, num_sms, stream);
+  }
+  return kbk_conv3x3_wgrad_simt(x, dy, dw, B, Cin, Cout, Cin_true, dtype, stream);
+}
+
+extern "C" int kb_pack_conv_weight(const float* w, void* wf, void* wd, int Cout, int Cin, int Cinp, int dtype,
+                                   cudaStream_t stream) {
+  KB_CHECK_ARG(w && wf && Cinp >= Cin, "kb_pack_conv_weight: bad arguments");
+  return kbk_pack_conv_weight(w, wf, wd, Cout, Cin, Cinp, dtype, stream);
+}

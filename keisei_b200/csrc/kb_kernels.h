@@ -1,0 +1,118 @@
+// kb_kernels.h — internal (C++) launcher prototypes shared between translation units.
+// Every launcher enqueues on the caller's stream, allocates nothing, and returns KB_OK or a
+// negative error code after kb_set_error().
+#pragma once
+#include <cuda_runtime.h>
+#include "conv_epilogue.cuh"
+
+// ---- conv_simt.cu ----
+int kbk_pack_conv_weight(const float* w, void* wf, void* wd, int Cout, int Cin, int Cinp, int dtype, cudaStream_t st);
+int kbk_pack_obs(const float* obs, void* out, int B, int Cin, int Cinp, int dtype, cudaStream_t st);
+int kbk_conv3x3_simt(const void* in, const void* w, void* out, int B, int Cin, int Cout, int dtype,
+                     const ConvEpi& epi, cudaStream_t st);
+int kbk_conv3x3_wgrad_simt(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true,
+                           int dtype, cudaStream_t st);
+
+// ---- conv_tc.cu (tcgen05 / TMEM / TMA, bf16) ----
+int kbk_conv3x3_tc_supported(int Cin, int Cout, int dtype);
+int kbk_conv3x3_tc(const void* in, const void* w, void* out, int B, int Cin, int Cout, const ConvEpi& epi,
+                   int num_sms, cudaStream_t st);
+int kbk_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true,
+                         int num_sms, cudaStream_t st);
+
+// ---- gemm_simt.cu ----
+struct GemmArgs {
+  // C[M,N] = epilogue( prologue(op(A))[M,K] * op(B)[K,N] )
+  const void* A; int a_dtype; long long lda; int transA;  // op(A)[m][k] = transA ? A[k*lda+m] : A[m*lda+k]
+  int a_group_rows; long long a_group_pitch;               // if >0: row m lives at (m/gr)*pitch + (m%gr)*lda
+  const float* a_pa; const float* a_pb; int a_relu;        // prologue: v = v*pa[k]+pb[k]; relu
+  const void* B; int b_dtype; long long ldb; int transB;   // op(B)[k][n] = transB ? B[n*ldb+k] : B[k*ldb+n]
+  void* C; int c_dtype; long long ldc;
+  int c_group_rows; long long c_group_pitch;
+  const float* bias;                                       // [N] or null
+  int relu;
+  const float* mask_src; long long ld_mask;                // v = mask_src[m][n] > 0 ? v : 0
+  int M, N, K;
+  int splitk;                                              // >1: fp32 atomicAdd into C (C pre-zeroed / accumulating)
+};
+int kbk_gemm(const GemmArgs& g, cudaStream_t st);
+// out[n] += sum_m X[m][n]  (X may be board-pitched like GemmArgs.A)
+int kbk_colsum(const void* X, int dtype, long long ldx, int group_rows, long long group_pitch, int M, int N,
+               float* out, cudaStream_t st);
+
+// ---- blocks.cu (BN / SE / pool elementwise + reductions) ----
+struct ApplyArgs {
+  // out = relu( (z*a[c]+b[c]) * sigmoid(se[b][c]) + se[b][C+c] + res ) + gbias[b][c]; optional pool stats of out
+  const void* z; const float* a; const float* b;  // a/b null -> identity
+  const float* se;      // [B][2C] (scale logits, shift) or null
+  const void* res;      // [B][81][C] or null
+  const float* gbias;   // [B][C] or null
+  void* out;
+  float* pool;          // [B][3C] or null
+  int B, C, dtype;
+};
+int kbk_apply(const ApplyArgs& a, cudaStream_t st);
+// eval-mode folded BN: a = w/sqrt(rv+eps), b = bias - rm*a
+int kbk_bn_eval_affine(const float* w, const float* bias, const float* rm, const float* rv, float eps, int C,
+                       float* a, float* b, cudaStream_t st);
+// training-mode BN finalize from double sums; updates running stats (momentum, unbiased var) and nbt
+int kbk_bn_finalize(double* sums /*[2][C], zeroed afterwards*/, double count, const float* w, const float* bias,
+                    const float* running_mean, const float* running_var, float* rm_out, float* rv_out, long long* nbt,
+                    float momentum, float eps, int C, float* a, float* b, float* mean, float* invstd, cudaStream_t st);
+// out[r][c] = in[r][c]*a[c] + b[c]  (fp32 [rows][C]; the SE squeeze input from the board means)
+int kbk_affine_rows(const float* in, const float* a, const float* b, float* out, long long rows, int C, cudaStream_t st);
+// per-channel sum / sum of squares over rows of a [M][C] fp32 matrix (policy head BN)
+int kbk_rows_stats(const float* x, long long M, int C, double* sums, cudaStream_t st);
+
+// ---- backward elementwise ----
+struct BlockBwdArgs {
+  int B, C, dtype;
+  const void* dxp;   // dL/d(block output) [B][81][C]
+  const void* xp;    // block output (post-ReLU)
+  const void* z2;    // raw conv2 output
+  const float* a2; const float* b2;       // BN2 affine (a = gamma*invstd, b = beta - mean*a)
+  const float* se;   // [B][2C]
+  float* s_du;       // [B][C]  sum_p du
+  float* s_duz;      // [B][C]  sum_p du*z2
+};
+int kbk_block_bwd_reduce(const BlockBwdArgs& a, cudaStream_t st);  // pass A
+// SE backward glue: dse[b][c] = (a2*s_duz + b2*s_du) * sig'(scale), dse[b][C+c] = s_du
+int kbk_se_bwd_prep(const float* s_du, const float* s_duz, const float* a2, const float* b2, const float* se,
+                    float* dse, int B, int C, cudaStream_t st);
+// BN2 backward channel sums: sum1[c] = sum_b (sig*s_du + dmean), sum2[c] = sum_b (sig*s_duz + dmean*bmean2)
+// dmean = d(se_in)*a2 is NOT pre-scaled here: pass the gradient wrt zhat2's board mean, i.e. dse_in; bmean2 = mean_p z2
+int kbk_bn2_bwd_sums(const float* s_du, const float* s_duz, const float* se, const float* dmean,
+                     const float* bmean2, int B, int C, double* sums /*[2][C]*/, cudaStream_t st);
+// BN backward finalize: from sums (sum dzh, sum dzh*z) -> m1, m2', dgamma, dbeta
+int kbk_bn_bwd_finalize(double* sums /*[2][C], zeroed afterwards*/, double count, const float* w, const float* mean,
+                        const float* invstd, float* k1, float* k2, float* k3, float* dgamma, float* dbeta, int C,
+                        cudaStream_t st);
+struct PassBArgs {
+  int B, C, dtype;
+  const void* dxp; const void* xp; const void* z2;
+  const float* se; const float* dse_in;  // [B][C] d(se_in) (gradient wrt the SE squeeze input)
+  const float* k1; const float* k2; const float* k3;  // dz = k1*dzh - k2*z - k3  (per channel)
+  void* dz2;
+};
+int kbk_block_bwd_dz2(const PassBArgs& a, cudaStream_t st);  // pass B
+// pass C: dz = k1*dzh - k2*z - k3 in place over dzh
+int kbk_bn_bwd_apply(void* dzh_inout, const void* z, const float* k1, const float* k2, const float* k3,
+                     long long rows, int C, int dtype, cudaStream_t st);
+struct PassDArgs {
+  int B, C, dtype;
+  const void* dxc;   // dgrad result (may be null -> 0)
+  const void* dxp;   // upstream grad of the block output (may be null)
+  const void* xp;    // block output (ReLU mask for dxp), may be null -> no mask
+  const void* x;     // block input (for pool backward)
+  const float* pool; // [B][3C] saved mean/max/std of x
+  const float* dpool;// [B][3C] grad wrt pool (may be null)
+  void* dx;          // out
+};
+int kbk_block_bwd_dx(const PassDArgs& a, cudaStream_t st);  // pass D
+// stem / generic: dzh = dy * (y > 0), channel sums of dzh and dzh*z   (y = post-activation, z = raw)
+int kbk_relu_bwd_stats(const void* dy, const void* y, const void* z, void* dzh, long long rows, int C, int dtype,
+                       double* sums, cudaStream_t st);
+// fp32 [M][C] variant for the policy head (mask by act > 0)
+int kbk_relu_bwd_stats_f32(float* d_inout, const float* act, const float* z, long long M, int C, double* sums,
+                           cudaStream_t st);
+int kbk_fill_zero(void* p, size_t bytes, cudaStream_t st);

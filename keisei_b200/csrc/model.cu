@@ -1,0 +1,503 @@
+// model.cu — the SE-ResNet forward / backward schedule (reference se_resnet.py:68-90, :132-159)
+// as a stream-ordered sequence of this library's kernels. Pure host code: no allocation, no
+// global state; the caller owns parameters, packed weights and the workspace.
+//
+// Parameter table order == PyTorch registration order of the reference model (so Adam state and
+// strict state_dict loads line up): input_conv.weight, input_bn.{weight,bias}, then per block
+// conv1.weight, bn1.{weight,bias}, conv2.weight, bn2.{weight,bias}, global_fc.{0,2}.{weight,bias},
+// se_fc1.{weight,bias}, se_fc2.{weight,bias}; then policy_conv1.weight, policy_bn1.{weight,bias},
+// policy_conv2.{weight,bias}, value_fc{1,2}.{weight,bias}, score_fc{1,2}.{weight,bias}.
+// Buffer table order: input_bn.{running_mean,running_var,num_batches_tracked}, per block bn1.*, bn2.*,
+// then policy_bn1.*.
+#include "kb_common.cuh"
+#include "kb_kernels.h"
+#include "../../include/keisei_b200.h"
+
+namespace {
+
+constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
+
+struct Bump {
+  char* base; size_t off;
+  explicit Bump(void* b) : base((char*)b), off(0) {}
+  void* take(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+  float* f32(size_t n) { return (float*)take(n * sizeof(float)); }
+};
+
+struct Dims {
+  int nb, C, S, G, Pc, V, S2, C0, C0p, B, dtype;
+  size_t esz;
+  long long M;  // B*81
+  size_t act() const { return (size_t)B * 81 * C * esz; }
+};
+
+Dims make_dims(const kb_seresnet_desc* d, int B, int dtype) {
+  Dims m;
+  m.nb = d->num_blocks; m.C = d->channels; m.S = d->se_hidden; m.G = d->gpool_channels; m.Pc = d->policy_channels;
+  m.V = d->value_fc; m.S2 = d->score_fc; m.C0 = d->obs_channels; m.C0p = ((d->obs_channels + 63) / 64) * 64;
+  m.B = B; m.dtype = dtype; m.esz = dtype == KB_F32 ? 4 : 2; m.M = (long long)B * 81;
+  return m;
+}
+
+inline int pi_blk(int i, int j) { return 3 + 14 * i + j; }
+inline int pi_head(const Dims& m, int j) { return 3 + 14 * m.nb + j; }
+inline int bi_blk(int i, int j) { return 3 + 6 * i + j; }
+inline int bi_pol(const Dims& m, int j) { return 3 + 6 * m.nb + j; }
+
+// packed-weight buffer: conv weights in the activation dtype, then eval-mode BN affines (fp32)
+struct WPack {
+  char* base;
+  void *stem_wf;
+  size_t conv_bytes, stem_bytes;
+  char* blocks;     // per block: conv1 wf, conv1 wd, conv2 wf, conv2 wd
+  float* bn_eval;   // [2*nb+2][2][Cmax]
+  int Cmax;
+  size_t total;
+  void* wf(int i, int conv) const { return blocks + ((size_t)i * 4 + conv * 2) * conv_bytes; }
+  void* wd(int i, int conv) const { return blocks + ((size_t)i * 4 + conv * 2 + 1) * conv_bytes; }
+  float* bn_a(int layer) const { return bn_eval + (size_t)layer * 2 * Cmax; }
+  float* bn_b(int layer) const { return bn_eval + (size_t)layer * 2 * Cmax + Cmax; }
+};
+// BN layer numbering: 0 = input_bn, 1+2i = block i bn1, 2+2i = block i bn2, 2nb+1 = policy_bn1
+WPack make_wpack(const Dims& m, void* base) {
+  WPack w;
+  w.base = (char*)base;
+  Bump b(base);
+  w.stem_bytes = (size_t)m.C * 9 * m.C0p * m.esz;
+  w.conv_bytes = (((size_t)m.C * 9 * m.C * m.esz) + 1023) & ~(size_t)1023;
+  w.stem_wf = b.take(w.stem_bytes);
+  b.off = (b.off + 1023) & ~(size_t)1023;
+  w.blocks = (char*)b.take((size_t)m.nb * 4 * w.conv_bytes);
+  w.Cmax = m.C > m.Pc ? m.C : m.Pc;
+  w.bn_eval = b.f32((size_t)(2 * m.nb + 2) * 2 * w.Cmax);
+  w.total = b.off + 256;
+  return w;
+}
+
+struct BlockWs {
+  void *z1, *a1, *z2, *xout;
+  float *gh, *bmean2, *se_in, *seh, *se;
+};
+
+struct Ws {
+  void *obs_p, *z0, *x0;
+  BlockWs* blk;            // host array, nb entries (filled by carve)
+  float* pools;            // [nb+1][B][3C]
+  float* bn;               // [2nb+2][4][Cmax]: a, b, mean, invstd
+  float *g, *p1raw, *p1act, *vh, *sh;
+  double* dsums;           // [2][Cmax]
+  // eval-only ping-pong
+  void *ea, *eb, *ey1, *ey2;
+  float *epool_a, *epool_b;
+  // backward temporaries
+  void *d0, *d1, *d2;
+  float *s_du, *s_duz, *dse_in, *dg, *dse, *dseh, *dgh, *dpool, *k123, *dp1, *dvh, *dsh;
+  int Cmax;
+  size_t total;
+  float* pool(const Dims& m, int i) const { return pools + (size_t)i * m.B * 3 * m.C; }
+  float* bn_a(int l) const { return bn + (size_t)l * 4 * Cmax; }
+  float* bn_b(int l) const { return bn + (size_t)l * 4 * Cmax + Cmax; }
+  float* bn_mean(int l) const { return bn + (size_t)l * 4 * Cmax + 2 * Cmax; }
+  float* bn_invstd(int l) const { return bn + (size_t)l * 4 * Cmax + 3 * Cmax; }
+};
+
+void carve(const Dims& m, void* base, int training, Ws& w, BlockWs* blk_storage) {
+  Bump b(base);
+  const size_t B = m.B;
+  w.Cmax = m.C > m.Pc ? m.C : m.Pc;
+  w.blk = blk_storage;
+  w.dsums = (double*)b.take(2 * (size_t)w.Cmax * sizeof(double));
+  w.obs_p = b.take(B * 81 * m.C0p * m.esz);
+  w.g = b.f32(B * m.C);
+  w.p1raw = b.f32((size_t)m.M * m.Pc);
+  w.p1act = b.f32((size_t)m.M * m.Pc);
+  w.vh = b.f32(B * m.V);
+  w.sh = b.f32(B * m.S2);
+  w.bn = b.f32((size_t)(2 * m.nb + 2) * 4 * w.Cmax);
+  if (training) {
+    w.z0 = b.take(m.act()); w.x0 = b.take(m.act());
+    w.pools = b.f32((size_t)(m.nb + 1) * B * 3 * m.C);
+    for (int i = 0; i < m.nb; ++i) {
+      BlockWs bw;
+      bw.z1 = b.take(m.act()); bw.a1 = b.take(m.act()); bw.z2 = b.take(m.act()); bw.xout = b.take(m.act());
+      bw.gh = b.f32(B * m.G); bw.bmean2 = b.f32(B * m.C); bw.se_in = b.f32(B * m.C); bw.seh = b.f32(B * m.S);
+      bw.se = b.f32(B * 2 * m.C);
+      if (blk_storage) blk_storage[i] = bw;
+    }
+    w.d0 = b.take(m.act()); w.d1 = b.take(m.act()); w.d2 = b.take(m.act());
+    w.s_du = b.f32(B * m.C); w.s_duz = b.f32(B * m.C); w.dse_in = b.f32(B * m.C); w.dg = b.f32(B * m.C);
+    w.dse = b.f32(B * 2 * m.C); w.dseh = b.f32(B * m.S); w.dgh = b.f32(B * m.G); w.dpool = b.f32(B * 3 * m.C);
+    w.k123 = b.f32(3 * (size_t)w.Cmax);
+    w.dp1 = b.f32((size_t)m.M * m.Pc);
+    w.dvh = b.f32(B * m.V); w.dsh = b.f32(B * m.S2);
+    w.ea = w.eb = w.ey1 = w.ey2 = nullptr; w.epool_a = w.epool_b = nullptr;
+  } else {
+    w.ea = b.take(m.act()); w.eb = b.take(m.act()); w.ey1 = b.take(m.act()); w.ey2 = b.take(m.act());
+    w.epool_a = b.f32(B * 3 * m.C); w.epool_b = b.f32(B * 3 * m.C);
+    BlockWs bw;
+    bw.z1 = bw.a1 = bw.z2 = bw.xout = nullptr;
+    bw.gh = b.f32(B * m.G); bw.bmean2 = b.f32(B * m.C); bw.se_in = nullptr; bw.seh = b.f32(B * m.S); bw.se = b.f32(B * 2 * m.C);
+    if (blk_storage) blk_storage[0] = bw;
+    w.z0 = w.x0 = nullptr; w.pools = nullptr;
+    w.d0 = w.d1 = w.d2 = nullptr;
+    w.s_du = w.s_duz = w.dse_in = w.dg = w.dse = w.dseh = w.dgh = w.dpool = w.k123 = w.dp1 = w.dvh = w.dsh = nullptr;
+  }
+  w.total = b.off + 256;
+}
+
+int conv3x3(const Dims& m, const void* in, const void* wgt, void* out, int Cin, int Cout, const ConvEpi& e, int use_tc,
+            int num_sms, cudaStream_t st) {
+  if (use_tc && kbk_conv3x3_tc_supported(Cin, Cout, m.dtype)) return kbk_conv3x3_tc(in, wgt, out, m.B, Cin, Cout, e, num_sms, st);
+  return kbk_conv3x3_simt(in, wgt, out, m.B, Cin, Cout, m.dtype, e, st);
+}
+int wgrad3x3(const Dims& m, const void* x, const void* dy, float* dw, int Cin, int Cout, int Cin_true, int use_tc,
+             int num_sms, cudaStream_t st) {
+  if (use_tc && kbk_conv3x3_tc_supported(Cin, Cout, m.dtype)) return kbk_conv3x3_wgrad_tc(x, dy, dw, m.B, Cin, Cout, Cin_true, num_sms, st);
+  return kbk_conv3x3_wgrad_simt(x, dy, dw, m.B, Cin, Cout, Cin_true, m.dtype, st);
+}
+
+GemmArgs gemm_base() { GemmArgs g; memset(&g, 0, sizeof(g)); g.splitk = 1; return g; }
+ConvEpi epi_base() { ConvEpi e; memset(&e, 0, sizeof(e)); e.board_scale = 1.f; return e; }
+
+// y[M,N] = act(x[M,K] * W[N,K]^T + bias)
+int linear_fwd(const void* x, int x_dtype, long long ldx, int M, int K, const float* W, int N, const float* bias, int relu,
+               void* y, int y_dtype, long long ldy, cudaStream_t st) {
+  GemmArgs g = gemm_base();
+  g.A = x; g.a_dtype = x_dtype; g.lda = ldx;
+  g.B = W; g.b_dtype = KB_F32; g.ldb = K; g.transB = 1;
+  g.C = y; g.c_dtype = y_dtype; g.ldc = ldy; g.bias = bias; g.relu = relu;
+  g.M = M; g.N = N; g.K = K;
+  return kbk_gemm(g, st);
+}
+// dx[M,K] = (dy[M,N] * W[N,K]) masked by mask_src > 0 ; accumulate -> atomic add onto dx
+int linear_bwd_x(const void* dy, int dy_dtype, long long ldy, int M, int N, const float* W, int K, void* dx, int dx_dtype,
+                 long long lddx, const float* mask_src, long long ld_mask, int accumulate, cudaStream_t st) {
+  GemmArgs g = gemm_base();
+  g.A = dy; g.a_dtype = dy_dtype; g.lda = ldy;
+  g.B = W; g.b_dtype = KB_F32; g.ldb = K; g.transB = 0;
+  g.C = dx; g.c_dtype = dx_dtype; g.ldc = lddx; g.mask_src = mask_src; g.ld_mask = ld_mask;
+  g.M = M; g.N = K; g.K = N; g.splitk = accumulate ? 2 : 1;
+  return kbk_gemm(g, st);
+}
+// dW[N,K] += dy[M,N]^T * x[M,K] ; db[N] += colsum(dy)
+int linear_bwd_w(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, int M, int N, int K,
+                 float* dW, float* db, cudaStream_t st) {
+  GemmArgs g = gemm_base();
+  g.A = dy; g.a_dtype = dy_dtype; g.lda = ldy; g.transA = 1;
+  g.B = x; g.b_dtype = x_dtype; g.ldb = ldx; g.transB = 0;
+  g.C = dW; g.c_dtype = KB_F32; g.ldc = K;
+  g.M = N; g.N = K; g.K = M;
+  const int tiles = kb_ceil_div(N, 64) * kb_ceil_div(K, 64);
+  int sk = kb_ceil_div(296, tiles);
+  const int max_sk = kb_ceil_div(M, 64);
+  if (sk > max_sk) sk = max_sk;
+  g.splitk = sk < 2 ? 2 : sk;  // always the atomic epilogue: dW accumulates into the pre-zeroed gradient
+  if (int r = kbk_gemm(g, st)) return r;
+  if (db) return kbk_colsum(dy, dy_dtype, ldy, 0, 0, M, N, db, st);
+  return KB_OK;
+}
+
+#define KB_TRY(expr) do { int r__ = (expr); if (r__ != KB_OK) return r__; } while (0)
+
+int check_desc(const kb_seresnet_desc* d) {
+  KB_CHECK_ARG(d != nullptr, "null model descriptor");
+  KB_CHECK_ARG(d->num_blocks >= 0 && d->num_blocks <= 1024, "num_blocks out of range");
+  KB_CHECK_ARG(d->channels >= 4 && d->channels % 4 == 0 && d->channels <= 1024, "channels=%d must be a multiple of 4 in [4,1024]", d->channels);
+  KB_CHECK_ARG(d->se_hidden >= 1 && d->gpool_channels >= 1 && d->policy_channels >= 1 && d->policy_channels <= 1024 &&
+               d->value_fc >= 1 && d->score_fc >= 1 && d->obs_channels >= 1 && d->obs_channels <= 128, "bad model descriptor");
+  return KB_OK;
+}
+
+}  // namespace
+
+extern "C" long long kb_seresnet_num_params(const kb_seresnet_desc* d) { return d ? 16 + 14LL * d->num_blocks : -1; }
+extern "C" long long kb_seresnet_num_buffers(const kb_seresnet_desc* d) { return d ? 6 + 6LL * d->num_blocks : -1; }
+
+extern "C" long long kb_seresnet_wpack_bytes(const kb_seresnet_desc* d, int dtype) {
+  if (check_desc(d) != KB_OK) return -1;
+  const Dims m = make_dims(d, 1, dtype);
+  return (long long)make_wpack(m, nullptr).total;
+}
+
+extern "C" long long kb_seresnet_workspace_bytes(const kb_seresnet_desc* d, int B, int training, int dtype) {
+  if (check_desc(d) != KB_OK || B < 0) return -1;
+  const Dims m = make_dims(d, B, dtype);
+  Ws w;
+  carve(m, nullptr, training, w, nullptr);
+  return (long long)w.total;
+}
+
+// Repack conv weights into the kernels' layouts (activation dtype) and fold eval-mode BatchNorm.
+extern "C" int kb_seresnet_pack_weights(const kb_seresnet_desc* d, const void* const* params, const void* const* buffers,
+                                        int dtype, void* wpack, long long wpack_bytes, cudaStream_t st) {
+  KB_TRY(check_desc(d));
+  KB_CHECK_ARG(dtype == KB_F32 || dtype == KB_BF16, "bad dtype");
+  const Dims m = make_dims(d, 1, dtype);
+  WPack w = make_wpack(m, wpack);
+  KB_CHECK_ARG(wpack && (size_t)wpack_bytes >= w.total, "wpack buffer too small: %lld < %zu", wpack_bytes, w.total);
+  KB_TRY(kbk_pack_conv_weight((const float*)params[0], w.stem_wf, nullptr, m.C, m.C0, m.C0p, dtype, st));
+  auto bn = [&](int layer, int pw, int bbase, int C) {
+    return kbk_bn_eval_affine((const float*)params[pw], (const float*)params[pw + 1], (const float*)buffers[bbase],
+                              (const float*)buffers[bbase + 1], kBnEps, C, w.bn_a(layer), w.bn_b(layer), st);
+  };
+  KB_TRY(bn(0, 1, 0, m.C));
+  for (int i = 0; i < m.nb; ++i) {
+    KB_TRY(kbk_pack_conv_weight((const float*)params[pi_blk(i, 0)], w.wf(i, 0), w.wd(i, 0), m.C, m.C, m.C, dtype, st));
+    KB_TRY(kbk_pack_conv_weight((const float*)params[pi_blk(i, 3)], w.wf(i, 1), w.wd(i, 1), m.C, m.C, m.C, dtype, st));
+    KB_TRY(bn(1 + 2 * i, pi_blk(i, 1), bi_blk(i, 0), m.C));
+    KB_TRY(bn(2 + 2 * i, pi_blk(i, 4), bi_blk(i, 3), m.C));
+  }
+  KB_TRY(bn(2 * m.nb + 1, pi_head(m, 1), bi_pol(m, 0), m.Pc));
+  return KB_OK;
+}
+
+extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const* params, void* const* buffers,
+                                   float* new_stats, const void* wpack, const float* obs, int B, int training, int dtype, void* workspace,
+                                   long long ws_bytes, void* policy_out, long long policy_pitch, float* value_out,
+                                   float* score_out, int use_tc, int num_sms, cudaStream_t st) {
+  KB_TRY(check_desc(d));
+  KB_CHECK_ARG(dtype == KB_F32 || dtype == KB_BF16, "bad dtype");
+  KB_CHECK_ARG(B >= 1, "batch must be >= 1");
+  KB_CHECK_ARG(policy_pitch >= 81LL * 139, "policy pitch %lld < 11259", policy_pitch);
+  KB_CHECK_ARG(params && buffers && wpack && obs && workspace && policy_out && value_out && score_out, "null pointer");
+  const Dims m = make_dims(d, B, dtype);
+  const WPack wp = make_wpack(m, const_cast<void*>(wpack));
+  BlockWs* blks = (BlockWs*)alloca(sizeof(BlockWs) * (m.nb > 0 ? m.nb : 1));
+  Ws w;
+  carve(m, workspace, training, w, blks);
+  KB_CHECK_ARG((size_t)ws_bytes >= w.total, "workspace too small: %lld < %zu", ws_bytes, w.total);
+  const int C = m.C;
+  auto P = [&](int i) { return (const float*)params[i]; };
+  auto BUF = [&](int i) { return (float*)buffers[i]; };
+  const double count = (double)m.M;
+  const int LP = 2 * m.nb + 1;  // policy BN layer id
+  // training-mode BatchNorm: new running statistics go to `new_stats` ([layer][2][Cmax]) when given
+  // (functional variant for autograd frameworks) or in place into `buffers` (num_batches_tracked too).
+  auto bn_fin = [&](int layer, int pw, int bbase, int Cl) {
+    float* rm_out = new_stats ? new_stats + (size_t)layer * 2 * w.Cmax : BUF(bbase);
+    float* rv_out = new_stats ? new_stats + (size_t)layer * 2 * w.Cmax + w.Cmax : BUF(bbase + 1);
+    long long* nbt = new_stats ? nullptr : (long long*)buffers[bbase + 2];
+    return kbk_bn_finalize(w.dsums, count, P(pw), P(pw + 1), BUF(bbase), BUF(bbase + 1), rm_out, rv_out, nbt, kBnMomentum,
+                           kBnEps, Cl, w.bn_a(layer), w.bn_b(layer), w.bn_mean(layer), w.bn_invstd(layer), st);
+  };
+
+  KB_TRY(kbk_fill_zero(w.dsums, 2 * (size_t)w.Cmax * sizeof(double), st));
+  KB_TRY(kbk_pack_obs(obs, w.obs_p, B, m.C0, m.C0p, dtype, st));
+
+  // ---- stem: x0 = relu(bn(conv(obs))), plus its global-pool statistics ----
+  void* x_cur; float* pool_cur;
+  if (training) {
+    ConvEpi e = epi_base();
+    e.ch_sum = w.dsums; e.ch_sumsq = w.dsums + C;
+    KB_TRY(conv3x3(m, w.obs_p, wp.stem_wf, w.z0, m.C0p, C, e, use_tc, num_sms, st));
+    KB_TRY(bn_fin(0, 1, 0, C));
+    ApplyArgs a; memset(&a, 0, sizeof(a));
+    a.z = w.z0; a.a = w.bn_a(0); a.b = w.bn_b(0); a.out = w.x0; a.pool = w.pool(m, 0); a.B = B; a.C = C; a.dtype = dtype;
+    KB_TRY(kbk_apply(a, st));
+    x_cur = w.x0; pool_cur = w.pool(m, 0);
+  } else {
+    ConvEpi e = epi_base();
+    e.scale = wp.bn_a(0); e.shift = wp.bn_b(0); e.relu = 1; e.pool = w.epool_a;
+    KB_TRY(conv3x3(m, w.obs_p, wp.stem_wf, w.ea, m.C0p, C, e, use_tc, num_sms, st));
+    x_cur = w.ea; pool_cur = w.epool_a;
+  }
+
+  // ---- residual tower ----
+  for (int i = 0; i < m.nb; ++i) {
+    BlockWs& bw = training ? blks[i] : blks[0];
+    const int l1 = 1 + 2 * i, l2 = 2 + 2 * i;
+    // global-pool bias from the block INPUT: g = W2 relu(W1 pool + b1) + b2   (se_resnet.py:73-78)
+    KB_TRY(linear_fwd(pool_cur, KB_F32, 3 * C, B, 3 * C, P(pi_blk(i, 6)), m.G, P(pi_blk(i, 7)), 1, bw.gh, KB_F32, m.G, st));
+    KB_TRY(linear_fwd(bw.gh, KB_F32, m.G, B, m.G, P(pi_blk(i, 8)), C, P(pi_blk(i, 9)), 0, w.g, KB_F32, C, st));
+    const void* z2; void* xout; float* pool_next; const float* se_in;
+    if (training) {
+      ConvEpi e = epi_base();
+      e.ch_sum = w.dsums; e.ch_sumsq = w.dsums + C;
+      KB_TRY(conv3x3(m, x_cur, wp.wf(i, 0), bw.z1, C, C, e, use_tc, num_sms, st));
+      KB_TRY(bn_fin(l1, pi_blk(i, 1), bi_blk(i, 0), C));
+      ApplyArgs a; memset(&a, 0, sizeof(a));
+      a.z = bw.z1; a.a = w.bn_a(l1); a.b = w.bn_b(l1); a.gbias = w.g; a.out = bw.a1; a.B = B; a.C = C; a.dtype = dtype;
+      KB_TRY(kbk_apply(a, st));
+      ConvEpi e2 = epi_base();
+      e2.ch_sum = w.dsums; e2.ch_sumsq = w.dsums + C; e2.board_sum = bw.bmean2; e2.board_scale = 1.f / 81.f;
+      KB_TRY(conv3x3(m, bw.a1, wp.wf(i, 1), bw.z2, C, C, e2, use_tc, num_sms, st));
+      KB_TRY(bn_fin(l2, pi_blk(i, 4), bi_blk(i, 3), C));
+      // SE squeeze input: mean_p(bn2(z2)) = a2 * mean_p(z2) + b2
+      KB_TRY(kbk_affine_rows(bw.bmean2, w.bn_a(l2), w.bn_b(l2), bw.se_in, B, C, st));
+      z2 = bw.z2; xout = bw.xout; pool_next = w.pool(m, i + 1); se_in = bw.se_in;
+    } else {
+      ConvEpi e = epi_base();
+      e.scale = wp.bn_a(l1); e.shift = wp.bn_b(l1); e.relu = 1; e.gbias = w.g;
+      KB_TRY(conv3x3(m, x_cur, wp.wf(i, 0), w.ey1, C, C, e, use_tc, num_sms, st));
+      ConvEpi e2 = epi_base();
+      e2.scale = wp.bn_a(l2); e2.shift = wp.bn_b(l2); e2.board_sum = bw.bmean2; e2.board_scale = 1.f / 81.f;
+      KB_TRY(conv3x3(m, w.ey1, wp.wf(i, 1), w.ey2, C, C, e2, use_tc, num_sms, st));
+      z2 = w.ey2; xout = (x_cur == w.ea) ? w.eb : w.ea; pool_next = (pool_cur == w.epool_a) ? w.epool_b : w.epool_a;
+      se_in = bw.bmean2;  // BN affine already applied in the conv epilogue
+    }
+    // SE excite: (scale, shift) = W2 relu(W1 se_in + b1) + b2   (se_resnet.py:83-86)
+    KB_TRY(linear_fwd(se_in, KB_F32, C, B, C, P(pi_blk(i, 10)), m.S, P(pi_blk(i, 11)), 1, bw.seh, KB_F32, m.S, st));
+    KB_TRY(linear_fwd(bw.seh, KB_F32, m.S, B, m.S, P(pi_blk(i, 12)), 2 * C, P(pi_blk(i, 13)), 0, bw.se, KB_F32, 2 * C, st));
+    // x' = relu(bn2(z2) * sigmoid(scale) + shift + x), plus the pool statistics of x' for the next consumer
+    ApplyArgs a; memset(&a, 0, sizeof(a));
+    a.z = z2; a.a = training ? w.bn_a(l2) : nullptr; a.b = training ? w.bn_b(l2) : nullptr; a.se = bw.se; a.res = x_cur;
+    a.out = xout; a.pool = pool_next; a.B = B; a.C = C; a.dtype = dtype;
+    KB_TRY(kbk_apply(a, st));
+    x_cur = xout; pool_cur = pool_next;
+  }
+
+  // ---- policy head: 1x1 conv -> BN -> ReLU -> 1x1 conv + bias, written NHWC into the padded logits buffer ----
+  const int Pc = m.Pc, M = (int)m.M;
+  KB_TRY(linear_fwd(x_cur, dtype, C, M, C, P(pi_head(m, 0)), Pc, nullptr, 0, w.p1raw, KB_F32, Pc, st));
+  const float *pa, *pb;
+  if (training) {
+    KB_TRY(kbk_rows_stats(w.p1raw, m.M, Pc, w.dsums, st));
+    KB_TRY(bn_fin(LP, pi_head(m, 1), bi_pol(m, 0), Pc));
+    pa = w.bn_a(LP); pb = w.bn_b(LP);
+  } else {
+    pa = wp.bn_a(LP); pb = wp.bn_b(LP);
+  }
+  {
+    ApplyArgs a; memset(&a, 0, sizeof(a));
+    a.z = w.p1raw; a.a = pa; a.b = pb; a.out = w.p1act; a.B = B; a.C = Pc; a.dtype = KB_F32;
+    KB_TRY(kbk_apply(a, st));
+    GemmArgs g = gemm_base();
+    g.A = w.p1act; g.a_dtype = KB_F32; g.lda = Pc;
+    g.B = P(pi_head(m, 3)); g.b_dtype = KB_F32; g.ldb = Pc; g.transB = 1;
+    g.C = policy_out; g.c_dtype = dtype; g.ldc = 139; g.c_group_rows = 81; g.c_group_pitch = policy_pitch;
+    g.bias = P(pi_head(m, 4)); g.M = M; g.N = 139; g.K = Pc;
+    KB_TRY(kbk_gemm(g, st));
+  }
+  // ---- value / score heads on the shared global pool of the trunk output ----
+  KB_TRY(linear_fwd(pool_cur, KB_F32, 3 * C, B, 3 * C, P(pi_head(m, 5)), m.V, P(pi_head(m, 6)), 1, w.vh, KB_F32, m.V, st));
+  KB_TRY(linear_fwd(w.vh, KB_F32, m.V, B, m.V, P(pi_head(m, 7)), 3, P(pi_head(m, 8)), 0, value_out, KB_F32, 3, st));
+  KB_TRY(linear_fwd(pool_cur, KB_F32, 3 * C, B, 3 * C, P(pi_head(m, 9)), m.S2, P(pi_head(m, 10)), 1, w.sh, KB_F32, m.S2, st));
+  KB_TRY(linear_fwd(w.sh, KB_F32, m.S2, B, m.S2, P(pi_head(m, 11)), 1, P(pi_head(m, 12)), 0, score_out, KB_F32, 1, st));
+  return KB_OK;
+}
+
+// Backward of the training-mode forward that filled `workspace`. `grads` must be pre-zeroed fp32
+// buffers shaped like the parameters (same table order).
+extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const* params, const void* wpack, int B,
+                                    int dtype, void* workspace, long long ws_bytes, const void* dpolicy,
+                                    long long policy_pitch, const float* dvalue, const float* dscore,
+                                    void* const* grads, int use_tc, int num_sms, cudaStream_t st) {
+  KB_TRY(check_desc(d));
+  KB_CHECK_ARG(dtype == KB_F32 || dtype == KB_BF16, "bad dtype");
+  KB_CHECK_ARG(B >= 1 && policy_pitch >= 81LL * 139, "bad shape");
+  KB_CHECK_ARG(params && wpack && workspace && dpolicy && dvalue && dscore && grads, "null pointer");
+  const Dims m = make_dims(d, B, dtype);
+  const WPack wp = make_wpack(m, const_cast<void*>(wpack));
+  BlockWs* blks = (BlockWs*)alloca(sizeof(BlockWs) * (m.nb > 0 ? m.nb : 1));
+  Ws w;
+  carve(m, workspace, 1, w, blks);
+  KB_CHECK_ARG((size_t)ws_bytes >= w.total, "workspace too small: %lld < %zu", ws_bytes, w.total);
+  const int C = m.C, Pc = m.Pc, M = (int)m.M;
+  auto P = [&](int i) { return (const float*)params[i]; };
+  auto G = [&](int i) { return (float*)grads[i]; };
+  const double count = (double)m.M;
+  const int LP = 2 * m.nb + 1;
+  float *k1 = w.k123, *k2 = w.k123 + w.Cmax, *k3 = w.k123 + 2 * w.Cmax;
+  const void* x_last = m.nb > 0 ? blks[m.nb - 1].xout : w.x0;
+  const float* pool_f = w.pool(m, m.nb);
+
+  // ---- policy head ----
+  {
+    GemmArgs g = gemm_base();  // dWp2[139][Pc] += dlogits^T * p1act
+    g.A = dpolicy; g.a_dtype = dtype; g.lda = 139; g.transA = 1; g.a_group_rows = 81; g.a_group_pitch = policy_pitch;
+    g.B = w.p1act; g.b_dtype = KB_F32; g.ldb = Pc; g.transB = 0;
+    g.C = G(pi_head(m, 3)); g.c_dtype = KB_F32; g.ldc = Pc; g.M = 139; g.N = Pc; g.K = M;
+    g.splitk = kb_ceil_div(M, 2048) < 2 ? 2 : kb_ceil_div(M, 2048);
+    KB_TRY(kbk_gemm(g, st));
+    KB_TRY(kbk_colsum(dpolicy, dtype, 139, 81, policy_pitch, M, 139, G(pi_head(m, 4)), st));
+    GemmArgs h = gemm_base();  // dp1[M][Pc] = dlogits * Wp2
+    h.A = dpolicy; h.a_dtype = dtype; h.lda = 139; h.a_group_rows = 81; h.a_group_pitch = policy_pitch;
+    h.B = P(pi_head(m, 3)); h.b_dtype = KB_F32; h.ldb = Pc; h.transB = 0;
+    h.C = w.dp1; h.c_dtype = KB_F32; h.ldc = Pc; h.M = M; h.N = Pc; h.K = 139;
+    KB_TRY(kbk_gemm(h, st));
+  }
+  KB_TRY(kbk_relu_bwd_stats_f32(w.dp1, w.p1act, w.p1raw, m.M, Pc, w.dsums, st));
+  KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(pi_head(m, 1)), w.bn_mean(LP), w.bn_invstd(LP), k1, k2, k3,
+                             G(pi_head(m, 1)), G(pi_head(m, 2)), Pc, st));
+  KB_TRY(kbk_bn_bwd_apply(w.dp1, w.p1raw, k1, k2, k3, m.M, Pc, KB_F32, st));
+  KB_TRY(linear_bwd_w(w.dp1, KB_F32, Pc, x_last, dtype, C, M, Pc, C, G(pi_head(m, 0)), nullptr, st));
+  KB_TRY(linear_bwd_x(w.dp1, KB_F32, Pc, M, Pc, P(pi_head(m, 0)), C, w.d1, dtype, C, nullptr, 0, 0, st));
+  // ---- value / score heads ----
+  KB_TRY(linear_bwd_w(dvalue, KB_F32, 3, w.vh, KB_F32, m.V, B, 3, m.V, G(pi_head(m, 7)), G(pi_head(m, 8)), st));
+  KB_TRY(linear_bwd_x(dvalue, KB_F32, 3, B, 3, P(pi_head(m, 7)), m.V, w.dvh, KB_F32, m.V, w.vh, m.V, 0, st));
+  KB_TRY(linear_bwd_w(w.dvh, KB_F32, m.V, pool_f, KB_F32, 3 * C, B, m.V, 3 * C, G(pi_head(m, 5)), G(pi_head(m, 6)), st));
+  KB_TRY(linear_bwd_x(w.dvh, KB_F32, m.V, B, m.V, P(pi_head(m, 5)), 3 * C, w.dpool, KB_F32, 3 * C, nullptr, 0, 0, st));
+  KB_TRY(linear_bwd_w(dscore, KB_F32, 1, w.sh, KB_F32, m.S2, B, 1, m.S2, G(pi_head(m, 11)), G(pi_head(m, 12)), st));
+  KB_TRY(linear_bwd_x(dscore, KB_F32, 1, B, 1, P(pi_head(m, 11)), m.S2, w.dsh, KB_F32, m.S2, w.sh, m.S2, 0, st));
+  KB_TRY(linear_bwd_w(w.dsh, KB_F32, m.S2, pool_f, KB_F32, 3 * C, B, m.S2, 3 * C, G(pi_head(m, 9)), G(pi_head(m, 10)), st));
+  KB_TRY(linear_bwd_x(w.dsh, KB_F32, m.S2, B, m.S2, P(pi_head(m, 9)), 3 * C, w.dpool, KB_F32, 3 * C, nullptr, 0, 1, st));
+  // dL/dx_last = policy path + global-pool backward
+  void *cur = w.d0, *t1 = w.d1, *t2 = w.d2;
+  {
+    PassDArgs a; memset(&a, 0, sizeof(a));
+    a.B = B; a.C = C; a.dtype = dtype; a.dxc = w.d1; a.x = x_last; a.pool = pool_f; a.dpool = w.dpool; a.dx = cur;
+    KB_TRY(kbk_block_bwd_dx(a, st));
+  }
+
+  // ---- residual tower, last block first ----
+  for (int i = m.nb - 1; i >= 0; --i) {
+    BlockWs& bw = blks[i];
+    const void* x_in = i > 0 ? blks[i - 1].xout : w.x0;
+    const float* pool_in = w.pool(m, i);
+    const int l1 = 1 + 2 * i, l2 = 2 + 2 * i;
+    // pass A: du = dx' * [x' > 0]; per-(board, channel) sums
+    BlockBwdArgs ra; memset(&ra, 0, sizeof(ra));
+    ra.B = B; ra.C = C; ra.dtype = dtype; ra.dxp = cur; ra.xp = bw.xout; ra.z2 = bw.z2; ra.s_du = w.s_du; ra.s_duz = w.s_duz;
+    KB_TRY(kbk_block_bwd_reduce(ra, st));
+    KB_TRY(kbk_se_bwd_prep(w.s_du, w.s_duz, w.bn_a(l2), w.bn_b(l2), bw.se, w.dse, B, C, st));
+    // SE MLP backward
+    KB_TRY(linear_bwd_w(w.dse, KB_F32, 2 * C, bw.seh, KB_F32, m.S, B, 2 * C, m.S, G(pi_blk(i, 12)), G(pi_blk(i, 13)), st));
+    KB_TRY(linear_bwd_x(w.dse, KB_F32, 2 * C, B, 2 * C, P(pi_blk(i, 12)), m.S, w.dseh, KB_F32, m.S, bw.seh, m.S, 0, st));
+    KB_TRY(linear_bwd_w(w.dseh, KB_F32, m.S, bw.se_in, KB_F32, C, B, m.S, C, G(pi_blk(i, 10)), G(pi_blk(i, 11)), st));
+    KB_TRY(linear_bwd_x(w.dseh, KB_F32, m.S, B, m.S, P(pi_blk(i, 10)), C, w.dse_in, KB_F32, C, nullptr, 0, 0, st));
+    // BN2 backward statistics from board-level sums, then dz2
+    KB_TRY(kbk_bn2_bwd_sums(w.s_du, w.s_duz, bw.se, w.dse_in, bw.bmean2, B, C, w.dsums, st));
+    KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(pi_blk(i, 4)), w.bn_mean(l2), w.bn_invstd(l2), k1, k2, k3,
+                               G(pi_blk(i, 4)), G(pi_blk(i, 5)), C, st));
+    PassBArgs pb; memset(&pb, 0, sizeof(pb));
+    pb.B = B; pb.C = C; pb.dtype = dtype; pb.dxp = cur; pb.xp = bw.xout; pb.z2 = bw.z2; pb.se = bw.se; pb.dse_in = w.dse_in;
+    pb.k1 = k1; pb.k2 = k2; pb.k3 = k3; pb.dz2 = t1;
+    KB_TRY(kbk_block_bwd_dz2(pb, st));
+    // conv2: weight gradient, then data gradient with the BN1/ReLU/gpool-bias backward fused in its epilogue
+    KB_TRY(wgrad3x3(m, bw.a1, t1, G(pi_blk(i, 3)), C, C, C, use_tc, num_sms, st));
+    ConvEpi e = epi_base();
+    e.mask_src = bw.z1; e.mask_a = w.bn_a(l1); e.mask_b = w.bn_b(l1);
+    e.ch_sum = w.dsums; e.ch_dot = w.dsums + C; e.board_sum = w.dg; e.board_scale = 1.f;
+    KB_TRY(conv3x3(m, t1, wp.wd(i, 1), t2, C, C, e, use_tc, num_sms, st));
+    KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(pi_blk(i, 1)), w.bn_mean(l1), w.bn_invstd(l1), k1, k2, k3,
+                               G(pi_blk(i, 1)), G(pi_blk(i, 2)), C, st));
+    // global-pool-bias MLP backward -> gradient wrt the pool statistics of the block input
+    KB_TRY(linear_bwd_w(w.dg, KB_F32, C, bw.gh, KB_F32, m.G, B, C, m.G, G(pi_blk(i, 8)), G(pi_blk(i, 9)), st));
+    KB_TRY(linear_bwd_x(w.dg, KB_F32, C, B, C, P(pi_blk(i, 8)), m.G, w.dgh, KB_F32, m.G, bw.gh, m.G, 0, st));
+    KB_TRY(linear_bwd_w(w.dgh, KB_F32, m.G, pool_in, KB_F32, 3 * C, B, m.G, 3 * C, G(pi_blk(i, 6)), G(pi_blk(i, 7)), st));
+    KB_TRY(linear_bwd_x(w.dgh, KB_F32, m.G, B, m.G, P(pi_blk(i, 6)), 3 * C, w.dpool, KB_F32, 3 * C, nullptr, 0, 0, st));
+    // pass C: dz1 in place; conv1 weight + data gradients
+    KB_TRY(kbk_bn_bwd_apply(t2, bw.z1, k1, k2, k3, m.M, C, dtype, st));
+    KB_TRY(wgrad3x3(m, x_in, t2, G(pi_blk(i, 0)), C, C, C, use_tc, num_sms, st));
+    ConvEpi e1 = epi_base();
+    KB_TRY(conv3x3(m, t2, wp.wd(i, 0), t1, C, C, e1, use_tc, num_sms, st));
+    // pass D: dx = dgrad + residual branch + global-pool backward
+    PassDArgs pd; memset(&pd, 0, sizeof(pd));
+    pd.B = B; pd.C = C; pd.dtype = dtype; pd.dxc = t1; pd.dxp = cur; pd.xp = bw.xout; pd.x = x_in; pd.pool = pool_in;
+    pd.dpool = w.dpool; pd.dx = t2;
+    KB_TRY(kbk_block_bwd_dx(pd, st));
+    void* nc = t2; t2 = t1; t1 = cur; cur = nc;
+  }
+
+  // ---- stem ----
+  KB_TRY(kbk_relu_bwd_stats(cur, w.x0, w.z0, t1, m.M, C, dtype, w.dsums, st));
+  KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(1), w.bn_mean(0), w.bn_invstd(0), k1, k2, k3, G(1), G(2), C, st));
+  KB_TRY(kbk_bn_bwd_apply(t1, w.z0, k1, k2, k3, m.M, C, dtype, st));
+  KB_TRY(wgrad3x3(m, w.obs_p, t1, G(0), m.C0p, C, m.C0, use_tc, num_sms, st));
+  return KB_OK;
+}

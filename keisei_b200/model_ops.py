@@ -1,0 +1,249 @@
+"""torch.library custom ops for the SE-ResNet forward / backward (csrc/model.cu).
+
+`keisei_b200::seresnet_forward`   one C call that enqueues the whole network on the current stream
+`keisei_b200::seresnet_backward`  the matching backward (training-mode workspaces only)
+
+Autograd is registered on the forward op: gradients flow from (policy, value_logits, score_lead)
+to every parameter. The observation never receives a gradient (reference: obs is data).
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int, c_longlong, c_void_p
+from typing import List
+
+import torch
+
+from . import _lib
+
+POLICY_A = 81 * 139          # 11,259
+POLICY_PITCH = 11264         # padded logits row (16-byte aligned in bf16 and fp32)
+
+
+class SeResnetDesc(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in ("num_blocks", "channels", "se_hidden", "gpool_channels", "policy_channels",
+                                      "value_fc", "score_fc", "obs_channels")]
+
+
+_P = c_void_p
+_lib.register_signature("kb_seresnet_num_params", c_longlong, [_P])
+_lib.register_signature("kb_seresnet_num_buffers", c_longlong, [_P])
+_lib.register_signature("kb_seresnet_wpack_bytes", c_longlong, [_P, c_int])
+_lib.register_signature("kb_seresnet_workspace_bytes", c_longlong, [_P, c_int, c_int, c_int])
+_lib.register_signature("kb_seresnet_pack_weights", c_int, [_P, _P, _P, c_int, _P, c_longlong, _P])
+_lib.register_signature("kb_seresnet_forward", c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_longlong, _P,
+                                                        c_longlong, _P, _P, c_int, c_int, _P])
+_lib.register_signature("kb_seresnet_backward", c_int, [_P, _P, _P, c_int, c_int, _P, c_longlong, _P, c_longlong, _P,
+                                                         _P, _P, c_int, c_int, _P])
+_lib.register_signature("kb_conv3x3_forward", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P,
+                                                       _P, _P, _P, c_int, _P])
+_lib.register_signature("kb_conv3x3_wgrad", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P])
+_lib.register_signature("kb_pack_conv_weight", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P])
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+_DT_INV = {0: torch.float32, 1: torch.bfloat16}
+_sm_count_cache: dict[int, int] = {}
+
+
+def sm_count(device: torch.device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _sm_count_cache:
+        _sm_count_cache[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _sm_count_cache[idx]
+
+
+def _desc(desc: List[int]) -> SeResnetDesc:
+    return SeResnetDesc(*[int(v) for v in desc])
+
+
+def _ptr_table(tensors) -> ctypes.Array:
+    arr = (c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def wpack_bytes(desc: List[int], dtype_code: int) -> int:
+    d = _desc(desc)
+    n = _lib.load().kb_seresnet_wpack_bytes(ctypes.byref(d), dtype_code)
+    if n < 0:
+        _lib.check(-1, "kb_seresnet_wpack_bytes")
+    return int(n)
+
+
+def workspace_bytes(desc: List[int], B: int, training: bool, dtype_code: int) -> int:
+    d = _desc(desc)
+    n = _lib.load().kb_seresnet_workspace_bytes(ctypes.byref(d), B, 1 if training else 0, dtype_code)
+    if n < 0:
+        _lib.check(-1, "kb_seresnet_workspace_bytes")
+    return int(n)
+
+
+def _check_tables(params, buffers, d: SeResnetDesc):
+    n_p, n_b = 16 + 14 * d.num_blocks, 6 + 6 * d.num_blocks
+    if len(params) != n_p or len(buffers) != n_b:
+        raise ValueError(f"expected {n_p} params / {n_b} buffers, got {len(params)} / {len(buffers)}")
+    for t in params:
+        if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+            raise ValueError("model parameters must be contiguous float32 CUDA tensors")
+
+
+@torch.no_grad()
+def pack_weights(params, buffers, desc: List[int], dtype_code: int, wpack: torch.Tensor) -> None:
+    d = _desc(desc)
+    _check_tables(params, buffers, d)
+    dev = wpack.device
+    pt, bt = _ptr_table(params), _ptr_table(buffers)
+    with torch.cuda.device(dev):
+        rc = _lib.load().kb_seresnet_pack_weights(ctypes.byref(d), pt, bt, dtype_code, wpack.data_ptr(),
+                                                  wpack.numel(), _lib.stream_ptr(dev))
+    _lib.check(rc, "kb_seresnet_pack_weights")
+
+
+@torch.library.custom_op("keisei_b200::seresnet_forward", mutates_args=())
+def seresnet_forward(obs: torch.Tensor, params: List[torch.Tensor], buffers: List[torch.Tensor], wpack: torch.Tensor,
+                     desc: List[int], training: bool, dtype_code: int,
+                     use_tc: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Returns (policy_buf (B, 11264) act-dtype, value_logits (B,3) f32, score_lead (B,1) f32, workspace u8,
+    new_stats f32 [(2*nb+2), 2, Cmax]: the updated BatchNorm running mean/var rows in training mode).
+    Functional: `buffers` is read-only here; the module copies new_stats back (see SEResNetModel)."""
+    if not obs.is_cuda:
+        raise _lib.KeiseiB200Error("keisei_b200::seresnet_forward needs CUDA tensors")
+    d = _desc(desc)
+    _check_tables(params, buffers, d)
+    dev = obs.device
+    B = obs.shape[0]
+    obs_c = obs.detach().to(torch.float32).contiguous()
+    ws = torch.empty(workspace_bytes(desc, B, training, dtype_code), dtype=torch.uint8, device=dev)
+    policy = torch.empty((B, POLICY_PITCH), dtype=_DT_INV[dtype_code], device=dev)
+    policy[:, POLICY_A:].zero_()
+    value = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    score = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    cmax = max(d.channels, d.policy_channels)
+    new_stats = torch.empty((2 * d.num_blocks + 2, 2, cmax) if training else (0,), dtype=torch.float32, device=dev)
+    pt, bt = _ptr_table(params), _ptr_table(buffers)
+    with torch.cuda.device(dev):
+        rc = _lib.load().kb_seresnet_forward(
+            ctypes.byref(d), pt, bt, new_stats.data_ptr() if training else None, wpack.data_ptr(), obs_c.data_ptr(), B, 1 if training else 0, dtype_code,
+            ws.data_ptr(), ws.numel(), policy.data_ptr(), POLICY_PITCH, value.data_ptr(), score.data_ptr(),
+            1 if use_tc else 0, sm_count(dev), _lib.stream_ptr(dev))
+    _lib.check(rc, "kb_seresnet_forward")
+    return policy, value, score, ws, new_stats
+
+
+@seresnet_forward.register_fake
+def _(obs, params, buffers, wpack, desc, training, dtype_code, use_tc):
+    B = obs.shape[0]
+    return (obs.new_empty((B, POLICY_PITCH), dtype=_DT_INV[dtype_code]), obs.new_empty((B, 3), dtype=torch.float32),
+            obs.new_empty((B, 1), dtype=torch.float32), obs.new_empty((1,), dtype=torch.uint8),
+            obs.new_empty((1,), dtype=torch.float32))
+
+
+@torch.library.custom_op("keisei_b200::seresnet_backward", mutates_args=())
+def seresnet_backward(params: List[torch.Tensor], wpack: torch.Tensor, ws: torch.Tensor, dpolicy: torch.Tensor,
+                      dvalue: torch.Tensor, dscore: torch.Tensor, desc: List[int], dtype_code: int,
+                      use_tc: bool) -> torch.Tensor:
+    """Returns ONE flat fp32 gradient buffer (parameters concatenated in table order)."""
+    d = _desc(desc)
+    dev = ws.device
+    B = dvalue.shape[0]
+    dpol = dpolicy
+    if dpol.dtype != _DT_INV[dtype_code] or dpol.stride(1) != 1 or dpol.stride(0) < POLICY_A:
+        dpol = dpol.to(_DT_INV[dtype_code]).contiguous()
+    dv = dvalue.to(torch.float32).contiguous()
+    ds = dscore.to(torch.float32).reshape(B).contiguous()
+    sizes = [p.numel() for p in params]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    grads = [g.view(p.shape) for g, p in zip(flat.split(sizes), params)]
+    pt, gt = _ptr_table(params), _ptr_table(grads)
+    with torch.cuda.device(dev):
+        rc = _lib.load().kb_seresnet_backward(
+            ctypes.byref(d), pt, wpack.data_ptr(), B, dtype_code, ws.data_ptr(), ws.numel(), dpol.data_ptr(),
+            dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), _lib.stream_ptr(dev))
+    _lib.check(rc, "kb_seresnet_backward")
+    return flat
+
+
+@seresnet_backward.register_fake
+def _(params, wpack, ws, dpolicy, dvalue, dscore, desc, dtype_code, use_tc):
+    return params[0].new_empty((sum(p.numel() for p in params),), dtype=torch.float32)
+
+
+def _fwd_setup(ctx, inputs, output):
+    obs, params, buffers, wpack, desc, training, dtype_code, use_tc = inputs
+    policy, value, score, ws, _new_stats = output
+    ctx.desc, ctx.dtype_code, ctx.use_tc, ctx.training = desc, dtype_code, use_tc, training
+    ctx.n_params = len(params)
+    ctx.n_buffers = len(buffers)
+    ctx.save_for_backward(wpack, ws, *params)
+    ctx.policy_meta = (policy.shape, policy.dtype, policy.device)
+    ctx.B = obs.shape[0]
+
+
+def _fwd_backward(ctx, g_policy, g_value, g_score, g_ws, g_stats):
+    if not ctx.training:
+        raise RuntimeError("keisei_b200::seresnet_forward was run in eval mode; backward needs training=True "
+                           "(batch-statistics BatchNorm and saved activations)")
+    wpack, ws, *params = ctx.saved_tensors
+    shape, dtype, dev = ctx.policy_meta
+    if g_policy is None:
+        g_policy = torch.zeros(shape, dtype=dtype, device=dev)
+    if g_value is None:
+        g_value = torch.zeros((ctx.B, 3), dtype=torch.float32, device=dev)
+    if g_score is None:
+        g_score = torch.zeros((ctx.B, 1), dtype=torch.float32, device=dev)
+    flat = seresnet_backward(list(params), wpack, ws, g_policy, g_value, g_score, ctx.desc, ctx.dtype_code, ctx.use_tc)
+    grads = [g.view(p.shape) for g, p in zip(flat.split([p.numel() for p in params]), params)]
+    return None, grads, [None] * ctx.n_buffers, None, None, None, None, None
+
+
+seresnet_forward.register_autograd(_fwd_backward, setup_context=_fwd_setup)
+
+
+# ---- single-conv helpers (tests / profiling) -------------------------------------------------
+@torch.no_grad()
+def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, cin_pad: int | None = None, with_dgrad: bool = False):
+    """(Cout,Cin,3,3) fp32 -> wf (Cout,9,Cinp) [, wd (Cinp,9,Cout)] in `dtype`."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    Cinp = cin_pad or Cin
+    wf = torch.empty((Cout, 9, Cinp), dtype=dtype, device=w.device)
+    wd = torch.empty((Cinp, 9, Cout), dtype=dtype, device=w.device) if with_dgrad else None
+    with torch.cuda.device(w.device):
+        rc = _lib.load().kb_pack_conv_weight(w.contiguous().data_ptr(), wf.data_ptr(), _lib.ptr(wd), Cout, Cin, Cinp,
+                                             _DT[dtype], _lib.stream_ptr(w.device))
+    _lib.check(rc, "kb_pack_conv_weight")
+    return (wf, wd) if with_dgrad else wf
+
+
+@torch.no_grad()
+def conv3x3(x: torch.Tensor, wf: torch.Tensor, backend: int = 0, scale=None, shift=None, relu: bool = False,
+            gbias=None, want_sums: bool = False, want_board_mean: bool = False, want_pool: bool = False):
+    """x (B,81,Cin) NHWC, wf (Cout,9,Cin). Returns (out, ch_sums|None, board_mean|None, pool|None)."""
+    B, _, Cin = x.shape
+    Cout = wf.shape[0]
+    dev = x.device
+    out = torch.empty((B, 81, Cout), dtype=x.dtype, device=dev)
+    sums = torch.zeros(2 * Cout, dtype=torch.float64, device=dev) if want_sums else None
+    bm = torch.empty((B, Cout), dtype=torch.float32, device=dev) if want_board_mean else None
+    pool = torch.empty((B, 3 * Cout), dtype=torch.float32, device=dev) if want_pool else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().kb_conv3x3_forward(
+            x.contiguous().data_ptr(), wf.contiguous().data_ptr(), out.data_ptr(), B, Cin, Cout, _DT[x.dtype], backend,
+            _lib.ptr(scale), _lib.ptr(shift), 1 if relu else 0, _lib.ptr(gbias), _lib.ptr(sums), _lib.ptr(bm),
+            _lib.ptr(pool), sm_count(dev), _lib.stream_ptr(dev))
+    _lib.check(rc, "kb_conv3x3_forward")
+    return out, sums, bm, pool
+
+
+@torch.no_grad()
+def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, cin_true: int | None = None, backend: int = 0) -> torch.Tensor:
+    """dW (Cout, Cin_true, 3, 3) fp32 from x (B,81,Cin) and dy (B,81,Cout)."""
+    B, _, Cin = x.shape
+    Cout = dy.shape[2]
+    ct = cin_true or Cin
+    dw = torch.zeros((Cout, ct, 3, 3), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().kb_conv3x3_wgrad(x.contiguous().data_ptr(), dy.contiguous().data_ptr(), dw.data_ptr(), B, Cin,
+                                          Cout, ct, _DT[x.dtype], backend, sm_count(x.device), _lib.stream_ptr(x.device))
+    _lib.check(rc, "kb_conv3x3_wgrad")
+    return dw

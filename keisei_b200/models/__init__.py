@@ -1,0 +1,3 @@
+"""Host-side mirrors of the reference model classes on the hot path (keisei/training/models/)."""
+from .katago_base import KataGoBaseModel, KataGoOutput  # noqa: F401
+from .se_resnet import GlobalPoolBiasBlock, SEResNetModel, SEResNetParams  # noqa: F401

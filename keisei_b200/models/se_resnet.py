@@ -1,0 +1,188 @@
+"""SE-ResNet with KataGo-style global-pool bias — drop-in for the reference's `se_resnet` registry
+entry (keisei/training/models/se_resnet.py:15-159).
+
+Parameters and buffers are ordinary fp32 `nn.Parameter`s held by standard `nn.Conv2d` /
+`nn.BatchNorm2d` / `nn.Linear` containers with the reference's attribute names, so `state_dict()`
+keys, shapes and registration order are identical (strict loads, positional Adam state).
+The containers are never *called* on CUDA: a CUDA observation runs the whole network through one
+C-ABI call (`keisei_b200::seresnet_forward`, csrc/model.cu) — tcgen05 implicit-GEMM convolutions
+in bf16 when AMP is configured, fp32-accurate SIMT kernels otherwise. CPU tensors (the reference's
+showcase sidecar and unit tests are CPU-only) run the same graph with plain PyTorch CPU ops.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import model_ops
+from .katago_base import KataGoBaseModel, KataGoOutput
+
+
+@dataclass(frozen=True)
+class SEResNetParams:
+    num_blocks: int = 40
+    channels: int = 256
+    se_reduction: int = 16
+    global_pool_channels: int = 128
+    policy_channels: int = 32
+    value_fc_size: int = 256
+    score_fc_size: int = 128
+    obs_channels: int = 50
+
+    def __post_init__(self) -> None:
+        for name in ("num_blocks", "channels", "se_reduction", "global_pool_channels", "policy_channels",
+                     "value_fc_size", "score_fc_size", "obs_channels"):
+            if getattr(self, name) < 1:
+                raise ValueError(f"{name} must be >= 1, got {getattr(self, name)}")
+        if self.channels // self.se_reduction < 1:
+            raise ValueError(
+                f"channels ({self.channels}) // se_reduction ({self.se_reduction}) must be >= 1")
+
+
+def _global_pool(x: torch.Tensor) -> torch.Tensor:
+    """(B,C,H,W) -> (B,3C): mean, max, population std (reference se_resnet.py:93-98)."""
+    return torch.cat([x.mean(dim=(-2, -1)), x.amax(dim=(-2, -1)), x.std(dim=(-2, -1), correction=0)], dim=-1)
+
+
+class GlobalPoolBiasBlock(nn.Module):
+    """conv1 -> BN -> ReLU -> + global_fc(pool(block input)) -> conv2 -> BN -> SE(scale, shift)
+    -> + residual -> ReLU  (reference se_resnet.py:40-90). Parameter container; `forward` is the
+    CPU path."""
+
+    def __init__(self, channels: int, se_reduction: int, global_pool_channels: int) -> None:
+        super().__init__()
+        self.conv1 = nn.Conv2d(channels, channels, 3, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(channels)
+        self.conv2 = nn.Conv2d(channels, channels, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(channels)
+        self.global_fc = nn.Sequential(
+            nn.Linear(channels * 3, global_pool_channels), nn.ReLU(), nn.Linear(global_pool_channels, channels))
+        se_hidden = channels // se_reduction
+        self.se_fc1 = nn.Linear(channels, se_hidden)
+        self.se_fc2 = nn.Linear(se_hidden, channels * 2)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = out + self.global_fc(_global_pool(x))[:, :, None, None]
+        out = self.bn2(self.conv2(out))
+        se = self.se_fc2(F.relu(self.se_fc1(out.mean(dim=(-2, -1)))))
+        scale, shift = se.chunk(2, dim=-1)
+        out = out * torch.sigmoid(scale)[:, :, None, None] + shift[:, :, None, None]
+        return F.relu(out + x)
+
+
+class SEResNetModel(KataGoBaseModel):
+    """3-head SE-ResNet. `forward(obs) -> KataGoOutput`; ValueError on a bad observation shape."""
+
+    def __init__(self, params: SEResNetParams) -> None:
+        super().__init__()
+        self.params = params
+        ch = params.channels
+        self.input_conv = nn.Conv2d(params.obs_channels, ch, 3, padding=1, bias=False)
+        self.input_bn = nn.BatchNorm2d(ch)
+        self.blocks = nn.Sequential(*[
+            GlobalPoolBiasBlock(ch, params.se_reduction, params.global_pool_channels)
+            for _ in range(params.num_blocks)])
+        self.policy_conv1 = nn.Conv2d(ch, params.policy_channels, 1, bias=False)
+        self.policy_bn1 = nn.BatchNorm2d(params.policy_channels)
+        self.policy_conv2 = nn.Conv2d(params.policy_channels, self.SPATIAL_MOVE_TYPES, 1)
+        self.value_fc1 = nn.Linear(ch * 3, params.value_fc_size)
+        self.value_fc2 = nn.Linear(params.value_fc_size, 3)
+        self.score_fc1 = nn.Linear(ch * 3, params.score_fc_size)
+        self.score_fc2 = nn.Linear(params.score_fc_size, 1)
+        # kernel-side state (not part of state_dict)
+        self._wpack: torch.Tensor | None = None
+        self._wpack_key: tuple | None = None
+        self.use_tensor_cores: bool = True   # tcgen05 convolutions whenever the bf16 path is selected
+        self.last_policy_buffer: torch.Tensor | None = None  # padded (B, 11264) logits of the last CUDA forward
+
+    # ---- kernel plumbing ---------------------------------------------------------------------
+    def _desc(self) -> list[int]:
+        p = self.params
+        return [p.num_blocks, p.channels, p.channels // p.se_reduction, p.global_pool_channels, p.policy_channels,
+                p.value_fc_size, p.score_fc_size, p.obs_channels]
+
+    def kernel_supported(self) -> bool:
+        p = self.params
+        return p.channels % 4 == 0 and p.channels <= 1024 and p.policy_channels <= 1024 and p.obs_channels <= 128
+
+    def _tables(self) -> tuple[list[torch.Tensor], list[torch.Tensor]]:
+        return list(self.parameters()), list(self.buffers())
+
+    def _act_dtype(self, device: torch.device) -> torch.dtype:
+        if self._amp_enabled and self._amp_dtype == torch.bfloat16:
+            return torch.bfloat16
+        if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            return torch.bfloat16
+        return torch.float32
+
+    def _packed(self, params, buffers, dtype: torch.dtype) -> torch.Tensor:
+        dev = params[0].device
+        key = (dtype, dev, sum(p._version for p in params) + sum(b._version for b in buffers),
+               params[0].data_ptr())
+        if self._wpack is None or self._wpack_key != key:
+            code = 0 if dtype == torch.float32 else 1
+            nbytes = model_ops.wpack_bytes(self._desc(), code)
+            if self._wpack is None or self._wpack.numel() != nbytes or self._wpack.device != dev:
+                self._wpack = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            model_ops.pack_weights(params, buffers, self._desc(), code, self._wpack)
+            self._wpack_key = key
+        return self._wpack
+
+    def _forward_cuda(self, obs: torch.Tensor) -> KataGoOutput:
+        if not self.kernel_supported():
+            raise model_ops._lib.KeiseiB200Error(
+                f"SEResNetParams {self.params} not supported by the CUDA kernels (channels must be a multiple of 4)")
+        params, buffers = self._tables()
+        dtype = self._act_dtype(obs.device)
+        code = 0 if dtype == torch.float32 else 1
+        training = self.training
+        wpack = self._packed(params, buffers, dtype)
+        policy_buf, value, score, _ws, new_stats = model_ops.seresnet_forward(
+            obs, params, buffers, wpack, self._desc(), training, code, bool(self.use_tensor_cores))
+        if training:
+            self._store_running_stats(buffers, new_stats)
+        B = obs.shape[0]
+        self.last_policy_buffer = policy_buf
+        policy = policy_buf[:, :model_ops.POLICY_A].view(B, 9, 9, self.SPATIAL_MOVE_TYPES)
+        return KataGoOutput(policy_logits=policy, value_logits=value, score_lead=score)
+
+    @torch.no_grad()
+    def _store_running_stats(self, buffers: list[torch.Tensor], new_stats: torch.Tensor) -> None:
+        """Copy the kernel's updated BatchNorm running statistics back into the registered buffers
+        (buffer order: running_mean, running_var, num_batches_tracked per BN layer) with batched
+        foreach ops; bumps the buffers' version counters so the folded eval weights get refreshed."""
+        dst, src, nbt = [], [], []
+        for layer in range(len(buffers) // 3):
+            rm, rv, n = buffers[3 * layer], buffers[3 * layer + 1], buffers[3 * layer + 2]
+            c = rm.numel()
+            dst += [rm, rv]
+            src += [new_stats[layer, 0, :c], new_stats[layer, 1, :c]]
+            nbt.append(n)
+        torch._foreach_copy_(dst, src)
+        torch._foreach_add_(nbt, 1)
+
+    # ---- CPU path (showcase sidecar, unit tests): plain PyTorch on the same parameters ----------
+    def _forward_host(self, obs: torch.Tensor) -> KataGoOutput:
+        x = F.relu(self.input_bn(self.input_conv(obs)))
+        x = self.blocks(x)
+        p = F.relu(self.policy_bn1(self.policy_conv1(x)))
+        p = self.policy_conv2(p).permute(0, 2, 3, 1)
+        pool = _global_pool(x)
+        v = self.value_fc2(F.relu(self.value_fc1(pool)))
+        s = self.score_fc2(F.relu(self.score_fc1(pool)))
+        return KataGoOutput(policy_logits=p, value_logits=v, score_lead=s)
+
+    def _forward_impl(self, obs: torch.Tensor) -> KataGoOutput:
+        p = self.params
+        if obs.ndim != 4 or obs.shape[1] != p.obs_channels or obs.shape[2] != 9 or obs.shape[3] != 9:
+            raise ValueError(f"Expected obs shape (batch, {p.obs_channels}, 9, 9), got {tuple(obs.shape)}")
+        if obs.is_cuda:
+            return self._forward_cuda(obs)
+        if self._amp_enabled:
+            with torch.amp.autocast(device_type=self._amp_device_type, dtype=self._amp_dtype):
+                return self._forward_host(obs)
+        return self._forward_host(obs)
