@@ -14,6 +14,7 @@ extern "C" int kb_conv3x3_forward(const void* in, const void* w, void* out, int 
   if (ch_sums) { e.ch_sum = ch_sums; e.ch_sumsq = ch_sums + Cout; }
   e.board_sum = board_mean; e.board_scale = 1.f / 81.f; e.pool = pool;
   if (backend == 1) {
+    KB_CHECK_ARG(B >= 3, "kb_conv3x3_forward: tcgen05 path needs at least 3 boards");
     KB_CHECK_ARG(kbk_conv3x3_tc_supported(Cin, Cout, dtype), "kb_conv3x3_forward: tcgen05 path needs bf16, Cin%%64==0, Cout%%128==0 (got %d,%d,dtype %d)", Cin, Cout, dtype);
     return kbk_conv3x3_tc(in, w, out, B, Cin, Cout, e, num_sms, stream);
   }

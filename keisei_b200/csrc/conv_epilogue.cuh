@@ -28,33 +28,48 @@ struct ConvEpi {
   float* pool;            // [B][3*Cout] or null: mean, max, population std of stored v
 };
 
+// Feature bits: a kernel may be instantiated for a fixed feature set F (branches resolved at compile
+// time — the tcgen05 epilogue is fully unrolled over 243 columns) or with kEpiDynamic, where the
+// null-ness of the ConvEpi pointers decides at run time (the SIMT kernels).
+enum : int {
+  kEpiAffine = 1, kEpiRelu = 2, kEpiGbias = 4, kEpiMask = 8, kEpiSum = 16, kEpiSumSq = 32, kEpiDot = 64,
+  kEpiBoard = 128, kEpiPool = 256, kEpiDynamic = -1
+};
+inline int conv_epi_features(const ConvEpi& e) {
+  return (e.scale ? kEpiAffine : 0) | (e.relu ? kEpiRelu : 0) | (e.gbias ? kEpiGbias : 0) | (e.mask_src ? kEpiMask : 0) |
+         (e.ch_sum ? kEpiSum : 0) | (e.ch_sumsq ? kEpiSumSq : 0) | (e.ch_dot ? kEpiDot : 0) | (e.board_sum ? kEpiBoard : 0) |
+         (e.pool ? kEpiPool : 0);
+}
+
 #ifdef __CUDACC__
 // Per-thread epilogue state for one output channel over NB boards.
-template <typename T, int NB>
+template <typename T, int NB, int F>
 struct ConvEpiThread {
   const ConvEpi& e;
   const int c, Cout, B;
   float sc, sh, ma, mb;
   float s[NB], ss[NB], mx[NB], dot[NB], pre[NB];
   float k0[NB], ds[NB], dss[NB];  // shifted-data accumulators for a cancellation-free board variance
+  static __device__ __forceinline__ bool on(int bit, bool runtime) { return F == kEpiDynamic ? runtime : (F & bit) != 0; }
   __device__ __forceinline__ ConvEpiThread(const ConvEpi& e_, int c_, int Cout_, int B_)
       : e(e_), c(c_), Cout(Cout_), B(B_) {
-    sc = e.scale ? e.scale[c] : 1.f;
-    sh = e.scale ? e.shift[c] : 0.f;
-    ma = e.mask_src ? e.mask_a[c] : 0.f;
-    mb = e.mask_src ? e.mask_b[c] : 0.f;
+    const bool aff = on(kEpiAffine, e.scale != nullptr), msk = on(kEpiMask, e.mask_src != nullptr);
+    sc = aff ? e.scale[c] : 1.f;
+    sh = aff ? e.shift[c] : 0.f;
+    ma = msk ? e.mask_a[c] : 0.f;
+    mb = msk ? e.mask_b[c] : 0.f;
 #pragma unroll
     for (int j = 0; j < NB; ++j) { s[j] = 0.f; ss[j] = 0.f; mx[j] = -INFINITY; dot[j] = 0.f; pre[j] = 0.f; k0[j] = 0.f; ds[j] = 0.f; dss[j] = 0.f; }
   }
   // one accumulator value: local board j (compile-time after unrolling), global board b, pixel p
   __device__ __forceinline__ void value(int j, int b, int p, float acc, T* __restrict__ out) {
     float v = acc;
-    if (e.scale) v = fmaf(v, sc, sh);
-    if (e.relu) v = fmaxf(v, 0.f);
-    if (e.gbias) v += e.gbias[(size_t)b * Cout + c];
+    if (on(kEpiAffine, e.scale != nullptr)) v = fmaf(v, sc, sh);
+    if (on(kEpiRelu, e.relu != 0)) v = fmaxf(v, 0.f);
+    if (on(kEpiGbias, e.gbias != nullptr)) v += e.gbias[(size_t)b * Cout + c];
     const size_t idx = ((size_t)b * 81 + p) * Cout + c;
     float msrc = 0.f;
-    if (e.mask_src) {
+    if (on(kEpiMask, e.mask_src != nullptr)) {
       pre[j] += v;
       msrc = kb_to_float<T>(((const T*)e.mask_src)[idx]);
       if (!(fmaf(msrc, ma, mb) > 0.f)) v = 0.f;
@@ -63,10 +78,10 @@ struct ConvEpiThread {
     out[idx] = stored;
     const float r = kb_to_float<T>(stored);
     s[j] += r;
-    ss[j] = fmaf(r, r, ss[j]);
-    mx[j] = fmaxf(mx[j], r);
-    dot[j] = fmaf(r, msrc, dot[j]);
-    if (e.pool) {
+    if (on(kEpiSumSq, e.ch_sumsq != nullptr)) ss[j] = fmaf(r, r, ss[j]);
+    if (on(kEpiDot, e.ch_dot != nullptr)) dot[j] = fmaf(r, msrc, dot[j]);
+    if (on(kEpiPool, e.pool != nullptr)) {
+      mx[j] = fmaxf(mx[j], r);
       if (p == 0) k0[j] = r;
       const float d = r - k0[j];
       ds[j] += d;
@@ -75,8 +90,9 @@ struct ConvEpiThread {
   }
   // after all pixels of local board j (global board b) have been fed
   __device__ __forceinline__ void board_done(int j, int b) {
-    if (e.board_sum) e.board_sum[(size_t)b * Cout + c] = e.board_scale * (e.mask_src ? pre[j] : s[j]);
-    if (e.pool) {
+    if (on(kEpiBoard, e.board_sum != nullptr))
+      e.board_sum[(size_t)b * Cout + c] = e.board_scale * (on(kEpiMask, e.mask_src != nullptr) ? pre[j] : s[j]);
+    if (on(kEpiPool, e.pool != nullptr)) {
       const float mean = s[j] * (1.f / 81.f);
       const float dm = ds[j] * (1.f / 81.f);
       const float var = fmaxf(dss[j] * (1.f / 81.f) - dm * dm, 0.f);
@@ -89,9 +105,9 @@ struct ConvEpiThread {
     float a = 0.f, q = 0.f, d = 0.f;
 #pragma unroll
     for (int j = 0; j < NB; ++j) if (j < nb_valid) { a += s[j]; q += ss[j]; d += dot[j]; }
-    if (e.ch_sum) atomicAdd(&e.ch_sum[c], (double)a);
-    if (e.ch_sumsq) atomicAdd(&e.ch_sumsq[c], (double)q);
-    if (e.ch_dot) atomicAdd(&e.ch_dot[c], (double)d);
+    if (on(kEpiSum, e.ch_sum != nullptr)) atomicAdd(&e.ch_sum[c], (double)a);
+    if (on(kEpiSumSq, e.ch_sumsq != nullptr)) atomicAdd(&e.ch_sumsq[c], (double)q);
+    if (on(kEpiDot, e.ch_dot != nullptr)) atomicAdd(&e.ch_dot[c], (double)d);
   }
 };
 #endif

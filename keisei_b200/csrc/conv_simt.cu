@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(CT) conv3x3_simt_kernel(const T* __restrict__ 
     }
   }
   if (c_ok) {
-    ConvEpiThread<T, 1> et(epi, c, Cout, B);
+    ConvEpiThread<T, 1, kEpiDynamic> et(epi, c, Cout, B);
 #pragma unroll
     for (int p = 0; p < 81; ++p) et.value(0, b, p, acc[p], out);
     et.board_done(0, b);

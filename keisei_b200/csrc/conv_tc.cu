@@ -1,10 +1,357 @@
-// conv_tc.cu — placeholder until the tcgen05 kernels land.
+// conv_tc.cu — 3x3 convolution on 9x9 boards as a tcgen05 / TMEM implicit GEMM fed by TMA (bf16).
+//
+//   D[cout, pixel] = sum_{tap, cin} W[cout, tap*Cin + cin] * X[board, y+dy-1, x+dx-1, cin]
+//
+// GEMM view per CTA tile:  M = 128 output channels (TMEM lanes), N = 256 pixel columns = 3 whole
+// boards (243 valid + 13 ignored), K = 9*Cin walked in 64-wide blocks (one tap x 64 input channels).
+//   * A (weights)      : 2-D TMA box [128 rows x 64 k] from the packed [Cout][9*Cin] matrix.
+//   * B (activations)  : 4-D TMA box [3 boards x 9 x 9 x 64 ch] from the NHWC tensor with the box
+//                        origin shifted by the tap (dx-1, dy-1): out-of-bounds rows/cols (the conv
+//                        padding) and boards past the batch are zero-filled by the TMA unit, so the
+//                        im2col never exists in memory and needs no halo in HBM.
+//   Both land in shared memory as K-major 128-byte rows with the 128B swizzle; one elected thread
+//   issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=256, K=16) four times per K block into a
+//   256-column fp32 accumulator in TMEM; the accumulator is double buffered (2 x 256 = all 512
+//   columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * Epilogue: 4 warps, thread = output channel (TMEM lane), columns = pixels, so BatchNorm
+//     statistics, SE squeeze, global-pool statistics, ReLU masks and bias are register-local
+//     (conv_epilogue.cuh). 16 tcgen05.ld.32x32b.x16 per tile.
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+// Persistent: grid = min(#SM, tiles); tile t -> (board group t / n_ct, channel tile t % n_ct) so
+// CTAs running together share the same boards in L2.
+//
+// Replaces F.conv2d at reference se_resnet.py:50,52,110 (forward) and its data gradient (same
+// kernel on the flipped/transposed weight pack). The weight gradient is conv3x3_wgrad below.
+#include <cuda.h>
 #include "kb_common.cuh"
+#include "conv_epilogue.cuh"
 #include "kb_kernels.h"
-int kbk_conv3x3_tc_supported(int, int, int) { return 0; }
-int kbk_conv3x3_tc(const void*, const void*, void*, int, int, int, const ConvEpi&, int, cudaStream_t) {
-  kb_set_error("tcgen05 conv not built"); return KB_ERR_UNSUPPORTED;
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kTileM = 128;                    // output channels per tile (TMEM lanes)
+constexpr int kTileN = 256;                    // pixel columns per tile
+constexpr int kBoards = 3;                     // whole boards per tile
+constexpr int kBlockK = 64;                    // bf16 elements per K block = one 128-byte swizzle row
+constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KB
+constexpr int kBBytes = kTileN * kBlockK * 2;  // 32 KB (31,104 written by TMA)
+constexpr int kBTxBytes = kBoards * 81 * kBlockK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kThreads = 192;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int kbk_conv3x3_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, cudaStream_t) {
-  kb_set_error("tcgen05 wgrad not built"); return KB_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> launch failure reported to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xfff) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("keisei_b200 conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t holder_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand, 128-byte rows, SWIZZLE_128B: 8-row groups 1024 bytes apart (SBO); LBO unused (=1).
+__device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: fp32 accumulate, bf16 A/B, both K-major, N (>>3) at bit 17, M (>>4) at bit 24
+constexpr uint32_t kIdescF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+// ---------------------------------------------------------------- forward / dgrad kernel
+template <int F>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                  bf16* __restrict__ out, int B, int Cin, int Cout, int num_tiles, ConvEpi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 + b); };
+  const uint32_t holder = bar_base + 8u * (2 * kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ct = Cout / kTileM;
+  const int kb_per_tap = Cin / kBlockK;
+  const int num_kb = 9 * kb_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_x);
+  }
+  if (warp == 1) {  // TMEM owner: all 512 columns (two 256-column accumulators)
+    tmem_alloc(holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *holder_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int ct = t % n_ct, grp = t / n_ct;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / kb_per_tap, cc = kb - tap * kb_per_tap;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), kABytes + kBTxBytes);
+          const uint32_t a_dst = smem_base + stage * kStageBytes;
+          tma_load_2d(a_dst, &map_w, full_bar(stage), kb * kBlockK, ct * kTileM);
+          tma_load_4d(a_dst + kABytes, &map_x, full_bar(stage), cc * kBlockK, tap % 3 - 1, tap / 3 - 1, grp * kBoards);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), tphase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kTileN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * kStageBytes;
+          const uint64_t adesc = smem_desc_k128(a_addr);
+          const uint64_t bdesc = smem_desc_k128(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdescF16, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(buf));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: thread = output channel =====
+    const int lane_grp = warp & 3;  // TMEM lanes 32*lane_grp .. +31 are the ones this warp may read
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int ct = t % n_ct, grp = t / n_ct;
+      const int buf = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      const int c = ct * kTileM + lane_grp * 32 + lane;
+      const int b0 = grp * kBoards;
+      const int nb_valid = min(kBoards, B - b0);
+      mbar_wait(tfull_bar(buf), tphase);
+      tc_fence_after();
+      ConvEpiThread<bf16, kBoards, F> et(epi, c, Cout, B);
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * kTileN);
+#pragma unroll
+      for (int ch = 0; ch < kTileN / 16; ++ch) {
+        if (ch * 16 < kBoards * 81) {
+          uint32_t r[16];
+          tmem_ld16(taddr + ch * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = ch * 16 + i;
+            if (col < kBoards * 81) {
+              const int j = col / 81, p = col % 81;
+              if (j < nb_valid) {
+                et.value(j, b0 + j, p, __uint_as_float(r[i]), out);
+                if (p == 80) et.board_done(j, b0 + j);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      et.finish(nb_valid);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;  // resolved once; benign race (same value)
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || p == nullptr) return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+int make_weight_map(CUtensorMap* m, const void* w, int rows, int K) {
+  EncodeTiledFn enc = get_encode_fn();
+  KB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KB_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return KB_OK;
+}
+
+int make_act_map(CUtensorMap* m, const void* x, int B, int C, int boards_per_box) {
+  EncodeTiledFn enc = get_encode_fn();
+  KB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)C, 9, 9, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * 9, (cuuint64_t)C * 2 * 81};
+  const cuuint32_t box[4] = {(cuuint32_t)kBlockK, 9, 9, (cuuint32_t)boards_per_box};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KB_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+  return KB_OK;
+}
+
+template <int F>
+int launch_fwd(const CUtensorMap& mw, const CUtensorMap& mx, bf16* out, int B, int Cin, int Cout, int num_tiles,
+               const ConvEpi& epi, int grid, cudaStream_t st) {
+  static bool attr_set = false;  // per instantiation; idempotent
+  if (!attr_set) {
+    KB_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  conv3x3_tc_kernel<F><<<grid, kThreads, kSmemBytes, st>>>(mw, mx, out, B, Cin, Cout, num_tiles, epi);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+}  // namespace
+
+int kbk_conv3x3_tc_supported(int Cin, int Cout, int dtype) {
+  return dtype == KB_BF16 && Cin % kBlockK == 0 && Cout % kTileM == 0 && Cin >= kBlockK;
+}
+
+int kbk_conv3x3_tc(const void* in, const void* w, void* out, int B, int Cin, int Cout, const ConvEpi& epi, int num_sms,
+                   cudaStream_t st) {
+  KB_CHECK_ARG(kbk_conv3x3_tc_supported(Cin, Cout, KB_BF16), "conv3x3_tc: unsupported shape Cin=%d Cout=%d", Cin, Cout);
+  if (B == 0) return KB_OK;
+  CUtensorMap mw, mx;
+  if (int r = make_weight_map(&mw, w, Cout, 9 * Cin)) return r;
+  if (int r = make_act_map(&mx, in, B, Cin, kBoards)) return r;
+  const int groups = kb_ceil_div(B, kBoards);
+  const int num_tiles = groups * (Cout / kTileM);
+  if (num_sms <= 0) num_sms = 148;
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  bf16* o = (bf16*)out;
+  const int f = conv_epi_features(epi);
+  switch (f) {
+    case 0: return launch_fwd<0>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
+    case kEpiSum | kEpiSumSq: return launch_fwd<kEpiSum | kEpiSumSq>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
+    case kEpiSum | kEpiSumSq | kEpiBoard: return launch_fwd<kEpiSum | kEpiSumSq | kEpiBoard>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
+    case kEpiAffine | kEpiRelu | kEpiGbias: return launch_fwd<kEpiAffine | kEpiRelu | kEpiGbias>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
+    case kEpiAffine | kEpiRelu | kEpiPool: return launch_fwd<kEpiAffine | kEpiRelu | kEpiPool>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
+    case kEpiAffine | kEpiBoard: return launch_fwd<kEpiAffine | kEpiBoard>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
+    case kEpiMask | kEpiSum | kEpiDot | kEpiBoard: return launch_fwd<kEpiMask | kEpiSum | kEpiDot | kEpiBoard>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
+    default: return launch_fwd<kEpiDynamic>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
+  }
+}
+
+int kbk_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true, int num_sms,
+                         cudaStream_t st) {
+  (void)num_sms;
+  // TODO(round 1): tcgen05 weight-gradient kernel (MN-major operands); SIMT fallback keeps the path correct.
+  return kbk_conv3x3_wgrad_simt(x, dy, dw, B, Cin, Cout, Cin_true, KB_BF16, st);
 }

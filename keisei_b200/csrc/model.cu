@@ -152,12 +152,12 @@ void carve(const Dims& m, void* base, int training, Ws& w, BlockWs* blk_storage)
 
 int conv3x3(const Dims& m, const void* in, const void* wgt, void* out, int Cin, int Cout, const ConvEpi& e, int use_tc,
             int num_sms, cudaStream_t st) {
-  if (use_tc && kbk_conv3x3_tc_supported(Cin, Cout, m.dtype)) return kbk_conv3x3_tc(in, wgt, out, m.B, Cin, Cout, e, num_sms, st);
+  if (use_tc && m.B >= 3 && kbk_conv3x3_tc_supported(Cin, Cout, m.dtype)) return kbk_conv3x3_tc(in, wgt, out, m.B, Cin, Cout, e, num_sms, st);
   return kbk_conv3x3_simt(in, wgt, out, m.B, Cin, Cout, m.dtype, e, st);
 }
 int wgrad3x3(const Dims& m, const void* x, const void* dy, float* dw, int Cin, int Cout, int Cin_true, int use_tc,
              int num_sms, cudaStream_t st) {
-  if (use_tc && kbk_conv3x3_tc_supported(Cin, Cout, m.dtype)) return kbk_conv3x3_wgrad_tc(x, dy, dw, m.B, Cin, Cout, Cin_true, num_sms, st);
+  if (use_tc && m.B >= 3 && kbk_conv3x3_tc_supported(Cin, Cout, m.dtype)) return kbk_conv3x3_wgrad_tc(x, dy, dw, m.B, Cin, Cout, Cin_true, num_sms, st);
   return kbk_conv3x3_wgrad_simt(x, dy, dw, m.B, Cin, Cout, Cin_true, m.dtype, st);
 }
 
