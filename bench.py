@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline benchmark (see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], config 5 shape per rank when N > 1): SE-ResNet 40x256 rollout
+inference, bf16, 4096 synthetic boards per GPU. One "step" = one `select_actions`-equivalent pass:
+network forward (eval BatchNorm) + legal-mask softmax + sample + log-prob + scalar value.
+`value` = positions/s with inputs resident in HBM (device-timed, max over ranks); `e2e` = the same
+through `KataGoPPOAlgorithm.select_actions` with HOST buffers (pinned H2D of obs + mask and D2H of
+actions/log-probs/values inside the timed region). Rollout shards across ranks with no collective
+(weak scaling). The line also carries `update` (BASELINE.json configs[2]: KataGo-PPO update,
+8192 samples split over the ranks, fwd+loss+bwd+all-reduce+clip+Adam) as extra keys, the dominant
+kernel's `roofline`, and the `cpu_baseline` (oracle port on the host cores, bounded sample).
+
+`--impl reference` times the reference's CPU path (the oracle restatement — the reference itself is
+Python/PyTorch and /root/reference does not exist on the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+MODEL_CFG = dict(num_blocks=40, channels=256)           # reference SEResNetParams defaults (se_resnet.py:15-24)
+ROLLOUT_B = 4096                                        # BASELINE.json configs[1]
+UPDATE_GLOBAL_B = 8192                                  # BASELINE.json configs[2]
+A = 11259
+CONV_FLOP_PER_POS = 2 * 81 * 256 * 2304                 # one 256->256 3x3 conv, SURVEY.md 8(d): 95.55 MFLOP
+FWD_FLOP_PER_POS = 18.66e6 + 80 * 95.55e6               # trunk convs only: 7.663 GFLOP
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_tflops": d.get("bf16_tflops", 1590.0), "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0),
+                "hbm_gbs": d.get("hbm_gbs", 6650.0), "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons via NVML during the timed region."""
+
+    def __init__(self, index: int) -> None:
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self) -> dict:
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def synth_boards(B: int, seed: int, device):
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randn(B, 50, 9, 9, generator=g)
+    mask = torch.zeros(B, A, dtype=torch.bool)
+    idx = torch.randint(0, A, (B, 80), generator=g)      # ~80 legal moves per position (realistic)
+    mask.scatter_(1, idx, True)
+    return obs.to(device), mask.to(device)
+
+
+def dist_setup(n: int):
+    import torch.distributed as dist
+    if n > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        return dist.get_rank(), dist.get_world_size(), local
+    return 0, 1, 0
+
+
+def timed(fn, steps: int, warmup: int, device, world: int) -> float:
+    """ms per step: CUDA events on the current stream, barrier + synchronize on both sides, max over ranks."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def cpu_baseline(batch: int = 32, reps: int = 2) -> dict:
+    """Oracle port (fp32 CPU PyTorch restatement of the reference) on the host cores: rollout step
+    (eval forward + mask/softmax/Categorical sample + log-prob + scalar value) on a bounded sample."""
+    from oracle import keisei_oracle as O
+    from keisei_b200.models import SEResNetModel, SEResNetParams
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = SEResNetModel(SEResNetParams(**MODEL_CFG)).state_dict()
+    g = torch.Generator().manual_seed(1)
+    obs = torch.randn(batch, 50, 9, 9, generator=g)
+    mask = torch.zeros(batch, A, dtype=torch.bool)
+    mask.scatter_(1, torch.randint(0, A, (batch, 80), generator=g), True)
+
+    def step():
+        with torch.no_grad():
+            p, v, s = O.seresnet_forward(sd, obs, MODEL_CFG["num_blocks"], training=False)
+            flat = p.reshape(batch, -1)
+            probs = torch.softmax(flat.masked_fill(~mask, float("-inf")), -1)
+            a = torch.distributions.Categorical(probs, validate_args=False).sample()
+            O.rollout_log_prob(flat, mask, a)
+            O.scalar_value(v)
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": batch / dt, "unit": "positions/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle fp32 CPU forward+sample, SE-ResNet 40x256, batch {batch}, {reps} reps after 1 warm-up"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 32
+    t0 = time.perf_counter()
+    cb = cpu_baseline(batch=batch, reps=max(1, min(args.steps, 3)))
+    line = {"metric": "rollout positions/s", "value": cb["value"], "unit": "positions/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * ROLLOUT_B / cb["value"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "SE-ResNet 40x256 rollout inference (select_actions), batch 4096 synthetic boards per GPU",
+                       "timed_sample": f"batch {batch} on host cores, scaled per position"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def conv_roofline(device, reps: int = 20) -> dict:
+    """Dominant kernel: conv3x3_tc_kernel (256->256, B=4096, folded-BN+ReLU+gpool-bias epilogue),
+    timed back to back with CUDA events on the launching stream."""
+    from keisei_b200 import model_ops
+    pk = peaks()
+    B, C = ROLLOUT_B, 256
+    torch.manual_seed(0)
+    xs = [torch.randn(B, 81, C, device=device).bfloat16() for _ in range(2)]  # 2 x 170 MB > 126 MB L2
+    wf = model_ops.pack_conv_weight(torch.randn(C, C, 3, 3, device=device) / 48, torch.bfloat16)
+    sc, sh = torch.ones(C, device=device), torch.zeros(C, device=device)
+    gb = torch.zeros(B, C, device=device)
+    for i in range(3):
+        model_ops.conv3x3(xs[i & 1], wf, backend=1, scale=sc, shift=sh, relu=True, gbias=gb)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        model_ops.conv3x3(xs[i & 1], wf, backend=1, scale=sc, shift=sh, relu=True, gbias=gb)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / reps
+    flops = CONV_FLOP_PER_POS * B
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = pk["bf16_tflops_sustained"]
+    return {"kernel": "conv3x3_tc_kernel (tcgen05, 256->256, B=4096, 3 boards x 128 ch tiles)", "bound": "tensor",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "ms_per_launch": ms, "flops_per_launch": flops, "peak_source": f"{pk['source']} bf16_tflops_sustained"}
+
+
+def run_ours(args) -> None:
+    from keisei_b200 import _lib
+    from keisei_b200.katago_ppo import KataGoPPOAlgorithm, KataGoPPOParams
+    from keisei_b200.models import SEResNetModel, SEResNetParams
+
+    rank, world, local = dist_setup(args.gpus)
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    torch.manual_seed(0)
+    model = SEResNetModel(SEResNetParams(**MODEL_CFG)).to(device)
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(use_amp=True, batch_size=UPDATE_GLOBAL_B // world), model)
+    obs, mask = synth_boards(ROLLOUT_B, 100 + rank, device)
+    # non-trivial running statistics: a few train-mode batches
+    model.train()
+    with torch.no_grad():
+        for i in range(2):
+            model(obs[i * 256:(i + 1) * 256])
+    B = ROLLOUT_B
+
+    def step_device():
+        algo.select_actions(obs, mask)
+
+    h_obs, h_mask = obs.cpu().pin_memory(), mask.cpu().pin_memory()
+    h_out = [torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(B).pin_memory(), torch.empty(B).pin_memory()]
+
+    def step_e2e():
+        d_obs = h_obs.to(device, non_blocking=True)
+        d_mask = h_mask.to(device, non_blocking=True)
+        a, lp, v = algo.select_actions(d_obs, d_mask)
+        h_out[0].copy_(a, non_blocking=True); h_out[1].copy_(lp, non_blocking=True); h_out[2].copy_(v, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+
+    with ClockSampler(local) as clk:
+        n0 = _lib.launch_count()
+        ms = timed(step_device, args.steps, args.warmup, device, world)
+        launches = (_lib.launch_count() - n0) * args.steps // (args.steps + args.warmup)
+    ms_e2e = timed(step_e2e, args.steps, args.warmup, device, world)
+    value = world * B / (ms * 1e-3)
+    e2e = world * B / (ms_e2e * 1e-3)
+
+    line = {"metric": "rollout positions/s", "value": value, "unit": "positions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "impl": "ours",
+            "config": {"workload": "SE-ResNet 40x256 rollout inference (select_actions), batch 4096 synthetic boards per GPU",
+                       "parallelism": f"shard{world}-no-comm", "cache": "inputs larger than L2 (170 MB activations per layer)"},
+            "e2e": {"value": e2e, "unit": "positions/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h_obs.numel() * 4 + h_mask.numel(), "d2h_bytes_per_step": B * 16},
+            "gpu_launches": int(launches), "clocks": clk.summary(),
+            "model_frac_of_tensor_roofline": (FWD_FLOP_PER_POS * B / (ms * 1e-3) / 1e12) / peaks()["bf16_tflops_sustained"]}
+
+    if not args.no_update:
+        line["update"] = bench_update(args, algo, model, device, rank, world)
+    if rank == 0:
+        line["roofline"] = conv_roofline(device)
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_update(args, algo, model, device, rank, world) -> dict:
+    """KataGo-PPO update step (BASELINE.json configs[2]): 8192 samples / world per rank; one step =
+    forward (batch-stat BN) + fused losses + backward + gradient all-reduce + unscale/clip/Adam."""
+    from keisei_b200.distributed import GradSync
+    Bu = UPDATE_GLOBAL_B // world
+    g = torch.Generator().manual_seed(7 + rank)
+    obs = torch.randn(Bu, 50, 9, 9, generator=g).to(device)
+    mask = torch.zeros(Bu, A, dtype=torch.bool)
+    actions = torch.randint(0, A, (Bu,), generator=g)
+    mask.scatter_(1, torch.randint(0, A, (Bu, 80), generator=g), True)
+    mask[torch.arange(Bu), actions] = True
+    mb = (mask.to(device), actions.to(device), (-3 * torch.rand(Bu, generator=g)).to(device), torch.randn(Bu, generator=g).to(device),
+          torch.randint(-1, 3, (Bu,), generator=g).to(device), torch.randn(Bu, generator=g).clamp(-1.5, 1.5).to(device))
+    if world > 1:
+        algo.grad_sync = GradSync()
+        algo.grad_sync.broadcast_parameters(model)
+    model.train()
+    km = algo._kernel_model(device)
+
+    def step():
+        algo._step_fused(km, obs, mb, None)
+        algo.scaler.unscale_(algo.optimizer)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), algo.params.grad_clip)
+        algo.scaler.step(algo.optimizer)
+        algo.scaler.update()
+
+    steps, warm = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
+    ms = timed(step, steps, warm, device, world)
+    # GAE over the reference-shaped buffer T=128 x N=64 (+ normalisation)
+    from keisei_b200 import gae as G
+    T, N = 128, 64
+    r, v = torch.randn(T, N, device=device), 0.3 * torch.randn(T, N, device=device)
+    term = torch.rand(T, N, device=device) < 0.02
+    nv = torch.randn(N, device=device)
+    def gae_step():
+        adv = G.compute_gae_gpu(r, v, term, nv, 0.99, 0.95).reshape(-1)
+        G.normalize_advantages_(adv)
+    gae_ms = timed(gae_step, 20, 3, device, world)
+    sps = UPDATE_GLOBAL_B / (ms * 1e-3)
+    return {"metric": "PPO update samples/s", "value": sps, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "warmup": warm,
+            "global_batch": UPDATE_GLOBAL_B, "per_gpu_batch": Bu, "scaling": "strong", "gae_T128_N64_ms": gae_ms,
+            "frac_of_tensor_roofline": (22.97e9 * UPDATE_GLOBAL_B / world / (ms * 1e-3) / 1e12) / peaks()["bf16_tflops_sustained"],
+            "includes": "fwd+losses+bwd+allreduce+unscale+clip+Adam"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-update", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback on the product path)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

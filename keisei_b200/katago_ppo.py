@@ -1,0 +1,586 @@
+"""KataGo-style multi-head PPO — drop-in for keisei/training/katago_ppo.py (reference lines cited
+per symbol). Same constructor, methods, attributes, metrics keys and exception types as the
+reference trainer; the device work on CUDA goes through the sm_100a kernels:
+
+  select_actions  -> one C call for the network + `kb_policy_sample` (mask/softmax/sample/log-prob/value)
+  update          -> `kb_gae_scan` + `kb_advantage_normalize`, then per minibatch
+                     `kb_seresnet_forward` / fused PPO losses / `kb_seresnet_backward`, with the
+                     gradients produced as ONE flat fp32 buffer (a single NCCL all-reduce in data-parallel
+                     runs, see keisei_b200/distributed.py). Optimiser, GradScaler and clipping stay PyTorch.
+
+Neither Triton nor torch.compile runs on this path: `compile_mode` is accepted for config
+compatibility and ignored (a warning is logged).
+"""
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass
+from typing import Any, Callable
+
+import torch
+import torch.nn.functional as F
+from torch.amp import GradScaler, autocast
+
+from . import gae as gae_mod
+from . import model_ops, policy_ops
+from .models.katago_base import KataGoBaseModel
+from .models.se_resnet import SEResNetModel
+
+SCORE_NORMALIZATION = 76.0  # reference keisei/sl/dataset.py:32
+
+_log = logging.getLogger(__name__)
+
+
+def _amp_dtype_and_device(use_amp: bool, device: torch.device) -> tuple[torch.dtype, str]:
+    """Reference katago_ppo.py:19-30."""
+    if not use_amp:
+        dtype = torch.float16
+    elif device.type == "cpu":
+        dtype = torch.bfloat16
+    elif torch.cuda.is_bf16_supported():
+        dtype = torch.bfloat16
+    else:
+        dtype = torch.float16
+    return dtype, device.type
+
+
+def ppo_clip_loss(new_log_probs, old_log_probs, advantages, clip_epsilon: float) -> torch.Tensor:
+    """Clipped surrogate (reference katago_ppo.py:33-43). Host-side form; the CUDA update path fuses
+    this into `keisei_b200::ppo_policy_loss`."""
+    ratio = (new_log_probs - old_log_probs).exp()
+    clipped = ratio.clamp(1 - clip_epsilon, 1 + clip_epsilon)
+    return -torch.min(ratio * advantages, clipped * advantages).mean()
+
+
+def wdl_cross_entropy_loss(value_logits: torch.Tensor, value_cats: torch.Tensor) -> torch.Tensor:
+    """W/D/L cross-entropy, ignore_index=-1, graph-connected zero when nothing is valid
+    (reference katago_ppo.py:46-57)."""
+    if not (value_cats >= 0).any():
+        return value_logits.sum() * 0.0
+    return F.cross_entropy(value_logits, value_cats, ignore_index=-1)
+
+
+def compute_value_metrics(value_logits: torch.Tensor, value_targets: torch.Tensor) -> dict[str, float]:
+    """Reference katago_ppo.py:60-78."""
+    pred = value_logits.argmax(dim=-1)
+    return {
+        "value_accuracy": (pred == value_targets).float().mean().item(),
+        "frac_predicted_win": (pred == 0).float().mean().item(),
+        "frac_predicted_draw": (pred == 1).float().mean().item(),
+        "frac_predicted_loss": (pred == 2).float().mean().item(),
+    }
+
+
+@dataclass(frozen=True)
+class KataGoPPOParams:
+    """Reference katago_ppo.py:81-116 (same fields, defaults and validation)."""
+    learning_rate: float = 2e-4
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_epsilon: float = 0.2
+    epochs_per_batch: int = 4
+    batch_size: int = 256
+    lambda_policy: float = 1.0
+    lambda_value: float = 1.5
+    lambda_score: float = 0.02
+    lambda_entropy: float = 0.01
+    score_normalization: float = SCORE_NORMALIZATION
+    grad_clip: float = 1.0
+    use_amp: bool = False
+    compile_mode: str | None = None
+    compile_dynamic: bool = True
+    entropy_decay_epochs: int = 0
+    score_blend_alpha: float = 0.0
+    use_terminated_for_gae: bool = True
+
+    def __post_init__(self) -> None:
+        if self.batch_size <= 0:
+            raise ValueError(f"batch_size must be > 0, got {self.batch_size}")
+        if self.epochs_per_batch <= 0:
+            raise ValueError(f"epochs_per_batch must be > 0, got {self.epochs_per_batch}")
+        if not 0.0 <= self.gamma <= 1.0:
+            raise ValueError(f"gamma must be in [0, 1], got {self.gamma}")
+        if not 0.0 <= self.gae_lambda <= 1.0:
+            raise ValueError(f"gae_lambda must be in [0, 1], got {self.gae_lambda}")
+        if self.clip_epsilon < 0.0:
+            raise ValueError(f"clip_epsilon must be >= 0, got {self.clip_epsilon}")
+        if self.learning_rate <= 0.0:
+            raise ValueError(f"learning_rate must be > 0, got {self.learning_rate}")
+        if self.grad_clip <= 0.0:
+            raise ValueError(f"grad_clip must be > 0, got {self.grad_clip}")
+
+
+class KataGoRolloutBuffer:
+    """Host-resident rollout storage with the reference's interface and guards
+    (katago_ppo.py:128-388): `add`, `flatten`, `clear`, `size`, `fill_alternating_perspective_overrides`."""
+
+    _FIELDS = ("observations", "actions", "log_probs", "values", "rewards", "dones", "terminated", "legal_masks",
+               "value_categories", "score_targets")
+
+    def __init__(self, num_envs: int, obs_shape: tuple[int, ...], action_space: int) -> None:
+        self.num_envs = num_envs
+        self.obs_shape = obs_shape
+        self.action_space = action_space
+        self._alloc_samples = 0
+        self._write_offset = 0
+        self._step_count = 0
+        self._storage: dict[str, torch.Tensor] = {}
+        self._has_env_ids = False
+        self._has_next_value_override = False
+
+    def _new_storage(self, cap: int) -> dict[str, torch.Tensor]:
+        st = {
+            "observations": torch.empty(cap, *self.obs_shape),
+            "actions": torch.empty(cap, dtype=torch.long),
+            "log_probs": torch.empty(cap),
+            "values": torch.empty(cap),
+            "rewards": torch.empty(cap),
+            "dones": torch.empty(cap, dtype=torch.bool),
+            "terminated": torch.empty(cap, dtype=torch.bool),
+            "legal_masks": torch.empty(cap, self.action_space, dtype=torch.bool),
+            "value_categories": torch.empty(cap, dtype=torch.long),
+            "score_targets": torch.empty(cap),
+        }
+        if self._has_env_ids:
+            st["env_ids"] = torch.empty(cap, dtype=torch.long)
+        if self._has_next_value_override:
+            st["next_value_override"] = torch.full((cap,), float("nan"))
+        return st
+
+    def _ensure_capacity(self, n_samples: int) -> None:
+        needed = self._write_offset + n_samples
+        if needed <= self._alloc_samples:
+            return
+        cap = max(needed * 2, 512 * self.num_envs)
+        fresh = self._new_storage(cap)
+        off = self._write_offset
+        if off > 0:
+            for key, t in fresh.items():
+                if key in self._storage:
+                    t[:off] = self._storage[key][:off]
+        self._storage = fresh
+        self._alloc_samples = cap
+
+    @property
+    def size(self) -> int:
+        return self._step_count
+
+    def clear(self) -> None:
+        self._write_offset = 0
+        self._step_count = 0
+
+    def add(self, obs, actions, log_probs, values, rewards, dones, terminated, legal_masks, value_categories,
+            score_targets, env_ids=None, next_value_override=None) -> None:
+        host = lambda t: t.detach().cpu()  # noqa: E731
+        obs_c, act_c, lp_c, val_c, rew_c = host(obs), host(actions), host(log_probs), host(values), host(rewards)
+        done_c, term_c = host(dones), host(terminated)
+        if (term_c.bool() & ~done_c.bool()).any():
+            raise AssertionError(
+                "terminated must be a subset of dones: every terminated position must also be done. "
+                "Got terminated=True where dones=False — likely a call site passing the merged signal.")
+        mask_c, cats_c, score_c = host(legal_masks), host(value_categories), host(score_targets)
+        invalid = set(cats_c.unique().tolist()) - {-1, 0, 1, 2}
+        if invalid:
+            raise ValueError(f"value_categories contains invalid values {invalid}. "
+                             f"Expected only {{-1=ignore, 0=W, 1=D, 2=L}}.")
+        if score_c.isnan().any():
+            raise ValueError("score_targets contains NaN. With per-step material balance, "
+                             "all targets should be real-valued.")
+        abs_max = score_c.abs().max()
+        if abs_max > 3.5:
+            raise ValueError(f"score_targets appear unnormalized: max abs value = {abs_max.item():.1f}. "
+                             f"Expected in [-1.7, +1.7] typical, theoretical max 2.58 (guard 3.5).")
+        n = obs_c.shape[0]
+        if self._step_count == 0 and env_ids is not None:
+            self._has_env_ids = True
+        if self._step_count == 0 and next_value_override is not None:
+            self._has_next_value_override = True
+        self._ensure_capacity(n)
+        sl = slice(self._write_offset, self._write_offset + n)
+        st = self._storage
+        for key, val in zip(self._FIELDS, (obs_c, act_c, lp_c, val_c, rew_c, done_c, term_c, mask_c, cats_c, score_c)):
+            st[key][sl] = val
+        if env_ids is not None:
+            if "env_ids" not in st:
+                st["env_ids"] = torch.empty(self._alloc_samples, dtype=torch.long)
+            st["env_ids"][sl] = host(env_ids)
+        if next_value_override is not None:
+            if "next_value_override" not in st:
+                st["next_value_override"] = torch.full((self._alloc_samples,), float("nan"))
+                self._has_next_value_override = True
+            st["next_value_override"][sl] = host(next_value_override).to(torch.float32)
+        elif self._has_next_value_override and "next_value_override" in st:
+            st["next_value_override"][sl] = float("nan")  # no stale cells from a previous epoch
+        self._write_offset += n
+        self._step_count += 1
+
+    def fill_alternating_perspective_overrides(self) -> None:
+        """Reference katago_ppo.py:320-362: for non-terminal cells without a caller override,
+        next_value_override[t] = -values[t+1] (the next ply is the opponent's frame)."""
+        if self._has_env_ids:
+            return
+        T, N = self._step_count, self.num_envs
+        if T <= 1 or self._write_offset != T * N:
+            return
+        if "next_value_override" not in self._storage:
+            self._storage["next_value_override"] = torch.full((self._alloc_samples,), float("nan"))
+            self._has_next_value_override = True
+        ov = self._storage["next_value_override"][:T * N].view(T, N)
+        values = self._storage["values"][:T * N].view(T, N)
+        term = self._storage["terminated"][:T * N].view(T, N).bool()
+        target = torch.isnan(ov[:-1]) & ~term[:-1]
+        ov[:-1][target] = -values[1:][target]
+
+    def flatten(self) -> dict[str, torch.Tensor]:
+        if self._step_count == 0:
+            raise ValueError("Cannot flatten an empty buffer. Call add() at least once before flatten().")
+        off = self._write_offset
+        st = self._storage
+        out = {
+            "observations": st["observations"][:off].reshape(-1, *self.obs_shape),
+            "legal_masks": st["legal_masks"][:off].reshape(-1, self.action_space),
+        }
+        for key in ("actions", "log_probs", "values", "rewards", "dones", "terminated", "value_categories", "score_targets"):
+            out[key] = st[key][:off].reshape(-1)
+        if self._has_env_ids and "env_ids" in st:
+            out["env_ids"] = st["env_ids"][:off].reshape(-1)
+        if self._has_next_value_override and "next_value_override" in st:
+            out["next_value_override"] = st["next_value_override"][:off].reshape(-1)
+        return out
+
+
+class KataGoPPOAlgorithm:
+    """Reference katago_ppo.py:391-991."""
+
+    def __init__(self, params: KataGoPPOParams, model: KataGoBaseModel, forward_model: torch.nn.Module | None = None,
+                 warmup_epochs: int = 0, warmup_entropy: float = 0.05) -> None:
+        self.params = params
+        self.model = model
+        self.forward_model = forward_model or model
+        fm_base = self.forward_model.module if hasattr(self.forward_model, "module") else self.forward_model
+        m_base = self.model.module if hasattr(self.model, "module") else self.model
+        assert fm_base is m_base, (
+            "forward_model and model must share parameters — compile + grad clipping requires this")
+        self.compiled_train: Callable[..., Any] | None = None
+        self.compiled_eval: Callable[..., Any] | None = None
+        if params.compile_mode is not None:
+            _log.warning("compile_mode=%r ignored: the keisei_b200 hot path runs hand-written sm_100a kernels, "
+                         "not torch.compile", params.compile_mode)
+        self._timing_events: dict[str, list] = {"select_actions_forward_ms": [], "update_forward_backward_ms": [], "gae_ms": []}
+        self.timings: dict[str, list[float]] = {"select_actions_forward_ms": [], "update_forward_backward_ms": [], "gae_ms": []}
+        device = next(model.parameters()).device
+        if hasattr(model, "configure_amp"):
+            amp_dtype, amp_dev = _amp_dtype_and_device(params.use_amp, device)
+            model.configure_amp(enabled=params.use_amp, dtype=amp_dtype, device_type=amp_dev)
+        self.optimizer = torch.optim.Adam(model.parameters(), lr=params.learning_rate)
+        self.scaler = GradScaler(enabled=params.use_amp and device.type == "cuda")
+        self.warmup_epochs = warmup_epochs
+        self.warmup_entropy = warmup_entropy
+        self.current_entropy_coeff = params.lambda_entropy
+        # keisei_b200 extensions (not in the reference): data-parallel gradient sync and guard strictness
+        self.grad_sync = None          # keisei_b200.distributed.GradSync or None
+        self.strict_guards = True      # check NaN / zero-legal flags every minibatch (1 host sync, reference: 2)
+        self._sample_seed: int | None = None
+
+    # ---- small helpers ---------------------------------------------------------------------------
+    def get_entropy_coeff(self, epoch: int) -> float:
+        """Reference katago_ppo.py:500-516."""
+        if epoch < self.warmup_epochs:
+            return self.warmup_entropy
+        decay = self.params.entropy_decay_epochs
+        elapsed = epoch - self.warmup_epochs
+        if decay <= 0 or elapsed >= decay:
+            return self.params.lambda_entropy
+        return self.warmup_entropy + (elapsed / decay) * (self.params.lambda_entropy - self.warmup_entropy)
+
+    def flush_timings(self) -> None:
+        """Reference katago_ppo.py:518-531: the only synchronisation point of the event timers."""
+        for key, pairs in self._timing_events.items():
+            self.timings[key] = [s.elapsed_time(e) for s, e in pairs]
+            pairs.clear()
+
+    @staticmethod
+    def scalar_value(value_logits: torch.Tensor) -> torch.Tensor:
+        """P(W) - P(L) (reference katago_ppo.py:533-541)."""
+        p = F.softmax(value_logits, dim=-1)
+        return p[:, 0] - p[:, 2]
+
+    def _base(self) -> torch.nn.Module:
+        return self.model.module if hasattr(self.model, "module") else self.model
+
+    def _kernel_model(self, device: torch.device) -> SEResNetModel | None:
+        """The fused C-ABI path applies when the (unwrapped) model is the keisei_b200 SE-ResNet on CUDA."""
+        base = self._base()
+        if device.type == "cuda" and isinstance(base, SEResNetModel) and base.kernel_supported():
+            return base
+        return None
+
+    def _events(self, device, key):
+        if device.type != "cuda":
+            return None
+        stream = torch.cuda.current_stream(device)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        return key, s, e, stream
+
+    def _events_end(self, tok) -> None:
+        if tok is not None:
+            key, s, e, stream = tok
+            e.record(stream)
+            self._timing_events[key].append((s, e))
+
+    # ---- rollout ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def select_actions(self, obs: torch.Tensor, legal_masks: torch.Tensor, value_adapter: Any | None = None):
+        """Reference katago_ppo.py:543-617: eval-mode forward, zero-legal guard (RuntimeError), masked
+        sample + log-prob, scalar value (blended through the adapter when given). Leaves
+        `forward_model` in train mode."""
+        device = next(self.model.parameters()).device
+        model = self.forward_model
+        model.eval()
+        try:
+            tok = self._events(device, "select_actions_forward_ms")
+            output = model(obs)
+            self._events_end(tok)
+            B = obs.shape[0]
+            if device.type == "cuda":
+                flat = output.policy_logits.reshape(B, -1)
+                alpha = float(getattr(value_adapter, "score_blend_alpha", 0.0)) if value_adapter is not None else 0.0
+                fused_value = value_adapter is None or hasattr(value_adapter, "score_blend_alpha")
+                actions, log_probs, values, legal, flags = policy_ops.policy_sample(
+                    flat, legal_masks, output.value_logits if fused_value else None, output.score_lead, alpha,
+                    seed=self._sample_seed)
+                if int(flags[0].item()) != 0:
+                    zero_envs = (legal == 0).nonzero(as_tuple=True)[0].tolist()
+                    raise RuntimeError(f"Environments {zero_envs} have zero legal actions — "
+                                       f"all-False legal mask would produce NaN")
+                if not fused_value:
+                    values = value_adapter.scalar_value_blended(output.value_logits, output.score_lead)
+                return actions, log_probs, values
+            legal_counts = legal_masks.sum(dim=-1)
+            if (legal_counts == 0).any():
+                zero_envs = (legal_counts == 0).nonzero(as_tuple=True)[0].tolist()
+                raise RuntimeError(f"Environments {zero_envs} have zero legal actions — "
+                                   f"all-False legal mask would produce NaN")
+            masked = output.policy_logits.reshape(B, -1).masked_fill(~legal_masks, float("-inf"))
+            dist = torch.distributions.Categorical(F.softmax(masked, dim=-1), validate_args=False)
+            actions = dist.sample()
+            log_probs = dist.log_prob(actions)
+            if value_adapter is not None:
+                values = value_adapter.scalar_value_blended(output.value_logits, output.score_lead)
+            else:
+                values = self.scalar_value(output.value_logits)
+            return actions, log_probs, values
+        finally:
+            self.forward_model.train()
+
+    # ---- advantages ------------------------------------------------------------------------------
+    def _advantages(self, data, T: int, N: int, next_values: torch.Tensor, device: torch.device) -> torch.Tensor:
+        """GAE over the buffer on `device` (reference katago_ppo.py:649-773): (T,N) grid, per-env padded
+        (env_ids) or flat fallback; fp32 forced; returns a flat fp32 tensor on `device`, un-normalised."""
+        p = self.params
+        key = "terminated" if p.use_terminated_for_gae else "dones"
+        total = data["rewards"].numel()
+        nv = next_values.detach().float()
+        if total == T * N:
+            ov = data.get("next_value_override")
+            tok = self._events(device, "gae_ms")
+            adv = gae_mod.compute_gae_gpu(
+                data["rewards"].reshape(T, N).float().to(device), data["values"].reshape(T, N).float().to(device),
+                data[key].reshape(T, N).to(device), nv.to(device), gamma=p.gamma, lam=p.gae_lambda,
+                next_value_override=None if ov is None else ov.reshape(T, N).float().to(device)) \
+                if device.type == "cuda" else gae_mod.compute_gae(
+                    data["rewards"].reshape(T, N).float(), data["values"].reshape(T, N).float(), data[key].reshape(T, N),
+                    nv.cpu(), gamma=p.gamma, lam=p.gae_lambda,
+                    next_value_override=None if ov is None else ov.reshape(T, N).float())
+            self._events_end(tok)
+            return adv.reshape(-1)
+        nv_cpu = nv.cpu()
+        if "env_ids" in data:
+            env_ids = data["env_ids"]
+            order = torch.argsort(env_ids, stable=True)
+            uniq, counts = env_ids[order].unique_consecutive(return_counts=True)
+            if uniq.max() >= nv_cpu.shape[0]:
+                raise IndexError(f"env_id {uniq.max().item()} >= next_values size {nv_cpu.shape[0]}")
+            lengths = counts
+            n_env, max_t = len(uniq), int(counts.max())
+            # (t, column) coordinates of every sample in the padded grid
+            col = torch.repeat_interleave(torch.arange(n_env), counts)
+            starts = torch.cumsum(counts, 0) - counts
+            row = torch.arange(total) - torch.repeat_interleave(starts, counts)
+            def pad(src, fill):
+                out = torch.full((max_t, n_env), fill, dtype=torch.float32)
+                out[row, col] = src[order].float()
+                return out
+            rewards_p, values_p = pad(data["rewards"], 0.0), pad(data["values"], 0.0)
+            term_p = pad(data[key], 1.0)  # padding = terminated so nothing propagates through it
+            ov_p = pad(data["next_value_override"], float("nan")) if "next_value_override" in data else None
+            nv_cols = nv_cpu[uniq]
+            fn = gae_mod.compute_gae_padded_gpu if device.type == "cuda" else gae_mod.compute_gae_padded
+            mv = (lambda t: t.to(device)) if device.type == "cuda" else (lambda t: t)
+            padded = fn(mv(rewards_p), mv(values_p), mv(term_p), mv(nv_cols), lengths, gamma=p.gamma, lam=p.gae_lambda,
+                        next_value_override=None if ov_p is None else mv(ov_p))
+            adv = torch.zeros(total, device=padded.device)
+            adv[order.to(padded.device)] = padded[row.to(padded.device), col.to(padded.device)]
+            return adv
+        adv = gae_mod.compute_gae(data["rewards"].float(), data["values"].float(), data[key], nv_cpu.mean(),
+                                  gamma=p.gamma, lam=p.gae_lambda)
+        return adv.to(device)
+
+    # ---- one optimisation step -----------------------------------------------------------------------
+    def _losses(self, flat_logits, value_logits, score_lead, mb, value_adapter):
+        """(loss, policy_loss, value_loss, score_loss, entropy, flags) for CUDA or CPU tensors
+        (reference katago_ppo.py:858-924)."""
+        p = self.params
+        masks, actions, old_lp, adv, cats, score_t = mb
+        if flat_logits.is_cuda:
+            out2, _, _, _, _, flags = policy_ops.ppo_policy_loss(flat_logits, masks, actions, old_lp, adv, p.clip_epsilon)
+            policy_loss, entropy = out2[0], out2[1]
+        else:
+            flags = None
+            if flat_logits.isnan().any():
+                raise RuntimeError("NaN in raw policy logits from model forward pass")
+            if (masks.sum(dim=-1) == 0).any():
+                raise RuntimeError("Batch contains samples with zero legal actions in update(). "
+                                   "Check that terminal-state masks are not stored in the buffer.")
+            logp_all = F.log_softmax(flat_logits.float().masked_fill(~masks, float("-inf")), dim=-1)
+            new_lp = logp_all.gather(1, actions.unsqueeze(1)).squeeze(1)
+            policy_loss = ppo_clip_loss(new_lp, old_lp, adv, p.clip_epsilon)
+            entropy = -(logp_all.exp() * logp_all.masked_fill(~masks, 0.0)).sum(dim=-1).mean()
+        if value_adapter is not None:
+            value_score = value_adapter.compute_value_loss(value_logits, returns=None, value_cats=cats,
+                                                           score_targets=score_t, score_pred=score_lead)
+            value_loss, score_loss = value_score, torch.zeros((), device=flat_logits.device)
+        elif flat_logits.is_cuda:
+            out3 = policy_ops.value_losses(value_logits, cats, score_lead, score_t)
+            value_loss, score_loss = out3[0], out3[1]
+            value_score = p.lambda_value * value_loss + p.lambda_score * score_loss
+        else:
+            value_loss = wdl_cross_entropy_loss(value_logits.float(), cats)
+            score_loss = F.mse_loss(score_lead.float().squeeze(-1), score_t)
+            value_score = p.lambda_value * value_loss + p.lambda_score * score_loss
+        loss = p.lambda_policy * policy_loss + value_score - self.current_entropy_coeff * entropy
+        return loss, policy_loss, value_loss, score_loss, entropy, flags
+
+    def _check_flags(self, flags) -> None:
+        if flags is None or not self.strict_guards:
+            return
+        zero_legal, nan_rows = flags.tolist()
+        if nan_rows:
+            raise RuntimeError("NaN in raw policy logits from model forward pass")
+        if zero_legal:
+            raise RuntimeError("Batch contains samples with zero legal actions in update(). "
+                               "Check that terminal-state masks are not stored in the buffer.")
+
+    def _step_fused(self, km: SEResNetModel, obs, mb, value_adapter):
+        """Forward, losses, backward through the C-ABI with ONE flat gradient buffer."""
+        params, buffers = km._tables()
+        dtype = km._act_dtype(obs.device)
+        code = 0 if dtype == torch.float32 else 1
+        wpack = km._packed(params, buffers, dtype)
+        desc = km._desc()
+        with torch.no_grad():
+            policy_buf, value, score, ws, new_stats = model_ops.seresnet_forward(
+                obs, params, buffers, wpack, desc, True, code, bool(km.use_tensor_cores))
+            km._store_running_stats(buffers, new_stats)
+        policy_buf.requires_grad_(True); value.requires_grad_(True); score.requires_grad_(True)
+        loss, pl, vl, sl, ent, flags = self._losses(policy_buf[:, :model_ops.POLICY_A], value, score, mb, value_adapter)
+        self._check_flags(flags)
+        self.optimizer.zero_grad(set_to_none=True)
+        self.scaler.scale(loss).backward()
+        with torch.no_grad():
+            flat = model_ops.seresnet_backward(params, wpack, ws, policy_buf.grad, value.grad, score.grad, desc, code,
+                                               bool(km.use_tensor_cores))
+            if self.grad_sync is not None:
+                self.grad_sync.all_reduce_flat(flat)
+            off = 0
+            for prm in params:
+                n = prm.numel()
+                prm.grad = flat[off:off + n].view(prm.shape)
+                off += n
+        return pl, vl, sl, ent, value.detach()
+
+    def _step_autograd(self, obs, mb, value_adapter, amp_dtype, amp_dev):
+        with autocast(device_type=amp_dev, dtype=amp_dtype, enabled=self.params.use_amp):
+            output = self.forward_model(obs)
+            flat_logits = output.policy_logits.reshape(obs.shape[0], -1)
+            loss, pl, vl, sl, ent, flags = self._losses(flat_logits, output.value_logits, output.score_lead, mb, value_adapter)
+        self._check_flags(flags)
+        self.optimizer.zero_grad(set_to_none=True)
+        self.scaler.scale(loss).backward()
+        if self.grad_sync is not None:
+            self.grad_sync.all_reduce_params(self.model.parameters())
+        return pl, vl, sl, ent, output.value_logits.detach()
+
+    # ---- update --------------------------------------------------------------------------------------
+    def update(self, buffer: KataGoRolloutBuffer, next_values: torch.Tensor, value_adapter: Any | None = None,
+               heartbeat_fn: Any | None = None) -> dict[str, float]:
+        """Reference katago_ppo.py:619-991. Returns the same metrics dict; clears the buffer; leaves
+        `forward_model` in train mode."""
+        self.forward_model.train()
+        assert self.forward_model.training
+        self._timing_events["update_forward_backward_ms"].clear()
+        self._timing_events["gae_ms"].clear()
+        data = buffer.flatten()
+        T, N = buffer.size, buffer.num_envs
+        total = data["rewards"].numel()
+        device = next(self.model.parameters()).device
+        p = self.params
+
+        if device.type == "cuda":
+            side = torch.cuda.Stream(device)
+            with torch.cuda.stream(side):
+                gpu_obs = data["observations"].pin_memory().to(device, non_blocking=True)
+                gpu_masks = data["legal_masks"].pin_memory().to(device, non_blocking=True)
+        else:
+            side = None
+            gpu_obs, gpu_masks = data["observations"], data["legal_masks"]
+
+        adv = self._advantages(data, T, N, next_values, device).float().contiguous()
+        if adv.numel() > 1:
+            gae_mod.normalize_advantages_(adv)
+        mv = lambda t: t.to(device, non_blocking=True)  # noqa: E731
+        g_actions, g_old, g_cats, g_score = mv(data["actions"]), mv(data["log_probs"]), mv(data["value_categories"]), mv(data["score_targets"])
+        if side is not None:
+            torch.cuda.current_stream(device).wait_stream(side)
+
+        batch_size = min(p.batch_size, total)
+        amp_dtype, amp_dev = _amp_dtype_and_device(p.use_amp, device)
+        km = self._kernel_model(device) if self.forward_model is self._base() else None
+        zero = lambda: torch.zeros((), device=device)  # noqa: E731
+        acc = {k: zero() for k in ("policy_loss", "value_loss", "score_loss", "entropy", "gradient_norm")}
+        n_updates = 0
+        last_value_logits = last_cats = None
+        for _ in range(p.epochs_per_batch):
+            perm = torch.randperm(total, device=device)
+            for start in range(0, total, batch_size):
+                idx = perm[start:start + batch_size]
+                obs_b = gpu_obs[idx]
+                mb = (gpu_masks[idx], g_actions[idx], g_old[idx], adv[idx], g_cats[idx], g_score[idx])
+                tok = self._events(device, "update_forward_backward_ms")
+                if km is not None:
+                    pl, vl, sl, ent, v_logits = self._step_fused(km, obs_b, mb, value_adapter)
+                else:
+                    pl, vl, sl, ent, v_logits = self._step_autograd(obs_b, mb, value_adapter, amp_dtype, amp_dev)
+                self.scaler.unscale_(self.optimizer)
+                grad_norm = torch.nn.utils.clip_grad_norm_(self.model.parameters(), p.grad_clip)
+                self.scaler.step(self.optimizer)
+                self.scaler.update()
+                self._events_end(tok)
+                acc["policy_loss"] += pl.detach(); acc["value_loss"] += vl.detach(); acc["score_loss"] += sl.detach()
+                acc["entropy"] += ent.detach()
+                acc["gradient_norm"] += grad_norm.detach() if isinstance(grad_norm, torch.Tensor) else float(grad_norm)
+                n_updates += 1
+                last_value_logits, last_cats = v_logits, mb[4]
+                if heartbeat_fn is not None:
+                    heartbeat_fn()
+        del gpu_obs, gpu_masks
+        buffer.clear()
+        denom = max(n_updates, 1)
+        metrics = {k: (v / denom).item() for k, v in acc.items()}
+        if last_value_logits is not None:
+            valid = last_cats >= 0
+            if valid.any():
+                metrics.update(compute_value_metrics(last_value_logits[valid], last_cats[valid]))
+        self.forward_model.train()
+        return metrics

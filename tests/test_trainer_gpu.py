@@ -1,0 +1,84 @@
+"""The drop-in trainer on CUDA: the fused update() (C-ABI forward/backward, flat gradients)
+against the reference's own update() golden run; rollout select_actions semantics."""
+import numpy as np
+import pytest
+import torch
+
+from keisei_b200 import _lib
+from keisei_b200.katago_ppo import KataGoPPOAlgorithm, KataGoPPOParams, KataGoRolloutBuffer
+from keisei_b200.model_registry import build_model
+from keisei_b200.value_adapter import get_value_adapter
+from test_trainer_host import TINY, check_update, run_update_against_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_update_matches_reference_golden_cuda_fp32():
+    n0 = _lib.launch_count()
+    g, model, metrics = run_update_against_golden(DEV)
+    assert _lib.launch_count() - n0 > 50  # the kernels ran
+    check_update(g, model, metrics, 2e-4)
+
+
+def test_update_env_ids_layout_and_adapter_cuda():
+    torch.manual_seed(0)
+    model = build_model("se_resnet", dict(TINY)).to(DEV)
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(batch_size=5, epochs_per_batch=2), model)
+    N, A = 3, 11259
+    buf = KataGoRolloutBuffer(N, (50, 9, 9), A)
+    for t in range(4):
+        n = 2 if t % 2 else 3  # ragged: split-merge style env subsets
+        ids = torch.arange(n)
+        obs = torch.randn(n, 50, 9, 9, device=DEV)
+        mask = torch.rand(n, A, device=DEV) < 0.01; mask[:, 3] = True
+        a, lp, v = algo.select_actions(obs, mask, get_value_adapter("multi_head", score_blend_alpha=0.2))
+        assert mask[torch.arange(n), a].all()
+        term = torch.zeros(n, dtype=torch.bool)
+        buf.add(obs, a, lp, v, torch.zeros(n), term, term, mask, torch.full((n,), -1), torch.zeros(n), env_ids=ids,
+                next_value_override=torch.full((n,), float("nan")))
+    before = [p.detach().clone() for p in model.parameters()]
+    m = algo.update(buf, torch.randn(N, device=DEV), value_adapter=get_value_adapter("multi_head"))
+    assert all(np.isfinite(v) for v in m.values()) and m["score_loss"] == 0.0
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
+    algo.flush_timings()
+    assert len(algo.timings["update_forward_backward_ms"]) == 2 * 2 and len(algo.timings["select_actions_forward_ms"]) == 4
+
+
+def test_select_actions_zero_legal_raises_cuda():
+    model = build_model("se_resnet", dict(TINY)).to(DEV)
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(), model)
+    obs = torch.randn(4, 50, 9, 9, device=DEV)
+    mask = torch.ones(4, 11259, dtype=torch.bool, device=DEV); mask[2] = False
+    with pytest.raises(RuntimeError, match=r"Environments \[2\] have zero legal actions"):
+        algo.select_actions(obs, mask)
+    assert model.training
+
+
+def test_update_bf16_amp_runs_tcgen05_and_tracks_fp32():
+    torch.manual_seed(1)
+    cfg = dict(num_blocks=2, channels=128, se_reduction=8, global_pool_channels=32, policy_channels=16,
+               value_fc_size=32, score_fc_size=32)
+    m32 = build_model("se_resnet", dict(cfg)).to(DEV)
+    m16 = build_model("se_resnet", dict(cfg)).to(DEV)
+    m16.load_state_dict(m32.state_dict())
+    N, T, A = 6, 4, 11259
+    g = torch.Generator().manual_seed(2)
+    def fill(buf):
+        gg = torch.Generator().manual_seed(3)
+        for t in range(T):
+            obs = torch.randn(N, 50, 9, 9, generator=gg)
+            mask = torch.rand(N, A, generator=gg) < 0.01
+            a = torch.randint(0, A, (N,), generator=gg); mask[torch.arange(N), a] = True
+            term = torch.rand(N, generator=gg) < 0.2
+            buf.add(obs, a, -2 * torch.rand(N, generator=gg), 0.3 * torch.randn(N, generator=gg), term.float(), term, term, mask,
+                    torch.where(term, torch.randint(0, 3, (N,), generator=gg), torch.full((N,), -1)), torch.randn(N, generator=gg).clamp(-1, 1))
+    out = {}
+    for name, model, amp in (("fp32", m32, False), ("bf16", m16, True)):
+        buf = KataGoRolloutBuffer(N, (50, 9, 9), A)
+        fill(buf)
+        algo = KataGoPPOAlgorithm(KataGoPPOParams(batch_size=N * T, epochs_per_batch=1, use_amp=amp), model)
+        out[name] = algo.update(buf, torch.zeros(N, device=DEV))
+    for k in ("policy_loss", "value_loss", "score_loss", "entropy"):
+        a, b = out["bf16"][k], out["fp32"][k]
+        assert abs(a - b) <= 2e-2 * max(abs(b), 1e-3), (k, a, b)

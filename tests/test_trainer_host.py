@@ -1,0 +1,142 @@
+"""Host logic of the drop-in trainer on CPU tensors: the update() composition (GAE -> advantage
+normalisation -> losses -> clip -> Adam) against the reference's own update() golden run, the
+buffer guards, registries and adapters. No CUDA needed."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, state_dict_from
+from keisei_b200 import gae as G
+from keisei_b200.algorithm_registry import validate_algorithm_params
+from keisei_b200.katago_ppo import KataGoPPOAlgorithm, KataGoPPOParams, KataGoRolloutBuffer
+from keisei_b200.model_registry import build_model, get_model_contract, get_obs_channels, validate_model_params
+from keisei_b200.value_adapter import MultiHeadValueAdapter, ScalarValueAdapter, get_value_adapter
+
+TINY = dict(num_blocks=2, channels=32, se_reduction=4, global_pool_channels=16, policy_channels=8,
+            value_fc_size=16, score_fc_size=16, obs_channels=50)
+
+
+def fill_buffer_from_golden(g, buf):
+    T = g["steps/obs"].shape[0]
+    for t in range(T):
+        s = {k[len("steps/"):]: torch.from_numpy(np.array(v[t])) for k, v in g.items() if k.startswith("steps/")}
+        buf.add(s["obs"], s["actions"], s["logp"], s["values"], s["rewards"], s["term"], s["term"], s["mask"], s["cats"],
+                s["score_t"], next_value_override=s["ov"])
+
+
+def run_update_against_golden(device):
+    g = load_golden("update_tiny.npz")
+    model = build_model("se_resnet", dict(TINY))
+    model.load_state_dict(state_dict_from(g), strict=True)
+    model = model.to(device)
+    T, N = g["steps/obs"].shape[:2]
+    buf = KataGoRolloutBuffer(N, (50, 9, 9), 11259)
+    fill_buffer_from_golden(g, buf)
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(batch_size=T * N, epochs_per_batch=1, learning_rate=1e-3), model)
+    metrics = algo.update(buf, torch.from_numpy(g["next_values"]).to(device))
+    assert buf.size == 0 and model.training
+    return g, model, metrics
+
+
+def check_update(g, model, metrics, tol):
+    for k in ("policy_loss", "value_loss", "score_loss", "entropy", "gradient_norm"):
+        ref = float(g["metrics/" + k])
+        assert abs(metrics[k] - ref) <= tol * max(abs(ref), 1e-6) + 1e-7, (k, metrics[k], ref)
+    sd = model.state_dict()
+    for k, v in sd.items():
+        ref = g["sd_after/" + k]
+        if "num_batches_tracked" in k:
+            assert int(v) == int(ref)
+            continue
+        # Adam's first step moves every weight by ~lr * sign(grad): compare the *update*, not the weight
+        before = g["sd/" + k]
+        d_ref, d_got = ref - before, v.detach().cpu().numpy() - before
+        scale = max(np.abs(d_ref).max(), 1e-12)
+        assert np.abs(d_got - d_ref).max() <= 0.02 * scale + 1e-7, k
+
+
+def test_update_matches_reference_golden_cpu():
+    g, model, metrics = run_update_against_golden("cpu")
+    check_update(g, model, metrics, 1e-4)
+
+
+def test_buffer_guards_and_roundtrip():
+    buf = KataGoRolloutBuffer(2, (50, 9, 9), 11259)
+    with pytest.raises(ValueError, match="Cannot flatten an empty buffer"):
+        buf.flatten()
+    obs = torch.zeros(2, 50, 9, 9); a = torch.zeros(2, dtype=torch.long); z = torch.zeros(2)
+    mask = torch.ones(2, 11259, dtype=torch.bool)
+    with pytest.raises(AssertionError, match="terminated must be a subset of dones"):
+        buf.add(obs, a, z, z, z, torch.tensor([False, False]), torch.tensor([True, False]), mask, torch.tensor([-1, -1]), z)
+    with pytest.raises(ValueError, match="invalid values"):
+        buf.add(obs, a, z, z, z, z.bool(), z.bool(), mask, torch.tensor([3, 0]), z)
+    with pytest.raises(ValueError, match="NaN"):
+        buf.add(obs, a, z, z, z, z.bool(), z.bool(), mask, torch.tensor([0, 0]), torch.tensor([float("nan"), 0.0]))
+    with pytest.raises(ValueError, match="unnormalized"):
+        buf.add(obs, a, z, z, z, z.bool(), z.bool(), mask, torch.tensor([0, 0]), torch.tensor([10.0, 0.0]))
+    for t in range(3):
+        buf.add(obs + t, a + t, z, z + t, z, z.bool(), z.bool(), mask, torch.tensor([-1, 1]), z)
+    assert buf.size == 3
+    d = buf.flatten()
+    assert d["observations"].shape == (6, 50, 9, 9) and d["legal_masks"].shape == (6, 11259)
+    assert d["values"].tolist() == [0, 0, 1, 1, 2, 2]
+    buf.fill_alternating_perspective_overrides()
+    ov = buf.flatten()["next_value_override"].reshape(3, 2)
+    assert ov[0].tolist() == [-1.0, -1.0] and ov[1].tolist() == [-2.0, -2.0] and torch.isnan(ov[2]).all()
+    buf.clear()
+    assert buf.size == 0
+
+
+def test_registries_and_adapters():
+    assert get_model_contract("se_resnet") == "multi_head" and get_obs_channels("se_resnet") == 50
+    with pytest.raises(ValueError, match="Unknown architecture"):
+        build_model("nope", {})
+    with pytest.raises(TypeError, match="Invalid params"):
+        validate_model_params("se_resnet", {"bogus": 1})
+    with pytest.raises(ValueError):
+        validate_model_params("se_resnet", {"channels": 8, "se_reduction": 16})
+    with pytest.raises(ValueError, match="Unknown algorithm"):
+        validate_algorithm_params("ppo", {})
+    assert isinstance(validate_algorithm_params("katago_ppo", {"batch_size": 64}), KataGoPPOParams)
+    with pytest.raises(ValueError):
+        KataGoPPOParams(batch_size=0)
+    assert isinstance(get_value_adapter("scalar"), ScalarValueAdapter)
+    ad = get_value_adapter("multi_head", 1.5, 0.02, 0.25)
+    assert isinstance(ad, MultiHeadValueAdapter)
+    with pytest.raises(ValueError, match="Unknown model contract"):
+        get_value_adapter("x")
+    with pytest.raises(ValueError):
+        MultiHeadValueAdapter(score_blend_alpha=1.5)
+    vl = torch.tensor([[2.0, 0.0, -1.0]]); sc = torch.tensor([[3.0]])
+    p = torch.softmax(vl, -1)
+    assert torch.allclose(ad.scalar_value_blended(vl, sc), 0.75 * (p[:, 0] - p[:, 2]) + 0.25 * 1.0)
+    with pytest.raises(ValueError, match="requires value_cats"):
+        ad.compute_value_loss(vl)
+    loss = ad.compute_value_loss(vl.requires_grad_(), value_cats=torch.tensor([-1]), score_targets=torch.tensor([0.0]), score_pred=sc)
+    loss.backward()
+    assert torch.all(vl.grad == 0)  # all-ignored -> graph-connected zero
+
+
+def test_entropy_schedule_and_select_actions_guards_cpu():
+    model = build_model("se_resnet", dict(TINY))
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(entropy_decay_epochs=10, lambda_entropy=0.01), model, warmup_epochs=5, warmup_entropy=0.05)
+    assert algo.get_entropy_coeff(0) == 0.05 and algo.get_entropy_coeff(15) == 0.01
+    assert abs(algo.get_entropy_coeff(10) - 0.03) < 1e-12
+    obs = torch.randn(3, 50, 9, 9)
+    mask = torch.zeros(3, 11259, dtype=torch.bool); mask[:, 7] = True
+    a, lp, v = algo.select_actions(obs, mask)
+    assert a.tolist() == [7, 7, 7] and lp.abs().max() < 1e-5 and v.abs().max() <= 1.0 and model.training
+    mask[1] = False
+    with pytest.raises(RuntimeError, match=r"Environments \[1\] have zero legal actions"):
+        algo.select_actions(obs, mask)
+
+
+def test_gae_host_path_matches_golden():
+    g = load_golden("gae.npz")
+    t = lambda k: torch.from_numpy(g[k])
+    np.testing.assert_array_equal(G.compute_gae(t("r"), t("v"), t("term"), t("nv"), 0.99, 0.95).numpy(), g["adv_plain"])
+    np.testing.assert_array_equal(G.compute_gae_gpu(t("r"), t("v"), t("term"), t("nv"), 0.99, 0.95, next_value_override=t("ov")).numpy(), g["adv_override"])
+    np.testing.assert_array_equal(G.compute_gae_padded(t("r"), t("v"), t("termp"), t("nv"), t("lengths"), 0.99, 0.95, next_value_override=t("ov")).numpy(), g["adv_padded_override"])
+    np.testing.assert_array_equal(G.compute_gae(t("r")[:, 0], t("v")[:, 0], t("term")[:, 0], t("nv")[0], 0.99, 0.95).numpy(), g["adv_1d"])
+    with pytest.raises(ValueError, match="only supports 2D"):
+        G.compute_gae_gpu(torch.zeros(4), torch.zeros(4), torch.zeros(4), torch.zeros(()), 0.99, 0.95)
