@@ -121,8 +121,10 @@ int kb_conv3x3_forward(const void* in, const void* w, void* out, int B, int Cin,
                        const float* scale, const float* shift, int relu, const float* gbias, double* ch_sums,
                        float* board_mean, float* pool, int num_sms, kb_stream_t stream);
 /* dw (Cout,Cin_true,3,3) float32 += sum over boards/pixels of dy (B,81,Cout) x shifted x (B,81,Cin) */
+/* backend 1 (tcgen05) needs a scratch buffer of kb_conv3x3_wgrad_ws_bytes() bytes for the per-slice partial tiles */
+long long kb_conv3x3_wgrad_ws_bytes(int Cin, int Cout, int num_sms);
 int kb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true, int dtype,
-                     int backend, int num_sms, kb_stream_t stream);
+                     int backend, void* ws, long long ws_bytes, int num_sms, kb_stream_t stream);
 /* w (Cout,Cin,3,3) float32 -> wf (Cout,9,Cinp) and optional wd (Cinp,9,Cout) (flipped taps) in `dtype` */
 int kb_pack_conv_weight(const float* w, void* wf, void* wd, int Cout, int Cin, int Cinp, int dtype, kb_stream_t stream);
 

@@ -21,13 +21,17 @@ extern "C" int kb_conv3x3_forward(const void* in, const void* w, void* out, int 
   return kbk_conv3x3_simt(in, w, out, B, Cin, Cout, dtype, e, stream);
 }
 
+extern "C" long long kb_conv3x3_wgrad_ws_bytes(int Cin, int Cout, int num_sms) {
+  return kbk_conv3x3_wgrad_tc_ws_bytes(Cin, Cout, num_sms);
+}
+
 extern "C" int kb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true,
-                                int dtype, int backend, int num_sms, cudaStream_t stream) {
+                                int dtype, int backend, void* ws, long long ws_bytes, int num_sms, cudaStream_t stream) {
   KB_CHECK_ARG(x && dy && dw, "kb_conv3x3_wgrad: null pointer");
   KB_CHECK_ARG(dtype == KB_F32 || dtype == KB_BF16, "kb_conv3x3_wgrad: bad dtype");
   if (backend == 1) {
-    KB_CHECK_ARG(kbk_conv3x3_tc_supported(Cin, Cout, dtype), "kb_conv3x3_wgrad: tcgen05 path unsupported for this shape/dtype");
-    return kbk_conv3x3_wgrad_tc(x, dy, dw, B, Cin, Cout, Cin_true, num_sms, stream);
+    KB_CHECK_ARG(kbk_conv3x3_tc_supported(Cin, Cout, dtype) && Cin <= 256, "kb_conv3x3_wgrad: tcgen05 path unsupported for this shape/dtype");
+    return kbk_conv3x3_wgrad_tc(x, dy, dw, B, Cin, Cout, Cin_true, (float*)ws, ws_bytes, num_sms, stream);
   }
   return kbk_conv3x3_wgrad_simt(x, dy, dw, B, Cin, Cout, Cin_true, dtype, stream);
 }

@@ -262,6 +262,152 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------- weight-gradient kernel
+// dW[co][ci][tap] = sum_{board, pixel} dY[board][pixel][co] * X[board][pixel + shift(tap)][ci]
+//
+// GEMM view per CTA: one (tap, 128-channel half of Cout) unit and one slice of the boards.
+//   D[co (128 TMEM lanes), ci (N = Cin columns)] += A[co, k] * B[ci, k],  k = pixels of one board.
+// Both operands are "MN-major": in NHWC memory the channel index is contiguous for a fixed pixel k.
+// TMA lands each board as 64-channel groups of [81 pixel rows x 128 B] (swizzle 128B); rows 81..95
+// of every group are zeroed once and never written, so K is padded 81 -> 96 = 6 x UMMA_K for free.
+// The tap shift is the TMA box origin on X (zero fill at the board edge), exactly as in the forward.
+// Partial tiles go to a workspace with coalesced stores; wgrad_reduce_kernel sums the board slices
+// and scatters into the PyTorch (Cout, Cin, 3, 3) fp32 gradient.
+constexpr int kWgStages = 3;
+constexpr int kWgRows = 96;                          // 81 pixels padded to a multiple of UMMA_K
+constexpr int kWgGroupBytes = kWgRows * 128;         // one 64-channel group of one board: 12 KB
+constexpr int kWgBoxBytes = 81 * 128;                // bytes TMA writes per group
+constexpr int kWgAGroups = 2;                        // 128 output channels
+constexpr int kWgMaxBGroups = 4;                     // up to 256 input channels
+constexpr int kWgStageBytes = (kWgAGroups + kWgMaxBGroups) * kWgGroupBytes;  // 72 KB
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 1024 + 256;
+
+// MN-major operand, SWIZZLE_128B: 64-element groups LBO apart, 8-row (k) groups SBO = 1024 B apart
+__device__ __forceinline__ uint64_t smem_desc_mn128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(kWgGroupBytes >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                        float* __restrict__ ws, int B, int Cin, int Cout, int units, int boards_per_slice) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + kWgStages * kWgStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kWgStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kWgStages);
+  const uint32_t holder = bar_base + 8u * (2 * kWgStages + 1);
+  volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kWgStages * kWgStageBytes + 8 * (2 * kWgStages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x % units, slice = blockIdx.x / units;
+  const int n_half = Cout / kTileM;
+  const int tap = unit / n_half, half = unit % n_half;
+  const int b_groups = Cin / 64;
+  const int b_begin = slice * boards_per_slice;
+  const int b_end = min(B, b_begin + boards_per_slice);
+  const int nboards = b_end - b_begin;
+
+  // zero the whole operand area once: the K-padding rows (81..95 of every group) must read as 0
+  {
+    uint4* p = reinterpret_cast<uint4*>(smem_gen);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < kWgStages * kWgStageBytes / 16; i += kThreads) p[i] = z;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_x);
+  }
+  if (warp == 1) {
+    tmem_alloc(holder, 256);
+    tmem_relinquish();
+  }
+  fence_proxy_async();  // generic-proxy zero fill -> visible to the async proxy (TMA / UMMA)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *holder_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int b = b_begin; b < b_end; ++b) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)((kWgAGroups + b_groups) * kWgBoxBytes));
+        const uint32_t a_dst = smem_base + stage * kWgStageBytes;
+#pragma unroll
+        for (int g = 0; g < kWgAGroups; ++g)
+          tma_load_4d(a_dst + g * kWgGroupBytes, &map_dy, full_bar(stage), half * kTileM + g * 64, 0, 0, b);
+        for (int g = 0; g < b_groups; ++g)
+          tma_load_4d(a_dst + (kWgAGroups + g) * kWgGroupBytes, &map_x, full_bar(stage), g * 64, tap % 3 - 1, tap / 3 - 1, b);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // M = 128, N = Cin, A and B MN-major (bits 15, 16), fp32 accumulate, bf16 inputs
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(Cin >> 3) << 17) |
+                             ((uint32_t)(kTileM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < nboards; ++i) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + stage * kWgStageBytes;
+        const uint64_t adesc = smem_desc_mn128(a_addr);
+        const uint64_t bdesc = smem_desc_mn128(a_addr + kWgAGroups * kWgGroupBytes);
+#pragma unroll
+        for (int k = 0; k < kWgRows / 16; ++k) {
+          // 16 pixel rows = 2048 bytes further down every group: +128 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int lane_grp = warp & 3;
+    float* dst = ws + ((size_t)blockIdx.x * Cin) * kTileM + lane_grp * 32 + lane;  // ws[cta][ci][co_local]
+    if (nboards > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+      for (int ch = 0; ch < Cin / 16; ++ch) {
+        uint32_t r[16];
+        tmem_ld16(taddr + ch * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dst[(size_t)(ch * 16 + i) * kTileM] = __uint_as_float(r[i]);
+      }
+    } else {
+      for (int ci = 0; ci < Cin; ++ci) dst[(size_t)ci * kTileM] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// dw[(co*Cin_true + ci)*9 + tap] += sum_slices ws[slice*units + tap*n_half + half][ci][co_local]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cin, int Cout, int Cin_true,
+                                    int units, int slices) {
+  const int co = blockIdx.x * 128 + threadIdx.x;  // blockDim = 128
+  const int ci = blockIdx.y, tap = blockIdx.z;
+  if (co >= Cout || ci >= Cin_true) return;
+  const int n_half = Cout / kTileM;
+  const int unit = tap * n_half + co / kTileM;
+  float s = 0.f;
+  for (int sl = 0; sl < slices; ++sl) s += ws[(((size_t)sl * units + unit) * Cin + ci) * kTileM + (co % kTileM)];
+  dw[((size_t)co * Cin_true + ci) * 9 + tap] += s;
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -349,9 +495,38 @@ int kbk_conv3x3_tc(const void* in, const void* w, void* out, int B, int Cin, int
   }
 }
 
-int kbk_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true, int num_sms,
-                         cudaStream_t st) {
-  (void)num_sms;
-  // TODO(round 1): tcgen05 weight-gradient kernel (MN-major operands); SIMT fallback keeps the path correct.
-  return kbk_conv3x3_wgrad_simt(x, dy, dw, B, Cin, Cout, Cin_true, KB_BF16, st);
+long long kbk_conv3x3_wgrad_tc_ws_bytes(int Cin, int Cout, int num_sms) {
+  if (num_sms <= 0) num_sms = 148;
+  const int units = 9 * (Cout / kTileM);
+  int slices = num_sms / units;
+  if (slices < 1) slices = 1;
+  return (long long)slices * units * Cin * kTileM * (long long)sizeof(float);
+}
+
+int kbk_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true, float* ws,
+                         long long ws_bytes, int num_sms, cudaStream_t st) {
+  KB_CHECK_ARG(kbk_conv3x3_tc_supported(Cin, Cout, KB_BF16) && Cin <= 64 * kWgMaxBGroups, "conv3x3_wgrad_tc: unsupported shape Cin=%d Cout=%d", Cin, Cout);
+  if (B == 0) return KB_OK;
+  if (num_sms <= 0) num_sms = 148;
+  const int units = 9 * (Cout / kTileM);
+  int slices = num_sms / units;
+  if (slices < 1) slices = 1;
+  if (slices > B) slices = B;
+  const int bps = kb_ceil_div(B, slices);
+  slices = kb_ceil_div(B, bps);
+  KB_CHECK_ARG(ws != nullptr && ws_bytes >= (long long)slices * units * Cin * kTileM * (long long)sizeof(float),
+               "conv3x3_wgrad_tc: workspace too small");
+  CUtensorMap mdy, mx;
+  if (int r = make_act_map(&mdy, dy, B, Cout, 1)) return r;
+  if (int r = make_act_map(&mx, x, B, Cin, 1)) return r;
+  static bool attr_set = false;
+  if (!attr_set) {
+    KB_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    attr_set = true;
+  }
+  conv3x3_wgrad_tc_kernel<<<units * slices, kThreads, kWgSmemBytes, st>>>(mdy, mx, ws, B, Cin, Cout, units, bps);
+  KB_CUDA_LAUNCH_CHECK();
+  wgrad_reduce_kernel<<<dim3(kb_ceil_div(Cout, 128), Cin_true, 9), 128, 0, st>>>(ws, dw, Cin, Cout, Cin_true, units, slices);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
 }

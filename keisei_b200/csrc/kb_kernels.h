@@ -17,8 +17,9 @@ int kbk_conv3x3_wgrad_simt(const void* x, const void* dy, float* dw, int B, int 
 int kbk_conv3x3_tc_supported(int Cin, int Cout, int dtype);
 int kbk_conv3x3_tc(const void* in, const void* w, void* out, int B, int Cin, int Cout, const ConvEpi& epi,
                    int num_sms, cudaStream_t st);
-int kbk_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true,
-                         int num_sms, cudaStream_t st);
+long long kbk_conv3x3_wgrad_tc_ws_bytes(int Cin, int Cout, int num_sms);
+int kbk_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true, float* ws,
+                         long long ws_bytes, int num_sms, cudaStream_t st);
 
 // ---- gemm_simt.cu ----
 struct GemmArgs {

@@ -97,6 +97,7 @@ struct Ws {
   // backward temporaries
   void *d0, *d1, *d2;
   float *s_du, *s_duz, *dse_in, *dg, *dse, *dseh, *dgh, *dpool, *k123, *dp1, *dvh, *dsh;
+  float* wg_ws; long long wg_ws_bytes;  // tcgen05 weight-gradient partial tiles
   int Cmax;
   size_t total;
   float* pool(const Dims& m, int i) const { return pools + (size_t)i * m.B * 3 * m.C; }
@@ -135,6 +136,8 @@ void carve(const Dims& m, void* base, int training, Ws& w, BlockWs* blk_storage)
     w.k123 = b.f32(3 * (size_t)w.Cmax);
     w.dp1 = b.f32((size_t)m.M * m.Pc);
     w.dvh = b.f32(B * m.V); w.dsh = b.f32(B * m.S2);
+    w.wg_ws_bytes = (m.dtype == KB_BF16 && m.C % 128 == 0 && m.C <= 256) ? kbk_conv3x3_wgrad_tc_ws_bytes(m.C, m.C, 148 * 2) : 0;
+    w.wg_ws = w.wg_ws_bytes ? (float*)b.take((size_t)w.wg_ws_bytes) : nullptr;
     w.ea = w.eb = w.ey1 = w.ey2 = nullptr; w.epool_a = w.epool_b = nullptr;
   } else {
     w.ea = b.take(m.act()); w.eb = b.take(m.act()); w.ey1 = b.take(m.act()); w.ey2 = b.take(m.act());
@@ -146,6 +149,7 @@ void carve(const Dims& m, void* base, int training, Ws& w, BlockWs* blk_storage)
     w.z0 = w.x0 = nullptr; w.pools = nullptr;
     w.d0 = w.d1 = w.d2 = nullptr;
     w.s_du = w.s_duz = w.dse_in = w.dg = w.dse = w.dseh = w.dgh = w.dpool = w.k123 = w.dp1 = w.dvh = w.dsh = nullptr;
+    w.wg_ws = nullptr; w.wg_ws_bytes = 0;
   }
   w.total = b.off + 256;
 }
@@ -156,8 +160,9 @@ int conv3x3(const Dims& m, const void* in, const void* wgt, void* out, int Cin, 
   return kbk_conv3x3_simt(in, wgt, out, m.B, Cin, Cout, m.dtype, e, st);
 }
 int wgrad3x3(const Dims& m, const void* x, const void* dy, float* dw, int Cin, int Cout, int Cin_true, int use_tc,
-             int num_sms, cudaStream_t st) {
-  if (use_tc && m.B >= 3 && kbk_conv3x3_tc_supported(Cin, Cout, m.dtype)) return kbk_conv3x3_wgrad_tc(x, dy, dw, m.B, Cin, Cout, Cin_true, num_sms, st);
+             int num_sms, float* wg_ws, long long wg_ws_bytes, cudaStream_t st) {
+  if (use_tc && m.B >= 3 && Cin <= 256 && wg_ws != nullptr && kbk_conv3x3_tc_supported(Cin, Cout, m.dtype))
+    return kbk_conv3x3_wgrad_tc(x, dy, dw, m.B, Cin, Cout, Cin_true, wg_ws, wg_ws_bytes, num_sms, st);
   return kbk_conv3x3_wgrad_simt(x, dy, dw, m.B, Cin, Cout, Cin_true, m.dtype, st);
 }
 
@@ -469,7 +474,7 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
     pb.k1 = k1; pb.k2 = k2; pb.k3 = k3; pb.dz2 = t1;
     KB_TRY(kbk_block_bwd_dz2(pb, st));
     // conv2: weight gradient, then data gradient with the BN1/ReLU/gpool-bias backward fused in its epilogue
-    KB_TRY(wgrad3x3(m, bw.a1, t1, G(pi_blk(i, 3)), C, C, C, use_tc, num_sms, st));
+    KB_TRY(wgrad3x3(m, bw.a1, t1, G(pi_blk(i, 3)), C, C, C, use_tc, num_sms, w.wg_ws, w.wg_ws_bytes, st));
     ConvEpi e = epi_base();
     e.mask_src = bw.z1; e.mask_a = w.bn_a(l1); e.mask_b = w.bn_b(l1);
     e.ch_sum = w.dsums; e.ch_dot = w.dsums + C; e.board_sum = w.dg; e.board_scale = 1.f;
@@ -483,7 +488,7 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
     KB_TRY(linear_bwd_x(w.dgh, KB_F32, m.G, B, m.G, P(pi_blk(i, 6)), 3 * C, w.dpool, KB_F32, 3 * C, nullptr, 0, 0, st));
     // pass C: dz1 in place; conv1 weight + data gradients
     KB_TRY(kbk_bn_bwd_apply(t2, bw.z1, k1, k2, k3, m.M, C, dtype, st));
-    KB_TRY(wgrad3x3(m, x_in, t2, G(pi_blk(i, 0)), C, C, C, use_tc, num_sms, st));
+    KB_TRY(wgrad3x3(m, x_in, t2, G(pi_blk(i, 0)), C, C, C, use_tc, num_sms, w.wg_ws, w.wg_ws_bytes, st));
     ConvEpi e1 = epi_base();
     KB_TRY(conv3x3(m, t2, wp.wd(i, 0), t1, C, C, e1, use_tc, num_sms, st));
     // pass D: dx = dgrad + residual branch + global-pool backward
@@ -498,6 +503,6 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
   KB_TRY(kbk_relu_bwd_stats(cur, w.x0, w.z0, t1, m.M, C, dtype, w.dsums, st));
   KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(1), w.bn_mean(0), w.bn_invstd(0), k1, k2, k3, G(1), G(2), C, st));
   KB_TRY(kbk_bn_bwd_apply(t1, w.z0, k1, k2, k3, m.M, C, dtype, st));
-  KB_TRY(wgrad3x3(m, w.obs_p, t1, G(0), m.C0p, C, m.C0, use_tc, num_sms, st));
+  KB_TRY(wgrad3x3(m, w.obs_p, t1, G(0), m.C0p, C, m.C0, use_tc, num_sms, w.wg_ws, w.wg_ws_bytes, st));
   return KB_OK;
 }

@@ -37,7 +37,8 @@ _lib.register_signature("kb_seresnet_backward", c_int, [_P, _P, _P, c_int, c_int
                                                          _P, _P, c_int, c_int, _P])
 _lib.register_signature("kb_conv3x3_forward", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P,
                                                        _P, _P, _P, c_int, _P])
-_lib.register_signature("kb_conv3x3_wgrad", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P])
+_lib.register_signature("kb_conv3x3_wgrad", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_longlong, c_int, _P])
+_lib.register_signature("kb_conv3x3_wgrad_ws_bytes", c_longlong, [c_int, c_int, c_int])
 _lib.register_signature("kb_pack_conv_weight", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P])
 
 _DT = {torch.float32: 0, torch.bfloat16: 1}
@@ -242,8 +243,12 @@ def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, cin_true: int | None = None
     Cout = dy.shape[2]
     ct = cin_true or Cin
     dw = torch.zeros((Cout, ct, 3, 3), dtype=torch.float32, device=x.device)
+    ws = None
+    if backend == 1:
+        ws = torch.empty(int(_lib.load().kb_conv3x3_wgrad_ws_bytes(Cin, Cout, sm_count(x.device))), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         rc = _lib.load().kb_conv3x3_wgrad(x.contiguous().data_ptr(), dy.contiguous().data_ptr(), dw.data_ptr(), B, Cin,
-                                          Cout, ct, _DT[x.dtype], backend, sm_count(x.device), _lib.stream_ptr(x.device))
+                                          Cout, ct, _DT[x.dtype], backend, _lib.ptr(ws), 0 if ws is None else ws.numel(),
+                                          sm_count(x.device), _lib.stream_ptr(x.device))
     _lib.check(rc, "kb_conv3x3_wgrad")
     return dw

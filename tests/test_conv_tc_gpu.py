@@ -83,3 +83,20 @@ def test_linearity_at_full_size():
     # and spot-check 3 boards against the SIMT kernel
     o3, *_ = model_ops.conv3x3(x[1000:1003].contiguous(), wf, backend=0)
     assert rel(o1[1000:1003].float().cpu().numpy(), o3.float().cpu().numpy()) < 1e-2
+
+
+@pytest.mark.parametrize("B,Cin,Cout,ct", [(3, 64, 128, None), (8, 64, 256, 50), (5, 256, 256, None), (130, 256, 256, None), (29, 128, 256, None)])
+def test_conv3x3_wgrad_tc(B, Cin, Cout, ct):
+    g = torch.Generator().manual_seed(100 + B)
+    x = torch.randn(B, Cin, 9, 9, generator=g).bfloat16()
+    if ct:
+        x[:, ct:] = 0
+    dy = torch.randn(B, Cout, 9, 9, generator=g).bfloat16()
+    w = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), w, padding=1).backward(dy.double())
+    want = (w.grad[:, :ct] if ct else w.grad).numpy()
+    got = model_ops.conv3x3_wgrad(nhwc(x).to(DEV), nhwc(dy).to(DEV), cin_true=ct, backend=1)
+    torch.cuda.synchronize()
+    assert rel(got.cpu().numpy(), want) < 2e-3
+    got0 = model_ops.conv3x3_wgrad(nhwc(x).to(DEV), nhwc(dy).to(DEV), cin_true=ct, backend=0)
+    assert rel(got.cpu().numpy(), got0.cpu().numpy()) < 2e-3
