@@ -288,6 +288,278 @@ __global__ void relu_bwd_stats_f32_kernel(float* __restrict__ d, const float* __
   }
 }
 
+// =================================================================================================
+// Vectorised variants: thread = 8 consecutive channels (one 16-byte bf16 / two 16-byte fp32 accesses)
+// x one of NPL pixel lanes; CTA = one board, 256 threads. C/8 channel groups * NPL lanes = 256, so a
+// warp reads whole 128..512-byte rows; per-(board, channel) reductions finish through shared memory.
+// Used when C % 8 == 0 and 256 % (C/8) == 0 (C = 16, 32, 64, 128, 256, 512 ...).
+// =================================================================================================
+template <typename T> struct V8;
+template <> struct V8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  static __device__ __forceinline__ void round(float (&)[8]) {}
+};
+template <> struct V8<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack(v[0], v[1]), pack(v[2], v[3]), pack(v[4], v[5]), pack(v[6], v[7]));
+  }
+  static __device__ __forceinline__ void round(float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+  }
+};
+__device__ __forceinline__ void ldf8(const float* p, float (&v)[8]) { V8<float>::load(p, v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
+  __shared__ float red[4][2048];  // [quantity][lane * C + c]
+  const int C = g.C, C8 = C >> 3, NPL = 256 / C8;
+  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
+  float a_[8], b_[8], sg[8], sf[8], gb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a_[i] = 1.f; b_[i] = 0.f; sg[i] = 1.f; sf[i] = 0.f; gb[i] = 0.f; }
+  if (g.a) { ldf8(g.a + c0, a_); ldf8(g.b + c0, b_); }
+  if (g.se) {
+    ldf8(g.se + (size_t)b * 2 * C + c0, sg); ldf8(g.se + (size_t)b * 2 * C + C + c0, sf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sg[i] = sigmoidf_(sg[i]);
+  }
+  if (g.gbias) ldf8(g.gbias + (size_t)b * C + c0, gb);
+  const size_t base = (size_t)b * 81 * C + c0;
+  float s[8], mx[8], k0[8], ds[8], dss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; mx[i] = -INFINITY; k0[i] = 0.f; ds[i] = 0.f; dss[i] = 0.f; }
+  int cnt = 0;
+  for (int p = pl; p < 81; p += NPL) {
+    float v[8], r[8];
+    V8<T>::load((const T*)g.z + base + (size_t)p * C, v);
+    if (g.res) V8<T>::load((const T*)g.res + base + (size_t)p * C, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = fmaf(fmaf(v[i], a_[i], b_[i]), sg[i], sf[i]);
+      if (g.res) t += r[i];
+      v[i] = fmaxf(t, 0.f) + gb[i];
+    }
+    V8<T>::store((T*)g.out + base + (size_t)p * C, v);
+    if (g.pool) {
+      V8<T>::round(v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (cnt == 0) k0[i] = v[i];
+        const float d = v[i] - k0[i];
+        s[i] += v[i]; mx[i] = fmaxf(mx[i], v[i]); ds[i] += d; dss[i] = fmaf(d, d, dss[i]);
+      }
+      ++cnt;
+    }
+  }
+  if (g.pool == nullptr) return;
+  // per-lane (count, mean, M2) -> Chan's parallel merge across the NPL pixel lanes
+  const float fc = (float)cnt;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int o = pl * C + c0 + i;
+    red[0][o] = s[i];
+    red[1][o] = mx[i];
+    red[2][o] = cnt > 0 ? k0[i] + ds[i] / fc : 0.f;            // lane mean
+    red[3][o] = cnt > 0 ? dss[i] - ds[i] * ds[i] / fc : 0.f;   // lane M2
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float S = 0.f, M = -INFINITY;
+    for (int l = 0; l < NPL; ++l) { S += red[0][l * C + c]; M = fmaxf(M, red[1][l * C + c]); }
+    const float mean = S * (1.f / 81.f);
+    float m2 = 0.f;
+    for (int l = 0; l < NPL; ++l) {
+      const int n_l = l < 81 ? (81 - l + NPL - 1) / NPL : 0;  // pixels lane l visited
+      const float dm = red[2][l * C + c] - mean;
+      m2 += red[3][l * C + c] + (float)n_l * dm * dm;
+    }
+    float* pr = g.pool + (size_t)b * 3 * C;
+    pr[c] = mean; pr[C + c] = M; pr[2 * C + c] = sqrtf(fmaxf(m2 * (1.f / 81.f), 0.f));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) block_bwd_reduce_vec_kernel(BlockBwdArgs g) {
+  __shared__ float red[2][2048];
+  const int C = g.C, C8 = C >> 3, NPL = 256 / C8;
+  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
+  const size_t base = (size_t)b * 81 * C + c0;
+  float s[8], sz[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; sz[i] = 0.f; }
+  for (int p = pl; p < 81; p += NPL) {
+    float d[8], x[8], z[8];
+    V8<T>::load((const T*)g.dxp + base + (size_t)p * C, d);
+    V8<T>::load((const T*)g.xp + base + (size_t)p * C, x);
+    V8<T>::load((const T*)g.z2 + base + (size_t)p * C, z);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float du = x[i] > 0.f ? d[i] : 0.f; s[i] += du; sz[i] = fmaf(du, z[i], sz[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][pl * C + c0 + i] = s[i]; red[1][pl * C + c0 + i] = sz[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = 0.f, q = 0.f;
+    for (int l = 0; l < NPL; ++l) { a += red[0][l * C + c]; q += red[1][l * C + c]; }
+    g.s_du[(size_t)b * C + c] = a;
+    g.s_duz[(size_t)b * C + c] = q;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) block_bwd_dz2_vec_kernel(PassBArgs g) {
+  const int C = g.C, C8 = C >> 3, NPL = 256 / C8;
+  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
+  const size_t base = (size_t)b * 81 * C + c0;
+  float sg[8], dm[8], k1[8], k2[8], k3[8];
+  ldf8(g.se + (size_t)b * 2 * C + c0, sg); ldf8(g.dse_in + (size_t)b * C + c0, dm);
+  ldf8(g.k1 + c0, k1); ldf8(g.k2 + c0, k2); ldf8(g.k3 + c0, k3);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sg[i] = sigmoidf_(sg[i]); dm[i] *= (1.f / 81.f); }
+  for (int p = pl; p < 81; p += NPL) {
+    float d[8], x[8], z[8];
+    V8<T>::load((const T*)g.dxp + base + (size_t)p * C, d);
+    V8<T>::load((const T*)g.xp + base + (size_t)p * C, x);
+    V8<T>::load((const T*)g.z2 + base + (size_t)p * C, z);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float du = x[i] > 0.f ? d[i] : 0.f;
+      d[i] = k1[i] * fmaf(du, sg[i], dm[i]) - k2[i] * z[i] - k3[i];
+    }
+    V8<T>::store((T*)g.dz2 + base + (size_t)p * C, d);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) block_bwd_dx_vec_kernel(PassDArgs g) {
+  __shared__ float red[2048];
+  const int C = g.C, C8 = C >> 3, NPL = 256 / C8;
+  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
+  const size_t base = (size_t)b * 81 * C + c0;
+  float gmean[8], gmax[8], gstd[8], mean[8], mx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { gmean[i] = 0.f; gmax[i] = 0.f; gstd[i] = 0.f; mean[i] = 0.f; mx[i] = 0.f; }
+  if (g.dpool) {
+    const float* pr = g.pool + (size_t)b * 3 * C;
+    const float* dp = g.dpool + (size_t)b * 3 * C;
+    float sd[8], dmean[8], dmaxv[8], dstd[8];
+    ldf8(pr + c0, mean); ldf8(pr + C + c0, mx); ldf8(pr + 2 * C + c0, sd);
+    ldf8(dp + c0, dmean); ldf8(dp + C + c0, dmaxv); ldf8(dp + 2 * C + c0, dstd);
+    float ties[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ties[i] = 0.f;
+    for (int p = pl; p < 81; p += NPL) {
+      float x[8];
+      V8<T>::load((const T*)g.x + base + (size_t)p * C, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ties[i] += (x[i] == mx[i]) ? 1.f : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl * C + c0 + i] = ties[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = 0.f;
+      for (int l = 0; l < NPL; ++l) t += red[l * C + c0 + i];
+      gmean[i] = dmean[i] * (1.f / 81.f);
+      gstd[i] = sd[i] > 0.f ? dstd[i] / (81.f * sd[i]) : 0.f;
+      gmax[i] = t > 0.f ? dmaxv[i] / t : 0.f;
+    }
+  }
+  for (int p = pl; p < 81; p += NPL) {
+    float v[8], t[8], y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (g.dxc) V8<T>::load((const T*)g.dxc + base + (size_t)p * C, v);
+    if (g.dxp) {
+      V8<T>::load((const T*)g.dxp + base + (size_t)p * C, t);
+      if (g.xp) {
+        V8<T>::load((const T*)g.xp + base + (size_t)p * C, y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += y[i] > 0.f ? t[i] : 0.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += t[i];
+      }
+    }
+    if (g.dpool) {
+      V8<T>::load((const T*)g.x + base + (size_t)p * C, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += gmean[i] + (t[i] == mx[i] ? gmax[i] : 0.f) + gstd[i] * (t[i] - mean[i]);
+    }
+    V8<T>::store((T*)g.dx + base + (size_t)p * C, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) relu_bwd_stats_vec_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                                                   const T* __restrict__ z, T* __restrict__ dzh, int C,
+                                                                   double* sums) {
+  __shared__ float red[2][2048];
+  const int C8 = C >> 3, NPL = 256 / C8;
+  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
+  const size_t base = (size_t)b * 81 * C + c0;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  for (int p = pl; p < 81; p += NPL) {
+    float d[8], a[8], zz[8];
+    V8<T>::load(dy + base + (size_t)p * C, d);
+    V8<T>::load(y + base + (size_t)p * C, a);
+    V8<T>::load(z + base + (size_t)p * C, zz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = a[i] > 0.f ? d[i] : 0.f;
+    V8<T>::store(dzh + base + (size_t)p * C, d);
+    V8<T>::round(d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1[i] += d[i]; s2[i] = fmaf(d[i], zz[i], s2[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][pl * C + c0 + i] = s1[i]; red[1][pl * C + c0 + i] = s2[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = 0.f, q = 0.f;
+    for (int l = 0; l < NPL; ++l) { a += red[0][l * C + c]; q += red[1][l * C + c]; }
+    atomicAdd(&sums[c], (double)a);
+    atomicAdd(&sums[C + c], (double)q);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_vec_kernel(T* __restrict__ d, const T* __restrict__ z,
+                                                                 const float* __restrict__ k1, const float* __restrict__ k2,
+                                                                 const float* __restrict__ k3, long long n8, int C) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)((i * 8) % C);
+    float v[8], zz[8], a[8], b[8], e[8];
+    V8<T>::load(d + i * 8, v); V8<T>::load(z + i * 8, zz);
+    ldf8(k1 + c0, a); ldf8(k2 + c0, b); ldf8(k3 + c0, e);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = a[j] * v[j] - b[j] * zz[j] - e[j];
+    V8<T>::store(d + i * 8, v);
+  }
+}
+
+inline bool vec_ok(int C) { return C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0; }
+
 inline int ch_threads(int C) { return ((C + 31) / 32) * 32; }
 
 }  // namespace
@@ -302,7 +574,8 @@ inline int ch_threads(int C) { return ((C + 31) / 32) * 32; }
 int kbk_apply(const ApplyArgs& a, cudaStream_t st) {
   KB_CHECK_ARG(a.C >= 1 && a.C <= 1024, "apply: C=%d out of range", a.C);
   if (a.B == 0) return KB_OK;
-  KB_DISPATCH_T(a.dtype, apply_kernel, a.B, ch_threads(a.C), 0, st, a);
+  if (vec_ok(a.C)) KB_DISPATCH_T(a.dtype, apply_vec_kernel, a.B, 256, 0, st, a);
+  else KB_DISPATCH_T(a.dtype, apply_kernel, a.B, ch_threads(a.C), 0, st, a);
   return KB_OK;
 }
 
@@ -340,7 +613,8 @@ int kbk_rows_stats(const float* x, long long M, int C, double* sums, cudaStream_
 
 int kbk_block_bwd_reduce(const BlockBwdArgs& a, cudaStream_t st) {
   KB_CHECK_ARG(a.C <= 1024, "block_bwd_reduce: C too large");
-  KB_DISPATCH_T(a.dtype, block_bwd_reduce_kernel, a.B, ch_threads(a.C), 0, st, a);
+  if (vec_ok(a.C)) KB_DISPATCH_T(a.dtype, block_bwd_reduce_vec_kernel, a.B, 256, 0, st, a);
+  else KB_DISPATCH_T(a.dtype, block_bwd_reduce_kernel, a.B, ch_threads(a.C), 0, st, a);
   return KB_OK;
 }
 
@@ -369,7 +643,8 @@ int kbk_bn_bwd_finalize(double* sums, double count, const float* w, const float*
 
 int kbk_block_bwd_dz2(const PassBArgs& a, cudaStream_t st) {
   KB_CHECK_ARG(a.C <= 1024, "block_bwd_dz2: C too large");
-  KB_DISPATCH_T(a.dtype, block_bwd_dz2_kernel, a.B, ch_threads(a.C), 0, st, a);
+  if (vec_ok(a.C)) KB_DISPATCH_T(a.dtype, block_bwd_dz2_vec_kernel, a.B, 256, 0, st, a);
+  else KB_DISPATCH_T(a.dtype, block_bwd_dz2_kernel, a.B, ch_threads(a.C), 0, st, a);
   return KB_OK;
 }
 
@@ -377,6 +652,14 @@ int kbk_bn_bwd_apply(void* d, const void* z, const float* k1, const float* k2, c
                      int dtype, cudaStream_t st) {
   const long long n = rows * C;
   if (n == 0) return KB_OK;
+  if (C % 8 == 0) {
+    const long long n8 = n / 8;
+    const int grid8 = (int)min((long long)148 * 16, (n8 + 255) / 256);
+    if (dtype == KB_F32) bn_bwd_apply_vec_kernel<float><<<grid8, 256, 0, st>>>((float*)d, (const float*)z, k1, k2, k3, n8, C);
+    else bn_bwd_apply_vec_kernel<bf16><<<grid8, 256, 0, st>>>((bf16*)d, (const bf16*)z, k1, k2, k3, n8, C);
+    KB_CUDA_LAUNCH_CHECK();
+    return KB_OK;
+  }
   const int grid = (int)min((long long)148 * 16, (n + 255) / 256);
   if (dtype == KB_F32) bn_bwd_apply_kernel<float><<<grid, 256, 0, st>>>((float*)d, (const float*)z, k1, k2, k3, n, C);
   else bn_bwd_apply_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)d, (const bf16*)z, k1, k2, k3, n, C);
@@ -386,7 +669,8 @@ int kbk_bn_bwd_apply(void* d, const void* z, const float* k1, const float* k2, c
 
 int kbk_block_bwd_dx(const PassDArgs& a, cudaStream_t st) {
   KB_CHECK_ARG(a.C <= 1024, "block_bwd_dx: C too large");
-  KB_DISPATCH_T(a.dtype, block_bwd_dx_kernel, a.B, ch_threads(a.C), 0, st, a);
+  if (vec_ok(a.C)) KB_DISPATCH_T(a.dtype, block_bwd_dx_vec_kernel, a.B, 256, 0, st, a);
+  else KB_DISPATCH_T(a.dtype, block_bwd_dx_kernel, a.B, ch_threads(a.C), 0, st, a);
   return KB_OK;
 }
 
@@ -394,6 +678,14 @@ int kbk_relu_bwd_stats(const void* dy, const void* y, const void* z, void* dzh, 
                        double* sums, cudaStream_t st) {
   KB_CHECK_ARG(rows % 81 == 0 && C <= 1024, "relu_bwd_stats: bad shape");
   const int B = (int)(rows / 81);
+  if (vec_ok(C)) {
+    if (dtype == KB_F32)
+      relu_bwd_stats_vec_kernel<float><<<B, 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)z, (float*)dzh, C, sums);
+    else
+      relu_bwd_stats_vec_kernel<bf16><<<B, 256, 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)z, (bf16*)dzh, C, sums);
+    KB_CUDA_LAUNCH_CHECK();
+    return KB_OK;
+  }
   if (dtype == KB_F32)
     relu_bwd_stats_kernel<float><<<B, ch_threads(C), 0, st>>>((const float*)dy, (const float*)y, (const float*)z, (float*)dzh, C, sums);
   else

@@ -61,18 +61,22 @@ struct ConvEpiThread {
 #pragma unroll
     for (int j = 0; j < NB; ++j) { s[j] = 0.f; ss[j] = 0.f; mx[j] = -INFINITY; dot[j] = 0.f; pre[j] = 0.f; k0[j] = 0.f; ds[j] = 0.f; dss[j] = 0.f; }
   }
-  // one accumulator value: local board j (compile-time after unrolling), global board b, pixel p
-  __device__ __forceinline__ void value(int j, int b, int p, float acc, T* __restrict__ out) {
+  // element index of (board b, pixel p) for this thread's channel
+  __device__ __forceinline__ size_t index(int b, int p) const { return ((size_t)b * 81 + p) * Cout + c; }
+  // one accumulator value: local board j (compile-time after unrolling), global board b, pixel p.
+  // `msrc` = the mask-source element at index(b, p), pre-loaded by the caller (lets the tcgen05
+  // epilogue keep several chunks of loads in flight); ignored when the mask feature is off.
+  __device__ __forceinline__ void value(int j, int b, int p, float acc, T* __restrict__ out, float msrc = 0.f) {
     float v = acc;
     if (on(kEpiAffine, e.scale != nullptr)) v = fmaf(v, sc, sh);
     if (on(kEpiRelu, e.relu != 0)) v = fmaxf(v, 0.f);
     if (on(kEpiGbias, e.gbias != nullptr)) v += e.gbias[(size_t)b * Cout + c];
     const size_t idx = ((size_t)b * 81 + p) * Cout + c;
-    float msrc = 0.f;
     if (on(kEpiMask, e.mask_src != nullptr)) {
       pre[j] += v;
-      msrc = kb_to_float<T>(((const T*)e.mask_src)[idx]);
       if (!(fmaf(msrc, ma, mb) > 0.f)) v = 0.f;
+    } else {
+      msrc = 0.f;
     }
     const T stored = kb_from_float<T>(v);
     out[idx] = stored;

@@ -229,9 +229,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       tc_fence_after();
       ConvEpiThread<bf16, kBoards, F> et(epi, c, Cout, B);
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * kTileN);
+      // Mask-source prefetch (data-gradient epilogue): the ReLU mask / BN-backward statistics need one
+      // activation element per accumulator. Loads are issued kPf chunks (of 16 columns) ahead of their
+      // use so ~64 independent loads per thread are in flight instead of one dependent load per column.
+      constexpr bool kMask = (F != kEpiDynamic) && (F & kEpiMask) != 0;
+      constexpr int kPf = 4, kChunks = (kBoards * 81 + 15) / 16;
+      bf16 pf[kPf + 1][16];
+      auto prefetch = [&](int ch) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = ch * 16 + i;
+          const int j = col / 81, p = col % 81;
+          pf[ch % (kPf + 1)][i] = (col < kBoards * 81 && j < nb_valid) ? ((const bf16*)epi.mask_src)[et.index(b0 + j, p)] : bf16(0.f);
+        }
+      };
+      if (kMask) {
+#pragma unroll
+        for (int ch = 0; ch < kPf; ++ch) prefetch(ch);
+      }
 #pragma unroll
       for (int ch = 0; ch < kTileN / 16; ++ch) {
         if (ch * 16 < kBoards * 81) {
+          if (kMask && ch + kPf < kChunks) prefetch(ch + kPf);
           uint32_t r[16];
           tmem_ld16(taddr + ch * 16, r);
           tmem_ld_wait();
@@ -241,7 +260,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
             if (col < kBoards * 81) {
               const int j = col / 81, p = col % 81;
               if (j < nb_valid) {
-                et.value(j, b0 + j, p, __uint_as_float(r[i]), out);
+                float ms = 0.f;
+                if (kMask) ms = __bfloat162float(pf[ch % (kPf + 1)][i]);
+                else if (F == kEpiDynamic && epi.mask_src != nullptr) ms = __bfloat162float(((const bf16*)epi.mask_src)[et.index(b0 + j, p)]);
+                et.value(j, b0 + j, p, __uint_as_float(r[i]), out, ms);
                 if (p == 80) et.board_done(j, b0 + j);
               }
             }

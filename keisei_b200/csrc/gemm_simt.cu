@@ -1,9 +1,10 @@
 // gemm_simt.cu — small dense layers of the model on CUDA cores, fp32 accumulate.
 //
 // Covers the Linear / 1x1-conv layers around the trunk (reference se_resnet.py:57-61 global_fc,
-// :63-66 SE, :119-130 heads) forward and backward: tiny GEMMs (M = boards or pixels) whose FLOPs
-// are ~0.2 % of the model. One generic 64x64x16 register-tiled kernel with optional operand
-// transposes, a per-k affine(+ReLU) prologue on A (BatchNorm+ReLU feeding the policy conv),
+// :63-66 SE, :119-130 heads) forward and backward: skinny GEMMs (M = boards or pixels) whose FLOPs
+// are ~0.2 % of the model. One register-tiled kernel (BMx64x16, 256 threads, 4 values of each operand
+// per thread per K step fetched as ONE 16-byte / 8-byte vector along the contiguous dimension,
+// register double buffering) with optional operand transposes, a per-k affine(+ReLU) prologue on A,
 // bias/ReLU/mask epilogue, board-pitched rows (the padded (B, 11264) policy buffer) and split-K
 // with fp32 atomics (weight gradients reduce over the batch).
 #include "kb_common.cuh"
@@ -11,73 +12,130 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BN = 64, BK = 16;
 
-__device__ __forceinline__ float ld_any(const void* p, int dtype, long long i) {
-  return dtype == KB_F32 ? ((const float*)p)[i] : __bfloat162float(((const bf16*)p)[i]);
+// 4 consecutive elements starting at element offset `off`
+__device__ __forceinline__ float4 ld4(const void* p, int dtype, long long off, bool vec_ok, int valid) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid <= 0) return v;
+  if (dtype == KB_F32) {
+    const float* f = (const float*)p + off;
+    if (vec_ok && valid >= 4) return __ldg(reinterpret_cast<const float4*>(f));
+    v.x = f[0];
+    if (valid > 1) v.y = f[1];
+    if (valid > 2) v.z = f[2];
+    if (valid > 3) v.w = f[3];
+  } else {
+    const bf16* h = (const bf16*)p + off;
+    if (vec_ok && valid >= 4) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(h));
+      v.x = __uint_as_float(u.x << 16); v.y = __uint_as_float(u.x & 0xffff0000u);
+      v.z = __uint_as_float(u.y << 16); v.w = __uint_as_float(u.y & 0xffff0000u);
+      return v;
+    }
+    v.x = __bfloat162float(h[0]);
+    if (valid > 1) v.y = __bfloat162float(h[1]);
+    if (valid > 2) v.z = __bfloat162float(h[2]);
+    if (valid > 3) v.w = __bfloat162float(h[3]);
+  }
+  return v;
 }
 
-__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g, int k_per_slice) {
+template <int BM>
+__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g, int k_per_slice, int a_vec, int b_vec) {
+  constexpr int TM = BM / 16;  // rows per thread (4 or 2)
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.z * k_per_slice;
   const int k_end = min(g.K, k_begin + k_per_slice);
-  float acc[4][4];
+  float acc[TM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+  // per-thread operand coordinates: 4 contiguous elements per K step
+  // A: !transA -> (m = tid/4, k4 = (tid%4)*4);  transA -> (k = tid/(BM/4), m4 = (tid%(BM/4))*4)
+  const bool a_active = g.transA ? (tid < BK * (BM / 4)) : (tid < BM * 4);
+  const int a_r = g.transA ? tid / (BM / 4) : tid / 4;          // transA: k row ; else m row
+  const int a_c = g.transA ? (tid % (BM / 4)) * 4 : (tid % 4) * 4;  // transA: m offset ; else k offset
+  // B: transB (B[n][k]) -> (n = tid/4, k4 = (tid%4)*4);  !transB (B[k][n]) -> (k = tid/16, n4 = (tid%16)*4)
+  const int b_r = g.transB ? tid / 4 : tid / 16;
+  const int b_c = g.transB ? (tid % 4) * 4 : (tid % 16) * 4;
+
+  auto a_row_off = [&](long long row) -> long long {
+    if (g.a_group_rows > 0) return (row / g.a_group_rows) * g.a_group_pitch + (row % g.a_group_rows) * g.lda;
+    return row * g.lda;
+  };
+  auto load_a = [&](int k0) -> float4 {
+    if (!a_active) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.transA) {
+      const int gk = k0 + a_r, gm = m0 + a_c;
+      if (gk >= k_end) return make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 v = ld4(g.A, g.a_dtype, a_row_off(gk) + gm, a_vec != 0, g.M - gm);
+      if (g.a_pa) { const float pa = g.a_pa[gk], pb = g.a_pb[gk]; v.x = fmaf(v.x, pa, pb); v.y = fmaf(v.y, pa, pb); v.z = fmaf(v.z, pa, pb); v.w = fmaf(v.w, pa, pb); }
+      if (g.a_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      return v;
+    }
+    const int gm = m0 + a_r, gk = k0 + a_c;
+    if (gm >= g.M) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = ld4(g.A, g.a_dtype, a_row_off(gm) + gk, a_vec != 0, k_end - gk);
+    if (g.a_pa) {
+      const int kk = min(gk, g.K - 4 > 0 ? g.K - 1 : 0);
+      (void)kk;
+      if (gk < k_end) v.x = fmaf(v.x, g.a_pa[gk], g.a_pb[gk]);
+      if (gk + 1 < k_end) v.y = fmaf(v.y, g.a_pa[gk + 1], g.a_pb[gk + 1]);
+      if (gk + 2 < k_end) v.z = fmaf(v.z, g.a_pa[gk + 2], g.a_pb[gk + 2]);
+      if (gk + 3 < k_end) v.w = fmaf(v.w, g.a_pa[gk + 3], g.a_pb[gk + 3]);
+    }
+    if (g.a_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    return v;
+  };
+  auto load_b = [&](int k0) -> float4 {
+    if (g.transB) {
+      const int gn = n0 + b_r, gk = k0 + b_c;
+      if (gn >= g.N) return make_float4(0.f, 0.f, 0.f, 0.f);
+      return ld4(g.B, g.b_dtype, (long long)gn * g.ldb + gk, b_vec != 0, k_end - gk);
+    }
+    const int gk = k0 + b_r, gn = n0 + b_c;
+    if (gk >= k_end) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return ld4(g.B, g.b_dtype, (long long)gk * g.ldb + gn, b_vec != 0, g.N - gn);
+  };
+  auto store_a = [&](const float4& v) {
+    if (!a_active) return;
+    if (g.transA) *reinterpret_cast<float4*>(&As[a_r][a_c]) = v;
+    else { As[a_c][a_r] = v.x; As[a_c + 1][a_r] = v.y; As[a_c + 2][a_r] = v.z; As[a_c + 3][a_r] = v.w; }
+  };
+  auto store_b = [&](const float4& v) {
+    if (g.transB) { Bs[b_c][b_r] = v.x; Bs[b_c + 1][b_r] = v.y; Bs[b_c + 2][b_r] = v.z; Bs[b_c + 3][b_r] = v.w; }
+    else *reinterpret_cast<float4*>(&Bs[b_r][b_c]) = v;
+  };
+
+  float4 ra = load_a(k_begin), rb = load_b(k_begin);
   for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-    // ---- A tile (BM x BK) ----
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int e = tid + it * 256;
-      int m, k;
-      if (g.transA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
-      const int gm = m0 + m, gk = k0 + k;
-      float v = 0.f;
-      if (gm < g.M && gk < k_end) {
-        const long long row = g.transA ? gk : gm, col = g.transA ? gm : gk;
-        long long off;
-        if (g.a_group_rows > 0) off = (row / g.a_group_rows) * g.a_group_pitch + (row % g.a_group_rows) * g.lda + col;
-        else off = row * g.lda + col;
-        v = ld_any(g.A, g.a_dtype, off);
-        if (g.a_pa) v = fmaf(v, g.a_pa[gk], g.a_pb[gk]);
-        if (g.a_relu) v = fmaxf(v, 0.f);
-      }
-      As[k][m] = v;
-    }
-    // ---- B tile (BK x BN) ----
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int e = tid + it * 256;
-      int n, k;
-      if (g.transB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
-      const int gn = n0 + n, gk = k0 + k;
-      float v = 0.f;
-      if (gn < g.N && gk < k_end) v = ld_any(g.B, g.b_dtype, g.transB ? (long long)gn * g.ldb + gk : (long long)gk * g.ldb + gn);
-      Bs[k][n] = v;
-    }
+    store_a(ra); store_b(rb);
     __syncthreads();
+    if (k0 + BK < k_end) { ra = load_a(k0 + BK); rb = load_b(k0 + BK); }  // prefetch while computing
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float av[TM];
+      if (TM == 4) { const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]); av[0] = a.x; av[1] = a.y; av[TM - 2] = a.z; av[TM - 1] = a.w; }
+      else { const float2 a = *reinterpret_cast<const float2*>(&As[k][ty * 2]); av[0] = a.x; av[1] = a.y; }
       const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < TM; ++i) {
+        acc[i][0] = fmaf(av[i], b.x, acc[i][0]); acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], b.z, acc[i][2]); acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+      }
     }
     __syncthreads();
   }
   // ---- epilogue ----
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
     if (gm >= g.M) continue;
     long long crow;
     if (g.c_group_rows > 0) crow = ((long long)gm / g.c_group_rows) * g.c_group_pitch + ((long long)gm % g.c_group_rows) * g.ldc;
@@ -113,7 +171,7 @@ __global__ void colsum_kernel(const void* __restrict__ X, int dtype, long long l
       long long off;
       if (group_rows > 0) off = ((long long)r / group_rows) * group_pitch + ((long long)r % group_rows) * ldx + n;
       else off = (long long)r * ldx + n;
-      s += ld_any(X, dtype, off);
+      s += dtype == KB_F32 ? ((const float*)X)[off] : __bfloat162float(((const bf16*)X)[off]);
     }
   sh[ry][cx] = s;
   __syncthreads();
@@ -122,6 +180,15 @@ __global__ void colsum_kernel(const void* __restrict__ X, int dtype, long long l
     for (int i = 0; i < 8; ++i) a += sh[i][cx];
     atomicAdd(&out[n], a);
   }
+}
+
+// can every 4-element group of this operand be fetched with one aligned vector load?
+bool vec4_ok(const void* p, int dtype, long long ld, int group_rows, long long group_pitch) {
+  const int esz = dtype == KB_F32 ? 4 : 2;
+  if (((uintptr_t)p) % (4 * esz) != 0) return false;
+  if (ld % 4 != 0) return false;
+  if (group_rows > 0 && group_pitch % 4 != 0) return false;
+  return true;
 }
 
 }  // namespace
@@ -136,7 +203,16 @@ int kbk_gemm(const GemmArgs& g, cudaStream_t st) {
   splitk = kb_ceil_div(g.K, kps);
   GemmArgs a = g;
   a.splitk = g.splitk > 1 ? 2 : 1;  // >1 only selects the atomic epilogue
-  gemm_kernel<<<dim3(kb_ceil_div(g.N, BN), kb_ceil_div(g.M, BM), splitk), 256, 0, st>>>(a, kps);
+  // vector loads need the 4-element groups to be aligned AND in-bounds handling via `valid`; the
+  // K offset of every slice is a multiple of 16, so alignment reduces to base/ld divisibility
+  const int a_vec = vec4_ok(g.A, g.a_dtype, g.lda, g.a_group_rows, g.a_group_pitch) ? 1 : 0;
+  const int b_vec = vec4_ok(g.B, g.b_dtype, g.ldb, 0, 0) ? 1 : 0;
+  const long long tiles64 = (long long)kb_ceil_div(g.N, BN) * kb_ceil_div(g.M, 64) * splitk;
+  if (tiles64 >= 2 * 148) {
+    gemm_kernel<64><<<dim3(kb_ceil_div(g.N, BN), kb_ceil_div(g.M, 64), splitk), 256, 0, st>>>(a, kps, a_vec, b_vec);
+  } else {
+    gemm_kernel<32><<<dim3(kb_ceil_div(g.N, BN), kb_ceil_div(g.M, 32), splitk), 256, 0, st>>>(a, kps, a_vec, b_vec);
+  }
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }
