@@ -327,19 +327,27 @@ template <> struct V8<bf16> {
 };
 __device__ __forceinline__ void ldf8(const float* p, float (&v)[8]) { V8<float>::load(p, v); }
 
-template <typename T>
+// SE = squeeze-excite scale/shift + residual present; POOL = emit global-pool statistics of the output.
+template <typename T, bool SE, bool POOL>
 __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
-  __shared__ float red[4][2048];  // [quantity][lane * C + c]
+  __shared__ float red[POOL ? 4 : 1][POOL ? 2048 : 1];  // [quantity][lane * C + c]
   const int C = g.C, C8 = C >> 3, NPL = 256 / C8;
   const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
   float a_[8], b_[8], sg[8], sf[8], gb[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { a_[i] = 1.f; b_[i] = 0.f; sg[i] = 1.f; sf[i] = 0.f; gb[i] = 0.f; }
   if (g.a) { ldf8(g.a + c0, a_); ldf8(g.b + c0, b_); }
-  if (g.se) {
+  if (SE) {
     ldf8(g.se + (size_t)b * 2 * C + c0, sg); ldf8(g.se + (size_t)b * 2 * C + C + c0, sf);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sg[i] = sigmoidf_(sg[i]);
+    for (int i = 0; i < 8; ++i) {
+      sg[i] = sigmoidf_(sg[i]);
+      // fold the BN affine into the SE scale/shift: (z*a+b)*sg+sf = z*(a*sg) + (b*sg+sf)
+      sf[i] = fmaf(b_[i], sg[i], sf[i]); sg[i] *= a_[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sg[i] = a_[i]; sf[i] = b_[i]; }
   }
   if (g.gbias) ldf8(g.gbias + (size_t)b * C + c0, gb);
   const size_t base = (size_t)b * 81 * C + c0;
@@ -347,18 +355,15 @@ __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; mx[i] = -INFINITY; k0[i] = 0.f; ds[i] = 0.f; dss[i] = 0.f; }
   int cnt = 0;
-  for (int p = pl; p < 81; p += NPL) {
-    float v[8], r[8];
-    V8<T>::load((const T*)g.z + base + (size_t)p * C, v);
-    if (g.res) V8<T>::load((const T*)g.res + base + (size_t)p * C, r);
+  auto finish = [&](float (&v)[8], const float (&r)[8], int p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float t = fmaf(fmaf(v[i], a_[i], b_[i]), sg[i], sf[i]);
-      if (g.res) t += r[i];
+      float t = fmaf(v[i], sg[i], sf[i]);
+      if (SE) t += r[i];
       v[i] = fmaxf(t, 0.f) + gb[i];
     }
     V8<T>::store((T*)g.out + base + (size_t)p * C, v);
-    if (g.pool) {
+    if (POOL) {
       V8<T>::round(v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -368,28 +373,40 @@ __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
       }
       ++cnt;
     }
+  };
+  for (int p = pl; p < 81; p += 2 * NPL) {  // two pixels per iteration: 2-4 independent 16-byte loads in flight
+    const bool two = p + NPL < 81;
+    float v0[8], r0[8], v1[8], r1[8];
+    V8<T>::load((const T*)g.z + base + (size_t)p * C, v0);
+    if (SE) V8<T>::load((const T*)g.res + base + (size_t)p * C, r0);
+    if (two) {
+      V8<T>::load((const T*)g.z + base + (size_t)(p + NPL) * C, v1);
+      if (SE) V8<T>::load((const T*)g.res + base + (size_t)(p + NPL) * C, r1);
+    }
+    finish(v0, r0, p);
+    if (two) finish(v1, r1, p + NPL);
   }
-  if (g.pool == nullptr) return;
+  if (!POOL) return;
   // per-lane (count, mean, M2) -> Chan's parallel merge across the NPL pixel lanes
   const float fc = (float)cnt;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int o = pl * C + c0 + i;
     red[0][o] = s[i];
-    red[1][o] = mx[i];
-    red[2][o] = cnt > 0 ? k0[i] + ds[i] / fc : 0.f;            // lane mean
-    red[3][o] = cnt > 0 ? dss[i] - ds[i] * ds[i] / fc : 0.f;   // lane M2
+    red[POOL ? 1 : 0][o] = mx[i];
+    red[POOL ? 2 : 0][o] = cnt > 0 ? k0[i] + ds[i] / fc : 0.f;            // lane mean
+    red[POOL ? 3 : 0][o] = cnt > 0 ? dss[i] - ds[i] * ds[i] / fc : 0.f;   // lane M2
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += 256) {
     float S = 0.f, M = -INFINITY;
-    for (int l = 0; l < NPL; ++l) { S += red[0][l * C + c]; M = fmaxf(M, red[1][l * C + c]); }
+    for (int l = 0; l < NPL; ++l) { S += red[0][l * C + c]; M = fmaxf(M, red[POOL ? 1 : 0][l * C + c]); }
     const float mean = S * (1.f / 81.f);
     float m2 = 0.f;
     for (int l = 0; l < NPL; ++l) {
       const int n_l = l < 81 ? (81 - l + NPL - 1) / NPL : 0;  // pixels lane l visited
-      const float dm = red[2][l * C + c] - mean;
-      m2 += red[3][l * C + c] + (float)n_l * dm * dm;
+      const float dm = red[POOL ? 2 : 0][l * C + c] - mean;
+      m2 += red[POOL ? 3 : 0][l * C + c] + (float)n_l * dm * dm;
     }
     float* pr = g.pool + (size_t)b * 3 * C;
     pr[c] = mean; pr[C + c] = M; pr[2 * C + c] = sqrtf(fmaxf(m2 * (1.f / 81.f), 0.f));
@@ -509,37 +526,66 @@ __global__ void __launch_bounds__(256) block_bwd_dx_vec_kernel(PassDArgs g) {
   }
 }
 
+// dzh = dy * [mask > 0] with mask = y (ma == null) or y*ma[c] + mb[c]; per-channel sums of dzh and
+// dzh*z (double atomics); optional per-(board, channel) sum of the UNMASKED dy (gpool-bias gradient).
+// dzh may alias dy (in place). Two pixels per iteration keep 4-6 independent 16-byte loads in flight.
 template <typename T>
-__global__ void __launch_bounds__(256) relu_bwd_stats_vec_kernel(const T* __restrict__ dy, const T* __restrict__ y,
-                                                                   const T* __restrict__ z, T* __restrict__ dzh, int C,
-                                                                   double* sums) {
-  __shared__ float red[2][2048];
+__global__ void __launch_bounds__(256) relu_bwd_stats_vec_kernel(const T* dy, const T* __restrict__ y,
+                                                                   const T* __restrict__ z, T* dzh, int C,
+                                                                   const float* __restrict__ ma, const float* __restrict__ mb,
+                                                                   float* __restrict__ board_sum, double* sums) {
+  __shared__ float red[3][2048];
   const int C8 = C >> 3, NPL = 256 / C8;
   const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
   const size_t base = (size_t)b * 81 * C + c0;
-  float s1[8], s2[8];
+  const bool same = (y == z);
+  float s1[8], s2[8], s0[8], fa[8], fb[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-  for (int p = pl; p < 81; p += NPL) {
-    float d[8], a[8], zz[8];
-    V8<T>::load(dy + base + (size_t)p * C, d);
-    V8<T>::load(y + base + (size_t)p * C, a);
-    V8<T>::load(z + base + (size_t)p * C, zz);
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; s0[i] = 0.f; fa[i] = 1.f; fb[i] = 0.f; }
+  if (ma) { ldf8(ma + c0, fa); ldf8(mb + c0, fb); }
+  for (int p = pl; p < 81; p += 2 * NPL) {
+    const bool two = p + NPL < 81;
+    float d0[8], a0[8], z0[8], d1[8], a1[8], z1[8];
+    V8<T>::load(dy + base + (size_t)p * C, d0);
+    V8<T>::load(y + base + (size_t)p * C, a0);
+    if (!same) V8<T>::load(z + base + (size_t)p * C, z0);
+    if (two) {
+      V8<T>::load(dy + base + (size_t)(p + NPL) * C, d1);
+      V8<T>::load(y + base + (size_t)(p + NPL) * C, a1);
+      if (!same) V8<T>::load(z + base + (size_t)(p + NPL) * C, z1);
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = a[i] > 0.f ? d[i] : 0.f;
-    V8<T>::store(dzh + base + (size_t)p * C, d);
-    V8<T>::round(d);
+    for (int i = 0; i < 8; ++i) {
+      s0[i] += d0[i];
+      if (same) z0[i] = a0[i];
+      d0[i] = fmaf(a0[i], fa[i], fb[i]) > 0.f ? d0[i] : 0.f;
+    }
+    V8<T>::store(dzh + base + (size_t)p * C, d0);
+    V8<T>::round(d0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s1[i] += d[i]; s2[i] = fmaf(d[i], zz[i], s2[i]); }
+    for (int i = 0; i < 8; ++i) { s1[i] += d0[i]; s2[i] = fmaf(d0[i], z0[i], s2[i]); }
+    if (two) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s0[i] += d1[i];
+        if (same) z1[i] = a1[i];
+        d1[i] = fmaf(a1[i], fa[i], fb[i]) > 0.f ? d1[i] : 0.f;
+      }
+      V8<T>::store(dzh + base + (size_t)(p + NPL) * C, d1);
+      V8<T>::round(d1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s1[i] += d1[i]; s2[i] = fmaf(d1[i], z1[i], s2[i]); }
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { red[0][pl * C + c0 + i] = s1[i]; red[1][pl * C + c0 + i] = s2[i]; }
+  for (int i = 0; i < 8; ++i) { red[0][pl * C + c0 + i] = s1[i]; red[1][pl * C + c0 + i] = s2[i]; red[2][pl * C + c0 + i] = s0[i]; }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += 256) {
-    float a = 0.f, q = 0.f;
-    for (int l = 0; l < NPL; ++l) { a += red[0][l * C + c]; q += red[1][l * C + c]; }
+    float a = 0.f, q = 0.f, u = 0.f;
+    for (int l = 0; l < NPL; ++l) { a += red[0][l * C + c]; q += red[1][l * C + c]; u += red[2][l * C + c]; }
     atomicAdd(&sums[c], (double)a);
     atomicAdd(&sums[C + c], (double)q);
+    if (board_sum) board_sum[(size_t)b * C + c] = u;
   }
 }
 
@@ -574,8 +620,22 @@ inline int ch_threads(int C) { return ((C + 31) / 32) * 32; }
 int kbk_apply(const ApplyArgs& a, cudaStream_t st) {
   KB_CHECK_ARG(a.C >= 1 && a.C <= 1024, "apply: C=%d out of range", a.C);
   if (a.B == 0) return KB_OK;
-  if (vec_ok(a.C)) KB_DISPATCH_T(a.dtype, apply_vec_kernel, a.B, 256, 0, st, a);
-  else KB_DISPATCH_T(a.dtype, apply_kernel, a.B, ch_threads(a.C), 0, st, a);
+  if (vec_ok(a.C) && ((a.se != nullptr) == (a.res != nullptr))) {
+    const bool se = a.se != nullptr, pool = a.pool != nullptr;
+#define KB_APPLY_VEC(SE_, POOL_)                                                                   \
+    do {                                                                                           \
+      if (a.dtype == KB_F32) apply_vec_kernel<float, SE_, POOL_><<<a.B, 256, 0, st>>>(a);          \
+      else apply_vec_kernel<bf16, SE_, POOL_><<<a.B, 256, 0, st>>>(a);                             \
+    } while (0)
+    if (se && pool) KB_APPLY_VEC(true, true);
+    else if (se) KB_APPLY_VEC(true, false);
+    else if (pool) KB_APPLY_VEC(false, true);
+    else KB_APPLY_VEC(false, false);
+#undef KB_APPLY_VEC
+    KB_CUDA_LAUNCH_CHECK();
+    return KB_OK;
+  }
+  KB_DISPATCH_T(a.dtype, apply_kernel, a.B, ch_threads(a.C), 0, st, a);
   return KB_OK;
 }
 
@@ -680,9 +740,9 @@ int kbk_relu_bwd_stats(const void* dy, const void* y, const void* z, void* dzh, 
   const int B = (int)(rows / 81);
   if (vec_ok(C)) {
     if (dtype == KB_F32)
-      relu_bwd_stats_vec_kernel<float><<<B, 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)z, (float*)dzh, C, sums);
+      relu_bwd_stats_vec_kernel<float><<<B, 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)z, (float*)dzh, C, nullptr, nullptr, nullptr, sums);
     else
-      relu_bwd_stats_vec_kernel<bf16><<<B, 256, 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)z, (bf16*)dzh, C, sums);
+      relu_bwd_stats_vec_kernel<bf16><<<B, 256, 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)z, (bf16*)dzh, C, nullptr, nullptr, nullptr, sums);
     KB_CUDA_LAUNCH_CHECK();
     return KB_OK;
   }
@@ -690,6 +750,20 @@ int kbk_relu_bwd_stats(const void* dy, const void* y, const void* z, void* dzh, 
     relu_bwd_stats_kernel<float><<<B, ch_threads(C), 0, st>>>((const float*)dy, (const float*)y, (const float*)z, (float*)dzh, C, sums);
   else
     relu_bwd_stats_kernel<bf16><<<B, ch_threads(C), 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)z, (bf16*)dzh, C, sums);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kbk_mask_bwd_stats_supported(int C) { return vec_ok(C) ? 1 : 0; }
+
+int kbk_mask_bwd_stats(void* d_inout, const void* z, const float* ma, const float* mb, float* board_sum, int B, int C,
+                       int dtype, double* sums, cudaStream_t st) {
+  KB_CHECK_ARG(vec_ok(C), "mask_bwd_stats: unsupported channel count %d", C);
+  if (B == 0) return KB_OK;
+  if (dtype == KB_F32)
+    relu_bwd_stats_vec_kernel<float><<<B, 256, 0, st>>>((const float*)d_inout, (const float*)z, (const float*)z, (float*)d_inout, C, ma, mb, board_sum, sums);
+  else
+    relu_bwd_stats_vec_kernel<bf16><<<B, 256, 0, st>>>((const bf16*)d_inout, (const bf16*)z, (const bf16*)z, (bf16*)d_inout, C, ma, mb, board_sum, sums);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

@@ -113,6 +113,11 @@ int kbk_block_bwd_dx(const PassDArgs& a, cudaStream_t st);  // pass D
 // stem / generic: dzh = dy * (y > 0), channel sums of dzh and dzh*z   (y = post-activation, z = raw)
 int kbk_relu_bwd_stats(const void* dy, const void* y, const void* z, void* dzh, long long rows, int C, int dtype,
                        double* sums, cudaStream_t st);
+// data-gradient tail when it is NOT fused in the conv epilogue: d = d * [z*ma+mb > 0] in place, channel sums of the
+// masked d and d*z, board sums of the unmasked d (the gpool-bias gradient). Needs kbk_mask_bwd_stats_supported(C).
+int kbk_mask_bwd_stats_supported(int C);
+int kbk_mask_bwd_stats(void* d_inout, const void* z, const float* ma, const float* mb, float* board_sum, int B, int C,
+                       int dtype, double* sums, cudaStream_t st);
 // fp32 [M][C] variant for the policy head (mask by act > 0)
 int kbk_relu_bwd_stats_f32(float* d_inout, const float* act, const float* z, long long M, int C, double* sums,
                            cudaStream_t st);

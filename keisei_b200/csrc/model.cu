@@ -475,10 +475,19 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
     KB_TRY(kbk_block_bwd_dz2(pb, st));
     // conv2: weight gradient, then data gradient with the BN1/ReLU/gpool-bias backward fused in its epilogue
     KB_TRY(wgrad3x3(m, bw.a1, t1, G(pi_blk(i, 3)), C, C, C, use_tc, num_sms, w.wg_ws, w.wg_ws_bytes, st));
-    ConvEpi e = epi_base();
-    e.mask_src = bw.z1; e.mask_a = w.bn_a(l1); e.mask_b = w.bn_b(l1);
-    e.ch_sum = w.dsums; e.ch_dot = w.dsums + C; e.board_sum = w.dg; e.board_scale = 1.f;
-    KB_TRY(conv3x3(m, t1, wp.wd(i, 1), t2, C, C, e, use_tc, num_sms, st));
+    // The fused epilogue (mask + statistics inside the conv) is latency-bound on its 2-byte mask loads for the
+    // tcgen05 kernel (profiles/): there the tail runs as one vectorised pass after a plain data-gradient conv.
+    const bool tc_conv = use_tc && B >= 3 && kbk_conv3x3_tc_supported(C, C, dtype);
+    if (tc_conv && kbk_mask_bwd_stats_supported(C)) {
+      ConvEpi e = epi_base();
+      KB_TRY(conv3x3(m, t1, wp.wd(i, 1), t2, C, C, e, use_tc, num_sms, st));
+      KB_TRY(kbk_mask_bwd_stats(t2, bw.z1, w.bn_a(l1), w.bn_b(l1), w.dg, B, C, dtype, w.dsums, st));
+    } else {
+      ConvEpi e = epi_base();
+      e.mask_src = bw.z1; e.mask_a = w.bn_a(l1); e.mask_b = w.bn_b(l1);
+      e.ch_sum = w.dsums; e.ch_dot = w.dsums + C; e.board_sum = w.dg; e.board_scale = 1.f;
+      KB_TRY(conv3x3(m, t1, wp.wd(i, 1), t2, C, C, e, use_tc, num_sms, st));
+    }
     KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(pi_blk(i, 1)), w.bn_mean(l1), w.bn_invstd(l1), k1, k2, k3,
                                G(pi_blk(i, 1)), G(pi_blk(i, 2)), C, st));
     // global-pool-bias MLP backward -> gradient wrt the pool statistics of the block input
