@@ -128,6 +128,16 @@ int kb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int Cin, i
 /* w (Cout,Cin,3,3) float32 -> wf (Cout,9,Cinp) and optional wd (Cinp,9,Cout) (flipped taps) in `dtype` */
 int kb_pack_conv_weight(const float* w, void* wf, void* wd, int Cout, int Cin, int Cinp, int dtype, kb_stream_t stream);
 
+/* ---- Linear / 1x1-conv layer on the tcgen05 path (nn.Linear at se_resnet.py:57-66, heads :119-130) ----
+ * w (N,K) float32 -> bf16 (Np,Kp) zero padded, Np % 128 == 0, Kp % 64 == 0. */
+int kb_pack_linear_weight(const float* w, void* out_bf16, int N, int K, int Np, int Kp, kb_stream_t stream);
+/* Y[m][n] = act((X[m][:] . W[n][:]) * scale[n] + bias[n]); X bf16 (M,Kp); out_f32 (M,ld_f) features < N and/or
+ * out_bf16 (M,ld_b) features < nb_store (zeros for n >= N); group_rows > 0: bf16 row m lives at
+ * (m / group_rows) * group_pitch + (m % group_rows) * ld_b (the padded policy-logit buffer). */
+int kb_linear_tc(const void* x_bf16, long long M, int Kp, const void* w_bf16, int N, int Np, const float* scale,
+                 const float* bias, int relu, float* out_f32, long long ld_f, void* out_bf16, long long ld_b,
+                 int nb_store, int group_rows, long long group_pitch, int num_sms, kb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,3 +41,16 @@ extern "C" int kb_pack_conv_weight(const float* w, void* wf, void* wd, int Cout,
   KB_CHECK_ARG(w && wf && Cinp >= Cin, "kb_pack_conv_weight: bad arguments");
   return kbk_pack_conv_weight(w, wf, wd, Cout, Cin, Cinp, dtype, stream);
 }
+
+extern "C" int kb_pack_linear_weight(const float* w, void* out_bf16, int N, int K, int Np, int Kp, cudaStream_t stream) {
+  KB_CHECK_ARG(w && out_bf16 && Np >= N && Kp >= K, "kb_pack_linear_weight: bad arguments");
+  return kbk_pack_linear_weight(w, out_bf16, N, K, Np, Kp, stream);
+}
+
+extern "C" int kb_linear_tc(const void* x_bf16, long long M, int Kp, const void* w_bf16, int N, int Np, const float* scale,
+                            const float* bias, int relu, float* out_f32, long long ld_f, void* out_bf16, long long ld_b,
+                            int nb_store, int group_rows, long long group_pitch, int num_sms, cudaStream_t stream) {
+  KB_CHECK_ARG(x_bf16 && w_bf16 && (out_f32 || out_bf16), "kb_linear_tc: null pointer");
+  return kbk_linear_tc(x_bf16, M, Kp, w_bf16, N, Np, scale, bias, relu, out_f32, ld_f, out_bf16, ld_b, nb_store, group_rows,
+                       group_pitch, num_sms, stream);
+}

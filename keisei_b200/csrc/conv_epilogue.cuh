@@ -63,15 +63,21 @@ struct ConvEpiThread {
   }
   // element index of (board b, pixel p) for this thread's channel
   __device__ __forceinline__ size_t index(int b, int p) const { return ((size_t)b * 81 + p) * Cout + c; }
-  // one accumulator value: local board j (compile-time after unrolling), global board b, pixel p.
-  // `msrc` = the mask-source element at index(b, p), pre-loaded by the caller (lets the tcgen05
-  // epilogue keep several chunks of loads in flight); ignored when the mask feature is off.
-  __device__ __forceinline__ void value(int j, int b, int p, float acc, T* __restrict__ out, float msrc = 0.f) {
+  // Per-board cursor: all 64-bit address arithmetic and the per-(board, channel) bias load happen once per
+  // board here, so the per-pixel code is a handful of FP ops and one store at a constant row offset.
+  T* optr;
+  float gb;
+  __device__ __forceinline__ void begin_board(int b, T* __restrict__ out) {
+    optr = out + index(b, 0);
+    gb = on(kEpiGbias, e.gbias != nullptr) ? e.gbias[(size_t)b * Cout + c] : 0.f;
+  }
+  // one accumulator value of the current board: local board j and pixel p are compile-time after unrolling.
+  // `msrc` = the mask-source element of this pixel, pre-loaded by the caller; ignored when the mask is off.
+  __device__ __forceinline__ void value(int j, int p, float acc, float msrc = 0.f) {
     float v = acc;
     if (on(kEpiAffine, e.scale != nullptr)) v = fmaf(v, sc, sh);
     if (on(kEpiRelu, e.relu != 0)) v = fmaxf(v, 0.f);
-    if (on(kEpiGbias, e.gbias != nullptr)) v += e.gbias[(size_t)b * Cout + c];
-    const size_t idx = ((size_t)b * 81 + p) * Cout + c;
+    if (on(kEpiGbias, e.gbias != nullptr)) v += gb;
     if (on(kEpiMask, e.mask_src != nullptr)) {
       pre[j] += v;
       if (!(fmaf(msrc, ma, mb) > 0.f)) v = 0.f;
@@ -79,7 +85,7 @@ struct ConvEpiThread {
       msrc = 0.f;
     }
     const T stored = kb_from_float<T>(v);
-    out[idx] = stored;
+    optr[(unsigned)p * (unsigned)Cout] = stored;
     const float r = kb_to_float<T>(stored);
     s[j] += r;
     if (on(kEpiSumSq, e.ch_sumsq != nullptr)) ss[j] = fmaf(r, r, ss[j]);

@@ -92,10 +92,11 @@ __global__ void __launch_bounds__(CT) conv3x3_simt_kernel(const T* __restrict__ 
   }
   if (c_ok) {
     ConvEpiThread<T, 1, kEpiDynamic> et(epi, c, Cout, B);
+    et.begin_board(b, out);
 #pragma unroll
     for (int p = 0; p < 81; ++p) {
       const float ms = epi.mask_src ? kb_to_float<T>(((const T*)epi.mask_src)[et.index(b, p)]) : 0.f;
-      et.value(0, b, p, acc[p], out, ms);
+      et.value(0, p, acc[p], ms);
     }
     et.board_done(0, b);
     et.finish(1);

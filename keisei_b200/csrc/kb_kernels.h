@@ -21,6 +21,15 @@ long long kbk_conv3x3_wgrad_tc_ws_bytes(int Cin, int Cout, int num_sms);
 int kbk_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true, float* ws,
                          long long ws_bytes, int num_sms, cudaStream_t st);
 
+// ---- gemm_tc.cu (tcgen05 Linear / 1x1-conv layers, bf16) ----
+int kbk_pack_linear_weight(const float* w, void* out_bf16, int N, int K, int Np, int Kp, cudaStream_t st);
+int kbk_cast_rows_bf16(const float* in, void* out_bf16, long long rows, int cols, int ld, cudaStream_t st);
+// Y[m][n] = act((X[m][:] . W[n][:]) * scale[n] + bias[n]); X bf16 [M][Kp], W bf16 [Np][Kp] (zero padded);
+// out_f32 [M][ld_f] (n < N) and/or out_bf16 [M][ld_b] (n < nb_store, zeros for n >= N; optionally board-pitched rows)
+int kbk_linear_tc(const void* x, long long M, int Kp, const void* w, int N, int Np, const float* scale, const float* bias,
+                  int relu, float* out_f32, long long ld_f, void* out_bf, long long ld_b, int nb_store, int group_rows,
+                  long long group_pitch, int num_sms, cudaStream_t st);
+
 // ---- gemm_simt.cu ----
 struct GemmArgs {
   // C[M,N] = epilogue( prologue(op(A))[M,K] * op(B)[K,N] )

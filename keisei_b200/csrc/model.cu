@@ -57,6 +57,11 @@ struct WPack {
   char* blocks;     // per block: conv1 wf, conv1 wd, conv2 wf, conv2 wd
   float* bn_eval;   // [2*nb+2][2][Cmax]
   int Cmax;
+  // bf16 zero-padded Linear / 1x1-conv weights for the tcgen05 GEMM ([Np][Kp], Np % 128 == 0, Kp % 64 == 0)
+  char* lin; size_t lin_blk_bytes, o_g1, o_g2, o_s1, o_s2, o_heads, o_p1, o_p2, o_v1, o_v2, o_c1, o_c2;
+  int Gp, Gk, Cp, Sp, Sk, C2p, Pp, Pk, Vp, Vk, Qp, Qk;
+  void* lin_blk(int i, size_t off) const { return lin + (size_t)i * lin_blk_bytes + off; }
+  void* lin_head(size_t off) const { return lin + o_heads + off; }
   size_t total;
   void* wf(int i, int conv) const { return blocks + ((size_t)i * 4 + conv * 2) * conv_bytes; }
   void* wd(int i, int conv) const { return blocks + ((size_t)i * 4 + conv * 2 + 1) * conv_bytes; }
@@ -75,6 +80,22 @@ WPack make_wpack(const Dims& m, void* base) {
   w.blocks = (char*)b.take((size_t)m.nb * 4 * w.conv_bytes);
   w.Cmax = m.C > m.Pc ? m.C : m.Pc;
   w.bn_eval = b.f32((size_t)(2 * m.nb + 2) * 2 * w.Cmax);
+  auto up = [](int v, int a) { return (v + a - 1) / a * a; };
+  w.Gp = up(m.G, 128); w.Gk = up(m.G, 64); w.Cp = up(m.C, 128); w.Sp = up(m.S, 128); w.Sk = up(m.S, 64);
+  w.C2p = up(2 * m.C, 128); w.Pp = up(m.Pc, 128); w.Pk = up(m.Pc, 64); w.Vp = up(m.V, 128); w.Vk = up(m.V, 64);
+  w.Qp = up(m.S2, 128); w.Qk = up(m.S2, 64);
+  const int K3 = up(3 * m.C, 64), Kc = up(m.C, 64);
+  size_t o = 0;
+  auto place = [&](size_t& slot, size_t rows, size_t cols) { slot = o; o += (rows * cols * 2 + 1023) & ~(size_t)1023; };
+  place(w.o_g1, w.Gp, K3); place(w.o_g2, w.Cp, w.Gk); place(w.o_s1, w.Sp, Kc); place(w.o_s2, w.C2p, w.Sk);
+  w.lin_blk_bytes = o;
+  o = 0;
+  place(w.o_p1, w.Pp, Kc); place(w.o_p2, 256, w.Pk); place(w.o_v1, w.Vp, K3); place(w.o_v2, 128, w.Vk);
+  place(w.o_c1, w.Qp, K3); place(w.o_c2, 128, w.Qk);
+  const size_t heads_bytes = o;
+  b.off = (b.off + 1023) & ~(size_t)1023;
+  w.lin = (char*)b.take((size_t)m.nb * w.lin_blk_bytes + heads_bytes);
+  w.o_heads = (size_t)m.nb * w.lin_blk_bytes;
   w.total = b.off + 256;
   return w;
 }
@@ -98,6 +119,7 @@ struct Ws {
   void *d0, *d1, *d2;
   float *s_du, *s_duz, *dse_in, *dg, *dse, *dseh, *dgh, *dpool, *k123, *dp1, *dvh, *dsh;
   float* wg_ws; long long wg_ws_bytes;  // tcgen05 weight-gradient partial tiles
+  void *pool_bf, *gh_bf, *sein_bf, *seh_bf, *vh_bf, *sh_bf, *p1act_bf;  // bf16 operands of the tcgen05 Linear layers
   int Cmax;
   size_t total;
   float* pool(const Dims& m, int i) const { return pools + (size_t)i * m.B * 3 * m.C; }
@@ -120,6 +142,12 @@ void carve(const Dims& m, void* base, int training, Ws& w, BlockWs* blk_storage)
   w.vh = b.f32(B * m.V);
   w.sh = b.f32(B * m.S2);
   w.bn = b.f32((size_t)(2 * m.nb + 2) * 4 * w.Cmax);
+  {
+    auto up64 = [](int v) { return (size_t)((v + 63) / 64 * 64); };
+    w.pool_bf = b.take(B * up64(3 * m.C) * 2); w.gh_bf = b.take(B * up64(m.G) * 2); w.sein_bf = b.take(B * up64(m.C) * 2);
+    w.seh_bf = b.take(B * up64(m.S) * 2); w.vh_bf = b.take(B * up64(m.V) * 2); w.sh_bf = b.take(B * up64(m.S2) * 2);
+    w.p1act_bf = b.take((size_t)m.M * up64(m.Pc) * 2);
+  }
   if (training) {
     w.z0 = b.take(m.act()); w.x0 = b.take(m.act());
     w.pools = b.f32((size_t)(m.nb + 1) * B * 3 * m.C);
@@ -165,6 +193,9 @@ int wgrad3x3(const Dims& m, const void* x, const void* dy, float* dw, int Cin, i
     return kbk_conv3x3_wgrad_tc(x, dy, dw, m.B, Cin, Cout, Cin_true, wg_ws, wg_ws_bytes, num_sms, st);
   return kbk_conv3x3_wgrad_simt(x, dy, dw, m.B, Cin, Cout, Cin_true, m.dtype, st);
 }
+
+// tcgen05 Linear path: bf16 activations, every K a multiple of 64 after padding the small hidden sizes
+bool lin_tc(const Dims& m, int use_tc) { return use_tc && m.dtype == KB_BF16 && m.C % 64 == 0 && m.B >= 1; }
 
 GemmArgs gemm_base() { GemmArgs g; memset(&g, 0, sizeof(g)); g.splitk = 1; return g; }
 ConvEpi epi_base() { ConvEpi e; memset(&e, 0, sizeof(e)); e.board_scale = 1.f; return e; }
@@ -258,6 +289,22 @@ extern "C" int kb_seresnet_pack_weights(const kb_seresnet_desc* d, const void* c
     KB_TRY(bn(2 + 2 * i, pi_blk(i, 4), bi_blk(i, 3), m.C));
   }
   KB_TRY(bn(2 * m.nb + 1, pi_head(m, 1), bi_pol(m, 0), m.Pc));
+  if (dtype == KB_BF16 && m.C % 64 == 0) {
+    auto P = [&](int i) { return (const float*)params[i]; };
+    const int K3 = 3 * m.C;
+    for (int i = 0; i < m.nb; ++i) {
+      KB_TRY(kbk_pack_linear_weight(P(pi_blk(i, 6)), w.lin_blk(i, w.o_g1), m.G, K3, w.Gp, K3, st));
+      KB_TRY(kbk_pack_linear_weight(P(pi_blk(i, 8)), w.lin_blk(i, w.o_g2), m.C, m.G, w.Cp, w.Gk, st));
+      KB_TRY(kbk_pack_linear_weight(P(pi_blk(i, 10)), w.lin_blk(i, w.o_s1), m.S, m.C, w.Sp, m.C, st));
+      KB_TRY(kbk_pack_linear_weight(P(pi_blk(i, 12)), w.lin_blk(i, w.o_s2), 2 * m.C, m.S, w.C2p, w.Sk, st));
+    }
+    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 0)), w.lin_head(w.o_p1), m.Pc, m.C, w.Pp, m.C, st));
+    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 3)), w.lin_head(w.o_p2), 139, m.Pc, 256, w.Pk, st));
+    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 5)), w.lin_head(w.o_v1), m.V, K3, w.Vp, K3, st));
+    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 7)), w.lin_head(w.o_v2), 3, m.V, 128, w.Vk, st));
+    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 9)), w.lin_head(w.o_c1), m.S2, K3, w.Qp, K3, st));
+    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 11)), w.lin_head(w.o_c2), 1, m.S2, 128, w.Qk, st));
+  }
   return KB_OK;
 }
 
@@ -312,13 +359,22 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
     x_cur = w.ea; pool_cur = w.epool_a;
   }
 
+  const bool ltc = lin_tc(m, use_tc);
   // ---- residual tower ----
   for (int i = 0; i < m.nb; ++i) {
     BlockWs& bw = training ? blks[i] : blks[0];
     const int l1 = 1 + 2 * i, l2 = 2 + 2 * i;
     // global-pool bias from the block INPUT: g = W2 relu(W1 pool + b1) + b2   (se_resnet.py:73-78)
-    KB_TRY(linear_fwd(pool_cur, KB_F32, 3 * C, B, 3 * C, P(pi_blk(i, 6)), m.G, P(pi_blk(i, 7)), 1, bw.gh, KB_F32, m.G, st));
-    KB_TRY(linear_fwd(bw.gh, KB_F32, m.G, B, m.G, P(pi_blk(i, 8)), C, P(pi_blk(i, 9)), 0, w.g, KB_F32, C, st));
+    if (ltc) {
+      KB_TRY(kbk_cast_rows_bf16(pool_cur, w.pool_bf, B, 3 * C, 3 * C, st));
+      KB_TRY(kbk_linear_tc(w.pool_bf, B, 3 * C, wp.lin_blk(i, wp.o_g1), m.G, wp.Gp, nullptr, P(pi_blk(i, 7)), 1, bw.gh, m.G,
+                           w.gh_bf, wp.Gk, wp.Gk, 0, 0, num_sms, st));
+      KB_TRY(kbk_linear_tc(w.gh_bf, B, wp.Gk, wp.lin_blk(i, wp.o_g2), C, wp.Cp, nullptr, P(pi_blk(i, 9)), 0, w.g, C, nullptr, 0, 0,
+                           0, 0, num_sms, st));
+    } else {
+      KB_TRY(linear_fwd(pool_cur, KB_F32, 3 * C, B, 3 * C, P(pi_blk(i, 6)), m.G, P(pi_blk(i, 7)), 1, bw.gh, KB_F32, m.G, st));
+      KB_TRY(linear_fwd(bw.gh, KB_F32, m.G, B, m.G, P(pi_blk(i, 8)), C, P(pi_blk(i, 9)), 0, w.g, KB_F32, C, st));
+    }
     const void* z2; void* xout; float* pool_next; const float* se_in;
     if (training) {
       ConvEpi e = epi_base();
@@ -346,8 +402,16 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
       se_in = bw.bmean2;  // BN affine already applied in the conv epilogue
     }
     // SE excite: (scale, shift) = W2 relu(W1 se_in + b1) + b2   (se_resnet.py:83-86)
-    KB_TRY(linear_fwd(se_in, KB_F32, C, B, C, P(pi_blk(i, 10)), m.S, P(pi_blk(i, 11)), 1, bw.seh, KB_F32, m.S, st));
-    KB_TRY(linear_fwd(bw.seh, KB_F32, m.S, B, m.S, P(pi_blk(i, 12)), 2 * C, P(pi_blk(i, 13)), 0, bw.se, KB_F32, 2 * C, st));
+    if (ltc) {
+      KB_TRY(kbk_cast_rows_bf16(se_in, w.sein_bf, B, C, C, st));
+      KB_TRY(kbk_linear_tc(w.sein_bf, B, C, wp.lin_blk(i, wp.o_s1), m.S, wp.Sp, nullptr, P(pi_blk(i, 11)), 1, bw.seh, m.S,
+                           w.seh_bf, wp.Sk, wp.Sk, 0, 0, num_sms, st));
+      KB_TRY(kbk_linear_tc(w.seh_bf, B, wp.Sk, wp.lin_blk(i, wp.o_s2), 2 * C, wp.C2p, nullptr, P(pi_blk(i, 13)), 0, bw.se, 2 * C,
+                           nullptr, 0, 0, 0, 0, num_sms, st));
+    } else {
+      KB_TRY(linear_fwd(se_in, KB_F32, C, B, C, P(pi_blk(i, 10)), m.S, P(pi_blk(i, 11)), 1, bw.seh, KB_F32, m.S, st));
+      KB_TRY(linear_fwd(bw.seh, KB_F32, m.S, B, m.S, P(pi_blk(i, 12)), 2 * C, P(pi_blk(i, 13)), 0, bw.se, KB_F32, 2 * C, st));
+    }
     // x' = relu(bn2(z2) * sigmoid(scale) + shift + x), plus the pool statistics of x' for the next consumer
     ApplyArgs a; memset(&a, 0, sizeof(a));
     a.z = z2; a.a = training ? w.bn_a(l2) : nullptr; a.b = training ? w.bn_b(l2) : nullptr; a.se = bw.se; a.res = x_cur;
@@ -358,6 +422,35 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
 
   // ---- policy head: 1x1 conv -> BN -> ReLU -> 1x1 conv + bias, written NHWC into the padded logits buffer ----
   const int Pc = m.Pc, M = (int)m.M;
+  if (ltc) {
+    const float *pa = wp.bn_a(LP), *pb = wp.bn_b(LP);
+    if (training) {
+      KB_TRY(kbk_linear_tc(x_cur, m.M, C, wp.lin_head(wp.o_p1), Pc, wp.Pp, nullptr, nullptr, 0, w.p1raw, Pc, nullptr, 0, 0, 0, 0,
+                           num_sms, st));
+      KB_TRY(kbk_rows_stats(w.p1raw, m.M, Pc, w.dsums, st));
+      KB_TRY(bn_fin(LP, pi_head(m, 1), bi_pol(m, 0), Pc));
+      ApplyArgs a; memset(&a, 0, sizeof(a));
+      a.z = w.p1raw; a.a = w.bn_a(LP); a.b = w.bn_b(LP); a.out = w.p1act; a.B = B; a.C = Pc; a.dtype = KB_F32;
+      KB_TRY(kbk_apply(a, st));
+      KB_TRY(kbk_cast_rows_bf16(w.p1act, w.p1act_bf, m.M, Pc, wp.Pk, st));
+    } else {
+      // eval: folded BatchNorm + ReLU ride in the GEMM epilogue
+      KB_TRY(kbk_linear_tc(x_cur, m.M, C, wp.lin_head(wp.o_p1), Pc, wp.Pp, pa, pb, 1, nullptr, 0, w.p1act_bf, wp.Pk, wp.Pk, 0, 0,
+                           num_sms, st));
+    }
+    KB_TRY(kbk_linear_tc(w.p1act_bf, m.M, wp.Pk, wp.lin_head(wp.o_p2), 139, 256, nullptr, P(pi_head(m, 4)), 0, nullptr, 0,
+                         policy_out, 139, 139, 81, policy_pitch, num_sms, st));
+    KB_TRY(kbk_cast_rows_bf16(pool_cur, w.pool_bf, B, 3 * C, 3 * C, st));
+    KB_TRY(kbk_linear_tc(w.pool_bf, B, 3 * C, wp.lin_head(wp.o_v1), m.V, wp.Vp, nullptr, P(pi_head(m, 6)), 1, w.vh, m.V, w.vh_bf,
+                         wp.Vk, wp.Vk, 0, 0, num_sms, st));
+    KB_TRY(kbk_linear_tc(w.vh_bf, B, wp.Vk, wp.lin_head(wp.o_v2), 3, 128, nullptr, P(pi_head(m, 8)), 0, value_out, 3, nullptr, 0, 0,
+                         0, 0, num_sms, st));
+    KB_TRY(kbk_linear_tc(w.pool_bf, B, 3 * C, wp.lin_head(wp.o_c1), m.S2, wp.Qp, nullptr, P(pi_head(m, 10)), 1, w.sh, m.S2, w.sh_bf,
+                         wp.Qk, wp.Qk, 0, 0, num_sms, st));
+    KB_TRY(kbk_linear_tc(w.sh_bf, B, wp.Qk, wp.lin_head(wp.o_c2), 1, 128, nullptr, P(pi_head(m, 12)), 0, score_out, 1, nullptr, 0, 0,
+                         0, 0, num_sms, st));
+    return KB_OK;
+  }
   KB_TRY(linear_fwd(x_cur, dtype, C, M, C, P(pi_head(m, 0)), Pc, nullptr, 0, w.p1raw, KB_F32, Pc, st));
   const float *pa, *pb;
   if (training) {

@@ -350,7 +350,7 @@ class KataGoPPOAlgorithm:
                 actions, log_probs, values, legal, flags = policy_ops.policy_sample(
                     flat, legal_masks, output.value_logits if fused_value else None, output.score_lead, alpha,
                     seed=self._sample_seed)
-                if int(flags[0].item()) != 0:
+                if self.strict_guards and int(flags[0].item()) != 0:
                     zero_envs = (legal == 0).nonzero(as_tuple=True)[0].tolist()
                     raise RuntimeError(f"Environments {zero_envs} have zero legal actions — "
                                        f"all-False legal mask would produce NaN")
@@ -474,14 +474,14 @@ class KataGoPPOAlgorithm:
 
     def _step_fused(self, km: SEResNetModel, obs, mb, value_adapter):
         """Forward, losses, backward through the C-ABI with ONE flat gradient buffer."""
-        params, buffers = km._tables()
+        tables = km._ptr_tables()
+        params, buffers = tables.params, tables.buffers
         dtype = km._act_dtype(obs.device)
         code = 0 if dtype == torch.float32 else 1
         wpack = km._packed(params, buffers, dtype)
-        desc = km._desc()
         with torch.no_grad():
-            policy_buf, value, score, ws, new_stats = model_ops.seresnet_forward(
-                obs, params, buffers, wpack, desc, True, code, bool(km.use_tensor_cores))
+            policy_buf, value, score, ws, new_stats = model_ops.seresnet_forward_raw(
+                obs, tables, wpack, True, code, bool(km.use_tensor_cores))
             km._store_running_stats(buffers, new_stats)
         policy_buf.requires_grad_(True); value.requires_grad_(True); score.requires_grad_(True)
         loss, pl, vl, sl, ent, flags = self._losses(policy_buf[:, :model_ops.POLICY_A], value, score, mb, value_adapter)
@@ -489,8 +489,8 @@ class KataGoPPOAlgorithm:
         self.optimizer.zero_grad(set_to_none=True)
         self.scaler.scale(loss).backward()
         with torch.no_grad():
-            flat = model_ops.seresnet_backward(params, wpack, ws, policy_buf.grad, value.grad, score.grad, desc, code,
-                                               bool(km.use_tensor_cores))
+            flat = model_ops.seresnet_backward_raw(tables, wpack, ws, policy_buf.grad, value.grad, score.grad, code,
+                                                   bool(km.use_tensor_cores), km._grad_sizes)
             if self.grad_sync is not None:
                 self.grad_sync.all_reduce_flat(flat)
             off = 0

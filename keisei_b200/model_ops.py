@@ -41,6 +41,10 @@ _lib.register_signature("kb_conv3x3_wgrad", c_int, [_P, _P, _P, c_int, c_int, c_
 _lib.register_signature("kb_conv3x3_wgrad_ws_bytes", c_longlong, [c_int, c_int, c_int])
 _lib.register_signature("kb_pack_conv_weight", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P])
 
+_lib.register_signature("kb_pack_linear_weight", c_int, [_P, _P, c_int, c_int, c_int, c_int, _P])
+_lib.register_signature("kb_linear_tc", c_int, [_P, c_longlong, c_int, _P, c_int, c_int, _P, _P, c_int, _P, c_longlong, _P,
+                                                 c_longlong, c_int, c_int, c_longlong, c_int, _P])
+
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 _DT_INV = {0: torch.float32, 1: torch.bfloat16}
 _sm_count_cache: dict[int, int] = {}
@@ -99,6 +103,79 @@ def pack_weights(params, buffers, desc: List[int], dtype_code: int, wpack: torch
         rc = _lib.load().kb_seresnet_pack_weights(ctypes.byref(d), pt, bt, dtype_code, wpack.data_ptr(),
                                                   wpack.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "kb_seresnet_pack_weights")
+
+
+class PointerTables:
+    """Host arrays of device pointers for a model's parameters / buffers, built once and reused while
+    the tensors keep their storage (building them costs ~1 ms for the 822 tensors of a 40-block net)."""
+
+    def __init__(self, params, buffers, desc: List[int]) -> None:
+        self.desc = _desc(desc)
+        _check_tables(params, buffers, self.desc)
+        self.params, self.buffers = params, buffers
+        self.pt, self.bt = _ptr_table(params), _ptr_table(buffers)
+        self._probe = (params[0].data_ptr(), params[-1].data_ptr(), buffers[0].data_ptr(), buffers[-1].data_ptr())
+
+    def valid(self) -> bool:
+        p, b = self.params, self.buffers
+        return self._probe == (p[0].data_ptr(), p[-1].data_ptr(), b[0].data_ptr(), b[-1].data_ptr())
+
+
+@torch.no_grad()
+def seresnet_forward_raw(obs: torch.Tensor, tables: PointerTables, wpack: torch.Tensor, training: bool, dtype_code: int,
+                         use_tc: bool):
+    """The C call without the torch.library dispatcher (no-grad callers: rollout, the fused trainer step).
+    Returns (policy_buf, value_logits, score_lead, workspace, new_stats)."""
+    if not obs.is_cuda:
+        raise _lib.KeiseiB200Error("keisei_b200 seresnet_forward needs CUDA tensors")
+    d = tables.desc
+    dev = obs.device
+    B = obs.shape[0]
+    obs_c = obs.detach().to(torch.float32).contiguous()
+    ws = torch.empty(int(_lib.load().kb_seresnet_workspace_bytes(ctypes.byref(d), B, 1 if training else 0, dtype_code)),
+                     dtype=torch.uint8, device=dev)
+    policy = torch.empty((B, POLICY_PITCH), dtype=_DT_INV[dtype_code], device=dev)
+    policy[:, POLICY_A:].zero_()
+    value = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    score = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    cmax = max(d.channels, d.policy_channels)
+    new_stats = torch.empty((2 * d.num_blocks + 2, 2, cmax) if training else (0,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().kb_seresnet_forward(
+            ctypes.byref(d), tables.pt, tables.bt, new_stats.data_ptr() if training else None, wpack.data_ptr(),
+            obs_c.data_ptr(), B, 1 if training else 0, dtype_code, ws.data_ptr(), ws.numel(), policy.data_ptr(),
+            POLICY_PITCH, value.data_ptr(), score.data_ptr(), 1 if use_tc else 0, sm_count(dev), _lib.stream_ptr(dev))
+    _lib.check(rc, "kb_seresnet_forward")
+    return policy, value, score, ws, new_stats
+
+
+@torch.no_grad()
+def seresnet_backward_raw(tables: PointerTables, wpack: torch.Tensor, ws: torch.Tensor, dpolicy: torch.Tensor,
+                          dvalue: torch.Tensor, dscore: torch.Tensor, dtype_code: int, use_tc: bool,
+                          sizes: List[int] | None = None) -> torch.Tensor:
+    """The C backward without the dispatcher. Returns the flat fp32 gradient (parameter-table order)."""
+    d = tables.desc
+    dev = ws.device
+    B = dvalue.shape[0]
+    dpol = dpolicy
+    if dpol.dtype != _DT_INV[dtype_code] or dpol.stride(1) != 1 or dpol.stride(0) < POLICY_A:
+        dpol = dpol.to(_DT_INV[dtype_code]).contiguous()
+    dv = dvalue.to(torch.float32).contiguous()
+    ds = dscore.to(torch.float32).reshape(B).contiguous()
+    if sizes is None:
+        sizes = [p.numel() for p in tables.params]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    gt = (c_void_p * len(sizes))()
+    base, off = flat.data_ptr(), 0
+    for i, n in enumerate(sizes):
+        gt[i] = base + 4 * off
+        off += n
+    with torch.cuda.device(dev):
+        rc = _lib.load().kb_seresnet_backward(
+            ctypes.byref(d), tables.pt, wpack.data_ptr(), B, dtype_code, ws.data_ptr(), ws.numel(), dpol.data_ptr(),
+            dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), _lib.stream_ptr(dev))
+    _lib.check(rc, "kb_seresnet_backward")
+    return flat
 
 
 @torch.library.custom_op("keisei_b200::seresnet_forward", mutates_args=())
@@ -252,3 +329,27 @@ def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, cin_true: int | None = None
                                           sm_count(x.device), _lib.stream_ptr(x.device))
     _lib.check(rc, "kb_conv3x3_wgrad")
     return dw
+
+
+@torch.no_grad()
+def linear_tc(x: torch.Tensor, w: torch.Tensor, bias=None, scale=None, relu: bool = False, want_f32: bool = True,
+              want_bf16: bool = False):
+    """Y = act((x @ w.T) * scale + bias) on the tcgen05 path. x (M,K) any float dtype (cast to bf16, K padded to 64),
+    w (N,K) fp32. Returns (y_f32 (M,N) | None, y_bf16 (M, ceil64(N)) | None)."""
+    M, K = x.shape
+    N = w.shape[0]
+    Kp, Np, Nb = (K + 63) // 64 * 64, (N + 127) // 128 * 128, (N + 63) // 64 * 64
+    dev = x.device
+    xb = torch.zeros((M, Kp), dtype=torch.bfloat16, device=dev)
+    xb[:, :K] = x
+    wp = torch.empty((Np, Kp), dtype=torch.bfloat16, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.kb_pack_linear_weight(w.float().contiguous().data_ptr(), wp.data_ptr(), N, K, Np, Kp, _lib.stream_ptr(dev)),
+                   "kb_pack_linear_weight")
+        yf = torch.empty((M, N), dtype=torch.float32, device=dev) if want_f32 else None
+        yb = torch.empty((M, Nb), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+        _lib.check(lib.kb_linear_tc(xb.data_ptr(), M, Kp, wp.data_ptr(), N, Np, _lib.ptr(scale), _lib.ptr(bias), 1 if relu else 0,
+                                    _lib.ptr(yf), N, _lib.ptr(yb), Nb, Nb, 0, 0, sm_count(dev), _lib.stream_ptr(dev)),
+                   "kb_linear_tc")
+    return yf, yb

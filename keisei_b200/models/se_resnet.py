@@ -98,6 +98,8 @@ class SEResNetModel(KataGoBaseModel):
         self._wpack_key: tuple | None = None
         self.use_tensor_cores: bool = True   # tcgen05 convolutions whenever the bf16 path is selected
         self.last_policy_buffer: torch.Tensor | None = None  # padded (B, 11264) logits of the last CUDA forward
+        self._tables_cache = None
+        self._grad_sizes: list[int] = []
 
     # ---- kernel plumbing ---------------------------------------------------------------------
     def _desc(self) -> list[int]:
@@ -111,6 +113,20 @@ class SEResNetModel(KataGoBaseModel):
 
     def _tables(self) -> tuple[list[torch.Tensor], list[torch.Tensor]]:
         return list(self.parameters()), list(self.buffers())
+
+    def _ptr_tables(self) -> "model_ops.PointerTables":
+        """Cached parameter/buffer pointer tables (rebuilt when the module is moved or re-materialised)."""
+        t = self._tables_cache
+        if t is None or not t.valid():
+            params, buffers = self._tables()
+            t = self._tables_cache = model_ops.PointerTables(params, buffers, self._desc())
+            self._grad_sizes = [p.numel() for p in params]
+        return t
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): storages change
+        self._tables_cache = None
+        self._wpack_key = None
+        return super()._apply(fn, *args, **kwargs)
 
     def _act_dtype(self, device: torch.device) -> torch.dtype:
         if self._amp_enabled and self._amp_dtype == torch.bfloat16:
@@ -136,13 +152,20 @@ class SEResNetModel(KataGoBaseModel):
         if not self.kernel_supported():
             raise model_ops._lib.KeiseiB200Error(
                 f"SEResNetParams {self.params} not supported by the CUDA kernels (channels must be a multiple of 4)")
-        params, buffers = self._tables()
+        tables = self._ptr_tables()
+        params, buffers = tables.params, tables.buffers
         dtype = self._act_dtype(obs.device)
         code = 0 if dtype == torch.float32 else 1
         training = self.training
         wpack = self._packed(params, buffers, dtype)
-        policy_buf, value, score, _ws, new_stats = model_ops.seresnet_forward(
-            obs, params, buffers, wpack, self._desc(), training, code, bool(self.use_tensor_cores))
+        if torch.is_grad_enabled() and training:
+            # autograd path: the torch.library op (gradients flow to every parameter)
+            policy_buf, value, score, _ws, new_stats = model_ops.seresnet_forward(
+                obs, params, buffers, wpack, self._desc(), training, code, bool(self.use_tensor_cores))
+        else:
+            # no graph needed (rollout / evaluation): straight to the C-ABI, no dispatcher overhead
+            policy_buf, value, score, _ws, new_stats = model_ops.seresnet_forward_raw(
+                obs, tables, wpack, training, code, bool(self.use_tensor_cores))
         if training:
             self._store_running_stats(buffers, new_stats)
         B = obs.shape[0]

@@ -100,3 +100,19 @@ def test_conv3x3_wgrad_tc(B, Cin, Cout, ct):
     assert rel(got.cpu().numpy(), want) < 2e-3
     got0 = model_ops.conv3x3_wgrad(nhwc(x).to(DEV), nhwc(dy).to(DEV), cin_true=ct, backend=0)
     assert rel(got.cpu().numpy(), got0.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.parametrize("M,K,N", [(7, 768, 128), (4096, 768, 128), (300, 128, 256), (1000, 256, 16), (513, 16, 512),
+                                   (81 * 40, 256, 32), (5000, 32, 139), (64, 256, 3), (64, 128, 1)])
+def test_linear_tc(M, K, N):
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5)
+    b = torch.randn(N, generator=g)
+    sc = torch.rand(N, generator=g) + 0.5
+    want = torch.relu((x.double() @ w.bfloat16().double().T) * sc.double() + b.double())
+    yf, yb = model_ops.linear_tc(x.to(DEV), w.to(DEV), bias=b.to(DEV), scale=sc.to(DEV), relu=True, want_bf16=True)
+    torch.cuda.synchronize()
+    assert rel(yf.cpu().numpy(), want.numpy()) < 2e-3
+    assert rel(yb[:, :N].float().cpu().numpy(), want.numpy()) < 1e-2
+    assert torch.all(yb[:, N:] == 0)  # K padding of the consumer layer is valid
