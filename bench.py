@@ -177,7 +177,7 @@ def run_reference(args) -> None:
     t0 = time.perf_counter()
     cb = cpu_baseline(batch=batch, reps=max(1, min(args.steps, 3)))
     line = {"metric": "rollout positions/s", "value": cb["value"], "unit": "positions/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * ROLLOUT_B / cb["value"], "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1000.0 * batch / cb["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "SE-ResNet 40x256 rollout inference (select_actions), batch 4096 synthetic boards per GPU",
                        "timed_sample": f"batch {batch} on host cores, scaled per position"},

@@ -294,8 +294,9 @@ __global__ void relu_bwd_stats_f32_kernel(float* __restrict__ d, const float* __
 // warp reads whole 128..512-byte rows; per-(board, channel) reductions finish through shared memory.
 // Used when C % 8 == 0 and 256 % (C/8) == 0 (C = 16, 32, 64, 128, 256, 512 ...).
 // =================================================================================================
-template <typename T> struct V8;
-template <> struct V8<float> {
+constexpr int kVW = 4;  // channels per thread in the vectorised kernels (4 -> half the register state of 8)
+template <typename T, int W> struct VV;
+template <> struct VV<float, 8> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -306,58 +307,83 @@ template <> struct V8<float> {
   }
   static __device__ __forceinline__ void round(float (&)[8]) {}
 };
-template <> struct V8<bf16> {
+template <> struct VV<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  static __device__ __forceinline__ void round(float (&)[4]) {}
+};
+__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> struct VV<bf16, 8> {
   static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
   }
-  static __device__ __forceinline__ uint32_t pack(float a, float b) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
-  }
   static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
-    *reinterpret_cast<uint4*>(p) = make_uint4(pack(v[0], v[1]), pack(v[2], v[3]), pack(v[4], v[5]), pack(v[6], v[7]));
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf162(v[0], v[1]), pack_bf162(v[2], v[3]), pack_bf162(v[4], v[5]), pack_bf162(v[6], v[7]));
   }
   static __device__ __forceinline__ void round(float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
   }
 };
-__device__ __forceinline__ void ldf8(const float* p, float (&v)[8]) { V8<float>::load(p, v); }
+template <> struct VV<bf16, 4> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+    v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[4]) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf162(v[0], v[1]), pack_bf162(v[2], v[3]));
+  }
+  static __device__ __forceinline__ void round(float (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+  }
+};
+template <typename T> using V8 = VV<T, kVW>;
+__device__ __forceinline__ void ldf8(const float* p, float (&v)[kVW]) { VV<float, kVW>::load(p, v); }
 
 // SE = squeeze-excite scale/shift + residual present; POOL = emit global-pool statistics of the output.
 template <typename T, bool SE, bool POOL>
 __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
-  __shared__ float red[POOL ? 4 : 1][POOL ? 2048 : 1];  // [quantity][lane * C + c]
-  const int C = g.C, C8 = C >> 3, NPL = 256 / C8;
-  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
-  float a_[8], b_[8], sg[8], sf[8], gb[8];
+  __shared__ float red[POOL ? 4 : 1][POOL ? 256 * kVW : 1];  // [quantity][lane * C + c]
+  const int C = g.C, C8 = C / kVW, NPL = 256 / C8;
+  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
+  float a_[kVW], b_[kVW], sg[kVW], sf[kVW], gb[kVW];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { a_[i] = 1.f; b_[i] = 0.f; sg[i] = 1.f; sf[i] = 0.f; gb[i] = 0.f; }
+  for (int i = 0; i < kVW; ++i) { a_[i] = 1.f; b_[i] = 0.f; sg[i] = 1.f; sf[i] = 0.f; gb[i] = 0.f; }
   if (g.a) { ldf8(g.a + c0, a_); ldf8(g.b + c0, b_); }
   if (SE) {
     ldf8(g.se + (size_t)b * 2 * C + c0, sg); ldf8(g.se + (size_t)b * 2 * C + C + c0, sf);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kVW; ++i) {
       sg[i] = sigmoidf_(sg[i]);
       // fold the BN affine into the SE scale/shift: (z*a+b)*sg+sf = z*(a*sg) + (b*sg+sf)
       sf[i] = fmaf(b_[i], sg[i], sf[i]); sg[i] *= a_[i];
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { sg[i] = a_[i]; sf[i] = b_[i]; }
+    for (int i = 0; i < kVW; ++i) { sg[i] = a_[i]; sf[i] = b_[i]; }
   }
   if (g.gbias) ldf8(g.gbias + (size_t)b * C + c0, gb);
   const size_t base = (size_t)b * 81 * C + c0;
-  float s[8], mx[8], k0[8], ds[8], dss[8];
+  float s[kVW], mx[kVW], k0[kVW], ds[kVW], dss[kVW];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s[i] = 0.f; mx[i] = -INFINITY; k0[i] = 0.f; ds[i] = 0.f; dss[i] = 0.f; }
+  for (int i = 0; i < kVW; ++i) { s[i] = 0.f; mx[i] = -INFINITY; k0[i] = 0.f; ds[i] = 0.f; dss[i] = 0.f; }
   int cnt = 0;
-  auto finish = [&](float (&v)[8], const float (&r)[8], int p) {
+  auto finish = [&](float (&v)[kVW], const float (&r)[kVW], int p) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kVW; ++i) {
       float t = fmaf(v[i], sg[i], sf[i]);
       if (SE) t += r[i];
       v[i] = fmaxf(t, 0.f) + gb[i];
@@ -366,7 +392,7 @@ __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
     if (POOL) {
       V8<T>::round(v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kVW; ++i) {
         if (cnt == 0) k0[i] = v[i];
         const float d = v[i] - k0[i];
         s[i] += v[i]; mx[i] = fmaxf(mx[i], v[i]); ds[i] += d; dss[i] = fmaf(d, d, dss[i]);
@@ -376,7 +402,7 @@ __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
   };
   for (int p = pl; p < 81; p += 2 * NPL) {  // two pixels per iteration: 2-4 independent 16-byte loads in flight
     const bool two = p + NPL < 81;
-    float v0[8], r0[8], v1[8], r1[8];
+    float v0[kVW], r0[kVW], v1[kVW], r1[kVW];
     V8<T>::load((const T*)g.z + base + (size_t)p * C, v0);
     if (SE) V8<T>::load((const T*)g.res + base + (size_t)p * C, r0);
     if (two) {
@@ -390,7 +416,7 @@ __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
   // per-lane (count, mean, M2) -> Chan's parallel merge across the NPL pixel lanes
   const float fc = (float)cnt;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < kVW; ++i) {
     const int o = pl * C + c0 + i;
     red[0][o] = s[i];
     red[POOL ? 1 : 0][o] = mx[i];
@@ -415,23 +441,23 @@ __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) block_bwd_reduce_vec_kernel(BlockBwdArgs g) {
-  __shared__ float red[2][2048];
-  const int C = g.C, C8 = C >> 3, NPL = 256 / C8;
-  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
+  __shared__ float red[2][256 * kVW];
+  const int C = g.C, C8 = C / kVW, NPL = 256 / C8;
+  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
   const size_t base = (size_t)b * 81 * C + c0;
-  float s[8], sz[8];
+  float s[kVW], sz[kVW];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s[i] = 0.f; sz[i] = 0.f; }
+  for (int i = 0; i < kVW; ++i) { s[i] = 0.f; sz[i] = 0.f; }
   for (int p = pl; p < 81; p += NPL) {
-    float d[8], x[8], z[8];
+    float d[kVW], x[kVW], z[kVW];
     V8<T>::load((const T*)g.dxp + base + (size_t)p * C, d);
     V8<T>::load((const T*)g.xp + base + (size_t)p * C, x);
     V8<T>::load((const T*)g.z2 + base + (size_t)p * C, z);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const float du = x[i] > 0.f ? d[i] : 0.f; s[i] += du; sz[i] = fmaf(du, z[i], sz[i]); }
+    for (int i = 0; i < kVW; ++i) { const float du = x[i] > 0.f ? d[i] : 0.f; s[i] += du; sz[i] = fmaf(du, z[i], sz[i]); }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { red[0][pl * C + c0 + i] = s[i]; red[1][pl * C + c0 + i] = sz[i]; }
+  for (int i = 0; i < kVW; ++i) { red[0][pl * C + c0 + i] = s[i]; red[1][pl * C + c0 + i] = sz[i]; }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += 256) {
     float a = 0.f, q = 0.f;
@@ -443,21 +469,21 @@ __global__ void __launch_bounds__(256) block_bwd_reduce_vec_kernel(BlockBwdArgs 
 
 template <typename T>
 __global__ void __launch_bounds__(256) block_bwd_dz2_vec_kernel(PassBArgs g) {
-  const int C = g.C, C8 = C >> 3, NPL = 256 / C8;
-  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
+  const int C = g.C, C8 = C / kVW, NPL = 256 / C8;
+  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
   const size_t base = (size_t)b * 81 * C + c0;
-  float sg[8], dm[8], k1[8], k2[8], k3[8];
+  float sg[kVW], dm[kVW], k1[kVW], k2[kVW], k3[kVW];
   ldf8(g.se + (size_t)b * 2 * C + c0, sg); ldf8(g.dse_in + (size_t)b * C + c0, dm);
   ldf8(g.k1 + c0, k1); ldf8(g.k2 + c0, k2); ldf8(g.k3 + c0, k3);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sg[i] = sigmoidf_(sg[i]); dm[i] *= (1.f / 81.f); }
+  for (int i = 0; i < kVW; ++i) { sg[i] = sigmoidf_(sg[i]); dm[i] *= (1.f / 81.f); }
   for (int p = pl; p < 81; p += NPL) {
-    float d[8], x[8], z[8];
+    float d[kVW], x[kVW], z[kVW];
     V8<T>::load((const T*)g.dxp + base + (size_t)p * C, d);
     V8<T>::load((const T*)g.xp + base + (size_t)p * C, x);
     V8<T>::load((const T*)g.z2 + base + (size_t)p * C, z);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kVW; ++i) {
       const float du = x[i] > 0.f ? d[i] : 0.f;
       d[i] = k1[i] * fmaf(du, sg[i], dm[i]) - k2[i] * z[i] - k3[i];
     }
@@ -467,33 +493,33 @@ __global__ void __launch_bounds__(256) block_bwd_dz2_vec_kernel(PassBArgs g) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) block_bwd_dx_vec_kernel(PassDArgs g) {
-  __shared__ float red[2048];
-  const int C = g.C, C8 = C >> 3, NPL = 256 / C8;
-  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
+  __shared__ float red[256 * kVW];
+  const int C = g.C, C8 = C / kVW, NPL = 256 / C8;
+  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
   const size_t base = (size_t)b * 81 * C + c0;
-  float gmean[8], gmax[8], gstd[8], mean[8], mx[8];
+  float gmean[kVW], gmax[kVW], gstd[kVW], mean[kVW], mx[kVW];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { gmean[i] = 0.f; gmax[i] = 0.f; gstd[i] = 0.f; mean[i] = 0.f; mx[i] = 0.f; }
+  for (int i = 0; i < kVW; ++i) { gmean[i] = 0.f; gmax[i] = 0.f; gstd[i] = 0.f; mean[i] = 0.f; mx[i] = 0.f; }
   if (g.dpool) {
     const float* pr = g.pool + (size_t)b * 3 * C;
     const float* dp = g.dpool + (size_t)b * 3 * C;
-    float sd[8], dmean[8], dmaxv[8], dstd[8];
+    float sd[kVW], dmean[kVW], dmaxv[kVW], dstd[kVW];
     ldf8(pr + c0, mean); ldf8(pr + C + c0, mx); ldf8(pr + 2 * C + c0, sd);
     ldf8(dp + c0, dmean); ldf8(dp + C + c0, dmaxv); ldf8(dp + 2 * C + c0, dstd);
-    float ties[8];
+    float ties[kVW];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ties[i] = 0.f;
+    for (int i = 0; i < kVW; ++i) ties[i] = 0.f;
     for (int p = pl; p < 81; p += NPL) {
-      float x[8];
+      float x[kVW];
       V8<T>::load((const T*)g.x + base + (size_t)p * C, x);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ties[i] += (x[i] == mx[i]) ? 1.f : 0.f;
+      for (int i = 0; i < kVW; ++i) ties[i] += (x[i] == mx[i]) ? 1.f : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) red[pl * C + c0 + i] = ties[i];
+    for (int i = 0; i < kVW; ++i) red[pl * C + c0 + i] = ties[i];
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kVW; ++i) {
       float t = 0.f;
       for (int l = 0; l < NPL; ++l) t += red[l * C + c0 + i];
       gmean[i] = dmean[i] * (1.f / 81.f);
@@ -502,25 +528,25 @@ __global__ void __launch_bounds__(256) block_bwd_dx_vec_kernel(PassDArgs g) {
     }
   }
   for (int p = pl; p < 81; p += NPL) {
-    float v[8], t[8], y[8];
+    float v[kVW], t[kVW], y[kVW];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    for (int i = 0; i < kVW; ++i) v[i] = 0.f;
     if (g.dxc) V8<T>::load((const T*)g.dxc + base + (size_t)p * C, v);
     if (g.dxp) {
       V8<T>::load((const T*)g.dxp + base + (size_t)p * C, t);
       if (g.xp) {
         V8<T>::load((const T*)g.xp + base + (size_t)p * C, y);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += y[i] > 0.f ? t[i] : 0.f;
+        for (int i = 0; i < kVW; ++i) v[i] += y[i] > 0.f ? t[i] : 0.f;
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += t[i];
+        for (int i = 0; i < kVW; ++i) v[i] += t[i];
       }
     }
     if (g.dpool) {
       V8<T>::load((const T*)g.x + base + (size_t)p * C, t);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += gmean[i] + (t[i] == mx[i] ? gmax[i] : 0.f) + gstd[i] * (t[i] - mean[i]);
+      for (int i = 0; i < kVW; ++i) v[i] += gmean[i] + (t[i] == mx[i] ? gmax[i] : 0.f) + gstd[i] * (t[i] - mean[i]);
     }
     V8<T>::store((T*)g.dx + base + (size_t)p * C, v);
   }
@@ -534,18 +560,18 @@ __global__ void __launch_bounds__(256) relu_bwd_stats_vec_kernel(const T* dy, co
                                                                    const T* __restrict__ z, T* dzh, int C,
                                                                    const float* __restrict__ ma, const float* __restrict__ mb,
                                                                    float* __restrict__ board_sum, double* sums) {
-  __shared__ float red[3][2048];
-  const int C8 = C >> 3, NPL = 256 / C8;
-  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * 8;
+  __shared__ float red[3][256 * kVW];
+  const int C8 = C / kVW, NPL = 256 / C8;
+  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
   const size_t base = (size_t)b * 81 * C + c0;
   const bool same = (y == z);
-  float s1[8], s2[8], s0[8], fa[8], fb[8];
+  float s1[kVW], s2[kVW], s0[kVW], fa[kVW], fb[kVW];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; s0[i] = 0.f; fa[i] = 1.f; fb[i] = 0.f; }
+  for (int i = 0; i < kVW; ++i) { s1[i] = 0.f; s2[i] = 0.f; s0[i] = 0.f; fa[i] = 1.f; fb[i] = 0.f; }
   if (ma) { ldf8(ma + c0, fa); ldf8(mb + c0, fb); }
   for (int p = pl; p < 81; p += 2 * NPL) {
     const bool two = p + NPL < 81;
-    float d0[8], a0[8], z0[8], d1[8], a1[8], z1[8];
+    float d0[kVW], a0[kVW], z0[kVW], d1[kVW], a1[kVW], z1[kVW];
     V8<T>::load(dy + base + (size_t)p * C, d0);
     V8<T>::load(y + base + (size_t)p * C, a0);
     if (!same) V8<T>::load(z + base + (size_t)p * C, z0);
@@ -555,7 +581,7 @@ __global__ void __launch_bounds__(256) relu_bwd_stats_vec_kernel(const T* dy, co
       if (!same) V8<T>::load(z + base + (size_t)(p + NPL) * C, z1);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kVW; ++i) {
       s0[i] += d0[i];
       if (same) z0[i] = a0[i];
       d0[i] = fmaf(a0[i], fa[i], fb[i]) > 0.f ? d0[i] : 0.f;
@@ -563,10 +589,10 @@ __global__ void __launch_bounds__(256) relu_bwd_stats_vec_kernel(const T* dy, co
     V8<T>::store(dzh + base + (size_t)p * C, d0);
     V8<T>::round(d0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s1[i] += d0[i]; s2[i] = fmaf(d0[i], z0[i], s2[i]); }
+    for (int i = 0; i < kVW; ++i) { s1[i] += d0[i]; s2[i] = fmaf(d0[i], z0[i], s2[i]); }
     if (two) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kVW; ++i) {
         s0[i] += d1[i];
         if (same) z1[i] = a1[i];
         d1[i] = fmaf(a1[i], fa[i], fb[i]) > 0.f ? d1[i] : 0.f;
@@ -574,11 +600,11 @@ __global__ void __launch_bounds__(256) relu_bwd_stats_vec_kernel(const T* dy, co
       V8<T>::store(dzh + base + (size_t)(p + NPL) * C, d1);
       V8<T>::round(d1);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s1[i] += d1[i]; s2[i] = fmaf(d1[i], z1[i], s2[i]); }
+      for (int i = 0; i < kVW; ++i) { s1[i] += d1[i]; s2[i] = fmaf(d1[i], z1[i], s2[i]); }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { red[0][pl * C + c0 + i] = s1[i]; red[1][pl * C + c0 + i] = s2[i]; red[2][pl * C + c0 + i] = s0[i]; }
+  for (int i = 0; i < kVW; ++i) { red[0][pl * C + c0 + i] = s1[i]; red[1][pl * C + c0 + i] = s2[i]; red[2][pl * C + c0 + i] = s0[i]; }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += 256) {
     float a = 0.f, q = 0.f, u = 0.f;
@@ -594,17 +620,17 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_vec_kernel(T* __restrict__ d
                                                                  const float* __restrict__ k1, const float* __restrict__ k2,
                                                                  const float* __restrict__ k3, long long n8, int C) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)((i * 8) % C);
-    float v[8], zz[8], a[8], b[8], e[8];
-    V8<T>::load(d + i * 8, v); V8<T>::load(z + i * 8, zz);
+    const int c0 = (int)((i * kVW) % C);
+    float v[kVW], zz[kVW], a[kVW], b[kVW], e[kVW];
+    V8<T>::load(d + i * kVW, v); V8<T>::load(z + i * kVW, zz);
     ldf8(k1 + c0, a); ldf8(k2 + c0, b); ldf8(k3 + c0, e);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = a[j] * v[j] - b[j] * zz[j] - e[j];
-    V8<T>::store(d + i * 8, v);
+    for (int j = 0; j < kVW; ++j) v[j] = a[j] * v[j] - b[j] * zz[j] - e[j];
+    V8<T>::store(d + i * kVW, v);
   }
 }
 
-inline bool vec_ok(int C) { return C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0; }
+inline bool vec_ok(int C) { return C % kVW == 0 && C / kVW <= 256 && 256 % (C / kVW) == 0; }
 
 inline int ch_threads(int C) { return ((C + 31) / 32) * 32; }
 
@@ -712,8 +738,8 @@ int kbk_bn_bwd_apply(void* d, const void* z, const float* k1, const float* k2, c
                      int dtype, cudaStream_t st) {
   const long long n = rows * C;
   if (n == 0) return KB_OK;
-  if (C % 8 == 0) {
-    const long long n8 = n / 8;
+  if (C % kVW == 0) {
+    const long long n8 = n / kVW;
     const int grid8 = (int)min((long long)148 * 16, (n8 + 255) / 256);
     if (dtype == KB_F32) bn_bwd_apply_vec_kernel<float><<<grid8, 256, 0, st>>>((float*)d, (const float*)z, k1, k2, k3, n8, C);
     else bn_bwd_apply_vec_kernel<bf16><<<grid8, 256, 0, st>>>((bf16*)d, (const bf16*)z, k1, k2, k3, n8, C);
