@@ -211,7 +211,10 @@ def conv_roofline(device, reps: int = 20) -> dict:
     achieved = flops / (ms * 1e-3) / 1e12
     peak = pk["bf16_tflops_sustained"]
     return {"kernel": "conv3x3_tc_kernel (tcgen05, 256->256, B=4096, 3 boards x 128 ch tiles)", "bound": "tensor",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture in
+            # profiles/ncu_full_r1_rollout_kernels.csv (171-175 MB read + 131 MB written; algorithmic 2 x 169.9 MB)
+            "traffic": 306.0e6, "traffic_unit": "bytes/launch",
             "ms_per_launch": ms, "flops_per_launch": flops, "peak_source": f"{pk['source']} bf16_tflops_sustained"}
 
 

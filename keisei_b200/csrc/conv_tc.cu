@@ -23,6 +23,7 @@
 // Replaces F.conv2d at reference se_resnet.py:50,52,110 (forward) and its data gradient (same
 // kernel on the flipped/transposed weight pack). The weight gradient is conv3x3_wgrad below.
 #include <cuda.h>
+#include <stdlib.h>
 #include "kb_common.cuh"
 #include "tc_ptx.cuh"
 #include "conv_epilogue.cuh"
@@ -48,9 +49,15 @@ using namespace tcptx;
 constexpr uint32_t kIdescF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
 // ---------------------------------------------------------------- forward / dgrad kernel
-template <int F>
+// kCl = true: launched as clusters of 2 CTAs that own the two 128-channel halves of the SAME board group.
+// The activation (B) tile is identical for both, so each CTA fetches only part of it (rank 0: boards 0-1,
+// rank 1: board 2) and TMA-multicasts it into both CTAs' shared memory: L2 -> SM operand traffic per tile
+// drops from 1.77 MB to 1.14 MB (ncu: the single-CTA kernel's MMA issuer stalls on the full barriers).
+// Stage release then needs both consumers: tcgen05.commit multicasts its arrive to both CTAs' empty barrier.
+template <int F, bool kCl>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                  const __grid_constant__ CUtensorMap map_x2, const __grid_constant__ CUtensorMap map_x1,
                   bf16* __restrict__ out, int B, int Cin, int Cout, int num_tiles, ConvEpi epi) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -67,13 +74,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   const int n_ct = Cout / kTileM;
   const int kb_per_tap = Cin / kBlockK;
   const int num_kb = 9 * kb_per_tap;
+  // tile walk: single CTA -> tiles blockIdx.x, +gridDim.x, ...; cluster -> this CTA always takes channel half
+  // `crank` of board groups cluster_id, +num_clusters, ... (both CTAs of a cluster run the same group sequence)
+  const uint32_t crank = kCl ? cluster_ctarank() : 0u;
+  const int t_first = kCl ? (int)(blockIdx.x >> 1) * 2 + (int)crank : (int)blockIdx.x;
+  const int t_step = (int)gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kCl ? 2 : 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     fence_barrier_init();
     tma_prefetch_desc(&map_w);
-    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(kCl ? (crank == 0 ? &map_x2 : &map_x1) : &map_x);
   }
   if (warp == 1) {  // TMEM owner: all 512 columns (two 256-column accumulators)
     tmem_alloc(holder, 512);
@@ -81,6 +93,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (kCl) cluster_sync_all();  // peer barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
 
@@ -88,15 +101,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = t_first; t < num_tiles; t += t_step) {
         const int ct = t % n_ct, grp = t / n_ct;
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / kb_per_tap, cc = kb - tap * kb_per_tap;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_wait(empty_bar(stage), phase ^ 1u);  // cluster: both CTAs' MMAs have retired this stage
           mbar_arrive_expect_tx(full_bar(stage), kABytes + kBTxBytes);
           const uint32_t a_dst = smem_base + stage * kStageBytes;
           tma_load_2d(a_dst, &map_w, full_bar(stage), kb * kBlockK, ct * kTileM);
-          tma_load_4d(a_dst + kABytes, &map_x, full_bar(stage), cc * kBlockK, tap % 3 - 1, tap / 3 - 1, grp * kBoards);
+          if (kCl) {
+            if (crank == 0)
+              tma_load_4d_mc(a_dst + kABytes, &map_x2, full_bar(stage), cc * kBlockK, tap % 3 - 1, tap / 3 - 1, grp * kBoards, (uint16_t)3);
+            else
+              tma_load_4d_mc(a_dst + kABytes + 2 * 81 * 128, &map_x1, full_bar(stage), cc * kBlockK, tap % 3 - 1, tap / 3 - 1,
+                             grp * kBoards + 2, (uint16_t)3);
+          } else {
+            tma_load_4d(a_dst + kABytes, &map_x, full_bar(stage), cc * kBlockK, tap % 3 - 1, tap / 3 - 1, grp * kBoards);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -106,7 +127,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = t_first; t < num_tiles; t += t_step, ++it) {
         const int buf = it & 1;
         const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(buf), tphase ^ 1u);  // epilogue has drained this accumulator
@@ -123,7 +144,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
             umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdescF16, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          if (kCl) umma_commit_mc(empty_bar(stage), (uint16_t)3);  // both producers write into this stage
+          else umma_commit(empty_bar(stage));                      // frees the smem stage when these MMAs retire
           if (kb == num_kb - 1) umma_commit(tfull_bar(buf));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -133,7 +155,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     // ===== epilogue: thread = output channel =====
     const int lane_grp = warp & 3;  // TMEM lanes 32*lane_grp .. +31 are the ones this warp may read
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = t_first; t < num_tiles; t += t_step, ++it) {
       const int ct = t % n_ct, grp = t / n_ct;
       const int buf = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
@@ -194,6 +216,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (kCl) cluster_sync_all();  // the peer may still multicast into / signal this CTA until it is done too
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -390,14 +413,27 @@ int make_act_map(CUtensorMap* m, const void* x, int B, int C, int boards_per_box
 }
 
 template <int F>
-int launch_fwd(const CUtensorMap& mw, const CUtensorMap& mx, bf16* out, int B, int Cin, int Cout, int num_tiles,
-               const ConvEpi& epi, int grid, cudaStream_t st) {
+int launch_fwd(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& mx2, const CUtensorMap& mx1, bf16* out, int B,
+               int Cin, int Cout, int num_tiles, const ConvEpi& epi, int grid, bool cluster, cudaStream_t st) {
   static bool attr_set = false;  // per instantiation; idempotent
   if (!attr_set) {
-    KB_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    KB_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    KB_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  conv3x3_tc_kernel<F><<<grid, kThreads, kSmemBytes, st>>>(mw, mx, out, B, Cin, Cout, num_tiles, epi);
+  if (cluster) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<F, true>, mw, mx, mx2, mx1, out, B, Cin, Cout, num_tiles, epi));
+    kb_count_launch();
+    return KB_OK;
+  }
+  conv3x3_tc_kernel<F, false><<<grid, kThreads, kSmemBytes, st>>>(mw, mx, mx2, mx1, out, B, Cin, Cout, num_tiles, epi);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }
@@ -412,25 +448,37 @@ int kbk_conv3x3_tc(const void* in, const void* w, void* out, int B, int Cin, int
                    cudaStream_t st) {
   KB_CHECK_ARG(kbk_conv3x3_tc_supported(Cin, Cout, KB_BF16), "conv3x3_tc: unsupported shape Cin=%d Cout=%d", Cin, Cout);
   if (B == 0) return KB_OK;
-  CUtensorMap mw, mx;
+  CUtensorMap mw, mx, mx2, mx1;
   if (int r = make_weight_map(&mw, w, Cout, 9 * Cin)) return r;
   if (int r = make_act_map(&mx, in, B, Cin, kBoards)) return r;
+  if (int r = make_act_map(&mx2, in, B, Cin, 2)) return r;
+  if (int r = make_act_map(&mx1, in, B, Cin, 1)) return r;
   const int groups = kb_ceil_div(B, kBoards);
-  const int num_tiles = groups * (Cout / kTileM);
+  const int n_ct = Cout / kTileM;
+  const int num_tiles = groups * n_ct;
   if (num_sms <= 0) num_sms = 148;
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  // cluster-of-2 multicast variant: the two channel halves of a board group share the activation tile.
+  // Measured on B200 (round 1): parity-green but NOT faster (0.300 vs 0.293 ms per 256->256 conv at B=4096) — the
+  // MMA issuer's full-barrier stalls are TMA latency vs the 4-stage (192 KB) ring, not L2 bytes. Opt-in only.
+  static int cluster_env = -1;
+  if (cluster_env < 0) { const char* e = getenv("KB_CONV_CLUSTER"); cluster_env = (e && e[0] == '1') ? 1 : 0; }
+  const bool cluster = cluster_env && n_ct == 2 && groups >= 2;
+  int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  if (cluster) { grid = 2 * (groups < num_sms / 2 ? groups : num_sms / 2); }
   bf16* o = (bf16*)out;
   const int f = conv_epi_features(epi);
+#define KB_FWD(FF) return launch_fwd<FF>(mw, mx, mx2, mx1, o, B, Cin, Cout, num_tiles, epi, grid, cluster, st)
   switch (f) {
-    case 0: return launch_fwd<0>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
-    case kEpiSum | kEpiSumSq: return launch_fwd<kEpiSum | kEpiSumSq>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
-    case kEpiSum | kEpiSumSq | kEpiBoard: return launch_fwd<kEpiSum | kEpiSumSq | kEpiBoard>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
-    case kEpiAffine | kEpiRelu | kEpiGbias: return launch_fwd<kEpiAffine | kEpiRelu | kEpiGbias>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
-    case kEpiAffine | kEpiRelu | kEpiPool: return launch_fwd<kEpiAffine | kEpiRelu | kEpiPool>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
-    case kEpiAffine | kEpiBoard: return launch_fwd<kEpiAffine | kEpiBoard>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
-    case kEpiMask | kEpiSum | kEpiDot | kEpiBoard: return launch_fwd<kEpiMask | kEpiSum | kEpiDot | kEpiBoard>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
-    default: return launch_fwd<kEpiDynamic>(mw, mx, o, B, Cin, Cout, num_tiles, epi, grid, st);
+    case 0: KB_FWD(0);
+    case kEpiSum | kEpiSumSq: KB_FWD(kEpiSum | kEpiSumSq);
+    case kEpiSum | kEpiSumSq | kEpiBoard: KB_FWD(kEpiSum | kEpiSumSq | kEpiBoard);
+    case kEpiAffine | kEpiRelu | kEpiGbias: KB_FWD(kEpiAffine | kEpiRelu | kEpiGbias);
+    case kEpiAffine | kEpiRelu | kEpiPool: KB_FWD(kEpiAffine | kEpiRelu | kEpiPool);
+    case kEpiAffine | kEpiBoard: KB_FWD(kEpiAffine | kEpiBoard);
+    case kEpiMask | kEpiSum | kEpiDot | kEpiBoard: KB_FWD(kEpiMask | kEpiSum | kEpiDot | kEpiBoard);
+    default: KB_FWD(kEpiDynamic);
   }
+#undef KB_FWD
 }
 
 long long kbk_conv3x3_wgrad_tc_ws_bytes(int Cin, int Cout, int num_sms) {
