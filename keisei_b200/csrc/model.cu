@@ -9,6 +9,7 @@
 // policy_conv2.{weight,bias}, value_fc{1,2}.{weight,bias}, score_fc{1,2}.{weight,bias}.
 // Buffer table order: input_bn.{running_mean,running_var,num_batches_tracked}, per block bn1.*, bn2.*,
 // then policy_bn1.*.
+#include <stdlib.h>
 #include "kb_common.cuh"
 #include "kb_kernels.h"
 #include "../../include/keisei_b200.h"
@@ -440,15 +441,12 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
     }
     KB_TRY(kbk_linear_tc(w.p1act_bf, m.M, wp.Pk, wp.lin_head(wp.o_p2), 139, 256, nullptr, P(pi_head(m, 4)), 0, nullptr, 0,
                          policy_out, 139, 139, 81, policy_pitch, num_sms, st));
-    KB_TRY(kbk_cast_rows_bf16(pool_cur, w.pool_bf, B, 3 * C, 3 * C, st));
-    KB_TRY(kbk_linear_tc(w.pool_bf, B, 3 * C, wp.lin_head(wp.o_v1), m.V, wp.Vp, nullptr, P(pi_head(m, 6)), 1, w.vh, m.V, w.vh_bf,
-                         wp.Vk, wp.Vk, 0, 0, num_sms, st));
-    KB_TRY(kbk_linear_tc(w.vh_bf, B, wp.Vk, wp.lin_head(wp.o_v2), 3, 128, nullptr, P(pi_head(m, 8)), 0, value_out, 3, nullptr, 0, 0,
-                         0, 0, num_sms, st));
-    KB_TRY(kbk_linear_tc(w.pool_bf, B, 3 * C, wp.lin_head(wp.o_c1), m.S2, wp.Qp, nullptr, P(pi_head(m, 10)), 1, w.sh, m.S2, w.sh_bf,
-                         wp.Qk, wp.Qk, 0, 0, num_sms, st));
-    KB_TRY(kbk_linear_tc(w.sh_bf, B, wp.Qk, wp.lin_head(wp.o_c2), 1, 128, nullptr, P(pi_head(m, 12)), 0, score_out, 1, nullptr, 0, 0,
-                         0, 0, num_sms, st));
+    // value / score heads stay fp32 end to end (4 tiny GEMMs on the fp32 pool statistics): their logits are the
+    // smallest-magnitude outputs of the network and carry the 2e-2 bf16 parity bar with the least headroom
+    KB_TRY(linear_fwd(pool_cur, KB_F32, 3 * C, B, 3 * C, P(pi_head(m, 5)), m.V, P(pi_head(m, 6)), 1, w.vh, KB_F32, m.V, st));
+    KB_TRY(linear_fwd(w.vh, KB_F32, m.V, B, m.V, P(pi_head(m, 7)), 3, P(pi_head(m, 8)), 0, value_out, KB_F32, 3, st));
+    KB_TRY(linear_fwd(pool_cur, KB_F32, 3 * C, B, 3 * C, P(pi_head(m, 9)), m.S2, P(pi_head(m, 10)), 1, w.sh, KB_F32, m.S2, st));
+    KB_TRY(linear_fwd(w.sh, KB_F32, m.S2, B, m.S2, P(pi_head(m, 11)), 1, P(pi_head(m, 12)), 0, score_out, KB_F32, 1, st));
     return KB_OK;
   }
   KB_TRY(linear_fwd(x_cur, dtype, C, M, C, P(pi_head(m, 0)), Pc, nullptr, 0, w.p1raw, KB_F32, Pc, st));
@@ -571,7 +569,9 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
     // The fused epilogue (mask + statistics inside the conv) is latency-bound on its 2-byte mask loads for the
     // tcgen05 kernel (profiles/): there the tail runs as one vectorised pass after a plain data-gradient conv.
     const bool tc_conv = use_tc && B >= 3 && kbk_conv3x3_tc_supported(C, C, dtype);
-    if (tc_conv && kbk_mask_bwd_stats_supported(C)) {
+    static int fused_env = -1;
+    if (fused_env < 0) { const char* fe = getenv("KB_FUSED_DGRAD"); fused_env = (fe && fe[0] == '1') ? 1 : 0; }
+    if (tc_conv && kbk_mask_bwd_stats_supported(C) && !fused_env) {
       ConvEpi e = epi_base();
       KB_TRY(conv3x3(m, t1, wp.wd(i, 1), t2, C, C, e, use_tc, num_sms, st));
       KB_TRY(kbk_mask_bwd_stats(t2, bw.z1, w.bn_a(l1), w.bn_b(l1), w.dg, B, C, dtype, w.dsums, st));
