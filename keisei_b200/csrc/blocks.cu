@@ -22,7 +22,7 @@ __global__ void apply_kernel(ApplyArgs g) {
   const T* z = (const T*)g.z + (size_t)b * 81 * C + c;
   const T* res = g.res ? (const T*)g.res + (size_t)b * 81 * C + c : nullptr;
   T* out = (T*)g.out + (size_t)b * 81 * C + c;
-  float s = 0.f, mx = -INFINITY, k0 = 0.f, ds = 0.f, dss = 0.f;
+  float s = 0.f, mx = -INFINITY, k0 = 0.f, ds = 0.f, dss = 0.f, tie = 0.f;
 #pragma unroll 9
   for (int p = 0; p < 81; ++p) {
     float v = fmaf(kb_to_float<T>(z[(size_t)p * C]), a_, b_);
@@ -34,8 +34,10 @@ __global__ void apply_kernel(ApplyArgs g) {
     const float r = kb_to_float<T>(st);
     if (p == 0) k0 = r;
     const float d = r - k0;
+    tie = r > mx ? 1.f : (r == mx ? tie + 1.f : tie);
     s += r; mx = fmaxf(mx, r); ds += d; dss = fmaf(d, d, dss);
   }
+  if (g.pool && g.ties) g.ties[(size_t)b * C + c] = tie;
   if (g.pool) {
     const float dm = ds * (1.f / 81.f);
     float* pr = g.pool + (size_t)b * 3 * C;
@@ -356,7 +358,7 @@ __device__ __forceinline__ void ldf8(const float* p, float (&v)[kVW]) { VV<float
 // SE = squeeze-excite scale/shift + residual present; POOL = emit global-pool statistics of the output.
 template <typename T, bool SE, bool POOL>
 __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
-  __shared__ float red[POOL ? 4 : 1][POOL ? 256 * kVW : 1];  // [quantity][lane * C + c]
+  __shared__ float red[POOL ? 5 : 1][POOL ? 256 * kVW : 1];  // [quantity][lane * C + c]
   const int C = g.C, C8 = C / kVW, NPL = 256 / C8;
   const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
   float a_[kVW], b_[kVW], sg[kVW], sf[kVW], gb[kVW];
@@ -377,9 +379,9 @@ __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
   }
   if (g.gbias) ldf8(g.gbias + (size_t)b * C + c0, gb);
   const size_t base = (size_t)b * 81 * C + c0;
-  float s[kVW], mx[kVW], k0[kVW], ds[kVW], dss[kVW];
+  float s[kVW], mx[kVW], k0[kVW], ds[kVW], dss[kVW], tie[kVW];
 #pragma unroll
-  for (int i = 0; i < kVW; ++i) { s[i] = 0.f; mx[i] = -INFINITY; k0[i] = 0.f; ds[i] = 0.f; dss[i] = 0.f; }
+  for (int i = 0; i < kVW; ++i) { s[i] = 0.f; mx[i] = -INFINITY; k0[i] = 0.f; ds[i] = 0.f; dss[i] = 0.f; tie[i] = 0.f; }
   int cnt = 0;
   auto finish = [&](float (&v)[kVW], const float (&r)[kVW], int p) {
 #pragma unroll
@@ -395,7 +397,10 @@ __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
       for (int i = 0; i < kVW; ++i) {
         if (cnt == 0) k0[i] = v[i];
         const float d = v[i] - k0[i];
-        s[i] += v[i]; mx[i] = fmaxf(mx[i], v[i]); ds[i] += d; dss[i] = fmaf(d, d, dss[i]);
+        s[i] += v[i]; ds[i] += d; dss[i] = fmaf(d, d, dss[i]);
+        // running (max, number of elements equal to it): amax backward splits evenly across ties
+        tie[i] = v[i] > mx[i] ? 1.f : (v[i] == mx[i] ? tie[i] + 1.f : tie[i]);
+        mx[i] = fmaxf(mx[i], v[i]);
       }
       ++cnt;
     }
@@ -422,6 +427,7 @@ __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
     red[POOL ? 1 : 0][o] = mx[i];
     red[POOL ? 2 : 0][o] = cnt > 0 ? k0[i] + ds[i] / fc : 0.f;            // lane mean
     red[POOL ? 3 : 0][o] = cnt > 0 ? dss[i] - ds[i] * ds[i] / fc : 0.f;   // lane M2
+    red[POOL ? 4 : 0][o] = tie[i];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += 256) {
@@ -436,6 +442,11 @@ __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
     }
     float* pr = g.pool + (size_t)b * 3 * C;
     pr[c] = mean; pr[C + c] = M; pr[2 * C + c] = sqrtf(fmaxf(m2 * (1.f / 81.f), 0.f));
+    if (g.ties) {
+      float t = 0.f;
+      for (int l = 0; l < NPL; ++l) if (red[POOL ? 1 : 0][l * C + c] == M) t += red[POOL ? 4 : 0][l * C + c];
+      g.ties[(size_t)b * C + c] = t;
+    }
   }
 }
 
@@ -503,115 +514,149 @@ __global__ void __launch_bounds__(256) block_bwd_dx_vec_kernel(PassDArgs g) {
   if (g.dpool) {
     const float* pr = g.pool + (size_t)b * 3 * C;
     const float* dp = g.dpool + (size_t)b * 3 * C;
-    float sd[kVW], dmean[kVW], dmaxv[kVW], dstd[kVW];
+    float sd[kVW], dmean[kVW], dmaxv[kVW], dstd[kVW], ties[kVW];
     ldf8(pr + c0, mean); ldf8(pr + C + c0, mx); ldf8(pr + 2 * C + c0, sd);
     ldf8(dp + c0, dmean); ldf8(dp + C + c0, dmaxv); ldf8(dp + 2 * C + c0, dstd);
-    float ties[kVW];
+    if (g.ties) {
+      ldf8(g.ties + (size_t)b * C + c0, ties);  // counted by the forward apply kernel
+    } else {
+      float tl[kVW];
 #pragma unroll
-    for (int i = 0; i < kVW; ++i) ties[i] = 0.f;
-    for (int p = pl; p < 81; p += NPL) {
-      float x[kVW];
-      V8<T>::load((const T*)g.x + base + (size_t)p * C, x);
+      for (int i = 0; i < kVW; ++i) tl[i] = 0.f;
+      for (int p = pl; p < 81; p += NPL) {
+        float x[kVW];
+        V8<T>::load((const T*)g.x + base + (size_t)p * C, x);
 #pragma unroll
-      for (int i = 0; i < kVW; ++i) ties[i] += (x[i] == mx[i]) ? 1.f : 0.f;
-    }
+        for (int i = 0; i < kVW; ++i) tl[i] += (x[i] == mx[i]) ? 1.f : 0.f;
+      }
 #pragma unroll
-    for (int i = 0; i < kVW; ++i) red[pl * C + c0 + i] = ties[i];
-    __syncthreads();
+      for (int i = 0; i < kVW; ++i) red[pl * C + c0 + i] = tl[i];
+      __syncthreads();
 #pragma unroll
-    for (int i = 0; i < kVW; ++i) {
-      float t = 0.f;
-      for (int l = 0; l < NPL; ++l) t += red[l * C + c0 + i];
-      gmean[i] = dmean[i] * (1.f / 81.f);
-      gstd[i] = sd[i] > 0.f ? dstd[i] / (81.f * sd[i]) : 0.f;
-      gmax[i] = t > 0.f ? dmaxv[i] / t : 0.f;
-    }
-  }
-  for (int p = pl; p < 81; p += NPL) {
-    float v[kVW], t[kVW], y[kVW];
-#pragma unroll
-    for (int i = 0; i < kVW; ++i) v[i] = 0.f;
-    if (g.dxc) V8<T>::load((const T*)g.dxc + base + (size_t)p * C, v);
-    if (g.dxp) {
-      V8<T>::load((const T*)g.dxp + base + (size_t)p * C, t);
-      if (g.xp) {
-        V8<T>::load((const T*)g.xp + base + (size_t)p * C, y);
-#pragma unroll
-        for (int i = 0; i < kVW; ++i) v[i] += y[i] > 0.f ? t[i] : 0.f;
-      } else {
-#pragma unroll
-        for (int i = 0; i < kVW; ++i) v[i] += t[i];
+      for (int i = 0; i < kVW; ++i) {
+        float t = 0.f;
+        for (int l = 0; l < NPL; ++l) t += red[l * C + c0 + i];
+        ties[i] = t;
       }
     }
-    if (g.dpool) {
-      V8<T>::load((const T*)g.x + base + (size_t)p * C, t);
 #pragma unroll
-      for (int i = 0; i < kVW; ++i) v[i] += gmean[i] + (t[i] == mx[i] ? gmax[i] : 0.f) + gstd[i] * (t[i] - mean[i]);
+    for (int i = 0; i < kVW; ++i) {
+      gmean[i] = dmean[i] * (1.f / 81.f);
+      gstd[i] = sd[i] > 0.f ? dstd[i] / (81.f * sd[i]) : 0.f;   // torch: d std/dx = 0 where std == 0
+      gmax[i] = ties[i] > 0.f ? dmaxv[i] / ties[i] : 0.f;       // amax backward splits evenly across ties
+    }
+  }
+  auto one = [&](int p, float (&v)[kVW], const float (&t)[kVW], const float (&y)[kVW], const float (&xx)[kVW]) {
+    if (g.dxp) {
+#pragma unroll
+      for (int i = 0; i < kVW; ++i) v[i] += (g.xp == nullptr || y[i] > 0.f) ? t[i] : 0.f;
+    }
+    if (g.dpool) {
+#pragma unroll
+      for (int i = 0; i < kVW; ++i) v[i] += gmean[i] + (xx[i] == mx[i] ? gmax[i] : 0.f) + gstd[i] * (xx[i] - mean[i]);
     }
     V8<T>::store((T*)g.dx + base + (size_t)p * C, v);
+  };
+  for (int p = pl; p < 81; p += 2 * NPL) {  // two pixels per iteration: up to 8 independent vector loads in flight
+    const bool two = p + NPL < 81;
+    const int p1 = p + NPL;
+    float v0[kVW], t0[kVW], y0[kVW], x0[kVW], v1[kVW], t1[kVW], y1[kVW], x1[kVW];
+#pragma unroll
+    for (int i = 0; i < kVW; ++i) { v0[i] = 0.f; v1[i] = 0.f; t0[i] = 0.f; t1[i] = 0.f; y0[i] = 0.f; y1[i] = 0.f; x0[i] = 0.f; x1[i] = 0.f; }
+    if (g.dxc) V8<T>::load((const T*)g.dxc + base + (size_t)p * C, v0);
+    if (g.dxp) V8<T>::load((const T*)g.dxp + base + (size_t)p * C, t0);
+    if (g.xp) V8<T>::load((const T*)g.xp + base + (size_t)p * C, y0);
+    if (g.dpool) V8<T>::load((const T*)g.x + base + (size_t)p * C, x0);
+    if (two) {
+      if (g.dxc) V8<T>::load((const T*)g.dxc + base + (size_t)p1 * C, v1);
+      if (g.dxp) V8<T>::load((const T*)g.dxp + base + (size_t)p1 * C, t1);
+      if (g.xp) V8<T>::load((const T*)g.xp + base + (size_t)p1 * C, y1);
+      if (g.dpool) V8<T>::load((const T*)g.x + base + (size_t)p1 * C, x1);
+    }
+    one(p, v0, t0, y0, x0);
+    if (two) one(p1, v1, t1, y1, x1);
   }
 }
 
 // dzh = dy * [mask > 0] with mask = y (ma == null) or y*ma[c] + mb[c]; per-channel sums of dzh and
 // dzh*z (double atomics); optional per-(board, channel) sum of the UNMASKED dy (gpool-bias gradient).
 // dzh may alias dy (in place). Two pixels per iteration keep 4-6 independent 16-byte loads in flight.
+constexpr int kStatsBoardsPerCta = 4;  // boards per CTA: 4x fewer double atomics on the 2*C channel accumulators
+
 template <typename T>
 __global__ void __launch_bounds__(256) relu_bwd_stats_vec_kernel(const T* dy, const T* __restrict__ y,
-                                                                   const T* __restrict__ z, T* dzh, int C,
+                                                                   const T* __restrict__ z, T* dzh, int B, int C,
                                                                    const float* __restrict__ ma, const float* __restrict__ mb,
                                                                    float* __restrict__ board_sum, double* sums) {
-  __shared__ float red[3][256 * kVW];
+  __shared__ float red[2][256 * kVW];
   const int C8 = C / kVW, NPL = 256 / C8;
-  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
-  const size_t base = (size_t)b * 81 * C + c0;
+  const int cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
   const bool same = (y == z);
-  float s1[kVW], s2[kVW], s0[kVW], fa[kVW], fb[kVW];
+  float s1[kVW], s2[kVW], fa[kVW], fb[kVW];
 #pragma unroll
-  for (int i = 0; i < kVW; ++i) { s1[i] = 0.f; s2[i] = 0.f; s0[i] = 0.f; fa[i] = 1.f; fb[i] = 0.f; }
+  for (int i = 0; i < kVW; ++i) { s1[i] = 0.f; s2[i] = 0.f; fa[i] = 1.f; fb[i] = 0.f; }
   if (ma) { ldf8(ma + c0, fa); ldf8(mb + c0, fb); }
-  for (int p = pl; p < 81; p += 2 * NPL) {
-    const bool two = p + NPL < 81;
-    float d0[kVW], a0[kVW], z0[kVW], d1[kVW], a1[kVW], z1[kVW];
-    V8<T>::load(dy + base + (size_t)p * C, d0);
-    V8<T>::load(y + base + (size_t)p * C, a0);
-    if (!same) V8<T>::load(z + base + (size_t)p * C, z0);
-    if (two) {
-      V8<T>::load(dy + base + (size_t)(p + NPL) * C, d1);
-      V8<T>::load(y + base + (size_t)(p + NPL) * C, a1);
-      if (!same) V8<T>::load(z + base + (size_t)(p + NPL) * C, z1);
-    }
+  const int b_end = min(B, (int)(blockIdx.x + 1) * kStatsBoardsPerCta);
+  for (int b = blockIdx.x * kStatsBoardsPerCta; b < b_end; ++b) {
+    const size_t base = (size_t)b * 81 * C + c0;
+    float s0[kVW];
 #pragma unroll
-    for (int i = 0; i < kVW; ++i) {
-      s0[i] += d0[i];
-      if (same) z0[i] = a0[i];
-      d0[i] = fmaf(a0[i], fa[i], fb[i]) > 0.f ? d0[i] : 0.f;
-    }
-    V8<T>::store(dzh + base + (size_t)p * C, d0);
-    V8<T>::round(d0);
-#pragma unroll
-    for (int i = 0; i < kVW; ++i) { s1[i] += d0[i]; s2[i] = fmaf(d0[i], z0[i], s2[i]); }
-    if (two) {
+    for (int i = 0; i < kVW; ++i) s0[i] = 0.f;
+    for (int p = pl; p < 81; p += 2 * NPL) {
+      const bool two = p + NPL < 81;
+      float d0[kVW], a0[kVW], z0[kVW], d1[kVW], a1[kVW], z1[kVW];
+      V8<T>::load(dy + base + (size_t)p * C, d0);
+      V8<T>::load(y + base + (size_t)p * C, a0);
+      if (!same) V8<T>::load(z + base + (size_t)p * C, z0);
+      if (two) {
+        V8<T>::load(dy + base + (size_t)(p + NPL) * C, d1);
+        V8<T>::load(y + base + (size_t)(p + NPL) * C, a1);
+        if (!same) V8<T>::load(z + base + (size_t)(p + NPL) * C, z1);
+      }
 #pragma unroll
       for (int i = 0; i < kVW; ++i) {
-        s0[i] += d1[i];
-        if (same) z1[i] = a1[i];
-        d1[i] = fmaf(a1[i], fa[i], fb[i]) > 0.f ? d1[i] : 0.f;
+        s0[i] += d0[i];
+        if (same) z0[i] = a0[i];
+        d0[i] = fmaf(a0[i], fa[i], fb[i]) > 0.f ? d0[i] : 0.f;
       }
-      V8<T>::store(dzh + base + (size_t)(p + NPL) * C, d1);
-      V8<T>::round(d1);
+      V8<T>::store(dzh + base + (size_t)p * C, d0);
+      V8<T>::round(d0);
 #pragma unroll
-      for (int i = 0; i < kVW; ++i) { s1[i] += d1[i]; s2[i] = fmaf(d1[i], z1[i], s2[i]); }
+      for (int i = 0; i < kVW; ++i) { s1[i] += d0[i]; s2[i] = fmaf(d0[i], z0[i], s2[i]); }
+      if (two) {
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) {
+          s0[i] += d1[i];
+          if (same) z1[i] = a1[i];
+          d1[i] = fmaf(a1[i], fa[i], fb[i]) > 0.f ? d1[i] : 0.f;
+        }
+        V8<T>::store(dzh + base + (size_t)(p + NPL) * C, d1);
+        V8<T>::round(d1);
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) { s1[i] += d1[i]; s2[i] = fmaf(d1[i], z1[i], s2[i]); }
+      }
+    }
+    if (board_sum) {  // per-(board, channel) sum of the unmasked gradient
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kVW; ++i) red[0][pl * C + c0 + i] = s0[i];
+      __syncthreads();
+      for (int c = threadIdx.x; c < C; c += 256) {
+        float u = 0.f;
+        for (int l = 0; l < NPL; ++l) u += red[0][l * C + c];
+        board_sum[(size_t)b * C + c] = u;
+      }
     }
   }
+  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < kVW; ++i) { red[0][pl * C + c0 + i] = s1[i]; red[1][pl * C + c0 + i] = s2[i]; red[2][pl * C + c0 + i] = s0[i]; }
+  for (int i = 0; i < kVW; ++i) { red[0][pl * C + c0 + i] = s1[i]; red[1][pl * C + c0 + i] = s2[i]; }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += 256) {
-    float a = 0.f, q = 0.f, u = 0.f;
-    for (int l = 0; l < NPL; ++l) { a += red[0][l * C + c]; q += red[1][l * C + c]; u += red[2][l * C + c]; }
+    float a = 0.f, q = 0.f;
+    for (int l = 0; l < NPL; ++l) { a += red[0][l * C + c]; q += red[1][l * C + c]; }
     atomicAdd(&sums[c], (double)a);
     atomicAdd(&sums[C + c], (double)q);
-    if (board_sum) board_sum[(size_t)b * C + c] = u;
   }
 }
 
@@ -766,9 +811,9 @@ int kbk_relu_bwd_stats(const void* dy, const void* y, const void* z, void* dzh, 
   const int B = (int)(rows / 81);
   if (vec_ok(C)) {
     if (dtype == KB_F32)
-      relu_bwd_stats_vec_kernel<float><<<B, 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)z, (float*)dzh, C, nullptr, nullptr, nullptr, sums);
+      relu_bwd_stats_vec_kernel<float><<<kb_ceil_div(B, kStatsBoardsPerCta), 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)z, (float*)dzh, B, C, nullptr, nullptr, nullptr, sums);
     else
-      relu_bwd_stats_vec_kernel<bf16><<<B, 256, 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)z, (bf16*)dzh, C, nullptr, nullptr, nullptr, sums);
+      relu_bwd_stats_vec_kernel<bf16><<<kb_ceil_div(B, kStatsBoardsPerCta), 256, 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)z, (bf16*)dzh, B, C, nullptr, nullptr, nullptr, sums);
     KB_CUDA_LAUNCH_CHECK();
     return KB_OK;
   }
@@ -787,9 +832,9 @@ int kbk_mask_bwd_stats(void* d_inout, const void* z, const float* ma, const floa
   KB_CHECK_ARG(vec_ok(C), "mask_bwd_stats: unsupported channel count %d", C);
   if (B == 0) return KB_OK;
   if (dtype == KB_F32)
-    relu_bwd_stats_vec_kernel<float><<<B, 256, 0, st>>>((const float*)d_inout, (const float*)z, (const float*)z, (float*)d_inout, C, ma, mb, board_sum, sums);
+    relu_bwd_stats_vec_kernel<float><<<kb_ceil_div(B, kStatsBoardsPerCta), 256, 0, st>>>((const float*)d_inout, (const float*)z, (const float*)z, (float*)d_inout, B, C, ma, mb, board_sum, sums);
   else
-    relu_bwd_stats_vec_kernel<bf16><<<B, 256, 0, st>>>((const bf16*)d_inout, (const bf16*)z, (const bf16*)z, (bf16*)d_inout, C, ma, mb, board_sum, sums);
+    relu_bwd_stats_vec_kernel<bf16><<<kb_ceil_div(B, kStatsBoardsPerCta), 256, 0, st>>>((const bf16*)d_inout, (const bf16*)z, (const bf16*)z, (bf16*)d_inout, B, C, ma, mb, board_sum, sums);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

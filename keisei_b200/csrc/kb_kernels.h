@@ -59,6 +59,7 @@ struct ApplyArgs {
   const float* gbias;   // [B][C] or null
   void* out;
   float* pool;          // [B][3C] or null
+  float* ties;          // [B][C] or null: number of pixels equal to the board max (needs pool; vectorised kernel only)
   int B, C, dtype;
 };
 int kbk_apply(const ApplyArgs& a, cudaStream_t st);
@@ -116,6 +117,7 @@ struct PassDArgs {
   const void* x;     // block input (for pool backward)
   const float* pool; // [B][3C] saved mean/max/std of x
   const float* dpool;// [B][3C] grad wrt pool (may be null)
+  const float* ties; // [B][C] tie counts of the board max from the forward (null -> counted here)
   void* dx;          // out
 };
 int kbk_block_bwd_dx(const PassDArgs& a, cudaStream_t st);  // pass D

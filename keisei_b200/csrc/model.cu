@@ -110,6 +110,7 @@ struct Ws {
   void *obs_p, *z0, *x0;
   BlockWs* blk;            // host array, nb entries (filled by carve)
   float* pools;            // [nb+1][B][3C]
+  float* tie_counts;       // [nb+1][B][C]: pixels equal to the board max (amax backward)
   float* bn;               // [2nb+2][4][Cmax]: a, b, mean, invstd
   float *g, *p1raw, *p1act, *vh, *sh;
   double* dsums;           // [2][Cmax]
@@ -124,6 +125,7 @@ struct Ws {
   int Cmax;
   size_t total;
   float* pool(const Dims& m, int i) const { return pools + (size_t)i * m.B * 3 * m.C; }
+  float* ties(const Dims& m, int i) const { return tie_counts + (size_t)i * m.B * m.C; }
   float* bn_a(int l) const { return bn + (size_t)l * 4 * Cmax; }
   float* bn_b(int l) const { return bn + (size_t)l * 4 * Cmax + Cmax; }
   float* bn_mean(int l) const { return bn + (size_t)l * 4 * Cmax + 2 * Cmax; }
@@ -152,6 +154,7 @@ void carve(const Dims& m, void* base, int training, Ws& w, BlockWs* blk_storage)
   if (training) {
     w.z0 = b.take(m.act()); w.x0 = b.take(m.act());
     w.pools = b.f32((size_t)(m.nb + 1) * B * 3 * m.C);
+    w.tie_counts = b.f32((size_t)(m.nb + 1) * B * m.C);
     for (int i = 0; i < m.nb; ++i) {
       BlockWs bw;
       bw.z1 = b.take(m.act()); bw.a1 = b.take(m.act()); bw.z2 = b.take(m.act()); bw.xout = b.take(m.act());
@@ -175,7 +178,7 @@ void carve(const Dims& m, void* base, int training, Ws& w, BlockWs* blk_storage)
     bw.z1 = bw.a1 = bw.z2 = bw.xout = nullptr;
     bw.gh = b.f32(B * m.G); bw.bmean2 = b.f32(B * m.C); bw.se_in = nullptr; bw.seh = b.f32(B * m.S); bw.se = b.f32(B * 2 * m.C);
     if (blk_storage) blk_storage[0] = bw;
-    w.z0 = w.x0 = nullptr; w.pools = nullptr;
+    w.z0 = w.x0 = nullptr; w.pools = nullptr; w.tie_counts = nullptr;
     w.d0 = w.d1 = w.d2 = nullptr;
     w.s_du = w.s_duz = w.dse_in = w.dg = w.dse = w.dseh = w.dgh = w.dpool = w.k123 = w.dp1 = w.dvh = w.dsh = nullptr;
     w.wg_ws = nullptr; w.wg_ws_bytes = 0;
@@ -350,7 +353,7 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
     KB_TRY(conv3x3(m, w.obs_p, wp.stem_wf, w.z0, m.C0p, C, e, use_tc, num_sms, st));
     KB_TRY(bn_fin(0, 1, 0, C));
     ApplyArgs a; memset(&a, 0, sizeof(a));
-    a.z = w.z0; a.a = w.bn_a(0); a.b = w.bn_b(0); a.out = w.x0; a.pool = w.pool(m, 0); a.B = B; a.C = C; a.dtype = dtype;
+    a.z = w.z0; a.a = w.bn_a(0); a.b = w.bn_b(0); a.out = w.x0; a.pool = w.pool(m, 0); a.ties = w.ties(m, 0); a.B = B; a.C = C; a.dtype = dtype;
     KB_TRY(kbk_apply(a, st));
     x_cur = w.x0; pool_cur = w.pool(m, 0);
   } else {
@@ -416,7 +419,7 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
     // x' = relu(bn2(z2) * sigmoid(scale) + shift + x), plus the pool statistics of x' for the next consumer
     ApplyArgs a; memset(&a, 0, sizeof(a));
     a.z = z2; a.a = training ? w.bn_a(l2) : nullptr; a.b = training ? w.bn_b(l2) : nullptr; a.se = bw.se; a.res = x_cur;
-    a.out = xout; a.pool = pool_next; a.B = B; a.C = C; a.dtype = dtype;
+    a.out = xout; a.pool = pool_next; a.ties = training ? w.ties(m, i + 1) : nullptr; a.B = B; a.C = C; a.dtype = dtype;
     KB_TRY(kbk_apply(a, st));
     x_cur = xout; pool_cur = pool_next;
   }
@@ -536,7 +539,7 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
   void *cur = w.d0, *t1 = w.d1, *t2 = w.d2;
   {
     PassDArgs a; memset(&a, 0, sizeof(a));
-    a.B = B; a.C = C; a.dtype = dtype; a.dxc = w.d1; a.x = x_last; a.pool = pool_f; a.dpool = w.dpool; a.dx = cur;
+    a.B = B; a.C = C; a.dtype = dtype; a.dxc = w.d1; a.x = x_last; a.pool = pool_f; a.dpool = w.dpool; a.ties = w.ties(m, m.nb); a.dx = cur;
     KB_TRY(kbk_block_bwd_dx(a, st));
   }
 
@@ -596,7 +599,7 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
     // pass D: dx = dgrad + residual branch + global-pool backward
     PassDArgs pd; memset(&pd, 0, sizeof(pd));
     pd.B = B; pd.C = C; pd.dtype = dtype; pd.dxc = t1; pd.dxp = cur; pd.xp = bw.xout; pd.x = x_in; pd.pool = pool_in;
-    pd.dpool = w.dpool; pd.dx = t2;
+    pd.dpool = w.dpool; pd.ties = w.ties(m, i); pd.dx = t2;
     KB_TRY(kbk_block_bwd_dx(pd, st));
     void* nc = t2; t2 = t1; t1 = cur; cur = nc;
   }
