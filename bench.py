@@ -137,7 +137,7 @@ def timed(fn, steps: int, warmup: int, device, world: int) -> float:
     return float(ms.item())
 
 
-def cpu_baseline(batch: int = 32, reps: int = 2) -> dict:
+def cpu_baseline(batch: int = 256, reps: int = 2) -> dict:
     """Oracle port (fp32 CPU PyTorch restatement of the reference) on the host cores: rollout step
     (eval forward + mask/softmax/Categorical sample + log-prob + scalar value) on a bounded sample."""
     from oracle import keisei_oracle as O
@@ -173,7 +173,7 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 32
+    batch = 256
     t0 = time.perf_counter()
     cb = cpu_baseline(batch=batch, reps=max(1, min(args.steps, 3)))
     line = {"metric": "rollout positions/s", "value": cb["value"], "unit": "positions/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -320,10 +320,50 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
         G.normalize_advantages_(adv)
     gae_ms = timed(gae_step, 20, 3, device, world)
     sps = UPDATE_GLOBAL_B / (ms * 1e-3)
-    return {"metric": "PPO update samples/s", "value": sps, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "warmup": warm,
+    e2e = update_e2e(algo, device, rank, world) if world == 1 else None
+    return {"metric": "PPO update samples/s", "e2e": e2e, "value": sps, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "warmup": warm,
             "global_batch": UPDATE_GLOBAL_B, "per_gpu_batch": Bu, "scaling": "strong", "gae_T128_N64_ms": gae_ms,
             "frac_of_tensor_roofline": (22.97e9 * UPDATE_GLOBAL_B / world / (ms * 1e-3) / 1e12) / peaks()["bf16_tflops_sustained"],
             "includes": "fwd+losses+bwd+allreduce+unscale+clip+Adam"}
+
+
+def update_e2e(algo, device, rank, world) -> dict:
+    """The public call a user makes: KataGoPPOAlgorithm.update(buffer, next_values) on a host-resident
+    KataGoRolloutBuffer of T=128 x N=64 = 8192 samples (the reference's profiled update shape,
+    scripts/profile_hotpath.py:411-455), one epoch, one minibatch of 8192: buffer flatten, H2D of
+    observations + masks (225 MB), GAE + normalisation, shuffle/gather, fwd+bwd+clip+Adam, metrics D2H."""
+    import dataclasses
+    from keisei_b200.katago_ppo import KataGoRolloutBuffer
+    T, N = 128, 64
+    g = torch.Generator().manual_seed(11 + rank)
+    buf = KataGoRolloutBuffer(N, (50, 9, 9), A)
+    steps = []
+    for t in range(T):
+        obs = torch.randn(N, 50, 9, 9, generator=g)
+        mask = torch.zeros(N, A, dtype=torch.bool)
+        actions = torch.randint(0, A, (N,), generator=g)
+        mask.scatter_(1, torch.randint(0, A, (N, 80), generator=g), True)
+        mask[torch.arange(N), actions] = True
+        term = torch.rand(N, generator=g) < 0.02
+        steps.append((obs, actions, -3 * torch.rand(N, generator=g), 0.3 * torch.randn(N, generator=g), term.float(), term, term, mask,
+                      torch.where(term, torch.randint(0, 3, (N,), generator=g), torch.full((N,), -1)), torch.randn(N, generator=g).clamp(-1.5, 1.5)))
+    old_params = algo.params
+    algo.params = dataclasses.replace(old_params, batch_size=T * N, epochs_per_batch=1)
+    nv = torch.randn(N, generator=g).to(device)
+    times = []
+    for rep in range(3):
+        for st in steps:
+            buf.add(*st)
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        algo.update(buf, nv)
+        torch.cuda.synchronize(device)
+        times.append(time.perf_counter() - t0)
+    algo.params = old_params
+    best = min(times[1:])
+    return {"value": T * N / best, "unit": "samples/s", "ms_per_update": best * 1e3, "samples": T * N,
+            "h2d_bytes_per_update": T * N * (50 * 81 * 4 + A + 8 + 4 * 4 + 8), "d2h_bytes_per_update": 9 * 8,
+            "note": "update(buffer, next_values): host buffer -> metrics dict, wall clock, best of 2 after 1 warm-up"}
 
 
 def main() -> None:
