@@ -4,6 +4,7 @@
 //
 // Layout: NHWC activations [B][81][C]; one CTA per board, one thread per channel, so every
 // per-(board, channel) reduction over the 81 pixels is a register loop with 2*C-byte coalesced rows.
+#include <stdlib.h>
 #include "kb_common.cuh"
 #include "kb_kernels.h"
 
@@ -41,9 +42,14 @@ __global__ void apply_kernel(ApplyArgs g) {
   if (g.pool) {
     const float dm = ds * (1.f / 81.f);
     float* pr = g.pool + (size_t)b * 3 * C;
-    pr[c] = s * (1.f / 81.f);
+    const float mean = s * (1.f / 81.f), sd = sqrtf(fmaxf(dss * (1.f / 81.f) - dm * dm, 0.f));
+    pr[c] = mean;
     pr[C + c] = mx;
-    pr[2 * C + c] = sqrtf(fmaxf(dss * (1.f / 81.f) - dm * dm, 0.f));
+    pr[2 * C + c] = sd;
+    if (g.pool_bf) {
+      bf16* pb = (bf16*)g.pool_bf + (size_t)b * 3 * C;
+      pb[c] = __float2bfloat16_rn(mean); pb[C + c] = __float2bfloat16_rn(mx); pb[2 * C + c] = __float2bfloat16_rn(sd);
+    }
   }
 }
 
@@ -58,11 +64,13 @@ __global__ void bn_eval_affine_kernel(const float* w, const float* bias, const f
 }
 
 __global__ void affine_rows_kernel(const float* __restrict__ in, const float* __restrict__ a, const float* __restrict__ b,
-                                   float* __restrict__ out, long long n, int C) {
+                                   float* __restrict__ out, bf16* __restrict__ out_bf, long long n, int C) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int c = (int)(i % C);
-  out[i] = fmaf(in[i], a[c], b[c]);
+  const float v = fmaf(in[i], a[c], b[c]);
+  out[i] = v;
+  if (out_bf) out_bf[i] = __float2bfloat16_rn(v);
 }
 
 __global__ void bn_finalize_kernel(double* sums, double count, const float* w, const float* bias, const float* rm,
@@ -356,96 +364,109 @@ template <typename T> using V8 = VV<T, kVW>;
 __device__ __forceinline__ void ldf8(const float* p, float (&v)[kVW]) { VV<float, kVW>::load(p, v); }
 
 // SE = squeeze-excite scale/shift + residual present; POOL = emit global-pool statistics of the output.
+// Each CTA walks kApplyBoardsPerCta boards (fewer, longer CTAs: less scheduling / tail overhead per board).
 template <typename T, bool SE, bool POOL>
-__global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g) {
+__global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g, int kApplyBoardsPerCta) {
   __shared__ float red[POOL ? 5 : 1][POOL ? 256 * kVW : 1];  // [quantity][lane * C + c]
   const int C = g.C, C8 = C / kVW, NPL = 256 / C8;
-  const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
-  float a_[kVW], b_[kVW], sg[kVW], sf[kVW], gb[kVW];
+  const int cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
+  float a_[kVW], b_[kVW];
 #pragma unroll
-  for (int i = 0; i < kVW; ++i) { a_[i] = 1.f; b_[i] = 0.f; sg[i] = 1.f; sf[i] = 0.f; gb[i] = 0.f; }
+  for (int i = 0; i < kVW; ++i) { a_[i] = 1.f; b_[i] = 0.f; }
   if (g.a) { ldf8(g.a + c0, a_); ldf8(g.b + c0, b_); }
-  if (SE) {
-    ldf8(g.se + (size_t)b * 2 * C + c0, sg); ldf8(g.se + (size_t)b * 2 * C + C + c0, sf);
+  const int b_end = min(g.B, (int)(blockIdx.x + 1) * kApplyBoardsPerCta);
+  for (int b = blockIdx.x * kApplyBoardsPerCta; b < b_end; ++b) {
+    float sg[kVW], sf[kVW], gb[kVW];
 #pragma unroll
-    for (int i = 0; i < kVW; ++i) {
-      sg[i] = sigmoidf_(sg[i]);
-      // fold the BN affine into the SE scale/shift: (z*a+b)*sg+sf = z*(a*sg) + (b*sg+sf)
-      sf[i] = fmaf(b_[i], sg[i], sf[i]); sg[i] *= a_[i];
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < kVW; ++i) { sg[i] = a_[i]; sf[i] = b_[i]; }
-  }
-  if (g.gbias) ldf8(g.gbias + (size_t)b * C + c0, gb);
-  const size_t base = (size_t)b * 81 * C + c0;
-  float s[kVW], mx[kVW], k0[kVW], ds[kVW], dss[kVW], tie[kVW];
-#pragma unroll
-  for (int i = 0; i < kVW; ++i) { s[i] = 0.f; mx[i] = -INFINITY; k0[i] = 0.f; ds[i] = 0.f; dss[i] = 0.f; tie[i] = 0.f; }
-  int cnt = 0;
-  auto finish = [&](float (&v)[kVW], const float (&r)[kVW], int p) {
-#pragma unroll
-    for (int i = 0; i < kVW; ++i) {
-      float t = fmaf(v[i], sg[i], sf[i]);
-      if (SE) t += r[i];
-      v[i] = fmaxf(t, 0.f) + gb[i];
-    }
-    V8<T>::store((T*)g.out + base + (size_t)p * C, v);
-    if (POOL) {
-      V8<T>::round(v);
+    for (int i = 0; i < kVW; ++i) gb[i] = 0.f;
+    if (SE) {
+      ldf8(g.se + (size_t)b * 2 * C + c0, sg); ldf8(g.se + (size_t)b * 2 * C + C + c0, sf);
 #pragma unroll
       for (int i = 0; i < kVW; ++i) {
-        if (cnt == 0) k0[i] = v[i];
-        const float d = v[i] - k0[i];
-        s[i] += v[i]; ds[i] += d; dss[i] = fmaf(d, d, dss[i]);
-        // running (max, number of elements equal to it): amax backward splits evenly across ties
-        tie[i] = v[i] > mx[i] ? 1.f : (v[i] == mx[i] ? tie[i] + 1.f : tie[i]);
-        mx[i] = fmaxf(mx[i], v[i]);
+        sg[i] = sigmoidf_(sg[i]);
+        // fold the BN affine into the SE scale/shift: (z*a+b)*sg+sf = z*(a*sg) + (b*sg+sf)
+        sf[i] = fmaf(b_[i], sg[i], sf[i]); sg[i] *= a_[i];
       }
-      ++cnt;
-    }
-  };
-  for (int p = pl; p < 81; p += 2 * NPL) {  // two pixels per iteration: 2-4 independent 16-byte loads in flight
-    const bool two = p + NPL < 81;
-    float v0[kVW], r0[kVW], v1[kVW], r1[kVW];
-    V8<T>::load((const T*)g.z + base + (size_t)p * C, v0);
-    if (SE) V8<T>::load((const T*)g.res + base + (size_t)p * C, r0);
-    if (two) {
-      V8<T>::load((const T*)g.z + base + (size_t)(p + NPL) * C, v1);
-      if (SE) V8<T>::load((const T*)g.res + base + (size_t)(p + NPL) * C, r1);
-    }
-    finish(v0, r0, p);
-    if (two) finish(v1, r1, p + NPL);
-  }
-  if (!POOL) return;
-  // per-lane (count, mean, M2) -> Chan's parallel merge across the NPL pixel lanes
-  const float fc = (float)cnt;
+    } else {
 #pragma unroll
-  for (int i = 0; i < kVW; ++i) {
-    const int o = pl * C + c0 + i;
-    red[0][o] = s[i];
-    red[POOL ? 1 : 0][o] = mx[i];
-    red[POOL ? 2 : 0][o] = cnt > 0 ? k0[i] + ds[i] / fc : 0.f;            // lane mean
-    red[POOL ? 3 : 0][o] = cnt > 0 ? dss[i] - ds[i] * ds[i] / fc : 0.f;   // lane M2
-    red[POOL ? 4 : 0][o] = tie[i];
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float S = 0.f, M = -INFINITY;
-    for (int l = 0; l < NPL; ++l) { S += red[0][l * C + c]; M = fmaxf(M, red[POOL ? 1 : 0][l * C + c]); }
-    const float mean = S * (1.f / 81.f);
-    float m2 = 0.f;
-    for (int l = 0; l < NPL; ++l) {
-      const int n_l = l < 81 ? (81 - l + NPL - 1) / NPL : 0;  // pixels lane l visited
-      const float dm = red[POOL ? 2 : 0][l * C + c] - mean;
-      m2 += red[POOL ? 3 : 0][l * C + c] + (float)n_l * dm * dm;
+      for (int i = 0; i < kVW; ++i) { sg[i] = a_[i]; sf[i] = b_[i]; }
     }
-    float* pr = g.pool + (size_t)b * 3 * C;
-    pr[c] = mean; pr[C + c] = M; pr[2 * C + c] = sqrtf(fmaxf(m2 * (1.f / 81.f), 0.f));
-    if (g.ties) {
-      float t = 0.f;
-      for (int l = 0; l < NPL; ++l) if (red[POOL ? 1 : 0][l * C + c] == M) t += red[POOL ? 4 : 0][l * C + c];
-      g.ties[(size_t)b * C + c] = t;
+    if (g.gbias) ldf8(g.gbias + (size_t)b * C + c0, gb);
+    const size_t base = (size_t)b * 81 * C + c0;
+    float s[kVW], mx[kVW], k0[kVW], ds[kVW], dss[kVW], tie[kVW];
+#pragma unroll
+    for (int i = 0; i < kVW; ++i) { s[i] = 0.f; mx[i] = -INFINITY; k0[i] = 0.f; ds[i] = 0.f; dss[i] = 0.f; tie[i] = 0.f; }
+    int cnt = 0;
+    auto finish = [&](float (&v)[kVW], const float (&r)[kVW], int p) {
+#pragma unroll
+      for (int i = 0; i < kVW; ++i) {
+        float t = fmaf(v[i], sg[i], sf[i]);
+        if (SE) t += r[i];
+        v[i] = fmaxf(t, 0.f) + gb[i];
+      }
+      V8<T>::store((T*)g.out + base + (size_t)p * C, v);
+      if (POOL) {
+        V8<T>::round(v);
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) {
+          if (cnt == 0) k0[i] = v[i];
+          const float d = v[i] - k0[i];
+          s[i] += v[i]; ds[i] += d; dss[i] = fmaf(d, d, dss[i]);
+          // running (max, number of elements equal to it): amax backward splits evenly across ties
+          tie[i] = v[i] > mx[i] ? 1.f : (v[i] == mx[i] ? tie[i] + 1.f : tie[i]);
+          mx[i] = fmaxf(mx[i], v[i]);
+        }
+        ++cnt;
+      }
+    };
+    for (int p = pl; p < 81; p += 2 * NPL) {  // two pixels per iteration: 2-4 independent vector loads in flight
+      const bool two = p + NPL < 81;
+      float v0[kVW], r0[kVW], v1[kVW], r1[kVW];
+      V8<T>::load((const T*)g.z + base + (size_t)p * C, v0);
+      if (SE) V8<T>::load((const T*)g.res + base + (size_t)p * C, r0);
+      if (two) {
+        V8<T>::load((const T*)g.z + base + (size_t)(p + NPL) * C, v1);
+        if (SE) V8<T>::load((const T*)g.res + base + (size_t)(p + NPL) * C, r1);
+      }
+      finish(v0, r0, p);
+      if (two) finish(v1, r1, p + NPL);
+    }
+    if (!POOL) continue;
+    // per-lane (count, mean, M2) -> Chan's parallel merge across the NPL pixel lanes
+    const float fc = (float)cnt;
+    __syncthreads();  // previous board's readers are done with `red`
+#pragma unroll
+    for (int i = 0; i < kVW; ++i) {
+      const int o = pl * C + c0 + i;
+      red[0][o] = s[i];
+      red[POOL ? 1 : 0][o] = mx[i];
+      red[POOL ? 2 : 0][o] = cnt > 0 ? k0[i] + ds[i] / fc : 0.f;            // lane mean
+      red[POOL ? 3 : 0][o] = cnt > 0 ? dss[i] - ds[i] * ds[i] / fc : 0.f;   // lane M2
+      red[POOL ? 4 : 0][o] = tie[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float S = 0.f, M = -INFINITY;
+      for (int l = 0; l < NPL; ++l) { S += red[0][l * C + c]; M = fmaxf(M, red[POOL ? 1 : 0][l * C + c]); }
+      const float mean = S * (1.f / 81.f);
+      float m2 = 0.f;
+      for (int l = 0; l < NPL; ++l) {
+        const int n_l = l < 81 ? (81 - l + NPL - 1) / NPL : 0;  // pixels lane l visited
+        const float dm = red[POOL ? 2 : 0][l * C + c] - mean;
+        m2 += red[POOL ? 3 : 0][l * C + c] + (float)n_l * dm * dm;
+      }
+      const float sd = sqrtf(fmaxf(m2 * (1.f / 81.f), 0.f));
+      float* pr = g.pool + (size_t)b * 3 * C;
+      pr[c] = mean; pr[C + c] = M; pr[2 * C + c] = sd;
+      if (g.pool_bf) {
+        bf16* pb = (bf16*)g.pool_bf + (size_t)b * 3 * C;
+        pb[c] = __float2bfloat16_rn(mean); pb[C + c] = __float2bfloat16_rn(M); pb[2 * C + c] = __float2bfloat16_rn(sd);
+      }
+      if (g.ties) {
+        float t = 0.f;
+        for (int l = 0; l < NPL; ++l) if (red[POOL ? 1 : 0][l * C + c] == M) t += red[POOL ? 4 : 0][l * C + c];
+        g.ties[(size_t)b * C + c] = t;
+      }
     }
   }
 }
@@ -693,10 +714,12 @@ int kbk_apply(const ApplyArgs& a, cudaStream_t st) {
   if (a.B == 0) return KB_OK;
   if (vec_ok(a.C) && ((a.se != nullptr) == (a.res != nullptr))) {
     const bool se = a.se != nullptr, pool = a.pool != nullptr;
+    static int bpc = 0;
+    if (bpc == 0) { const char* e = getenv("KB_APPLY_BPC"); bpc = e ? atoi(e) : 1; if (bpc < 1) bpc = 1; }
 #define KB_APPLY_VEC(SE_, POOL_)                                                                   \
     do {                                                                                           \
-      if (a.dtype == KB_F32) apply_vec_kernel<float, SE_, POOL_><<<a.B, 256, 0, st>>>(a);          \
-      else apply_vec_kernel<bf16, SE_, POOL_><<<a.B, 256, 0, st>>>(a);                             \
+      if (a.dtype == KB_F32) apply_vec_kernel<float, SE_, POOL_><<<kb_ceil_div(a.B, bpc), 256, 0, st>>>(a, bpc); \
+      else apply_vec_kernel<bf16, SE_, POOL_><<<kb_ceil_div(a.B, bpc), 256, 0, st>>>(a, bpc);               \
     } while (0)
     if (se && pool) KB_APPLY_VEC(true, true);
     else if (se) KB_APPLY_VEC(true, false);
@@ -726,10 +749,11 @@ int kbk_bn_finalize(double* sums, double count, const float* w, const float* bia
   return KB_OK;
 }
 
-int kbk_affine_rows(const float* in, const float* a, const float* b, float* out, long long rows, int C, cudaStream_t st) {
+int kbk_affine_rows(const float* in, const float* a, const float* b, float* out, void* out_bf16, long long rows, int C,
+                    cudaStream_t st) {
   const long long n = rows * C;
   if (n == 0) return KB_OK;
-  affine_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, a, b, out, n, C);
+  affine_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, a, b, out, (bf16*)out_bf16, n, C);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

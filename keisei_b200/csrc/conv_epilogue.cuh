@@ -25,6 +25,7 @@ struct ConvEpi {
   double* ch_dot;         // [Cout] or null: += sum of stored v * mask_src
   float* board_sum;       // [B][Cout] or null: board_scale * sum over the board of v (taken BEFORE the mask when mask_src is set)
   float board_scale;      // e.g. 1/81 for the SE squeeze (mean), 1 for the gpool-bias gradient
+  void* board_bf;         // [B][Cout] bf16 or null: copy of board_sum (operand of the tcgen05 SE layer)
   float* pool;            // [B][3*Cout] or null: mean, max, population std of stored v
 };
 
@@ -100,8 +101,11 @@ struct ConvEpiThread {
   }
   // after all pixels of local board j (global board b) have been fed
   __device__ __forceinline__ void board_done(int j, int b) {
-    if (on(kEpiBoard, e.board_sum != nullptr))
-      e.board_sum[(size_t)b * Cout + c] = e.board_scale * (on(kEpiMask, e.mask_src != nullptr) ? pre[j] : s[j]);
+    if (on(kEpiBoard, e.board_sum != nullptr)) {
+      const float bs = e.board_scale * (on(kEpiMask, e.mask_src != nullptr) ? pre[j] : s[j]);
+      e.board_sum[(size_t)b * Cout + c] = bs;
+      if (e.board_bf) ((bf16*)e.board_bf)[(size_t)b * Cout + c] = __float2bfloat16_rn(bs);
+    }
     if (on(kEpiPool, e.pool != nullptr)) {
       const float mean = s[j] * (1.f / 81.f);
       const float dm = ds[j] * (1.f / 81.f);

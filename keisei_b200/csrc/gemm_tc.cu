@@ -43,7 +43,6 @@ struct LinArgs {
   int nb_store;
   int group_rows; long long group_pitch;  // bf16 output only: row m at (m/gr)*pitch + (m%gr)*ld_b
   int M, N, Kp, Np;
-  int dbg;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -81,7 +80,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   const uint32_t tmem_base = *holder_ptr;
 
   if (warp == 0) {
-    if (lane == 0 && g.dbg != 3) {
+    if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int ct = t % n_ct, mt = t / n_ct;
@@ -96,7 +95,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && g.dbg != 3) {
+    if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -134,10 +133,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       const float bi = (g.bias && n_ok) ? g.bias[n] : 0.f;
       const bool st_f = g.out_f32 != nullptr && n_ok;
       const bool st_b = g.out_bf != nullptr && n < g.nb_store;
-      if (g.dbg != 3) mbar_wait(tfull_bar(buf), tphase);
+      mbar_wait(tfull_bar(buf), tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * kTileN);
-      const int rows = g.dbg == 2 ? 0 : min(kTileN, g.M - m0);
+      const int rows = min(kTileN, g.M - m0);
       // Epilogue address arithmetic is hoisted out of the per-column code: both output pointers advance
       // by one row per column (board-pitched rows add the pitch adjustment every `group_rows` rows).
       float* pf = g.out_f32 + ((long long)m0 * g.ld_f + n);
@@ -152,27 +151,49 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       bf16* pb = g.out_bf + (boff + n);
       const long long ldf = g.ld_f, ldb = g.ld_b;
       const int gr = g.group_rows;
-      for (int bt = 0; bt < kTileN / 32; ++bt) {
-        if (bt * 32 >= rows) break;
-        uint32_t r[2][16];
-        tmem_ld16(taddr + bt * 32, r[0]);
-        tmem_ld16(taddr + bt * 32 + 16, r[1]);
-        tmem_ld_wait();
-        const int nvalid = min(32, rows - bt * 32);
+      const float scm = n_ok ? sc : 0.f, bim = n_ok ? bi : 0.f;  // features past N come out as exact zeros
+      if (rows == kTileN && gr == 0) {
+        // full tile, plain rows: no per-column predicates at all
+        for (int bt = 0; bt < kTileN / 32; ++bt) {
+          uint32_t r[2][16];
+          tmem_ld16(taddr + bt * 32, r[0]);
+          tmem_ld16(taddr + bt * 32 + 16, r[1]);
+          tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+          for (int q = 0; q < 2; ++q) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (q * 16 + i < nvalid) {
-              float v = fmaf(__uint_as_float(r[q][i]), sc, bi);
+            for (int i = 0; i < 16; ++i) {
+              float v = fmaf(__uint_as_float(r[q][i]), scm, bim);
               if (g.relu) v = fmaxf(v, 0.f);
-              if (!n_ok) v = 0.f;
-              if (st_f) *pf = v;
-              if (st_b) *pb = __float2bfloat16_rn(v);
+              if (st_f) pf[(long long)(q * 16 + i) * ldf] = v;
+              if (st_b) pb[(long long)(q * 16 + i) * ldb] = __float2bfloat16_rn(v);
             }
-            pf += ldf;
-            pb += ldb;
-            if (gr > 0 && ++rem == gr) { rem = 0; pb += adj; }
+          }
+          pf += 32 * ldf;
+          pb += 32 * ldb;
+        }
+      } else {
+        for (int bt = 0; bt < kTileN / 32; ++bt) {
+          if (bt * 32 >= rows) break;
+          uint32_t r[2][16];
+          tmem_ld16(taddr + bt * 32, r[0]);
+          tmem_ld16(taddr + bt * 32 + 16, r[1]);
+          tmem_ld_wait();
+          const int nvalid = min(32, rows - bt * 32);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (q * 16 + i < nvalid) {
+                float v = fmaf(__uint_as_float(r[q][i]), scm, bim);
+                if (g.relu) v = fmaxf(v, 0.f);
+                if (st_f) *pf = v;
+                if (st_b) *pb = __float2bfloat16_rn(v);
+              }
+              pf += ldf;
+              pb += ldb;
+              if (gr > 0 && ++rem == gr) { rem = 0; pb += adj; }
+            }
           }
         }
       }
@@ -262,11 +283,9 @@ int kbk_linear_tc(const void* x, long long M, int Kp, const void* w, int N, int 
   LinArgs g;
   g.scale = scale; g.bias = bias; g.relu = relu; g.out_f32 = out_f32; g.ld_f = ld_f; g.out_bf = (bf16*)out_bf; g.ld_b = ld_b;
   g.nb_store = nb_store; g.group_rows = group_rows; g.group_pitch = group_pitch; g.M = (int)M; g.N = N; g.Kp = Kp; g.Np = Np;
-  int num_tiles = kb_ceil_div(M, kTileN) * (Np / kTileM);
+  const int num_tiles = kb_ceil_div(M, kTileN) * (Np / kTileM);
   if (num_sms <= 0) num_sms = 148;
   const int grid_tiles = num_tiles;
-  g.dbg = 0;
-  if (const char* dbg = getenv("KB_LIN_DBG")) { if (dbg[0] == '1') num_tiles = 0; else g.dbg = dbg[0] - '0'; }  // probes
   static bool attr_set = false;
   if (!attr_set) {
     KB_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));

@@ -59,7 +59,8 @@ struct ApplyArgs {
   const float* gbias;   // [B][C] or null
   void* out;
   float* pool;          // [B][3C] or null
-  float* ties;          // [B][C] or null: number of pixels equal to the board max (needs pool; vectorised kernel only)
+  float* ties;          // [B][C] or null: number of pixels equal to the board max (needs pool)
+  void* pool_bf;        // [B][3C] bf16 or null: copy of pool for the tcgen05 Linear layers
   int B, C, dtype;
 };
 int kbk_apply(const ApplyArgs& a, cudaStream_t st);
@@ -71,7 +72,8 @@ int kbk_bn_finalize(double* sums /*[2][C], zeroed afterwards*/, double count, co
                     const float* running_mean, const float* running_var, float* rm_out, float* rv_out, long long* nbt,
                     float momentum, float eps, int C, float* a, float* b, float* mean, float* invstd, cudaStream_t st);
 // out[r][c] = in[r][c]*a[c] + b[c]  (fp32 [rows][C]; the SE squeeze input from the board means)
-int kbk_affine_rows(const float* in, const float* a, const float* b, float* out, long long rows, int C, cudaStream_t st);
+int kbk_affine_rows(const float* in, const float* a, const float* b, float* out, void* out_bf16, long long rows, int C,
+                    cudaStream_t st);
 // per-channel sum / sum of squares over rows of a [M][C] fp32 matrix (policy head BN)
 int kbk_rows_stats(const float* x, long long M, int C, double* sums, cudaStream_t st);
 

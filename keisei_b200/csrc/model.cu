@@ -364,13 +364,14 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
   }
 
   const bool ltc = lin_tc(m, use_tc);
+  bool pool_bf_ready = false;  // the producing apply kernel also writes the bf16 copy of the pool statistics
   // ---- residual tower ----
   for (int i = 0; i < m.nb; ++i) {
     BlockWs& bw = training ? blks[i] : blks[0];
     const int l1 = 1 + 2 * i, l2 = 2 + 2 * i;
     // global-pool bias from the block INPUT: g = W2 relu(W1 pool + b1) + b2   (se_resnet.py:73-78)
     if (ltc) {
-      KB_TRY(kbk_cast_rows_bf16(pool_cur, w.pool_bf, B, 3 * C, 3 * C, st));
+      if (!pool_bf_ready) KB_TRY(kbk_cast_rows_bf16(pool_cur, w.pool_bf, B, 3 * C, 3 * C, st));
       KB_TRY(kbk_linear_tc(w.pool_bf, B, 3 * C, wp.lin_blk(i, wp.o_g1), m.G, wp.Gp, nullptr, P(pi_blk(i, 7)), 1, bw.gh, m.G,
                            w.gh_bf, wp.Gk, wp.Gk, 0, 0, num_sms, st));
       KB_TRY(kbk_linear_tc(w.gh_bf, B, wp.Gk, wp.lin_blk(i, wp.o_g2), C, wp.Cp, nullptr, P(pi_blk(i, 9)), 0, w.g, C, nullptr, 0, 0,
@@ -393,7 +394,7 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
       KB_TRY(conv3x3(m, bw.a1, wp.wf(i, 1), bw.z2, C, C, e2, use_tc, num_sms, st));
       KB_TRY(bn_fin(l2, pi_blk(i, 4), bi_blk(i, 3), C));
       // SE squeeze input: mean_p(bn2(z2)) = a2 * mean_p(z2) + b2
-      KB_TRY(kbk_affine_rows(bw.bmean2, w.bn_a(l2), w.bn_b(l2), bw.se_in, B, C, st));
+      KB_TRY(kbk_affine_rows(bw.bmean2, w.bn_a(l2), w.bn_b(l2), bw.se_in, ltc ? w.sein_bf : nullptr, B, C, st));
       z2 = bw.z2; xout = bw.xout; pool_next = w.pool(m, i + 1); se_in = bw.se_in;
     } else {
       ConvEpi e = epi_base();
@@ -401,13 +402,13 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
       KB_TRY(conv3x3(m, x_cur, wp.wf(i, 0), w.ey1, C, C, e, use_tc, num_sms, st));
       ConvEpi e2 = epi_base();
       e2.scale = wp.bn_a(l2); e2.shift = wp.bn_b(l2); e2.board_sum = bw.bmean2; e2.board_scale = 1.f / 81.f;
+      e2.board_bf = ltc ? w.sein_bf : nullptr;
       KB_TRY(conv3x3(m, w.ey1, wp.wf(i, 1), w.ey2, C, C, e2, use_tc, num_sms, st));
       z2 = w.ey2; xout = (x_cur == w.ea) ? w.eb : w.ea; pool_next = (pool_cur == w.epool_a) ? w.epool_b : w.epool_a;
       se_in = bw.bmean2;  // BN affine already applied in the conv epilogue
     }
     // SE excite: (scale, shift) = W2 relu(W1 se_in + b1) + b2   (se_resnet.py:83-86)
     if (ltc) {
-      KB_TRY(kbk_cast_rows_bf16(se_in, w.sein_bf, B, C, C, st));
       KB_TRY(kbk_linear_tc(w.sein_bf, B, C, wp.lin_blk(i, wp.o_s1), m.S, wp.Sp, nullptr, P(pi_blk(i, 11)), 1, bw.seh, m.S,
                            w.seh_bf, wp.Sk, wp.Sk, 0, 0, num_sms, st));
       KB_TRY(kbk_linear_tc(w.seh_bf, B, wp.Sk, wp.lin_blk(i, wp.o_s2), 2 * C, wp.C2p, nullptr, P(pi_blk(i, 13)), 0, bw.se, 2 * C,
@@ -420,7 +421,9 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
     ApplyArgs a; memset(&a, 0, sizeof(a));
     a.z = z2; a.a = training ? w.bn_a(l2) : nullptr; a.b = training ? w.bn_b(l2) : nullptr; a.se = bw.se; a.res = x_cur;
     a.out = xout; a.pool = pool_next; a.ties = training ? w.ties(m, i + 1) : nullptr; a.B = B; a.C = C; a.dtype = dtype;
+    a.pool_bf = ltc ? w.pool_bf : nullptr;  // consumed by the next block's global_fc GEMM
     KB_TRY(kbk_apply(a, st));
+    pool_bf_ready = ltc;
     x_cur = xout; pool_cur = pool_next;
   }
 
