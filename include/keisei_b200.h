@@ -111,6 +111,31 @@ int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const* params, c
                          long long policy_pitch, const float* dvalue, const float* dscore,
                          void* const* grads, int use_tc, int num_sms, kb_stream_t stream);
 
+/* ---- plain ResNet baseline: keisei/training/models/resnet.py:25-84 ResidualBlock / ResNetModel.forward
+ *      (the `resnet` registry entry, scalar value contract; BASELINE.json configs[3]) and its autograd ----
+ * params[15 + 6*num_layers] float32 and buffers[9 + 6*num_layers] in the reference's registration order
+ * (see keisei_b200/csrc/resnet.cu header). policy_out: (B, policy_pitch >= 11259) flat logits in the
+ * activation dtype; value_out (B,1) float32, tanh-activated. new_stats: [2*num_layers+3][2][hidden_size]
+ * float32 (same convention as kb_seresnet_forward). */
+typedef struct {
+  int num_layers, hidden_size, obs_channels;
+} kb_resnet_desc;
+
+long long kb_resnet_num_params(const kb_resnet_desc* d);
+long long kb_resnet_num_buffers(const kb_resnet_desc* d);
+long long kb_resnet_wpack_bytes(const kb_resnet_desc* d, int dtype);
+long long kb_resnet_workspace_bytes(const kb_resnet_desc* d, int B, int training, int dtype);
+int kb_resnet_pack_weights(const kb_resnet_desc* d, const void* const* params, const void* const* buffers, int dtype,
+                           void* wpack, long long wpack_bytes, kb_stream_t stream);
+int kb_resnet_forward(const kb_resnet_desc* d, const void* const* params, void* const* buffers, float* new_stats,
+                      const void* wpack, const float* obs, int B, int training, int dtype, void* workspace,
+                      long long ws_bytes, void* policy_out, long long policy_pitch, float* value_out, int use_tc,
+                      int num_sms, kb_stream_t stream);
+/* grads: float32 buffers shaped like params, PRE-ZEROED by the caller */
+int kb_resnet_backward(const kb_resnet_desc* d, const void* const* params, const void* wpack, int B, int dtype,
+                       void* workspace, long long ws_bytes, const void* dpolicy, long long policy_pitch,
+                       const float* dvalue, void* const* grads, int use_tc, int num_sms, kb_stream_t stream);
+
 /* ---- single 3x3 convolution on NHWC 9x9 boards (unit-test / profiling entry points):
  *      F.conv2d(padding=1, bias=False) at se_resnet.py:50,52,110 ----
  * in (B,81,Cin), w (Cout,9,Cin) packed, out (B,81,Cout), all `dtype`. backend 0 = SIMT fp32-accumulate,

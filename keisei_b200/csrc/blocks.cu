@@ -253,8 +253,8 @@ __global__ void block_bwd_dx_kernel(PassDArgs g) {
 }
 
 template <typename T>
-__global__ void relu_bwd_stats_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ z,
-                                      T* __restrict__ dzh, int C, double* sums) {
+__global__ void relu_bwd_stats_kernel(const T* dy, const T* __restrict__ y, const T* __restrict__ z,
+                                      T* dzh, int C, double* sums) {  // dzh may alias dy
   const int b = blockIdx.x, c = threadIdx.x;
   if (c >= C) return;
   const size_t base = (size_t)b * 81 * C + c;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) apply_vec_kernel(ApplyArgs g, int kApplyB
     float sg[kVW], sf[kVW], gb[kVW];
 #pragma unroll
     for (int i = 0; i < kVW; ++i) gb[i] = 0.f;
-    if (SE) {
+    if (SE && g.se != nullptr) {  // SE = residual present; the squeeze-excite scale/shift itself is optional (plain ResNet)
       ldf8(g.se + (size_t)b * 2 * C + c0, sg); ldf8(g.se + (size_t)b * 2 * C + C + c0, sf);
 #pragma unroll
       for (int i = 0; i < kVW; ++i) {
@@ -712,8 +712,8 @@ inline int ch_threads(int C) { return ((C + 31) / 32) * 32; }
 int kbk_apply(const ApplyArgs& a, cudaStream_t st) {
   KB_CHECK_ARG(a.C >= 1 && a.C <= 1024, "apply: C=%d out of range", a.C);
   if (a.B == 0) return KB_OK;
-  if (vec_ok(a.C) && ((a.se != nullptr) == (a.res != nullptr))) {
-    const bool se = a.se != nullptr, pool = a.pool != nullptr;
+  if (vec_ok(a.C) && (a.se == nullptr || a.res != nullptr)) {
+    const bool se = a.res != nullptr, pool = a.pool != nullptr;
     static int bpc = 0;
     if (bpc == 0) { const char* e = getenv("KB_APPLY_BPC"); bpc = e ? atoi(e) : 1; if (bpc < 1) bpc = 1; }
 #define KB_APPLY_VEC(SE_, POOL_)                                                                   \

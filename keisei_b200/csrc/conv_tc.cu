@@ -473,6 +473,8 @@ int kbk_conv3x3_tc(const void* in, const void* w, void* out, int B, int Cin, int
     case kEpiSum | kEpiSumSq: KB_FWD(kEpiSum | kEpiSumSq);
     case kEpiSum | kEpiSumSq | kEpiBoard: KB_FWD(kEpiSum | kEpiSumSq | kEpiBoard);
     case kEpiAffine | kEpiRelu | kEpiGbias: KB_FWD(kEpiAffine | kEpiRelu | kEpiGbias);
+    case kEpiAffine | kEpiRelu: KB_FWD(kEpiAffine | kEpiRelu);  // plain ResNet eval: conv1 / stem
+    case kEpiAffine: KB_FWD(kEpiAffine);                        // plain ResNet eval: conv2
     case kEpiAffine | kEpiRelu | kEpiPool: KB_FWD(kEpiAffine | kEpiRelu | kEpiPool);
     case kEpiAffine | kEpiBoard: KB_FWD(kEpiAffine | kEpiBoard);
     case kEpiMask | kEpiSum | kEpiDot | kEpiBoard: KB_FWD(kEpiMask | kEpiSum | kEpiDot | kEpiBoard);

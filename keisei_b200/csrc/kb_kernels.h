@@ -135,3 +135,21 @@ int kbk_mask_bwd_stats(void* d_inout, const void* z, const float* ma, const floa
 int kbk_relu_bwd_stats_f32(float* d_inout, const float* act, const float* z, long long M, int C, double* sums,
                            cudaStream_t st);
 int kbk_fill_zero(void* p, size_t bytes, cudaStream_t st);
+
+// ---- resnet_heads.cu (plain ResNet policy / value head front ends, reference models/resnet.py:49-59,76-84) ----
+// raw [B*81][3] fp32 = x [B][81][C] . {policy_conv rows 0,1; value_conv}; sums (optional) double[6] =
+// {sum p0, sum p1, sumsq p0, sumsq p1, sum v, sumsq v} (policy as a [2][2] BN block, value as a [2][1] block at +4)
+int kbk_resnet_head_conv(const void* x, int dtype, const float* wp, const float* wv, float* raw, int B, int C, double* sums,
+                         cudaStream_t st);
+// BN affine + ReLU + NCHW flatten -> p_flat [B][162] (+ bf16 copy with pitch_bf >= 162, pad zeroed), v_flat [B][81]
+int kbk_resnet_head_act(const float* raw, const float* ap, const float* bp, const float* av, const float* bv, float* p_flat,
+                        void* p_flat_bf, int pitch_bf, float* v_flat, int B, cudaStream_t st);
+// ReLU mask + un-flatten -> d3 [B*81][3]; sums double[6] = {sum d p0, sum d p1, sum d*raw p0, sum d*raw p1, sum d v, sum d*raw v}
+int kbk_resnet_head_bwd_act(const float* dp_flat, const float* dv_flat, const float* raw, const float* ap, const float* bp,
+                            const float* av, const float* bv, float* d3, int B, double* sums, cudaStream_t st);
+// BN backward (k1,k2,k3 at kp/kv + {0, kstride, 2*kstride}), dx [B][81][C] written, dwp [2][C] / dwv [C] accumulated
+int kbk_resnet_head_bwd_x(const void* x, int dtype, const float* d3, const float* raw, const float* kp, const float* kv,
+                          int kstride, const float* wp, const float* wv, void* dx, float* dwp, float* dwv, int B, int C,
+                          cudaStream_t st);
+int kbk_tanh_fwd(const float* in, float* out, float* out2, long long n, cudaStream_t st);
+int kbk_tanh_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t st);

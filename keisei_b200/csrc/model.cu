@@ -12,23 +12,14 @@
 #include <stdlib.h>
 #include "kb_common.cuh"
 #include "kb_kernels.h"
+#include "schedule_common.cuh"
 #include "../../include/keisei_b200.h"
 
 namespace {
 
-constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
+using namespace kbs;
 
-struct Bump {
-  char* base; size_t off;
-  explicit Bump(void* b) : base((char*)b), off(0) {}
-  void* take(size_t bytes) {
-    off = (off + 255) & ~(size_t)255;
-    void* p = base ? base + off : nullptr;
-    off += bytes;
-    return p;
-  }
-  float* f32(size_t n) { return (float*)take(n * sizeof(float)); }
-};
+constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
 
 struct Dims {
   int nb, C, S, G, Pc, V, S2, C0, C0p, B, dtype;
@@ -200,49 +191,6 @@ int wgrad3x3(const Dims& m, const void* x, const void* dy, float* dw, int Cin, i
 
 // tcgen05 Linear path: bf16 activations, every K a multiple of 64 after padding the small hidden sizes
 bool lin_tc(const Dims& m, int use_tc) { return use_tc && m.dtype == KB_BF16 && m.C % 64 == 0 && m.B >= 1; }
-
-GemmArgs gemm_base() { GemmArgs g; memset(&g, 0, sizeof(g)); g.splitk = 1; return g; }
-ConvEpi epi_base() { ConvEpi e; memset(&e, 0, sizeof(e)); e.board_scale = 1.f; return e; }
-
-// y[M,N] = act(x[M,K] * W[N,K]^T + bias)
-int linear_fwd(const void* x, int x_dtype, long long ldx, int M, int K, const float* W, int N, const float* bias, int relu,
-               void* y, int y_dtype, long long ldy, cudaStream_t st) {
-  GemmArgs g = gemm_base();
-  g.A = x; g.a_dtype = x_dtype; g.lda = ldx;
-  g.B = W; g.b_dtype = KB_F32; g.ldb = K; g.transB = 1;
-  g.C = y; g.c_dtype = y_dtype; g.ldc = ldy; g.bias = bias; g.relu = relu;
-  g.M = M; g.N = N; g.K = K;
-  return kbk_gemm(g, st);
-}
-// dx[M,K] = (dy[M,N] * W[N,K]) masked by mask_src > 0 ; accumulate -> atomic add onto dx
-int linear_bwd_x(const void* dy, int dy_dtype, long long ldy, int M, int N, const float* W, int K, void* dx, int dx_dtype,
-                 long long lddx, const float* mask_src, long long ld_mask, int accumulate, cudaStream_t st) {
-  GemmArgs g = gemm_base();
-  g.A = dy; g.a_dtype = dy_dtype; g.lda = ldy;
-  g.B = W; g.b_dtype = KB_F32; g.ldb = K; g.transB = 0;
-  g.C = dx; g.c_dtype = dx_dtype; g.ldc = lddx; g.mask_src = mask_src; g.ld_mask = ld_mask;
-  g.M = M; g.N = K; g.K = N; g.splitk = accumulate ? 2 : 1;
-  return kbk_gemm(g, st);
-}
-// dW[N,K] += dy[M,N]^T * x[M,K] ; db[N] += colsum(dy)
-int linear_bwd_w(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, int M, int N, int K,
-                 float* dW, float* db, cudaStream_t st) {
-  GemmArgs g = gemm_base();
-  g.A = dy; g.a_dtype = dy_dtype; g.lda = ldy; g.transA = 1;
-  g.B = x; g.b_dtype = x_dtype; g.ldb = ldx; g.transB = 0;
-  g.C = dW; g.c_dtype = KB_F32; g.ldc = K;
-  g.M = N; g.N = K; g.K = M;
-  const int tiles = kb_ceil_div(N, 64) * kb_ceil_div(K, 64);
-  int sk = kb_ceil_div(296, tiles);
-  const int max_sk = kb_ceil_div(M, 64);
-  if (sk > max_sk) sk = max_sk;
-  g.splitk = sk < 2 ? 2 : sk;  // always the atomic epilogue: dW accumulates into the pre-zeroed gradient
-  if (int r = kbk_gemm(g, st)) return r;
-  if (db) return kbk_colsum(dy, dy_dtype, ldy, 0, 0, M, N, db, st);
-  return KB_OK;
-}
-
-#define KB_TRY(expr) do { int r__ = (expr); if (r__ != KB_OK) return r__; } while (0)
 
 int check_desc(const kb_seresnet_desc* d) {
   KB_CHECK_ARG(d != nullptr, "null model descriptor");

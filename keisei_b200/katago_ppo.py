@@ -428,25 +428,30 @@ class KataGoPPOAlgorithm:
         return adv.to(device)
 
     # ---- one optimisation step -----------------------------------------------------------------------
+    def _policy_terms(self, flat_logits, masks, actions, old_lp, adv):
+        """(policy_loss, entropy, flags): masked log-softmax, gather, entropy and the clipped surrogate
+        (reference katago_ppo.py:858-888, :33-43) — one fused kernel on CUDA."""
+        p = self.params
+        if flat_logits.is_cuda:
+            out2, _, _, _, _, flags = policy_ops.ppo_policy_loss(flat_logits, masks, actions, old_lp, adv, p.clip_epsilon)
+            return out2[0], out2[1], flags
+        if flat_logits.isnan().any():
+            raise RuntimeError("NaN in raw policy logits from model forward pass")
+        if (masks.sum(dim=-1) == 0).any():
+            raise RuntimeError("Batch contains samples with zero legal actions in update(). "
+                               "Check that terminal-state masks are not stored in the buffer.")
+        logp_all = F.log_softmax(flat_logits.float().masked_fill(~masks, float("-inf")), dim=-1)
+        new_lp = logp_all.gather(1, actions.unsqueeze(1)).squeeze(1)
+        policy_loss = ppo_clip_loss(new_lp, old_lp, adv, p.clip_epsilon)
+        entropy = -(logp_all.exp() * logp_all.masked_fill(~masks, 0.0)).sum(dim=-1).mean()
+        return policy_loss, entropy, None
+
     def _losses(self, flat_logits, value_logits, score_lead, mb, value_adapter):
         """(loss, policy_loss, value_loss, score_loss, entropy, flags) for CUDA or CPU tensors
         (reference katago_ppo.py:858-924)."""
         p = self.params
-        masks, actions, old_lp, adv, cats, score_t = mb
-        if flat_logits.is_cuda:
-            out2, _, _, _, _, flags = policy_ops.ppo_policy_loss(flat_logits, masks, actions, old_lp, adv, p.clip_epsilon)
-            policy_loss, entropy = out2[0], out2[1]
-        else:
-            flags = None
-            if flat_logits.isnan().any():
-                raise RuntimeError("NaN in raw policy logits from model forward pass")
-            if (masks.sum(dim=-1) == 0).any():
-                raise RuntimeError("Batch contains samples with zero legal actions in update(). "
-                                   "Check that terminal-state masks are not stored in the buffer.")
-            logp_all = F.log_softmax(flat_logits.float().masked_fill(~masks, float("-inf")), dim=-1)
-            new_lp = logp_all.gather(1, actions.unsqueeze(1)).squeeze(1)
-            policy_loss = ppo_clip_loss(new_lp, old_lp, adv, p.clip_epsilon)
-            entropy = -(logp_all.exp() * logp_all.masked_fill(~masks, 0.0)).sum(dim=-1).mean()
+        masks, actions, old_lp, adv, cats, score_t = mb[:6]
+        policy_loss, entropy, flags = self._policy_terms(flat_logits, masks, actions, old_lp, adv)
         if value_adapter is not None:
             value_score = value_adapter.compute_value_loss(value_logits, returns=None, value_cats=cats,
                                                            score_targets=score_t, score_pred=score_lead)
@@ -537,6 +542,7 @@ class KataGoPPOAlgorithm:
             gpu_obs, gpu_masks = data["observations"], data["legal_masks"]
 
         adv = self._advantages(data, T, N, next_values, device).float().contiguous()
+        returns = adv + data["values"].reshape(-1).float().to(device)  # value targets of the scalar contract (ppo.py)
         if adv.numel() > 1:
             gae_mod.normalize_advantages_(adv)
         mv = lambda t: t.to(device, non_blocking=True)  # noqa: E731
@@ -556,7 +562,7 @@ class KataGoPPOAlgorithm:
             for start in range(0, total, batch_size):
                 idx = perm[start:start + batch_size]
                 obs_b = gpu_obs[idx]
-                mb = (gpu_masks[idx], g_actions[idx], g_old[idx], adv[idx], g_cats[idx], g_score[idx])
+                mb = (gpu_masks[idx], g_actions[idx], g_old[idx], adv[idx], g_cats[idx], g_score[idx], returns[idx])
                 tok = self._events(device, "update_forward_backward_ms")
                 if km is not None:
                     pl, vl, sl, ent, v_logits = self._step_fused(km, obs_b, mb, value_adapter)
@@ -578,7 +584,7 @@ class KataGoPPOAlgorithm:
         buffer.clear()
         denom = max(n_updates, 1)
         metrics = {k: (v / denom).item() for k, v in acc.items()}
-        if last_value_logits is not None:
+        if last_value_logits is not None and last_value_logits.shape[-1] == 3:
             valid = last_cats >= 0
             if valid.any():
                 metrics.update(compute_value_metrics(last_value_logits[valid], last_cats[valid]))

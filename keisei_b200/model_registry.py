@@ -7,6 +7,7 @@ from typing import Any, NamedTuple
 
 import torch.nn as nn
 
+from .models.resnet import ResNetModel, ResNetParams
 from .models.se_resnet import SEResNetModel, SEResNetParams
 
 
@@ -18,6 +19,7 @@ class ArchitectureSpec(NamedTuple):
 
 
 _REGISTRY: dict[str, ArchitectureSpec] = {
+    "resnet": ArchitectureSpec(ResNetModel, ResNetParams, "scalar", 50),
     "se_resnet": ArchitectureSpec(SEResNetModel, SEResNetParams, "multi_head", 50),
 }
 
@@ -44,6 +46,11 @@ def validate_model_params(architecture: str, params: dict[str, Any]) -> object:
         if validated.channels // validated.se_reduction < 1:
             raise ValueError(f"se_resnet: channels ({validated.channels}) // se_reduction "
                              f"({validated.se_reduction}) must be >= 1")
+    elif architecture == "resnet":
+        if validated.hidden_size <= 0:
+            raise ValueError(f"resnet: hidden_size must be > 0, got {validated.hidden_size}")
+        if validated.num_layers < 0:
+            raise ValueError(f"resnet: num_layers must be >= 0, got {validated.num_layers}")
     return validated
 
 

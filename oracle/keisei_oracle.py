@@ -135,6 +135,43 @@ def seresnet_forward(sd: Mapping[str, torch.Tensor], obs: torch.Tensor, num_bloc
 
 
 # ---------------------------------------------------------------------------------------------
+# Plain ResNet baseline — reference keisei/training/models/resnet.py (BASELINE.json configs[3])
+# ---------------------------------------------------------------------------------------------
+def resnet_forward(sd: Mapping[str, torch.Tensor], obs: torch.Tensor, num_layers: int, training: bool,
+                   new_stats: dict | None = None):
+    """Functional restatement of ResNetModel.forward (resnet.py:64-84) and ResidualBlock.forward
+    (resnet.py:33-37) over a state_dict. Returns (policy_logits (B,11259), value (B,1) tanh)."""
+    x = F.relu(_bn(F.conv2d(obs, sd["input_conv.weight"], padding=1), sd, "input_bn", training, new_stats))
+    for i in range(num_layers):
+        p = f"blocks.{i}."
+        out = F.relu(_bn(F.conv2d(x, sd[p + "conv1.weight"], padding=1), sd, p + "bn1", training, new_stats))
+        out = _bn(F.conv2d(out, sd[p + "conv2.weight"], padding=1), sd, p + "bn2", training, new_stats)
+        x = F.relu(out + x)
+    pol = F.relu(_bn(F.conv2d(x, sd["policy_conv.weight"]), sd, "policy_bn", training, new_stats)).flatten(1)
+    logits = F.linear(pol, sd["policy_fc.weight"], sd["policy_fc.bias"])
+    v = F.relu(_bn(F.conv2d(x, sd["value_conv.weight"]), sd, "value_bn", training, new_stats)).flatten(1)
+    v = F.relu(F.linear(v, sd["value_fc1.weight"], sd["value_fc1.bias"]))
+    return logits, torch.tanh(F.linear(v, sd["value_fc2.weight"], sd["value_fc2.bias"]))
+
+
+def scalar_ppo_losses(policy_logits, value, legal_mask, actions, old_log_probs, advantages, returns,
+                      clip_epsilon=0.2, value_loss_coeff=0.5, entropy_coeff=0.01):
+    """Standard PPO for the scalar contract. COMPOSITION UNPINNED (the reference trainer was deleted,
+    CHANGELOG.md:250-254): ppo_clip_loss (katago_ppo.py:33-43) + value_loss_coeff * MSE(value.squeeze(-1),
+    returns) (ScalarValueAdapter.compute_value_loss, value_adapter.py:49-59) - entropy_coeff * masked
+    entropy (katago_ppo.py:880-888), coefficients from PPOParams (algorithm_registry.py:11-19)."""
+    logp_all = masked_log_softmax(policy_logits, legal_mask)
+    new_logp = logp_all.gather(1, actions.unsqueeze(1)).squeeze(1)
+    ratio = (new_logp - old_log_probs).exp()
+    policy_loss = -torch.min(ratio * advantages, ratio.clamp(1 - clip_epsilon, 1 + clip_epsilon) * advantages).mean()
+    entropy = -(logp_all.exp() * logp_all.masked_fill(~legal_mask, 0.0)).sum(dim=-1).mean()
+    value_loss = F.mse_loss(value.float().squeeze(-1), returns)
+    loss = policy_loss + value_loss_coeff * value_loss - entropy_coeff * entropy
+    return {"loss": loss, "policy_loss": policy_loss, "value_loss": value_loss, "entropy": entropy,
+            "new_log_probs": new_logp}
+
+
+# ---------------------------------------------------------------------------------------------
 # KataGo-PPO losses — reference keisei/training/katago_ppo.py
 # ---------------------------------------------------------------------------------------------
 def masked_log_softmax(flat_logits, legal_mask):

@@ -214,6 +214,62 @@ def golden_update():
     print("update_tiny.npz ok", metrics)
 
 
+def golden_resnet():
+    """ResNetModel (the `resnet` registry entry) forward train/eval, BN running stats, and the gradients of the
+    restated scalar-PPO loss — model + autograd from the REAL reference classes, the loss from the surviving
+    reference functions (ppo_clip_loss, ScalarValueAdapter)."""
+    from keisei.training.model_registry import build_model
+    from keisei.training.katago_ppo import ppo_clip_loss
+    from keisei.training.value_adapter import ScalarValueAdapter
+    import torch.nn.functional as F
+
+    torch.manual_seed(3)
+    model = build_model("resnet", dict(hidden_size=32, num_layers=2))
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for name, buf in model.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(0.1 * torch.randn(buf.shape, generator=g))
+            elif name.endswith("running_var"):
+                buf.copy_(0.5 + torch.rand(buf.shape, generator=g))
+        for name, p in model.named_parameters():
+            if ".bn" in name or "_bn" in name:
+                if name.endswith("weight"):
+                    p.copy_(0.5 + torch.rand(p.shape, generator=g))
+                else:
+                    p.copy_(0.1 * torch.randn(p.shape, generator=g))
+        # keep the fixture small: the 11259 x 162 policy_fc matrix snapped to a 1/64 grid compresses ~8x
+        model.policy_fc.weight.copy_(torch.round(model.policy_fc.weight * 64) / 64)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    B = 6
+    obs, mask, actions, old_logp, adv, _cats, _score = make_inputs(B, seed=5)
+    returns = torch.randn(B, generator=g).clamp(-1, 1)
+    out = {f"sd/{k}": _np(v) for k, v in sd0.items()}
+    out.update(obs=_np(obs), mask=_np(mask), actions=_np(actions), old_logp=_np(old_logp), adv=_np(adv), returns=_np(returns))
+    model.eval()
+    with torch.no_grad():
+        pl_e, v_e = model(obs)
+    out.update(eval_policy=_np(pl_e), eval_value=_np(v_e))
+    model.train()
+    logits, value = model(obs)
+    logp_all = F.log_softmax(logits.masked_fill(~mask, float("-inf")), dim=-1)
+    new_logp = logp_all.gather(1, actions.unsqueeze(1)).squeeze(1)
+    pl = ppo_clip_loss(new_logp, old_logp, adv, 0.2)
+    ent = -(logp_all.exp() * logp_all.masked_fill(~mask, 0.0)).sum(-1).mean()
+    vl = ScalarValueAdapter().compute_value_loss(value, returns, None, None)
+    loss = pl + 0.5 * vl - 0.01 * ent
+    loss.backward()
+    out.update(train_policy=_np(logits), train_value=_np(value), loss=_np(loss), policy_loss=_np(pl), value_loss=_np(vl),
+               entropy=_np(ent), new_logp=_np(new_logp))
+    for k, p in model.named_parameters():
+        out[f"grad/{k}"] = _np(p.grad)
+    for k, v in model.state_dict().items():
+        if "running_" in k or "num_batches" in k:
+            out[f"sd_after/{k}"] = _np(v)
+    np.savez_compressed(OUT / "resnet_tiny.npz", **out)
+    print("resnet_tiny.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB raw")
+
+
 if __name__ == "__main__":
     if not REF.exists():
         sys.exit("needs /root/reference (build container only)")
@@ -224,3 +280,4 @@ if __name__ == "__main__":
     golden_rollout()
     golden_model()
     golden_update()
+    golden_resnet()
