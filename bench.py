@@ -270,6 +270,11 @@ def run_ours(args) -> None:
 
     if not args.no_update:
         line["update"] = bench_update(args, algo, model, device, rank, world)
+    if not args.no_extra:
+        line["league_rollout"] = bench_league(algo, device, rank, world)
+        algo.optimizer.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        line["resnet_update"] = bench_resnet_update(args, device, rank, world)
     if rank == 0:
         line["roofline"] = conv_roofline(device)
         if world == 1 and not args.no_cpu:
@@ -327,6 +332,78 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
             "includes": "fwd+losses+bwd+allreduce+unscale+clip+Adam"}
 
 
+def bench_resnet_update(args, device, rank, world) -> dict:
+    """BASELINE.json configs[3]: ResNet baseline (hidden 256 x 40 layers, 50-ch obs, scalar value) standard-PPO
+    update, global batch 4096 split over the ranks, bf16: forward (batch-stat BN) + fused policy loss + MSE value
+    loss + backward + gradient all-reduce + unscale/clip/Adam. Loss composition unpinned (see keisei_b200/ppo.py)."""
+    from keisei_b200.algorithm_registry import PPOParams
+    from keisei_b200.distributed import GradSync
+    from keisei_b200.models import ResNetModel, ResNetParams
+    from keisei_b200.ppo import PPOAlgorithm
+    GB = 4096
+    Bu = GB // world
+    torch.manual_seed(1)
+    model = ResNetModel(ResNetParams(hidden_size=256, num_layers=40)).to(device)
+    algo = PPOAlgorithm(PPOParams(batch_size=Bu), model, use_amp=True)
+    g = torch.Generator().manual_seed(17 + rank)
+    obs = torch.randn(Bu, 50, 9, 9, generator=g).to(device)
+    mask = torch.zeros(Bu, A, dtype=torch.bool)
+    actions = torch.randint(0, A, (Bu,), generator=g)
+    mask.scatter_(1, torch.randint(0, A, (Bu, 80), generator=g), True)
+    mask[torch.arange(Bu), actions] = True
+    mb = (mask.to(device), actions.to(device), (-3 * torch.rand(Bu, generator=g)).to(device), torch.randn(Bu, generator=g).to(device),
+          None, None, torch.randn(Bu, generator=g).clamp(-1, 1).to(device))
+    if world > 1:
+        algo.grad_sync = GradSync()
+        algo.grad_sync.broadcast_parameters(model)
+    model.train()
+    km = algo._kernel_model(device)
+
+    def step():
+        algo._step_fused(km, obs, mb, None)
+        algo.scaler.unscale_(algo.optimizer)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), algo.params.grad_clip)
+        algo.scaler.step(algo.optimizer)
+        algo.scaler.update()
+
+    steps, warm = max(2, min(args.steps, 5)), 3
+    ms = timed(step, steps, warm, device, world)
+    # rollout on the same model: select_actions at 4096 boards per GPU
+    r_obs, r_mask = synth_boards(GB, 300 + rank, device)
+    ms_roll = timed(lambda: algo.select_actions(r_obs, r_mask), steps, warm, device, world)
+    flop_fwd = 18.66e6 + 80 * 95.55e6
+    out = {"metric": "standard-PPO update samples/s (ResNet 40x256, batch 4096)", "value": GB / (ms * 1e-3), "unit": "samples/s",
+           "ms_per_step": ms, "steps": steps, "warmup": warm, "global_batch": GB, "per_gpu_batch": Bu, "scaling": "strong",
+           "frac_of_tensor_roofline": ((3 * flop_fwd - 18.66e6) * Bu / (ms * 1e-3) / 1e12) / peaks()["bf16_tflops_sustained"],
+           "rollout_positions_per_s": world * GB / (ms_roll * 1e-3), "rollout_ms_per_step": ms_roll,
+           "includes": "fwd+losses+bwd+allreduce+unscale+clip+Adam", "parity": "model pinned (tests/golden/resnet_tiny.npz); loss composition unpinned"}
+    del model, algo
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_league(algo, device, rank, world) -> dict:
+    """BASELINE.json configs[4]: league-scale rollout, 512 envs per GPU (the `num_games` cap, config.py:574), 128
+    consecutive select_actions steps timed end to end incl. launch overhead; and the split variant 256 learner +
+    4 x 64 opponent sub-batches per step (katago_loop.py:284-431). No communication between ranks."""
+    Bl = 512
+    obs, mask = synth_boards(Bl, 500 + rank, device)
+    def run128():
+        for _ in range(128):
+            algo.select_actions(obs, mask)
+    ms = timed(run128, 2, 3, device, world)
+    parts = [(0, 256)] + [(256 + 64 * k, 320 + 64 * k) for k in range(4)]
+    def split128():
+        for _ in range(128):
+            for lo, hi in parts:
+                algo.select_actions(obs[lo:hi], mask[lo:hi])
+    ms_split = timed(split128, 2, 3, device, world)
+    return {"metric": "league rollout positions/s (512 envs per GPU, 128 consecutive steps)", "value": world * Bl * 128 / (ms * 1e-3),
+            "unit": "positions/s", "ms_per_128_steps": ms, "envs_per_gpu": Bl, "scaling": "weak",
+            "split_variant": {"value": world * Bl * 128 / (ms_split * 1e-3), "unit": "positions/s", "ms_per_128_steps": ms_split,
+                              "sub_batches": "256 learner + 4 x 64 opponents (same weights: synthetic)"}}
+
+
 def update_e2e(algo, device, rank, world) -> dict:
     """The public call a user makes: KataGoPPOAlgorithm.update(buffer, next_values) on a host-resident
     KataGoRolloutBuffer of T=128 x N=64 = 8192 samples (the reference's profiled update shape,
@@ -374,6 +451,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-update", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[3] (ResNet PPO) and configs[4] (league rollout) legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -153,6 +153,16 @@ int kb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int Cin, i
 /* w (Cout,Cin,3,3) float32 -> wf (Cout,9,Cinp) and optional wd (Cinp,9,Cout) (flipped taps) in `dtype` */
 int kb_pack_conv_weight(const float* w, void* wf, void* wd, int Cout, int Cin, int Cinp, int dtype, kb_stream_t stream);
 
+/* ---- tail of a GlobalPoolBiasBlock as one kernel (unit-test / profiling entry point): se_resnet.py:83-90 + the
+ *      next block's _global_pool (:93-98). bf16 NHWC tiles staged by TMA bulk copies; 64 <= C <= 256, C % 8 == 0.
+ * se_in = board_mean * bn_a + bn_b (bn_a/bn_b null: identity); se = W2 relu(W1 se_in + b1) + b2 (w1 (S,C), w2 (2C,S));
+ * out = relu((z*bn_a+bn_b) * sigmoid(se[:C]) + se[C:] + res); pool (B,3C) = mean,max,std of out; ties (B,C) optional.
+ * se_out (B,2C) is required (kernel-internal hand-off): raw logits when se_raw != 0, else its first half holds sigmoid(scale). */
+int kb_se_block_tail(const void* z, const void* res, void* out, const float* bn_a, const float* bn_b,
+                     const float* board_mean, const float* w1, const float* b1, const float* w2, const float* b2,
+                     float* se_in_out, float* seh_out, float* se_out, int se_raw, float* pool, void* pool_bf16,
+                     float* ties, int B, int C, int S, int num_sms, kb_stream_t stream);
+
 /* ---- Linear / 1x1-conv layer on the tcgen05 path (nn.Linear at se_resnet.py:57-66, heads :119-130) ----
  * w (N,K) float32 -> bf16 (Np,Kp) zero padded, Np % 128 == 0, Kp % 64 == 0. */
 int kb_pack_linear_weight(const float* w, void* out_bf16, int N, int K, int Np, int Kp, kb_stream_t stream);

@@ -3,6 +3,7 @@
 // negative error code after kb_set_error().
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include "conv_epilogue.cuh"
 
 // ---- conv_simt.cu ----
@@ -135,6 +136,28 @@ int kbk_mask_bwd_stats(void* d_inout, const void* z, const float* ma, const floa
 int kbk_relu_bwd_stats_f32(float* d_inout, const float* act, const float* z, long long M, int C, double* sums,
                            cudaStream_t st);
 int kbk_fill_zero(void* p, size_t bytes, cudaStream_t st);
+
+// ---- se_apply.cu: SE MLP + scale/shift + residual + ReLU + next-block pool statistics, TMA-bulk staged (bf16) ----
+struct SeApplyArgs {
+  const __nv_bfloat16* z;    // [B][81][C] conv2 output (raw when a/b are given, BN already folded when they are null)
+  const __nv_bfloat16* res;  // [B][81][C] block input
+  __nv_bfloat16* out;        // [B][81][C] block output
+  const float* a; const float* b;            // [C] BN2 affine or null
+  const float* bmean;        // [B][C] board means of z (before the a/b affine)
+  const float* w1; const float* b1;          // se_fc1 [S][C], [S]
+  const float* w2; const float* b2;          // se_fc2 [2C][S], [2C]
+  float* se_in_out;          // [B][C] or null   (saved for backward)
+  float* seh_out;            // [B][S] or null
+  float* se_out;             // [B][2C] REQUIRED (scratch in eval): se_raw != 0 -> raw logits (saved for backward),
+                             //         se_raw == 0 -> the scale half holds sigmoid(scale)
+  int se_raw;
+  float* pool;               // [B][3C] mean, max, std of out
+  __nv_bfloat16* pool_bf;    // [B][3C] or null
+  float* ties;               // [B][C] or null: pixels equal to the board max
+  int B, C, S;
+};
+int kbk_se_apply_supported(int C, int S);
+int kbk_se_apply(const SeApplyArgs& a, int num_sms, cudaStream_t st);
 
 // ---- resnet_heads.cu (plain ResNet policy / value head front ends, reference models/resnet.py:49-59,76-84) ----
 // raw [B*81][3] fp32 = x [B][81][C] . {policy_conv rows 0,1; value_conv}; sums (optional) double[6] =

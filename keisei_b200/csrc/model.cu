@@ -312,6 +312,10 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
   }
 
   const bool ltc = lin_tc(m, use_tc);
+  // SE MLP + scale/shift + residual + ReLU + pool statistics as one TMA-bulk-staged kernel (se_apply.cu)
+  static int no_se_apply = -1;
+  if (no_se_apply < 0) { const char* e = getenv("KB_NO_SE_APPLY"); no_se_apply = (e && e[0] == '1') ? 1 : 0; }
+  const bool fuse_se = ltc && !no_se_apply && kbk_se_apply_supported(C, m.S);
   bool pool_bf_ready = false;  // the producing apply kernel also writes the bf16 copy of the pool statistics
   // ---- residual tower ----
   for (int i = 0; i < m.nb; ++i) {
@@ -342,7 +346,7 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
       KB_TRY(conv3x3(m, bw.a1, wp.wf(i, 1), bw.z2, C, C, e2, use_tc, num_sms, st));
       KB_TRY(bn_fin(l2, pi_blk(i, 4), bi_blk(i, 3), C));
       // SE squeeze input: mean_p(bn2(z2)) = a2 * mean_p(z2) + b2
-      KB_TRY(kbk_affine_rows(bw.bmean2, w.bn_a(l2), w.bn_b(l2), bw.se_in, ltc ? w.sein_bf : nullptr, B, C, st));
+      if (!fuse_se) KB_TRY(kbk_affine_rows(bw.bmean2, w.bn_a(l2), w.bn_b(l2), bw.se_in, ltc ? w.sein_bf : nullptr, B, C, st));
       z2 = bw.z2; xout = bw.xout; pool_next = w.pool(m, i + 1); se_in = bw.se_in;
     } else {
       ConvEpi e = epi_base();
@@ -350,10 +354,24 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
       KB_TRY(conv3x3(m, x_cur, wp.wf(i, 0), w.ey1, C, C, e, use_tc, num_sms, st));
       ConvEpi e2 = epi_base();
       e2.scale = wp.bn_a(l2); e2.shift = wp.bn_b(l2); e2.board_sum = bw.bmean2; e2.board_scale = 1.f / 81.f;
-      e2.board_bf = ltc ? w.sein_bf : nullptr;
+      e2.board_bf = (ltc && !fuse_se) ? w.sein_bf : nullptr;
       KB_TRY(conv3x3(m, w.ey1, wp.wf(i, 1), w.ey2, C, C, e2, use_tc, num_sms, st));
       z2 = w.ey2; xout = (x_cur == w.ea) ? w.eb : w.ea; pool_next = (pool_cur == w.epool_a) ? w.epool_b : w.epool_a;
       se_in = bw.bmean2;  // BN affine already applied in the conv epilogue
+    }
+    if (fuse_se) {
+      SeApplyArgs sa; memset(&sa, 0, sizeof(sa));
+      sa.z = (const bf16*)z2; sa.res = (const bf16*)x_cur; sa.out = (bf16*)xout;
+      sa.a = training ? w.bn_a(l2) : nullptr; sa.b = training ? w.bn_b(l2) : nullptr;
+      sa.bmean = bw.bmean2;
+      sa.w1 = P(pi_blk(i, 10)); sa.b1 = P(pi_blk(i, 11)); sa.w2 = P(pi_blk(i, 12)); sa.b2 = P(pi_blk(i, 13));
+      sa.se_in_out = training ? bw.se_in : nullptr; sa.seh_out = training ? bw.seh : nullptr; sa.se_out = bw.se; sa.se_raw = training ? 1 : 0;
+      sa.pool = pool_next; sa.pool_bf = (bf16*)w.pool_bf; sa.ties = training ? w.ties(m, i + 1) : nullptr;
+      sa.B = B; sa.C = C; sa.S = m.S;
+      KB_TRY(kbk_se_apply(sa, num_sms, st));
+      pool_bf_ready = true;
+      x_cur = xout; pool_cur = pool_next;
+      continue;
     }
     // SE excite: (scale, shift) = W2 relu(W1 se_in + b1) + b2   (se_resnet.py:83-86)
     if (ltc) {
