@@ -105,6 +105,22 @@ int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const* params, vo
                         float* new_stats, const void* wpack, const float* obs, int B, int training, int dtype, void* workspace,
                         long long ws_bytes, void* policy_out, long long policy_pitch, float* value_out,
                         float* score_out, int use_tc, int num_sms, kb_stream_t stream);
+/* SyncBatchNorm variants — the reference's data-parallel default (`sync_batchnorm = true`: katago_loop.py:494-508 wraps
+ * the model in torch.nn.SyncBatchNorm before DDP). `hook(user, buf, n_doubles, stream)` must sum `buf` (device doubles)
+ * over the `world` ranks in stream order and return 0; it is called once per BatchNorm layer in the forward (batch
+ * sum / sum of squares) and once in the backward (sum dz, sum dz*z; dgamma/dbeta keep the rank's own share, as
+ * torch.nn.SyncBatchNorm does). hook == NULL or world == 1 reproduces kb_seresnet_forward / _backward. */
+typedef int (*kb_allreduce_hook)(void* user, void* buf, long long n_doubles, kb_stream_t stream);
+int kb_seresnet_forward_sync(const kb_seresnet_desc* d, const void* const* params, void* const* buffers,
+                             float* new_stats, const void* wpack, const float* obs, int B, int training, int dtype,
+                             void* workspace, long long ws_bytes, void* policy_out, long long policy_pitch,
+                             float* value_out, float* score_out, int use_tc, int num_sms, kb_allreduce_hook hook,
+                             void* hook_user, int world, kb_stream_t stream);
+int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* const* params, const void* wpack, int B,
+                              int dtype, void* workspace, long long ws_bytes, const void* dpolicy,
+                              long long policy_pitch, const float* dvalue, const float* dscore, void* const* grads,
+                              int use_tc, int num_sms, kb_allreduce_hook hook, void* hook_user, int world,
+                              kb_stream_t stream);
 /* grads: float32 buffers shaped like params, PRE-ZEROED by the caller */
 int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const* params, const void* wpack, int B,
                          int dtype, void* workspace, long long ws_bytes, const void* dpolicy,

@@ -171,17 +171,22 @@ __global__ void bn2_bwd_sums_kernel(const float* s_du, const float* s_duz, const
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(double* sums, double count, const float* w, const float* mean, const float* invstd,
-                                       float* k1, float* k2, float* k3, float* dgamma, float* dbeta, int C) {
+// sums: [2][C] (sum dzh, sum dzh*z) over the batch that defines the BatchNorm statistics (all ranks under
+// SyncBatchNorm); sums_local (optional): this rank's share, used for dgamma / dbeta (data-parallel gradient
+// averaging sums the ranks' shares, exactly like torch.nn.SyncBatchNorm's backward).
+__global__ void bn_bwd_finalize_kernel(double* sums, double* sums_local, double count, const float* w, const float* mean,
+                                       const float* invstd, float* k1, float* k2, float* k3, float* dgamma, float* dbeta, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double S1 = sums[c], S2 = sums[C + c];
   sums[c] = 0.0; sums[C + c] = 0.0;
+  double L1 = S1, L2 = S2;
+  if (sums_local) { L1 = sums_local[c]; L2 = sums_local[C + c]; }
   const double mu = mean[c], is = invstd[c];
   const double dg = is * (S2 - mu * S1);
   const double kk1 = (double)w[c] * is;
-  if (dgamma) dgamma[c] = (float)dg;
-  if (dbeta) dbeta[c] = (float)S1;
+  if (dgamma) dgamma[c] = (float)(is * (L2 - mu * L1));
+  if (dbeta) dbeta[c] = (float)L1;
   k1[c] = (float)kk1;
   k2[c] = (float)(kk1 * is * dg / count);
   k3[c] = (float)(kk1 * (S1 / count - mu * is * dg / count));
@@ -199,7 +204,7 @@ __global__ void block_bwd_dz2_kernel(PassBArgs g) {
   const float k1 = g.k1[c], k2 = g.k2[c], k3 = g.k3[c];
 #pragma unroll 9
   for (int p = 0; p < 81; ++p) {
-    const float du = kb_to_float<T>(xp[(size_t)p * C]) > 0.f ? kb_to_float<T>(dxp[(size_t)p * C]) : 0.f;
+    const float du = (g.xp == nullptr || kb_to_float<T>(xp[(size_t)p * C]) > 0.f) ? kb_to_float<T>(dxp[(size_t)p * C]) : 0.f;
     const float dzh = fmaf(du, sg, dm);
     dz2[(size_t)p * C] = kb_from_float<T>(k1 * dzh - k2 * kb_to_float<T>(z2[(size_t)p * C]) - k3);
   }
@@ -224,7 +229,7 @@ __global__ void block_bwd_dx_kernel(PassDArgs g) {
   const T* dxp = g.dxp ? (const T*)g.dxp + base : nullptr;
   const T* xp = g.xp ? (const T*)g.xp + base : nullptr;
   T* dx = (T*)g.dx + base;
-  float gmean = 0.f, gmax = 0.f, gstd = 0.f, mean = 0.f, mx = 0.f;
+  float gmean = 0.f, gmax = 0.f, gstd = 0.f, mean = 0.f, mx = 0.f, hs = 0.f, hsz = 0.f;
   if (g.dpool) {
     const float* pr = g.pool + (size_t)b * 3 * C;
     const float* dp = g.dpool + (size_t)b * 3 * C;
@@ -248,8 +253,16 @@ __global__ void block_bwd_dx_kernel(PassDArgs g) {
       const float xv = kb_to_float<T>(x[(size_t)p * C]);
       v += gmean + (xv == mx ? gmax : 0.f) + gstd * (xv - mean);
     }
-    dx[(size_t)p * C] = kb_from_float<T>(v);
+    if (g.mask_out && !(kb_to_float<T>(x[(size_t)p * C]) > 0.f)) v = 0.f;
+    const T st = kb_from_float<T>(v);
+    dx[(size_t)p * C] = st;
+    if (g.z_next) {
+      const float r = kb_to_float<T>(st);
+      hs += r;
+      hsz = fmaf(r, kb_to_float<T>(((const T*)g.z_next)[base + (size_t)p * C]), hsz);
+    }
   }
+  if (g.z_next) { g.s_du[(size_t)b * C + c] = hs; g.s_duz[(size_t)b * C + c] = hsz; }
 }
 
 template <typename T>
@@ -511,12 +524,14 @@ __global__ void __launch_bounds__(256) block_bwd_dz2_vec_kernel(PassBArgs g) {
   for (int i = 0; i < kVW; ++i) { sg[i] = sigmoidf_(sg[i]); dm[i] *= (1.f / 81.f); }
   for (int p = pl; p < 81; p += NPL) {
     float d[kVW], x[kVW], z[kVW];
+#pragma unroll
+    for (int i = 0; i < kVW; ++i) x[i] = 0.f;
     V8<T>::load((const T*)g.dxp + base + (size_t)p * C, d);
-    V8<T>::load((const T*)g.xp + base + (size_t)p * C, x);
+    if (g.xp) V8<T>::load((const T*)g.xp + base + (size_t)p * C, x);  // null: dxp is already masked (du)
     V8<T>::load((const T*)g.z2 + base + (size_t)p * C, z);
 #pragma unroll
     for (int i = 0; i < kVW; ++i) {
-      const float du = x[i] > 0.f ? d[i] : 0.f;
+      const float du = (g.xp == nullptr || x[i] > 0.f) ? d[i] : 0.f;
       d[i] = k1[i] * fmaf(du, sg[i], dm[i]) - k2[i] * z[i] - k3[i];
     }
     V8<T>::store((T*)g.dz2 + base + (size_t)p * C, d);
@@ -524,14 +539,16 @@ __global__ void __launch_bounds__(256) block_bwd_dz2_vec_kernel(PassBArgs g) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) block_bwd_dx_vec_kernel(PassDArgs g) {
+__global__ void __launch_bounds__(256, 4) block_bwd_dx_vec_kernel(PassDArgs g) {
   __shared__ float red[256 * kVW];
+  __shared__ float red2[256 * kVW];
   const int C = g.C, C8 = C / kVW, NPL = 256 / C8;
   const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
   const size_t base = (size_t)b * 81 * C + c0;
-  float gmean[kVW], gmax[kVW], gstd[kVW], mean[kVW], mx[kVW];
+  float gmean[kVW], gmax[kVW], gstd[kVW], mean[kVW], mx[kVW], hs[kVW], hsz[kVW];
+  const bool need_x = g.dpool != nullptr || g.mask_out != 0;
 #pragma unroll
-  for (int i = 0; i < kVW; ++i) { gmean[i] = 0.f; gmax[i] = 0.f; gstd[i] = 0.f; mean[i] = 0.f; mx[i] = 0.f; }
+  for (int i = 0; i < kVW; ++i) { gmean[i] = 0.f; gmax[i] = 0.f; gstd[i] = 0.f; mean[i] = 0.f; mx[i] = 0.f; hs[i] = 0.f; hsz[i] = 0.f; }
   if (g.dpool) {
     const float* pr = g.pool + (size_t)b * 3 * C;
     const float* dp = g.dpool + (size_t)b * 3 * C;
@@ -576,7 +593,18 @@ __global__ void __launch_bounds__(256) block_bwd_dx_vec_kernel(PassDArgs g) {
 #pragma unroll
       for (int i = 0; i < kVW; ++i) v[i] += gmean[i] + (xx[i] == mx[i] ? gmax[i] : 0.f) + gstd[i] * (xx[i] - mean[i]);
     }
+    if (g.mask_out) {
+#pragma unroll
+      for (int i = 0; i < kVW; ++i) v[i] = xx[i] > 0.f ? v[i] : 0.f;
+    }
     V8<T>::store((T*)g.dx + base + (size_t)p * C, v);
+    if (g.z_next) {
+      float zn[kVW];
+      V8<T>::load((const T*)g.z_next + base + (size_t)p * C, zn);
+      V8<T>::round(v);
+#pragma unroll
+      for (int i = 0; i < kVW; ++i) { hs[i] += v[i]; hsz[i] = fmaf(v[i], zn[i], hsz[i]); }
+    }
   };
   for (int p = pl; p < 81; p += 2 * NPL) {  // two pixels per iteration: up to 8 independent vector loads in flight
     const bool two = p + NPL < 81;
@@ -587,15 +615,27 @@ __global__ void __launch_bounds__(256) block_bwd_dx_vec_kernel(PassDArgs g) {
     if (g.dxc) V8<T>::load((const T*)g.dxc + base + (size_t)p * C, v0);
     if (g.dxp) V8<T>::load((const T*)g.dxp + base + (size_t)p * C, t0);
     if (g.xp) V8<T>::load((const T*)g.xp + base + (size_t)p * C, y0);
-    if (g.dpool) V8<T>::load((const T*)g.x + base + (size_t)p * C, x0);
+    if (need_x) V8<T>::load((const T*)g.x + base + (size_t)p * C, x0);
     if (two) {
       if (g.dxc) V8<T>::load((const T*)g.dxc + base + (size_t)p1 * C, v1);
       if (g.dxp) V8<T>::load((const T*)g.dxp + base + (size_t)p1 * C, t1);
       if (g.xp) V8<T>::load((const T*)g.xp + base + (size_t)p1 * C, y1);
-      if (g.dpool) V8<T>::load((const T*)g.x + base + (size_t)p1 * C, x1);
+      if (need_x) V8<T>::load((const T*)g.x + base + (size_t)p1 * C, x1);
     }
     one(p, v0, t0, y0, x0);
     if (two) one(p1, v1, t1, y1, x1);
+  }
+  if (g.z_next) {  // per-(board, channel) sums of du and du * z_next across the pixel lanes
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kVW; ++i) { red[pl * C + c0 + i] = hs[i]; red2[pl * C + c0 + i] = hsz[i]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float a = 0.f, q = 0.f;
+      for (int l = 0; l < NPL; ++l) { a += red[l * C + c]; q += red2[l * C + c]; }
+      g.s_du[(size_t)b * C + c] = a;
+      g.s_duz[(size_t)b * C + c] = q;
+    }
   }
 }
 
@@ -605,7 +645,7 @@ __global__ void __launch_bounds__(256) block_bwd_dx_vec_kernel(PassDArgs g) {
 constexpr int kStatsBoardsPerCta = 4;  // boards per CTA: 4x fewer double atomics on the 2*C channel accumulators
 
 template <typename T>
-__global__ void __launch_bounds__(256) relu_bwd_stats_vec_kernel(const T* dy, const T* __restrict__ y,
+__global__ void __launch_bounds__(256, 4) relu_bwd_stats_vec_kernel(const T* dy, const T* __restrict__ y,
                                                                    const T* __restrict__ z, T* dzh, int B, int C,
                                                                    const float* __restrict__ ma, const float* __restrict__ mb,
                                                                    float* __restrict__ board_sum, double* sums) {
@@ -790,8 +830,8 @@ int kbk_bn2_bwd_sums(const float* s_du, const float* s_duz, const float* se, con
 }
 
 int kbk_bn_bwd_finalize(double* sums, double count, const float* w, const float* mean, const float* invstd, float* k1,
-                        float* k2, float* k3, float* dgamma, float* dbeta, int C, cudaStream_t st) {
-  bn_bwd_finalize_kernel<<<kb_ceil_div(C, 128), 128, 0, st>>>(sums, count, w, mean, invstd, k1, k2, k3, dgamma, dbeta, C);
+                        float* k2, float* k3, float* dgamma, float* dbeta, int C, cudaStream_t st, double* sums_local) {
+  bn_bwd_finalize_kernel<<<kb_ceil_div(C, 128), 128, 0, st>>>(sums, sums_local, count, w, mean, invstd, k1, k2, k3, dgamma, dbeta, C);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

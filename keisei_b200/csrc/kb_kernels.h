@@ -100,7 +100,7 @@ int kbk_bn2_bwd_sums(const float* s_du, const float* s_duz, const float* se, con
 // BN backward finalize: from sums (sum dzh, sum dzh*z) -> m1, m2', dgamma, dbeta
 int kbk_bn_bwd_finalize(double* sums /*[2][C], zeroed afterwards*/, double count, const float* w, const float* mean,
                         const float* invstd, float* k1, float* k2, float* k3, float* dgamma, float* dbeta, int C,
-                        cudaStream_t st);
+                        cudaStream_t st, double* sums_local = nullptr);
 struct PassBArgs {
   int B, C, dtype;
   const void* dxp; const void* xp; const void* z2;
@@ -122,6 +122,14 @@ struct PassDArgs {
   const float* dpool;// [B][3C] grad wrt pool (may be null)
   const float* ties; // [B][C] tie counts of the board max from the forward (null -> counted here)
   void* dx;          // out
+  // Hand-off to the producing block (whose output is x): when mask_out != 0 the result is stored as
+  // du = dx * [x > 0] (the gradient after that block's final ReLU), and with z_next (that block's raw conv2 output)
+  // the per-(board, channel) sums of du and du * z_next come out as well — the producing block then needs no
+  // separate reduction pass and never re-reads its output for the mask.
+  int mask_out;
+  const void* z_next; // [B][81][C] or null
+  float* s_du;        // [B][C]  (with z_next)
+  float* s_duz;       // [B][C]
 };
 int kbk_block_bwd_dx(const PassDArgs& a, cudaStream_t st);  // pass D
 // stem / generic: dzh = dy * (y > 0), channel sums of dzh and dzh*z   (y = post-activation, z = raw)

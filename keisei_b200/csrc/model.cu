@@ -105,6 +105,7 @@ struct Ws {
   float* bn;               // [2nb+2][4][Cmax]: a, b, mean, invstd
   float *g, *p1raw, *p1act, *vh, *sh;
   double* dsums;           // [2][Cmax]
+  double* dsums_local;     // [2][Cmax]: this rank's sums under SyncBatchNorm (dgamma / dbeta)
   // eval-only ping-pong
   void *ea, *eb, *ey1, *ey2;
   float *epool_a, *epool_b;
@@ -129,6 +130,7 @@ void carve(const Dims& m, void* base, int training, Ws& w, BlockWs* blk_storage)
   w.Cmax = m.C > m.Pc ? m.C : m.Pc;
   w.blk = blk_storage;
   w.dsums = (double*)b.take(2 * (size_t)w.Cmax * sizeof(double));
+  w.dsums_local = (double*)b.take(2 * (size_t)w.Cmax * sizeof(double));
   w.obs_p = b.take(B * 81 * m.C0p * m.esz);
   w.g = b.f32(B * m.C);
   w.p1raw = b.f32((size_t)m.M * m.Pc);
@@ -264,6 +266,19 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
                                    float* new_stats, const void* wpack, const float* obs, int B, int training, int dtype, void* workspace,
                                    long long ws_bytes, void* policy_out, long long policy_pitch, float* value_out,
                                    float* score_out, int use_tc, int num_sms, cudaStream_t st) {
+  return kb_seresnet_forward_sync(d, params, buffers, new_stats, wpack, obs, B, training, dtype, workspace, ws_bytes, policy_out,
+                                  policy_pitch, value_out, score_out, use_tc, num_sms, nullptr, nullptr, 1, st);
+}
+
+// SyncBatchNorm variant (reference katago_loop.py:494-508 wraps the model in SyncBatchNorm + DDP by default): `hook`
+// all-reduces (sum) the per-channel double sums across `world` ranks between each convolution and its BatchNorm
+// finalize, so every rank normalises with the statistics of the GLOBAL batch. hook == NULL / world == 1: local.
+extern "C" int kb_seresnet_forward_sync(const kb_seresnet_desc* d, const void* const* params, void* const* buffers,
+                                        float* new_stats, const void* wpack, const float* obs, int B, int training, int dtype,
+                                        void* workspace, long long ws_bytes, void* policy_out, long long policy_pitch,
+                                        float* value_out, float* score_out, int use_tc, int num_sms, kb_allreduce_hook hook,
+                                        void* hook_user, int world, cudaStream_t st) {
+  KB_CHECK_ARG(world >= 1, "world must be >= 1");
   KB_TRY(check_desc(d));
   KB_CHECK_ARG(dtype == KB_F32 || dtype == KB_BF16, "bad dtype");
   KB_CHECK_ARG(B >= 1, "batch must be >= 1");
@@ -278,7 +293,7 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
   const int C = m.C;
   auto P = [&](int i) { return (const float*)params[i]; };
   auto BUF = [&](int i) { return (float*)buffers[i]; };
-  const double count = (double)m.M;
+  const double count = (double)m.M * world;
   const int LP = 2 * m.nb + 1;  // policy BN layer id
   // training-mode BatchNorm: new running statistics go to `new_stats` ([layer][2][Cmax]) when given
   // (functional variant for autograd frameworks) or in place into `buffers` (num_batches_tracked too).
@@ -286,6 +301,10 @@ extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const*
     float* rm_out = new_stats ? new_stats + (size_t)layer * 2 * w.Cmax : BUF(bbase);
     float* rv_out = new_stats ? new_stats + (size_t)layer * 2 * w.Cmax + w.Cmax : BUF(bbase + 1);
     long long* nbt = new_stats ? nullptr : (long long*)buffers[bbase + 2];
+    if (hook && world > 1) {
+      const int hr = hook(hook_user, w.dsums, 2LL * Cl, (kb_stream_t)st);
+      if (hr != 0) { kb_set_error("BatchNorm all-reduce hook failed (rc=%d)", hr); return KB_ERR_INVALID; }
+    }
     return kbk_bn_finalize(w.dsums, count, P(pw), P(pw + 1), BUF(bbase), BUF(bbase + 1), rm_out, rv_out, nbt, kBnMomentum,
                            kBnEps, Cl, w.bn_a(layer), w.bn_b(layer), w.bn_mean(layer), w.bn_invstd(layer), st);
   };
@@ -455,6 +474,18 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
                                     int dtype, void* workspace, long long ws_bytes, const void* dpolicy,
                                     long long policy_pitch, const float* dvalue, const float* dscore,
                                     void* const* grads, int use_tc, int num_sms, cudaStream_t st) {
+  return kb_seresnet_backward_sync(d, params, wpack, B, dtype, workspace, ws_bytes, dpolicy, policy_pitch, dvalue, dscore, grads,
+                                   use_tc, num_sms, nullptr, nullptr, 1, st);
+}
+
+// Backward of kb_seresnet_forward_sync: the BatchNorm-backward sums (sum dz, sum dz*z) are all-reduced through `hook`
+// for the data gradient; dgamma / dbeta keep this rank's share (gradient averaging adds the ranks up afterwards).
+extern "C" int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* const* params, const void* wpack, int B,
+                                         int dtype, void* workspace, long long ws_bytes, const void* dpolicy,
+                                         long long policy_pitch, const float* dvalue, const float* dscore, void* const* grads,
+                                         int use_tc, int num_sms, kb_allreduce_hook hook, void* hook_user, int world,
+                                         cudaStream_t st) {
+  KB_CHECK_ARG(world >= 1, "world must be >= 1");
   KB_TRY(check_desc(d));
   KB_CHECK_ARG(dtype == KB_F32 || dtype == KB_BF16, "bad dtype");
   KB_CHECK_ARG(B >= 1 && policy_pitch >= 81LL * 139, "bad shape");
@@ -468,9 +499,20 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
   const int C = m.C, Pc = m.Pc, M = (int)m.M;
   auto P = [&](int i) { return (const float*)params[i]; };
   auto G = [&](int i) { return (float*)grads[i]; };
-  const double count = (double)m.M;
+  const double count = (double)m.M * world;
   const int LP = 2 * m.nb + 1;
   float *k1 = w.k123, *k2 = w.k123 + w.Cmax, *k3 = w.k123 + 2 * w.Cmax;
+  const bool sync = hook != nullptr && world > 1;
+  // BatchNorm backward finalize; under SyncBatchNorm the sums are all-reduced first (local copy kept for dgamma / dbeta)
+  auto bn_bwd_fin = [&](int pw, int layer, float* dgamma, float* dbeta, int Cl) -> int {
+    if (sync) {
+      KB_CUDA_CHECK(cudaMemcpyAsync(w.dsums_local, w.dsums, 2 * (size_t)Cl * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      const int hr = hook(hook_user, w.dsums, 2LL * Cl, (kb_stream_t)st);
+      if (hr != 0) { kb_set_error("BatchNorm all-reduce hook failed (rc=%d)", hr); return KB_ERR_INVALID; }
+    }
+    return kbk_bn_bwd_finalize(w.dsums, count, P(pw), w.bn_mean(layer), w.bn_invstd(layer), k1, k2, k3, dgamma, dbeta, Cl, st,
+                               sync ? w.dsums_local : nullptr);
+  };
   const void* x_last = m.nb > 0 ? blks[m.nb - 1].xout : w.x0;
   const float* pool_f = w.pool(m, m.nb);
 
@@ -490,8 +532,7 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
     KB_TRY(kbk_gemm(h, st));
   }
   KB_TRY(kbk_relu_bwd_stats_f32(w.dp1, w.p1act, w.p1raw, m.M, Pc, w.dsums, st));
-  KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(pi_head(m, 1)), w.bn_mean(LP), w.bn_invstd(LP), k1, k2, k3,
-                             G(pi_head(m, 1)), G(pi_head(m, 2)), Pc, st));
+  KB_TRY(bn_bwd_fin(pi_head(m, 1), LP, G(pi_head(m, 1)), G(pi_head(m, 2)), Pc));
   KB_TRY(kbk_bn_bwd_apply(w.dp1, w.p1raw, k1, k2, k3, m.M, Pc, KB_F32, st));
   KB_TRY(linear_bwd_w(w.dp1, KB_F32, Pc, x_last, dtype, C, M, Pc, C, G(pi_head(m, 0)), nullptr, st));
   KB_TRY(linear_bwd_x(w.dp1, KB_F32, Pc, M, Pc, P(pi_head(m, 0)), C, w.d1, dtype, C, nullptr, 0, 0, st));
@@ -509,6 +550,9 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
   {
     PassDArgs a; memset(&a, 0, sizeof(a));
     a.B = B; a.C = C; a.dtype = dtype; a.dxc = w.d1; a.x = x_last; a.pool = pool_f; a.dpool = w.dpool; a.ties = w.ties(m, m.nb); a.dx = cur;
+    // stored as du = dx * [x_last > 0] together with the last block's board sums (see PassDArgs)
+    a.mask_out = 1;
+    if (m.nb > 0) { a.z_next = blks[m.nb - 1].z2; a.s_du = w.s_du; a.s_duz = w.s_duz; }
     KB_TRY(kbk_block_bwd_dx(a, st));
   }
 
@@ -518,10 +562,8 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
     const void* x_in = i > 0 ? blks[i - 1].xout : w.x0;
     const float* pool_in = w.pool(m, i);
     const int l1 = 1 + 2 * i, l2 = 2 + 2 * i;
-    // pass A: du = dx' * [x' > 0]; per-(board, channel) sums
-    BlockBwdArgs ra; memset(&ra, 0, sizeof(ra));
-    ra.B = B; ra.C = C; ra.dtype = dtype; ra.dxp = cur; ra.xp = bw.xout; ra.z2 = bw.z2; ra.s_du = w.s_du; ra.s_duz = w.s_duz;
-    KB_TRY(kbk_block_bwd_reduce(ra, st));
+    // `cur` already holds du = dx' * [x' > 0] and w.s_du / w.s_duz its per-(board, channel) sums: both were produced
+    // by the consumer's data-gradient pass (PassDArgs.mask_out / z_next), so this block never re-reads x' for the mask
     KB_TRY(kbk_se_bwd_prep(w.s_du, w.s_duz, w.bn_a(l2), w.bn_b(l2), bw.se, w.dse, B, C, st));
     // SE MLP backward
     KB_TRY(linear_bwd_w(w.dse, KB_F32, 2 * C, bw.seh, KB_F32, m.S, B, 2 * C, m.S, G(pi_blk(i, 12)), G(pi_blk(i, 13)), st));
@@ -530,10 +572,9 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
     KB_TRY(linear_bwd_x(w.dseh, KB_F32, m.S, B, m.S, P(pi_blk(i, 10)), C, w.dse_in, KB_F32, C, nullptr, 0, 0, st));
     // BN2 backward statistics from board-level sums, then dz2
     KB_TRY(kbk_bn2_bwd_sums(w.s_du, w.s_duz, bw.se, w.dse_in, bw.bmean2, B, C, w.dsums, st));
-    KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(pi_blk(i, 4)), w.bn_mean(l2), w.bn_invstd(l2), k1, k2, k3,
-                               G(pi_blk(i, 4)), G(pi_blk(i, 5)), C, st));
+    KB_TRY(bn_bwd_fin(pi_blk(i, 4), l2, G(pi_blk(i, 4)), G(pi_blk(i, 5)), C));
     PassBArgs pb; memset(&pb, 0, sizeof(pb));
-    pb.B = B; pb.C = C; pb.dtype = dtype; pb.dxp = cur; pb.xp = bw.xout; pb.z2 = bw.z2; pb.se = bw.se; pb.dse_in = w.dse_in;
+    pb.B = B; pb.C = C; pb.dtype = dtype; pb.dxp = cur; pb.xp = nullptr; pb.z2 = bw.z2; pb.se = bw.se; pb.dse_in = w.dse_in;
     pb.k1 = k1; pb.k2 = k2; pb.k3 = k3; pb.dz2 = t1;
     KB_TRY(kbk_block_bwd_dz2(pb, st));
     // conv2: weight gradient, then data gradient with the BN1/ReLU/gpool-bias backward fused in its epilogue
@@ -553,8 +594,7 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
       e.ch_sum = w.dsums; e.ch_dot = w.dsums + C; e.board_sum = w.dg; e.board_scale = 1.f;
       KB_TRY(conv3x3(m, t1, wp.wd(i, 1), t2, C, C, e, use_tc, num_sms, st));
     }
-    KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(pi_blk(i, 1)), w.bn_mean(l1), w.bn_invstd(l1), k1, k2, k3,
-                               G(pi_blk(i, 1)), G(pi_blk(i, 2)), C, st));
+    KB_TRY(bn_bwd_fin(pi_blk(i, 1), l1, G(pi_blk(i, 1)), G(pi_blk(i, 2)), C));
     // global-pool-bias MLP backward -> gradient wrt the pool statistics of the block input
     KB_TRY(linear_bwd_w(w.dg, KB_F32, C, bw.gh, KB_F32, m.G, B, C, m.G, G(pi_blk(i, 8)), G(pi_blk(i, 9)), st));
     KB_TRY(linear_bwd_x(w.dg, KB_F32, C, B, C, P(pi_blk(i, 8)), m.G, w.dgh, KB_F32, m.G, bw.gh, m.G, 0, st));
@@ -567,15 +607,17 @@ extern "C" int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const
     KB_TRY(conv3x3(m, t2, wp.wd(i, 0), t1, C, C, e1, use_tc, num_sms, st));
     // pass D: dx = dgrad + residual branch + global-pool backward
     PassDArgs pd; memset(&pd, 0, sizeof(pd));
-    pd.B = B; pd.C = C; pd.dtype = dtype; pd.dxc = t1; pd.dxp = cur; pd.xp = bw.xout; pd.x = x_in; pd.pool = pool_in;
+    pd.B = B; pd.C = C; pd.dtype = dtype; pd.dxc = t1; pd.dxp = cur; pd.xp = nullptr; pd.x = x_in; pd.pool = pool_in;
     pd.dpool = w.dpool; pd.ties = w.ties(m, i); pd.dx = t2;
+    pd.mask_out = 1;  // hand du (masked by the producer's ReLU) to block i-1 / the stem
+    if (i > 0) { pd.z_next = blks[i - 1].z2; pd.s_du = w.s_du; pd.s_duz = w.s_duz; }
     KB_TRY(kbk_block_bwd_dx(pd, st));
     void* nc = t2; t2 = t1; t1 = cur; cur = nc;
   }
 
   // ---- stem ----
   KB_TRY(kbk_relu_bwd_stats(cur, w.x0, w.z0, t1, m.M, C, dtype, w.dsums, st));
-  KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(1), w.bn_mean(0), w.bn_invstd(0), k1, k2, k3, G(1), G(2), C, st));
+  KB_TRY(bn_bwd_fin(1, 0, G(1), G(2), C));
   KB_TRY(kbk_bn_bwd_apply(t1, w.z0, k1, k2, k3, m.M, C, dtype, st));
   KB_TRY(wgrad3x3(m, w.obs_p, t1, G(0), m.C0p, C, m.C0, use_tc, num_sms, w.wg_ws, w.wg_ws_bytes, st));
   return KB_OK;

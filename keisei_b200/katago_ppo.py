@@ -340,7 +340,8 @@ class KataGoPPOAlgorithm:
         model.eval()
         try:
             tok = self._events(device, "select_actions_forward_ms")
-            output = model(obs)
+            # small batches replay a captured CUDA graph of the network (launch-bound otherwise)
+            output = model.rollout_forward(obs) if isinstance(model, SEResNetModel) else model(obs)
             self._events_end(tok)
             B = obs.shape[0]
             if device.type == "cuda":

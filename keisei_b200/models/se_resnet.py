@@ -100,6 +100,8 @@ class SEResNetModel(KataGoBaseModel):
         self.last_policy_buffer: torch.Tensor | None = None  # padded (B, 11264) logits of the last CUDA forward
         self._tables_cache = None
         self._grad_sizes: list[int] = []
+        self._graphs: dict = {}              # (batch, dtype, device, use_tc) -> captured rollout forward
+        self.graph_max_batch: int = 1024     # rollout batches up to this size replay a CUDA graph (0 disables)
 
     # ---- kernel plumbing ---------------------------------------------------------------------
     def _desc(self) -> list[int]:
@@ -126,6 +128,7 @@ class SEResNetModel(KataGoBaseModel):
     def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): storages change
         self._tables_cache = None
         self._wpack_key = None
+        self._graphs = {}
         return super()._apply(fn, *args, **kwargs)
 
     def _act_dtype(self, device: torch.device) -> torch.dtype:
@@ -169,6 +172,50 @@ class SEResNetModel(KataGoBaseModel):
         if training:
             self._store_running_stats(buffers, new_stats)
         B = obs.shape[0]
+        self.last_policy_buffer = policy_buf
+        policy = policy_buf[:, :model_ops.POLICY_A].view(B, 9, 9, self.SPATIAL_MOVE_TYPES)
+        return KataGoOutput(policy_logits=policy, value_logits=value, score_lead=score)
+
+    # ---- CUDA-graph replay for small rollout batches ---------------------------------------------
+    @torch.no_grad()
+    def rollout_forward(self, obs: torch.Tensor) -> KataGoOutput:
+        """Eval-mode no-grad forward for action selection (reference katago_ppo.py:575-580 / katago_loop.py:337-344,
+        404-406: per-step inference on 64..512 boards, several sub-batches per step in league play).
+
+        For batches up to `graph_max_batch` the ~290 kernel launches of the network are captured ONCE per
+        (batch, dtype) into a CUDA graph and replayed: at these sizes the step is launch-bound, not GPU-bound.
+        The returned tensors are views of the graph's static output buffers — valid until the next
+        `rollout_forward` with the same batch size (`select_actions` consumes them immediately). Larger batches,
+        CPU tensors and training mode go through the ordinary `forward`."""
+        if (self.training or not obs.is_cuda or obs.shape[0] > self.graph_max_batch or not self.kernel_supported()
+                or obs.ndim != 4 or tuple(obs.shape[1:]) != (self.params.obs_channels, 9, 9)):
+            return self._forward_impl(obs)
+        tables = self._ptr_tables()
+        dtype = self._act_dtype(obs.device)
+        code = 0 if dtype == torch.float32 else 1
+        wpack = self._packed(tables.params, tables.buffers, dtype)   # re-packs in place when a parameter changed
+        B = obs.shape[0]
+        key = (B, code, obs.device, bool(self.use_tensor_cores))
+        ent = self._graphs.get(key)
+        if ent is None or ent["wpack_ptr"] != wpack.data_ptr() or ent["tables"] is not tables:
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            static_obs = torch.empty((B, self.params.obs_channels, 9, 9), dtype=torch.float32, device=obs.device)
+            static_obs.copy_(obs)
+            cur = torch.cuda.current_stream(obs.device)
+            side = torch.cuda.Stream(obs.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up outside the capture: one-time function attributes / driver lookups
+                model_ops.seresnet_forward_raw(static_obs, tables, wpack, False, code, bool(self.use_tensor_cores))
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = model_ops.seresnet_forward_raw(static_obs, tables, wpack, False, code, bool(self.use_tensor_cores))
+            ent = self._graphs[key] = {"graph": graph, "obs": static_obs, "out": out, "wpack_ptr": wpack.data_ptr(),
+                                       "tables": tables}
+        ent["obs"].copy_(obs)
+        ent["graph"].replay()
+        policy_buf, value, score, _ws, _ = ent["out"]
         self.last_policy_buffer = policy_buf
         policy = policy_buf[:, :model_ops.POLICY_A].view(B, 9, 9, self.SPATIAL_MOVE_TYPES)
         return KataGoOutput(policy_logits=policy, value_logits=value, score_lead=score)

@@ -198,3 +198,38 @@ def test_bad_obs_shape_raises_valueerror():
         m(torch.zeros(2, 46, 9, 9, device=DEV))
     with pytest.raises(ValueError):
         m(torch.zeros(2, 50, 9, 8, device=DEV))
+
+
+@pytest.mark.parametrize("channels", [24, 64])
+def test_model_gradients_vs_oracle_autograd_fp32(channels):
+    """All parameter gradients of a random config against autograd through the oracle: channels=24 runs the scalar
+    (thread-per-channel) block kernels, 64 the vectorised ones."""
+    torch.manual_seed(channels)
+    p = SEResNetParams(num_blocks=3, channels=channels, se_reduction=4, global_pool_channels=16, policy_channels=8,
+                       value_fc_size=16, score_fc_size=16)
+    m = SEResNetModel(p)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in m.state_dict().items()}
+    B = 7
+    g = torch.Generator().manual_seed(9)
+    obs = torch.randn(B, 50, 9, 9, generator=g)
+    mask = torch.rand(B, 11259, generator=g) < 0.01
+    acts = torch.randint(0, 11259, (B,), generator=g)
+    mask[torch.arange(B), acts] = True
+    old = -3 * torch.rand(B, generator=g); adv = torch.randn(B, generator=g)
+    cats = torch.randint(-1, 3, (B,), generator=g); st = torch.randn(B, generator=g).clamp(-1.5, 1.5)
+    wp, wv, ws = O.seresnet_forward(sd, obs, 3, training=True)
+    want = O.ppo_losses(wp, wv, ws, mask, acts, old, adv, cats, st)
+    want["loss"].backward()
+    m = m.to(DEV).train()
+    o = m(obs.to(DEV))
+    out2, *_ = policy_ops.ppo_policy_loss(o.policy_logits.reshape(B, -1), mask.to(DEV), acts.to(DEV), old.to(DEV), adv.to(DEV), 0.2)
+    out3 = policy_ops.value_losses(o.value_logits, cats.to(DEV), o.score_lead, st.to(DEV))
+    loss = out2[0] + 1.5 * out3[0] + 0.02 * out3[1] - 0.01 * out2[1]
+    assert rel(loss.item(), want["loss"].item()) < 1e-4
+    loss.backward()
+    bad = {}
+    for name, prm in m.named_parameters():
+        r = rel(prm.grad.cpu().numpy(), sd[name].grad.numpy())
+        if r > 1e-3:
+            bad[name] = r
+    assert not bad, bad

