@@ -289,7 +289,7 @@ def run_ours(args) -> None:
 def bench_update(args, algo, model, device, rank, world) -> dict:
     """KataGo-PPO update step (BASELINE.json configs[2]): 8192 samples / world per rank; one step =
     forward (batch-stat BN) + fused losses + backward + gradient all-reduce + unscale/clip/Adam."""
-    from keisei_b200.distributed import GradSync
+    from keisei_b200.distributed import BatchNormSync, GradSync
     Bu = UPDATE_GLOBAL_B // world
     g = torch.Generator().manual_seed(7 + rank)
     obs = torch.randn(Bu, 50, 9, 9, generator=g).to(device)
@@ -313,7 +313,14 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
         algo.scaler.update()
 
     steps, warm = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
+    ms_local_bn = None
+    if world > 1:
+        # per-rank BatchNorm statistics first (plain DDP), then the reference's default: SyncBatchNorm
+        # (katago_loop.py:494-497, sync_batchnorm = true) — the headline number for N > 1
+        ms_local_bn = timed(step, steps, warm, device, world)
+        model.convert_sync_batchnorm(BatchNormSync())
     ms = timed(step, steps, warm, device, world)
+    model.convert_sync_batchnorm(None)
     # GAE over the reference-shaped buffer T=128 x N=64 (+ normalisation)
     from keisei_b200 import gae as G
     T, N = 128, 64
@@ -329,7 +336,9 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
     return {"metric": "PPO update samples/s", "e2e": e2e, "value": sps, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "warmup": warm,
             "global_batch": UPDATE_GLOBAL_B, "per_gpu_batch": Bu, "scaling": "strong", "gae_T128_N64_ms": gae_ms,
             "frac_of_tensor_roofline": (22.97e9 * UPDATE_GLOBAL_B / world / (ms * 1e-3) / 1e12) / peaks()["bf16_tflops_sustained"],
-            "includes": "fwd+losses+bwd+allreduce+unscale+clip+Adam"}
+            "includes": "fwd+losses+bwd+allreduce+unscale+clip+Adam",
+            "batchnorm": "local (1 rank)" if world == 1 else "SyncBatchNorm (reference default under DDP)",
+            "ms_per_step_local_batchnorm": ms_local_bn}
 
 
 def bench_resnet_update(args, device, rank, world) -> dict:

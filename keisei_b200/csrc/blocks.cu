@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(256) block_bwd_reduce_vec_kernel(BlockBwdArgs 
   }
 }
 
-template <typename T>
+template <typename T, bool XP>  // XP: dxp is the raw gradient and xp (the block output) supplies the ReLU mask
 __global__ void __launch_bounds__(256) block_bwd_dz2_vec_kernel(PassBArgs g) {
   const int C = g.C, C8 = C / kVW, NPL = 256 / C8;
   const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
@@ -522,40 +522,58 @@ __global__ void __launch_bounds__(256) block_bwd_dz2_vec_kernel(PassBArgs g) {
   ldf8(g.k1 + c0, k1); ldf8(g.k2 + c0, k2); ldf8(g.k3 + c0, k3);
 #pragma unroll
   for (int i = 0; i < kVW; ++i) { sg[i] = sigmoidf_(sg[i]); dm[i] *= (1.f / 81.f); }
-  for (int p = pl; p < 81; p += NPL) {
-    float d[kVW], x[kVW], z[kVW];
+  constexpr int PIX = 4;  // pixels in flight per thread: 8 independent vector loads (2 streams) before the first use
+  for (int p = pl; p < 81; p += PIX * NPL) {
+    float d[PIX][kVW], x[PIX][kVW], z[PIX][kVW];
 #pragma unroll
-    for (int i = 0; i < kVW; ++i) x[i] = 0.f;
-    V8<T>::load((const T*)g.dxp + base + (size_t)p * C, d);
-    if (g.xp) V8<T>::load((const T*)g.xp + base + (size_t)p * C, x);  // null: dxp is already masked (du)
-    V8<T>::load((const T*)g.z2 + base + (size_t)p * C, z);
+    for (int j = 0; j < PIX; ++j) {
+      const int pj = p + j * NPL;
 #pragma unroll
-    for (int i = 0; i < kVW; ++i) {
-      const float du = (g.xp == nullptr || x[i] > 0.f) ? d[i] : 0.f;
-      d[i] = k1[i] * fmaf(du, sg[i], dm[i]) - k2[i] * z[i] - k3[i];
+      for (int i = 0; i < kVW; ++i) x[j][i] = 0.f;
+      if (pj < 81) {
+        V8<T>::load((const T*)g.dxp + base + (size_t)pj * C, d[j]);
+        if (XP) V8<T>::load((const T*)g.xp + base + (size_t)pj * C, x[j]);  // else: dxp is already masked (du)
+        V8<T>::load((const T*)g.z2 + base + (size_t)pj * C, z[j]);
+      }
     }
-    V8<T>::store((T*)g.dz2 + base + (size_t)p * C, d);
+#pragma unroll
+    for (int j = 0; j < PIX; ++j) {
+      const int pj = p + j * NPL;
+      if (pj < 81) {
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) {
+          const float du = (!XP || x[j][i] > 0.f) ? d[j][i] : 0.f;
+          d[j][i] = k1[i] * fmaf(du, sg[i], dm[i]) - k2[i] * z[j][i] - k3[i];
+        }
+        V8<T>::store((T*)g.dz2 + base + (size_t)pj * C, d[j]);
+      }
+    }
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256, 4) block_bwd_dx_vec_kernel(PassDArgs g) {
+// HOT: the in-tower configuration (conv data gradient + pre-masked residual gradient + pool backward with forward tie
+// counts + masked output + next block's board sums) with every pointer test folded at compile time.
+template <typename T, bool HOT>
+__global__ void __launch_bounds__(256, 3) block_bwd_dx_vec_kernel(PassDArgs g) {
+  const bool has_dxc = HOT || g.dxc != nullptr, has_dxp = HOT || g.dxp != nullptr, has_xp = !HOT && g.xp != nullptr;
+  const bool has_dpool = HOT || g.dpool != nullptr, has_ties = HOT || g.ties != nullptr, has_zn = HOT || g.z_next != nullptr;
+  const bool mask_out = HOT || g.mask_out != 0;
   __shared__ float red[256 * kVW];
   __shared__ float red2[256 * kVW];
   const int C = g.C, C8 = C / kVW, NPL = 256 / C8;
   const int b = blockIdx.x, cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
   const size_t base = (size_t)b * 81 * C + c0;
   float gmean[kVW], gmax[kVW], gstd[kVW], mean[kVW], mx[kVW], hs[kVW], hsz[kVW];
-  const bool need_x = g.dpool != nullptr || g.mask_out != 0;
+  const bool need_x = has_dpool || mask_out;
 #pragma unroll
   for (int i = 0; i < kVW; ++i) { gmean[i] = 0.f; gmax[i] = 0.f; gstd[i] = 0.f; mean[i] = 0.f; mx[i] = 0.f; hs[i] = 0.f; hsz[i] = 0.f; }
-  if (g.dpool) {
+  if (has_dpool) {
     const float* pr = g.pool + (size_t)b * 3 * C;
     const float* dp = g.dpool + (size_t)b * 3 * C;
     float sd[kVW], dmean[kVW], dmaxv[kVW], dstd[kVW], ties[kVW];
     ldf8(pr + c0, mean); ldf8(pr + C + c0, mx); ldf8(pr + 2 * C + c0, sd);
     ldf8(dp + c0, dmean); ldf8(dp + C + c0, dmaxv); ldf8(dp + 2 * C + c0, dstd);
-    if (g.ties) {
+    if (has_ties) {
       ldf8(g.ties + (size_t)b * C + c0, ties);  // counted by the forward apply kernel
     } else {
       float tl[kVW];
@@ -584,23 +602,22 @@ __global__ void __launch_bounds__(256, 4) block_bwd_dx_vec_kernel(PassDArgs g) {
       gmax[i] = ties[i] > 0.f ? dmaxv[i] / ties[i] : 0.f;       // amax backward splits evenly across ties
     }
   }
-  auto one = [&](int p, float (&v)[kVW], const float (&t)[kVW], const float (&y)[kVW], const float (&xx)[kVW]) {
-    if (g.dxp) {
+  auto one = [&](int p, float (&v)[kVW], const float (&t)[kVW], const float (&y)[kVW], const float (&xx)[kVW],
+                 const float (&zn)[kVW]) {
+    if (has_dxp) {
 #pragma unroll
-      for (int i = 0; i < kVW; ++i) v[i] += (g.xp == nullptr || y[i] > 0.f) ? t[i] : 0.f;
+      for (int i = 0; i < kVW; ++i) v[i] += (!has_xp || y[i] > 0.f) ? t[i] : 0.f;
     }
-    if (g.dpool) {
+    if (has_dpool) {
 #pragma unroll
       for (int i = 0; i < kVW; ++i) v[i] += gmean[i] + (xx[i] == mx[i] ? gmax[i] : 0.f) + gstd[i] * (xx[i] - mean[i]);
     }
-    if (g.mask_out) {
+    if (mask_out) {
 #pragma unroll
       for (int i = 0; i < kVW; ++i) v[i] = xx[i] > 0.f ? v[i] : 0.f;
     }
     V8<T>::store((T*)g.dx + base + (size_t)p * C, v);
-    if (g.z_next) {
-      float zn[kVW];
-      V8<T>::load((const T*)g.z_next + base + (size_t)p * C, zn);
+    if (has_zn) {
       V8<T>::round(v);
 #pragma unroll
       for (int i = 0; i < kVW; ++i) { hs[i] += v[i]; hsz[i] = fmaf(v[i], zn[i], hsz[i]); }
@@ -609,23 +626,27 @@ __global__ void __launch_bounds__(256, 4) block_bwd_dx_vec_kernel(PassDArgs g) {
   for (int p = pl; p < 81; p += 2 * NPL) {  // two pixels per iteration: up to 8 independent vector loads in flight
     const bool two = p + NPL < 81;
     const int p1 = p + NPL;
-    float v0[kVW], t0[kVW], y0[kVW], x0[kVW], v1[kVW], t1[kVW], y1[kVW], x1[kVW];
+    float v0[kVW], t0[kVW], y0[kVW], x0[kVW], n0[kVW], v1[kVW], t1[kVW], y1[kVW], x1[kVW], n1[kVW];
 #pragma unroll
-    for (int i = 0; i < kVW; ++i) { v0[i] = 0.f; v1[i] = 0.f; t0[i] = 0.f; t1[i] = 0.f; y0[i] = 0.f; y1[i] = 0.f; x0[i] = 0.f; x1[i] = 0.f; }
-    if (g.dxc) V8<T>::load((const T*)g.dxc + base + (size_t)p * C, v0);
-    if (g.dxp) V8<T>::load((const T*)g.dxp + base + (size_t)p * C, t0);
-    if (g.xp) V8<T>::load((const T*)g.xp + base + (size_t)p * C, y0);
-    if (need_x) V8<T>::load((const T*)g.x + base + (size_t)p * C, x0);
-    if (two) {
-      if (g.dxc) V8<T>::load((const T*)g.dxc + base + (size_t)p1 * C, v1);
-      if (g.dxp) V8<T>::load((const T*)g.dxp + base + (size_t)p1 * C, t1);
-      if (g.xp) V8<T>::load((const T*)g.xp + base + (size_t)p1 * C, y1);
-      if (need_x) V8<T>::load((const T*)g.x + base + (size_t)p1 * C, x1);
+    for (int i = 0; i < kVW; ++i) {
+      v0[i] = 0.f; v1[i] = 0.f; t0[i] = 0.f; t1[i] = 0.f; y0[i] = 0.f; y1[i] = 0.f; x0[i] = 0.f; x1[i] = 0.f; n0[i] = 0.f; n1[i] = 0.f;
     }
-    one(p, v0, t0, y0, x0);
-    if (two) one(p1, v1, t1, y1, x1);
+    if (has_dxc) V8<T>::load((const T*)g.dxc + base + (size_t)p * C, v0);
+    if (has_dxp) V8<T>::load((const T*)g.dxp + base + (size_t)p * C, t0);
+    if (has_xp) V8<T>::load((const T*)g.xp + base + (size_t)p * C, y0);
+    if (need_x) V8<T>::load((const T*)g.x + base + (size_t)p * C, x0);
+    if (has_zn) V8<T>::load((const T*)g.z_next + base + (size_t)p * C, n0);
+    if (two) {
+      if (has_dxc) V8<T>::load((const T*)g.dxc + base + (size_t)p1 * C, v1);
+      if (has_dxp) V8<T>::load((const T*)g.dxp + base + (size_t)p1 * C, t1);
+      if (has_xp) V8<T>::load((const T*)g.xp + base + (size_t)p1 * C, y1);
+      if (need_x) V8<T>::load((const T*)g.x + base + (size_t)p1 * C, x1);
+      if (has_zn) V8<T>::load((const T*)g.z_next + base + (size_t)p1 * C, n1);
+    }
+    one(p, v0, t0, y0, x0, n0);
+    if (two) one(p1, v1, t1, y1, x1, n1);
   }
-  if (g.z_next) {  // per-(board, channel) sums of du and du * z_next across the pixel lanes
+  if (has_zn) {  // per-(board, channel) sums of du and du * z_next across the pixel lanes
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kVW; ++i) { red[pl * C + c0 + i] = hs[i]; red2[pl * C + c0 + i] = hsz[i]; }
@@ -721,6 +742,76 @@ __global__ void __launch_bounds__(256, 4) relu_bwd_stats_vec_kernel(const T* dy,
   }
 }
 
+// The block variant of relu_bwd_stats_vec_kernel (mask = z*ma + mb > 0, dy rewritten in place): two streams only, so
+// FOUR pixels per thread are kept in flight (8 independent vector loads) to cover the HBM latency.
+template <typename T>
+__global__ void __launch_bounds__(256, 3) mask_bwd_stats_vec_kernel(T* d, const T* __restrict__ z, int B, int C,
+                                                                   const float* __restrict__ ma, const float* __restrict__ mb,
+                                                                   float* __restrict__ board_sum, double* sums) {
+  __shared__ float red[2][256 * kVW];
+  constexpr int PIX = 4;
+  const int C8 = C / kVW, NPL = 256 / C8;
+  const int cg = threadIdx.x % C8, pl = threadIdx.x / C8, c0 = cg * kVW;
+  float s1[kVW], s2[kVW], fa[kVW], fb[kVW];
+#pragma unroll
+  for (int i = 0; i < kVW; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  ldf8(ma + c0, fa); ldf8(mb + c0, fb);
+  const int b_end = min(B, (int)(blockIdx.x + 1) * kStatsBoardsPerCta);
+  for (int b = blockIdx.x * kStatsBoardsPerCta; b < b_end; ++b) {
+    const size_t base = (size_t)b * 81 * C + c0;
+    float s0[kVW];
+#pragma unroll
+    for (int i = 0; i < kVW; ++i) s0[i] = 0.f;
+    for (int p = pl; p < 81; p += PIX * NPL) {
+      float dd[PIX][kVW], zz[PIX][kVW];
+#pragma unroll
+      for (int j = 0; j < PIX; ++j) {
+        const int pj = p + j * NPL;
+        if (pj < 81) {
+          V8<T>::load(d + base + (size_t)pj * C, dd[j]);
+          V8<T>::load(z + base + (size_t)pj * C, zz[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PIX; ++j) {
+        const int pj = p + j * NPL;
+        if (pj < 81) {
+#pragma unroll
+          for (int i = 0; i < kVW; ++i) {
+            s0[i] += dd[j][i];
+            dd[j][i] = fmaf(zz[j][i], fa[i], fb[i]) > 0.f ? dd[j][i] : 0.f;
+          }
+          V8<T>::store(d + base + (size_t)pj * C, dd[j]);
+          V8<T>::round(dd[j]);
+#pragma unroll
+          for (int i = 0; i < kVW; ++i) { s1[i] += dd[j][i]; s2[i] = fmaf(dd[j][i], zz[j][i], s2[i]); }
+        }
+      }
+    }
+    if (board_sum) {  // per-(board, channel) sum of the unmasked gradient
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kVW; ++i) red[0][pl * C + c0 + i] = s0[i];
+      __syncthreads();
+      for (int c = threadIdx.x; c < C; c += 256) {
+        float u = 0.f;
+        for (int l = 0; l < NPL; ++l) u += red[0][l * C + c];
+        board_sum[(size_t)b * C + c] = u;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kVW; ++i) { red[0][pl * C + c0 + i] = s1[i]; red[1][pl * C + c0 + i] = s2[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = 0.f, q = 0.f;
+    for (int l = 0; l < NPL; ++l) { a += red[0][l * C + c]; q += red[1][l * C + c]; }
+    atomicAdd(&sums[c], (double)a);
+    atomicAdd(&sums[C + c], (double)q);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_vec_kernel(T* __restrict__ d, const T* __restrict__ z,
                                                                  const float* __restrict__ k1, const float* __restrict__ k2,
@@ -733,6 +824,164 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_vec_kernel(T* __restrict__ d
 #pragma unroll
     for (int j = 0; j < kVW; ++j) v[j] = a[j] * v[j] - b[j] * zz[j] - e[j];
     V8<T>::store(d + i * kVW, v);
+  }
+}
+
+// =================================================================================================
+// Column kernels: one thread owns kVW channels of ONE board for all 81 pixels (C/kVW threads per board,
+// 256/(C/kVW) boards per CTA pass). Per-(board, channel) reductions are thread-local — no shared memory, no
+// barriers in the streaming loop — and the per-board preamble is amortised over 81 pixels. 81 = 27 x 3: three
+// pixels (x 2-5 streams) of independent vector loads are in flight per thread, with no tail iteration.
+// =================================================================================================
+constexpr int kColPix = 3;
+inline bool col_ok(int C) { return C % kVW == 0 && C / kVW <= 256 && 256 % (C / kVW) == 0; }
+inline int col_grid(int B, int C) {
+  const int bpc = 256 / (C / kVW);
+  const int want = kb_ceil_div(B, bpc);
+  return want < 148 * 8 ? want : 148 * 8;
+}
+
+__device__ __forceinline__ void stf4(float* p, const float (&v)[kVW]) {
+  static_assert(kVW == 4, "stf4 assumes 4 channels per thread");
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// pass B: dz2 = k1 * (du * sigmoid(scale) + dse_in / 81) - k2 * z2 - k3     (du already masked by the block's ReLU)
+template <typename T>
+__global__ void __launch_bounds__(256) block_bwd_dz2_col_kernel(PassBArgs g) {
+  const int C = g.C, TPB = C / kVW, BPC = 256 / TPB;
+  const int slot = threadIdx.x / TPB, c0 = (threadIdx.x % TPB) * kVW;
+  float k1[kVW], k2[kVW], k3[kVW];
+  ldf8(g.k1 + c0, k1); ldf8(g.k2 + c0, k2); ldf8(g.k3 + c0, k3);
+  for (int b = blockIdx.x * BPC + slot; b < g.B; b += gridDim.x * BPC) {
+    const size_t base = (size_t)b * 81 * C + c0;
+    float sg[kVW], dm[kVW];
+    ldf8(g.se + (size_t)b * 2 * C + c0, sg); ldf8(g.dse_in + (size_t)b * C + c0, dm);
+#pragma unroll
+    for (int i = 0; i < kVW; ++i) { sg[i] = k1[i] * sigmoidf_(sg[i]); dm[i] = k1[i] * dm[i] * (1.f / 81.f) - k3[i]; }
+#pragma unroll 1
+    for (int p = 0; p < 81; p += kColPix) {
+      float d[kColPix][kVW], z[kColPix][kVW];
+#pragma unroll
+      for (int j = 0; j < kColPix; ++j) {
+        V8<T>::load((const T*)g.dxp + base + (size_t)(p + j) * C, d[j]);
+        V8<T>::load((const T*)g.z2 + base + (size_t)(p + j) * C, z[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kColPix; ++j) {
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) d[j][i] = fmaf(d[j][i], sg[i], dm[i]) - k2[i] * z[j][i];
+        V8<T>::store((T*)g.dz2 + base + (size_t)(p + j) * C, d[j]);
+      }
+    }
+  }
+}
+
+// pass D, in-tower configuration (see PassDArgs): dx = [x > 0] * (dxc + du' + pool backward), plus the board sums
+// of dx and dx * z_next for the producing block.
+template <typename T, bool ZN>
+__global__ void __launch_bounds__(256, 3) block_bwd_dx_col_kernel(PassDArgs g) {
+  const int C = g.C, TPB = C / kVW, BPC = 256 / TPB;
+  const int slot = threadIdx.x / TPB, c0 = (threadIdx.x % TPB) * kVW;
+  for (int b = blockIdx.x * BPC + slot; b < g.B; b += gridDim.x * BPC) {
+    const size_t base = (size_t)b * 81 * C + c0;
+    float gmean[kVW], gmax[kVW], gstd[kVW], mean[kVW], mx[kVW], hs[kVW], hsz[kVW];
+    {
+      const float* pr = g.pool + (size_t)b * 3 * C;
+      const float* dp = g.dpool + (size_t)b * 3 * C;
+      float sd[kVW], dmean[kVW], dmaxv[kVW], dstd[kVW], ties[kVW];
+      ldf8(pr + c0, mean); ldf8(pr + C + c0, mx); ldf8(pr + 2 * C + c0, sd);
+      ldf8(dp + c0, dmean); ldf8(dp + C + c0, dmaxv); ldf8(dp + 2 * C + c0, dstd);
+      ldf8(g.ties + (size_t)b * C + c0, ties);
+#pragma unroll
+      for (int i = 0; i < kVW; ++i) {
+        gstd[i] = sd[i] > 0.f ? dstd[i] / (81.f * sd[i]) : 0.f;   // torch: d std/dx = 0 where std == 0
+        gmax[i] = ties[i] > 0.f ? dmaxv[i] / ties[i] : 0.f;       // amax backward splits evenly across ties
+        gmean[i] = dmean[i] * (1.f / 81.f);
+        hs[i] = 0.f; hsz[i] = 0.f;
+      }
+    }
+#pragma unroll 1
+    for (int p = 0; p < 81; p += kColPix) {
+      float v[kColPix][kVW], t[kColPix][kVW], x[kColPix][kVW], zn[kColPix][kVW];
+#pragma unroll
+      for (int j = 0; j < kColPix; ++j) {
+        const size_t o = base + (size_t)(p + j) * C;
+        V8<T>::load((const T*)g.dxc + o, v[j]);
+        V8<T>::load((const T*)g.dxp + o, t[j]);
+        V8<T>::load((const T*)g.x + o, x[j]);
+        if (ZN) V8<T>::load((const T*)g.z_next + o, zn[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kColPix; ++j) {
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) {
+          const float xv = x[j][i];
+          float r = v[j][i] + t[j][i];
+          r += gmean[i] + (xv == mx[i] ? gmax[i] : 0.f) + gstd[i] * (xv - mean[i]);
+          v[j][i] = xv > 0.f ? r : 0.f;
+        }
+        V8<T>::store((T*)g.dx + base + (size_t)(p + j) * C, v[j]);
+        if (ZN) {
+          V8<T>::round(v[j]);
+#pragma unroll
+          for (int i = 0; i < kVW; ++i) { hs[i] += v[j][i]; hsz[i] = fmaf(v[j][i], zn[j][i], hsz[i]); }
+        }
+      }
+    }
+    if (ZN) { stf4(g.s_du + (size_t)b * C + c0, hs); stf4(g.s_duz + (size_t)b * C + c0, hsz); }
+  }
+}
+
+// mask_bwd_stats, column form: d <- d * [z*ma + mb > 0] in place; board_sum[b][c] = sum_p d (unmasked);
+// sums += per-channel sums of the masked gradient and of masked gradient * z (double atomics, once per CTA).
+template <typename T>
+__global__ void __launch_bounds__(256) mask_bwd_stats_col_kernel(T* d, const T* __restrict__ z, int B, int C,
+                                                                 const float* __restrict__ ma, const float* __restrict__ mb,
+                                                                 float* __restrict__ board_sum, double* sums) {
+  __shared__ float red[2][256 * kVW];
+  const int TPB = C / kVW, BPC = 256 / TPB;
+  const int slot = threadIdx.x / TPB, c0 = (threadIdx.x % TPB) * kVW;
+  float s1[kVW], s2[kVW], fa[kVW], fb[kVW];
+#pragma unroll
+  for (int i = 0; i < kVW; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  ldf8(ma + c0, fa); ldf8(mb + c0, fb);
+  for (int b = blockIdx.x * BPC + slot; b < B; b += gridDim.x * BPC) {
+    const size_t base = (size_t)b * 81 * C + c0;
+    float s0[kVW];
+#pragma unroll
+    for (int i = 0; i < kVW; ++i) s0[i] = 0.f;
+#pragma unroll 1
+    for (int p = 0; p < 81; p += kColPix) {
+      float dd[kColPix][kVW], zz[kColPix][kVW];
+#pragma unroll
+      for (int j = 0; j < kColPix; ++j) {
+        V8<T>::load(d + base + (size_t)(p + j) * C, dd[j]);
+        V8<T>::load(z + base + (size_t)(p + j) * C, zz[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kColPix; ++j) {
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) {
+          s0[i] += dd[j][i];
+          dd[j][i] = fmaf(zz[j][i], fa[i], fb[i]) > 0.f ? dd[j][i] : 0.f;
+        }
+        V8<T>::store(d + base + (size_t)(p + j) * C, dd[j]);
+        V8<T>::round(dd[j]);
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) { s1[i] += dd[j][i]; s2[i] = fmaf(dd[j][i], zz[j][i], s2[i]); }
+      }
+    }
+    if (board_sum) stf4(board_sum + (size_t)b * C + c0, s0);
+  }
+#pragma unroll
+  for (int i = 0; i < kVW; ++i) { red[0][slot * C + c0 + i] = s1[i]; red[1][slot * C + c0 + i] = s2[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = 0.f, q = 0.f;
+    for (int l = 0; l < BPC; ++l) { a += red[0][l * C + c]; q += red[1][l * C + c]; }
+    atomicAdd(&sums[c], (double)a);
+    atomicAdd(&sums[C + c], (double)q);
   }
 }
 
@@ -838,7 +1087,22 @@ int kbk_bn_bwd_finalize(double* sums, double count, const float* w, const float*
 
 int kbk_block_bwd_dz2(const PassBArgs& a, cudaStream_t st) {
   KB_CHECK_ARG(a.C <= 1024, "block_bwd_dz2: C too large");
-  if (vec_ok(a.C)) KB_DISPATCH_T(a.dtype, block_bwd_dz2_vec_kernel, a.B, 256, 0, st, a);
+  static int col = -1;
+  if (col < 0) { const char* e = getenv("KB_COL_KERNELS"); col = (e && e[0] == '0') ? 0 : 1; }
+  if (col && col_ok(a.C) && a.xp == nullptr) {
+    KB_DISPATCH_T(a.dtype, block_bwd_dz2_col_kernel, col_grid(a.B, a.C), 256, 0, st, a);
+    return KB_OK;
+  }
+  if (vec_ok(a.C)) {
+    if (a.xp != nullptr) {
+      if (a.dtype == KB_F32) block_bwd_dz2_vec_kernel<float, true><<<a.B, 256, 0, st>>>(a);
+      else block_bwd_dz2_vec_kernel<bf16, true><<<a.B, 256, 0, st>>>(a);
+    } else {
+      if (a.dtype == KB_F32) block_bwd_dz2_vec_kernel<float, false><<<a.B, 256, 0, st>>>(a);
+      else block_bwd_dz2_vec_kernel<bf16, false><<<a.B, 256, 0, st>>>(a);
+    }
+    KB_CUDA_LAUNCH_CHECK();
+  }
   else KB_DISPATCH_T(a.dtype, block_bwd_dz2_kernel, a.B, ch_threads(a.C), 0, st, a);
   return KB_OK;
 }
@@ -864,7 +1128,31 @@ int kbk_bn_bwd_apply(void* d, const void* z, const float* k1, const float* k2, c
 
 int kbk_block_bwd_dx(const PassDArgs& a, cudaStream_t st) {
   KB_CHECK_ARG(a.C <= 1024, "block_bwd_dx: C too large");
-  if (vec_ok(a.C)) KB_DISPATCH_T(a.dtype, block_bwd_dx_vec_kernel, a.B, 256, 0, st, a);
+  static int col = -1;
+  if (col < 0) { const char* e = getenv("KB_COL_KERNELS"); col = (e && e[0] == '0') ? 0 : 1; }
+  if (col && col_ok(a.C) && a.dxc && a.dxp && !a.xp && a.dpool && a.ties && a.mask_out) {
+    const int grid = col_grid(a.B, a.C);
+    if (a.z_next) {
+      if (a.dtype == KB_F32) block_bwd_dx_col_kernel<float, true><<<grid, 256, 0, st>>>(a);
+      else block_bwd_dx_col_kernel<bf16, true><<<grid, 256, 0, st>>>(a);
+    } else {
+      if (a.dtype == KB_F32) block_bwd_dx_col_kernel<float, false><<<grid, 256, 0, st>>>(a);
+      else block_bwd_dx_col_kernel<bf16, false><<<grid, 256, 0, st>>>(a);
+    }
+    KB_CUDA_LAUNCH_CHECK();
+    return KB_OK;
+  }
+  if (vec_ok(a.C)) {
+    const bool hot = a.dxc && a.dxp && !a.xp && a.dpool && a.ties && a.z_next && a.mask_out;
+    if (hot) {
+      if (a.dtype == KB_F32) block_bwd_dx_vec_kernel<float, true><<<a.B, 256, 0, st>>>(a);
+      else block_bwd_dx_vec_kernel<bf16, true><<<a.B, 256, 0, st>>>(a);
+    } else {
+      if (a.dtype == KB_F32) block_bwd_dx_vec_kernel<float, false><<<a.B, 256, 0, st>>>(a);
+      else block_bwd_dx_vec_kernel<bf16, false><<<a.B, 256, 0, st>>>(a);
+    }
+    KB_CUDA_LAUNCH_CHECK();
+  }
   else KB_DISPATCH_T(a.dtype, block_bwd_dx_kernel, a.B, ch_threads(a.C), 0, st, a);
   return KB_OK;
 }
@@ -895,10 +1183,20 @@ int kbk_mask_bwd_stats(void* d_inout, const void* z, const float* ma, const floa
                        int dtype, double* sums, cudaStream_t st) {
   KB_CHECK_ARG(vec_ok(C), "mask_bwd_stats: unsupported channel count %d", C);
   if (B == 0) return KB_OK;
+  KB_CHECK_ARG(ma != nullptr && mb != nullptr, "mask_bwd_stats: mask coefficients missing");
+  static int col = -1;
+  if (col < 0) { const char* e = getenv("KB_COL_KERNELS"); col = (e && e[0] == '0') ? 0 : 1; }
+  if (col && col_ok(C)) {
+    const int grid = col_grid(B, C);
+    if (dtype == KB_F32) mask_bwd_stats_col_kernel<float><<<grid, 256, 0, st>>>((float*)d_inout, (const float*)z, B, C, ma, mb, board_sum, sums);
+    else mask_bwd_stats_col_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)d_inout, (const bf16*)z, B, C, ma, mb, board_sum, sums);
+    KB_CUDA_LAUNCH_CHECK();
+    return KB_OK;
+  }
   if (dtype == KB_F32)
-    relu_bwd_stats_vec_kernel<float><<<kb_ceil_div(B, kStatsBoardsPerCta), 256, 0, st>>>((const float*)d_inout, (const float*)z, (const float*)z, (float*)d_inout, B, C, ma, mb, board_sum, sums);
+    mask_bwd_stats_vec_kernel<float><<<kb_ceil_div(B, kStatsBoardsPerCta), 256, 0, st>>>((float*)d_inout, (const float*)z, B, C, ma, mb, board_sum, sums);
   else
-    relu_bwd_stats_vec_kernel<bf16><<<kb_ceil_div(B, kStatsBoardsPerCta), 256, 0, st>>>((const bf16*)d_inout, (const bf16*)z, (const bf16*)z, (bf16*)d_inout, B, C, ma, mb, board_sum, sums);
+    mask_bwd_stats_vec_kernel<bf16><<<kb_ceil_div(B, kStatsBoardsPerCta), 256, 0, st>>>((bf16*)d_inout, (const bf16*)z, B, C, ma, mb, board_sum, sums);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

@@ -101,6 +101,12 @@ int kbk_bn2_bwd_sums(const float* s_du, const float* s_duz, const float* se, con
 int kbk_bn_bwd_finalize(double* sums /*[2][C], zeroed afterwards*/, double count, const float* w, const float* mean,
                         const float* invstd, float* k1, float* k2, float* k3, float* dgamma, float* dbeta, int C,
                         cudaStream_t st, double* sums_local = nullptr);
+// ---- se_bwd.cu: the whole squeeze-excite branch backward of one block in one launch (C <= 256, S in {4,8,16,32}) ----
+int kbk_se_mlp_bwd_supported(int C, int S);
+int kbk_se_mlp_bwd(const float* s_du, const float* s_duz, const float* a2, const float* b2, const float* se,
+                   const float* seh, const float* se_in, const float* bmean2, const float* W1, const float* W2,
+                   float* dse_in, float* dW1, float* db1, float* dW2, float* db2, double* sums, int B, int C, int S,
+                   int num_sms, cudaStream_t st);
 struct PassBArgs {
   int B, C, dtype;
   const void* dxp; const void* xp; const void* z2;

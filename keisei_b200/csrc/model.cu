@@ -564,14 +564,21 @@ extern "C" int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* 
     const int l1 = 1 + 2 * i, l2 = 2 + 2 * i;
     // `cur` already holds du = dx' * [x' > 0] and w.s_du / w.s_duz its per-(board, channel) sums: both were produced
     // by the consumer's data-gradient pass (PassDArgs.mask_out / z_next), so this block never re-reads x' for the mask
-    KB_TRY(kbk_se_bwd_prep(w.s_du, w.s_duz, w.bn_a(l2), w.bn_b(l2), bw.se, w.dse, B, C, st));
-    // SE MLP backward
-    KB_TRY(linear_bwd_w(w.dse, KB_F32, 2 * C, bw.seh, KB_F32, m.S, B, 2 * C, m.S, G(pi_blk(i, 12)), G(pi_blk(i, 13)), st));
-    KB_TRY(linear_bwd_x(w.dse, KB_F32, 2 * C, B, 2 * C, P(pi_blk(i, 12)), m.S, w.dseh, KB_F32, m.S, bw.seh, m.S, 0, st));
-    KB_TRY(linear_bwd_w(w.dseh, KB_F32, m.S, bw.se_in, KB_F32, C, B, m.S, C, G(pi_blk(i, 10)), G(pi_blk(i, 11)), st));
-    KB_TRY(linear_bwd_x(w.dseh, KB_F32, m.S, B, m.S, P(pi_blk(i, 10)), C, w.dse_in, KB_F32, C, nullptr, 0, 0, st));
-    // BN2 backward statistics from board-level sums, then dz2
-    KB_TRY(kbk_bn2_bwd_sums(w.s_du, w.s_duz, bw.se, w.dse_in, bw.bmean2, B, C, w.dsums, st));
+    if (kbk_se_mlp_bwd_supported(C, m.S)) {
+      // one launch: SE MLP backward (both weight gradients, dse_in) + the BatchNorm-2 backward statistics
+      KB_TRY(kbk_se_mlp_bwd(w.s_du, w.s_duz, w.bn_a(l2), w.bn_b(l2), bw.se, bw.seh, bw.se_in, bw.bmean2, P(pi_blk(i, 10)),
+                            P(pi_blk(i, 12)), w.dse_in, G(pi_blk(i, 10)), G(pi_blk(i, 11)), G(pi_blk(i, 12)), G(pi_blk(i, 13)),
+                            w.dsums, B, C, m.S, num_sms, st));
+    } else {
+      KB_TRY(kbk_se_bwd_prep(w.s_du, w.s_duz, w.bn_a(l2), w.bn_b(l2), bw.se, w.dse, B, C, st));
+      // SE MLP backward
+      KB_TRY(linear_bwd_w(w.dse, KB_F32, 2 * C, bw.seh, KB_F32, m.S, B, 2 * C, m.S, G(pi_blk(i, 12)), G(pi_blk(i, 13)), st));
+      KB_TRY(linear_bwd_x(w.dse, KB_F32, 2 * C, B, 2 * C, P(pi_blk(i, 12)), m.S, w.dseh, KB_F32, m.S, bw.seh, m.S, 0, st));
+      KB_TRY(linear_bwd_w(w.dseh, KB_F32, m.S, bw.se_in, KB_F32, C, B, m.S, C, G(pi_blk(i, 10)), G(pi_blk(i, 11)), st));
+      KB_TRY(linear_bwd_x(w.dseh, KB_F32, m.S, B, m.S, P(pi_blk(i, 10)), C, w.dse_in, KB_F32, C, nullptr, 0, 0, st));
+      // BN2 backward statistics from board-level sums, then dz2
+      KB_TRY(kbk_bn2_bwd_sums(w.s_du, w.s_duz, bw.se, w.dse_in, bw.bmean2, B, C, w.dsums, st));
+    }
     KB_TRY(bn_bwd_fin(pi_blk(i, 4), l2, G(pi_blk(i, 4)), G(pi_blk(i, 5)), C));
     PassBArgs pb; memset(&pb, 0, sizeof(pb));
     pb.B = B; pb.C = C; pb.dtype = dtype; pb.dxp = cur; pb.xp = nullptr; pb.z2 = bw.z2; pb.se = bw.se; pb.dse_in = w.dse_in;

@@ -98,6 +98,27 @@ def seed_all_ranks(seed: int) -> None:
     random.seed(seed)
 
 
+class BatchNormSync:
+    """SyncBatchNorm exchange for `SEResNetModel.convert_sync_batchnorm` (reference katago_loop.py:494-497:
+    `torch.nn.SyncBatchNorm.convert_sync_batchnorm` before the DDP wrap, `sync_batchnorm = true` by default).
+
+    The C schedule hands over one (2*C,) float64 device slice per BatchNorm layer — (sum x, sum x^2) in the forward,
+    (sum dz, sum dz*z) in the backward — and this object sums it over the ranks on the current stream (NCCL orders
+    itself after the producing kernel and before the consuming one). 4 KB per call, 2*(2*blocks+2) calls per step."""
+
+    def __init__(self, process_group=None) -> None:
+        if not dist.is_initialized():
+            raise RuntimeError("BatchNormSync needs an initialised process group (setup_distributed)")
+        self.group = process_group
+        self.world_size = dist.get_world_size(process_group)
+
+    @torch.no_grad()
+    def all_reduce_(self, sums: torch.Tensor) -> torch.Tensor:
+        if self.world_size > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        return sums
+
+
 class GradSync:
     """Gradient averaging across ranks for `KataGoPPOAlgorithm.grad_sync`.
 

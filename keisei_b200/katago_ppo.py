@@ -487,7 +487,7 @@ class KataGoPPOAlgorithm:
         wpack = km._packed(params, buffers, dtype)
         with torch.no_grad():
             policy_buf, value, score, ws, new_stats = model_ops.seresnet_forward_raw(
-                obs, tables, wpack, True, code, bool(km.use_tensor_cores))
+                obs, tables, wpack, True, code, bool(km.use_tensor_cores), km.bn_sync)
             km._store_running_stats(buffers, new_stats)
         policy_buf.requires_grad_(True); value.requires_grad_(True); score.requires_grad_(True)
         loss, pl, vl, sl, ent, flags = self._losses(policy_buf[:, :model_ops.POLICY_A], value, score, mb, value_adapter)
@@ -496,7 +496,7 @@ class KataGoPPOAlgorithm:
         self.scaler.scale(loss).backward()
         with torch.no_grad():
             flat = model_ops.seresnet_backward_raw(tables, wpack, ws, policy_buf.grad, value.grad, score.grad, code,
-                                                   bool(km.use_tensor_cores), km._grad_sizes)
+                                                   bool(km.use_tensor_cores), km._grad_sizes, km.bn_sync)
             if self.grad_sync is not None:
                 self.grad_sync.all_reduce_flat(flat)
             off = 0

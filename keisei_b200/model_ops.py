@@ -35,6 +35,10 @@ _lib.register_signature("kb_seresnet_forward", c_int, [_P, _P, _P, _P, _P, _P, c
                                                         c_longlong, _P, _P, c_int, c_int, _P])
 _lib.register_signature("kb_seresnet_backward", c_int, [_P, _P, _P, c_int, c_int, _P, c_longlong, _P, c_longlong, _P,
                                                          _P, _P, c_int, c_int, _P])
+_lib.register_signature("kb_seresnet_forward_sync", c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_longlong,
+                                                             _P, c_longlong, _P, _P, c_int, c_int, _P, _P, c_int, _P])
+_lib.register_signature("kb_seresnet_backward_sync", c_int, [_P, _P, _P, c_int, c_int, _P, c_longlong, _P, c_longlong,
+                                                              _P, _P, _P, c_int, c_int, _P, _P, c_int, _P])
 _lib.register_signature("kb_conv3x3_forward", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P,
                                                        _P, _P, _P, c_int, _P])
 _lib.register_signature("kb_conv3x3_wgrad", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_longlong, c_int, _P])
@@ -50,6 +54,56 @@ _lib.register_signature("kb_se_block_tail", c_int, [_P] * 13 + [c_int] + [_P] * 
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 _DT_INV = {0: torch.float32, 1: torch.bfloat16}
 _sm_count_cache: dict[int, int] = {}
+
+
+# ---- SyncBatchNorm plumbing (include/keisei_b200.h: kb_allreduce_hook) ------------------------
+_HOOK_T = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_longlong, c_void_p)
+_BN_SYNCS: dict[int, object] = {}     # handle -> sync object, for the torch.library ops (schemas carry ints only)
+
+
+def register_bn_sync(sync) -> int:
+    """Handle for a BatchNorm sync object (`.world_size`, `.all_reduce_(float64 tensor)`); 0 means none."""
+    if sync is None:
+        return 0
+    h = id(sync)
+    _BN_SYNCS[h] = sync
+    return h
+
+
+class _BnHook:
+    """C callback that sums a (2*C,) float64 slice of the workspace over the ranks, in stream order.
+    The schedule calls it between each convolution and its BatchNorm finalize (forward) and before each
+    BatchNorm-backward finalize. Exceptions cannot cross the C frame: they are parked and re-raised after."""
+
+    def __init__(self, ws: torch.Tensor, sync) -> None:
+        self.error: BaseException | None = None
+        base, nbytes = ws.data_ptr(), ws.numel()
+
+        def cb(_user, buf, n, _stream):
+            try:
+                off = buf - base
+                if off < 0 or off + 8 * n > nbytes:
+                    raise _lib.KeiseiB200Error("BatchNorm sync buffer lies outside the workspace")
+                sync.all_reduce_(ws[off:off + 8 * n].view(torch.float64))
+                return 0
+            except BaseException as e:  # noqa: BLE001
+                self.error = e
+                return 1
+
+        self.fn = _HOOK_T(cb)
+        self.ptr = ctypes.cast(self.fn, c_void_p)
+
+    def check(self) -> None:
+        if self.error is not None:
+            raise self.error
+
+
+def _sync_args(ws: torch.Tensor, sync):
+    """(hook object | None, hook pointer | None, world) for the *_sync entry points."""
+    if sync is None or int(sync.world_size) <= 1:
+        return None, None, 1
+    h = _BnHook(ws, sync)
+    return h, h.ptr, int(sync.world_size)
 
 
 def sm_count(device: torch.device) -> int:
@@ -125,7 +179,7 @@ class PointerTables:
 
 @torch.no_grad()
 def seresnet_forward_raw(obs: torch.Tensor, tables: PointerTables, wpack: torch.Tensor, training: bool, dtype_code: int,
-                         use_tc: bool):
+                         use_tc: bool, bn_sync=None):
     """The C call without the torch.library dispatcher (no-grad callers: rollout, the fused trainer step).
     Returns (policy_buf, value_logits, score_lead, workspace, new_stats)."""
     if not obs.is_cuda:
@@ -142,11 +196,15 @@ def seresnet_forward_raw(obs: torch.Tensor, tables: PointerTables, wpack: torch.
     score = torch.empty((B, 1), dtype=torch.float32, device=dev)
     cmax = max(d.channels, d.policy_channels)
     new_stats = torch.empty((2 * d.num_blocks + 2, 2, cmax) if training else (0,), dtype=torch.float32, device=dev)
+    hook, hook_ptr, world = _sync_args(ws, bn_sync if training else None)
     with torch.cuda.device(dev):
-        rc = _lib.load().kb_seresnet_forward(
+        rc = _lib.load().kb_seresnet_forward_sync(
             ctypes.byref(d), tables.pt, tables.bt, new_stats.data_ptr() if training else None, wpack.data_ptr(),
             obs_c.data_ptr(), B, 1 if training else 0, dtype_code, ws.data_ptr(), ws.numel(), policy.data_ptr(),
-            POLICY_PITCH, value.data_ptr(), score.data_ptr(), 1 if use_tc else 0, sm_count(dev), _lib.stream_ptr(dev))
+            POLICY_PITCH, value.data_ptr(), score.data_ptr(), 1 if use_tc else 0, sm_count(dev), hook_ptr, None, world,
+            _lib.stream_ptr(dev))
+    if hook is not None:
+        hook.check()
     _lib.check(rc, "kb_seresnet_forward")
     return policy, value, score, ws, new_stats
 
@@ -154,7 +212,7 @@ def seresnet_forward_raw(obs: torch.Tensor, tables: PointerTables, wpack: torch.
 @torch.no_grad()
 def seresnet_backward_raw(tables: PointerTables, wpack: torch.Tensor, ws: torch.Tensor, dpolicy: torch.Tensor,
                           dvalue: torch.Tensor, dscore: torch.Tensor, dtype_code: int, use_tc: bool,
-                          sizes: List[int] | None = None) -> torch.Tensor:
+                          sizes: List[int] | None = None, bn_sync=None) -> torch.Tensor:
     """The C backward without the dispatcher. Returns the flat fp32 gradient (parameter-table order)."""
     d = tables.desc
     dev = ws.device
@@ -172,18 +230,22 @@ def seresnet_backward_raw(tables: PointerTables, wpack: torch.Tensor, ws: torch.
     for i, n in enumerate(sizes):
         gt[i] = base + 4 * off
         off += n
+    hook, hook_ptr, world = _sync_args(ws, bn_sync)
     with torch.cuda.device(dev):
-        rc = _lib.load().kb_seresnet_backward(
+        rc = _lib.load().kb_seresnet_backward_sync(
             ctypes.byref(d), tables.pt, wpack.data_ptr(), B, dtype_code, ws.data_ptr(), ws.numel(), dpol.data_ptr(),
-            dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), _lib.stream_ptr(dev))
+            dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), hook_ptr, None, world,
+            _lib.stream_ptr(dev))
+    if hook is not None:
+        hook.check()
     _lib.check(rc, "kb_seresnet_backward")
     return flat
 
 
 @torch.library.custom_op("keisei_b200::seresnet_forward", mutates_args=())
 def seresnet_forward(obs: torch.Tensor, params: List[torch.Tensor], buffers: List[torch.Tensor], wpack: torch.Tensor,
-                     desc: List[int], training: bool, dtype_code: int,
-                     use_tc: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+                     desc: List[int], training: bool, dtype_code: int, use_tc: bool,
+                     bn_sync: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Returns (policy_buf (B, 11264) act-dtype, value_logits (B,3) f32, score_lead (B,1) f32, workspace u8,
     new_stats f32 [(2*nb+2), 2, Cmax]: the updated BatchNorm running mean/var rows in training mode).
     Functional: `buffers` is read-only here; the module copies new_stats back (see SEResNetModel)."""
@@ -202,17 +264,20 @@ def seresnet_forward(obs: torch.Tensor, params: List[torch.Tensor], buffers: Lis
     cmax = max(d.channels, d.policy_channels)
     new_stats = torch.empty((2 * d.num_blocks + 2, 2, cmax) if training else (0,), dtype=torch.float32, device=dev)
     pt, bt = _ptr_table(params), _ptr_table(buffers)
+    hook, hook_ptr, world = _sync_args(ws, _BN_SYNCS[bn_sync] if (bn_sync and training) else None)
     with torch.cuda.device(dev):
-        rc = _lib.load().kb_seresnet_forward(
+        rc = _lib.load().kb_seresnet_forward_sync(
             ctypes.byref(d), pt, bt, new_stats.data_ptr() if training else None, wpack.data_ptr(), obs_c.data_ptr(), B, 1 if training else 0, dtype_code,
             ws.data_ptr(), ws.numel(), policy.data_ptr(), POLICY_PITCH, value.data_ptr(), score.data_ptr(),
-            1 if use_tc else 0, sm_count(dev), _lib.stream_ptr(dev))
+            1 if use_tc else 0, sm_count(dev), hook_ptr, None, world, _lib.stream_ptr(dev))
+    if hook is not None:
+        hook.check()
     _lib.check(rc, "kb_seresnet_forward")
     return policy, value, score, ws, new_stats
 
 
 @seresnet_forward.register_fake
-def _(obs, params, buffers, wpack, desc, training, dtype_code, use_tc):
+def _(obs, params, buffers, wpack, desc, training, dtype_code, use_tc, bn_sync):
     B = obs.shape[0]
     return (obs.new_empty((B, POLICY_PITCH), dtype=_DT_INV[dtype_code]), obs.new_empty((B, 3), dtype=torch.float32),
             obs.new_empty((B, 1), dtype=torch.float32), obs.new_empty((1,), dtype=torch.uint8),
@@ -222,7 +287,7 @@ def _(obs, params, buffers, wpack, desc, training, dtype_code, use_tc):
 @torch.library.custom_op("keisei_b200::seresnet_backward", mutates_args=())
 def seresnet_backward(params: List[torch.Tensor], wpack: torch.Tensor, ws: torch.Tensor, dpolicy: torch.Tensor,
                       dvalue: torch.Tensor, dscore: torch.Tensor, desc: List[int], dtype_code: int,
-                      use_tc: bool) -> torch.Tensor:
+                      use_tc: bool, bn_sync: int) -> torch.Tensor:
     """Returns ONE flat fp32 gradient buffer (parameters concatenated in table order)."""
     d = _desc(desc)
     dev = ws.device
@@ -236,23 +301,27 @@ def seresnet_backward(params: List[torch.Tensor], wpack: torch.Tensor, ws: torch
     flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
     grads = [g.view(p.shape) for g, p in zip(flat.split(sizes), params)]
     pt, gt = _ptr_table(params), _ptr_table(grads)
+    hook, hook_ptr, world = _sync_args(ws, _BN_SYNCS[bn_sync] if bn_sync else None)
     with torch.cuda.device(dev):
-        rc = _lib.load().kb_seresnet_backward(
+        rc = _lib.load().kb_seresnet_backward_sync(
             ctypes.byref(d), pt, wpack.data_ptr(), B, dtype_code, ws.data_ptr(), ws.numel(), dpol.data_ptr(),
-            dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), _lib.stream_ptr(dev))
+            dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), hook_ptr, None, world,
+            _lib.stream_ptr(dev))
+    if hook is not None:
+        hook.check()
     _lib.check(rc, "kb_seresnet_backward")
     return flat
 
 
 @seresnet_backward.register_fake
-def _(params, wpack, ws, dpolicy, dvalue, dscore, desc, dtype_code, use_tc):
+def _(params, wpack, ws, dpolicy, dvalue, dscore, desc, dtype_code, use_tc, bn_sync):
     return params[0].new_empty((sum(p.numel() for p in params),), dtype=torch.float32)
 
 
 def _fwd_setup(ctx, inputs, output):
-    obs, params, buffers, wpack, desc, training, dtype_code, use_tc = inputs
+    obs, params, buffers, wpack, desc, training, dtype_code, use_tc, bn_sync = inputs
     policy, value, score, ws, _new_stats = output
-    ctx.desc, ctx.dtype_code, ctx.use_tc, ctx.training = desc, dtype_code, use_tc, training
+    ctx.desc, ctx.dtype_code, ctx.use_tc, ctx.training, ctx.bn_sync = desc, dtype_code, use_tc, training, bn_sync
     ctx.n_params = len(params)
     ctx.n_buffers = len(buffers)
     ctx.save_for_backward(wpack, ws, *params)
@@ -272,9 +341,10 @@ def _fwd_backward(ctx, g_policy, g_value, g_score, g_ws, g_stats):
         g_value = torch.zeros((ctx.B, 3), dtype=torch.float32, device=dev)
     if g_score is None:
         g_score = torch.zeros((ctx.B, 1), dtype=torch.float32, device=dev)
-    flat = seresnet_backward(list(params), wpack, ws, g_policy, g_value, g_score, ctx.desc, ctx.dtype_code, ctx.use_tc)
+    flat = seresnet_backward(list(params), wpack, ws, g_policy, g_value, g_score, ctx.desc, ctx.dtype_code, ctx.use_tc,
+                             ctx.bn_sync)
     grads = [g.view(p.shape) for g, p in zip(flat.split([p.numel() for p in params]), params)]
-    return None, grads, [None] * ctx.n_buffers, None, None, None, None, None
+    return None, grads, [None] * ctx.n_buffers, None, None, None, None, None, None
 
 
 seresnet_forward.register_autograd(_fwd_backward, setup_context=_fwd_setup)

@@ -102,6 +102,7 @@ class SEResNetModel(KataGoBaseModel):
         self._grad_sizes: list[int] = []
         self._graphs: dict = {}              # (batch, dtype, device, use_tc) -> captured rollout forward
         self.graph_max_batch: int = 1024     # rollout batches up to this size replay a CUDA graph (0 disables)
+        self.bn_sync = None                  # distributed.BatchNormSync: global-batch BatchNorm statistics (SyncBatchNorm)
 
     # ---- kernel plumbing ---------------------------------------------------------------------
     def _desc(self) -> list[int]:
@@ -112,6 +113,16 @@ class SEResNetModel(KataGoBaseModel):
     def kernel_supported(self) -> bool:
         p = self.params
         return p.channels % 4 == 0 and p.channels <= 1024 and p.policy_channels <= 1024 and p.obs_channels <= 128
+
+    def convert_sync_batchnorm(self, bn_sync) -> "SEResNetModel":
+        """The CUDA-path counterpart of `torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)` (reference
+        katago_loop.py:494-497, on by default under DDP): training-mode BatchNorm layers normalise with the statistics
+        of the batch over ALL ranks. `bn_sync` is a `keisei_b200.distributed.BatchNormSync` (anything with
+        `.world_size` and `.all_reduce_(float64 tensor)`); None switches back to per-rank statistics. Modules, parameter
+        names and `state_dict` are untouched. CPU tensors keep the plain PyTorch path (torch's SyncBatchNorm itself is
+        GPU-only)."""
+        self.bn_sync = bn_sync
+        return self
 
     def _tables(self) -> tuple[list[torch.Tensor], list[torch.Tensor]]:
         return list(self.parameters()), list(self.buffers())
@@ -164,11 +175,12 @@ class SEResNetModel(KataGoBaseModel):
         if torch.is_grad_enabled() and training:
             # autograd path: the torch.library op (gradients flow to every parameter)
             policy_buf, value, score, _ws, new_stats = model_ops.seresnet_forward(
-                obs, params, buffers, wpack, self._desc(), training, code, bool(self.use_tensor_cores))
+                obs, params, buffers, wpack, self._desc(), training, code, bool(self.use_tensor_cores),
+                model_ops.register_bn_sync(self.bn_sync))
         else:
             # no graph needed (rollout / evaluation): straight to the C-ABI, no dispatcher overhead
             policy_buf, value, score, _ws, new_stats = model_ops.seresnet_forward_raw(
-                obs, tables, wpack, training, code, bool(self.use_tensor_cores))
+                obs, tables, wpack, training, code, bool(self.use_tensor_cores), self.bn_sync)
         if training:
             self._store_running_stats(buffers, new_stats)
         B = obs.shape[0]

@@ -1,0 +1,150 @@
+"""SyncBatchNorm on the CUDA path (SEResNetModel.convert_sync_batchnorm; reference katago_loop.py:494-497 wraps the
+model in torch.nn.SyncBatchNorm under DDP by default).
+
+Two "ranks" are emulated on ONE GPU by two threads, each with its own model replica and CUDA stream; the BatchNorm
+exchange object sums the per-layer statistics across the threads (the NCCL version is `distributed.BatchNormSync`,
+exercised by bench.py at N > 1). Property: with synchronised statistics the two half-batches reproduce the single
+process full-batch run — outputs, running statistics, and (summed over ranks) every parameter gradient — and the
+full-batch forward is itself checked against the oracle."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from keisei_b200.models import SEResNetModel, SEResNetParams
+from oracle import keisei_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class ThreadSum:
+    """all_reduce_(sum) across `n` in-process ranks; `handle(r)` is rank r's exchange object (the backward runs on an
+    autograd worker thread, so the rank is bound to the object, not to the calling thread)."""
+
+    def __init__(self, n: int) -> None:
+        self.n = n
+        self.barrier = threading.Barrier(n, timeout=60)
+        self.slots: list = [None] * n
+        self.calls = 0
+
+    def handle(self, rank: int) -> "RankHandle":
+        return RankHandle(self, rank)
+
+
+class RankHandle:
+    def __init__(self, shared: ThreadSum, rank: int) -> None:
+        self.shared, self.rank, self.world_size = shared, rank, shared.n
+
+    def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
+        sh = self.shared
+        torch.cuda.current_stream().synchronize()
+        sh.slots[self.rank] = t
+        sh.barrier.wait()
+        total = torch.stack(sh.slots).sum(0)
+        torch.cuda.current_stream().synchronize()
+        sh.barrier.wait()
+        t.copy_(total)
+        if self.rank == 0:
+            sh.calls += 1
+        return t
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
+
+
+@pytest.mark.parametrize("amp", [False, True])
+def test_two_ranks_with_sync_bn_match_full_batch(amp):
+    torch.manual_seed(3)
+    p = SEResNetParams(num_blocks=2, channels=64, se_reduction=8, global_pool_channels=16, policy_channels=8,
+                       value_fc_size=16, score_fc_size=16)
+    ref = SEResNetModel(p)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    W, Bh = 2, 5
+    g = torch.Generator().manual_seed(4)
+    obs = torch.randn(W * Bh, 50, 9, 9, generator=g)
+    wp = torch.randn(W * Bh, 9, 9, 139, generator=g); wv = torch.randn(W * Bh, 3, generator=g); wsc = torch.randn(W * Bh, 1, generator=g)
+
+    def loss_of(out, lo, hi):
+        return ((out.policy_logits.float() * wp[lo:hi].to(DEV)).sum() + (out.value_logits * wv[lo:hi].to(DEV)).sum()
+                + (out.score_lead * wsc[lo:hi].to(DEV)).sum()) / (W * Bh)
+
+    # single process, whole batch, ordinary BatchNorm
+    ref = ref.to(DEV).train()
+    if amp:
+        ref.configure_amp(True, torch.bfloat16, "cuda")
+    full = ref(obs.to(DEV))
+    loss_of(full, 0, W * Bh).backward()
+    if not amp:  # the full-batch run itself against the oracle (fp32 bar 1e-4)
+        with torch.no_grad():
+            op, ov, osc = O.seresnet_forward({k: v.clone() for k, v in sd.items()}, obs, p.num_blocks, training=True)
+        assert rel(full.policy_logits.detach().cpu().numpy(), op.numpy()) < 1e-4
+        assert rel(full.value_logits.detach().cpu().numpy(), ov.numpy()) < 1e-4
+
+    sync = ThreadSum(W)
+    results: list = [None] * W
+    errors: list = []
+
+    def rank_main(r: int) -> None:
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream(DEV)):
+                m = SEResNetModel(p)
+                m.load_state_dict(sd)
+                m = m.to(DEV).train().convert_sync_batchnorm(sync.handle(r))
+                if amp:
+                    m.configure_amp(True, torch.bfloat16, "cuda")
+                lo, hi = r * Bh, (r + 1) * Bh
+                out = m(obs[lo:hi].to(DEV))
+                loss_of(out, lo, hi).backward()
+                torch.cuda.current_stream().synchronize()
+                results[r] = (out, {n: q.grad.clone() for n, q in m.named_parameters()},
+                              {n: b.clone() for n, b in m.named_buffers()})
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            sync.barrier.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(W)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    assert sync.calls == 2 * (2 * p.num_blocks + 2)   # one exchange per BatchNorm layer, forward and backward
+
+    tol_out, tol_grad = (3e-2, 6e-2) if amp else (1e-4, 1e-3)
+    for r in range(W):
+        out = results[r][0]
+        lo, hi = r * Bh, (r + 1) * Bh
+        assert rel(out.policy_logits.detach().float().cpu(), full.policy_logits[lo:hi].detach().float().cpu()) < tol_out
+        assert rel(out.value_logits.detach().cpu(), full.value_logits[lo:hi].detach().cpu()) < tol_out
+        assert rel(out.score_lead.detach().cpu(), full.score_lead[lo:hi].detach().cpu()) < tol_out
+        # running statistics: every rank holds the GLOBAL batch statistics (unbiased variance over W*Bh*81)
+        for n, b in ref.named_buffers():
+            if b.is_floating_point():
+                assert rel(results[r][2][n].cpu(), b.cpu()) < (1e-2 if amp else 1e-5), n
+    bad = {}
+    for n, q in ref.named_parameters():
+        tot = sum(results[r][1][n] for r in range(W))
+        e = rel(tot.cpu(), q.grad.cpu())
+        if e > tol_grad:
+            bad[n] = e
+    assert not bad, bad
+
+
+def test_sync_hook_error_surfaces_as_exception():
+    class Broken:
+        world_size = 2
+
+        def all_reduce_(self, t):
+            raise RuntimeError("link down")
+
+    m = SEResNetModel(SEResNetParams(num_blocks=1, channels=32, se_reduction=4, global_pool_channels=8, policy_channels=8,
+                                     value_fc_size=8, score_fc_size=8)).to(DEV).train().convert_sync_batchnorm(Broken())
+    with pytest.raises(RuntimeError, match="link down"):
+        m(torch.randn(2, 50, 9, 9, device=DEV))
+    m.convert_sync_batchnorm(None)
+    m(torch.randn(2, 50, 9, 9, device=DEV))
