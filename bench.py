@@ -333,7 +333,8 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
     gae_ms = timed(gae_step, 20, 3, device, world)
     sps = UPDATE_GLOBAL_B / (ms * 1e-3)
     e2e = update_e2e(algo, device, rank, world) if world == 1 else None
-    return {"metric": "PPO update samples/s", "e2e": e2e, "value": sps, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "warmup": warm,
+    e2e_dev = update_e2e(algo, device, rank, world, device_buffer=True) if world == 1 else None
+    return {"metric": "PPO update samples/s", "e2e": e2e, "e2e_device_buffer": e2e_dev, "value": sps, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "warmup": warm,
             "global_batch": UPDATE_GLOBAL_B, "per_gpu_batch": Bu, "scaling": "strong", "gae_T128_N64_ms": gae_ms,
             "frac_of_tensor_roofline": (22.97e9 * UPDATE_GLOBAL_B / world / (ms * 1e-3) / 1e12) / peaks()["bf16_tflops_sustained"],
             "includes": "fwd+losses+bwd+allreduce+unscale+clip+Adam",
@@ -413,7 +414,7 @@ def bench_league(algo, device, rank, world) -> dict:
                               "sub_batches": "256 learner + 4 x 64 opponents (same weights: synthetic)"}}
 
 
-def update_e2e(algo, device, rank, world) -> dict:
+def update_e2e(algo, device, rank, world, device_buffer: bool = False) -> dict:
     """The public call a user makes: KataGoPPOAlgorithm.update(buffer, next_values) on a host-resident
     KataGoRolloutBuffer of T=128 x N=64 = 8192 samples (the reference's profiled update shape,
     scripts/profile_hotpath.py:411-455), one epoch, one minibatch of 8192: buffer flatten, H2D of
@@ -422,7 +423,7 @@ def update_e2e(algo, device, rank, world) -> dict:
     from keisei_b200.katago_ppo import KataGoRolloutBuffer
     T, N = 128, 64
     g = torch.Generator().manual_seed(11 + rank)
-    buf = KataGoRolloutBuffer(N, (50, 9, 9), A)
+    buf = KataGoRolloutBuffer(N, (50, 9, 9), A, device=device if device_buffer else None)
     steps = []
     for t in range(T):
         obs = torch.randn(N, 50, 9, 9, generator=g)
@@ -447,6 +448,11 @@ def update_e2e(algo, device, rank, world) -> dict:
         times.append(time.perf_counter() - t0)
     algo.params = old_params
     best = min(times[1:])
+    if device_buffer:
+        return {"value": T * N / best, "unit": "samples/s", "ms_per_update": best * 1e3, "samples": T * N,
+                "h2d_bytes_per_update": 0, "d2h_bytes_per_update": 9 * 8,
+                "note": "update(buffer, next_values) with KataGoRolloutBuffer(device=cuda): the rollout steps were stored in "
+                        "HBM as they were produced, so the update ships nothing; wall clock, best of 2 after 1 warm-up"}
     return {"value": T * N / best, "unit": "samples/s", "ms_per_update": best * 1e3, "samples": T * N,
             "h2d_bytes_per_update": T * N * (50 * 81 * 4 + A + 8 + 4 * 4 + 8), "d2h_bytes_per_update": 9 * 8,
             "note": "update(buffer, next_values): host buffer -> metrics dict, wall clock, best of 2 after 1 warm-up"}

@@ -321,7 +321,9 @@ constexpr int kVW = 4;  // channels per thread in the vectorised kernels (4 -> h
 template <typename T, int W> struct VV;
 template <> struct VV<float, 8> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    float4 a, b;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p) : "memory");
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 4) : "memory");
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
   static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
@@ -332,7 +334,10 @@ template <> struct VV<float, 8> {
 };
 template <> struct VV<float, 4> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    // volatile: ptxas otherwise sinks the loads of an unrolled group next to their uses (one pair in flight instead
+    // of the whole group — seen in the ncu source view as a full-latency stall per pixel)
+    float4 a;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p) : "memory");
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
   }
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
@@ -346,7 +351,8 @@ __device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
 }
 template <> struct VV<bf16, 8> {
   static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    uint4 u;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p) : "memory");
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
@@ -361,7 +367,8 @@ template <> struct VV<bf16, 8> {
 };
 template <> struct VV<bf16, 4> {
   static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
-    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    uint2 u;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(u.x), "=r"(u.y) : "l"(p) : "memory");
     v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
     v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
   }
@@ -374,7 +381,13 @@ template <> struct VV<bf16, 4> {
   }
 };
 template <typename T> using V8 = VV<T, kVW>;
-__device__ __forceinline__ void ldf8(const float* p, float (&v)[kVW]) { VV<float, kVW>::load(p, v); }
+// small fp32 vectors that are re-read by many threads (BatchNorm coefficients, per-board SE / bias values): the cached
+// read-only path (L1-allocating), unlike the streaming activation loads above
+__device__ __forceinline__ void ldf8(const float* p, float (&v)[kVW]) {
+  static_assert(kVW == 4, "ldf8 assumes 4 channels per thread");
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
 
 // SE = squeeze-excite scale/shift + residual present; POOL = emit global-pool statistics of the output.
 // Each CTA walks kApplyBoardsPerCta boards (fewer, longer CTAs: less scheduling / tail overhead per board).
@@ -848,7 +861,7 @@ __device__ __forceinline__ void stf4(float* p, const float (&v)[kVW]) {
 
 // pass B: dz2 = k1 * (du * sigmoid(scale) + dse_in / 81) - k2 * z2 - k3     (du already masked by the block's ReLU)
 template <typename T>
-__global__ void __launch_bounds__(256) block_bwd_dz2_col_kernel(PassBArgs g) {
+__global__ void __launch_bounds__(256, 3) block_bwd_dz2_col_kernel(PassBArgs g) {
   const int C = g.C, TPB = C / kVW, BPC = 256 / TPB;
   const int slot = threadIdx.x / TPB, c0 = (threadIdx.x % TPB) * kVW;
   float k1[kVW], k2[kVW], k3[kVW];
@@ -936,7 +949,7 @@ __global__ void __launch_bounds__(256, 3) block_bwd_dx_col_kernel(PassDArgs g) {
 // mask_bwd_stats, column form: d <- d * [z*ma + mb > 0] in place; board_sum[b][c] = sum_p d (unmasked);
 // sums += per-channel sums of the masked gradient and of masked gradient * z (double atomics, once per CTA).
 template <typename T>
-__global__ void __launch_bounds__(256) mask_bwd_stats_col_kernel(T* d, const T* __restrict__ z, int B, int C,
+__global__ void __launch_bounds__(256, 3) mask_bwd_stats_col_kernel(T* d, const T* __restrict__ z, int B, int C,
                                                                  const float* __restrict__ ma, const float* __restrict__ mb,
                                                                  float* __restrict__ board_sum, double* sums) {
   __shared__ float red[2][256 * kVW];
@@ -985,6 +998,84 @@ __global__ void __launch_bounds__(256) mask_bwd_stats_col_kernel(T* d, const T* 
   }
 }
 
+// out = relu(z*a[c] + b[c]) + gbias[board][c], flat: the whole tensor is one contiguous stream (consecutive CTAs read
+// consecutive 2 KB segments, the DRAM-friendliest pattern; bn_bwd_apply_vec_kernel has the same shape). The grid stride
+// is a multiple of C, so a thread keeps the same channels and its BatchNorm coefficients live in registers; the
+// per-board bias is a 16-byte L1/L2 hit per vector. Four vectors per thread are in flight.
+template <typename T>
+__global__ void __launch_bounds__(256, 4) apply_flat_kernel(ApplyArgs g, unsigned rows) {
+  constexpr int U = 4;
+  const int C = g.C, cpv = C / kVW;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned rs = (gridDim.x * blockDim.x) / cpv;   // pixel rows advanced per grid stride (exact: see launcher)
+  const int c0 = (int)(tid % cpv) * kVW;
+  float a_[kVW], b_[kVW];
+#pragma unroll
+  for (int i = 0; i < kVW; ++i) { a_[i] = 1.f; b_[i] = 0.f; }
+  if (g.a) { ldf8(g.a + c0, a_); ldf8(g.b + c0, b_); }
+  for (unsigned row = tid / cpv; row < rows; row += U * rs) {
+    float v[U][kVW], gb[U][kVW];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      // clamped, branch-free loads (a branch would pin each conversion next to its load and serialise the group)
+      const unsigned ru = min(row + u * rs, rows - 1);
+#pragma unroll
+      for (int k = 0; k < kVW; ++k) gb[u][k] = 0.f;
+      V8<T>::load((const T*)g.z + (size_t)ru * C + c0, v[u]);
+      if (g.gbias) ldf8(g.gbias + (size_t)(ru / 81u) * C + c0, gb[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned ru = row + u * rs;
+      if (ru < rows) {
+#pragma unroll
+        for (int k = 0; k < kVW; ++k) v[u][k] = fmaxf(fmaf(v[u][k], a_[k], b_[k]), 0.f) + gb[u][k];
+        V8<T>::store((T*)g.out + (size_t)ru * C + c0, v[u]);
+      }
+    }
+  }
+}
+
+// dz = k1[c]*dzh - k2[c]*z - k3[c] in place, flat (same shape as apply_flat_kernel: coefficients in registers, four
+// branch-free vector pairs in flight per thread, consecutive CTAs on consecutive 2 KB segments).
+template <typename T>
+__global__ void __launch_bounds__(256, 4) bn_bwd_apply_flat_kernel(T* d, const T* __restrict__ z, const float* __restrict__ k1,
+                                                                  const float* __restrict__ k2, const float* __restrict__ k3,
+                                                                  unsigned rows, int C) {
+  constexpr int U = 4;
+  const int cpv = C / kVW;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned rs = (gridDim.x * blockDim.x) / cpv;
+  const int c0 = (int)(tid % cpv) * kVW;
+  float a[kVW], b[kVW], e[kVW];
+  ldf8(k1 + c0, a); ldf8(k2 + c0, b); ldf8(k3 + c0, e);
+  for (unsigned row = tid / cpv; row < rows; row += U * rs) {
+    float v[U][kVW], zz[U][kVW];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned ru = min(row + u * rs, rows - 1);
+      V8<T>::load(d + (size_t)ru * C + c0, v[u]);
+      V8<T>::load(z + (size_t)ru * C + c0, zz[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned ru = row + u * rs;
+      if (ru < rows) {
+#pragma unroll
+        for (int j = 0; j < kVW; ++j) v[u][j] = a[j] * v[u][j] - b[j] * zz[u][j] - e[j];
+        V8<T>::store(d + (size_t)ru * C + c0, v[u]);
+      }
+    }
+  }
+}
+
+inline int flat_grid(long long rows, int cpv) {
+  long long ctas = (rows * cpv + 256 * 4 - 1) / (256 * 4);
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  while (((ctas * 256) % cpv) != 0) ++ctas;  // thread total must be a multiple of the vectors per pixel row
+  return (int)ctas;
+}
+
 inline bool vec_ok(int C) { return C % kVW == 0 && C / kVW <= 256 && 256 % (C / kVW) == 0; }
 
 inline int ch_threads(int C) { return ((C + 31) / 32) * 32; }
@@ -1001,6 +1092,15 @@ inline int ch_threads(int C) { return ((C + 31) / 32) * 32; }
 int kbk_apply(const ApplyArgs& a, cudaStream_t st) {
   KB_CHECK_ARG(a.C >= 1 && a.C <= 1024, "apply: C=%d out of range", a.C);
   if (a.B == 0) return KB_OK;
+  if (a.C % kVW == 0 && a.se == nullptr && a.res == nullptr && a.pool == nullptr && a.pool_bf == nullptr && a.ties == nullptr) {
+    // plain BatchNorm + ReLU + bias: flat streaming kernel; grid * 256 threads is a multiple of C / kVW
+    const long long rows = (long long)a.B * 81;
+    const int cpv = a.C / kVW;                       // vectors per pixel row
+    if (rows < (1LL << 31)) {
+      KB_DISPATCH_T(a.dtype, apply_flat_kernel, flat_grid(rows, cpv), 256, 0, st, a, (unsigned)rows);
+      return KB_OK;
+    }
+  }
   if (vec_ok(a.C) && (a.se == nullptr || a.res != nullptr)) {
     const bool se = a.res != nullptr, pool = a.pool != nullptr;
     static int bpc = 0;
@@ -1111,6 +1211,13 @@ int kbk_bn_bwd_apply(void* d, const void* z, const float* k1, const float* k2, c
                      int dtype, cudaStream_t st) {
   const long long n = rows * C;
   if (n == 0) return KB_OK;
+  if (C % kVW == 0 && rows < (1LL << 31)) {
+    const int grid = flat_grid(rows, C / kVW);
+    if (dtype == KB_F32) bn_bwd_apply_flat_kernel<float><<<grid, 256, 0, st>>>((float*)d, (const float*)z, k1, k2, k3, (unsigned)rows, C);
+    else bn_bwd_apply_flat_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)d, (const bf16*)z, k1, k2, k3, (unsigned)rows, C);
+    KB_CUDA_LAUNCH_CHECK();
+    return KB_OK;
+  }
   if (C % kVW == 0) {
     const long long n8 = n / kVW;
     const int grid8 = (int)min((long long)148 * 16, (n8 + 255) / 256);

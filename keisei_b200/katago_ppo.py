@@ -111,16 +111,24 @@ class KataGoPPOParams:
 
 
 class KataGoRolloutBuffer:
-    """Host-resident rollout storage with the reference's interface and guards
-    (katago_ppo.py:128-388): `add`, `flatten`, `clear`, `size`, `fill_alternating_perspective_overrides`."""
+    """Rollout storage with the reference's interface and guards (katago_ppo.py:128-388): `add`, `flatten`, `clear`,
+    `size`, `fill_alternating_perspective_overrides`.
+
+    `device=None` (default) is the reference's host-resident buffer: every `add` copies the step to the CPU and
+    `update()` ships observations + masks back (225 MB for T=128 x N=64). `device="cuda:k"` keeps the same storage in
+    HBM: `add` is device-to-device, the guards run as one fused flag reduction with a single
+    host read per step, `flatten()` returns device views and `update()` performs no host<->device copy of the
+    per-sample data at all."""
 
     _FIELDS = ("observations", "actions", "log_probs", "values", "rewards", "dones", "terminated", "legal_masks",
                "value_categories", "score_targets")
 
-    def __init__(self, num_envs: int, obs_shape: tuple[int, ...], action_space: int) -> None:
+    def __init__(self, num_envs: int, obs_shape: tuple[int, ...], action_space: int,
+                 device: torch.device | str | None = None) -> None:
         self.num_envs = num_envs
         self.obs_shape = obs_shape
         self.action_space = action_space
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
         self._alloc_samples = 0
         self._write_offset = 0
         self._step_count = 0
@@ -129,22 +137,23 @@ class KataGoRolloutBuffer:
         self._has_next_value_override = False
 
     def _new_storage(self, cap: int) -> dict[str, torch.Tensor]:
+        dev = self.device
         st = {
-            "observations": torch.empty(cap, *self.obs_shape),
-            "actions": torch.empty(cap, dtype=torch.long),
-            "log_probs": torch.empty(cap),
-            "values": torch.empty(cap),
-            "rewards": torch.empty(cap),
-            "dones": torch.empty(cap, dtype=torch.bool),
-            "terminated": torch.empty(cap, dtype=torch.bool),
-            "legal_masks": torch.empty(cap, self.action_space, dtype=torch.bool),
-            "value_categories": torch.empty(cap, dtype=torch.long),
-            "score_targets": torch.empty(cap),
+            "observations": torch.empty(cap, *self.obs_shape, device=dev),
+            "actions": torch.empty(cap, dtype=torch.long, device=dev),
+            "log_probs": torch.empty(cap, device=dev),
+            "values": torch.empty(cap, device=dev),
+            "rewards": torch.empty(cap, device=dev),
+            "dones": torch.empty(cap, dtype=torch.bool, device=dev),
+            "terminated": torch.empty(cap, dtype=torch.bool, device=dev),
+            "legal_masks": torch.empty(cap, self.action_space, dtype=torch.bool, device=dev),
+            "value_categories": torch.empty(cap, dtype=torch.long, device=dev),
+            "score_targets": torch.empty(cap, device=dev),
         }
         if self._has_env_ids:
-            st["env_ids"] = torch.empty(cap, dtype=torch.long)
+            st["env_ids"] = torch.empty(cap, dtype=torch.long, device=dev)
         if self._has_next_value_override:
-            st["next_value_override"] = torch.full((cap,), float("nan"))
+            st["next_value_override"] = torch.full((cap,), float("nan"), device=dev)
         return st
 
     def _ensure_capacity(self, n_samples: int) -> None:
@@ -152,6 +161,9 @@ class KataGoRolloutBuffer:
         if needed <= self._alloc_samples:
             return
         cap = max(needed * 2, 512 * self.num_envs)
+        if self.device.type == "cuda":
+            # HBM is not host RAM: no speculative 512-step floor (that alone would be 0.9 GB for 64 envs)
+            cap = max(needed, min(cap, 2 * max(needed, 128 * self.num_envs)))
         fresh = self._new_storage(cap)
         off = self._write_offset
         if off > 0:
@@ -171,23 +183,38 @@ class KataGoRolloutBuffer:
 
     def add(self, obs, actions, log_probs, values, rewards, dones, terminated, legal_masks, value_categories,
             score_targets, env_ids=None, next_value_override=None) -> None:
-        host = lambda t: t.detach().cpu()  # noqa: E731
+        dev = self.device
+        host = lambda t: t.detach().to(dev)  # noqa: E731  (CPU buffer: the reference's .cpu(); CUDA buffer: stays in HBM)
         obs_c, act_c, lp_c, val_c, rew_c = host(obs), host(actions), host(log_probs), host(values), host(rewards)
         done_c, term_c = host(dones), host(terminated)
-        if (term_c.bool() & ~done_c.bool()).any():
+        mask_c, cats_c, score_c = host(legal_masks), host(value_categories), host(score_targets)
+        if dev.type == "cuda":
+            # the four guards as one device-side flag vector and a single host read
+            abs_max = score_c.abs().max()
+            bad_term, bad_cats, nan_score, big_score = torch.stack([
+                (term_c.bool() & ~done_c.bool()).any(), ((cats_c < -1) | (cats_c > 2)).any(), score_c.isnan().any(),
+                abs_max > 3.5]).tolist()
+        else:
+            bad_term = bool((term_c.bool() & ~done_c.bool()).any())
+            bad_cats = nan_score = big_score = None
+        if bad_term:
             raise AssertionError(
                 "terminated must be a subset of dones: every terminated position must also be done. "
                 "Got terminated=True where dones=False — likely a call site passing the merged signal.")
-        mask_c, cats_c, score_c = host(legal_masks), host(value_categories), host(score_targets)
-        invalid = set(cats_c.unique().tolist()) - {-1, 0, 1, 2}
-        if invalid:
-            raise ValueError(f"value_categories contains invalid values {invalid}. "
-                             f"Expected only {{-1=ignore, 0=W, 1=D, 2=L}}.")
-        if score_c.isnan().any():
+        if bad_cats is None or bad_cats:
+            invalid = set(cats_c.unique().tolist()) - {-1, 0, 1, 2}
+            if invalid:
+                raise ValueError(f"value_categories contains invalid values {invalid}. "
+                                 f"Expected only {{-1=ignore, 0=W, 1=D, 2=L}}.")
+        if nan_score is None:
+            nan_score = bool(score_c.isnan().any())
+        if nan_score:
             raise ValueError("score_targets contains NaN. With per-step material balance, "
                              "all targets should be real-valued.")
-        abs_max = score_c.abs().max()
-        if abs_max > 3.5:
+        if big_score is None:
+            abs_max = score_c.abs().max()
+            big_score = bool(abs_max > 3.5)
+        if big_score:
             raise ValueError(f"score_targets appear unnormalized: max abs value = {abs_max.item():.1f}. "
                              f"Expected in [-1.7, +1.7] typical, theoretical max 2.58 (guard 3.5).")
         n = obs_c.shape[0]
@@ -202,11 +229,11 @@ class KataGoRolloutBuffer:
             st[key][sl] = val
         if env_ids is not None:
             if "env_ids" not in st:
-                st["env_ids"] = torch.empty(self._alloc_samples, dtype=torch.long)
+                st["env_ids"] = torch.empty(self._alloc_samples, dtype=torch.long, device=dev)
             st["env_ids"][sl] = host(env_ids)
         if next_value_override is not None:
             if "next_value_override" not in st:
-                st["next_value_override"] = torch.full((self._alloc_samples,), float("nan"))
+                st["next_value_override"] = torch.full((self._alloc_samples,), float("nan"), device=dev)
                 self._has_next_value_override = True
             st["next_value_override"][sl] = host(next_value_override).to(torch.float32)
         elif self._has_next_value_override and "next_value_override" in st:
@@ -223,7 +250,7 @@ class KataGoRolloutBuffer:
         if T <= 1 or self._write_offset != T * N:
             return
         if "next_value_override" not in self._storage:
-            self._storage["next_value_override"] = torch.full((self._alloc_samples,), float("nan"))
+            self._storage["next_value_override"] = torch.full((self._alloc_samples,), float("nan"), device=self.device)
             self._has_next_value_override = True
         ov = self._storage["next_value_override"][:T * N].view(T, N)
         values = self._storage["values"][:T * N].view(T, N)
@@ -397,6 +424,8 @@ class KataGoPPOAlgorithm:
             self._events_end(tok)
             return adv.reshape(-1)
         nv_cpu = nv.cpu()
+        # ragged buffers (split-merge rollouts): the index bookkeeping below is host-side, on the small 1-D fields only
+        data = {k: (v.cpu() if v.is_cuda and k not in ("observations", "legal_masks") else v) for k, v in data.items()}
         if "env_ids" in data:
             env_ids = data["env_ids"]
             order = torch.argsort(env_ids, stable=True)
@@ -533,7 +562,10 @@ class KataGoPPOAlgorithm:
         device = next(self.model.parameters()).device
         p = self.params
 
-        if device.type == "cuda":
+        if device.type == "cuda" and data["observations"].device == device:
+            side = None   # device-resident buffer (KataGoRolloutBuffer(device=...)): nothing to ship
+            gpu_obs, gpu_masks = data["observations"], data["legal_masks"]
+        elif device.type == "cuda":
             side = torch.cuda.Stream(device)
             with torch.cuda.stream(side):
                 gpu_obs = data["observations"].pin_memory().to(device, non_blocking=True)

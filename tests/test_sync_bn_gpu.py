@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 import torch
 
+from keisei_b200 import model_ops
 from keisei_b200.models import SEResNetModel, SEResNetParams
 from oracle import keisei_oracle as O
 
@@ -98,11 +99,28 @@ def test_two_ranks_with_sync_bn_match_full_batch(amp):
                 if amp:
                     m.configure_amp(True, torch.bfloat16, "cuda")
                 lo, hi = r * Bh, (r + 1) * Bh
-                out = m(obs[lo:hi].to(DEV))
-                loss_of(out, lo, hi).backward()
+                # the trainer's path (KataGoPPOAlgorithm._step_fused): raw C-ABI forward / backward on THIS thread.
+                # (autograd would run both ranks' backward on the one per-device engine thread: the first rank to
+                # reach an exchange would wait forever for the second — an artefact of emulating ranks with threads)
+                tables = m._ptr_tables()
+                dtype = m._act_dtype(torch.device(DEV))
+                code = 0 if dtype == torch.float32 else 1
+                wpack = m._packed(tables.params, tables.buffers, dtype)
+                pol, val, sco, ws, new_stats = model_ops.seresnet_forward_raw(
+                    obs[lo:hi].to(DEV), tables, wpack, True, code, bool(m.use_tensor_cores), m.bn_sync)
+                m._store_running_stats(tables.buffers, new_stats)
+                dpol = torch.zeros_like(pol)
+                dpol[:, :model_ops.POLICY_A] = (wp[lo:hi].reshape(Bh, -1) / (W * Bh)).to(DEV)
+                flat = model_ops.seresnet_backward_raw(tables, wpack, ws, dpol, (wv[lo:hi] / (W * Bh)).to(DEV),
+                                                       (wsc[lo:hi] / (W * Bh)).to(DEV), code, bool(m.use_tensor_cores),
+                                                       m._grad_sizes, m.bn_sync)
                 torch.cuda.current_stream().synchronize()
-                results[r] = (out, {n: q.grad.clone() for n, q in m.named_parameters()},
-                              {n: b.clone() for n, b in m.named_buffers()})
+                grads, off = {}, 0
+                for n, q in m.named_parameters():
+                    grads[n] = flat[off:off + q.numel()].view(q.shape).clone()
+                    off += q.numel()
+                out = type(full)(policy_logits=pol[:, :model_ops.POLICY_A].view(Bh, 9, 9, 139), value_logits=val, score_lead=sco)
+                results[r] = (out, grads, {n: b.clone() for n, b in m.named_buffers()})
         except BaseException as e:  # noqa: BLE001
             errors.append(e)
             sync.barrier.abort()

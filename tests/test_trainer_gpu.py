@@ -82,3 +82,71 @@ def test_update_bf16_amp_runs_tcgen05_and_tracks_fp32():
     for k in ("policy_loss", "value_loss", "score_loss", "entropy"):
         a, b = out["bf16"][k], out["fp32"][k]
         assert abs(a - b) <= 2e-2 * max(abs(b), 1e-3), (k, a, b)
+
+
+def _fill(buf, N, T, A, seed, dev=None, with_override=False):
+    gg = torch.Generator().manual_seed(seed)
+    for t in range(T):
+        obs = torch.randn(N, 50, 9, 9, generator=gg)
+        mask = torch.rand(N, A, generator=gg) < 0.01
+        a = torch.randint(0, A, (N,), generator=gg); mask[torch.arange(N), a] = True
+        term = torch.rand(N, generator=gg) < 0.2
+        fields = [obs, a, -2 * torch.rand(N, generator=gg), 0.3 * torch.randn(N, generator=gg), term.float(), term, term, mask,
+                  torch.where(term, torch.randint(0, 3, (N,), generator=gg), torch.full((N,), -1)),
+                  torch.randn(N, generator=gg).clamp(-1, 1)]
+        ov = torch.where(torch.rand(N, generator=gg) < 0.3, torch.randn(N, generator=gg), torch.full((N,), float("nan")))
+        if dev is not None:
+            fields = [f.to(dev) for f in fields]
+            ov = ov.to(dev)
+        buf.add(*fields, next_value_override=ov if with_override else None)
+
+
+def test_device_resident_buffer_matches_host_buffer():
+    """KataGoRolloutBuffer(device=cuda): same flatten() contents, same perspective overrides, and a
+    bit-identical update() (same seeds -> same shuffles) with no host<->device copy of observations or masks."""
+    N, T, A = 5, 6, 11259
+    host, devb = KataGoRolloutBuffer(N, (50, 9, 9), A), KataGoRolloutBuffer(N, (50, 9, 9), A, device=DEV)
+    _fill(host, N, T, A, 7)
+    _fill(devb, N, T, A, 7, dev=DEV)
+    host.fill_alternating_perspective_overrides(); devb.fill_alternating_perspective_overrides()
+    fh, fd = host.flatten(), devb.flatten()
+    assert fh.keys() == fd.keys()
+    for k in fh:
+        assert fd[k].device.type == "cuda" and fd[k].dtype == fh[k].dtype and fd[k].shape == fh[k].shape, k
+        assert torch.equal(fd[k].cpu().nan_to_num(7.0), fh[k].nan_to_num(7.0)), k
+    results = []
+    for buf in (host, devb):
+        torch.manual_seed(5)
+        model = build_model("se_resnet", dict(TINY)).to(DEV)
+        algo = KataGoPPOAlgorithm(KataGoPPOParams(batch_size=10, epochs_per_batch=2), model)
+        torch.manual_seed(6)
+        m = algo.update(buf, torch.linspace(-1, 1, N, device=DEV))
+        assert buf.size == 0
+        results.append((m, [p.detach().clone() for p in model.parameters()]))
+    assert results[0][0].keys() == results[1][0].keys()
+    for k, v in results[0][0].items():
+        assert abs(v - results[1][0][k]) <= 1e-5 * max(1.0, abs(v)), k
+    for a, b in zip(results[0][1], results[1][1]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+
+
+def test_device_resident_buffer_guards():
+    N, A = 3, 11259
+    buf = KataGoRolloutBuffer(N, (50, 9, 9), A, device=DEV)
+    z = lambda *s, **k: torch.zeros(*s, device=DEV, **k)  # noqa: E731
+    ok = dict(obs=z(N, 50, 9, 9), actions=z(N, dtype=torch.long), log_probs=z(N), values=z(N), rewards=z(N),
+              dones=z(N, dtype=torch.bool), terminated=z(N, dtype=torch.bool), legal_masks=z(N, A, dtype=torch.bool),
+              value_categories=z(N, dtype=torch.long), score_targets=z(N))
+    with pytest.raises(ValueError, match="Cannot flatten an empty buffer"):
+        buf.flatten()
+    with pytest.raises(AssertionError, match="terminated must be a subset of dones"):
+        buf.add(**{**ok, "terminated": torch.ones(N, dtype=torch.bool, device=DEV)})
+    with pytest.raises(ValueError, match=r"invalid values \{5\}"):
+        buf.add(**{**ok, "value_categories": torch.tensor([0, 5, -1], device=DEV)})
+    with pytest.raises(ValueError, match="contains NaN"):
+        buf.add(**{**ok, "score_targets": torch.tensor([0.0, float("nan"), 0.0], device=DEV)})
+    with pytest.raises(ValueError, match="unnormalized"):
+        buf.add(**{**ok, "score_targets": torch.tensor([0.0, 40.0, 0.0], device=DEV)})
+    assert buf.size == 0
+    buf.add(**ok)
+    assert buf.size == 1 and buf.flatten()["observations"].is_cuda
