@@ -357,16 +357,38 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
 }
 
 // dw[(co*Cin_true + ci)*9 + tap] += sum_slices ws[slice*units + tap*n_half + half][ci][co_local]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cin, int Cout, int Cin_true,
-                                    int units, int slices) {
-  const int co = blockIdx.x * 128 + threadIdx.x;  // blockDim = 128
-  const int ci = blockIdx.y, tap = blockIdx.z;
-  if (co >= Cout || ci >= Cin_true) return;
+// The workspace is co-fastest, the PyTorch gradient is (ci, tap)-fastest: a CTA takes a 32 co x 8 ci x 9 tap brick,
+// reads it with 128-byte rows (co contiguous), transposes through shared memory and writes, per output channel, one
+// contiguous run of 8*9 floats — both sides coalesced (the direct scatter used a 9 KB stride per thread).
+constexpr int kRedCi = 8;
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cin, int Cout,
+                                                           int Cin_true, int units, int slices) {
+  __shared__ float tile[32][kRedCi * 9 + 1];  // [co][ci * 9 + tap]
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * kRedCi;
   const int n_half = Cout / kTileM;
-  const int unit = tap * n_half + co / kTileM;
-  float s = 0.f;
-  for (int sl = 0; sl < slices; ++sl) s += ws[(((size_t)sl * units + unit) * Cin + ci) * kTileM + (co % kTileM)];
-  dw[((size_t)co * Cin_true + ci) * 9 + tap] += s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // 8 warps
+  const int co = co0 + lane;
+  const size_t slice_stride = (size_t)units * Cin * kTileM;
+  for (int r = wid; r < kRedCi * 9; r += 8) {  // r = ci_local * 9 + tap: one 128-byte row of the brick per warp step
+    const int cil = r / 9, tap = r - cil * 9, ci = ci0 + cil;
+    float s = 0.f;
+    if (co < Cout && ci < Cin_true) {
+      const int unit = tap * n_half + co / kTileM;
+      const float* p = ws + ((size_t)unit * Cin + ci) * kTileM + (co % kTileM);
+#pragma unroll 4
+      for (int sl = 0; sl < slices; ++sl) s += p[(size_t)sl * slice_stride];
+    }
+    tile[lane][r] = s;
+  }
+  __syncthreads();
+  const int ci_n = min(kRedCi, Cin_true - ci0);
+  if (ci_n <= 0) return;
+  const int run = ci_n * 9;  // contiguous floats per output channel
+  for (int c = wid; c < 32; c += 8) {
+    if (co0 + c >= Cout) break;
+    float* out = dw + ((size_t)(co0 + c) * Cin_true + ci0) * 9;
+    for (int i = lane; i < run; i += 32) out[i] += tile[c][i];
+  }
 }
 
 // ---------------------------------------------------------------- host side
@@ -514,7 +536,7 @@ int kbk_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int Ci
   }
   conv3x3_wgrad_tc_kernel<<<units * slices, kThreads, kWgSmemBytes, st>>>(mdy, mx, ws, B, Cin, Cout, units, bps);
   KB_CUDA_LAUNCH_CHECK();
-  wgrad_reduce_kernel<<<dim3(kb_ceil_div(Cout, 128), Cin_true, 9), 128, 0, st>>>(ws, dw, Cin, Cout, Cin_true, units, slices);
+  wgrad_reduce_kernel<<<dim3(kb_ceil_div(Cout, 32), kb_ceil_div(Cin_true, kRedCi)), 256, 0, st>>>(ws, dw, Cin, Cout, Cin_true, units, slices);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

@@ -41,11 +41,28 @@ __device__ __forceinline__ float4 ld4(const void* p, int dtype, long long off, b
   return v;
 }
 
-template <int BM>
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// TF32 = true (BM = 64 only): the same tiles and operand staging, but the inner product runs on the tensor cores as
+// warp-level m16n8k8 TF32 MMAs with fp32 accumulation (operands rounded to TF32 when they are staged). Used for the
+// bf16 / AMP path only, where the reference itself computes these Linear layers in bf16 under autocast (TF32 keeps 3
+// more mantissa bits); the fp32 path keeps exact fp32 FMAs. These GEMMs are far too small for a tcgen05 pipeline to
+// pay off (K or N of 32..768) but large enough (M = 8192 boards) to be CUDA-core bound as SIMT.
+template <int BM, bool TF32>
 __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g, int k_per_slice, int a_vec, int b_vec) {
   constexpr int TM = BM / 16;  // rows per thread (4 or 2)
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
+  constexpr int PAD = TF32 ? 8 : 4;  // +8: the (k = lane%4, m = lane/4) fragment reads hit 32 distinct banks
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.z * k_per_slice;
@@ -103,12 +120,14 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g, int k_per_slice, 
     if (gk >= k_end) return make_float4(0.f, 0.f, 0.f, 0.f);
     return ld4(g.B, g.b_dtype, (long long)gk * g.ldb + gn, b_vec != 0, g.N - gn);
   };
-  auto store_a = [&](const float4& v) {
+  auto store_a = [&](float4 v) {
     if (!a_active) return;
+    if (TF32) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
     if (g.transA) *reinterpret_cast<float4*>(&As[a_r][a_c]) = v;
     else { As[a_c][a_r] = v.x; As[a_c + 1][a_r] = v.y; As[a_c + 2][a_r] = v.z; As[a_c + 3][a_r] = v.w; }
   };
-  auto store_b = [&](const float4& v) {
+  auto store_b = [&](float4 v) {
+    if (TF32) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
     if (g.transB) { Bs[b_c][b_r] = v.x; Bs[b_c + 1][b_r] = v.y; Bs[b_c + 2][b_r] = v.z; Bs[b_c + 3][b_r] = v.w; }
     else *reinterpret_cast<float4*>(&Bs[b_r][b_c]) = v;
   };
@@ -118,6 +137,25 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g, int k_per_slice, 
     store_a(ra); store_b(rb);
     __syncthreads();
     if (k0 + BK < k_end) { ra = load_a(k0 + BK); rb = load_b(k0 + BK); }  // prefetch while computing
+    if constexpr (TF32) {
+      // warp (wm, wn) of a 4 x 2 grid owns rows 16*wm..+15 and columns 32*wn..+31 (four m16n8 tiles)
+      const int lane = tid & 31, wid = tid >> 5, wm = wid & 3, wn = wid >> 2, gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+      for (int ks = 0; ks < BK; ks += 8) {
+        uint32_t af[4];
+        af[0] = __float_as_uint(As[ks + tq][wm * 16 + gq]);
+        af[1] = __float_as_uint(As[ks + tq][wm * 16 + gq + 8]);
+        af[2] = __float_as_uint(As[ks + tq + 4][wm * 16 + gq]);
+        af[3] = __float_as_uint(As[ks + tq + 4][wm * 16 + gq + 8]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          uint32_t bfr[2];
+          bfr[0] = __float_as_uint(Bs[ks + tq][wn * 32 + nt * 8 + gq]);
+          bfr[1] = __float_as_uint(Bs[ks + tq + 4][wn * 32 + nt * 8 + gq]);
+          mma_tf32_16x8x8(acc[nt], af, bfr);
+        }
+      }
+    } else {
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float av[TM];
@@ -130,31 +168,39 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g, int k_per_slice, 
         acc[i][2] = fmaf(av[i], b.z, acc[i][2]); acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
       }
     }
+    }
     __syncthreads();
   }
   // ---- epilogue ----
-#pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int gm = m0 + ty * TM + i;
-    if (gm >= g.M) continue;
+  auto emit = [&](int gm, int gn, float v) {
+    if (gm >= g.M || gn >= g.N) return;
     long long crow;
     if (g.c_group_rows > 0) crow = ((long long)gm / g.c_group_rows) * g.c_group_pitch + ((long long)gm % g.c_group_rows) * g.ldc;
     else crow = (long long)gm * g.ldc;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + tx * 4 + j;
-      if (gn >= g.N) continue;
-      float v = acc[i][j];
-      if (g.bias && blockIdx.z == 0) v += g.bias[gn];
-      if (g.splitk > 1) {
-        atomicAdd(((float*)g.C) + crow + gn, v);
-      } else {
-        if (g.relu) v = fmaxf(v, 0.f);
-        if (g.mask_src && !(g.mask_src[(long long)gm * g.ld_mask + gn] > 0.f)) v = 0.f;
-        if (g.c_dtype == KB_F32) ((float*)g.C)[crow + gn] = v;
-        else ((bf16*)g.C)[crow + gn] = __float2bfloat16_rn(v);
-      }
+    if (g.bias && blockIdx.z == 0) v += g.bias[gn];
+    if (g.splitk > 1) {
+      atomicAdd(((float*)g.C) + crow + gn, v);
+    } else {
+      if (g.relu) v = fmaxf(v, 0.f);
+      if (g.mask_src && !(g.mask_src[(long long)gm * g.ld_mask + gn] > 0.f)) v = 0.f;
+      if (g.c_dtype == KB_F32) ((float*)g.C)[crow + gn] = v;
+      else ((bf16*)g.C)[crow + gn] = __float2bfloat16_rn(v);
     }
+  };
+  if constexpr (TF32) {
+    // m16n8 accumulator: c0/c1 -> row lane/4, cols 2*(lane%4) + {0,1}; c2/c3 -> row lane/4 + 8
+    const int lane = tid & 31, wid = tid >> 5, wm = wid & 3, wn = wid >> 2, gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int gn = n0 + wn * 32 + nt * 8 + 2 * tq, gm = m0 + wm * 16 + gq;
+      emit(gm, gn, acc[nt][0]); emit(gm, gn + 1, acc[nt][1]);
+      emit(gm + 8, gn, acc[nt][2]); emit(gm + 8, gn + 1, acc[nt][3]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) emit(m0 + ty * TM + i, n0 + tx * 4 + j, acc[i][j]);
   }
 }
 
@@ -208,10 +254,12 @@ int kbk_gemm(const GemmArgs& g, cudaStream_t st) {
   const int a_vec = vec4_ok(g.A, g.a_dtype, g.lda, g.a_group_rows, g.a_group_pitch) ? 1 : 0;
   const int b_vec = vec4_ok(g.B, g.b_dtype, g.ldb, 0, 0) ? 1 : 0;
   const long long tiles64 = (long long)kb_ceil_div(g.N, BN) * kb_ceil_div(g.M, 64) * splitk;
-  if (tiles64 >= 2 * 148) {
-    gemm_kernel<64><<<dim3(kb_ceil_div(g.N, BN), kb_ceil_div(g.M, 64), splitk), 256, 0, st>>>(a, kps, a_vec, b_vec);
+  if (g.tf32) {
+    gemm_kernel<64, true><<<dim3(kb_ceil_div(g.N, BN), kb_ceil_div(g.M, 64), splitk), 256, 0, st>>>(a, kps, a_vec, b_vec);
+  } else if (tiles64 >= 2 * 148) {
+    gemm_kernel<64, false><<<dim3(kb_ceil_div(g.N, BN), kb_ceil_div(g.M, 64), splitk), 256, 0, st>>>(a, kps, a_vec, b_vec);
   } else {
-    gemm_kernel<32><<<dim3(kb_ceil_div(g.N, BN), kb_ceil_div(g.M, 32), splitk), 256, 0, st>>>(a, kps, a_vec, b_vec);
+    gemm_kernel<32, false><<<dim3(kb_ceil_div(g.N, BN), kb_ceil_div(g.M, 32), splitk), 256, 0, st>>>(a, kps, a_vec, b_vec);
   }
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;

@@ -45,6 +45,7 @@ struct GemmArgs {
   const float* mask_src; long long ld_mask;                // v = mask_src[m][n] > 0 ? v : 0
   int M, N, K;
   int splitk;                                              // >1: fp32 atomicAdd into C (C pre-zeroed / accumulating)
+  int tf32;                                                // inner product as TF32 tensor-core MMAs (bf16 / AMP path only)
 };
 int kbk_gemm(const GemmArgs& g, cudaStream_t st);
 // out[n] += sum_m X[m][n]  (X may be board-pitched like GemmArgs.A)
@@ -172,6 +173,9 @@ struct SeApplyArgs {
 };
 int kbk_se_apply_supported(int C, int S);
 int kbk_se_apply(const SeApplyArgs& a, int num_sms, cudaStream_t st);
+// se_apply_col.cu: the same contract as a thread-per-channel MLP kernel + one column-layout streaming pass (default)
+int kbk_se_apply_col_supported(int C, int S);
+int kbk_se_apply_col(const SeApplyArgs& a, int num_sms, cudaStream_t st);
 
 // ---- resnet_heads.cu (plain ResNet policy / value head front ends, reference models/resnet.py:49-59,76-84) ----
 // raw [B*81][3] fp32 = x [B][81][C] . {policy_conv rows 0,1; value_conv}; sums (optional) double[6] =

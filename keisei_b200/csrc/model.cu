@@ -503,6 +503,7 @@ extern "C" int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* 
   const int LP = 2 * m.nb + 1;
   float *k1 = w.k123, *k2 = w.k123 + w.Cmax, *k3 = w.k123 + 2 * w.Cmax;
   const bool sync = hook != nullptr && world > 1;
+  Tf32Scope tf32_scope(dtype == KB_BF16 && use_tc ? 1 : 0);  // MLP / head backward GEMMs on the tensor cores (AMP path only)
   // BatchNorm backward finalize; under SyncBatchNorm the sums are all-reduced first (local copy kept for dgamma / dbeta)
   auto bn_bwd_fin = [&](int pw, int layer, float* dgamma, float* dbeta, int Cl) -> int {
     if (sync) {

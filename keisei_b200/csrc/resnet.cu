@@ -296,6 +296,7 @@ extern "C" int kb_resnet_backward(const kb_resnet_desc* d, const void* const* pa
   Ws w;
   carve(m, workspace, 1, w, blks);
   KB_CHECK_ARG((size_t)ws_bytes >= w.total, "workspace too small: %lld < %zu", ws_bytes, w.total);
+  Tf32Scope tf32_scope(dtype == KB_BF16 && use_tc ? 1 : 0);  // head backward GEMMs on the tensor cores (AMP path only)
   const int C = m.C;
   auto P = [&](int i) { return (const float*)params[i]; };
   auto G = [&](int i) { return (float*)grads[i]; };

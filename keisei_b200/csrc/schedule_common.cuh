@@ -20,7 +20,15 @@ struct Bump {
   float* f32(size_t n) { return (float*)take(n * sizeof(float)); }
 };
 
-inline GemmArgs gemm_base() { GemmArgs g; memset(&g, 0, sizeof(g)); g.splitk = 1; return g; }
+// TF32 tensor-core inner product for the small GEMMs (GemmArgs.tf32): switched on for the duration of a bf16 / AMP
+// backward schedule, where the reference runs these Linear layers in bf16 under autocast; never in the fp32 path.
+inline int& gemm_tf32_flag() { static thread_local int f = 0; return f; }
+struct Tf32Scope {
+  int prev;
+  explicit Tf32Scope(int on) : prev(gemm_tf32_flag()) { gemm_tf32_flag() = on; }
+  ~Tf32Scope() { gemm_tf32_flag() = prev; }
+};
+inline GemmArgs gemm_base() { GemmArgs g; memset(&g, 0, sizeof(g)); g.splitk = 1; g.tf32 = gemm_tf32_flag(); return g; }
 inline ConvEpi epi_base() { ConvEpi e; memset(&e, 0, sizeof(e)); e.board_scale = 1.f; return e; }
 
 // y[M,N] = act(x[M,K] * W[N,K]^T + bias)
@@ -52,7 +60,7 @@ inline int linear_bwd_w(const void* dy, int dy_dtype, long long ldy, const void*
   g.C = dW; g.c_dtype = KB_F32; g.ldc = K;
   g.M = N; g.N = K; g.K = M;
   const int tiles = kb_ceil_div(N, 64) * kb_ceil_div(K, 64);
-  int sk = kb_ceil_div(296, tiles);
+  int sk = kb_ceil_div(148 * 5, tiles);  // ~5 resident CTAs per SM: the K loop is a 1-deep prefetch, latency is hidden by occupancy
   const int max_sk = kb_ceil_div(M, 64);
   if (sk > max_sk) sk = max_sk;
   g.splitk = sk < 2 ? 2 : sk;  // always the atomic epilogue: dW accumulates into the pre-zeroed gradient

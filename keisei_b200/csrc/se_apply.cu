@@ -13,6 +13,7 @@
 // whole kernel; the MLP of the next board overlaps the bulk copies. Output rows are written with 16-byte
 // coalesced stores; per-(board, channel) statistics use a common shift (the pixel-0 value) so partial sums of
 // the 16 pixel lanes merge by plain addition, through the drained stage buffer as scratch.
+#include <stdlib.h>
 #include "kb_common.cuh"
 #include "kb_kernels.h"
 #include "tc_ptx.cuh"
@@ -291,13 +292,37 @@ __global__ void __launch_bounds__(kThreads, 1) se_apply_tma_kernel(SeApplyArgs g
 
 }  // namespace
 
-int kbk_se_apply_supported(int C, int S) {
+static int kbk_se_apply_tma_supported(int C, int S) {
   if (C % 8 != 0 || C < 64 || C > 256 || kGroupThreads % (C / 8) != 0 || kGroupThreads / (C / 8) > 81 || S < 1 || S > 64) return 0;
   return (make_layout(C, S, false).total <= 227 * 1024 && make_layout(C, S, true).total <= 227 * 1024) ? 1 : 0;
 }
 
+// Dispatch (measured on B200, profiles/): training (tie counts, raw SE outputs saved) -> the column pair in
+// se_apply_col.cu (183 + 36 us vs 237 us at B = 8192); evaluation -> the TMA-bulk-staged kernel below (118 us vs
+// 95 + 24 us at B = 4096, and one launch instead of two for the small graph-replayed batches).
+// KB_SE_APPLY=tma / col forces one of them.
+static int forced_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KB_SE_APPLY"); v = !e ? 0 : (e[0] == 't' ? 1 : (e[0] == 'c' ? 2 : 0)); }
+  return v;
+}
+int kbk_se_apply_supported(int C, int S) {
+  return (kbk_se_apply_col_supported(C, S) || kbk_se_apply_tma_supported(C, S)) ? 1 : 0;
+}
+
+static int kbk_se_apply_tma(const SeApplyArgs& a, int num_sms, cudaStream_t st);
+
 int kbk_se_apply(const SeApplyArgs& a, int num_sms, cudaStream_t st) {
-  KB_CHECK_ARG(kbk_se_apply_supported(a.C, a.S), "se_apply: unsupported shape C=%d S=%d", a.C, a.S);
+  const bool col_ok = kbk_se_apply_col_supported(a.C, a.S) != 0, tma_ok = kbk_se_apply_tma_supported(a.C, a.S) != 0;
+  KB_CHECK_ARG(col_ok || tma_ok, "se_apply: unsupported shape C=%d S=%d", a.C, a.S);
+  const int f = forced_variant();
+  const bool want_col = f == 2 || (f == 0 && a.ties != nullptr);
+  if (col_ok && (want_col || !tma_ok)) return kbk_se_apply_col(a, num_sms, st);
+  return kbk_se_apply_tma(a, num_sms, st);
+}
+
+static int kbk_se_apply_tma(const SeApplyArgs& a, int num_sms, cudaStream_t st) {
+  KB_CHECK_ARG(kbk_se_apply_tma_supported(a.C, a.S), "se_apply: unsupported shape C=%d S=%d", a.C, a.S);
   KB_CHECK_ARG(a.z && a.res && a.out && a.bmean && a.w1 && a.b1 && a.w2 && a.b2 && a.pool && a.se_out, "se_apply: null pointer");
   if (a.B == 0) return KB_OK;
   const Layout L = make_layout(a.C, a.S, a.ties != nullptr);

@@ -299,7 +299,10 @@ class KataGoPPOAlgorithm:
         if hasattr(model, "configure_amp"):
             amp_dtype, amp_dev = _amp_dtype_and_device(params.use_amp, device)
             model.configure_amp(enabled=params.use_amp, dtype=amp_dtype, device_type=amp_dev)
-        self.optimizer = torch.optim.Adam(model.parameters(), lr=params.learning_rate)
+        # Same optimiser and hyper-parameters as the reference (katago_ppo.py:494: Adam defaults); on CUDA PyTorch's fused
+        # multi-tensor implementation (one launch per ~64 tensors for the whole moment/parameter update instead of five
+        # foreach passes) — identical `state_dict()` layout, so checkpoints interchange (checkpoint.py:123).
+        self.optimizer = torch.optim.Adam(model.parameters(), lr=params.learning_rate, fused=device.type == "cuda")
         self.scaler = GradScaler(enabled=params.use_amp and device.type == "cuda")
         self.warmup_epochs = warmup_epochs
         self.warmup_entropy = warmup_entropy

@@ -11,6 +11,8 @@ showcase sidecar and unit tests are CPU-only) run the same graph with plain PyTo
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 
 import torch
@@ -101,7 +103,8 @@ class SEResNetModel(KataGoBaseModel):
         self._tables_cache = None
         self._grad_sizes: list[int] = []
         self._graphs: dict = {}              # (batch, dtype, device, use_tc) -> captured rollout forward
-        self.graph_max_batch: int = 1024     # rollout batches up to this size replay a CUDA graph (0 disables)
+        # rollout batches up to this size replay a CUDA graph (0 disables); KB_GRAPH_MAX_BATCH overrides the default
+        self.graph_max_batch: int = int(os.environ.get("KB_GRAPH_MAX_BATCH", "1024"))
         self.bn_sync = None                  # distributed.BatchNormSync: global-batch BatchNorm statistics (SyncBatchNorm)
 
     # ---- kernel plumbing ---------------------------------------------------------------------
