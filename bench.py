@@ -251,9 +251,11 @@ def run_ours(args) -> None:
         torch.cuda.current_stream(device).synchronize()
 
     with ClockSampler(local) as clk:
-        n0 = _lib.launch_count()
+        # kernels of this library launched in the timed region: direct launches (kb_launch_count) + the kernels inside
+        # the CUDA graph that select_actions replays (counted once at capture, added per replay by the model)
+        n0 = _lib.launch_count() + model.graph_replayed_kernels
         ms = timed(step_device, args.steps, args.warmup, device, world)
-        launches = (_lib.launch_count() - n0) * args.steps // (args.steps + args.warmup)
+        launches = (_lib.launch_count() + model.graph_replayed_kernels - n0) * args.steps // (args.steps + args.warmup)
     ms_e2e = timed(step_e2e, args.steps, args.warmup, device, world)
     value = world * B / (ms * 1e-3)
     e2e = world * B / (ms_e2e * 1e-3)

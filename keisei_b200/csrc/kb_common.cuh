@@ -51,6 +51,14 @@ void kb_count_launch(void);  // bumps the library-wide kernel-launch counter (kb
 
 static inline int kb_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Kernels meant to run NEXT TO a tcgen05 convolution (side-stream weight gradients, two-branch rollout) ask for the
+// same shared-memory carve-out as the convolution (maximum shared memory): an SM only hosts CTAs of kernels whose
+// L1 / shared split agrees, so a streaming kernel with the default (maximum L1) preference would wait for the SM to drain.
+template <typename K>
+static inline void kb_prefer_max_smem_carveout(K kernel) {
+  cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 #ifdef __CUDACC__
 
 typedef __nv_bfloat16 bf16;

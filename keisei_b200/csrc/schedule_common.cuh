@@ -2,6 +2,7 @@
 // resnet.cu: plain ResNet): workspace bump allocator and the Linear-layer forward/backward
 // compositions over the SIMT GEMM.
 #pragma once
+#include <stdlib.h>
 #include <string.h>
 #include "kb_common.cuh"
 #include "kb_kernels.h"
@@ -70,6 +71,54 @@ inline int linear_bwd_w(const void* dy, int dy_dtype, long long ldy, const void*
 }
 
 #define KB_TRY(expr) do { int r__ = (expr); if (r__ != KB_OK) return r__; } while (0)
+
+// Side stream for the backward schedules: the weight-gradient convolutions (tensor-bound, 45 registers, no dependants
+// until the optimiser) run on it while the caller's stream carries the data-gradient chain — so the HBM-bound
+// elementwise passes of that chain share the SMs with a tensor-bound kernel instead of alternating with it.
+// One lazily created stream + event pool PER HOST THREAD AND DEVICE (concurrent callers never share
+// events); everything is joined back into the caller's stream before the schedule returns, so callers see plain
+// stream-ordered semantics. KB_BWD_OVERLAP=0 disables it; it is also off while the caller's stream is being captured.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t* ev = nullptr;
+  int n_ev = 0, device = -1;
+  ~SideStream() {
+    for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
+    free(ev);
+    if (s) cudaStreamDestroy(s);
+  }
+  int ensure(int device_id, int events) {
+    if (s == nullptr || device != device_id) {
+      if (s) { for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]); free(ev); ev = nullptr; n_ev = 0; cudaStreamDestroy(s); s = nullptr; }
+      int lo = 0, hi = 0;
+      KB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      // Lowest priority (= the default stream's): measured on B200, a high-priority side stream does not help — the
+      // convolutions and the streaming kernels both live off L2 -> SM bandwidth (a conv moves ~17 TB/s of operands), so
+      // co-residency buys little; what the side stream does buy is that the tail of one tensor-bound kernel overlaps
+      // the head of the next (KB_SIDE_PRIO=hi to compare).
+      static int prio_hi = -1;
+      if (prio_hi < 0) { const char* e = getenv("KB_SIDE_PRIO"); prio_hi = (e && e[0] == 'h') ? 1 : 0; }
+      KB_CUDA_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi ? hi : lo));
+      device = device_id;
+    }
+    if (events > n_ev) {
+      cudaEvent_t* ne = (cudaEvent_t*)realloc(ev, sizeof(cudaEvent_t) * events);
+      if (!ne) { kb_set_error("out of host memory for the event pool"); return KB_ERR_INVALID; }
+      ev = ne;
+      for (; n_ev < events; ++n_ev) KB_CUDA_CHECK(cudaEventCreateWithFlags(&ev[n_ev], cudaEventDisableTiming));
+    }
+    return KB_OK;
+  }
+};
+inline SideStream& side_stream_tls() { static thread_local SideStream ss; return ss; }
+inline bool bwd_overlap_enabled(cudaStream_t st) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("KB_BWD_OVERLAP"); env = (e && e[0] == '0') ? 0 : 1; }
+  if (!env) return false;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs == cudaStreamCaptureStatusNone;
+}
 
 
 }  // namespace kbs

@@ -34,16 +34,23 @@ __device__ __forceinline__ float warp_multi_sum(float (&v)[S], int lane) {  // s
 }
 
 // thread = channel; W1 [S][C] and W2^T [S][2C] in shared memory; CTAs walk boards with the next board's mean in flight
-template <int S>
+// WSM = true: both weight matrices staged in shared memory (96 KB for C = 256, S = 32). WSM = false: weights read
+// through L1/L2 every board (393 MB of L2 traffic per 4096 boards — noise next to a convolution's 4.8 GB) and only
+// 1.3 KB of shared memory, so the kernel can sit on an SM NEXT TO a convolution CTA (two-branch rollout).
+template <int S, bool WSM>
 __global__ void __launch_bounds__(256) se_mlp_fwd_kernel(SeApplyArgs g) {
   extern __shared__ float sm[];
   const int C = g.C, c = threadIdx.x, lane = c & 31, warp = c >> 5, nwarps = C >> 5;
-  float* W2t = sm;                 // [S][2C]
-  float* W1s = W2t + S * 2 * C;    // [S][C]
-  float* hs = W1s + S * C;         // [S]
+  float* hs = sm;                  // [S]
   float* red = hs + S;             // [8][S]
-  for (int i = c; i < 2 * C * S; i += C) { const int j = i / S, s = i - j * S; W2t[s * 2 * C + j] = g.w2[i]; }
-  for (int i = c; i < S * C; i += C) W1s[i] = g.w1[i];
+  float* W2t = red + 8 * S;        // [S][2C]   (WSM only)
+  float* W1s = W2t + S * 2 * C;    // [S][C]    (WSM only)
+  if (WSM) {
+    for (int i = c; i < 2 * C * S; i += C) { const int j = i / S, s = i - j * S; W2t[s * 2 * C + j] = g.w2[i]; }
+    for (int i = c; i < S * C; i += C) W1s[i] = g.w1[i];
+  }
+  const float* w2a = g.w2 + (size_t)c * S;        // rows of se_fc2 for this channel's scale / shift outputs
+  const float* w2b = g.w2 + (size_t)(C + c) * S;
   const float a2 = g.a ? g.a[c] : 1.f, b2 = g.a ? g.b[c] : 0.f;
   const float bias_sc = g.b2[c], bias_sh = g.b2[C + c];
   const float b1 = c < S ? g.b1[c] : 0.f;
@@ -56,7 +63,7 @@ __global__ void __launch_bounds__(256) se_mlp_fwd_kernel(SeApplyArgs g) {
     if (g.se_in_out) g.se_in_out[(size_t)b * C + c] = v;
     float part[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) part[s] = W1s[s * C + c] * v;
+    for (int s = 0; s < S; ++s) part[s] = (WSM ? W1s[s * C + c] : __ldg(g.w1 + s * C + c)) * v;
     const float ps = warp_multi_sum<S>(part, lane);
     if (lane < S) red[warp * S + lane] = ps;
     __syncthreads();
@@ -72,8 +79,8 @@ __global__ void __launch_bounds__(256) se_mlp_fwd_kernel(SeApplyArgs g) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const float h = hs[s];
-      sc = fmaf(W2t[s * 2 * C + c], h, sc);
-      sh = fmaf(W2t[s * 2 * C + C + c], h, sh);
+      sc = fmaf(WSM ? W2t[s * 2 * C + c] : __ldg(w2a + s), h, sc);
+      sh = fmaf(WSM ? W2t[s * 2 * C + C + c] : __ldg(w2b + s), h, sh);
     }
     // eval (se_raw == 0): the scale half is stored with the sigmoid already applied
     g.se_out[(size_t)b * 2 * C + c] = g.se_raw ? sc : sigmoid_f(sc);
@@ -189,11 +196,18 @@ template <int S>
 int launch_mlp(const SeApplyArgs& a, int num_sms, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    KB_CUDA_CHECK(cudaFuncSetAttribute(se_mlp_fwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    KB_CUDA_CHECK(cudaFuncSetAttribute(se_mlp_fwd_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  const int grid = a.B < 2 * num_sms ? a.B : 2 * num_sms;
-  se_mlp_fwd_kernel<S><<<grid, a.C, mlp_smem(a.C, S), st>>>(a);
+  if (a.ties == nullptr) {
+    // evaluation: small enough to share an SM with a convolution CTA of the other rollout branch
+    const int grid = a.B < 4 * num_sms ? a.B : 4 * num_sms;
+    kb_prefer_max_smem_carveout(se_mlp_fwd_kernel<S, false>);
+    se_mlp_fwd_kernel<S, false><<<grid, a.C, (size_t)(9 * S) * sizeof(float), st>>>(a);
+  } else {
+    const int grid = a.B < 2 * num_sms ? a.B : 2 * num_sms;
+    se_mlp_fwd_kernel<S, true><<<grid, a.C, mlp_smem(a.C, S), st>>>(a);
+  }
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }
@@ -222,7 +236,7 @@ int kbk_se_apply_col(const SeApplyArgs& a, int num_sms, cudaStream_t st) {
   int grid = kb_ceil_div(a.B, bpc);
   if (grid > num_sms * 8) grid = num_sms * 8;
   if (a.ties) se_apply_col_kernel<true><<<grid, 256, 0, st>>>(a);
-  else se_apply_col_kernel<false><<<grid, 256, 0, st>>>(a);
+  else { kb_prefer_max_smem_carveout(se_apply_col_kernel<false>); se_apply_col_kernel<false><<<grid, 256, 0, st>>>(a); }
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

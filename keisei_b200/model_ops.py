@@ -179,9 +179,10 @@ class PointerTables:
 
 @torch.no_grad()
 def seresnet_forward_raw(obs: torch.Tensor, tables: PointerTables, wpack: torch.Tensor, training: bool, dtype_code: int,
-                         use_tc: bool, bn_sync=None):
+                         use_tc: bool, bn_sync=None, out=None):
     """The C call without the torch.library dispatcher (no-grad callers: rollout, the fused trainer step).
-    Returns (policy_buf, value_logits, score_lead, workspace, new_stats)."""
+    Returns (policy_buf, value_logits, score_lead, workspace, new_stats). `out` = (policy_buf, value, score) row
+    slices of caller-owned buffers to write into (the two-stream rollout runs half batches side by side)."""
     if not obs.is_cuda:
         raise _lib.KeiseiB200Error("keisei_b200 seresnet_forward needs CUDA tensors")
     d = tables.desc
@@ -190,10 +191,16 @@ def seresnet_forward_raw(obs: torch.Tensor, tables: PointerTables, wpack: torch.
     obs_c = obs.detach().to(torch.float32).contiguous()
     ws = torch.empty(int(_lib.load().kb_seresnet_workspace_bytes(ctypes.byref(d), B, 1 if training else 0, dtype_code)),
                      dtype=torch.uint8, device=dev)
-    policy = torch.empty((B, POLICY_PITCH), dtype=_DT_INV[dtype_code], device=dev)
+    if out is None:
+        policy = torch.empty((B, POLICY_PITCH), dtype=_DT_INV[dtype_code], device=dev)
+        value = torch.empty((B, 3), dtype=torch.float32, device=dev)
+        score = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    else:
+        policy, value, score = out
+        if (policy.shape != (B, POLICY_PITCH) or policy.dtype != _DT_INV[dtype_code] or not policy.is_contiguous()
+                or value.shape != (B, 3) or not value.is_contiguous() or score.shape != (B, 1) or not score.is_contiguous()):
+            raise ValueError("seresnet_forward_raw: `out` buffers have the wrong shape / dtype / layout")
     policy[:, POLICY_A:].zero_()
-    value = torch.empty((B, 3), dtype=torch.float32, device=dev)
-    score = torch.empty((B, 1), dtype=torch.float32, device=dev)
     cmax = max(d.channels, d.policy_channels)
     new_stats = torch.empty((2 * d.num_blocks + 2, 2, cmax) if training else (0,), dtype=torch.float32, device=dev)
     hook, hook_ptr, world = _sync_args(ws, bn_sync if training else None)

@@ -104,8 +104,13 @@ class SEResNetModel(KataGoBaseModel):
         self._grad_sizes: list[int] = []
         self._graphs: dict = {}              # (batch, dtype, device, use_tc) -> captured rollout forward
         # rollout batches up to this size replay a CUDA graph (0 disables); KB_GRAPH_MAX_BATCH overrides the default
-        self.graph_max_batch: int = int(os.environ.get("KB_GRAPH_MAX_BATCH", "1024"))
+        self.graph_max_batch: int = int(os.environ.get("KB_GRAPH_MAX_BATCH", "4096"))
+        self.graph_replayed_kernels: int = 0  # library kernels launched through graph replays (kb_launch_count sees captures only)
         self.bn_sync = None                  # distributed.BatchNormSync: global-batch BatchNorm statistics (SyncBatchNorm)
+        # graph-replayed rollout batches of at least this many boards run as two half batches on two captured branches:
+        # boards are independent in eval mode, so one half's HBM-bound block tails execute under the other half's
+        # tensor-bound convolutions (0 disables; KB_ROLLOUT_SPLIT_MIN overrides)
+        self.rollout_split_min: int = int(os.environ.get("KB_ROLLOUT_SPLIT_MIN", "2048"))
 
     # ---- kernel plumbing ---------------------------------------------------------------------
     def _desc(self) -> list[int]:
@@ -224,16 +229,46 @@ class SEResNetModel(KataGoBaseModel):
                 model_ops.seresnet_forward_raw(static_obs, tables, wpack, False, code, bool(self.use_tensor_cores))
             cur.wait_stream(side)
             graph = torch.cuda.CUDAGraph()
+            n0 = model_ops._lib.launch_count()
             with torch.cuda.graph(graph):
-                out = model_ops.seresnet_forward_raw(static_obs, tables, wpack, False, code, bool(self.use_tensor_cores))
-            ent = self._graphs[key] = {"graph": graph, "obs": static_obs, "out": out, "wpack_ptr": wpack.data_ptr(),
+                out = self._captured_forward(static_obs, tables, wpack, code)
+            n_kernels = model_ops._lib.launch_count() - n0   # library kernels inside the graph (each replay launches them)
+            ent = self._graphs[key] = {"graph": graph, "obs": static_obs, "out": out, "kernels": n_kernels, "wpack_ptr": wpack.data_ptr(),
                                        "tables": tables}
         ent["obs"].copy_(obs)
         ent["graph"].replay()
+        self.graph_replayed_kernels += ent["kernels"]
         policy_buf, value, score, _ws, _ = ent["out"]
         self.last_policy_buffer = policy_buf
         policy = policy_buf[:, :model_ops.POLICY_A].view(B, 9, 9, self.SPATIAL_MOVE_TYPES)
         return KataGoOutput(policy_logits=policy, value_logits=value, score_lead=score)
+
+    def _captured_forward(self, obs: torch.Tensor, tables, wpack: torch.Tensor, code: int):
+        """Body of the rollout graph: one C call, or two half-batch calls on two branches of the capture."""
+        B = obs.shape[0]
+        use_tc = bool(self.use_tensor_cores)
+        if self.rollout_split_min <= 0 or B < self.rollout_split_min:
+            return model_ops.seresnet_forward_raw(obs, tables, wpack, False, code, use_tc)
+        # split on a 3-board tile boundary; the first part gets a whole number of conv rounds (74 board groups x 2
+        # channel halves = one CTA per SM) so only the second part pays a partial last round
+        groups = (B + 2) // 3
+        g1 = max(74, int(round(groups / 2 / 74)) * 74) if groups >= 4 * 74 else groups // 2
+        h = min(B - 1, max(1, g1 * 3))
+        dev = obs.device
+        dtype = torch.float32 if code == 0 else torch.bfloat16
+        policy = torch.empty((B, model_ops.POLICY_PITCH), dtype=dtype, device=dev)
+        value = torch.empty((B, 3), dtype=torch.float32, device=dev)
+        score = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        _, _, _, ws1, _ = model_ops.seresnet_forward_raw(obs[:h], tables, wpack, False, code, use_tc,
+                                                         out=(policy[:h], value[:h], score[:h]))
+        with torch.cuda.stream(side):
+            _, _, _, ws2, _ = model_ops.seresnet_forward_raw(obs[h:], tables, wpack, False, code, use_tc,
+                                                             out=(policy[h:], value[h:], score[h:]))
+        cur.wait_stream(side)
+        return policy, value, score, (ws1, ws2), None
 
     @torch.no_grad()
     def _store_running_stats(self, buffers: list[torch.Tensor], new_stats: torch.Tensor) -> None:

@@ -63,3 +63,23 @@ def test_select_actions_uses_graph_and_stays_correct():
     m.graph_max_batch = 0
     a3, lp3, v3 = algo.select_actions(obs, mask)
     assert torch.equal(v3, v1)
+
+
+@pytest.mark.parametrize("B", [7, 300, 601])
+def test_two_branch_split_rollout_is_bit_identical(B):
+    """Graph-replayed batches >= rollout_split_min run as two half batches on two captured branches
+    (SEResNetModel._captured_forward): boards are independent in eval mode, so the result is bit-identical."""
+    torch.manual_seed(2)
+    m = SEResNetModel(SEResNetParams(**CFG)).to(DEV).eval()
+    m.configure_amp(True, torch.bfloat16, "cuda")
+    obs = torch.randn(B, 50, 9, 9, device=DEV)
+    m.rollout_split_min = 0
+    with torch.no_grad():
+        w = m.rollout_forward(obs)
+        want = (w.policy_logits.clone(), w.value_logits.clone(), w.score_lead.clone())
+    m._graphs = {}
+    m.rollout_split_min = 2
+    for _ in range(2):
+        got = m.rollout_forward(obs)
+        assert torch.equal(got.policy_logits, want[0]) and torch.equal(got.value_logits, want[1]) and torch.equal(got.score_lead, want[2])
+    assert m.last_policy_buffer[:, 11259:].abs().sum().item() == 0
