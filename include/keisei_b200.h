@@ -178,6 +178,13 @@ int kb_se_block_tail(const void* z, const void* res, void* out, const float* bn_
                      const float* board_mean, const float* w1, const float* b1, const float* w2, const float* b2,
                      float* se_in_out, float* seh_out, float* se_out, int se_raw, float* pool, void* pool_bf16,
                      float* ties, int B, int C, int S, int num_sms, kb_stream_t stream);
+/* Same, with the implementation chosen explicitly: 0 = the library default, 1 = one persistent kernel staging board tiles
+ * with TMA bulk copies (csrc/se_apply.cu), 2 = SE-MLP kernel + column-layout streaming pass (csrc/se_apply_col.cu). The
+ * two sum in different orders (results agree to rounding, not bit for bit), so the network schedule uses ONE of them. */
+int kb_se_block_tail_variant(const void* z, const void* res, void* out, const float* bn_a, const float* bn_b,
+                             const float* board_mean, const float* w1, const float* b1, const float* w2, const float* b2,
+                             float* se_in_out, float* seh_out, float* se_out, int se_raw, float* pool, void* pool_bf16,
+                             float* ties, int B, int C, int S, int variant, int num_sms, kb_stream_t stream);
 
 /* ---- Linear / 1x1-conv layer on the tcgen05 path (nn.Linear at se_resnet.py:57-66, heads :119-130) ----
  * w (N,K) float32 -> bf16 (Np,Kp) zero padded, Np % 128 == 0, Kp % 64 == 0. */

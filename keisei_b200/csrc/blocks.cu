@@ -1190,8 +1190,8 @@ int kbk_block_bwd_dz2(const PassBArgs& a, cudaStream_t st) {
   static int col = -1;
   if (col < 0) { const char* e = getenv("KB_COL_KERNELS"); col = (e && e[0] == '0') ? 0 : 1; }
   if (col && col_ok(a.C) && a.xp == nullptr) {
-    if (a.dtype == KB_F32) { kb_prefer_max_smem_carveout(block_bwd_dz2_col_kernel<float>); block_bwd_dz2_col_kernel<float><<<col_grid(a.B, a.C), 256, 0, st>>>(a); }
-    else { kb_prefer_max_smem_carveout(block_bwd_dz2_col_kernel<bf16>); block_bwd_dz2_col_kernel<bf16><<<col_grid(a.B, a.C), 256, 0, st>>>(a); }
+    if (a.dtype == KB_F32) { block_bwd_dz2_col_kernel<float><<<col_grid(a.B, a.C), 256, 0, st>>>(a); }
+    else { block_bwd_dz2_col_kernel<bf16><<<col_grid(a.B, a.C), 256, 0, st>>>(a); }
     KB_CUDA_LAUNCH_CHECK();
     return KB_OK;
   }
@@ -1215,8 +1215,8 @@ int kbk_bn_bwd_apply(void* d, const void* z, const float* k1, const float* k2, c
   if (n == 0) return KB_OK;
   if (C % kVW == 0 && rows < (1LL << 31)) {
     const int grid = flat_grid(rows, C / kVW);
-    if (dtype == KB_F32) { kb_prefer_max_smem_carveout(bn_bwd_apply_flat_kernel<float>); bn_bwd_apply_flat_kernel<float><<<grid, 256, 0, st>>>((float*)d, (const float*)z, k1, k2, k3, (unsigned)rows, C); }
-    else { kb_prefer_max_smem_carveout(bn_bwd_apply_flat_kernel<bf16>); bn_bwd_apply_flat_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)d, (const bf16*)z, k1, k2, k3, (unsigned)rows, C); }
+    if (dtype == KB_F32) { bn_bwd_apply_flat_kernel<float><<<grid, 256, 0, st>>>((float*)d, (const float*)z, k1, k2, k3, (unsigned)rows, C); }
+    else { bn_bwd_apply_flat_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)d, (const bf16*)z, k1, k2, k3, (unsigned)rows, C); }
     KB_CUDA_LAUNCH_CHECK();
     return KB_OK;
   }
@@ -1242,11 +1242,11 @@ int kbk_block_bwd_dx(const PassDArgs& a, cudaStream_t st) {
   if (col && col_ok(a.C) && a.dxc && a.dxp && !a.xp && a.dpool && a.ties && a.mask_out) {
     const int grid = col_grid(a.B, a.C);
     if (a.z_next) {
-      if (a.dtype == KB_F32) { kb_prefer_max_smem_carveout(block_bwd_dx_col_kernel<float, true>); block_bwd_dx_col_kernel<float, true><<<grid, 256, 0, st>>>(a); }
-      else { kb_prefer_max_smem_carveout(block_bwd_dx_col_kernel<bf16, true>); block_bwd_dx_col_kernel<bf16, true><<<grid, 256, 0, st>>>(a); }
+      if (a.dtype == KB_F32) { block_bwd_dx_col_kernel<float, true><<<grid, 256, 0, st>>>(a); }
+      else { block_bwd_dx_col_kernel<bf16, true><<<grid, 256, 0, st>>>(a); }
     } else {
-      if (a.dtype == KB_F32) { kb_prefer_max_smem_carveout(block_bwd_dx_col_kernel<float, false>); block_bwd_dx_col_kernel<float, false><<<grid, 256, 0, st>>>(a); }
-      else { kb_prefer_max_smem_carveout(block_bwd_dx_col_kernel<bf16, false>); block_bwd_dx_col_kernel<bf16, false><<<grid, 256, 0, st>>>(a); }
+      if (a.dtype == KB_F32) { block_bwd_dx_col_kernel<float, false><<<grid, 256, 0, st>>>(a); }
+      else { block_bwd_dx_col_kernel<bf16, false><<<grid, 256, 0, st>>>(a); }
     }
     KB_CUDA_LAUNCH_CHECK();
     return KB_OK;
@@ -1297,8 +1297,8 @@ int kbk_mask_bwd_stats(void* d_inout, const void* z, const float* ma, const floa
   if (col < 0) { const char* e = getenv("KB_COL_KERNELS"); col = (e && e[0] == '0') ? 0 : 1; }
   if (col && col_ok(C)) {
     const int grid = col_grid(B, C);
-    if (dtype == KB_F32) { kb_prefer_max_smem_carveout(mask_bwd_stats_col_kernel<float>); mask_bwd_stats_col_kernel<float><<<grid, 256, 0, st>>>((float*)d_inout, (const float*)z, B, C, ma, mb, board_sum, sums); }
-    else { kb_prefer_max_smem_carveout(mask_bwd_stats_col_kernel<bf16>); mask_bwd_stats_col_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)d_inout, (const bf16*)z, B, C, ma, mb, board_sum, sums); }
+    if (dtype == KB_F32) { mask_bwd_stats_col_kernel<float><<<grid, 256, 0, st>>>((float*)d_inout, (const float*)z, B, C, ma, mb, board_sum, sums); }
+    else { mask_bwd_stats_col_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)d_inout, (const bf16*)z, B, C, ma, mb, board_sum, sums); }
     KB_CUDA_LAUNCH_CHECK();
     return KB_OK;
   }

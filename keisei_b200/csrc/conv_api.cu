@@ -59,10 +59,20 @@ extern "C" int kb_se_block_tail(const void* z, const void* res, void* out, const
                                 const float* board_mean, const float* w1, const float* b1, const float* w2, const float* b2,
                                 float* se_in_out, float* seh_out, float* se_out, int se_raw, float* pool, void* pool_bf16,
                                 float* ties, int B, int C, int S, int num_sms, cudaStream_t stream) {
+  return kb_se_block_tail_variant(z, res, out, bn_a, bn_b, board_mean, w1, b1, w2, b2, se_in_out, seh_out, se_out, se_raw, pool,
+                                  pool_bf16, ties, B, C, S, 0, num_sms, stream);
+}
+
+extern "C" int kb_se_block_tail_variant(const void* z, const void* res, void* out, const float* bn_a, const float* bn_b,
+                                        const float* board_mean, const float* w1, const float* b1, const float* w2,
+                                        const float* b2, float* se_in_out, float* seh_out, float* se_out, int se_raw,
+                                        float* pool, void* pool_bf16, float* ties, int B, int C, int S, int variant,
+                                        int num_sms, cudaStream_t stream) {
+  KB_CHECK_ARG(variant >= 0 && variant <= 2, "kb_se_block_tail_variant: variant must be 0, 1 or 2");
   KB_CHECK_ARG(kbk_se_apply_supported(C, S), "kb_se_block_tail: needs bf16 tiles with C %% 8 == 0, 64 <= C <= 256 (got C=%d S=%d)", C, S);
   SeApplyArgs a; memset(&a, 0, sizeof(a));
   a.z = (const __nv_bfloat16*)z; a.res = (const __nv_bfloat16*)res; a.out = (__nv_bfloat16*)out; a.a = bn_a; a.b = bn_b;
   a.bmean = board_mean; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.se_in_out = se_in_out; a.seh_out = seh_out; a.se_out = se_out; a.se_raw = se_raw;
   a.pool = pool; a.pool_bf = (__nv_bfloat16*)pool_bf16; a.ties = ties; a.B = B; a.C = C; a.S = S;
-  return kbk_se_apply(a, num_sms, stream);
+  return kbk_se_apply_variant(a, variant, num_sms, stream);
 }

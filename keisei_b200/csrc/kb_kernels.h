@@ -173,6 +173,7 @@ struct SeApplyArgs {
 };
 int kbk_se_apply_supported(int C, int S);
 int kbk_se_apply(const SeApplyArgs& a, int num_sms, cudaStream_t st);
+int kbk_se_apply_variant(const SeApplyArgs& a, int variant /*0 default, 1 TMA-staged, 2 column pair*/, int num_sms, cudaStream_t st);
 // se_apply_col.cu: the same contract as a thread-per-channel MLP kernel + one column-layout streaming pass (default)
 int kbk_se_apply_col_supported(int C, int S);
 int kbk_se_apply_col(const SeApplyArgs& a, int num_sms, cudaStream_t st);

@@ -300,8 +300,7 @@ static int kbk_se_apply_tma_supported(int C, int S) {
 // Dispatch: the column pair in se_apply_col.cu by default. Training: 183 + 36 us vs 237 us for the TMA-staged kernel
 // below at B = 8192. Evaluation: the same speed in isolation (95 + 24 us vs 118 us at B = 4096), but the column kernels
 // need (almost) no shared memory, so in the two-branch rollout they run next to the other branch's convolution
-// (+3-4 % positions/s; the TMA kernel's 166 KB ring cannot share an SM with a convolution). Small evaluation batches
-// (< 1000 boards, never split) stay on the TMA kernel: one launch, and 4 % faster there. KB_SE_APPLY=tma / col forces one.
+// (+3-4 % positions/s; the TMA kernel's 166 KB ring cannot share an SM with a convolution). KB_SE_APPLY=tma / col forces one.
 static int forced_variant() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("KB_SE_APPLY"); v = !e ? 0 : (e[0] == 't' ? 1 : (e[0] == 'c' ? 2 : 0)); }
@@ -313,13 +312,16 @@ int kbk_se_apply_supported(int C, int S) {
 
 static int kbk_se_apply_tma(const SeApplyArgs& a, int num_sms, cudaStream_t st);
 
-int kbk_se_apply(const SeApplyArgs& a, int num_sms, cudaStream_t st) {
+int kbk_se_apply(const SeApplyArgs& a, int num_sms, cudaStream_t st) { return kbk_se_apply_variant(a, 0, num_sms, st); }
+
+// variant: 0 = default (KB_SE_APPLY or the column pair), 1 = TMA-staged kernel, 2 = column pair
+int kbk_se_apply_variant(const SeApplyArgs& a, int variant, int num_sms, cudaStream_t st) {
   const bool col_ok = kbk_se_apply_col_supported(a.C, a.S) != 0, tma_ok = kbk_se_apply_tma_supported(a.C, a.S) != 0;
   KB_CHECK_ARG(col_ok || tma_ok, "se_apply: unsupported shape C=%d S=%d", a.C, a.S);
-  const int f = forced_variant();
-  // evaluation calls of >= 1000 boards are the half batches of the two-branch rollout (SEResNetModel.rollout_split_min);
-  // smaller (graph-replayed league / split-merge) batches keep the single-launch TMA kernel
-  const bool want_col = f == 2 || (f == 0 && (a.ties != nullptr || a.B >= 1000));
+  const int f = variant != 0 ? variant : forced_variant();
+  // ONE variant for every batch size: eval-mode results must not depend on what else is in the batch (the two kernels
+  // sum in different orders, so mixing them by batch size would break bit-exact batch invariance)
+  const bool want_col = f != 1;
   if (col_ok && (want_col || !tma_ok)) return kbk_se_apply_col(a, num_sms, st);
   return kbk_se_apply_tma(a, num_sms, st);
 }

@@ -199,8 +199,9 @@ int launch_mlp(const SeApplyArgs& a, int num_sms, cudaStream_t st) {
     KB_CUDA_CHECK(cudaFuncSetAttribute(se_mlp_fwd_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  if (a.ties == nullptr) {
-    // evaluation: small enough to share an SM with a convolution CTA of the other rollout branch
+  if (a.ties == nullptr && a.B >= 1000) {
+    // evaluation half batches of the two-branch rollout: small enough to share an SM with a convolution CTA of the other
+    // branch (bit-identical to the shared-memory variant: same arithmetic, same order, only the weight source differs)
     const int grid = a.B < 4 * num_sms ? a.B : 4 * num_sms;
     kb_prefer_max_smem_carveout(se_mlp_fwd_kernel<S, false>);
     se_mlp_fwd_kernel<S, false><<<grid, a.C, (size_t)(9 * S) * sizeof(float), st>>>(a);

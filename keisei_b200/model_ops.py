@@ -50,6 +50,7 @@ _lib.register_signature("kb_linear_tc", c_int, [_P, c_longlong, c_int, _P, c_int
                                                  c_longlong, c_int, c_int, c_longlong, c_int, _P])
 
 _lib.register_signature("kb_se_block_tail", c_int, [_P] * 13 + [c_int] + [_P] * 3 + [c_int, c_int, c_int, c_int, _P])
+_lib.register_signature("kb_se_block_tail_variant", c_int, [_P] * 13 + [c_int] + [_P] * 3 + [c_int, c_int, c_int, c_int, c_int, _P])
 
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 _DT_INV = {0: torch.float32, 1: torch.bfloat16}
@@ -436,7 +437,7 @@ def linear_tc(x: torch.Tensor, w: torch.Tensor, bias=None, scale=None, relu: boo
 
 @torch.no_grad()
 def se_block_tail(z: torch.Tensor, res: torch.Tensor, board_mean: torch.Tensor, w1, b1, w2, b2, bn_a=None, bn_b=None,
-                  want_ties: bool = False, se_raw: bool = True):
+                  want_ties: bool = False, se_raw: bool = True, variant: int = 0):
     """Fused SE MLP + scale/shift + residual + ReLU + pool statistics (csrc/se_apply.cu) on bf16 (B,81,C) tiles.
     Returns (out, pool (B,3C), ties|None, se_in (B,C), seh (B,S), se (B,2C))."""
     B, _, C = z.shape
@@ -447,10 +448,11 @@ def se_block_tail(z: torch.Tensor, res: torch.Tensor, board_mean: torch.Tensor, 
     pool, se_in, seh, se = f(B, 3 * C), f(B, C), f(B, S), f(B, 2 * C)
     ties = f(B, C) if want_ties else None
     with torch.cuda.device(dev):
-        rc = _lib.load().kb_se_block_tail(
+        rc = _lib.load().kb_se_block_tail_variant(
             z.contiguous().data_ptr(), res.contiguous().data_ptr(), out.data_ptr(), _lib.ptr(bn_a), _lib.ptr(bn_b),
             board_mean.contiguous().data_ptr(), w1.contiguous().data_ptr(), b1.contiguous().data_ptr(),
             w2.contiguous().data_ptr(), b2.contiguous().data_ptr(), se_in.data_ptr(), seh.data_ptr(), se.data_ptr(),
-            1 if se_raw else 0, pool.data_ptr(), None, _lib.ptr(ties), B, C, S, sm_count(dev), _lib.stream_ptr(dev))
+            1 if se_raw else 0, pool.data_ptr(), None, _lib.ptr(ties), B, C, S, int(variant), sm_count(dev),
+            _lib.stream_ptr(dev))
     _lib.check(rc, "kb_se_block_tail")
     return out, pool, ties, se_in, seh, se

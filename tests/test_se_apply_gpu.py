@@ -1,5 +1,6 @@
-"""The TMA-bulk-staged block tail (csrc/se_apply.cu) vs a float64 restatement of reference se_resnet.py:83-98
-on the same bf16-rounded inputs: SE MLP, scale/shift, residual, ReLU, pool statistics, tie counts."""
+"""The block tail — both implementations: 1 = TMA-bulk-staged kernel (csrc/se_apply.cu), 2 = SE-MLP kernel + column
+streaming pass (csrc/se_apply_col.cu) — vs a float64 restatement of reference se_resnet.py:83-98 on the same
+bf16-rounded inputs: SE MLP, scale/shift, residual, ReLU, pool statistics, tie counts."""
 import numpy as np
 import pytest
 import torch
@@ -10,9 +11,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("B,C,S,with_bn,train", [(1, 64, 4, True, True), (5, 128, 8, False, False), (300, 256, 16, True, True),
                                                  (149, 256, 16, False, False), (4096, 256, 16, False, False)])
-def test_se_block_tail_vs_float64(B, C, S, with_bn, train):
+def test_se_block_tail_vs_float64(B, C, S, with_bn, train, variant):
     g = torch.Generator().manual_seed(B * 7 + C)
     z = torch.randn(B, 81, C, generator=g).bfloat16()
     res = torch.randn(B, 81, C, generator=g).clamp_min(0).bfloat16()
@@ -26,7 +28,7 @@ def test_se_block_tail_vs_float64(B, C, S, with_bn, train):
     bmean = z.float().mean(dim=1)
     d = lambda t: None if t is None else t.to(DEV)  # noqa: E731
     out, pool, ties, se_in, seh, se = model_ops.se_block_tail(d(z), d(res), d(bmean), d(w1), d(b1), d(w2), d(b2), d(a), d(b),
-                                                             want_ties=train, se_raw=train)
+                                                             want_ties=train, se_raw=train, variant=variant)
     # float64 restatement
     Z, R = z.double(), res.double()
     A = a.double() if with_bn else torch.ones(C, dtype=torch.float64)
