@@ -315,12 +315,30 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
         algo.scaler.update()
 
     steps, warm = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
-    ms_local_bn = None
+    ms_local_bn = ms_nccl_bn = None
+    bn_kind = "local (1 rank)"
     if world > 1:
         # per-rank BatchNorm statistics first (plain DDP), then the reference's default: SyncBatchNorm
-        # (katago_loop.py:494-497, sync_batchnorm = true) — the headline number for N > 1
+        # (katago_loop.py:494-497, sync_batchnorm = true) — the headline number for N > 1. The statistic exchange is
+        # timed both ways: NCCL all-reduce per layer, and this library's one-kernel exchange over NVLink peer memory.
+        from keisei_b200.distributed import PeerBatchNormSync
         ms_local_bn = timed(step, steps, warm, device, world)
         model.convert_sync_batchnorm(BatchNormSync())
+        ms_nccl_bn = timed(step, steps, warm, device, world)
+        bn_kind = "SyncBatchNorm (reference default under DDP), NCCL all-reduce per layer"
+        try:
+            peer = PeerBatchNormSync()
+            ok = torch.ones(1, device=device)
+        except Exception as e:  # noqa: BLE001  (no IPC peer access on this box: keep NCCL)
+            peer, ok = None, torch.zeros(1, device=device)
+            if rank == 0:
+                print(f"PeerBatchNormSync unavailable ({e}); SyncBatchNorm stays on NCCL", file=sys.stderr)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        if float(ok.item()) > 0:
+            model.convert_sync_batchnorm(peer)
+            bn_kind = "SyncBatchNorm (reference default under DDP), one-kernel exchange over NVLink peer memory"
+        else:
+            ms_nccl_bn = None
     ms = timed(step, steps, warm, device, world)
     model.convert_sync_batchnorm(None)
     # GAE over the reference-shaped buffer T=128 x N=64 (+ normalisation)
@@ -340,8 +358,7 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
             "global_batch": UPDATE_GLOBAL_B, "per_gpu_batch": Bu, "scaling": "strong", "gae_T128_N64_ms": gae_ms,
             "frac_of_tensor_roofline": (22.97e9 * UPDATE_GLOBAL_B / world / (ms * 1e-3) / 1e12) / peaks()["bf16_tflops_sustained"],
             "includes": "fwd+losses+bwd+allreduce+unscale+clip+Adam",
-            "batchnorm": "local (1 rank)" if world == 1 else "SyncBatchNorm (reference default under DDP)",
-            "ms_per_step_local_batchnorm": ms_local_bn}
+            "batchnorm": bn_kind, "ms_per_step_local_batchnorm": ms_local_bn, "ms_per_step_nccl_syncbn": ms_nccl_bn}
 
 
 def bench_resnet_update(args, device, rank, world) -> dict:

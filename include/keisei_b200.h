@@ -121,6 +121,26 @@ int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* const* para
                               long long policy_pitch, const float* dvalue, const float* dscore, void* const* grads,
                               int use_tc, int num_sms, kb_allreduce_hook hook, void* hook_user, int world,
                               kb_stream_t stream);
+/* ---- SyncBatchNorm exchange over NVLink peer memory (csrc/peer_sync.cu): one kernel per exchange instead of an NCCL
+ *      collective. Every rank of the node creates one buffer, ships its 64-byte CUDA IPC handle to the others (any host
+ *      transport: torch.distributed all_gather_object in keisei_b200/distributed.py), opens theirs, and fills a
+ *      kb_peer_ctx struct on the host (caller-owned). These are the only entry points of the library that allocate:
+ *      kb_peer_buffer_create = cudaMalloc (IPC needs a whole allocation), released by kb_peer_buffer_destroy. */
+typedef struct kb_peer_ctx {
+  void* peers[16];             /* device pointers of every rank's buffer as mapped in THIS process; peers[rank] = own buffer */
+  int rank, world, n_slots, reserved;
+  long long slot_doubles;      /* capacity of one exchange (>= 2 * max channels) */
+  unsigned long long seq;      /* exchanges done so far; advanced by kb_peer_allreduce_hook */
+} kb_peer_ctx;
+long long kb_peer_buffer_bytes(int world, int n_slots, long long slot_doubles);
+int kb_peer_buffer_create(long long bytes, void** ptr, unsigned char* handle64);   /* zero-filled; handle64: 64 bytes out */
+int kb_peer_buffer_open(const unsigned char* handle64, void** ptr);                /* map a peer's buffer */
+int kb_peer_buffer_close(void* ptr);
+int kb_peer_buffer_destroy(void* ptr);
+/* buf (n doubles, device) <- sum over ranks, in rank order (bit-identical on every rank), stream-ordered */
+int kb_peer_allreduce_f64(void* buf, long long n, const kb_peer_ctx* ctx, unsigned long long seq, kb_stream_t stream);
+/* a kb_allreduce_hook: user = kb_peer_ctx* */
+int kb_peer_allreduce_hook(void* user, void* buf, long long n_doubles, kb_stream_t stream);
 /* grads: float32 buffers shaped like params, PRE-ZEROED by the caller */
 int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const* params, const void* wpack, int B,
                          int dtype, void* workspace, long long ws_bytes, const void* dpolicy,

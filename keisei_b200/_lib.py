@@ -36,6 +36,13 @@ _SIGS: dict[str, tuple[object, list[object]]] = {
                                   c_longlong, _P]),
     "kb_value_losses_fwd": (c_int, [_P, _P, _P, _P, c_int, _P, _P]),
     "kb_value_losses_bwd": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
+    "kb_peer_buffer_bytes": (c_longlong, [c_int, c_int, c_longlong]),
+    "kb_peer_buffer_create": (c_int, [c_longlong, _P, _P]),
+    "kb_peer_buffer_open": (c_int, [_P, _P]),
+    "kb_peer_buffer_close": (c_int, [_P]),
+    "kb_peer_buffer_destroy": (c_int, [_P]),
+    "kb_peer_allreduce_f64": (c_int, [_P, c_longlong, _P, c_ulonglong, _P]),
+    "kb_peer_allreduce_hook": (c_int, [_P, _P, c_longlong, _P]),
 }
 
 

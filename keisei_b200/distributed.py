@@ -11,6 +11,7 @@ broadcast from rank 0 at construction.
 """
 from __future__ import annotations
 
+import ctypes
 import logging
 import os
 import random
@@ -117,6 +118,96 @@ class BatchNormSync:
         if self.world_size > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
         return sums
+
+
+class KbPeerCtx(ctypes.Structure):
+    """include/keisei_b200.h: kb_peer_ctx"""
+    _fields_ = [("peers", ctypes.c_void_p * 16), ("rank", ctypes.c_int), ("world", ctypes.c_int), ("n_slots", ctypes.c_int),
+                ("reserved", ctypes.c_int), ("slot_doubles", ctypes.c_longlong), ("seq", ctypes.c_ulonglong)]
+
+
+class PeerBatchNormSync:
+    """SyncBatchNorm exchange as ONE kernel over NVLink peer memory (csrc/peer_sync.cu) instead of an NCCL collective:
+    every rank of the node owns a CUDA-IPC-shared buffer; an exchange stores this rank's sums into all peers' buffers,
+    raises a flag there, waits for the peers' flags locally and adds the rows in rank order (bit-identical statistics
+    on every rank). ~5 us instead of ~21 us per exchange, 164 exchanges per 40-block step, and no Python in the loop:
+    the C schedule calls `kb_peer_allreduce_hook` directly. Single node only (all ranks must be IPC peers); use
+    `BatchNormSync` (NCCL) otherwise. `close()` unmaps and frees (also on garbage collection)."""
+
+    def __init__(self, process_group=None, max_channels: int = 1024, n_slots: int = 4) -> None:
+        from . import _lib
+        if not dist.is_initialized():
+            raise RuntimeError("PeerBatchNormSync needs an initialised process group (setup_distributed)")
+        self._lib = _lib
+        lib = _lib.load()
+        self.group = process_group
+        self.world_size = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        if self.world_size > 16:
+            raise ValueError("PeerBatchNormSync supports up to 16 ranks of one node")
+        slot = 2 * int(max_channels)
+        nbytes = lib.kb_peer_buffer_bytes(self.world_size, n_slots, slot)
+        own, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        _lib.check(lib.kb_peer_buffer_create(nbytes, ctypes.byref(own), handle), "kb_peer_buffer_create")
+        self._own = own.value
+        handles: list = [None] * self.world_size
+        dist.all_gather_object(handles, bytes(handle), group=process_group)
+        self.ctx = KbPeerCtx()
+        self._opened: list[int] = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ctx.peers[r] = self._own
+                continue
+            p = ctypes.c_void_p()
+            hb = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            _lib.check(lib.kb_peer_buffer_open(hb, ctypes.byref(p)), f"kb_peer_buffer_open(rank {r})")
+            self.ctx.peers[r] = p.value
+            self._opened.append(p.value)
+        self.ctx.rank, self.ctx.world, self.ctx.n_slots, self.ctx.slot_doubles, self.ctx.seq = \
+            self.rank, self.world_size, n_slots, slot, 0
+        self.c_hook = ctypes.cast(lib.kb_peer_allreduce_hook, ctypes.c_void_p)
+        self.c_user = ctypes.cast(ctypes.pointer(self.ctx), ctypes.c_void_p)
+        dist.barrier(group=process_group)  # every rank has mapped every buffer before the first exchange
+
+    @classmethod
+    def from_local_buffers(cls, ptrs: list[int], rank: int, slot_doubles: int, n_slots: int = 4) -> "PeerBatchNormSync":
+        """Ranks emulated inside ONE process (tests): the 'peers' are plain device buffers of this process."""
+        from . import _lib
+        self = cls.__new__(cls)
+        self._lib, self.group, self.world_size, self.rank = _lib, None, len(ptrs), rank
+        self._own, self._opened = None, []
+        self.ctx = KbPeerCtx()
+        for r, p in enumerate(ptrs):
+            self.ctx.peers[r] = p
+        self.ctx.rank, self.ctx.world, self.ctx.n_slots, self.ctx.slot_doubles, self.ctx.seq = rank, len(ptrs), n_slots, slot_doubles, 0
+        self.c_hook = ctypes.cast(_lib.load().kb_peer_allreduce_hook, ctypes.c_void_p)
+        self.c_user = ctypes.cast(ctypes.pointer(self.ctx), ctypes.c_void_p)
+        return self
+
+    @torch.no_grad()
+    def all_reduce_(self, sums: torch.Tensor) -> torch.Tensor:
+        """The same exchange from Python (float64 tensor on this rank's device), e.g. for tests."""
+        if self.world_size > 1:
+            with torch.cuda.device(sums.device):
+                rc = self._lib.load().kb_peer_allreduce_hook(self.c_user, sums.data_ptr(), sums.numel(),
+                                                             torch.cuda.current_stream(sums.device).cuda_stream)
+            self._lib.check(rc, "kb_peer_allreduce_hook")
+        return sums
+
+    def close(self) -> None:
+        lib = self._lib.load()
+        for p in self._opened:
+            lib.kb_peer_buffer_close(p)
+        self._opened = []
+        if self._own:
+            lib.kb_peer_buffer_destroy(self._own)
+            self._own = None
+
+    def __del__(self) -> None:  # pragma: no cover - interpreter shutdown order
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class GradSync:

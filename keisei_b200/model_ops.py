@@ -99,12 +99,26 @@ class _BnHook:
             raise self.error
 
 
+class _NativeHook:
+    """A sync object that brings its own C hook (`c_hook` function pointer, `c_user` context pointer): the schedule calls
+    straight into the library (distributed.PeerBatchNormSync -> kb_peer_allreduce_hook), no Python in the loop."""
+
+    def __init__(self, sync) -> None:
+        self.ptr, self.user = sync.c_hook, sync.c_user
+
+    def check(self) -> None:
+        return None
+
+
 def _sync_args(ws: torch.Tensor, sync):
-    """(hook object | None, hook pointer | None, world) for the *_sync entry points."""
+    """(hook object | None, hook pointer | None, hook user pointer | None, world) for the *_sync entry points."""
     if sync is None or int(sync.world_size) <= 1:
-        return None, None, 1
+        return None, None, None, 1
+    if getattr(sync, "c_hook", None) is not None:
+        h = _NativeHook(sync)
+        return h, h.ptr, h.user, int(sync.world_size)
     h = _BnHook(ws, sync)
-    return h, h.ptr, int(sync.world_size)
+    return h, h.ptr, None, int(sync.world_size)
 
 
 def sm_count(device: torch.device) -> int:
@@ -204,12 +218,12 @@ def seresnet_forward_raw(obs: torch.Tensor, tables: PointerTables, wpack: torch.
     policy[:, POLICY_A:].zero_()
     cmax = max(d.channels, d.policy_channels)
     new_stats = torch.empty((2 * d.num_blocks + 2, 2, cmax) if training else (0,), dtype=torch.float32, device=dev)
-    hook, hook_ptr, world = _sync_args(ws, bn_sync if training else None)
+    hook, hook_ptr, hook_user, world = _sync_args(ws, bn_sync if training else None)
     with torch.cuda.device(dev):
         rc = _lib.load().kb_seresnet_forward_sync(
             ctypes.byref(d), tables.pt, tables.bt, new_stats.data_ptr() if training else None, wpack.data_ptr(),
             obs_c.data_ptr(), B, 1 if training else 0, dtype_code, ws.data_ptr(), ws.numel(), policy.data_ptr(),
-            POLICY_PITCH, value.data_ptr(), score.data_ptr(), 1 if use_tc else 0, sm_count(dev), hook_ptr, None, world,
+            POLICY_PITCH, value.data_ptr(), score.data_ptr(), 1 if use_tc else 0, sm_count(dev), hook_ptr, hook_user, world,
             _lib.stream_ptr(dev))
     if hook is not None:
         hook.check()
@@ -238,11 +252,11 @@ def seresnet_backward_raw(tables: PointerTables, wpack: torch.Tensor, ws: torch.
     for i, n in enumerate(sizes):
         gt[i] = base + 4 * off
         off += n
-    hook, hook_ptr, world = _sync_args(ws, bn_sync)
+    hook, hook_ptr, hook_user, world = _sync_args(ws, bn_sync)
     with torch.cuda.device(dev):
         rc = _lib.load().kb_seresnet_backward_sync(
             ctypes.byref(d), tables.pt, wpack.data_ptr(), B, dtype_code, ws.data_ptr(), ws.numel(), dpol.data_ptr(),
-            dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), hook_ptr, None, world,
+            dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), hook_ptr, hook_user, world,
             _lib.stream_ptr(dev))
     if hook is not None:
         hook.check()
@@ -272,12 +286,12 @@ def seresnet_forward(obs: torch.Tensor, params: List[torch.Tensor], buffers: Lis
     cmax = max(d.channels, d.policy_channels)
     new_stats = torch.empty((2 * d.num_blocks + 2, 2, cmax) if training else (0,), dtype=torch.float32, device=dev)
     pt, bt = _ptr_table(params), _ptr_table(buffers)
-    hook, hook_ptr, world = _sync_args(ws, _BN_SYNCS[bn_sync] if (bn_sync and training) else None)
+    hook, hook_ptr, hook_user, world = _sync_args(ws, _BN_SYNCS[bn_sync] if (bn_sync and training) else None)
     with torch.cuda.device(dev):
         rc = _lib.load().kb_seresnet_forward_sync(
             ctypes.byref(d), pt, bt, new_stats.data_ptr() if training else None, wpack.data_ptr(), obs_c.data_ptr(), B, 1 if training else 0, dtype_code,
             ws.data_ptr(), ws.numel(), policy.data_ptr(), POLICY_PITCH, value.data_ptr(), score.data_ptr(),
-            1 if use_tc else 0, sm_count(dev), hook_ptr, None, world, _lib.stream_ptr(dev))
+            1 if use_tc else 0, sm_count(dev), hook_ptr, hook_user, world, _lib.stream_ptr(dev))
     if hook is not None:
         hook.check()
     _lib.check(rc, "kb_seresnet_forward")
@@ -309,11 +323,11 @@ def seresnet_backward(params: List[torch.Tensor], wpack: torch.Tensor, ws: torch
     flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
     grads = [g.view(p.shape) for g, p in zip(flat.split(sizes), params)]
     pt, gt = _ptr_table(params), _ptr_table(grads)
-    hook, hook_ptr, world = _sync_args(ws, _BN_SYNCS[bn_sync] if bn_sync else None)
+    hook, hook_ptr, hook_user, world = _sync_args(ws, _BN_SYNCS[bn_sync] if bn_sync else None)
     with torch.cuda.device(dev):
         rc = _lib.load().kb_seresnet_backward_sync(
             ctypes.byref(d), pt, wpack.data_ptr(), B, dtype_code, ws.data_ptr(), ws.numel(), dpol.data_ptr(),
-            dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), hook_ptr, None, world,
+            dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), hook_ptr, hook_user, world,
             _lib.stream_ptr(dev))
     if hook is not None:
         hook.check()

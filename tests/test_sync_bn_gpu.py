@@ -57,8 +57,56 @@ def rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
 
 
+def _peer_handles(world: int, slot_doubles: int):
+    """`world` in-process ranks of the NVLink peer-memory exchange (csrc/peer_sync.cu): the 'peer' buffers are plain
+    device buffers of this process, one PeerBatchNormSync per rank."""
+    from keisei_b200 import _lib
+    from keisei_b200.distributed import PeerBatchNormSync
+    nbytes = _lib.load().kb_peer_buffer_bytes(world, 4, slot_doubles)
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=DEV) for _ in range(world)]
+    torch.cuda.synchronize()
+    return bufs, [PeerBatchNormSync.from_local_buffers([b.data_ptr() for b in bufs], r, slot_doubles) for r in range(world)]
+
+
+def test_peer_memory_allreduce_kernel_three_ranks_many_rounds():
+    """kb_peer_allreduce_hook: sums in rank order, bit-identical on every rank, slots reused over many exchanges."""
+    W, n = 3, 512
+    bufs, handles = _peer_handles(W, n)
+    g = torch.Generator().manual_seed(0)
+    rounds = [[torch.randn(n - 7 * k, generator=g, dtype=torch.float64) for _ in range(W)] for k in range(11)]
+    got: list = [[] for _ in range(W)]
+    errors: list = []
+
+    def rank_main(r: int) -> None:
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream(DEV)):
+                for k in range(len(rounds)):
+                    t = rounds[k][r].to(DEV)
+                    handles[r].all_reduce_(t)
+                    got[r].append(t.cpu())
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(W)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    for k, parts in enumerate(rounds):
+        want = parts[0].clone()
+        for q in parts[1:]:
+            want += q                      # rank order
+        for r in range(W):
+            assert torch.equal(got[r][k], want), (k, r)
+    assert all(h.ctx.seq == len(rounds) for h in handles)
+    del bufs
+
+
+@pytest.mark.parametrize("kind", ["python_hook", "peer_memory"])
 @pytest.mark.parametrize("amp", [False, True])
-def test_two_ranks_with_sync_bn_match_full_batch(amp):
+def test_two_ranks_with_sync_bn_match_full_batch(amp, kind):
     torch.manual_seed(3)
     p = SEResNetParams(num_blocks=2, channels=64, se_reduction=8, global_pool_channels=16, policy_channels=8,
                        value_fc_size=16, score_fc_size=16)
@@ -86,6 +134,7 @@ def test_two_ranks_with_sync_bn_match_full_batch(amp):
         assert rel(full.value_logits.detach().cpu().numpy(), ov.numpy()) < 1e-4
 
     sync = ThreadSum(W)
+    peer_bufs, peer_handles = _peer_handles(W, 2 * 64) if kind == "peer_memory" else (None, None)
     results: list = [None] * W
     errors: list = []
 
@@ -95,7 +144,7 @@ def test_two_ranks_with_sync_bn_match_full_batch(amp):
             with torch.cuda.stream(torch.cuda.Stream(DEV)):
                 m = SEResNetModel(p)
                 m.load_state_dict(sd)
-                m = m.to(DEV).train().convert_sync_batchnorm(sync.handle(r))
+                m = m.to(DEV).train().convert_sync_batchnorm(peer_handles[r] if kind == "peer_memory" else sync.handle(r))
                 if amp:
                     m.configure_amp(True, torch.bfloat16, "cuda")
                 lo, hi = r * Bh, (r + 1) * Bh
@@ -131,7 +180,8 @@ def test_two_ranks_with_sync_bn_match_full_batch(amp):
     for t in threads:
         t.join(120)
     assert not errors, errors
-    assert sync.calls == 2 * (2 * p.num_blocks + 2)   # one exchange per BatchNorm layer, forward and backward
+    n_exchanges = 2 * (2 * p.num_blocks + 2)   # one exchange per BatchNorm layer, forward and backward
+    assert (peer_handles[0].ctx.seq if kind == "peer_memory" else sync.calls) == n_exchanges
 
     tol_out, tol_grad = (3e-2, 6e-2) if amp else (1e-4, 1e-3)
     for r in range(W):
