@@ -76,7 +76,7 @@ struct Ws {
   float *raw3, *p_flat, *v_flat, *vh, *vpre, *bn;
   void *z0, *x0; BlockWs* blk; float* vout;
   void *ea, *eb, *ey1, *ey2;
-  void *d0, *d1, *d2;
+  void *d0, *d1, *d2, *d4;  // d4: fourth rotating gradient buffer (side-stream weight gradients, see model.cu)
   float *d3, *dp_flat, *dv_flat, *dvh, *dvpre, *k123;
   float* wg_ws; long long wg_ws_bytes;
   int C; size_t total;
@@ -105,7 +105,7 @@ void carve(const RDims& m, void* base, int training, Ws& w, BlockWs* storage) {
       if (storage) storage[i] = bw;
     }
     w.vout = b.f32(B);
-    w.d0 = b.take(m.act()); w.d1 = b.take(m.act()); w.d2 = b.take(m.act());
+    w.d0 = b.take(m.act()); w.d1 = b.take(m.act()); w.d2 = b.take(m.act()); w.d4 = b.take(m.act());
     w.d3 = b.f32((size_t)m.M * 3); w.dp_flat = b.f32(B * kPF); w.dv_flat = b.f32(B * 81); w.dvh = b.f32(B * m.C);
     w.dvpre = b.f32(B); w.k123 = b.f32(2 * 3 * (size_t)m.C);
     w.wg_ws_bytes = (m.dtype == KB_BF16 && m.C % 128 == 0 && m.C <= 256) ? kbk_conv3x3_wgrad_tc_ws_bytes(m.C, m.C, 148 * 2) : 0;
@@ -113,7 +113,7 @@ void carve(const RDims& m, void* base, int training, Ws& w, BlockWs* storage) {
     w.ea = w.eb = w.ey1 = w.ey2 = nullptr;
   } else {
     w.ea = b.take(m.act()); w.eb = b.take(m.act()); w.ey1 = b.take(m.act()); w.ey2 = b.take(m.act());
-    w.z0 = w.x0 = nullptr; w.vout = nullptr; w.d0 = w.d1 = w.d2 = nullptr;
+    w.z0 = w.x0 = nullptr; w.vout = nullptr; w.d0 = w.d1 = w.d2 = w.d4 = nullptr;
     w.d3 = w.dp_flat = w.dv_flat = w.dvh = w.dvpre = w.k123 = nullptr; w.wg_ws = nullptr; w.wg_ws_bytes = 0;
   }
   w.total = b.off + 256;
@@ -330,7 +330,19 @@ extern "C" int kb_resnet_backward(const kb_resnet_desc* d, const void* const* pa
                              G(pi_head(m, 1)), G(pi_head(m, 2)), 2, st));
   KB_TRY(kbk_bn_bwd_finalize(w.dsums + 4, count, P(pi_head(m, 6)), w.bn_mean(LVAL), w.bn_invstd(LVAL), kv, kv + C, kv + 2 * C,
                              G(pi_head(m, 6)), G(pi_head(m, 7)), 1, st));
-  void *cur = w.d0, *t1 = w.d1, *t2 = w.d2;
+  // weight-gradient convolutions on the side stream, exactly as in the SE-ResNet schedule (model.cu): each one is
+  // released just before its data-gradient conv; events per block: [0]/[1] operand ready (main -> side),
+  // [2]/[3] conv2 / conv1 weight gradient done (side -> main); a fourth buffer takes pass D's output
+  const bool overlap = m.L > 0 && bwd_overlap_enabled(st);
+  SideStream& side = side_stream_tls();
+  if (overlap) {
+    int dev = 0;
+    KB_CUDA_CHECK(cudaGetDevice(&dev));
+    KB_TRY(side.ensure(dev, 4 * m.L + 1));
+  }
+  cudaStream_t wst = overlap ? side.s : st;
+  auto ev = [&](int blk, int k) { return side.ev[4 * blk + k]; };
+  void *cur = w.d0, *t1 = w.d1, *t2 = w.d2, *t3 = w.d4;
   KB_TRY(kbk_resnet_head_bwd_x(x_last, dtype, w.d3, w.raw3, k1, kv, C, P(pi_head(m, 0)), P(pi_head(m, 5)), cur, G(pi_head(m, 0)),
                                G(pi_head(m, 5)), B, C, st));
 
@@ -344,7 +356,9 @@ extern "C" int kb_resnet_backward(const kb_resnet_desc* d, const void* const* pa
     KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(pi_blk(i, 4)), w.bn_mean(l2), w.bn_invstd(l2), k1, k2, k3, G(pi_blk(i, 4)),
                                G(pi_blk(i, 5)), C, st));
     KB_TRY(kbk_bn_bwd_apply(t1, bw.z2, k1, k2, k3, m.M, C, dtype, st));
-    KB_TRY(wgrad3x3(m, bw.a1, t1, G(pi_blk(i, 3)), C, C, C, use_tc, num_sms, w.wg_ws, w.wg_ws_bytes, st));
+    if (overlap) { KB_CUDA_CHECK(cudaEventRecord(ev(i, 0), st)); KB_CUDA_CHECK(cudaStreamWaitEvent(wst, ev(i, 0), 0)); }
+    KB_TRY(wgrad3x3(m, bw.a1, t1, G(pi_blk(i, 3)), C, C, C, use_tc, num_sms, w.wg_ws, w.wg_ws_bytes, wst));
+    if (overlap) KB_CUDA_CHECK(cudaEventRecord(ev(i, 2), wst));
     ConvEpi e = epi_base();
     KB_TRY(conv3x3(m, t1, wp.wd(i, 1), t2, C, C, e, use_tc, num_sms, st));
     // ReLU mask of a1, BN1 backward -> dz1
@@ -352,13 +366,24 @@ extern "C" int kb_resnet_backward(const kb_resnet_desc* d, const void* const* pa
     KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(pi_blk(i, 1)), w.bn_mean(l1), w.bn_invstd(l1), k1, k2, k3, G(pi_blk(i, 1)),
                                G(pi_blk(i, 2)), C, st));
     KB_TRY(kbk_bn_bwd_apply(t2, bw.z1, k1, k2, k3, m.M, C, dtype, st));
-    KB_TRY(wgrad3x3(m, x_in, t2, G(pi_blk(i, 0)), C, C, C, use_tc, num_sms, w.wg_ws, w.wg_ws_bytes, st));
+    if (overlap) { KB_CUDA_CHECK(cudaEventRecord(ev(i, 1), st)); KB_CUDA_CHECK(cudaStreamWaitEvent(wst, ev(i, 1), 0)); }
+    KB_TRY(wgrad3x3(m, x_in, t2, G(pi_blk(i, 0)), C, C, C, use_tc, num_sms, w.wg_ws, w.wg_ws_bytes, wst));
+    if (overlap) {
+      KB_CUDA_CHECK(cudaEventRecord(ev(i, 3), wst));
+      KB_CUDA_CHECK(cudaStreamWaitEvent(st, ev(i, 2), 0));  // t1 (dz2) is about to be overwritten
+    }
     KB_TRY(conv3x3(m, t2, wp.wd(i, 0), t1, C, C, e, use_tc, num_sms, st));
-    // dx = data gradient + skip branch (du recomputed from dx' and the ReLU mask of x')
+    // dx = data gradient + skip branch (du recomputed from dx' and the ReLU mask of x'); written to the fourth buffer:
+    // t2 (dz1) is still read by this block's conv1 weight gradient, t3 was the previous block's dz1
     PassDArgs pd; memset(&pd, 0, sizeof(pd));
-    pd.B = B; pd.C = C; pd.dtype = dtype; pd.dxc = t1; pd.dxp = cur; pd.xp = bw.xout; pd.dx = t2;
+    pd.B = B; pd.C = C; pd.dtype = dtype; pd.dxc = t1; pd.dxp = cur; pd.xp = bw.xout; pd.dx = t3;
+    if (overlap && i + 1 < m.L) KB_CUDA_CHECK(cudaStreamWaitEvent(st, ev(i + 1, 3), 0));
     KB_TRY(kbk_block_bwd_dx(pd, st));
-    void* nc = t2; t2 = t1; t1 = cur; cur = nc;
+    void* nc = t3; t3 = t2; t2 = t1; t1 = cur; cur = nc;
+  }
+  if (overlap) {  // join before the stem's weight gradient reuses the partial-tile workspace
+    KB_CUDA_CHECK(cudaEventRecord(side.ev[4 * m.L], wst));
+    KB_CUDA_CHECK(cudaStreamWaitEvent(st, side.ev[4 * m.L], 0));
   }
   // ---- stem ----
   KB_TRY(kbk_relu_bwd_stats(cur, w.x0, w.z0, t1, m.M, C, dtype, w.dsums, st));
