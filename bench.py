@@ -137,7 +137,7 @@ def timed(fn, steps: int, warmup: int, device, world: int) -> float:
     return float(ms.item())
 
 
-def cpu_baseline(batch: int = 256, reps: int = 2) -> dict:
+def cpu_baseline(batch: int = 256, reps: int = 6) -> dict:
     """Oracle port (fp32 CPU PyTorch restatement of the reference) on the host cores: rollout step
     (eval forward + mask/softmax/Categorical sample + log-prob + scalar value) on a bounded sample."""
     from oracle import keisei_oracle as O

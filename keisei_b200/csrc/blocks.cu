@@ -1076,6 +1076,77 @@ inline int flat_grid(long long rows, int cpv) {
   return (int)ctas;
 }
 
+// relu_bwd_stats, column form: dzh = dy * [y > 0] (dzh may alias dy); sums += per-channel sums of dzh and dzh * z.
+// SAME: y and z are the same tensor (two input streams instead of three).
+template <typename T, bool SAME>
+__global__ void __launch_bounds__(256, 3) relu_bwd_stats_col_kernel(const T* dy, const T* __restrict__ y, const T* __restrict__ z,
+                                                                   T* dzh, int B, int C, double* sums) {
+  __shared__ float red[2][256 * kVW];
+  const int TPB = C / kVW, BPC = 256 / TPB;
+  const int slot = threadIdx.x / TPB, c0 = (threadIdx.x % TPB) * kVW;
+  float s1[kVW], s2[kVW];
+#pragma unroll
+  for (int i = 0; i < kVW; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  for (int b = blockIdx.x * BPC + slot; b < B; b += gridDim.x * BPC) {
+    const size_t base = (size_t)b * 81 * C + c0;
+#pragma unroll 1
+    for (int p = 0; p < 81; p += kColPix) {
+      float dd[kColPix][kVW], yy[kColPix][kVW], zz[kColPix][kVW];
+#pragma unroll
+      for (int j = 0; j < kColPix; ++j) {
+        V8<T>::load(dy + base + (size_t)(p + j) * C, dd[j]);
+        V8<T>::load(y + base + (size_t)(p + j) * C, yy[j]);
+        if (!SAME) V8<T>::load(z + base + (size_t)(p + j) * C, zz[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kColPix; ++j) {
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) dd[j][i] = yy[j][i] > 0.f ? dd[j][i] : 0.f;
+        V8<T>::store(dzh + base + (size_t)(p + j) * C, dd[j]);
+        V8<T>::round(dd[j]);
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) { s1[i] += dd[j][i]; s2[i] = fmaf(dd[j][i], SAME ? yy[j][i] : zz[j][i], s2[i]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kVW; ++i) { red[0][slot * C + c0 + i] = s1[i]; red[1][slot * C + c0 + i] = s2[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = 0.f, q = 0.f;
+    for (int l = 0; l < BPC; ++l) { a += red[0][l * C + c]; q += red[1][l * C + c]; }
+    atomicAdd(&sums[c], (double)a);
+    atomicAdd(&sums[C + c], (double)q);
+  }
+}
+
+// pass D of a plain residual block, column form: dx = dxc + dxp * [xp > 0]  (no pool branch, unmasked output)
+template <typename T>
+__global__ void __launch_bounds__(256, 3) resblock_bwd_dx_col_kernel(PassDArgs g) {
+  const int C = g.C, TPB = C / kVW, BPC = 256 / TPB;
+  const int slot = threadIdx.x / TPB, c0 = (threadIdx.x % TPB) * kVW;
+  for (int b = blockIdx.x * BPC + slot; b < g.B; b += gridDim.x * BPC) {
+    const size_t base = (size_t)b * 81 * C + c0;
+#pragma unroll 1
+    for (int p = 0; p < 81; p += kColPix) {
+      float v[kColPix][kVW], t[kColPix][kVW], y[kColPix][kVW];
+#pragma unroll
+      for (int j = 0; j < kColPix; ++j) {
+        const size_t o = base + (size_t)(p + j) * C;
+        V8<T>::load((const T*)g.dxc + o, v[j]);
+        V8<T>::load((const T*)g.dxp + o, t[j]);
+        V8<T>::load((const T*)g.xp + o, y[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kColPix; ++j) {
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) v[j][i] += y[j][i] > 0.f ? t[j][i] : 0.f;
+        V8<T>::store((T*)g.dx + base + (size_t)(p + j) * C, v[j]);
+      }
+    }
+  }
+}
+
 inline bool vec_ok(int C) { return C % kVW == 0 && C / kVW <= 256 && 256 % (C / kVW) == 0; }
 
 inline int ch_threads(int C) { return ((C + 31) / 32) * 32; }
@@ -1251,6 +1322,10 @@ int kbk_block_bwd_dx(const PassDArgs& a, cudaStream_t st) {
     KB_CUDA_LAUNCH_CHECK();
     return KB_OK;
   }
+  if (col && col_ok(a.C) && a.dxc && a.dxp && a.xp && !a.dpool && !a.z_next && !a.mask_out) {
+    KB_DISPATCH_T(a.dtype, resblock_bwd_dx_col_kernel, col_grid(a.B, a.C), 256, 0, st, a);
+    return KB_OK;
+  }
   if (vec_ok(a.C)) {
     const bool hot = a.dxc && a.dxp && !a.xp && a.dpool && a.ties && a.z_next && a.mask_out;
     if (hot) {
@@ -1270,6 +1345,21 @@ int kbk_relu_bwd_stats(const void* dy, const void* y, const void* z, void* dzh, 
                        double* sums, cudaStream_t st) {
   KB_CHECK_ARG(rows % 81 == 0 && C <= 1024, "relu_bwd_stats: bad shape");
   const int B = (int)(rows / 81);
+  static int col = -1;
+  if (col < 0) { const char* e = getenv("KB_COL_KERNELS"); col = (e && e[0] == '0') ? 0 : 1; }
+  if (col && col_ok(C)) {
+    const int grid = col_grid(B, C);
+    const bool same = (y == z);
+    if (dtype == KB_F32) {
+      if (same) relu_bwd_stats_col_kernel<float, true><<<grid, 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)z, (float*)dzh, B, C, sums);
+      else relu_bwd_stats_col_kernel<float, false><<<grid, 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)z, (float*)dzh, B, C, sums);
+    } else {
+      if (same) relu_bwd_stats_col_kernel<bf16, true><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)z, (bf16*)dzh, B, C, sums);
+      else relu_bwd_stats_col_kernel<bf16, false><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)y, (const bf16*)z, (bf16*)dzh, B, C, sums);
+    }
+    KB_CUDA_LAUNCH_CHECK();
+    return KB_OK;
+  }
   if (vec_ok(C)) {
     if (dtype == KB_F32)
       relu_bwd_stats_vec_kernel<float><<<kb_ceil_div(B, kStatsBoardsPerCta), 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)z, (float*)dzh, B, C, nullptr, nullptr, nullptr, sums);
