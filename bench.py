@@ -427,10 +427,17 @@ def bench_league(algo, device, rank, world) -> dict:
             for lo, hi in parts:
                 algo.select_actions(obs[lo:hi], mask[lo:hi])
     ms_split = timed(split128, 2, 3, device, world)
+    subs = [(obs[lo:hi], mask[lo:hi]) for lo, hi in parts]
+    def grouped128():   # the same five sub-batches as parallel branches of one replayed graph
+        for _ in range(128):
+            algo.select_actions_many(subs)
+    ms_grouped = timed(grouped128, 2, 3, device, world)
     return {"metric": "league rollout positions/s (512 envs per GPU, 128 consecutive steps)", "value": world * Bl * 128 / (ms * 1e-3),
             "unit": "positions/s", "ms_per_128_steps": ms, "envs_per_gpu": Bl, "scaling": "weak",
             "split_variant": {"value": world * Bl * 128 / (ms_split * 1e-3), "unit": "positions/s", "ms_per_128_steps": ms_split,
-                              "sub_batches": "256 learner + 4 x 64 opponents (same weights: synthetic)"}}
+                              "sub_batches": "256 learner + 4 x 64 opponents (same weights: synthetic)",
+                              "grouped_value": world * Bl * 128 / (ms_grouped * 1e-3), "grouped_ms_per_128_steps": ms_grouped,
+                              "grouped": "select_actions_many: the five sub-batches as parallel branches of one CUDA graph"}}
 
 
 def update_e2e(algo, device, rank, world, device_buffer: bool = False) -> dict:

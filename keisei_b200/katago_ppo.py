@@ -405,6 +405,52 @@ class KataGoPPOAlgorithm:
         finally:
             self.forward_model.train()
 
+    @torch.no_grad()
+    def select_actions_many(self, batches, models=None, value_adapter: Any | None = None):
+        """Action selection for several independent sub-batches in one go — the learner's and the league opponents'
+        sub-batches of a split-merge step (reference katago_loop.py:284-431 runs one model after the other).
+
+        `batches`: list of (obs, legal_masks); `models`: one model per batch (default: this algorithm's forward model for
+        all). On CUDA the networks run as parallel branches of ONE replayed CUDA graph (`rollout_forward_many`), then each
+        sub-batch is sampled exactly as in `select_actions`. Returns a list of (actions, log_probs, values)."""
+        if models is None:
+            models = [self.forward_model] * len(batches)
+        if len(models) != len(batches):
+            raise ValueError("select_actions_many: one model per batch expected")
+        device = next(self.model.parameters()).device
+        grouped = device.type == "cuda" and all(isinstance(m, SEResNetModel) for m in models)
+        if not grouped:
+            return [self.select_actions(o, k, value_adapter) for o, k in batches]
+        was_training = [m.training for m in models]
+        for m in models:
+            m.eval()
+        try:
+            from .models import rollout_forward_many
+            outs = rollout_forward_many([(m, o) for m, (o, _) in zip(models, batches)])
+            alpha = float(getattr(value_adapter, "score_blend_alpha", 0.0)) if value_adapter is not None else 0.0
+            fused_value = value_adapter is None or hasattr(value_adapter, "score_blend_alpha")
+            results, checks = [], []
+            for out, (obs, masks) in zip(outs, batches):
+                flat = out.policy_logits.reshape(obs.shape[0], -1)
+                actions, log_probs, values, legal, flags = policy_ops.policy_sample(
+                    flat, masks, out.value_logits if fused_value else None, out.score_lead, alpha, seed=self._sample_seed)
+                if not fused_value:
+                    values = value_adapter.scalar_value_blended(out.value_logits, out.score_lead)
+                results.append((actions, log_probs, values))
+                checks.append((flags, legal))
+            if self.strict_guards:   # one host read for all sub-batches
+                bad = torch.stack([f[0] for f, _ in checks]).tolist()
+                for i, b in enumerate(bad):
+                    if int(b) != 0:
+                        zero_envs = (checks[i][1] == 0).nonzero(as_tuple=True)[0].tolist()
+                        raise RuntimeError(f"Environments {zero_envs} have zero legal actions — "
+                                           f"all-False legal mask would produce NaN")
+            return results
+        finally:
+            for m, t in zip(models, was_training):
+                m.train(t)
+            self.forward_model.train()
+
     # ---- advantages ------------------------------------------------------------------------------
     def _advantages(self, data, T: int, N: int, next_values: torch.Tensor, device: torch.device) -> torch.Tensor:
         """GAE over the buffer on `device` (reference katago_ppo.py:649-773): (T,N) grid, per-env padded

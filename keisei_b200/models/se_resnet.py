@@ -306,3 +306,78 @@ class SEResNetModel(KataGoBaseModel):
             with torch.amp.autocast(device_type=self._amp_device_type, dtype=self._amp_dtype):
                 return self._forward_host(obs)
         return self._forward_host(obs)
+
+
+# ---- grouped rollout: several (model, sub-batch) pairs as parallel branches of ONE CUDA graph -------------------------
+_GROUP_GRAPHS: dict = {}
+
+
+@torch.no_grad()
+def rollout_forward_many(pairs: "list[tuple[SEResNetModel, torch.Tensor]]") -> "list[KataGoOutput]":
+    """Eval-mode forward of several independent (model, observations) pairs — the learner and its K league opponents
+    on their sub-batches (reference katago_loop.py:284-431 `split_merge_step`, match_utils.py:124-293 `play_batch`: one
+    sequential forward per model per step, 64..256 boards each). At these sizes a forward is a chain of ~290 kernels of
+    10-20 us that fill a fraction of the GPU, so the pairs are captured as PARALLEL BRANCHES of one CUDA graph (one
+    branch per pair, each on its own stream during capture) and replayed with a single launch: the GPU runs the
+    branches side by side. Results are bit-identical to `model.rollout_forward(obs)` per pair. Returned tensors are views
+    of the graph's static buffers (valid until the next call with the same signature). Falls back to one
+    `rollout_forward` per pair for CPU tensors, training-mode models or unsupported shapes."""
+    if not pairs:
+        return []
+    ok = all(isinstance(m, SEResNetModel) and not m.training and o.is_cuda and m.kernel_supported() and o.ndim == 4
+             and tuple(o.shape[1:]) == (m.params.obs_channels, 9, 9) and 0 < o.shape[0] <= max(m.graph_max_batch, 0)
+             for m, o in pairs) and len({o.device for _, o in pairs}) == 1
+    if not ok or len(pairs) == 1:
+        return [m.rollout_forward(o) for m, o in pairs]
+    dev = pairs[0][1].device
+    prep = []
+    for m, o in pairs:
+        tables = m._ptr_tables()
+        dtype = m._act_dtype(dev)
+        code = 0 if dtype == torch.float32 else 1
+        wpack = m._packed(tables.params, tables.buffers, dtype)
+        prep.append((m, o, tables, wpack, code))
+    key = (dev,) + tuple((id(m), o.shape[0], code, bool(m.use_tensor_cores), wpack.data_ptr(), id(tables))
+                         for m, o, tables, wpack, code in prep)
+    ent = _GROUP_GRAPHS.get(key)
+    if ent is None:
+        if len(_GROUP_GRAPHS) >= 8:
+            _GROUP_GRAPHS.pop(next(iter(_GROUP_GRAPHS)))
+        statics = [torch.empty_like(o, dtype=torch.float32).copy_(o) for _, o, *_ in prep]
+        cur = torch.cuda.current_stream(dev)
+        warm = torch.cuda.Stream(dev)
+        warm.wait_stream(cur)
+        with torch.cuda.stream(warm):  # warm-up outside the capture: one-time function attributes / driver lookups
+            for (m, _, tables, wpack, code), so in zip(prep, statics):
+                model_ops.seresnet_forward_raw(so, tables, wpack, False, code, bool(m.use_tensor_cores))
+        cur.wait_stream(warm)
+        graph = torch.cuda.CUDAGraph()
+        n0 = model_ops._lib.launch_count()
+        outs = []
+        with torch.cuda.graph(graph):
+            cap = torch.cuda.current_stream(dev)
+            branches = []
+            for i, ((m, _, tables, wpack, code), so) in enumerate(zip(prep, statics)):
+                if i == 0:
+                    outs.append(m._captured_forward(so, tables, wpack, code))
+                    continue
+                br = torch.cuda.Stream(dev)
+                br.wait_stream(cap)
+                with torch.cuda.stream(br):
+                    outs.append(m._captured_forward(so, tables, wpack, code))
+                branches.append(br)
+            for br in branches:
+                cap.wait_stream(br)
+        ent = _GROUP_GRAPHS[key] = {"graph": graph, "obs": statics, "outs": outs, "kernels": model_ops._lib.launch_count() - n0,
+                                    "keep": [(tables, wpack) for _, _, tables, wpack, _ in prep]}
+    for so, (_, o, *_rest) in zip(ent["obs"], prep):
+        so.copy_(o)
+    ent["graph"].replay()
+    pairs[0][0].graph_replayed_kernels += ent["kernels"]
+    res = []
+    for (m, o, *_rest), out in zip(prep, ent["outs"]):
+        policy_buf, value, score = out[0], out[1], out[2]
+        m.last_policy_buffer = policy_buf
+        res.append(KataGoOutput(policy_logits=policy_buf[:, :model_ops.POLICY_A].view(o.shape[0], 9, 9, m.SPATIAL_MOVE_TYPES),
+                                value_logits=value, score_lead=score))
+    return res

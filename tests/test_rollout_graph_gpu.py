@@ -83,3 +83,47 @@ def test_two_branch_split_rollout_is_bit_identical(B):
         got = m.rollout_forward(obs)
         assert torch.equal(got.policy_logits, want[0]) and torch.equal(got.value_logits, want[1]) and torch.equal(got.score_lead, want[2])
     assert m.last_policy_buffer[:, 11259:].abs().sum().item() == 0
+
+
+def test_grouped_rollout_many_models_is_bit_identical_and_select_actions_many():
+    """rollout_forward_many / select_actions_many: learner + opponents' sub-batches as parallel branches of one graph."""
+    from keisei_b200.models import rollout_forward_many
+    torch.manual_seed(3)
+    ms = [SEResNetModel(SEResNetParams(**CFG)).to(DEV).eval() for _ in range(3)]
+    for m in ms:
+        m.configure_amp(True, torch.bfloat16, "cuda")
+    sizes = [40, 9, 17, 9]
+    models = [ms[0], ms[1], ms[2], ms[1]]                      # one model appears twice
+    obs = [torch.randn(b, 50, 9, 9, device=DEV) for b in sizes]
+    with torch.no_grad():
+        want = []
+        for m, o in zip(models, obs):
+            w = m(o)
+            want.append((w.policy_logits.clone(), w.value_logits.clone(), w.score_lead.clone()))
+    for _ in range(2):
+        got = rollout_forward_many(list(zip(models, obs)))
+        for g, w in zip(got, want):
+            assert torch.equal(g.policy_logits, w[0]) and torch.equal(g.value_logits, w[1]) and torch.equal(g.score_lead, w[2])
+    # weights change -> the replay follows (in-place re-pack)
+    with torch.no_grad():
+        for p in ms[1].parameters():
+            p.add_(0.01 * torch.randn_like(p))
+        w1 = ms[1](obs[1]).policy_logits.clone()
+    got = rollout_forward_many(list(zip(models, obs)))
+    assert torch.equal(got[1].policy_logits, w1) and torch.equal(got[0].policy_logits, want[0][0])
+    # trainer-level call
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(use_amp=True), ms[0])
+    algo._sample_seed = 7
+    masks = [torch.rand(b, 11259, device=DEV) < 0.01 for b in sizes]
+    for k in masks:
+        k[:, 5] = True
+    res = algo.select_actions_many(list(zip(obs, masks)), models=models)
+    assert len(res) == 4
+    for (a, lp, v), k, o in zip(res, masks, obs):
+        assert a.shape == (o.shape[0],) and k[torch.arange(o.shape[0], device=DEV), a].all() and (lp <= 0).all() and v.abs().max() <= 1
+    single = algo.select_actions(obs[0], masks[0])
+    assert torch.equal(single[2], res[0][2])                  # same network output -> same scalar values
+    assert ms[0].training                                      # forward model left in train mode, as select_actions does
+    bad = masks[2].clone(); bad[3] = False
+    with pytest.raises(RuntimeError, match=r"Environments \[3\] have zero legal actions"):
+        algo.select_actions_many([(obs[0], masks[0]), (obs[2], bad)], models=[ms[0], ms[2]])
