@@ -309,10 +309,7 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
 
     def step():
         algo._step_fused(km, obs, mb, None)
-        algo.scaler.unscale_(algo.optimizer)
-        torch.nn.utils.clip_grad_norm_(model.parameters(), algo.params.grad_clip)
-        algo.scaler.step(algo.optimizer)
-        algo.scaler.update()
+        algo._optimizer_tail()
 
     steps, warm = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
     ms_local_bn = ms_nccl_bn = None
@@ -390,10 +387,7 @@ def bench_resnet_update(args, device, rank, world) -> dict:
 
     def step():
         algo._step_fused(km, obs, mb, None)
-        algo.scaler.unscale_(algo.optimizer)
-        torch.nn.utils.clip_grad_norm_(model.parameters(), algo.params.grad_clip)
-        algo.scaler.step(algo.optimizer)
-        algo.scaler.update()
+        algo._optimizer_tail()
 
     steps, warm = max(2, min(args.steps, 5)), 3
     ms = timed(step, steps, warm, device, world)

@@ -116,6 +116,7 @@ class PPOAlgorithm(KataGoPPOAlgorithm):
                                                   bool(km.use_tensor_cores), km._grad_sizes)
             if self.grad_sync is not None:
                 self.grad_sync.all_reduce_flat(flat)
+            self._flat_grad = flat   # consumed by KataGoPPOAlgorithm._optimizer_tail
             off = 0
             for prm in params:
                 n = prm.numel()

@@ -34,10 +34,7 @@ else:
     km = algo._kernel_model(dev)
     def step():
         algo._step_fused(km, obs, mb, None)
-        algo.scaler.unscale_(algo.optimizer)
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-        algo.scaler.step(algo.optimizer)
-        algo.scaler.update()
+        algo._optimizer_tail()
 for _ in range(2):
     step()
 torch.cuda.synchronize()
