@@ -357,10 +357,10 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
 }
 
 // dw[(co*Cin_true + ci)*9 + tap] += sum_slices ws[slice*units + tap*n_half + half][ci][co_local]
-// The workspace is co-fastest, the PyTorch gradient is (ci, tap)-fastest: a CTA takes a 32 co x 8 ci x 9 tap brick,
+// The workspace is co-fastest, the PyTorch gradient is (ci, tap)-fastest: a CTA takes a 32 co x kRedCi ci x 9 tap brick,
 // reads it with 128-byte rows (co contiguous), transposes through shared memory and writes, per output channel, one
-// contiguous run of 8*9 floats — both sides coalesced (the direct scatter used a 9 KB stride per thread).
-constexpr int kRedCi = 8;
+// contiguous run of kRedCi*9 floats — both sides coalesced (the direct scatter used a 9 KB stride per thread).
+constexpr int kRedCi = 2;  // 32 co x 2 ci x 9 taps per CTA: 1024 CTAs for a 256x256 conv, 2-3 rows per warp (the kernel is latency-bound)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cin, int Cout,
                                                            int Cin_true, int units, int slices) {
   __shared__ float tile[32][kRedCi * 9 + 1];  // [co][ci * 9 + tap]
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     if (co < Cout && ci < Cin_true) {
       const int unit = tap * n_half + co / kTileM;
       const float* p = ws + ((size_t)unit * Cin + ci) * kTileM + (co % kTileM);
-#pragma unroll 4
+#pragma unroll 8
       for (int sl = 0; sl < slices; ++sl) s += p[(size_t)sl * slice_stride];
     }
     tile[lane][r] = s;
