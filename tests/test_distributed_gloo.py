@@ -21,7 +21,8 @@ def _free_port():
 
 def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
-    from keisei_b200.distributed import GradSync, cleanup_distributed, get_distributed_context, seed_all_ranks, setup_distributed
+    from keisei_b200.distributed import (BatchNormSync, GradSync, cleanup_distributed, get_distributed_context, seed_all_ranks,
+                                         setup_distributed)
     from keisei_b200.katago_ppo import KataGoPPOAlgorithm, KataGoPPOParams, KataGoRolloutBuffer
     from keisei_b200.model_registry import build_model
     torch.set_num_threads(1)
@@ -36,6 +37,10 @@ def _worker(rank, world, port, out_dir):
     flat = torch.full((5,), float(rank + 1))
     algo.grad_sync.all_reduce_flat(flat)
     assert torch.allclose(flat, torch.full((5,), 1.5))
+    # the SyncBatchNorm exchange object (NCCL variant; gloo here): a plain SUM of the (2*C,) float64 statistics
+    bn = BatchNormSync()
+    sums = torch.arange(6, dtype=torch.float64) * (rank + 1)
+    assert bn.world_size == world and torch.equal(bn.all_reduce_(sums), torch.arange(6, dtype=torch.float64) * 3)
     N, A = 4, 11259
     buf = KataGoRolloutBuffer(N, (50, 9, 9), A)
     for t in range(2):

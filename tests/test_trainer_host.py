@@ -140,3 +140,38 @@ def test_gae_host_path_matches_golden():
     np.testing.assert_array_equal(G.compute_gae(t("r")[:, 0], t("v")[:, 0], t("term")[:, 0], t("nv")[0], 0.99, 0.95).numpy(), g["adv_1d"])
     with pytest.raises(ValueError, match="only supports 2D"):
         G.compute_gae_gpu(torch.zeros(4), torch.zeros(4), torch.zeros(4), torch.zeros(()), 0.99, 0.95)
+
+
+def test_select_actions_many_and_device_kwarg_on_cpu():
+    """The CUDA-only fast paths degrade to the reference behaviour on CPU tensors: select_actions_many = one
+    select_actions per sub-batch; KataGoRolloutBuffer(device="cpu") is the reference buffer; SyncBatchNorm conversion is
+    accepted and ignored by the CPU path (torch's own SyncBatchNorm is GPU-only)."""
+    torch.manual_seed(0)
+    model = build_model("se_resnet", dict(TINY))
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(), model)
+    batches = []
+    for n in (3, 5):
+        mask = torch.rand(n, 11259) < 0.01
+        mask[:, 7] = True
+        batches.append((torch.randn(n, 50, 9, 9), mask))
+    res = algo.select_actions_many(batches)
+    assert len(res) == 2
+    for (a, lp, v), (o, k) in zip(res, batches):
+        assert a.shape == (o.shape[0],) and k[torch.arange(o.shape[0]), a].all() and (lp <= 0).all() and v.abs().max() <= 1
+    assert model.training
+    with pytest.raises(ValueError, match="one model per batch"):
+        algo.select_actions_many(batches, models=[model])
+    buf = KataGoRolloutBuffer(2, (50, 9, 9), 11259, device="cpu")
+    z = torch.zeros(2)
+    buf.add(torch.zeros(2, 50, 9, 9), z.long(), z, z, z, z.bool(), z.bool(), torch.ones(2, 11259, dtype=torch.bool), z.long(), z)
+    assert buf.size == 1 and buf.flatten()["observations"].device.type == "cpu"
+
+    class FakeSync:
+        world_size = 2
+
+        def all_reduce_(self, t):  # pragma: no cover - never reached on CPU
+            raise AssertionError("the CPU path must not exchange BatchNorm statistics")
+
+    model.convert_sync_batchnorm(FakeSync())
+    out = model(torch.randn(2, 50, 9, 9))
+    assert out.policy_logits.shape == (2, 9, 9, 139)
