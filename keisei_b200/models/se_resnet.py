@@ -111,6 +111,7 @@ class SEResNetModel(KataGoBaseModel):
         # boards are independent in eval mode, so one half's HBM-bound block tails execute under the other half's
         # tensor-bound convolutions (0 disables; KB_ROLLOUT_SPLIT_MIN overrides)
         self.rollout_split_min: int = int(os.environ.get("KB_ROLLOUT_SPLIT_MIN", "2048"))
+        self.rollout_split_ways: int = int(os.environ.get("KB_ROLLOUT_SPLIT_WAYS", "2"))   # number of parallel branches
 
     # ---- kernel plumbing ---------------------------------------------------------------------
     def _desc(self) -> list[int]:
@@ -249,26 +250,39 @@ class SEResNetModel(KataGoBaseModel):
         use_tc = bool(self.use_tensor_cores)
         if self.rollout_split_min <= 0 or B < self.rollout_split_min:
             return model_ops.seresnet_forward_raw(obs, tables, wpack, False, code, use_tc)
-        # split on a 3-board tile boundary; the first part gets a whole number of conv rounds (74 board groups x 2
-        # channel halves = one CTA per SM) so only the second part pays a partial last round
+        # split on 3-board tile boundaries; every part but the last gets a whole number of conv rounds (74 board groups x
+        # 2 channel halves = one CTA per SM), so only the last part pays a partial round
         groups = (B + 2) // 3
-        g1 = max(74, int(round(groups / 2 / 74)) * 74) if groups >= 4 * 74 else groups // 2
-        h = min(B - 1, max(1, g1 * 3))
+        ways = max(2, min(self.rollout_split_ways, groups))
+        if groups >= 2 * ways * 74:
+            per = max(74, int(round(groups / ways / 74)) * 74)
+        else:
+            per = max(1, groups // ways)
+        cuts = [min(B, k * per * 3) for k in range(1, ways)]
+        bounds = sorted(set([0] + [c for c in cuts if 0 < c < B] + [B]))
         dev = obs.device
         dtype = torch.float32 if code == 0 else torch.bfloat16
         policy = torch.empty((B, model_ops.POLICY_PITCH), dtype=dtype, device=dev)
         value = torch.empty((B, 3), dtype=torch.float32, device=dev)
         score = torch.empty((B, 1), dtype=torch.float32, device=dev)
         cur = torch.cuda.current_stream(dev)
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(cur)
-        _, _, _, ws1, _ = model_ops.seresnet_forward_raw(obs[:h], tables, wpack, False, code, use_tc,
-                                                         out=(policy[:h], value[:h], score[:h]))
-        with torch.cuda.stream(side):
-            _, _, _, ws2, _ = model_ops.seresnet_forward_raw(obs[h:], tables, wpack, False, code, use_tc,
-                                                             out=(policy[h:], value[h:], score[h:]))
-        cur.wait_stream(side)
-        return policy, value, score, (ws1, ws2), None
+        spans = list(zip(bounds[:-1], bounds[1:]))
+        # fork every side branch BEFORE anything is enqueued on the capturing stream: a branch that waited on the stream
+        # after part 0 was enqueued would depend on all of part 0 and the parts would run one after the other
+        sides = [torch.cuda.Stream(dev) for _ in spans[1:]]
+        for side in sides:
+            side.wait_stream(cur)
+        workspaces = []
+        for k, (lo, hi) in enumerate(spans):
+            outs = (policy[lo:hi], value[lo:hi], score[lo:hi])
+            if k == 0:
+                workspaces.append(model_ops.seresnet_forward_raw(obs[lo:hi], tables, wpack, False, code, use_tc, out=outs)[3])
+            else:
+                with torch.cuda.stream(sides[k - 1]):
+                    workspaces.append(model_ops.seresnet_forward_raw(obs[lo:hi], tables, wpack, False, code, use_tc, out=outs)[3])
+        for side in sides:
+            cur.wait_stream(side)
+        return policy, value, score, tuple(workspaces), None
 
     @torch.no_grad()
     def _store_running_stats(self, buffers: list[torch.Tensor], new_stats: torch.Tensor) -> None:
@@ -356,16 +370,16 @@ def rollout_forward_many(pairs: "list[tuple[SEResNetModel, torch.Tensor]]") -> "
         outs = []
         with torch.cuda.graph(graph):
             cap = torch.cuda.current_stream(dev)
-            branches = []
+            # fork every branch before anything is enqueued on the capturing stream (a later fork would depend on pair 0)
+            branches = [torch.cuda.Stream(dev) for _ in prep[1:]]
+            for br in branches:
+                br.wait_stream(cap)
             for i, ((m, _, tables, wpack, code), so) in enumerate(zip(prep, statics)):
                 if i == 0:
                     outs.append(m._captured_forward(so, tables, wpack, code))
-                    continue
-                br = torch.cuda.Stream(dev)
-                br.wait_stream(cap)
-                with torch.cuda.stream(br):
-                    outs.append(m._captured_forward(so, tables, wpack, code))
-                branches.append(br)
+                else:
+                    with torch.cuda.stream(branches[i - 1]):
+                        outs.append(m._captured_forward(so, tables, wpack, code))
             for br in branches:
                 cap.wait_stream(br)
         ent = _GROUP_GRAPHS[key] = {"graph": graph, "obs": statics, "outs": outs, "kernels": model_ops._lib.launch_count() - n0,
