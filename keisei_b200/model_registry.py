@@ -3,7 +3,7 @@ the hot path. `install_into_reference()` swaps these classes into the reference'
 `keisei.training.model_registry.build_model("se_resnet", ...)` returns the B200 implementation."""
 from __future__ import annotations
 
-from typing import Any, NamedTuple
+from typing import Any, Callable, NamedTuple
 
 import torch.nn as nn
 
@@ -22,49 +22,51 @@ _REGISTRY: dict[str, ArchitectureSpec] = {
     "resnet": ArchitectureSpec(ResNetModel, ResNetParams, "scalar", 50),
     "se_resnet": ArchitectureSpec(SEResNetModel, SEResNetParams, "multi_head", 50),
 }
+VALID_ARCHITECTURES = set(_REGISTRY)
 
-VALID_ARCHITECTURES = set(_REGISTRY.keys())
+# value checks per architecture: (field, predicate, requirement text) — the dataclass only checks names / arity
+_POSITIVE = (lambda v: v > 0, "must be > 0")
+_NON_NEGATIVE = (lambda v: v >= 0, "must be >= 0")
+_FIELD_RULES: dict[str, tuple[tuple[str, tuple[Callable[[Any], bool], str]], ...]] = {
+    "se_resnet": (("channels", _POSITIVE), ("se_reduction", _POSITIVE)),
+    "resnet": (("hidden_size", _POSITIVE), ("num_layers", _NON_NEGATIVE)),
+}
 
 
-def _get_spec(architecture: str) -> ArchitectureSpec:
-    if architecture not in _REGISTRY:
-        raise ValueError(f"Unknown architecture '{architecture}'. Valid: {sorted(VALID_ARCHITECTURES)}")
-    return _REGISTRY[architecture]
+def _spec_of(architecture: str) -> ArchitectureSpec:
+    try:
+        return _REGISTRY[architecture]
+    except KeyError:
+        raise ValueError(f"Unknown architecture '{architecture}'. Valid: {sorted(VALID_ARCHITECTURES)}") from None
 
 
 def validate_model_params(architecture: str, params: dict[str, Any]) -> object:
-    spec = _get_spec(architecture)
+    """`params_cls(**params)` plus the value checks: TypeError for bad keyword names, ValueError for bad values or an
+    unknown architecture (reference model_registry.py:34-72)."""
+    spec = _spec_of(architecture)
     try:
-        validated = spec.params_cls(**params)
+        obj = spec.params_cls(**params)
     except TypeError as e:
         raise TypeError(f"Invalid params for '{architecture}': {e}") from e
-    if architecture == "se_resnet":
-        if validated.channels <= 0:
-            raise ValueError(f"se_resnet: channels must be > 0, got {validated.channels}")
-        if validated.se_reduction <= 0:
-            raise ValueError(f"se_resnet: se_reduction must be > 0, got {validated.se_reduction}")
-        if validated.channels // validated.se_reduction < 1:
-            raise ValueError(f"se_resnet: channels ({validated.channels}) // se_reduction "
-                             f"({validated.se_reduction}) must be >= 1")
-    elif architecture == "resnet":
-        if validated.hidden_size <= 0:
-            raise ValueError(f"resnet: hidden_size must be > 0, got {validated.hidden_size}")
-        if validated.num_layers < 0:
-            raise ValueError(f"resnet: num_layers must be >= 0, got {validated.num_layers}")
-    return validated
+    for field, (ok, text) in _FIELD_RULES.get(architecture, ()):
+        value = getattr(obj, field)
+        if not ok(value):
+            raise ValueError(f"{architecture}: {field} {text}, got {value}")
+    if architecture == "se_resnet" and obj.channels // obj.se_reduction < 1:   # the SE hidden width would be zero
+        raise ValueError(f"se_resnet: channels ({obj.channels}) // se_reduction ({obj.se_reduction}) must be >= 1")
+    return obj
 
 
 def build_model(architecture: str, params: dict[str, Any]) -> nn.Module:
-    validated = validate_model_params(architecture, params)
-    return _get_spec(architecture).model_cls(validated)
+    return _spec_of(architecture).model_cls(validate_model_params(architecture, params))
 
 
 def get_model_contract(architecture: str) -> str:
-    return _get_spec(architecture).contract
+    return _spec_of(architecture).contract
 
 
 def get_obs_channels(architecture: str) -> int:
-    return _get_spec(architecture).obs_channels
+    return _spec_of(architecture).obs_channels
 
 
 def install_into_reference() -> None:
