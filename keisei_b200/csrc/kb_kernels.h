@@ -14,6 +14,20 @@ int kbk_conv3x3_simt(const void* in, const void* w, void* out, int B, int Cin, i
 int kbk_conv3x3_wgrad_simt(const void* x, const void* dy, float* dw, int B, int Cin, int Cout, int Cin_true,
                            int dtype, cudaStream_t st);
 
+// ---- pack_batched.cu: all weight re-packs of a network in one launch per 256 jobs ----
+#define KB_PACK_CONV 0    // s0 = w (Cout,Cin,3,3) fp32; d0 = wf [Cout][9][Cinp], d1 = wd [Cinp][9][Cout] or null; n0..n2 = Cout, Cin, Cinp
+#define KB_PACK_LINEAR 1  // s0 = w (N,K) fp32; d0 = bf16 [Np][Kp]; n0..n3 = N, K, Np, Kp
+#define KB_PACK_BN 2      // s0..s3 = weight, bias, running_mean, running_var; d0 = a, d1 = b; count = C
+struct PackJob {
+  const float *s0, *s1, *s2, *s3;
+  void *d0, *d1;
+  long long count;        // elements of d0 this job writes
+  int kind, dtype, n0, n1, n2, n3;
+  float eps;
+  int pad_;
+};
+int kbk_pack_batched(const PackJob* jobs, int n_jobs, cudaStream_t st);
+
 // ---- conv_tc.cu (tcgen05 / TMEM / TMA, bf16) ----
 int kbk_conv3x3_tc_supported(int Cin, int Cout, int dtype);
 int kbk_conv3x3_tc(const void* in, const void* w, void* out, int B, int Cin, int Cout, const ConvEpi& epi,

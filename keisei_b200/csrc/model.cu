@@ -10,6 +10,7 @@
 // Buffer table order: input_bn.{running_mean,running_var,num_batches_tracked}, per block bn1.*, bn2.*,
 // then policy_bn1.*.
 #include <stdlib.h>
+#include <vector>
 #include "kb_common.cuh"
 #include "kb_kernels.h"
 #include "schedule_common.cuh"
@@ -230,36 +231,55 @@ extern "C" int kb_seresnet_pack_weights(const kb_seresnet_desc* d, const void* c
   const Dims m = make_dims(d, 1, dtype);
   WPack w = make_wpack(m, wpack);
   KB_CHECK_ARG(wpack && (size_t)wpack_bytes >= w.total, "wpack buffer too small: %lld < %zu", wpack_bytes, w.total);
-  KB_TRY(kbk_pack_conv_weight((const float*)params[0], w.stem_wf, nullptr, m.C, m.C0, m.C0p, dtype, st));
-  auto bn = [&](int layer, int pw, int bbase, int C) {
-    return kbk_bn_eval_affine((const float*)params[pw], (const float*)params[pw + 1], (const float*)buffers[bbase],
-                              (const float*)buffers[bbase + 1], kBnEps, C, w.bn_a(layer), w.bn_b(layer), st);
+  // one job list, a handful of launches (pack_batched.cu) instead of ~8 launches per block
+  const int max_jobs = 2 + 8 * m.nb + 1 + 6;
+  std::vector<PackJob> jobs_v((size_t)max_jobs);
+  PackJob* jobs = jobs_v.data();
+  int nj = 0;
+  auto conv = [&](const void* wsrc, void* wf, void* wd, int Cout, int Cin, int Cinp) {
+    PackJob j; memset(&j, 0, sizeof(j));
+    j.kind = KB_PACK_CONV; j.dtype = dtype; j.s0 = (const float*)wsrc; j.d0 = wf; j.d1 = wd; j.n0 = Cout; j.n1 = Cin; j.n2 = Cinp;
+    j.count = (long long)Cout * 9 * Cinp;
+    jobs[nj++] = j;
   };
-  KB_TRY(bn(0, 1, 0, m.C));
+  auto bn = [&](int layer, int pw, int bbase, int C) {
+    PackJob j; memset(&j, 0, sizeof(j));
+    j.kind = KB_PACK_BN; j.s0 = (const float*)params[pw]; j.s1 = (const float*)params[pw + 1];
+    j.s2 = (const float*)buffers[bbase]; j.s3 = (const float*)buffers[bbase + 1];
+    j.d0 = w.bn_a(layer); j.d1 = w.bn_b(layer); j.count = C; j.eps = kBnEps;
+    jobs[nj++] = j;
+  };
+  auto lin = [&](const void* wsrc, void* out, int N, int K, int Np, int Kp) {
+    PackJob j; memset(&j, 0, sizeof(j));
+    j.kind = KB_PACK_LINEAR; j.s0 = (const float*)wsrc; j.d0 = out; j.n0 = N; j.n1 = K; j.n2 = Np; j.n3 = Kp;
+    j.count = (long long)Np * Kp;
+    jobs[nj++] = j;
+  };
+  conv(params[0], w.stem_wf, nullptr, m.C, m.C0, m.C0p);
+  bn(0, 1, 0, m.C);
   for (int i = 0; i < m.nb; ++i) {
-    KB_TRY(kbk_pack_conv_weight((const float*)params[pi_blk(i, 0)], w.wf(i, 0), w.wd(i, 0), m.C, m.C, m.C, dtype, st));
-    KB_TRY(kbk_pack_conv_weight((const float*)params[pi_blk(i, 3)], w.wf(i, 1), w.wd(i, 1), m.C, m.C, m.C, dtype, st));
-    KB_TRY(bn(1 + 2 * i, pi_blk(i, 1), bi_blk(i, 0), m.C));
-    KB_TRY(bn(2 + 2 * i, pi_blk(i, 4), bi_blk(i, 3), m.C));
+    conv(params[pi_blk(i, 0)], w.wf(i, 0), w.wd(i, 0), m.C, m.C, m.C);
+    conv(params[pi_blk(i, 3)], w.wf(i, 1), w.wd(i, 1), m.C, m.C, m.C);
+    bn(1 + 2 * i, pi_blk(i, 1), bi_blk(i, 0), m.C);
+    bn(2 + 2 * i, pi_blk(i, 4), bi_blk(i, 3), m.C);
   }
-  KB_TRY(bn(2 * m.nb + 1, pi_head(m, 1), bi_pol(m, 0), m.Pc));
+  bn(2 * m.nb + 1, pi_head(m, 1), bi_pol(m, 0), m.Pc);
   if (dtype == KB_BF16 && m.C % 64 == 0) {
-    auto P = [&](int i) { return (const float*)params[i]; };
     const int K3 = 3 * m.C;
     for (int i = 0; i < m.nb; ++i) {
-      KB_TRY(kbk_pack_linear_weight(P(pi_blk(i, 6)), w.lin_blk(i, w.o_g1), m.G, K3, w.Gp, K3, st));
-      KB_TRY(kbk_pack_linear_weight(P(pi_blk(i, 8)), w.lin_blk(i, w.o_g2), m.C, m.G, w.Cp, w.Gk, st));
-      KB_TRY(kbk_pack_linear_weight(P(pi_blk(i, 10)), w.lin_blk(i, w.o_s1), m.S, m.C, w.Sp, m.C, st));
-      KB_TRY(kbk_pack_linear_weight(P(pi_blk(i, 12)), w.lin_blk(i, w.o_s2), 2 * m.C, m.S, w.C2p, w.Sk, st));
+      lin(params[pi_blk(i, 6)], w.lin_blk(i, w.o_g1), m.G, K3, w.Gp, K3);
+      lin(params[pi_blk(i, 8)], w.lin_blk(i, w.o_g2), m.C, m.G, w.Cp, w.Gk);
+      lin(params[pi_blk(i, 10)], w.lin_blk(i, w.o_s1), m.S, m.C, w.Sp, m.C);
+      lin(params[pi_blk(i, 12)], w.lin_blk(i, w.o_s2), 2 * m.C, m.S, w.C2p, w.Sk);
     }
-    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 0)), w.lin_head(w.o_p1), m.Pc, m.C, w.Pp, m.C, st));
-    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 3)), w.lin_head(w.o_p2), 139, m.Pc, 256, w.Pk, st));
-    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 5)), w.lin_head(w.o_v1), m.V, K3, w.Vp, K3, st));
-    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 7)), w.lin_head(w.o_v2), 3, m.V, 128, w.Vk, st));
-    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 9)), w.lin_head(w.o_c1), m.S2, K3, w.Qp, K3, st));
-    KB_TRY(kbk_pack_linear_weight(P(pi_head(m, 11)), w.lin_head(w.o_c2), 1, m.S2, 128, w.Qk, st));
+    lin(params[pi_head(m, 0)], w.lin_head(w.o_p1), m.Pc, m.C, w.Pp, m.C);
+    lin(params[pi_head(m, 3)], w.lin_head(w.o_p2), 139, m.Pc, 256, w.Pk);
+    lin(params[pi_head(m, 5)], w.lin_head(w.o_v1), m.V, K3, w.Vp, K3);
+    lin(params[pi_head(m, 7)], w.lin_head(w.o_v2), 3, m.V, 128, w.Vk);
+    lin(params[pi_head(m, 9)], w.lin_head(w.o_c1), m.S2, K3, w.Qp, K3);
+    lin(params[pi_head(m, 11)], w.lin_head(w.o_c2), 1, m.S2, 128, w.Qk);
   }
-  return KB_OK;
+  return kbk_pack_batched(jobs, nj, st);
 }
 
 extern "C" int kb_seresnet_forward(const kb_seresnet_desc* d, const void* const* params, void* const* buffers,
