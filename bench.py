@@ -313,6 +313,7 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
 
     steps, warm = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
     ms_local_bn = ms_nccl_bn = None
+    peer = None
     bn_kind = "local (1 rank)"
     if world > 1:
         # per-rank BatchNorm statistics first (plain DDP), then the reference's default: SyncBatchNorm
@@ -331,13 +332,20 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
             if rank == 0:
                 print(f"PeerBatchNormSync unavailable ({e}); SyncBatchNorm stays on NCCL", file=sys.stderr)
         torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
-        if float(ok.item()) > 0:
+        peer_everywhere = float(ok.item()) > 0
+        if not peer_everywhere and peer is not None:
+            peer.close(collective=False)   # some other rank could not map the buffers: nobody will use them
+            peer = None
+        if peer_everywhere:
             model.convert_sync_batchnorm(peer)
             bn_kind = "SyncBatchNorm (reference default under DDP), one-kernel exchange over NVLink peer memory"
         else:
             ms_nccl_bn = None
     ms = timed(step, steps, warm, device, world)
     model.convert_sync_batchnorm(None)
+    if world > 1 and peer is not None:
+        torch.cuda.synchronize(device)
+        peer.close()   # collective: unmap everywhere, barrier, then free
     # GAE over the reference-shaped buffer T=128 x N=64 (+ normalisation)
     from keisei_b200 import gae as G
     T, N = 128, 64

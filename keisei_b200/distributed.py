@@ -132,7 +132,8 @@ class PeerBatchNormSync:
     raises a flag there, waits for the peers' flags locally and adds the rows in rank order (bit-identical statistics
     on every rank). ~5 us instead of ~21 us per exchange, 164 exchanges per 40-block step, and no Python in the loop:
     the C schedule calls `kb_peer_allreduce_hook` directly. Single node only (all ranks must be IPC peers); use
-    `BatchNormSync` (NCCL) otherwise. `close()` unmaps and frees (also on garbage collection)."""
+    `BatchNormSync` (NCCL) otherwise. Call `close()` on every rank when done (collective; garbage collection only
+    unmaps and frees without the barrier if the process group is already gone)."""
 
     def __init__(self, process_group=None, max_channels: int = 1024, n_slots: int = 4) -> None:
         from . import _lib
@@ -150,19 +151,32 @@ class PeerBatchNormSync:
         own, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
         _lib.check(lib.kb_peer_buffer_create(nbytes, ctypes.byref(own), handle), "kb_peer_buffer_create")
         self._own = own.value
+        self._collective = self.world_size > 1   # close() meets the other ranks at a barrier before freeing
         handles: list = [None] * self.world_size
         dist.all_gather_object(handles, bytes(handle), group=process_group)
         self.ctx = KbPeerCtx()
         self._opened: list[int] = []
-        for r, h in enumerate(handles):
-            if r == self.rank:
-                self.ctx.peers[r] = self._own
-                continue
-            p = ctypes.c_void_p()
-            hb = (ctypes.c_ubyte * 64).from_buffer_copy(h)
-            _lib.check(lib.kb_peer_buffer_open(hb, ctypes.byref(p)), f"kb_peer_buffer_open(rank {r})")
-            self.ctx.peers[r] = p.value
-            self._opened.append(p.value)
+        failure: Exception | None = None
+        try:
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.ctx.peers[r] = self._own
+                    continue
+                p = ctypes.c_void_p()
+                hb = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                _lib.check(lib.kb_peer_buffer_open(hb, ctypes.byref(p)), f"kb_peer_buffer_open(rank {r})")
+                self.ctx.peers[r] = p.value
+                self._opened.append(p.value)
+        except Exception as e:  # noqa: BLE001
+            failure = e
+        # every rank learns whether EVERY rank mapped every buffer; on any failure all ranks back out together (a rank
+        # that raised alone would leave the others waiting in the next collective)
+        oks: list = [None] * self.world_size
+        dist.all_gather_object(oks, failure is None, group=process_group)
+        if not all(oks):
+            self.close()   # collective: unmap, barrier, free
+            raise RuntimeError(f"PeerBatchNormSync: CUDA IPC mapping failed on rank(s) {[r for r, o in enumerate(oks) if not o]}"
+                               + (f": {failure}" if failure is not None else ""))
         self.ctx.rank, self.ctx.world, self.ctx.n_slots, self.ctx.slot_doubles, self.ctx.seq = \
             self.rank, self.world_size, n_slots, slot, 0
         self.c_hook = ctypes.cast(lib.kb_peer_allreduce_hook, ctypes.c_void_p)
@@ -175,7 +189,7 @@ class PeerBatchNormSync:
         from . import _lib
         self = cls.__new__(cls)
         self._lib, self.group, self.world_size, self.rank = _lib, None, len(ptrs), rank
-        self._own, self._opened = None, []
+        self._own, self._opened, self._collective = None, [], False
         self.ctx = KbPeerCtx()
         for r, p in enumerate(ptrs):
             self.ctx.peers[r] = p
@@ -194,18 +208,27 @@ class PeerBatchNormSync:
             self._lib.check(rc, "kb_peer_allreduce_hook")
         return sums
 
-    def close(self) -> None:
+    def close(self, collective: bool = True) -> None:
+        """Unmap the peers' buffers, then free this rank's. COLLECTIVE (unless `collective=False`) when the object was built
+        over a process group:
+        a buffer must not be freed while another rank still has it mapped (CUDA IPC), so every rank unmaps first and
+        the ranks meet at a barrier before any of them frees. Idempotent."""
         lib = self._lib.load()
         for p in self._opened:
             lib.kb_peer_buffer_close(p)
         self._opened = []
         if self._own:
+            if collective and getattr(self, "_collective", False) and dist.is_available() and dist.is_initialized():
+                try:
+                    dist.barrier(group=self.group)
+                except Exception:  # noqa: BLE001  (process group already torn down: nothing left to wait for)
+                    pass
             lib.kb_peer_buffer_destroy(self._own)
             self._own = None
 
     def __del__(self) -> None:  # pragma: no cover - interpreter shutdown order
         try:
-            self.close()
+            self.close(collective=False)
         except Exception:
             pass
 
