@@ -270,6 +270,78 @@ def golden_resnet():
     print("resnet_tiny.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB raw")
 
 
+def _buffer_steps(seed: int, T: int, N: int, ragged: bool, A: int = 11259):
+    """Seeded rollout steps; `ragged`: split-merge style env subsets with env_ids (katago_loop.py:284-431)."""
+    g = torch.Generator().manual_seed(seed)
+    steps = []
+    for t in range(T):
+        ids = torch.arange(N) if not ragged else torch.sort(torch.randperm(N, generator=g)[: max(1, N - (t % 3))]).values
+        n = ids.numel()
+        obs = torch.randn(n, 50, 9, 9, generator=g)
+        mask = torch.rand(n, A, generator=g) < 0.01
+        actions = torch.randint(0, A, (n,), generator=g)
+        mask[torch.arange(n), actions] = True
+        term = torch.rand(n, generator=g) < 0.15
+        trunc = (torch.rand(n, generator=g) < 0.1) & ~term
+        dones = term | trunc
+        rewards = torch.where(term, torch.randint(-1, 2, (n,), generator=g).float(), torch.zeros(n))
+        cats = torch.where(term, torch.randint(0, 3, (n,), generator=g), torch.full((n,), -1))
+        ov = torch.where(trunc, torch.randn(n, generator=g), torch.full((n,), float("nan")))
+        steps.append(dict(obs=obs, actions=actions, logp=-3 * torch.rand(n, generator=g), values=0.5 * torch.randn(n, generator=g),
+                          rewards=rewards, dones=dones, term=term, mask=mask, cats=cats,
+                          score_t=torch.randn(n, generator=g).clamp(-1.5, 1.5), ids=ids, ov=ov))
+    return steps
+
+
+def golden_buffer():
+    """KataGoRolloutBuffer (katago_ppo.py:128-388): flatten() of the (T, N) grid layout after
+    fill_alternating_perspective_overrides(), flatten() of the ragged env_ids layout, and the reference update() on the
+    ragged buffer (per-env padded GAE, katago_ppo.py:649-773) — metrics and a parameter checksum."""
+    from keisei.training.katago_ppo import KataGoPPOAlgorithm, KataGoPPOParams, KataGoRolloutBuffer
+    from keisei.training.model_registry import build_model
+
+    out = {}
+    T, N, A = 5, 4, 11259
+    for name, ragged in (("grid", False), ("ragged", True)):
+        steps = _buffer_steps(21 if not ragged else 22, T, N, ragged)
+        buf = KataGoRolloutBuffer(N, (50, 9, 9), A)
+        for st in steps:
+            buf.add(st["obs"], st["actions"], st["logp"], st["values"], st["rewards"], st["dones"], st["term"], st["mask"],
+                    st["cats"], st["score_t"], env_ids=st["ids"] if ragged else None, next_value_override=st["ov"])
+        buf.fill_alternating_perspective_overrides()
+        flat = buf.flatten()
+        for k, v in flat.items():
+            if k in ("observations", "legal_masks"):
+                # content is checked through a checksum (the raw tensors are regenerated from the seed by the test)
+                out[f"{name}/{k}_sum"] = np.array(v.double().sum().item() if v.dtype != torch.bool else int(v.sum().item()))
+            else:
+                out[f"{name}/{k}"] = _np(v)
+        out[f"{name}/size"] = np.array(buf.size)
+    # the reference update() on the ragged buffer
+    steps = _buffer_steps(22, T, N, True)
+    torch.manual_seed(0)
+    model = build_model("se_resnet", dict(TINY))
+    for k, v in model.state_dict().items():
+        out["sd/" + k] = _np(v).copy()   # a copy: update() below changes the parameters in place
+    buf = KataGoRolloutBuffer(N, (50, 9, 9), A)
+    for st in steps:
+        buf.add(st["obs"], st["actions"], st["logp"], st["values"], st["rewards"], st["dones"], st["term"], st["mask"],
+                st["cats"], st["score_t"], env_ids=st["ids"], next_value_override=st["ov"])
+    total = sum(st["ids"].numel() for st in steps)
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(batch_size=total, epochs_per_batch=1, learning_rate=1e-3), model)
+    nv = torch.linspace(-0.5, 0.5, N)
+    torch.manual_seed(5)
+    metrics = algo.update(buf, nv)
+    out["update/next_values"] = _np(nv)
+    for k, v in metrics.items():
+        out["update/metric/" + k] = np.array(v)
+    for k, v in model.state_dict().items():
+        if v.is_floating_point():
+            out["update/after/" + k] = _np(v)
+    np.savez_compressed(OUT / "buffer.npz", **out)
+    print("buffer.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB raw")
+
+
 if __name__ == "__main__":
     if not REF.exists():
         sys.exit("needs /root/reference (build container only)")
@@ -281,3 +353,4 @@ if __name__ == "__main__":
     golden_model()
     golden_update()
     golden_resnet()
+    golden_buffer()

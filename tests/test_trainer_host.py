@@ -175,3 +175,58 @@ def test_select_actions_many_and_device_kwarg_on_cpu():
     model.convert_sync_batchnorm(FakeSync())
     out = model(torch.randn(2, 50, 9, 9))
     assert out.policy_logits.shape == (2, 9, 9, 139)
+
+
+def _fill_from_steps(buf, steps, ragged):
+    for st in steps:
+        buf.add(st["obs"], st["actions"], st["logp"], st["values"], st["rewards"], st["dones"], st["term"], st["mask"],
+                st["cats"], st["score_t"], env_ids=st["ids"] if ragged else None, next_value_override=st["ov"])
+
+
+@pytest.mark.parametrize("layout", ["grid", "ragged"])
+def test_buffer_flatten_matches_reference_buffer_golden(layout):
+    """KataGoRolloutBuffer against the REAL reference buffer (tests/golden/buffer.npz, oracle/make_golden.py:golden_buffer):
+    the (T, N) grid layout after fill_alternating_perspective_overrides() and the ragged split-merge env_ids layout."""
+    from oracle.make_golden import _buffer_steps
+    g = load_golden("buffer.npz")
+    ragged = layout == "ragged"
+    steps = _buffer_steps(22 if ragged else 21, 5, 4, ragged)
+    buf = KataGoRolloutBuffer(4, (50, 9, 9), 11259)
+    _fill_from_steps(buf, steps, ragged)
+    buf.fill_alternating_perspective_overrides()
+    flat = buf.flatten()
+    assert buf.size == int(g[f"{layout}/size"])
+    want_keys = {k.split("/", 1)[1] for k in g if k.startswith(layout + "/")} - {"size"}
+    assert {k if k not in ("observations", "legal_masks") else k + "_sum" for k in flat} == want_keys
+    for k, v in flat.items():
+        if k == "observations":
+            assert abs(v.double().sum().item() - float(g[f"{layout}/observations_sum"])) < 1e-6
+        elif k == "legal_masks":
+            assert int(v.sum().item()) == int(g[f"{layout}/legal_masks_sum"])
+        else:
+            want = g[f"{layout}/{k}"]
+            assert v.numpy().dtype == want.dtype and v.shape == want.shape, k
+            np.testing.assert_array_equal(v.numpy(), want, err_msg=k)   # NaN == NaN position-wise
+
+
+def test_update_on_ragged_env_ids_buffer_matches_reference_golden():
+    """update() through the per-env padded GAE path (reference katago_ppo.py:649-773) on the ragged buffer: metrics and
+    every parameter after the Adam step against the reference's own run."""
+    from oracle.make_golden import _buffer_steps
+    g = load_golden("buffer.npz")
+    steps = _buffer_steps(22, 5, 4, True)
+    model = build_model("se_resnet", dict(TINY))
+    model.load_state_dict({k[3:]: torch.from_numpy(np.array(v)) for k, v in g.items() if k.startswith("sd/")}, strict=True)
+    buf = KataGoRolloutBuffer(4, (50, 9, 9), 11259)
+    _fill_from_steps(buf, steps, True)
+    total = sum(st["ids"].numel() for st in steps)
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(batch_size=total, epochs_per_batch=1, learning_rate=1e-3), model)
+    torch.manual_seed(5)
+    metrics = algo.update(buf, torch.from_numpy(g["update/next_values"]))
+    for k in ("policy_loss", "value_loss", "score_loss", "entropy", "gradient_norm"):
+        want = float(g["update/metric/" + k])
+        assert abs(metrics[k] - want) <= 2e-4 * max(1.0, abs(want)), (k, metrics[k], want)
+    for name, v in model.state_dict().items():
+        if v.is_floating_point():
+            want = g["update/after/" + name]
+            assert np.abs(v.numpy() - want).max() <= 2e-4 * max(1e-2, np.abs(want).max()), name
