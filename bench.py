@@ -36,6 +36,8 @@ MODEL_CFG = dict(num_blocks=40, channels=256)           # reference SEResNetPara
 ROLLOUT_B = 4096                                        # BASELINE.json configs[1]
 UPDATE_GLOBAL_B = 8192                                  # BASELINE.json configs[2]
 A = 11259
+WORKLOAD = "SE-ResNet 40x256 rollout (select_actions), 4096 boards/GPU"
+CONV_TRAFFIC_BYTES = 306.0e6                            # ncu dram read+write per launch (profiles/, refreshed per round)
 CONV_FLOP_PER_POS = 2 * 81 * 256 * 2304                 # one 256->256 3x3 conv, SURVEY.md 8(d): 95.55 MFLOP
 FWD_FLOP_PER_POS = 18.66e6 + 80 * 95.55e6               # trunk convs only: 7.663 GFLOP
 
@@ -137,13 +139,18 @@ def timed(fn, steps: int, warmup: int, device, world: int) -> float:
     return float(ms.item())
 
 
-def cpu_baseline(batch: int = 256, reps: int = 6) -> dict:
+def _cpu_threads() -> int:
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    return torch.get_num_threads()
+
+
+def cpu_baseline(batch: int = 256, reps: int = 6, warmup: int = 1) -> dict:
     """Oracle port (fp32 CPU PyTorch restatement of the reference) on the host cores: rollout step
     (eval forward + mask/softmax/Categorical sample + log-prob + scalar value) on a bounded sample."""
     from oracle import keisei_oracle as O
     from keisei_b200.models import SEResNetModel, SEResNetParams
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = _cpu_threads()
     torch.manual_seed(0)
     sd = SEResNetModel(SEResNetParams(**MODEL_CFG)).state_dict()
     g = torch.Generator().manual_seed(1)
@@ -160,35 +167,91 @@ def cpu_baseline(batch: int = 256, reps: int = 6) -> dict:
             O.rollout_log_prob(flat, mask, a)
             O.scalar_value(v)
 
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": batch / dt, "unit": "positions/s", "cores": cores, "kind": "port",
+            "sample": f"oracle fp32 rollout step, 40x256, batch {batch}, {reps} reps"}
+
+
+def _oracle_train_step(cfg: dict, batch: int, seed: int):
+    """Closure running one KataGo-PPO minibatch forward + losses + backward of the oracle (fp32, CPU)."""
+    from oracle import keisei_oracle as O
+    from keisei_b200.models import SEResNetModel, SEResNetParams
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in SEResNetModel(SEResNetParams(**cfg)).state_dict().items()}
+    for t in sd.values():
+        if t.is_floating_point():
+            t.requires_grad_(True)
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randn(batch, 50, 9, 9, generator=g)
+    mask = torch.rand(batch, A, generator=g) < 0.01          # ~110 legal per row (SURVEY 8(d) config 1)
+    acts = torch.randint(0, A, (batch,), generator=g)
+    mask[torch.arange(batch), acts] = True
+    old, adv = -3 * torch.rand(batch, generator=g), torch.randn(batch, generator=g)
+    cats = torch.randint(-1, 3, (batch,), generator=g)
+    score_t = torch.randn(batch, generator=g).clamp(-1.5, 1.5)
+    nb = cfg["num_blocks"]
+
+    def step():
+        for t in sd.values():
+            t.grad = None
+        p, v, s = O.seresnet_forward(sd, obs, nb, training=True)
+        O.ppo_losses(p, v, s, mask, acts, old, adv, cats, score_t)["loss"].backward()
+    return step
+
+
+def cpu_config1(reps: int = 5) -> dict:
+    """BASELINE.json configs[0] — the mandatory CPU point: SE-ResNet 4x64 KataGo-PPO minibatch
+    fwd+bwd, batch 256, all host cores, fp32, median of `reps` after 1 warm-up (profile_hotpath.py:168-206 discipline)."""
+    cores = _cpu_threads()
+    step = _oracle_train_step(dict(num_blocks=4, channels=64), 256, 3)
+    step()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
+    med = sorted(ts)[len(ts) // 2]
+    return {"value": 256 / med, "unit": "samples/s", "cores": cores, "ms_per_step": med * 1e3, "kind": "port"}
+
+
+def cpu_update_baseline(batch: int = 32, reps: int = 2) -> dict:
+    """CPU baseline of configs[2]: oracle fwd + ppo_losses + backward of the 40x256 model on a bounded sample
+    (batch 32, per-sample throughput), all host cores."""
+    cores = _cpu_threads()
+    step = _oracle_train_step(MODEL_CFG, batch, 4)
     step()
     t0 = time.perf_counter()
     for _ in range(reps):
         step()
     dt = (time.perf_counter() - t0) / reps
-    return {"value": batch / dt, "unit": "positions/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle fp32 CPU forward+sample, SE-ResNet 40x256, batch {batch}, {reps} reps after 1 warm-up"}
+    return {"value": batch / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"oracle fp32 fwd+loss+bwd, 40x256, batch {batch}, {reps} reps"}
 
 
 def run_reference(args) -> None:
+    """The reference's CPU path (oracle port) for the same metric / config: every step is one rollout pass over a bounded
+    sample (batch 256 of the 4096 boards), exactly `--steps` timed steps after `--warmup` warm-ups."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     batch = 256
     t0 = time.perf_counter()
-    cb = cpu_baseline(batch=batch, reps=max(1, min(args.steps, 3)))
-    line = {"metric": "rollout positions/s", "value": cb["value"], "unit": "positions/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * batch / cb["value"], "higher_is_better": True, "scaling": "weak",
+    cb = cpu_baseline(batch=batch, reps=max(1, args.steps), warmup=max(1, args.warmup))
+    line = {"metric": "rollout positions/s", "value": cb["value"], "unit": "positions/s", "n_gpus": args.gpus, "steps": max(1, args.steps),
+            "warmup": max(1, args.warmup), "ms_per_step": 1000.0 * batch / cb["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "SE-ResNet 40x256 rollout inference (select_actions), batch 4096 synthetic boards per GPU",
-                       "timed_sample": f"batch {batch} on host cores, scaled per position"},
+            "config": {"workload": WORKLOAD, "timed_sample": f"batch {batch} per step on host cores, scaled per position"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+            "gpu_launches": 0, "wall_s": round(time.perf_counter() - t0, 1)}
     print(json.dumps(line), flush=True)
 
 
 def conv_roofline(device, reps: int = 20) -> dict:
-    """Dominant kernel: conv3x3_tc_kernel (256->256, B=4096, folded-BN+ReLU+gpool-bias epilogue),
-    timed back to back with CUDA events on the launching stream."""
+    """Dominant kernel: conv3x3_tc_kernel (256->256, B=4096, folded-BN+ReLU+gpool-bias epilogue), timed back to back
+    with CUDA events on the launching stream, alone — so the denominator is the measured BURST bf16 peak."""
     from keisei_b200 import model_ops
     pk = peaks()
     B, C = ROLLOUT_B, 256
@@ -209,13 +272,89 @@ def conv_roofline(device, reps: int = 20) -> dict:
     ms = e0.elapsed_time(e1) / reps
     flops = CONV_FLOP_PER_POS * B
     achieved = flops / (ms * 1e-3) / 1e12
-    peak = pk["bf16_tflops_sustained"]
-    return {"kernel": "conv3x3_tc_kernel (tcgen05, 256->256, B=4096, 3 boards x 128 ch tiles)", "bound": "tensor",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture in
-            # profiles/ncu_full_r1_rollout_kernels.csv (171-175 MB read + 131 MB written; algorithmic 2 x 169.9 MB)
-            "traffic": 306.0e6, "traffic_unit": "bytes/launch",
-            "ms_per_launch": ms, "flops_per_launch": flops, "peak_source": f"{pk['source']} bf16_tflops_sustained"}
+    peak = pk["bf16_tflops"]
+    return {"kernel": "conv3x3_tc_kernel 256->256 B=4096", "bound": "tensor", "achieved": round(achieved, 1), "peak": peak,
+            "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "frac_sustained": round(achieved / pk["bf16_tflops_sustained"], 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture under profiles/
+            "traffic": CONV_TRAFFIC_BYTES, "ms_per_launch": round(ms, 4), "peak_source": f"{pk['source']} burst"}
+
+
+def hbm_kernels(device) -> dict:
+    """Achieved fraction of the measured HBM copy peak for the bandwidth-bound kernels of the path, each timed alone
+    with CUDA events over alternating inputs larger than L2. Algorithmic bytes per unit: SURVEY.md 8(d)."""
+    from keisei_b200 import policy_ops
+    pk = peaks()["hbm_gbs"]
+    out = {}
+    g = torch.Generator(device=device).manual_seed(5)
+
+    def timeit(fn, reps=10):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(device)
+        return e0.elapsed_time(e1) / reps
+
+    def rows(B):
+        sets = []
+        for _ in range(2):
+            lg = torch.randn(B, 11264, device=device, generator=g).bfloat16()
+            mk = torch.rand(B, A, device=device, generator=g) < 0.007
+            ac = torch.randint(0, A, (B,), device=device, generator=g)
+            mk[torch.arange(B, device=device), ac] = True
+            sets.append((lg, mk, ac))
+        return sets
+    B = ROLLOUT_B
+    sets = rows(B)
+    vl = torch.randn(B, 3, device=device)
+    ms = timeit(lambda i: policy_ops.policy_sample(sets[i & 1][0][:, :A], sets[i & 1][1], vl))
+    bytes_row = A * 2 + policy_ops.mask_row_bytes(sets[0][1])
+    out["policy_sample"] = {"ms": round(ms, 4), "gbs": round(B * bytes_row / ms / 1e6, 1), "frac": round(B * bytes_row / ms / 1e6 / pk, 3)}
+    B = UPDATE_GLOBAL_B
+    sets = rows(B)
+    old, adv = -3 * torch.rand(B, device=device), torch.randn(B, device=device)
+    keep = {}
+
+    def fwd(i):
+        lg, mk, ac = sets[i & 1]
+        keep[i & 1] = policy_ops.ppo_policy_loss(lg[:, :A], mk, ac, old, adv, 0.2)
+    ms = timeit(fwd)
+    out["ppo_policy_fwd"] = {"ms": round(ms, 4), "gbs": round(B * bytes_row / ms / 1e6, 1), "frac": round(B * bytes_row / ms / 1e6 / pk, 3)}
+    g2 = torch.ones(2, device=device)
+
+    def bwd(i):
+        lg, mk, ac = sets[i & 1]
+        o = keep[i & 1]
+        policy_ops.ppo_policy_loss_backward(lg[:, :A], mk, ac, o[3], o[2], o[4], g2)
+    ms = timeit(bwd)
+    bwd_bytes = bytes_row + A * 2
+    out["ppo_policy_bwd"] = {"ms": round(ms, 4), "gbs": round(B * bwd_bytes / ms / 1e6, 1), "frac": round(B * bwd_bytes / ms / 1e6 / pk, 3)}
+    return out
+
+
+def eager_port_gpu(device, obs, mask) -> dict:
+    """Informational: the oracle port (plain PyTorch ops) on the SAME B200 under bf16 autocast — what PyTorch itself
+    dispatches (cuDNN convolutions) for the rollout step, timed like the product arm. Library kernels, not this repo's."""
+    from oracle import keisei_oracle as O
+    from keisei_b200.models import SEResNetModel, SEResNetParams
+    torch.manual_seed(0)
+    sd = {k: v.to(device) for k, v in SEResNetModel(SEResNetParams(**MODEL_CFG)).state_dict().items()}
+    B = obs.shape[0]
+
+    def step():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            p, v, s = O.seresnet_forward(sd, obs, MODEL_CFG["num_blocks"], training=False)
+            flat = p.reshape(B, -1)
+            probs = torch.softmax(flat.masked_fill(~mask, float("-inf")), -1)
+            a = torch.distributions.Categorical(probs, validate_args=False).sample()
+            O.rollout_log_prob(flat, mask, a)
+            O.scalar_value(v)
+    ms = timed(step, 5, 3, device, 1)
+    return {"value": B / (ms * 1e-3), "unit": "positions/s", "ms_per_step": ms, "what": "oracle port, torch eager + cuDNN, bf16 autocast, channels-first"}
 
 
 def run_ours(args) -> None:
@@ -236,19 +375,12 @@ def run_ours(args) -> None:
         for i in range(2):
             model(obs[i * 256:(i + 1) * 256])
     B = ROLLOUT_B
+    detail: dict = {}
 
     def step_device():
         algo.select_actions(obs, mask)
 
-    h_obs, h_mask = obs.cpu().pin_memory(), mask.cpu().pin_memory()
-    h_out = [torch.empty(B, dtype=torch.int64).pin_memory(), torch.empty(B).pin_memory(), torch.empty(B).pin_memory()]
-
-    def step_e2e():
-        d_obs = h_obs.to(device, non_blocking=True)
-        d_mask = h_mask.to(device, non_blocking=True)
-        a, lp, v = algo.select_actions(d_obs, d_mask)
-        h_out[0].copy_(a, non_blocking=True); h_out[1].copy_(lp, non_blocking=True); h_out[2].copy_(v, non_blocking=True)
-        torch.cuda.current_stream(device).synchronize()
+    ingest = RolloutIngest(algo, obs.cpu(), mask.cpu(), device)
 
     with ClockSampler(local) as clk:
         # kernels of this library launched in the timed region: direct launches (kb_launch_count) + the kernels inside
@@ -256,31 +388,57 @@ def run_ours(args) -> None:
         n0 = _lib.launch_count() + model.graph_replayed_kernels
         ms = timed(step_device, args.steps, args.warmup, device, world)
         launches = (_lib.launch_count() + model.graph_replayed_kernels - n0) * args.steps // (args.steps + args.warmup)
-    ms_e2e = timed(step_e2e, args.steps, args.warmup, device, world)
+    ms_e2e = timed(ingest.step, args.steps, args.warmup, device, world)
     value = world * B / (ms * 1e-3)
     e2e = world * B / (ms_e2e * 1e-3)
+    pk = peaks()
 
-    line = {"metric": "rollout positions/s", "value": value, "unit": "positions/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    line = {"metric": "rollout positions/s", "value": round(value, 1), "unit": "positions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "impl": "ours",
-            "config": {"workload": "SE-ResNet 40x256 rollout inference (select_actions), batch 4096 synthetic boards per GPU",
-                       "parallelism": f"shard{world}-no-comm", "cache": "inputs larger than L2 (170 MB activations per layer)"},
-            "e2e": {"value": e2e, "unit": "positions/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h_obs.numel() * 4 + h_mask.numel(), "d2h_bytes_per_step": B * 16},
+            "config": {"workload": WORKLOAD, "parallelism": f"shard{world}-no-comm", "cache": "inputs > L2 (170 MB/layer)"},
+            "e2e": {"value": round(e2e, 1), "unit": "positions/s", "ms_per_step": round(ms_e2e, 4),
+                    "h2d_bytes_per_step": ingest.h2d_bytes, "d2h_bytes_per_step": ingest.d2h_bytes},
             "gpu_launches": int(launches), "clocks": clk.summary(),
-            "model_frac_of_tensor_roofline": (FWD_FLOP_PER_POS * B / (ms * 1e-3) / 1e12) / peaks()["bf16_tflops_sustained"]}
+            "model_frac": round((FWD_FLOP_PER_POS * B / (ms * 1e-3) / 1e12) / pk["bf16_tflops_sustained"], 4)}
 
+    upd = None
     if not args.no_update:
-        line["update"] = bench_update(args, algo, model, device, rank, world)
-    if not args.no_extra:
-        line["league_rollout"] = bench_league(algo, device, rank, world)
+        upd, upd_detail = bench_update(args, algo, model, device, rank, world)
+        detail["update"] = upd_detail
+    if args.extra:
+        detail["league_rollout"] = bench_league(algo, device, rank, world)
         algo.optimizer.zero_grad(set_to_none=True)
         torch.cuda.empty_cache()
-        line["resnet_update"] = bench_resnet_update(args, device, rank, world)
+        detail["resnet_update"] = bench_resnet_update(args, device, rank, world)
     if rank == 0:
         line["roofline"] = conv_roofline(device)
+        hk = hbm_kernels(device)
+        detail["hbm_kernels"] = hk
+        line["hbm_frac"] = {k: v["frac"] for k, v in hk.items()}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
+            c1 = cpu_config1()
+            detail["cpu_config1"] = c1
+            line["cpu_config1"] = {"value": round(c1["value"], 1), "unit": "samples/s", "cores": c1["cores"],
+                                   "what": "4x64 b256 PPO fwd+bwd fp32"}
+            line["cpu_baseline"]["value"] = round(line["cpu_baseline"]["value"], 2)
+            if upd is not None:
+                cu = cpu_update_baseline()
+                detail["update_cpu_baseline"] = cu
+                upd["cpu"] = {"value": round(cu["value"], 2), "cores": cu["cores"], "kind": "port", "sample": "40x256 b32 fwd+loss+bwd"}
+            if args.extra:
+                try:
+                    detail["gpu_eager_port"] = eager_port_gpu(device, obs, mask)
+                    line["eager_port"] = round(detail["gpu_eager_port"]["value"], 1)
+                except Exception as e:  # noqa: BLE001  (informational leg only)
+                    detail["gpu_eager_port"] = {"error": repr(e)[:200]}
+        if upd is not None:
+            line["update"] = upd       # LAST key: the driver keeps the tail of the line
+        print("BENCH_DETAIL " + json.dumps(detail), file=sys.stderr, flush=True)
+        if args.detail_file:
+            Path(args.detail_file).parent.mkdir(parents=True, exist_ok=True)
+            Path(args.detail_file).write_text(json.dumps({"line": line, "detail": detail}, indent=1))
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -288,12 +446,28 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
-def bench_update(args, algo, model, device, rank, world) -> dict:
-    """KataGo-PPO update step (BASELINE.json configs[2]): 8192 samples / world per rank; one step =
-    forward (batch-stat BN) + fused losses + backward + gradient all-reduce + unscale/clip/Adam."""
-    from keisei_b200.distributed import BatchNormSync, GradSync
-    Bu = UPDATE_GLOBAL_B // world
-    g = torch.Generator().manual_seed(7 + rank)
+class RolloutIngest:
+    """End-to-end rollout step from HOST buffers through the public `select_actions` call: pinned host observations +
+    legal masks -> device (H2D inside the timed region), action selection, D2H of actions / log-probs / values."""
+
+    def __init__(self, algo, obs_cpu, mask_cpu, device) -> None:
+        self.algo, self.device = algo, device
+        self.h_obs, self.h_mask = obs_cpu.pin_memory(), mask_cpu.pin_memory()
+        n = obs_cpu.shape[0]
+        self.h_out = [torch.empty(n, dtype=torch.int64).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n).pin_memory()]
+        self.h2d_bytes = self.h_obs.numel() * 4 + self.h_mask.numel()
+        self.d2h_bytes = n * 16
+
+    def step(self) -> None:
+        d_obs = self.h_obs.to(self.device, non_blocking=True)
+        d_mask = self.h_mask.to(self.device, non_blocking=True)
+        a, lp, v = self.algo.select_actions(d_obs, d_mask)
+        self.h_out[0].copy_(a, non_blocking=True); self.h_out[1].copy_(lp, non_blocking=True); self.h_out[2].copy_(v, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+
+
+def _update_batch(Bu: int, seed: int, device):
+    g = torch.Generator().manual_seed(seed)
     obs = torch.randn(Bu, 50, 9, 9, generator=g).to(device)
     mask = torch.zeros(Bu, A, dtype=torch.bool)
     actions = torch.randint(0, A, (Bu,), generator=g)
@@ -301,6 +475,17 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
     mask[torch.arange(Bu), actions] = True
     mb = (mask.to(device), actions.to(device), (-3 * torch.rand(Bu, generator=g)).to(device), torch.randn(Bu, generator=g).to(device),
           torch.randint(-1, 3, (Bu,), generator=g).to(device), torch.randn(Bu, generator=g).clamp(-1.5, 1.5).to(device))
+    return obs, mb
+
+
+def bench_update(args, algo, model, device, rank, world) -> tuple[dict, dict]:
+    """KataGo-PPO update step (BASELINE.json configs[2]): 8192 samples / world per rank; one step =
+    forward (batch-stat BN) + fused losses + backward + gradient all-reduce + unscale/clip/Adam.
+    Returns (compact dict for the JSON line, detail dict)."""
+    import torch.distributed as dist
+    from keisei_b200.distributed import BatchNormSync, GradSync
+    Bu = UPDATE_GLOBAL_B // world
+    obs, mb = _update_batch(Bu, 7 + rank, device)
     if world > 1:
         algo.grad_sync = GradSync()
         algo.grad_sync.broadcast_parameters(model)
@@ -311,19 +496,28 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
         algo._step_fused(km, obs, mb, None)
         algo._optimizer_tail()
 
-    steps, warm = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
-    ms_local_bn = ms_nccl_bn = None
+    steps, warm = max(2, args.steps), max(3, args.warmup)
+    detail: dict = {"steps": steps, "warmup": warm, "global_batch": UPDATE_GLOBAL_B, "per_gpu_batch": Bu}
+    ms_local_bn = ms_nccl_bn = ms_no_ar = allreduce_ms = None
     peer = None
-    bn_kind = "local (1 rank)"
+    bn_kind = "local"
     if world > 1:
         # per-rank BatchNorm statistics first (plain DDP), then the reference's default: SyncBatchNorm
         # (katago_loop.py:494-497, sync_batchnorm = true) — the headline number for N > 1. The statistic exchange is
         # timed both ways: NCCL all-reduce per layer, and this library's one-kernel exchange over NVLink peer memory.
         from keisei_b200.distributed import PeerBatchNormSync
+        gs = algo.grad_sync
+        algo.grad_sync = None
+        ms_no_ar = timed(step, steps, warm, device, world)          # no gradient exchange at all (weights diverge: timing only)
+        algo.grad_sync = gs
+        gs.broadcast_parameters(model)
         ms_local_bn = timed(step, steps, warm, device, world)
+        flat = torch.zeros(sum(p.numel() for p in model.parameters()), device=device)
+        allreduce_ms = timed(lambda: dist.all_reduce(flat), 10, 3, device, world)   # the 213.7 MB flat gradient, alone
+        del flat
         model.convert_sync_batchnorm(BatchNormSync())
         ms_nccl_bn = timed(step, steps, warm, device, world)
-        bn_kind = "SyncBatchNorm (reference default under DDP), NCCL all-reduce per layer"
+        bn_kind = "syncbn-nccl"
         try:
             peer = PeerBatchNormSync()
             ok = torch.ones(1, device=device)
@@ -331,39 +525,57 @@ def bench_update(args, algo, model, device, rank, world) -> dict:
             peer, ok = None, torch.zeros(1, device=device)
             if rank == 0:
                 print(f"PeerBatchNormSync unavailable ({e}); SyncBatchNorm stays on NCCL", file=sys.stderr)
-        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         peer_everywhere = float(ok.item()) > 0
         if not peer_everywhere and peer is not None:
             peer.close(collective=False)   # some other rank could not map the buffers: nobody will use them
             peer = None
         if peer_everywhere:
             model.convert_sync_batchnorm(peer)
-            bn_kind = "SyncBatchNorm (reference default under DDP), one-kernel exchange over NVLink peer memory"
-        else:
-            ms_nccl_bn = None
+            bn_kind = "syncbn-peer"
     ms = timed(step, steps, warm, device, world)
     model.convert_sync_batchnorm(None)
     if world > 1 and peer is not None:
         torch.cuda.synchronize(device)
         peer.close()   # collective: unmap everywhere, barrier, then free
+    # batch-independent cost of a step (launch latency, small GEMMs, optimiser, re-pack): the same step on 24 boards
+    obs_s, mb_s = _update_batch(24, 99 + rank, device)
+    gs, algo.grad_sync = algo.grad_sync, None
+
+    def small_step():
+        algo._step_fused(km, obs_s, mb_s, None)
+        algo._optimizer_tail()
+    fixed_ms = timed(small_step, 5, 3, device, world)
+    algo.grad_sync = gs
     # GAE over the reference-shaped buffer T=128 x N=64 (+ normalisation)
     from keisei_b200 import gae as G
     T, N = 128, 64
     r, v = torch.randn(T, N, device=device), 0.3 * torch.randn(T, N, device=device)
     term = torch.rand(T, N, device=device) < 0.02
     nv = torch.randn(N, device=device)
+
     def gae_step():
         adv = G.compute_gae_gpu(r, v, term, nv, 0.99, 0.95).reshape(-1)
         G.normalize_advantages_(adv)
     gae_ms = timed(gae_step, 20, 3, device, world)
     sps = UPDATE_GLOBAL_B / (ms * 1e-3)
-    e2e = update_e2e(algo, device, rank, world) if world == 1 else None
-    e2e_dev = update_e2e(algo, device, rank, world, device_buffer=True) if world == 1 else None
-    return {"metric": "PPO update samples/s", "e2e": e2e, "e2e_device_buffer": e2e_dev, "value": sps, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "warmup": warm,
-            "global_batch": UPDATE_GLOBAL_B, "per_gpu_batch": Bu, "scaling": "strong", "gae_T128_N64_ms": gae_ms,
-            "frac_of_tensor_roofline": (22.97e9 * UPDATE_GLOBAL_B / world / (ms * 1e-3) / 1e12) / peaks()["bf16_tflops_sustained"],
-            "includes": "fwd+losses+bwd+allreduce+unscale+clip+Adam",
-            "batchnorm": bn_kind, "ms_per_step_local_batchnorm": ms_local_bn, "ms_per_step_nccl_syncbn": ms_nccl_bn}
+    frac = (22.97e9 * UPDATE_GLOBAL_B / world / (ms * 1e-3) / 1e12) / peaks()["bf16_tflops_sustained"]
+    compact = {"metric": "PPO update samples/s", "value": round(sps, 1), "unit": "samples/s", "ms_per_step": round(ms, 3),
+               "global_batch": UPDATE_GLOBAL_B, "scaling": "strong", "frac": round(frac, 4), "bn": bn_kind,
+               "fixed_ms": round(fixed_ms, 3), "gae_ms": round(gae_ms, 4)}
+    if world > 1:
+        compact.update({"allreduce_ms": round(allreduce_ms, 3), "allreduce_exposed_ms": round(ms_local_bn - ms_no_ar, 3),
+                        "syncbn_ms": round(ms - ms_local_bn, 3), "ms_local_bn": round(ms_local_bn, 3), "ms_nccl_bn": None if ms_nccl_bn is None else round(ms_nccl_bn, 3)})
+    if world == 1:
+        e2e = update_e2e(algo, device, rank, world)
+        e2e_dev = update_e2e(algo, device, rank, world, device_buffer=True)
+        ref_sched = update_e2e(algo, device, rank, world, device_buffer=True, batch_size=256, epochs=4)
+        detail.update({"e2e": e2e, "e2e_device_buffer": e2e_dev, "reference_schedule_256x32x4": ref_sched})
+        compact.update({"e2e": round(e2e["value"], 1), "e2e_devbuf": round(e2e_dev["value"], 1),
+                        "ref_sched_256x32x4": round(ref_sched["value"], 1)})
+    detail.update({"includes": "fwd+losses+bwd+allreduce+unscale+clip+Adam", "batchnorm": bn_kind, "ms_no_allreduce": ms_no_ar,
+                   "ms_local_bn": ms_local_bn, "ms_nccl_syncbn": ms_nccl_bn, "allreduce_alone_ms": allreduce_ms, "fixed_ms_b24": fixed_ms})
+    return compact, detail
 
 
 def bench_resnet_update(args, device, rank, world) -> dict:
@@ -442,7 +654,7 @@ def bench_league(algo, device, rank, world) -> dict:
                               "grouped": "select_actions_many: the five sub-batches as parallel branches of one CUDA graph"}}
 
 
-def update_e2e(algo, device, rank, world, device_buffer: bool = False) -> dict:
+def update_e2e(algo, device, rank, world, device_buffer: bool = False, batch_size: int | None = None, epochs: int = 1) -> dict:
     """The public call a user makes: KataGoPPOAlgorithm.update(buffer, next_values) on a host-resident
     KataGoRolloutBuffer of T=128 x N=64 = 8192 samples (the reference's profiled update shape,
     scripts/profile_hotpath.py:411-455), one epoch, one minibatch of 8192: buffer flatten, H2D of
@@ -463,10 +675,10 @@ def update_e2e(algo, device, rank, world, device_buffer: bool = False) -> dict:
         steps.append((obs, actions, -3 * torch.rand(N, generator=g), 0.3 * torch.randn(N, generator=g), term.float(), term, term, mask,
                       torch.where(term, torch.randint(0, 3, (N,), generator=g), torch.full((N,), -1)), torch.randn(N, generator=g).clamp(-1.5, 1.5)))
     old_params = algo.params
-    algo.params = dataclasses.replace(old_params, batch_size=T * N, epochs_per_batch=1)
+    algo.params = dataclasses.replace(old_params, batch_size=batch_size or T * N, epochs_per_batch=epochs)
     nv = torch.randn(N, generator=g).to(device)
     times = []
-    for rep in range(3):
+    for rep in range(3 if epochs == 1 else 2):
         for st in steps:
             buf.add(*st)
         torch.cuda.synchronize(device)
@@ -476,6 +688,11 @@ def update_e2e(algo, device, rank, world, device_buffer: bool = False) -> dict:
         times.append(time.perf_counter() - t0)
     algo.params = old_params
     best = min(times[1:])
+    if epochs != 1 or batch_size is not None:
+        n_steps = epochs * ((T * N + (batch_size or T * N) - 1) // (batch_size or T * N))
+        return {"value": epochs * T * N / best, "unit": "samples/s", "ms_per_update": best * 1e3, "optimizer_steps": n_steps,
+                "ms_per_minibatch": best * 1e3 / n_steps, "note": f"update() with batch_size={batch_size}, {epochs} epochs over 8192 samples "
+                "(the reference's profiled schedule, profile_hotpath.py:411-455), device buffer, wall clock"}
     if device_buffer:
         return {"value": T * N / best, "unit": "samples/s", "ms_per_update": best * 1e3, "samples": T * N,
                 "h2d_bytes_per_update": 0, "d2h_bytes_per_update": 9 * 8,
@@ -494,7 +711,10 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-update", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the configs[3] (ResNet PPO) and configs[4] (league rollout) legs")
+    ap.add_argument("--extra", action="store_true", help="also run configs[3] (ResNet PPO), configs[4] (league rollout) and the "
+                    "informational torch-eager port on the GPU; results go to the detail record")
+    ap.add_argument("--no-extra", action="store_true", help="(default; kept for compatibility)")
+    ap.add_argument("--detail-file", default=None, help="also write the full detail record (JSON) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -131,12 +131,17 @@ typedef struct kb_peer_ctx {
   int rank, world, n_slots, reserved;
   long long slot_doubles;      /* capacity of one exchange (>= 2 * max channels) */
   unsigned long long seq;      /* exchanges done so far; advanced by kb_peer_allreduce_hook */
+  unsigned long long* status;  /* kb_peer_status_create word or NULL: set non-zero by an exchange that timed out waiting for a
+                                  peer (bits 0-47: seq+1 of the exchange, bits 48-63: 1 + the rank that never arrived) */
+  long long timeout_ms;        /* how long an exchange waits for the slowest rank; <= 0: 120 000 ms */
 } kb_peer_ctx;
 long long kb_peer_buffer_bytes(int world, int n_slots, long long slot_doubles);
 int kb_peer_buffer_create(long long bytes, void** ptr, unsigned char* handle64);   /* zero-filled; handle64: 64 bytes out */
 int kb_peer_buffer_open(const unsigned char* handle64, void** ptr);                /* map a peer's buffer */
 int kb_peer_buffer_close(void* ptr);
 int kb_peer_buffer_destroy(void* ptr);
+int kb_peer_status_create(unsigned long long** word);   /* pinned, device-mapped host word, zeroed */
+int kb_peer_status_destroy(unsigned long long* word);
 /* buf (n doubles, device) <- sum over ranks, in rank order (bit-identical on every rank), stream-ordered */
 int kb_peer_allreduce_f64(void* buf, long long n, const kb_peer_ctx* ctx, unsigned long long seq, kb_stream_t stream);
 /* a kb_allreduce_hook: user = kb_peer_ctx* */

@@ -91,8 +91,10 @@ __global__ void bn_finalize_kernel(double* sums, double count, const float* w, c
   invstd_o[c] = invstd;
   if (rm != nullptr) {
     const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-    rm_out[c] = (1.f - momentum) * rm[c] + momentum * (float)mean;
-    rv_out[c] = (1.f - momentum) * rv[c] + momentum * (float)unb;
+    // a failed SyncBatchNorm exchange (lost peer: the sums come back NaN) must not be committed to the running statistics
+    const bool ok = isfinite(mean) && isfinite(unb);
+    rm_out[c] = ok ? (1.f - momentum) * rm[c] + momentum * (float)mean : rm[c];
+    rv_out[c] = ok ? (1.f - momentum) * rv[c] + momentum * (float)unb : rv[c];
   }
 }
 

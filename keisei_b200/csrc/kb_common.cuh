@@ -141,7 +141,8 @@ __device__ __forceinline__ kb_philox4 kb_philox4x32_10(uint64_t seed, uint64_t c
   kb_philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
   return o;
 }
-// uniform in the open interval (0,1)
-__device__ __forceinline__ float kb_u32_to_unit(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// uniform in the OPEN interval (0,1): 23 random bits + 0.5 — the largest value, (2^23 - 0.5) / 2^23 = 0.99999994, is
+// representable in fp32 (with 24 bits the top value rounds to exactly 1.0 and -log(-log(u)) becomes +inf)
+__device__ __forceinline__ float kb_u32_to_unit(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
 #endif  // __CUDACC__

@@ -9,8 +9,11 @@
 // and an exchange is one CTA on the caller's stream:
 //   1. store this rank's n doubles into slot (seq % n_slots), row `rank`, of EVERY rank's buffer (NVLink P2P stores);
 //   2. fence.sys, then release-store seq+1 into flags[slot][rank] of every rank's buffer;
-//   3. acquire-spin on the `world` flags of the LOCAL buffer until all read >= seq+1 (bounded: a lost peer poisons the
-//      result with NaN instead of hanging the GPU);
+//   3. acquire-spin on the `world` flags of the LOCAL buffer until all read >= seq+1. The wait is bounded in TIME
+//      (ctx->timeout_ms, default 120 s — rank skew of many seconds is normal: checkpointing, evaluation, first-call
+//      builds): a lost peer then poisons the result with NaN instead of hanging the GPU AND raises the host-visible
+//      status word (ctx->status, pinned mapped host memory) so the trainer reports "peer rank lost" instead of
+//      training on NaN; the BatchNorm finalize kernel does not commit non-finite statistics to the running buffers;
 //   4. sum the `world` rows of the local slot in rank order — every rank adds the same numbers in the same order, so
 //      the statistics are bit-identical across ranks — and write the result over the input.
 // A rank can be at most one exchange ahead of the slowest (it needs that rank's flag to finish the next one), so
@@ -34,8 +37,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* buf, int n, PeerPtrs pp, int rank, int world,
-                                                                unsigned long long seq, int n_slots, long long slot_doubles) {
+                                                                unsigned long long seq, int n_slots, long long slot_doubles,
+                                                                unsigned long long timeout_ns, unsigned long long* status) {
   __shared__ int timed_out;
   const int slot = (int)(seq % (unsigned long long)n_slots);
   const size_t row = ((size_t)slot * world + rank) * (size_t)slot_doubles;
@@ -52,10 +62,18 @@ __global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* buf, in
   // 3. wait for every rank's contribution to land HERE
   if (threadIdx.x < world) {
     const unsigned long long* f = pp.flags[rank] + (size_t)slot * world + threadIdx.x;
-    long long spins = 0;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
     while (ld_acquire_sys(f) < seq + 1ull) {
       __nanosleep(64);
-      if (++spins > (1ll << 26)) { timed_out = 1; break; }   // ~ several seconds: a peer is gone
+      if ((++spins & 0x3ffu) == 0 && global_timer_ns() - t0 > timeout_ns) {   // a peer is gone
+        timed_out = 1;
+        if (status != nullptr) {   // first failure wins; the host reads this word (mapped pinned memory) once per step
+          atomicCAS_system(status, 0ull, ((unsigned long long)(threadIdx.x + 1) << 48) | ((seq + 1ull) & 0xffffffffffffull));
+          __threadfence_system();
+        }
+        break;
+      }
     }
   }
   __syncthreads();
@@ -111,6 +129,22 @@ extern "C" int kb_peer_buffer_destroy(void* ptr) {
   return KB_OK;
 }
 
+// Host-visible failure word of the exchange kernels: pinned, device-mapped host memory (the kernel writes it with a
+// system-scope atomic on timeout; the host reads it without a copy). 0 = no failure.
+extern "C" int kb_peer_status_create(unsigned long long** word) {
+  KB_CHECK_ARG(word != nullptr, "kb_peer_status_create: null pointer");
+  void* p = nullptr;
+  KB_CUDA_CHECK(cudaHostAlloc(&p, sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
+  *(volatile unsigned long long*)p = 0ull;
+  *word = (unsigned long long*)p;
+  return KB_OK;
+}
+
+extern "C" int kb_peer_status_destroy(unsigned long long* word) {
+  if (word) KB_CUDA_CHECK(cudaFreeHost(word));
+  return KB_OK;
+}
+
 extern "C" int kb_peer_allreduce_f64(void* buf, long long n, const kb_peer_ctx* ctx, unsigned long long seq, kb_stream_t stream) {
   KB_CHECK_ARG(buf && ctx, "kb_peer_allreduce_f64: null pointer");
   KB_CHECK_ARG(ctx->world >= 1 && ctx->world <= kMaxWorld && ctx->rank >= 0 && ctx->rank < ctx->world && ctx->n_slots >= 2,
@@ -124,8 +158,9 @@ extern "C" int kb_peer_allreduce_f64(void* buf, long long n, const kb_peer_ctx* 
     pp.data[r] = (double*)ctx->peers[r];
     pp.flags[r] = (unsigned long long*)((double*)ctx->peers[r] + data_doubles);
   }
+  const unsigned long long timeout_ns = (unsigned long long)(ctx->timeout_ms > 0 ? ctx->timeout_ms : 120000) * 1000000ull;
   peer_allreduce_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((double*)buf, (int)n, pp, ctx->rank, ctx->world, seq, ctx->n_slots,
-                                                                ctx->slot_doubles);
+                                                                ctx->slot_doubles, timeout_ns, ctx->status);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

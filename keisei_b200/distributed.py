@@ -1,5 +1,5 @@
-"""Data-parallel plumbing — mirror of keisei/training/distributed.py:39-157 plus the gradient
-exchange that replaces the reference's DistributedDataParallel wrap (katago_loop.py:494-508).
+"""Data-parallel plumbing: the gradient exchange and the SyncBatchNorm statistic exchange that replace the reference's
+DistributedDataParallel + SyncBatchNorm wrap (katago_loop.py:494-508).
 
 One process per GPU (torchrun env: RANK / LOCAL_RANK / WORLD_SIZE), NCCL over NVLink 5 / NVSwitch
 for CUDA, gloo for CPU tests. The PPO update's only exchange step is the gradient average: the
@@ -14,89 +14,62 @@ from __future__ import annotations
 import ctypes
 import logging
 import os
-import random
-from dataclasses import dataclass, field
-from typing import Iterable
+from typing import Iterable, NamedTuple
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
 logger = logging.getLogger(__name__)
 
 
-def _resolve_device(is_distributed: bool, local_rank: int) -> torch.device:
-    if is_distributed and torch.cuda.is_available():
-        return torch.device(f"cuda:{local_rank}")
-    if torch.cuda.is_available():
-        return torch.device("cuda")
-    return torch.device("cpu")
+# The process-group bootstrap (torchrun env discovery, init / destroy, per-rank seeding) is NOT part of the hot path:
+# under the reference's loop its own `keisei.training.distributed` keeps doing that job (katago_loop.py:1962-1985) and
+# this package only plugs GradSync / BatchNormSync into the trainer. The names are re-exported when the reference is
+# importable so `from keisei_b200.distributed import setup_distributed` keeps working in a drop-in install.
+try:  # pragma: no cover - depends on the environment
+    from keisei.training.distributed import (DistributedContext, cleanup_distributed, get_distributed_context,  # noqa: F401
+                                             seed_all_ranks, setup_distributed)
+except Exception:  # noqa: BLE001  (standalone use: bench.py, tests)
+    pass
 
 
-@dataclass(frozen=True, slots=True)
-class DistributedContext:
+class RankEnv(NamedTuple):
+    """What the launcher (torchrun) told this process. `launched` is False for a plain single process."""
     rank: int
     local_rank: int
     world_size: int
-    is_distributed: bool
-    device: torch.device = field(init=False)
-
-    def __post_init__(self) -> None:
-        object.__setattr__(self, "device", _resolve_device(self.is_distributed, self.local_rank))
-
-    @property
-    def is_main(self) -> bool:
-        return self.rank == 0
+    launched: bool
 
 
-def _require_env(key: str) -> str:
-    val = os.environ.get(key)
-    if val is None:
-        raise RuntimeError(f"torchrun env var {key!r} is missing. Ensure RANK, LOCAL_RANK, and WORLD_SIZE are all set. "
-                           f"Launch with: torchrun --nproc_per_node=N your_script.py")
-    return val
+def rank_env() -> RankEnv:
+    """Standalone launcher-env reader for bench.py / tests: RANK, LOCAL_RANK and WORLD_SIZE come as a set."""
+    have = {k: os.environ.get(k) for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    if have["RANK"] is None:
+        return RankEnv(0, 0, 1, False)
+    missing = [k for k, v in have.items() if v is None]
+    if missing:
+        raise RuntimeError(f"launcher environment incomplete: RANK is set but {missing} missing (use torchrun)")
+    return RankEnv(int(have["RANK"]), int(have["LOCAL_RANK"]), int(have["WORLD_SIZE"]), True)
 
 
-def get_distributed_context() -> DistributedContext:
-    rank = os.environ.get("RANK")
-    if rank is None:
-        return DistributedContext(rank=0, local_rank=0, world_size=1, is_distributed=False)
-    return DistributedContext(rank=int(rank), local_rank=int(_require_env("LOCAL_RANK")),
-                              world_size=int(_require_env("WORLD_SIZE")), is_distributed=True)
+def init_from_env(backend: str | None = None) -> RankEnv:
+    """One process per GPU: bind the local device and join the process group (NCCL on CUDA, gloo on CPU)."""
+    env = rank_env()
+    if env.launched and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        cuda = torch.cuda.is_available()
+        backend = backend or ("nccl" if cuda else "gloo")
+        if backend == "nccl":
+            torch.cuda.set_device(env.local_rank)
+            dist.init_process_group(backend, device_id=torch.device(f"cuda:{env.local_rank}"))
+        else:
+            dist.init_process_group(backend)
+    return env
 
 
-def setup_distributed(ctx: DistributedContext, backend: str | None = None) -> None:
-    if not ctx.is_distributed:
-        return
-    if backend is None:
-        backend = "nccl" if torch.cuda.is_available() else "gloo"
-    elif backend == "nccl" and not torch.cuda.is_available():
-        raise RuntimeError("backend='nccl' requires CUDA but torch.cuda.is_available() is False. "
-                           "Use backend='gloo' for CPU-only distributed training, or set backend=None to auto-select.")
-    try:
-        if torch.cuda.is_available():
-            torch.cuda.set_device(ctx.local_rank)
-        dist.init_process_group(backend=backend)
-        logger.info("DP initialized: rank=%d, local_rank=%d, world_size=%d, backend=%s", ctx.rank, ctx.local_rank,
-                    ctx.world_size, backend)
-    except Exception:
-        logger.error("DP init failed: rank=%d, local_rank=%d, world_size=%d, MASTER_ADDR=%s, MASTER_PORT=%s", ctx.rank,
-                     ctx.local_rank, ctx.world_size, os.environ.get("MASTER_ADDR", "<unset>"),
-                     os.environ.get("MASTER_PORT", "<unset>"))
-        raise
-
-
-def cleanup_distributed(ctx: DistributedContext) -> None:
-    if ctx.is_distributed and dist.is_initialized():
+def shutdown() -> None:
+    if dist.is_available() and dist.is_initialized():
         dist.destroy_process_group()
-
-
-def seed_all_ranks(seed: int) -> None:
-    torch.manual_seed(seed)
-    if torch.cuda.is_available():
-        torch.cuda.manual_seed(seed)
-    np.random.seed(seed)
-    random.seed(seed)
 
 
 class BatchNormSync:
@@ -119,11 +92,38 @@ class BatchNormSync:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
         return sums
 
+    def begin_update(self, n_samples: int, batch_size: int, device) -> None:
+        """Called by `KataGoPPOAlgorithm.update()` before the first minibatch (collective)."""
+        _check_equal_shards(self.group, self.world_size, n_samples, batch_size, device)
+
+    def check(self) -> None:
+        """NCCL reports a lost peer itself (watchdog / timeout): nothing to poll."""
+
 
 class KbPeerCtx(ctypes.Structure):
     """include/keisei_b200.h: kb_peer_ctx"""
     _fields_ = [("peers", ctypes.c_void_p * 16), ("rank", ctypes.c_int), ("world", ctypes.c_int), ("n_slots", ctypes.c_int),
-                ("reserved", ctypes.c_int), ("slot_doubles", ctypes.c_longlong), ("seq", ctypes.c_ulonglong)]
+                ("reserved", ctypes.c_int), ("slot_doubles", ctypes.c_longlong), ("seq", ctypes.c_ulonglong),
+                ("status", ctypes.POINTER(ctypes.c_ulonglong)), ("timeout_ms", ctypes.c_longlong)]
+
+
+class PeerLostError(RuntimeError):
+    """A SyncBatchNorm exchange gave up waiting for a peer rank (the step's statistics and gradients are NaN)."""
+
+
+def _check_equal_shards(group, world: int, n_samples: int, batch_size: int, device) -> None:
+    """SyncBatchNorm normalises with count = local_batch * world and every rank must make the same number of exchanges:
+    all ranks have to run the same minibatch size and the same number of minibatches (the reference's DDP +
+    SyncBatchNorm deadlocks or mis-normalises in the same situation). Checked once per update(), one tiny all-gather."""
+    if world <= 1:
+        return
+    mine = torch.tensor([int(n_samples), int(batch_size)], dtype=torch.int64, device=device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    seen = {tuple(int(v) for v in p.tolist()) for p in parts}
+    if len(seen) != 1:
+        raise RuntimeError(f"SyncBatchNorm needs equal shards on every rank: (samples, batch_size) per rank = "
+                           f"{[tuple(int(v) for v in p.tolist()) for p in parts]}")
 
 
 class PeerBatchNormSync:
@@ -135,8 +135,9 @@ class PeerBatchNormSync:
     `BatchNormSync` (NCCL) otherwise. Call `close()` on every rank when done (collective; garbage collection only
     unmaps and frees without the barrier if the process group is already gone)."""
 
-    def __init__(self, process_group=None, max_channels: int = 1024, n_slots: int = 4) -> None:
+    def __init__(self, process_group=None, max_channels: int = 1024, n_slots: int = 4, timeout_s: float | None = None) -> None:
         from . import _lib
+        self._status = None
         if not dist.is_initialized():
             raise RuntimeError("PeerBatchNormSync needs an initialised process group (setup_distributed)")
         self._lib = _lib
@@ -179,12 +180,14 @@ class PeerBatchNormSync:
                                + (f": {failure}" if failure is not None else ""))
         self.ctx.rank, self.ctx.world, self.ctx.n_slots, self.ctx.slot_doubles, self.ctx.seq = \
             self.rank, self.world_size, n_slots, slot, 0
+        self._arm_status(timeout_s)
         self.c_hook = ctypes.cast(lib.kb_peer_allreduce_hook, ctypes.c_void_p)
         self.c_user = ctypes.cast(ctypes.pointer(self.ctx), ctypes.c_void_p)
         dist.barrier(group=process_group)  # every rank has mapped every buffer before the first exchange
 
     @classmethod
-    def from_local_buffers(cls, ptrs: list[int], rank: int, slot_doubles: int, n_slots: int = 4) -> "PeerBatchNormSync":
+    def from_local_buffers(cls, ptrs: list[int], rank: int, slot_doubles: int, n_slots: int = 4,
+                           timeout_s: float | None = None) -> "PeerBatchNormSync":
         """Ranks emulated inside ONE process (tests): the 'peers' are plain device buffers of this process."""
         from . import _lib
         self = cls.__new__(cls)
@@ -194,9 +197,41 @@ class PeerBatchNormSync:
         for r, p in enumerate(ptrs):
             self.ctx.peers[r] = p
         self.ctx.rank, self.ctx.world, self.ctx.n_slots, self.ctx.slot_doubles, self.ctx.seq = rank, len(ptrs), n_slots, slot_doubles, 0
+        self._status = None
+        self._arm_status(timeout_s)
         self.c_hook = ctypes.cast(_lib.load().kb_peer_allreduce_hook, ctypes.c_void_p)
         self.c_user = ctypes.cast(ctypes.pointer(self.ctx), ctypes.c_void_p)
         return self
+
+    def _arm_status(self, timeout_s: float | None) -> None:
+        """Host-visible failure word (pinned mapped memory) + how long an exchange waits for the slowest rank. Ranks skew
+        by seconds in normal operation (checkpointing / evaluation on rank 0, uneven CPU rollouts, first-call builds), so
+        the default is two minutes (KB_PEER_TIMEOUT_S overrides)."""
+        if timeout_s is None:
+            timeout_s = float(os.environ.get("KB_PEER_TIMEOUT_S", "120"))
+        word = ctypes.POINTER(ctypes.c_ulonglong)()
+        self._lib.check(self._lib.load().kb_peer_status_create(ctypes.byref(word)), "kb_peer_status_create")
+        self._status = word
+        self.ctx.status = word
+        self.ctx.timeout_ms = max(1, int(timeout_s * 1000))
+
+    def begin_update(self, n_samples: int, batch_size: int, device) -> None:
+        """Called by `KataGoPPOAlgorithm.update()` before the first minibatch (collective): checks the equal-shard
+        assumption of the exchange and lines the ranks up on the host, so the first exchange of the update does not
+        start with whatever skew the rollout phase left."""
+        if self.group is None and not (dist.is_available() and dist.is_initialized()):
+            return   # thread-emulated ranks (tests)
+        _check_equal_shards(self.group, self.world_size, n_samples, batch_size, device)
+
+    def check(self) -> None:
+        """Raise `PeerLostError` if any exchange since the last check timed out. Reads one pinned host word; meaningful
+        after the stream has been synchronised (the trainer calls it right after its per-step host reads)."""
+        if self._status and self._status[0] != 0:
+            word = int(self._status[0])
+            self._status[0] = 0
+            raise PeerLostError(f"SyncBatchNorm exchange #{(word & 0xffffffffffff) - 1} on rank {self.rank} timed out waiting for rank "
+                                f"{(word >> 48) - 1} (after {self.ctx.timeout_ms / 1000:.0f} s): peer rank lost. The step's statistics were "
+                                f"poisoned with NaN and NOT committed to the BatchNorm running buffers.")
 
     @torch.no_grad()
     def all_reduce_(self, sums: torch.Tensor) -> torch.Tensor:
@@ -217,6 +252,10 @@ class PeerBatchNormSync:
         for p in self._opened:
             lib.kb_peer_buffer_close(p)
         self._opened = []
+        if getattr(self, "_status", None):
+            self.ctx.status = ctypes.POINTER(ctypes.c_ulonglong)()
+            lib.kb_peer_status_destroy(self._status)
+            self._status = None
         if self._own:
             if collective and getattr(self, "_collective", False) and dist.is_available() and dist.is_initialized():
                 try:
@@ -253,6 +292,9 @@ class GradSync:
         """Reference DDP ctor semantics: every rank starts from rank 0's parameters and buffers."""
         for t in list(module.parameters()) + list(module.buffers()):
             dist.broadcast(t.data, src=src, group=self.group)
+        for m in module.modules():   # writes through .data bypass the autograd version counters the weight cache keys on
+            if hasattr(m, "invalidate_packed_weights"):
+                m.invalidate_packed_weights()
 
     @torch.no_grad()
     def all_reduce_flat(self, flat: torch.Tensor) -> torch.Tensor:

@@ -14,6 +14,7 @@ compatibility and ignored (a warning is logged).
 from __future__ import annotations
 
 import logging
+import sys
 from dataclasses import dataclass
 from typing import Any, Callable
 
@@ -29,6 +30,20 @@ from .models.se_resnet import SEResNetModel
 SCORE_NORMALIZATION = 76.0  # reference keisei/sl/dataset.py:32
 
 _log = logging.getLogger(__name__)
+
+
+def _gae_fn(name: str):
+    """`compute_gae*` resolved by MODULE ATTRIBUTE at call time: the reference's `update()` does a local
+    `from keisei.training.gae import ...`, so its tests (tests/test_split_merge_gae_opt.py:336-372) and callers patch
+    `keisei.training.gae.<name>` and expect the trainer to see it. When that module is loaded and the attribute is NOT
+    the reference's own pristine function (a spy, or this package's kernel-backed function put there by
+    `install_into_reference()`), it wins; otherwise this package's `gae` module is used (also looked up per call)."""
+    ref = sys.modules.get("keisei.training.gae")
+    if ref is not None:
+        fn = getattr(ref, name, None)
+        if fn is not None and getattr(fn, "__module__", None) != "keisei.training.gae":
+            return fn
+    return getattr(gae_mod, name)
 
 
 def _amp_dtype_and_device(use_amp: bool, device: torch.device) -> tuple[torch.dtype, str]:
@@ -463,11 +478,11 @@ class KataGoPPOAlgorithm:
         if total == T * N:
             ov = data.get("next_value_override")
             tok = self._events(device, "gae_ms")
-            adv = gae_mod.compute_gae_gpu(
+            adv = _gae_fn("compute_gae_gpu")(
                 data["rewards"].reshape(T, N).float().to(device), data["values"].reshape(T, N).float().to(device),
                 data[key].reshape(T, N).to(device), nv.to(device), gamma=p.gamma, lam=p.gae_lambda,
                 next_value_override=None if ov is None else ov.reshape(T, N).float().to(device)) \
-                if device.type == "cuda" else gae_mod.compute_gae(
+                if device.type == "cuda" else _gae_fn("compute_gae")(
                     data["rewards"].reshape(T, N).float(), data["values"].reshape(T, N).float(), data[key].reshape(T, N),
                     nv.cpu(), gamma=p.gamma, lam=p.gae_lambda,
                     next_value_override=None if ov is None else ov.reshape(T, N).float())
@@ -496,14 +511,14 @@ class KataGoPPOAlgorithm:
             term_p = pad(data[key], 1.0)  # padding = terminated so nothing propagates through it
             ov_p = pad(data["next_value_override"], float("nan")) if "next_value_override" in data else None
             nv_cols = nv_cpu[uniq]
-            fn = gae_mod.compute_gae_padded_gpu if device.type == "cuda" else gae_mod.compute_gae_padded
+            fn = _gae_fn("compute_gae_padded_gpu") if device.type == "cuda" else _gae_fn("compute_gae_padded")
             mv = (lambda t: t.to(device)) if device.type == "cuda" else (lambda t: t)
             padded = fn(mv(rewards_p), mv(values_p), mv(term_p), mv(nv_cols), lengths, gamma=p.gamma, lam=p.gae_lambda,
                         next_value_override=None if ov_p is None else mv(ov_p))
             adv = torch.zeros(total, device=padded.device)
             adv[order.to(padded.device)] = padded[row.to(padded.device), col.to(padded.device)]
             return adv
-        adv = gae_mod.compute_gae(data["rewards"].float(), data["values"].float(), data[key], nv_cpu.mean(),
+        adv = _gae_fn("compute_gae")(data["rewards"].float(), data["values"].float(), data[key], nv_cpu.mean(),
                                   gamma=p.gamma, lam=p.gae_lambda)
         return adv.to(device)
 
@@ -571,6 +586,8 @@ class KataGoPPOAlgorithm:
         policy_buf.requires_grad_(True); value.requires_grad_(True); score.requires_grad_(True)
         loss, pl, vl, sl, ent, flags = self._losses(policy_buf[:, :model_ops.POLICY_A], value, score, mb, value_adapter)
         self._check_flags(flags)
+        if self.strict_guards and km.bn_sync is not None and hasattr(km.bn_sync, "check"):
+            km.bn_sync.check()   # after the host read above: a forward exchange that lost a peer raises here, not as NaN later
         self.optimizer.zero_grad(set_to_none=True)
         self.scaler.scale(loss).backward()
         with torch.no_grad():
@@ -597,6 +614,9 @@ class KataGoPPOAlgorithm:
         p = self.params
         flat = getattr(self, "_flat_grad", None)
         self._flat_grad = None
+        base = self._base()
+        if hasattr(base, "invalidate_packed_weights"):
+            base.invalidate_packed_weights()   # the fused optimiser does not bump Tensor._version: re-pack explicitly
         params = self.optimizer.param_groups[0]["params"] if len(self.optimizer.param_groups) == 1 else None
         usable = (flat is not None and params is not None and len(params) > 0 and params[0].grad is not None
                   and params[0].grad.data_ptr() == flat.data_ptr()
@@ -679,6 +699,11 @@ class KataGoPPOAlgorithm:
         batch_size = min(p.batch_size, total)
         amp_dtype, amp_dev = _amp_dtype_and_device(p.use_amp, device)
         km = self._kernel_model(device) if self.forward_model is self._base() else None
+        bn_sync = getattr(km, "bn_sync", None) if km is not None else None
+        if bn_sync is not None and hasattr(bn_sync, "begin_update"):
+            # SyncBatchNorm exchanges assume equal shards and the same number of minibatches on every rank (count =
+            # local batch x world): verified here, and the ranks are lined up before the first exchange
+            bn_sync.begin_update(total, batch_size, device)
         zero = lambda: torch.zeros((), device=device)  # noqa: E731
         acc = {k: zero() for k in ("policy_loss", "value_loss", "score_loss", "entropy", "gradient_norm")}
         n_updates = 0
@@ -707,6 +732,8 @@ class KataGoPPOAlgorithm:
         buffer.clear()
         denom = max(n_updates, 1)
         metrics = {k: (v / denom).item() for k, v in acc.items()}
+        if bn_sync is not None and hasattr(bn_sync, "check"):
+            bn_sync.check()   # the .item() reads above synchronised the stream: report a lost peer instead of NaN metrics
         if last_value_logits is not None and last_value_logits.shape[-1] == 3:
             valid = last_cats >= 0
             if valid.any():

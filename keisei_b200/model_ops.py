@@ -107,7 +107,7 @@ class _NativeHook:
         self.ptr, self.user = sync.c_hook, sync.c_user
 
     def check(self) -> None:
-        return None
+        return None   # the kernels are only enqueued here; a lost peer is reported by sync.check() after the step's host read
 
 
 def _sync_args(ws: torch.Tensor, sync):

@@ -70,16 +70,7 @@ def get_obs_channels(architecture: str) -> int:
 
 
 def install_into_reference() -> None:
-    """Drop-in: replace the `se_resnet` entry of an importable `keisei` with this implementation
-    (see INTEGRATION.md). The reference's params dataclass is kept so its isinstance checks hold."""
-    import keisei.training.model_registry as ref  # noqa: PLC0415 — optional dependency
-
-    old = ref._REGISTRY["se_resnet"]
-
-    class _Adapter(SEResNetModel):
-        def __init__(self, params):  # accepts the reference's SEResNetParams
-            super().__init__(SEResNetParams(**{f: getattr(params, f) for f in SEResNetParams.__dataclass_fields__}))
-            self.params = params
-
-    _Adapter.__name__ = "SEResNetModel"
-    ref._REGISTRY["se_resnet"] = ref.ArchitectureSpec(_Adapter, old.params_cls, old.contract, old.obs_channels)
+    """Drop-in: see `keisei_b200.dropin.install_into_reference` (registry entries, trainer, buffer and GAE functions of an
+    importable `keisei`; INTEGRATION.md)."""
+    from .dropin import install_into_reference as _install  # noqa: PLC0415
+    _install()

@@ -12,7 +12,8 @@ showcase sidecar and unit tests are CPU-only) run the same graph with plain PyTo
 from __future__ import annotations
 
 import os
-
+import threading
+from collections import OrderedDict
 from dataclasses import dataclass
 
 import torch
@@ -42,6 +43,81 @@ class SEResNetParams:
         if self.channels // self.se_reduction < 1:
             raise ValueError(
                 f"channels ({self.channels}) // se_reduction ({self.se_reduction}) must be >= 1")
+
+
+def rollout_bucket(batch: int) -> int:
+    """Graph-replayed rollout batches are padded up to a bucket so that the learner / opponent sub-batches of a
+    split-merge step — whose sizes change on almost every step (`obs[learner_mask]`, katago_loop.py:337-344) — hit a
+    handful of captured graphs instead of capturing a new one per size. Eval-mode boards are independent, so the padding
+    rows only cost their (launch-bound) share of compute and the outputs are sliced back."""
+    step = 8 if batch <= 64 else 32 if batch <= 512 else 128 if batch <= 2048 else 256
+    return (batch + step - 1) // step * step
+
+
+class _GraphCache:
+    """Captured rollout graphs of one model. Keys carry the calling THREAD (a tournament thread or DynamicTrainer using the
+    same model concurrently gets its own graphs and static output buffers, dynamic_trainer.py:44-50), the bucketed batch
+    size(s), dtype and device. LRU, bounded by bytes of static buffers and by entry count. A key is captured on its
+    SECOND sighting: a size that shows up once never pays a warm-up + capture + instantiate."""
+
+    def __init__(self, max_bytes: int, max_entries: int = 32) -> None:
+        self.max_bytes, self.max_entries = max_bytes, max_entries
+        self.entries: "OrderedDict[tuple, dict]" = OrderedDict()
+        self.sightings: dict = {}
+        self.bytes = 0
+        self.captures = self.hits = self.misses = 0
+        self.lock = threading.Lock()
+
+    def __len__(self) -> int:
+        return len(self.entries)
+
+    def clear(self) -> None:
+        with self.lock:
+            self.entries.clear(); self.sightings.clear(); self.bytes = 0
+
+    def lookup(self, key):
+        with self.lock:
+            ent = self.entries.get(key)
+            if ent is not None:
+                self.entries.move_to_end(key)
+                self.hits += 1
+            else:
+                self.misses += 1
+            return ent
+
+    def drop(self, key) -> None:
+        with self.lock:
+            ent = self.entries.pop(key, None)
+            if ent is not None:
+                self.bytes -= ent["nbytes"]
+
+    def should_capture(self, key) -> bool:
+        with self.lock:
+            n = self.sightings.get(key, 0) + 1
+            if len(self.sightings) > 4096:
+                self.sightings.clear()
+            self.sightings[key] = n
+            return n >= 2
+
+    def store(self, key, ent: dict) -> None:
+        with self.lock:
+            self.entries[key] = ent
+            self.bytes += ent["nbytes"]
+            self.captures += 1
+            while len(self.entries) > 1 and (self.bytes > self.max_bytes or len(self.entries) > self.max_entries):
+                _, old = self.entries.popitem(last=False)
+                self.bytes -= old["nbytes"]
+
+
+def _tensor_bytes(obj) -> int:
+    if isinstance(obj, torch.Tensor):
+        return obj.numel() * obj.element_size()
+    if isinstance(obj, (tuple, list)):
+        return sum(_tensor_bytes(o) for o in obj)
+    return 0
+
+
+_capture_lock = threading.Lock()   # stream capture is process-wide state: one capture at a time
 
 
 def _global_pool(x: torch.Tensor) -> torch.Tensor:
@@ -102,7 +178,9 @@ class SEResNetModel(KataGoBaseModel):
         self.last_policy_buffer: torch.Tensor | None = None  # padded (B, 11264) logits of the last CUDA forward
         self._tables_cache = None
         self._grad_sizes: list[int] = []
-        self._graphs: dict = {}              # (batch, dtype, device, use_tc) -> captured rollout forward
+        # captured rollout forwards: (thread, bucketed batch, dtype, device, use_tc) -> graph (see _GraphCache)
+        self._graphs = _GraphCache(int(float(os.environ.get("KB_GRAPH_CACHE_GB", "24")) * (1 << 30)))
+        self._group_graphs = _GraphCache(int(float(os.environ.get("KB_GRAPH_CACHE_GB", "24")) * (1 << 30)))
         # rollout batches up to this size replay a CUDA graph (0 disables); KB_GRAPH_MAX_BATCH overrides the default
         self.graph_max_batch: int = int(os.environ.get("KB_GRAPH_MAX_BATCH", "4096"))
         self.graph_replayed_kernels: int = 0  # library kernels launched through graph replays (kb_launch_count sees captures only)
@@ -148,8 +226,21 @@ class SEResNetModel(KataGoBaseModel):
     def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): storages change
         self._tables_cache = None
         self._wpack_key = None
-        self._graphs = {}
+        self._graphs.clear()
+        self._group_graphs.clear()
         return super()._apply(fn, *args, **kwargs)
+
+    def invalidate_packed_weights(self) -> None:
+        """Force a re-pack of the kernel-side weight shadow before the next CUDA forward. The cache key also watches the
+        autograd version counters, but writes that bypass them — `Adam(fused=True).step()`, `t.data` writes such as
+        `GradSync.broadcast_parameters`, `p.data.copy_` — need this explicit call (the trainer makes it after every
+        optimiser step; `load_state_dict` does through the hook below)."""
+        self._wpack_key = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_packed_weights()
+        return out
 
     def _act_dtype(self, device: torch.device) -> torch.dtype:
         if self._amp_enabled and self._amp_dtype == torch.bfloat16:
@@ -203,43 +294,52 @@ class SEResNetModel(KataGoBaseModel):
         """Eval-mode no-grad forward for action selection (reference katago_ppo.py:575-580 / katago_loop.py:337-344,
         404-406: per-step inference on 64..512 boards, several sub-batches per step in league play).
 
-        For batches up to `graph_max_batch` the ~290 kernel launches of the network are captured ONCE per
-        (batch, dtype) into a CUDA graph and replayed: at these sizes the step is launch-bound, not GPU-bound.
-        The returned tensors are views of the graph's static output buffers — valid until the next
-        `rollout_forward` with the same batch size (`select_actions` consumes them immediately). Larger batches,
-        CPU tensors and training mode go through the ordinary `forward`."""
+        For batches up to `graph_max_batch` the ~290 kernel launches of the network are captured into a CUDA graph per
+        (thread, batch BUCKET, dtype) and replayed: at these sizes the step is launch-bound, not GPU-bound. The batch is
+        padded up to `rollout_bucket(B)` inside the graph's static input (boards are independent in eval mode) so
+        varying sub-batch sizes share a few graphs; a bucket is captured the second time it is seen. The returned
+        tensors are views of the graph's static output buffers — owned by the calling thread, valid until its next
+        `rollout_forward` in the same bucket (`select_actions` consumes them immediately). Larger batches, CPU tensors
+        and training mode go through the ordinary `forward`."""
         if (self.training or not obs.is_cuda or obs.shape[0] > self.graph_max_batch or not self.kernel_supported()
-                or obs.ndim != 4 or tuple(obs.shape[1:]) != (self.params.obs_channels, 9, 9)):
+                or obs.ndim != 4 or tuple(obs.shape[1:]) != (self.params.obs_channels, 9, 9) or obs.shape[0] < 1):
             return self._forward_impl(obs)
         tables = self._ptr_tables()
         dtype = self._act_dtype(obs.device)
         code = 0 if dtype == torch.float32 else 1
         wpack = self._packed(tables.params, tables.buffers, dtype)   # re-packs in place when a parameter changed
         B = obs.shape[0]
-        key = (B, code, obs.device, bool(self.use_tensor_cores))
-        ent = self._graphs.get(key)
-        if ent is None or ent["wpack_ptr"] != wpack.data_ptr() or ent["tables"] is not tables:
-            if len(self._graphs) >= 8:
-                self._graphs.pop(next(iter(self._graphs)))
-            static_obs = torch.empty((B, self.params.obs_channels, 9, 9), dtype=torch.float32, device=obs.device)
-            static_obs.copy_(obs)
-            cur = torch.cuda.current_stream(obs.device)
-            side = torch.cuda.Stream(obs.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):  # warm-up outside the capture: one-time function attributes / driver lookups
-                model_ops.seresnet_forward_raw(static_obs, tables, wpack, False, code, bool(self.use_tensor_cores))
-            cur.wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            n0 = model_ops._lib.launch_count()
-            with torch.cuda.graph(graph):
-                out = self._captured_forward(static_obs, tables, wpack, code)
-            n_kernels = model_ops._lib.launch_count() - n0   # library kernels inside the graph (each replay launches them)
-            ent = self._graphs[key] = {"graph": graph, "obs": static_obs, "out": out, "kernels": n_kernels, "wpack_ptr": wpack.data_ptr(),
-                                       "tables": tables}
-        ent["obs"].copy_(obs)
+        Bb = rollout_bucket(B)
+        key = (threading.get_ident(), Bb, code, obs.device, bool(self.use_tensor_cores))
+        ent = self._graphs.lookup(key)
+        if ent is not None and (ent["wpack_ptr"] != wpack.data_ptr() or ent["tables"] is not tables):
+            self._graphs.drop(key)
+            ent = None
+        if ent is None:
+            if not self._graphs.should_capture(key):
+                return self._forward_impl(obs)
+            static_obs = torch.zeros((Bb, self.params.obs_channels, 9, 9), dtype=torch.float32, device=obs.device)
+            static_obs[:B].copy_(obs)
+            with _capture_lock:
+                cur = torch.cuda.current_stream(obs.device)
+                side = torch.cuda.Stream(obs.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):  # warm-up outside the capture: one-time function attributes / driver lookups
+                    model_ops.seresnet_forward_raw(static_obs, tables, wpack, False, code, bool(self.use_tensor_cores))
+                cur.wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                n0 = model_ops._lib.launch_count()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    out = self._captured_forward(static_obs, tables, wpack, code)
+                n_kernels = model_ops._lib.launch_count() - n0   # library kernels inside the graph (each replay launches them)
+            ent = {"graph": graph, "obs": static_obs, "out": out, "kernels": n_kernels, "wpack_ptr": wpack.data_ptr(),
+                   "tables": tables, "nbytes": _tensor_bytes(static_obs) + _tensor_bytes(out)}
+            self._graphs.store(key, ent)
+        ent["obs"][:B].copy_(obs)
         ent["graph"].replay()
         self.graph_replayed_kernels += ent["kernels"]
         policy_buf, value, score, _ws, _ = ent["out"]
+        policy_buf, value, score = policy_buf[:B], value[:B], score[:B]
         self.last_policy_buffer = policy_buf
         policy = policy_buf[:, :model_ops.POLICY_A].view(B, 9, 9, self.SPATIAL_MOVE_TYPES)
         return KataGoOutput(policy_logits=policy, value_logits=value, score_lead=score)
@@ -323,9 +423,6 @@ class SEResNetModel(KataGoBaseModel):
 
 
 # ---- grouped rollout: several (model, sub-batch) pairs as parallel branches of ONE CUDA graph -------------------------
-_GROUP_GRAPHS: dict = {}
-
-
 @torch.no_grad()
 def rollout_forward_many(pairs: "list[tuple[SEResNetModel, torch.Tensor]]") -> "list[KataGoOutput]":
     """Eval-mode forward of several independent (model, observations) pairs — the learner and its K league opponents
@@ -333,9 +430,12 @@ def rollout_forward_many(pairs: "list[tuple[SEResNetModel, torch.Tensor]]") -> "
     sequential forward per model per step, 64..256 boards each). At these sizes a forward is a chain of ~290 kernels of
     10-20 us that fill a fraction of the GPU, so the pairs are captured as PARALLEL BRANCHES of one CUDA graph (one
     branch per pair, each on its own stream during capture) and replayed with a single launch: the GPU runs the
-    branches side by side. Results are bit-identical to `model.rollout_forward(obs)` per pair. Returned tensors are views
-    of the graph's static buffers (valid until the next call with the same signature). Falls back to one
-    `rollout_forward` per pair for CPU tensors, training-mode models or unsupported shapes."""
+    branches side by side. Sub-batches are padded to `rollout_bucket` sizes inside the graph's static inputs, so the
+    varying learner / opponent splits of consecutive steps reuse a few graphs (captured on the second sighting; the
+    first falls back to one `rollout_forward` per pair). Results are bit-identical to `model.rollout_forward(obs)` per
+    pair. Returned tensors are views of static buffers owned by the calling thread (valid until its next call with the
+    same bucket signature). The cache lives on the first model of the group. Falls back to one `rollout_forward` per
+    pair for CPU tensors, training-mode models or unsupported shapes."""
     if not pairs:
         return []
     ok = all(isinstance(m, SEResNetModel) and not m.training and o.is_cuda and m.kernel_supported() and o.ndim == 4
@@ -351,47 +451,56 @@ def rollout_forward_many(pairs: "list[tuple[SEResNetModel, torch.Tensor]]") -> "
         code = 0 if dtype == torch.float32 else 1
         wpack = m._packed(tables.params, tables.buffers, dtype)
         prep.append((m, o, tables, wpack, code))
-    key = (dev,) + tuple((id(m), o.shape[0], code, bool(m.use_tensor_cores), wpack.data_ptr(), id(tables))
-                         for m, o, tables, wpack, code in prep)
-    ent = _GROUP_GRAPHS.get(key)
+    cache = pairs[0][0]._group_graphs
+    key = (threading.get_ident(), dev) + tuple((id(m), rollout_bucket(o.shape[0]), code, bool(m.use_tensor_cores), wpack.data_ptr(), id(tables))
+                                               for m, o, tables, wpack, code in prep)
+    ent = cache.lookup(key)
     if ent is None:
-        if len(_GROUP_GRAPHS) >= 8:
-            _GROUP_GRAPHS.pop(next(iter(_GROUP_GRAPHS)))
-        statics = [torch.empty_like(o, dtype=torch.float32).copy_(o) for _, o, *_ in prep]
-        cur = torch.cuda.current_stream(dev)
-        warm = torch.cuda.Stream(dev)
-        warm.wait_stream(cur)
-        with torch.cuda.stream(warm):  # warm-up outside the capture: one-time function attributes / driver lookups
-            for (m, _, tables, wpack, code), so in zip(prep, statics):
-                model_ops.seresnet_forward_raw(so, tables, wpack, False, code, bool(m.use_tensor_cores))
-        cur.wait_stream(warm)
-        graph = torch.cuda.CUDAGraph()
-        n0 = model_ops._lib.launch_count()
-        outs = []
-        with torch.cuda.graph(graph):
-            cap = torch.cuda.current_stream(dev)
-            # fork every branch before anything is enqueued on the capturing stream (a later fork would depend on pair 0)
-            branches = [torch.cuda.Stream(dev) for _ in prep[1:]]
-            for br in branches:
-                br.wait_stream(cap)
-            for i, ((m, _, tables, wpack, code), so) in enumerate(zip(prep, statics)):
-                if i == 0:
-                    outs.append(m._captured_forward(so, tables, wpack, code))
-                else:
-                    with torch.cuda.stream(branches[i - 1]):
+        if not cache.should_capture(key):
+            return [m.rollout_forward(o) for m, o in pairs]
+        statics = []
+        for _, o, *_rest in prep:
+            so = torch.zeros((rollout_bucket(o.shape[0]),) + tuple(o.shape[1:]), dtype=torch.float32, device=dev)
+            so[:o.shape[0]].copy_(o)
+            statics.append(so)
+        with _capture_lock:
+            cur = torch.cuda.current_stream(dev)
+            warm = torch.cuda.Stream(dev)
+            warm.wait_stream(cur)
+            with torch.cuda.stream(warm):  # warm-up outside the capture: one-time function attributes / driver lookups
+                for (m, _, tables, wpack, code), so in zip(prep, statics):
+                    model_ops.seresnet_forward_raw(so, tables, wpack, False, code, bool(m.use_tensor_cores))
+            cur.wait_stream(warm)
+            graph = torch.cuda.CUDAGraph()
+            n0 = model_ops._lib.launch_count()
+            outs = []
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                cap = torch.cuda.current_stream(dev)
+                # fork every branch before anything is enqueued on the capturing stream (a later fork would depend on pair 0)
+                branches = [torch.cuda.Stream(dev) for _ in prep[1:]]
+                for br in branches:
+                    br.wait_stream(cap)
+                for i, ((m, _, tables, wpack, code), so) in enumerate(zip(prep, statics)):
+                    if i == 0:
                         outs.append(m._captured_forward(so, tables, wpack, code))
-            for br in branches:
-                cap.wait_stream(br)
-        ent = _GROUP_GRAPHS[key] = {"graph": graph, "obs": statics, "outs": outs, "kernels": model_ops._lib.launch_count() - n0,
-                                    "keep": [(tables, wpack) for _, _, tables, wpack, _ in prep]}
+                    else:
+                        with torch.cuda.stream(branches[i - 1]):
+                            outs.append(m._captured_forward(so, tables, wpack, code))
+                for br in branches:
+                    cap.wait_stream(br)
+            n_kernels = model_ops._lib.launch_count() - n0
+        ent = {"graph": graph, "obs": statics, "outs": outs, "kernels": n_kernels,
+               "keep": [(tables, wpack) for _, _, tables, wpack, _ in prep], "nbytes": _tensor_bytes(statics) + _tensor_bytes(outs)}
+        cache.store(key, ent)
     for so, (_, o, *_rest) in zip(ent["obs"], prep):
-        so.copy_(o)
+        so[:o.shape[0]].copy_(o)
     ent["graph"].replay()
     pairs[0][0].graph_replayed_kernels += ent["kernels"]
     res = []
     for (m, o, *_rest), out in zip(prep, ent["outs"]):
-        policy_buf, value, score = out[0], out[1], out[2]
+        n = o.shape[0]
+        policy_buf, value, score = out[0][:n], out[1][:n], out[2][:n]
         m.last_policy_buffer = policy_buf
-        res.append(KataGoOutput(policy_logits=policy_buf[:, :model_ops.POLICY_A].view(o.shape[0], 9, 9, m.SPATIAL_MOVE_TYPES),
+        res.append(KataGoOutput(policy_logits=policy_buf[:, :model_ops.POLICY_A].view(n, 9, 9, m.SPATIAL_MOVE_TYPES),
                                 value_logits=value, score_lead=score))
     return res

@@ -31,6 +31,11 @@ def _check_logits(logits: torch.Tensor) -> tuple[int, int, int]:
     return logits.shape[0], logits.shape[1], logits.stride(0)
 
 
+def mask_row_bytes(mask: torch.Tensor) -> int:
+    """Bytes of legal-mask storage the kernels read per row (algorithmic-traffic accounting in bench.py)."""
+    return int(mask.shape[1]) * mask.element_size()
+
+
 def _mask_u8(mask: torch.Tensor, B: int, A: int) -> torch.Tensor:
     if mask.shape != (B, A):
         raise ValueError(f"legal mask shape {tuple(mask.shape)} != {(B, A)}")

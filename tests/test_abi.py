@@ -40,7 +40,7 @@ def test_peer_sync_host_side_checks_do_not_need_a_gpu():
     # data [slots][world][slot_doubles] doubles + flags [slots][world] u64
     assert lib.kb_peer_buffer_bytes(8, 4, 512) == 4 * 8 * 512 * 8 + 4 * 8 * 8
     assert lib.kb_peer_buffer_bytes(17, 4, 512) < 0 and lib.kb_peer_buffer_bytes(2, 1, 512) < 0
-    assert ctypes.sizeof(KbPeerCtx) == 16 * 8 + 4 * 4 + 8 + 8
+    assert ctypes.sizeof(KbPeerCtx) == 16 * 8 + 4 * 4 + 8 + 8 + 8 + 8   # + status word pointer, timeout_ms
     ctx = KbPeerCtx()
     ctx.rank, ctx.world, ctx.n_slots, ctx.slot_doubles = 3, 2, 4, 512          # rank outside the world
     dummy = ctypes.c_void_p(16)

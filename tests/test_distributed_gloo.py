@@ -21,15 +21,13 @@ def _free_port():
 
 def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
-    from keisei_b200.distributed import (BatchNormSync, GradSync, cleanup_distributed, get_distributed_context, seed_all_ranks,
-                                         setup_distributed)
+    from keisei_b200.distributed import BatchNormSync, GradSync, init_from_env, shutdown
     from keisei_b200.katago_ppo import KataGoPPOAlgorithm, KataGoPPOParams, KataGoRolloutBuffer
     from keisei_b200.model_registry import build_model
     torch.set_num_threads(1)
-    ctx = get_distributed_context()
-    assert ctx.is_distributed and ctx.world_size == world and ctx.rank == rank and ctx.is_main == (rank == 0)
-    setup_distributed(ctx, backend="gloo")
-    seed_all_ranks(100 + rank)               # different init + different rollouts per rank
+    env = init_from_env(backend="gloo")
+    assert env.launched and env.world_size == world and env.rank == rank and env.local_rank == rank
+    torch.manual_seed(100 + rank)            # different init + different rollouts per rank
     model = build_model("se_resnet", dict(TINY))
     algo = KataGoPPOAlgorithm(KataGoPPOParams(batch_size=8, epochs_per_batch=1), model)
     algo.grad_sync = GradSync()
@@ -54,7 +52,7 @@ def _worker(rank, world, port, out_dir):
     sd = {k: v for k, v in model.state_dict().items() if "running_" not in k and "num_batches" not in k}
     torch.save(sd, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
-    cleanup_distributed(ctx)
+    shutdown()
 
 
 @pytest.mark.timeout(180)
@@ -67,13 +65,13 @@ def test_two_rank_gloo_update_keeps_weights_in_sync(tmp_path):
         assert torch.equal(a[k], b[k]), k
 
 
-def test_context_without_torchrun_env(monkeypatch):
-    from keisei_b200.distributed import get_distributed_context, setup_distributed
+def test_rank_env_without_and_with_partial_launcher_env(monkeypatch):
+    from keisei_b200.distributed import init_from_env, rank_env
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         monkeypatch.delenv(k, raising=False)
-    ctx = get_distributed_context()
-    assert not ctx.is_distributed and ctx.world_size == 1 and ctx.is_main
-    setup_distributed(ctx)  # no-op
+    env = rank_env()
+    assert not env.launched and env.world_size == 1 and env.rank == 0
+    assert init_from_env() == env  # no launcher: nothing to join
     monkeypatch.setenv("RANK", "0")
     with pytest.raises(RuntimeError, match="LOCAL_RANK"):
-        get_distributed_context()
+        rank_env()

@@ -41,7 +41,11 @@ def test_graph_replay_matches_plain_forward_and_tracks_weight_updates(amp):
     assert not torch.equal(got.policy_logits, want[0][0])
     # training mode and oversize batches fall through to the ordinary path
     m.graph_max_batch = 8
-    assert torch.equal(m.rollout_forward(obs[1]).value_logits, want[1][1]) or True
+    n_before = len(m._graphs)
+    with torch.no_grad():
+        w3 = m(obs[1]).value_logits.clone()
+    assert torch.equal(m.rollout_forward(obs[1]).value_logits, w3)
+    assert len(m._graphs) == n_before   # 24 boards > graph_max_batch: no capture, the plain launch sequence ran
 
 
 def test_select_actions_uses_graph_and_stays_correct():
@@ -52,6 +56,8 @@ def test_select_actions_uses_graph_and_stays_correct():
     obs = torch.randn(16, 50, 9, 9, device=DEV)
     mask = torch.rand(16, 11259, device=DEV) < 0.01
     mask[:, 5] = True
+    a1, lp1, v1 = algo.select_actions(obs, mask)
+    assert len(m._graphs) == 0          # a bucket is captured on its second sighting
     a1, lp1, v1 = algo.select_actions(obs, mask)
     assert len(m._graphs) == 1
     n0 = _lib.launch_count()
@@ -77,9 +83,9 @@ def test_two_branch_split_rollout_is_bit_identical(B):
     with torch.no_grad():
         w = m.rollout_forward(obs)
         want = (w.policy_logits.clone(), w.value_logits.clone(), w.score_lead.clone())
-    m._graphs = {}
+    m._graphs.clear()
     m.rollout_split_min = 2
-    for _ in range(2):
+    for _ in range(3):
         got = m.rollout_forward(obs)
         assert torch.equal(got.policy_logits, want[0]) and torch.equal(got.value_logits, want[1]) and torch.equal(got.score_lead, want[2])
     assert m.last_policy_buffer[:, 11259:].abs().sum().item() == 0
@@ -100,7 +106,7 @@ def test_grouped_rollout_many_models_is_bit_identical_and_select_actions_many():
         for m, o in zip(models, obs):
             w = m(o)
             want.append((w.policy_logits.clone(), w.value_logits.clone(), w.score_lead.clone()))
-    for _ in range(2):
+    for _ in range(3):
         got = rollout_forward_many(list(zip(models, obs)))
         for g, w in zip(got, want):
             assert torch.equal(g.policy_logits, w[0]) and torch.equal(g.value_logits, w[1]) and torch.equal(g.score_lead, w[2])
@@ -127,3 +133,58 @@ def test_grouped_rollout_many_models_is_bit_identical_and_select_actions_many():
     bad = masks[2].clone(); bad[3] = False
     with pytest.raises(RuntimeError, match=r"Environments \[3\] have zero legal actions"):
         algo.select_actions_many([(obs[0], masks[0]), (obs[2], bad)], models=[ms[0], ms[2]])
+
+
+def test_bucketed_batches_share_one_graph_and_stay_bit_identical():
+    """Sub-batch sizes vary from step to step in a split-merge rollout (katago_loop.py:337-344): sizes of one bucket replay
+    ONE captured graph (padded static input, outputs sliced back), with results bit-identical to the plain forward."""
+    from keisei_b200.models.se_resnet import rollout_bucket
+    assert [rollout_bucket(b) for b in (1, 8, 9, 64, 65, 96, 512, 513, 2048, 2049, 4096)] == [8, 8, 16, 64, 96, 96, 512, 640, 2048, 2304, 4096]
+    torch.manual_seed(4)
+    m = SEResNetModel(SEResNetParams(**CFG)).to(DEV).eval()
+    m.configure_amp(True, torch.bfloat16, "cuda")
+    sizes = [70, 65, 96, 81, 70, 90]                      # all in bucket 96
+    for i, b in enumerate(sizes):
+        obs = torch.randn(b, 50, 9, 9, device=DEV)
+        with torch.no_grad():
+            w = m(obs)
+            want = (w.policy_logits.clone(), w.value_logits.clone(), w.score_lead.clone())
+        n0 = _lib.launch_count()
+        got = m.rollout_forward(obs)
+        assert got.policy_logits.shape == (b, 9, 9, 139) and got.value_logits.shape == (b, 3)
+        assert torch.equal(got.policy_logits, want[0]) and torch.equal(got.value_logits, want[1]) and torch.equal(got.score_lead, want[2])
+        if i >= 2:
+            assert _lib.launch_count() == n0            # replayed: no direct launch through the library
+    assert len(m._graphs) == 1 and m._graphs.captures == 1
+    # LRU bounded by bytes: a tiny budget keeps only the most recent graph
+    m._graphs.max_bytes = 1
+    for b in (8, 8, 16, 16, 24, 24):
+        m.rollout_forward(torch.randn(b, 50, 9, 9, device=DEV))
+    assert len(m._graphs) == 1
+
+
+def test_graph_buffers_are_per_thread():
+    """A tournament thread / DynamicTrainer may run the same model concurrently (dynamic_trainer.py:44-50): its replay
+    must not overwrite the static output buffers the training thread is still reading."""
+    import threading
+    torch.manual_seed(5)
+    m = SEResNetModel(SEResNetParams(**CFG)).to(DEV).eval()
+    a, b = torch.randn(16, 50, 9, 9, device=DEV), torch.randn(16, 50, 9, 9, device=DEV)
+    with torch.no_grad():
+        want_a, want_b = m(a).value_logits.clone(), m(b).value_logits.clone()
+    m.rollout_forward(a)
+    mine = m.rollout_forward(a)                           # replayed: views of this thread's static buffers
+    assert torch.equal(mine.value_logits, want_a)
+    other = {}
+
+    def worker():
+        with torch.cuda.stream(torch.cuda.Stream(DEV)):
+            m.rollout_forward(b)
+            other["out"] = m.rollout_forward(b).value_logits.clone()
+            torch.cuda.current_stream().synchronize()
+
+    t = threading.Thread(target=worker)
+    t.start(); t.join(120)
+    assert torch.equal(other["out"], want_b)
+    assert torch.equal(mine.value_logits, want_a)        # untouched by the other thread's replay
+    assert len(m._graphs) == 2
