@@ -36,7 +36,7 @@ MODEL_CFG = dict(num_blocks=40, channels=256)           # reference SEResNetPara
 ROLLOUT_B = 4096                                        # BASELINE.json configs[1]
 UPDATE_GLOBAL_B = 8192                                  # BASELINE.json configs[2]
 A = 11259
-WORKLOAD = "SE-ResNet 40x256 rollout (select_actions), 4096 boards/GPU"
+WORKLOAD = "SE-ResNet 40x256 rollout, 4096 boards/GPU"
 CONV_TRAFFIC_BYTES = 306.0e6                            # ncu dram read+write per launch (profiles/, refreshed per round)
 CONV_FLOP_PER_POS = 2 * 81 * 256 * 2304                 # one 256->256 3x3 conv, SURVEY.md 8(d): 95.55 MFLOP
 FWD_FLOP_PER_POS = 18.66e6 + 80 * 95.55e6               # trunk convs only: 7.663 GFLOP
@@ -174,7 +174,7 @@ def cpu_baseline(batch: int = 256, reps: int = 6, warmup: int = 1) -> dict:
         step()
     dt = (time.perf_counter() - t0) / reps
     return {"value": batch / dt, "unit": "positions/s", "cores": cores, "kind": "port",
-            "sample": f"oracle fp32 rollout step, 40x256, batch {batch}, {reps} reps"}
+            "sample": f"oracle fp32 rollout, batch {batch} x {reps}"}
 
 
 def _oracle_train_step(cfg: dict, batch: int, seed: int):
@@ -273,10 +273,11 @@ def conv_roofline(device, reps: int = 20) -> dict:
     flops = CONV_FLOP_PER_POS * B
     achieved = flops / (ms * 1e-3) / 1e12
     peak = pk["bf16_tflops"]
-    return {"kernel": "conv3x3_tc_kernel 256->256 B=4096", "bound": "tensor", "achieved": round(achieved, 1), "peak": peak,
-            "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "frac_sustained": round(achieved / pk["bf16_tflops_sustained"], 4),
+    return {"kernel": "conv3x3_tc 256->256 B=4096", "bound": "tensor", "achieved": round(achieved, 1), "peak": peak,
+            "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture under profiles/
-            "traffic": CONV_TRAFFIC_BYTES, "ms_per_launch": round(ms, 4), "peak_source": f"{pk['source']} burst"}
+            "traffic": CONV_TRAFFIC_BYTES, "ms": round(ms, 4), "peak_src": f"{pk['source']} burst",
+            "frac_sustained": round(achieved / pk["bf16_tflops_sustained"], 4)}
 
 
 def hbm_kernels(device) -> dict:
@@ -396,7 +397,7 @@ def run_ours(args) -> None:
     line = {"metric": "rollout positions/s", "value": round(value, 1), "unit": "positions/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "impl": "ours",
-            "config": {"workload": WORKLOAD, "parallelism": f"shard{world}-no-comm", "cache": "inputs > L2 (170 MB/layer)"},
+            "config": {"workload": WORKLOAD, "parallelism": f"shard{world}-no-comm", "cache": "inputs>L2"},
             "e2e": {"value": round(e2e, 1), "unit": "positions/s", "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": ingest.h2d_bytes, "d2h_bytes_per_step": ingest.d2h_bytes},
             "gpu_launches": int(launches), "clocks": clk.summary(),
@@ -420,13 +421,12 @@ def run_ours(args) -> None:
             line["cpu_baseline"] = cpu_baseline()
             c1 = cpu_config1()
             detail["cpu_config1"] = c1
-            line["cpu_config1"] = {"value": round(c1["value"], 1), "unit": "samples/s", "cores": c1["cores"],
-                                   "what": "4x64 b256 PPO fwd+bwd fp32"}
+            line["cpu_config1_4x64_b256_fwdbwd"] = {"value": round(c1["value"], 1), "unit": "samples/s", "cores": c1["cores"]}
             line["cpu_baseline"]["value"] = round(line["cpu_baseline"]["value"], 2)
             if upd is not None:
                 cu = cpu_update_baseline()
                 detail["update_cpu_baseline"] = cu
-                upd["cpu"] = {"value": round(cu["value"], 2), "cores": cu["cores"], "kind": "port", "sample": "40x256 b32 fwd+loss+bwd"}
+                upd["cpu"] = {"value": round(cu["value"], 2), "cores": cu["cores"], "kind": "port", "sample": "b32 fwd+bwd"}
             if args.extra:
                 try:
                     detail["gpu_eager_port"] = eager_port_gpu(device, obs, mask)
@@ -560,8 +560,8 @@ def bench_update(args, algo, model, device, rank, world) -> tuple[dict, dict]:
     gae_ms = timed(gae_step, 20, 3, device, world)
     sps = UPDATE_GLOBAL_B / (ms * 1e-3)
     frac = (22.97e9 * UPDATE_GLOBAL_B / world / (ms * 1e-3) / 1e12) / peaks()["bf16_tflops_sustained"]
-    compact = {"metric": "PPO update samples/s", "value": round(sps, 1), "unit": "samples/s", "ms_per_step": round(ms, 3),
-               "global_batch": UPDATE_GLOBAL_B, "scaling": "strong", "frac": round(frac, 4), "bn": bn_kind,
+    compact = {"value": round(sps, 1), "unit": "samples/s", "ms_per_step": round(ms, 3), "batch": UPDATE_GLOBAL_B,
+               "frac": round(frac, 4), "bn": bn_kind,
                "fixed_ms": round(fixed_ms, 3), "gae_ms": round(gae_ms, 4)}
     if world > 1:
         compact.update({"allreduce_ms": round(allreduce_ms, 3), "allreduce_exposed_ms": round(ms_local_bn - ms_no_ar, 3),

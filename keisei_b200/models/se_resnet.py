@@ -71,6 +71,13 @@ class _GraphCache:
     def __len__(self) -> int:
         return len(self.entries)
 
+    # copy.deepcopy(model) / pickling (opponent snapshots, torch.save(model)): captured graphs never travel with a copy
+    def __deepcopy__(self, memo) -> "_GraphCache":
+        return _GraphCache(self.max_bytes, self.max_entries)
+
+    def __reduce__(self):
+        return (_GraphCache, (self.max_bytes, self.max_entries))
+
     def clear(self) -> None:
         with self.lock:
             self.entries.clear(); self.sightings.clear(); self.bytes = 0

@@ -1,6 +1,12 @@
 """pytest config: `gpu` marker; CPU-only runs use `-m "not gpu"`."""
+import os
 import sys
 from pathlib import Path
+
+# Thread-emulated ranks (tests/test_sync_bn_gpu.py) run two spin-waiting exchange kernels on ONE GPU: their streams must
+# not share a hardware work queue (false serialisation = deadlock until the exchange times out). The default is 8 queues;
+# real multi-process runs (one GPU per rank) are not affected. Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np
 import pytest

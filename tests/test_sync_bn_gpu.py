@@ -65,7 +65,7 @@ def _peer_handles(world: int, slot_doubles: int):
     nbytes = _lib.load().kb_peer_buffer_bytes(world, 4, slot_doubles)
     bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=DEV) for _ in range(world)]
     torch.cuda.synchronize()
-    return bufs, [PeerBatchNormSync.from_local_buffers([b.data_ptr() for b in bufs], r, slot_doubles) for r in range(world)]
+    return bufs, [PeerBatchNormSync.from_local_buffers([b.data_ptr() for b in bufs], r, slot_doubles, timeout_s=30) for r in range(world)]
 
 
 def test_peer_memory_allreduce_kernel_three_ranks_many_rounds():
@@ -216,3 +216,40 @@ def test_sync_hook_error_surfaces_as_exception():
         m(torch.randn(2, 50, 9, 9, device=DEV))
     m.convert_sync_batchnorm(None)
     m(torch.randn(2, 50, 9, 9, device=DEV))
+
+
+def test_lost_peer_is_reported_to_the_host_and_not_committed():
+    """A peer that never arrives: the exchange gives up after its (configurable) timeout, the sums come back NaN, the
+    host-visible status word makes `check()` raise PeerLostError, and BatchNorm finalize leaves the running statistics
+    untouched (no silent NaN poisoning)."""
+    from keisei_b200 import _lib
+    from keisei_b200.distributed import PeerBatchNormSync, PeerLostError
+    nbytes = _lib.load().kb_peer_buffer_bytes(2, 4, 64)
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=DEV) for _ in range(2)]
+    h = PeerBatchNormSync.from_local_buffers([b.data_ptr() for b in bufs], 0, 64, timeout_s=0.3)
+    h.check()                                   # nothing pending
+    t = torch.ones(8, dtype=torch.float64, device=DEV)
+    h.all_reduce_(t)                            # rank 1 never shows up
+    torch.cuda.synchronize()
+    assert bool(t.isnan().all())
+    with pytest.raises(PeerLostError, match="waiting for rank 1"):
+        h.check()
+    h.check()                                   # reported once, then cleared
+    # NaN statistics are not committed: a training forward on such sums keeps the running buffers
+    m = SEResNetModel(SEResNetParams(num_blocks=1, channels=32, se_reduction=4, global_pool_channels=8, policy_channels=8,
+                                     value_fc_size=8, score_fc_size=8)).to(DEV).train()
+    before = {n: b.clone() for n, b in m.named_buffers() if b.is_floating_point()}
+
+    class Poison:
+        world_size = 2
+
+        def all_reduce_(self, sums):
+            return sums.fill_(float("nan"))
+
+    m.convert_sync_batchnorm(Poison())
+    with torch.no_grad():
+        m(torch.randn(4, 50, 9, 9, device=DEV))
+    for n, b in m.named_buffers():
+        if b.is_floating_point():
+            assert torch.equal(b, before[n]), n
+    h.close(collective=False)

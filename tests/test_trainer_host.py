@@ -230,3 +230,22 @@ def test_update_on_ragged_env_ids_buffer_matches_reference_golden():
         if v.is_floating_point():
             want = g["update/after/" + name]
             assert np.abs(v.numpy() - want).max() <= 2e-4 * max(1e-2, np.abs(want).max()), name
+
+
+def test_model_deepcopy_pickle_and_weight_cache_invalidation():
+    """Opponent snapshots deep-copy the learner (league / tournament code); captured rollout graphs and their locks must
+    not travel. The packed-weight cache is invalidated explicitly by load_state_dict and by the trainer's optimiser tail
+    (Adam(fused=True) does not bump Tensor._version)."""
+    import copy
+    import pickle
+    m = build_model("se_resnet", dict(TINY))
+    m2 = copy.deepcopy(m)
+    assert m2._graphs is not m._graphs and len(m2._graphs) == 0
+    m3 = pickle.loads(pickle.dumps(m))
+    assert list(m3.state_dict()) == list(m.state_dict())
+    m._wpack_key = ("stale",)
+    m.load_state_dict(m2.state_dict())
+    assert m._wpack_key is None
+    m._wpack_key = ("stale",)
+    m.invalidate_packed_weights()
+    assert m._wpack_key is None
