@@ -144,6 +144,9 @@ int kb_peer_status_create(unsigned long long** word);   /* pinned, device-mapped
 int kb_peer_status_destroy(unsigned long long* word);
 /* buf (n doubles, device) <- sum over ranks, in rank order (bit-identical on every rank), stream-ordered */
 int kb_peer_allreduce_f64(void* buf, long long n, const kb_peer_ctx* ctx, unsigned long long seq, kb_stream_t stream);
+/* test helper: all `world` ranks of one exchange emulated on ONE GPU as a single cooperative launch (block r = rank r on
+ * bufs[r] / ctxs[r]; the contexts' buffers are plain device allocations of this process); advances every ctx->seq */
+int kb_peer_allreduce_emulate(void* const* bufs, long long n, kb_peer_ctx* const* ctxs, int world, kb_stream_t stream);
 /* a kb_allreduce_hook: user = kb_peer_ctx* */
 int kb_peer_allreduce_hook(void* user, void* buf, long long n_doubles, kb_stream_t stream);
 /* grads: float32 buffers shaped like params, PRE-ZEROED by the caller */
@@ -180,12 +183,21 @@ int kb_resnet_backward(const kb_resnet_desc* d, const void* const* params, const
 /* ---- single 3x3 convolution on NHWC 9x9 boards (unit-test / profiling entry points):
  *      F.conv2d(padding=1, bias=False) at se_resnet.py:50,52,110 ----
  * in (B,81,Cin), w (Cout,9,Cin) packed, out (B,81,Cout), all `dtype`. backend 0 = SIMT fp32-accumulate,
- * 1 = tcgen05 (bf16 only). Optional fused epilogue pieces (null = off): per-channel scale/shift,
+ * 1 = tcgen05 (bf16 only; kernel chosen automatically), 2 = tcgen05 single-CTA kernel, 3 = tcgen05 CTA-pair kernel
+ * (cta_group::2, Cout %% 256 == 0). Optional fused epilogue pieces (null = off): per-channel scale/shift,
  * relu, per-(board,channel) bias, channel sums (double[2*Cout]: sum, sum of squares),
  * board_mean (B,Cout), pool (B,3*Cout: mean,max,std). */
 int kb_conv3x3_forward(const void* in, const void* w, void* out, int B, int Cin, int Cout, int dtype, int backend,
                        const float* scale, const float* shift, int relu, const float* gbias, double* ch_sums,
                        float* board_mean, float* pool, int num_sms, kb_stream_t stream);
+/* conv2 of a GlobalPoolBiasBlock in evaluation mode with the rest of the block fused into the convolution's epilogue
+ * (reference se_resnet.py:79-90): out = relu(bn2(conv(in)) * sigmoid(se_scale) + se_shift + res), where
+ * (se_scale, se_shift) = se_fc2(relu(se_fc1(board mean of bn2(conv(in))))); pool (B,3*Cout) / pool_bf16 receive the
+ * global-pool statistics (mean, max, population std) of `out` (se_resnet.py:93-98). tcgen05 CTA-pair kernel:
+ * bf16, Cout == 256, S == 16, Cin %% 64 == 0, B >= 3. scale/shift = folded eval BatchNorm. */
+int kb_conv3x3_se_tail(const void* in, const void* w, void* out, int B, int Cin, int Cout, const float* scale,
+                       const float* shift, const void* res, const float* se_w1, const float* se_b1, const float* se_w2,
+                       const float* se_b2, int S, float* pool, void* pool_bf16, int num_sms, kb_stream_t stream);
 /* dw (Cout,Cin_true,3,3) float32 += sum over boards/pixels of dy (B,81,Cout) x shifted x (B,81,Cin) */
 /* backend 1 (tcgen05) needs a scratch buffer of kb_conv3x3_wgrad_ws_bytes() bytes for the per-slice partial tiles */
 long long kb_conv3x3_wgrad_ws_bytes(int Cin, int Cout, int num_sms);

@@ -44,6 +44,7 @@ _SIGS: dict[str, tuple[object, list[object]]] = {
     "kb_peer_status_create": (c_int, [_P]),
     "kb_peer_status_destroy": (c_int, [_P]),
     "kb_peer_allreduce_f64": (c_int, [_P, c_longlong, _P, c_ulonglong, _P]),
+    "kb_peer_allreduce_emulate": (c_int, [_P, c_longlong, _P, c_int, _P]),
     "kb_peer_allreduce_hook": (c_int, [_P, _P, c_longlong, _P]),
 }
 

@@ -13,12 +13,26 @@ extern "C" int kb_conv3x3_forward(const void* in, const void* w, void* out, int 
   e.scale = scale; e.shift = shift; e.relu = relu; e.gbias = gbias;
   if (ch_sums) { e.ch_sum = ch_sums; e.ch_sumsq = ch_sums + Cout; }
   e.board_sum = board_mean; e.board_scale = 1.f / 81.f; e.pool = pool;
-  if (backend == 1) {
+  if (backend >= 1 && backend <= 3) {   // 1: tcgen05, kernel chosen automatically; 2: single-CTA kernel; 3: CTA-pair (cta_group::2) kernel
     KB_CHECK_ARG(B >= 3, "kb_conv3x3_forward: tcgen05 path needs at least 3 boards");
     KB_CHECK_ARG(kbk_conv3x3_tc_supported(Cin, Cout, dtype), "kb_conv3x3_forward: tcgen05 path needs bf16, Cin%%64==0, Cout%%128==0 (got %d,%d,dtype %d)", Cin, Cout, dtype);
-    return kbk_conv3x3_tc(in, w, out, B, Cin, Cout, e, num_sms, stream);
+    return kbk_conv3x3_tc_mode(in, w, out, B, Cin, Cout, e, num_sms, backend - 1, stream);
   }
   return kbk_conv3x3_simt(in, w, out, B, Cin, Cout, dtype, e, stream);
+}
+
+// conv2 of a GlobalPoolBiasBlock in evaluation mode with the whole block tail fused into the epilogue (CTA-pair kernel)
+extern "C" int kb_conv3x3_se_tail(const void* in, const void* w, void* out, int B, int Cin, int Cout, const float* scale,
+                                  const float* shift, const void* res, const float* se_w1, const float* se_b1,
+                                  const float* se_w2, const float* se_b2, int S, float* pool, void* pool_bf16, int num_sms,
+                                  cudaStream_t stream) {
+  KB_CHECK_ARG(in && w && out && scale && shift && res && se_w1 && se_b1 && se_w2 && se_b2 && pool, "kb_conv3x3_se_tail: null pointer");
+  KB_CHECK_ARG(B >= 3, "kb_conv3x3_se_tail: needs at least 3 boards");
+  KB_CHECK_ARG(kbk_conv3x3_se_tail_supported(Cin, Cout, S, KB_BF16), "kb_conv3x3_se_tail: needs Cout == 256, S == 16, Cin %% 64 == 0 (got %d, %d, %d)", Cout, S, Cin);
+  ConvEpi e; memset(&e, 0, sizeof(e));
+  e.scale = scale; e.shift = shift; e.res = res; e.se_w1 = se_w1; e.se_b1 = se_b1; e.se_w2 = se_w2; e.se_b2 = se_b2;
+  e.pool = pool; e.pool_bf = pool_bf16;
+  return kbk_conv3x3_tc_mode(in, w, out, B, Cin, Cout, e, num_sms, 2, stream);
 }
 
 extern "C" long long kb_conv3x3_wgrad_ws_bytes(int Cin, int Cout, int num_sms) {

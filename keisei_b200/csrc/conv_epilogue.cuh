@@ -27,6 +27,15 @@ struct ConvEpi {
   float board_scale;      // e.g. 1/81 for the SE squeeze (mean), 1 for the gpool-bias gradient
   void* board_bf;         // [B][Cout] bf16 or null: copy of board_sum (operand of the tcgen05 SE layer)
   float* pool;            // [B][3*Cout] or null: mean, max, population std of stored v
+  // ---- fused evaluation tail of a GlobalPoolBiasBlock (conv3x3_tc2_kernel<.., kSeTail = true> only; se_resnet.py:83-90):
+  // out = relu((acc*scale + shift) * sigmoid(se_scale) + se_shift + res), (se_scale, se_shift) = W2 relu(W1 mean + b1) + b2
+  // with mean = board mean of acc*scale + shift; pool / pool_bf receive the global-pool statistics of `out`
+  const void* res;        // [B][81][Cout] block input (activation dtype) or null
+  const float* se_w1;     // [S][Cout]
+  const float* se_b1;     // [S]
+  const float* se_w2;     // [2*Cout][S]
+  const float* se_b2;     // [2*Cout]
+  void* pool_bf;          // [B][3*Cout] bf16 copy of pool or null (operand of the next block's tcgen05 global_fc)
 };
 
 // Feature bits: a kernel may be instantiated for a fixed feature set F (branches resolved at compile

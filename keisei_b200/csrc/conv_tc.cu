@@ -48,6 +48,55 @@ using namespace tcptx;
 // instruction descriptor: fp32 accumulate, bf16 A/B, both K-major, N (>>3) at bit 17, M (>>4) at bit 24
 constexpr uint32_t kIdescF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
+// One accumulator tile (128 channels x 3 boards) through the fused epilogue: thread = output channel `et.c`, columns =
+// pixels. Shared by the single-CTA and the CTA-pair kernels.
+template <int F>
+__device__ __forceinline__ void epilogue_tile(const ConvEpi& epi, ConvEpiThread<bf16, kBoards, F>& et, uint32_t taddr, int b0,
+                                              int nb_valid, int Cout, bf16* __restrict__ out) {
+      // Mask-source prefetch (data-gradient epilogue): the ReLU mask / BN-backward statistics need one
+      // activation element per accumulator. Loads are issued kPf chunks (of 16 columns) ahead of their
+      // use so ~64 independent loads per thread are in flight instead of one dependent load per column.
+      constexpr bool kMask = (F != kEpiDynamic) && (F & kEpiMask) != 0;
+      constexpr int kPf = 4, kChunks = (kBoards * 81 + 15) / 16;
+      bf16 pf[kPf + 1][16];
+      const bf16* mbase = kMask ? (const bf16*)epi.mask_src + et.index(b0, 0) : nullptr;
+      auto prefetch = [&](int ch) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = ch * 16 + i;  // boards are contiguous in memory: element (col) sits col*Cout further
+          pf[ch % (kPf + 1)][i] = (col < kBoards * 81 && col / 81 < nb_valid) ? mbase[(unsigned)col * (unsigned)Cout] : bf16(0.f);
+        }
+      };
+      if (kMask) {
+#pragma unroll
+        for (int ch = 0; ch < kPf; ++ch) prefetch(ch);
+      }
+#pragma unroll
+      for (int ch = 0; ch < kTileN / 16; ++ch) {
+        if (ch * 16 < kBoards * 81) {
+          if (kMask && ch + kPf < kChunks) prefetch(ch + kPf);
+          uint32_t r[16];
+          tmem_ld16(taddr + ch * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = ch * 16 + i;
+            if (col < kBoards * 81) {
+              const int j = col / 81, p = col % 81;
+              if (j < nb_valid) {
+                if (p == 0) et.begin_board(b0 + j, out);
+                float ms = 0.f;
+                if (kMask) ms = __bfloat162float(pf[ch % (kPf + 1)][i]);
+                else if (F == kEpiDynamic && epi.mask_src != nullptr) ms = __bfloat162float(((const bf16*)epi.mask_src)[et.index(b0 + j, p)]);
+                et.value(j, p, __uint_as_float(r[i]), ms);
+                if (p == 80) et.board_done(j, b0 + j);
+              }
+            }
+          }
+        }
+      }
+}
+
 // ---------------------------------------------------------------- forward / dgrad kernel
 // kCl = true: launched as clusters of 2 CTAs that own the two 128-channel halves of the SAME board group.
 // The activation (B) tile is identical for both, so each CTA fetches only part of it (rank 0: boards 0-1,
@@ -98,47 +147,50 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   const uint32_t tmem_base = *holder_ptr;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = t_first; t < num_tiles; t += t_step) {
-        const int ct = t % n_ct, grp = t / n_ct;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / kb_per_tap, cc = kb - tap * kb_per_tap;
-          mbar_wait(empty_bar(stage), phase ^ 1u);  // cluster: both CTAs' MMAs have retired this stage
+    // ===== TMA producer: the warp runs the loop uniformly, one elected lane issues =====
+    const bool issuer = elect_one_sync();
+    int stage = 0; uint32_t phase = 0;
+    for (int t = t_first; t < num_tiles; t += t_step) {
+      const int ct = t % n_ct, grp = t / n_ct;
+      int tap = 0, cc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);  // cluster: both CTAs' MMAs have retired this stage
+        const uint32_t a_dst = smem_base + stage * kStageBytes;
+        const int sx = tap % 3 - 1, sy = tap / 3 - 1;
+        if (issuer) {
           mbar_arrive_expect_tx(full_bar(stage), kABytes + kBTxBytes);
-          const uint32_t a_dst = smem_base + stage * kStageBytes;
           tma_load_2d(a_dst, &map_w, full_bar(stage), kb * kBlockK, ct * kTileM);
           if (kCl) {
             if (crank == 0)
-              tma_load_4d_mc(a_dst + kABytes, &map_x2, full_bar(stage), cc * kBlockK, tap % 3 - 1, tap / 3 - 1, grp * kBoards, (uint16_t)3);
+              tma_load_4d_mc(a_dst + kABytes, &map_x2, full_bar(stage), cc * kBlockK, sx, sy, grp * kBoards, (uint16_t)3);
             else
-              tma_load_4d_mc(a_dst + kABytes + 2 * 81 * 128, &map_x1, full_bar(stage), cc * kBlockK, tap % 3 - 1, tap / 3 - 1,
-                             grp * kBoards + 2, (uint16_t)3);
+              tma_load_4d_mc(a_dst + kABytes + 2 * 81 * 128, &map_x1, full_bar(stage), cc * kBlockK, sx, sy, grp * kBoards + 2, (uint16_t)3);
           } else {
-            tma_load_4d(a_dst + kABytes, &map_x, full_bar(stage), cc * kBlockK, tap % 3 - 1, tap / 3 - 1, grp * kBoards);
+            tma_load_4d(a_dst + kABytes, &map_x, full_bar(stage), cc * kBlockK, sx, sy, grp * kBoards);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        if (++cc == kb_per_tap) { cc = 0; ++tap; }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int t = t_first; t < num_tiles; t += t_step, ++it) {
-        const int buf = it & 1;
-        const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(tempty_bar(buf), tphase ^ 1u);  // epilogue has drained this accumulator
+    // ===== MMA issuer: uniform loop, one elected lane issues the MMAs and their commits =====
+    const bool issuer = elect_one_sync();
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int t = t_first; t < num_tiles; t += t_step, ++it) {
+      const int buf = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(buf), tphase ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kTileN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kTileN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * kStageBytes;
-          const uint64_t adesc = smem_desc_k128(a_addr);
-          const uint64_t bdesc = smem_desc_k128(a_addr + kABytes);
+        const uint32_t a_addr = smem_base + stage * kStageBytes;
+        const uint64_t adesc = smem_desc_k128(a_addr);
+        const uint64_t bdesc = smem_desc_k128(a_addr + kABytes);
+        if (issuer) {
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
@@ -147,8 +199,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
           if (kCl) umma_commit_mc(empty_bar(stage), (uint16_t)3);  // both producers write into this stage
           else umma_commit(empty_bar(stage));                      // frees the smem stage when these MMAs retire
           if (kb == num_kb - 1) umma_commit(tfull_bar(buf));
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -166,48 +219,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       tc_fence_after();
       ConvEpiThread<bf16, kBoards, F> et(epi, c, Cout, B);
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * kTileN);
-      // Mask-source prefetch (data-gradient epilogue): the ReLU mask / BN-backward statistics need one
-      // activation element per accumulator. Loads are issued kPf chunks (of 16 columns) ahead of their
-      // use so ~64 independent loads per thread are in flight instead of one dependent load per column.
-      constexpr bool kMask = (F != kEpiDynamic) && (F & kEpiMask) != 0;
-      constexpr int kPf = 4, kChunks = (kBoards * 81 + 15) / 16;
-      bf16 pf[kPf + 1][16];
-      const bf16* mbase = kMask ? (const bf16*)epi.mask_src + et.index(b0, 0) : nullptr;
-      auto prefetch = [&](int ch) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = ch * 16 + i;  // boards are contiguous in memory: element (col) sits col*Cout further
-          pf[ch % (kPf + 1)][i] = (col < kBoards * 81 && col / 81 < nb_valid) ? mbase[(unsigned)col * (unsigned)Cout] : bf16(0.f);
-        }
-      };
-      if (kMask) {
-#pragma unroll
-        for (int ch = 0; ch < kPf; ++ch) prefetch(ch);
-      }
-#pragma unroll
-      for (int ch = 0; ch < kTileN / 16; ++ch) {
-        if (ch * 16 < kBoards * 81) {
-          if (kMask && ch + kPf < kChunks) prefetch(ch + kPf);
-          uint32_t r[16];
-          tmem_ld16(taddr + ch * 16, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int col = ch * 16 + i;
-            if (col < kBoards * 81) {
-              const int j = col / 81, p = col % 81;
-              if (j < nb_valid) {
-                if (p == 0) et.begin_board(b0 + j, out);
-                float ms = 0.f;
-                if (kMask) ms = __bfloat162float(pf[ch % (kPf + 1)][i]);
-                else if (F == kEpiDynamic && epi.mask_src != nullptr) ms = __bfloat162float(((const bf16*)epi.mask_src)[et.index(b0 + j, p)]);
-                et.value(j, p, __uint_as_float(r[i]), ms);
-                if (p == 80) et.board_done(j, b0 + j);
-              }
-            }
-          }
-        }
-      }
+      epilogue_tile<F>(epi, et, taddr, b0, nb_valid, Cout, out);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -220,6 +232,394 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------- fused evaluation tail (CTA-pair kernel only)
+// conv2 of a GlobalPoolBiasBlock in eval mode, everything after the convolution in the epilogue (se_resnet.py:83-98):
+//   v    = acc * scale + shift                      (folded BatchNorm 2)
+//   mean = board mean of v  -> SE MLP (C -> S -> 2C) -> (sigmoid(se_scale), se_shift) per (board, channel)
+//   out  = relu(v * sigmoid(se_scale) + se_shift + residual);   pool = (mean, max, population std)(out)
+// The accumulator is read from TMEM twice. Pass 1 sums the 81 columns of each board per thread (= channel); the 3 x 256
+// means cross the CTA pair through distributed shared memory (each thread stores its three means locally and, with
+// st.async, into the peer, crediting the peer's exchange barrier with transaction bytes — no cluster-scope fence); both CTAs then run the small MLP redundantly — each warp takes 4 hidden
+// units (W1 slices through L1), a warp-shuffle reduction per hidden unit, W2's two rows of this thread's channel in
+// registers; pass 2 applies scale / shift / residual / ReLU, stores bf16 and accumulates the global-pool statistics of
+// the stored values. Residual elements are requested kPf chunks of 16 columns ahead of their use (the first ones before
+// pass 1); TMEM reads are double-buffered in registers (chunk k+1 in flight while chunk k is consumed). Boards never mix: results do not depend on what
+// else is in the batch. This replaces se_mlp_fwd_kernel + se_apply_col_kernel<0> and two of the block's three
+// activation-tensor passes in the rollout.
+constexpr int kSeC = 256, kSeS = 16;
+struct SeTailSmem {
+  float mean[2][kBoards][kSeC];   // [tile parity][board][channel]: board means of both CTAs' channels
+  float hid[2][kBoards][kSeS];    // hidden layer of the SE MLP
+};
+struct SeTailRegs {               // per-thread constants, loaded once per CTA lifetime
+  float b1[4];                    // b1[4*lane_grp + q]
+  float b2s, b2h, sc, sh;
+};
+
+__device__ __forceinline__ void se_tail_load(const ConvEpi& epi, int c, int lane_grp, int lane, SeTailRegs& R) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) R.b1[q] = epi.se_b1[4 * lane_grp + q];
+  R.b2s = epi.se_b2[c]; R.b2h = epi.se_b2[kSeC + c];
+  R.sc = epi.scale[c]; R.sh = epi.shift[c];
+}
+
+// TMEM -> registers, two 16-column chunks in flight: the load of chunk k+1 is issued before chunk k is consumed.
+// body(r, chunk) sees compile-time chunk indices after unrolling.
+template <int NCHUNKS, typename Fn>
+__device__ __forceinline__ void tmem_pipeline(uint32_t taddr, Fn&& body) {
+  uint32_t r0[16], r1[16];
+  tmem_ld16(taddr, r0);
+#pragma unroll
+  for (int ch = 0; ch < NCHUNKS; ch += 2) {
+    tmem_ld_wait();
+    if (ch + 1 < NCHUNKS) tmem_ld16(taddr + (ch + 1) * 16, r1);
+    body(r0, ch);
+    if (ch + 1 < NCHUNKS) {
+      tmem_ld_wait();
+      if (ch + 2 < NCHUNKS) tmem_ld16(taddr + (ch + 2) * 16, r0);
+      body(r1, ch + 1);
+    }
+  }
+}
+
+// two floats -> packed bf16x2 (round to nearest even) in ONE ALU-rate instruction (F2FP); a lone cvt.rn.bf16.f32 is an F2F
+// on the quarter-rate conversion pipe. `lo` lands in bits 0..15.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// kFull: all three boards of the tile exist (every tile but possibly the last): no per-column validity predicates
+template <bool kFull>
+__device__ __forceinline__ void se_tail_tile(const ConvEpi& epi, const SeTailRegs& R, SeTailSmem* sm, uint32_t sm_addr, uint32_t se_bar,
+                                             uint32_t crank, int g, uint32_t parity, uint32_t taddr, int c, int lane_grp, int lane,
+                                             int b0, int nb_valid, bf16* __restrict__ out) {
+  constexpr int kChunks = (kBoards * 81 + 15) / 16;
+  constexpr int kPf = 3;
+  const int pb = g;   // this warp group's exchange buffers
+  // residual prefetch ring: chunk k + kPf is requested while chunk k is consumed; the first kPf chunks are requested
+  // here, before pass 1, so their latency hides under it
+  unsigned short pf[kPf + 1][16];
+  const unsigned short* rbase = (const unsigned short*)epi.res + ((size_t)b0 * 81) * kSeC + c;
+  auto prefetch = [&](int ch) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int col = ch * 16 + i;
+      if (col < kBoards * 81) pf[ch % (kPf + 1)][i] = (kFull || col / 81 < nb_valid) ? __ldg(rbase + (unsigned)col * (unsigned)kSeC) : (unsigned short)0;
+    }
+  };
+#pragma unroll
+  for (int ch = 0; ch < kPf; ++ch) prefetch(ch);
+  // ---- pass 1: board sums of the BatchNorm-2 output
+  float bs[kBoards];
+#pragma unroll
+  for (int j = 0; j < kBoards; ++j) bs[j] = 0.f;
+  tmem_pipeline<kChunks>(taddr, [&](const uint32_t(&r)[16], int chunk) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int col = chunk * 16 + i;
+      if (col < kBoards * 81) bs[col / 81] += fmaf(__uint_as_float(r[i]), R.sc, R.sh);
+    }
+  });
+  // ---- exchange the means across the pair
+  {
+    // own half: plain shared stores + a CTA-scope arrive; peer half: asynchronous DSMEM stores that credit transaction
+    // bytes to the PEER's exchange barrier (128 threads x 3 floats = 1536 bytes per tile, expected by one local thread)
+    const uint32_t own = sm_addr + (uint32_t)(((pb * kBoards) * kSeC + c) * 4);
+    const uint32_t peer = mapa_peer(own, crank ^ 1u);
+    const uint32_t peer_bar = mapa_peer(se_bar, crank ^ 1u);
+#pragma unroll
+    for (int j = 0; j < kBoards; ++j) {
+      const float m = bs[j] * (1.f / 81.f);
+      sm->mean[pb][j][c] = m;
+      st_async_f32(peer + (uint32_t)(j * kSeC * 4), m, peer_bar);
+    }
+    if (lane_grp == 0 && lane == 0) mbar_arrive_expect_tx(se_bar, (uint32_t)(kTileM * kBoards * 4));
+    else mbar_arrive(se_bar);
+    mbar_wait(se_bar, parity);
+  }
+  // ---- SE MLP, hidden layer: this warp's 4 units for the 3 boards
+  {
+    float part[4][kBoards];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < kBoards; ++j) part[q][j] = 0.f;
+    // W1 rows of this warp's 4 hidden units, [lane + 32*k] slices: 16 KB in all, L1-resident across tiles
+    const float* w1p = epi.se_w1 + (size_t)(4 * lane_grp) * kSeC + lane;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float wq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wq[q] = __ldg(w1p + q * kSeC + 32 * k);
+#pragma unroll
+      for (int j = 0; j < kBoards; ++j) {
+        const float m = sm->mean[pb][j][lane + 32 * k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) part[q][j] = fmaf(wq[q], m, part[q][j]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < kBoards; ++j) {
+        float v = part[q][j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sm->hid[pb][j][4 * lane_grp + q] = fmaxf(v + R.b1[q], 0.f);
+      }
+  }
+  named_bar_sync(1 + g, 128);   // the four warps of this epilogue group
+  float sig[kBoards], shf[kBoards];
+  {
+    // W2 rows c and C + c (16 floats each, 64 contiguous bytes: four float4 loads per row, L1 / L2 resident)
+    const float4* w2s = reinterpret_cast<const float4*>(epi.se_w2 + (size_t)c * kSeS);
+    const float4* w2h = reinterpret_cast<const float4*>(epi.se_w2 + (size_t)(kSeC + c) * kSeS);
+    float a[kBoards], b[kBoards];
+#pragma unroll
+    for (int j = 0; j < kBoards; ++j) { a[j] = R.b2s; b[j] = R.b2h; }
+#pragma unroll
+    for (int s4 = 0; s4 < kSeS / 4; ++s4) {
+      const float4 ws = __ldg(w2s + s4), wh = __ldg(w2h + s4);
+#pragma unroll
+      for (int j = 0; j < kBoards; ++j) {
+        const float4 h = *reinterpret_cast<const float4*>(&sm->hid[pb][j][4 * s4]);
+        a[j] = fmaf(ws.x, h.x, a[j]); a[j] = fmaf(ws.y, h.y, a[j]); a[j] = fmaf(ws.z, h.z, a[j]); a[j] = fmaf(ws.w, h.w, a[j]);
+        b[j] = fmaf(wh.x, h.x, b[j]); b[j] = fmaf(wh.y, h.y, b[j]); b[j] = fmaf(wh.z, h.z, b[j]); b[j] = fmaf(wh.w, h.w, b[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kBoards; ++j) { sig[j] = 1.f / (1.f + __expf(-a[j])); shf[j] = b[j]; }
+  }
+  // ---- pass 2: scale / shift / residual / ReLU, store, global-pool statistics of the stored values.
+  // Columns go in pairs so that the bf16 rounding is one packed conversion per two outputs.
+  float mx = -INFINITY, k0 = 0.f, ds = 0.f, dss = 0.f;
+  unsigned short* optr = reinterpret_cast<unsigned short*>(out);
+  auto finish_value = [&](int col, uint32_t bits) {   // bits: the stored bf16 in the low half
+    const int j = col / 81, p = col % 81;
+    if (kFull || j < nb_valid) {
+      if (p == 0) { optr = reinterpret_cast<unsigned short*>(out) + ((size_t)(b0 + j) * 81) * kSeC + c; mx = -INFINITY; ds = 0.f; dss = 0.f; }
+      optr[(unsigned)p * (unsigned)kSeC] = (unsigned short)bits;
+      const float rr = __uint_as_float(bits << 16);
+      mx = fmaxf(mx, rr);
+      if (p == 0) k0 = rr;
+      const float d = rr - k0;   // shifted data: mean = k0 + ds / 81, variance without cancellation
+      ds += d;
+      dss = fmaf(d, d, dss);
+      if (p == 80) {
+        const float dm = ds * (1.f / 81.f);
+        const float mean = k0 + dm;
+        const float sd = sqrtf(fmaxf(dss * (1.f / 81.f) - dm * dm, 0.f));
+        float* pr = epi.pool + (size_t)(b0 + j) * 3 * kSeC;
+        pr[c] = mean; pr[kSeC + c] = mx; pr[2 * kSeC + c] = sd;
+        if (epi.pool_bf) {
+          bf16* pq = (bf16*)epi.pool_bf + (size_t)(b0 + j) * 3 * kSeC;
+          pq[c] = __float2bfloat16_rn(mean); pq[kSeC + c] = __float2bfloat16_rn(mx); pq[2 * kSeC + c] = __float2bfloat16_rn(sd);
+        }
+      }
+    }
+  };
+  tmem_pipeline<kChunks>(taddr, [&](const uint32_t(&r)[16], int chunk) {
+    if (chunk + kPf < kChunks) prefetch(chunk + kPf);
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const int col = chunk * 16 + i;
+      if (col < kBoards * 81) {
+        const int j0 = col / 81, j1 = (col + 1) / 81;
+        const float v0 = fmaf(__uint_as_float(r[i]), R.sc, R.sh);
+        const float o0 = fmaxf(fmaf(v0, sig[j0], shf[j0]) + __uint_as_float((uint32_t)pf[chunk % (kPf + 1)][i] << 16), 0.f);
+        float o1 = 0.f;
+        if (col + 1 < kBoards * 81) {
+          const float v1 = fmaf(__uint_as_float(r[i + 1]), R.sc, R.sh);
+          o1 = fmaxf(fmaf(v1, sig[j1], shf[j1]) + __uint_as_float((uint32_t)pf[chunk % (kPf + 1)][i + 1] << 16), 0.f);
+        }
+        const uint32_t pk = pack_bf16x2(o0, o1);
+        finish_value(col, pk & 0xffffu);
+        if (col + 1 < kBoards * 81) finish_value(col + 1, pk >> 16);
+      }
+    }
+  });
+}
+
+// ---------------------------------------------------------------- forward / dgrad kernel, CTA pair (cta_group::2)
+// The two SMs of a TPC compute ONE 256-channel x 3-board tile with M = 256 UMMAs: each CTA stages its own 128 weight
+// rows (A, 16 KB per K block) and HALF of the pixel columns (B, 128 rows = 16 KB), the tensor cores of both SMs read
+// both halves. Per stage a CTA holds 32 KB instead of 47 KB -> 6 stages in the same 192 KB, and the L2 -> SM operand
+// bytes per FLOP drop by a third (the single-CTA kernel's MMA issuer stalls on the full barriers, profiles/).
+// The 256-column tile is split at column 128, which is NOT a board boundary (81 pixels per board): CTA 0 takes board 0,
+// rows 0-4 of board 1 and the first 2 pixels of its row 5; CTA 1 the other 7 pixels of that row, rows 6-8 and board 2
+// (115 columns; the last 13 are never written and never read back) — five TMA box shapes, each shifted by the tap.
+// One thread of the leader CTA issues every MMA; both producers credit the leader's full barrier; tcgen05.commit
+// multicasts the stage release / accumulator-ready arrivals to both CTAs; the epilogue warps of both CTAs (each owns
+// its CTA's 128 TMEM lanes = output channels) release the accumulator on the leader's barrier.
+constexpr int kBHalfBytes = 128 * kBlockK * 2;          // 16 KB
+constexpr int kStageBytes2 = kABytes + kBHalfBytes;     // 32 KB
+// Warp roles of the pair kernel (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue as
+// TWO groups of four warps that take alternate tiles (group g always drains accumulator buffer g). One group alone is the
+// pacing stage of the single-CTA kernel: with one epilogue warp per scheduler every dependent instruction exposes its
+// latency (ncu: 4.5-6 cycles per issued instruction), and the epilogue of a tile takes about as long as its MMAs. Two
+// groups give each tile's epilogue two MMA periods and every scheduler two warps to interleave.
+constexpr int kThreads2 = 320;
+template <bool kSeTail> struct PairCfg {
+  static constexpr int kStages = 6;
+  static constexpr int kRingBytes = kStages * kStageBytes2;
+  static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + (kSeTail ? (int)sizeof(SeTailSmem) : 0);
+};
+constexpr uint32_t kTxBytes2 = 2u * kABytes + 128u * 128u + 115u * 128u;   // both CTAs' boxes (OOB-filled elements count)
+constexpr uint32_t kIdescF16M256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+struct PairMaps { CUtensorMap full, rows5, x2, x7, rows3; };
+
+template <int F, bool kSeTail>
+__global__ void __launch_bounds__(kThreads2, 1)
+conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ PairMaps mx,
+                   bf16* __restrict__ out, int B, int Cin, int Cout, int num_groups, ConvEpi epi) {
+  constexpr int kStages2 = PairCfg<kSeTail>::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages2 * kStageBytes2;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages2 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kStages2 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kStages2 + 2 + b); };
+  const uint32_t holder = bar_base + 8u * (2 * kStages2 + 4);
+  auto se_bar = [&](int g) { return bar_base + 8u * (2 * kStages2 + 5 + g); };   // means exchange per epilogue group (fused tail)
+  const uint32_t se_sm_addr = bar_base + 256u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages2 * kStageBytes2 + 8 * (2 * kStages2 + 4));
+  SeTailSmem* se_sm = reinterpret_cast<SeTailSmem*>(smem_gen + kStages2 * kStageBytes2 + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_per_tap = Cin / kBlockK;
+  const int num_kb = 9 * kb_per_tap;
+  const uint32_t crank = cluster_ctarank();
+  const int n_pairs = Cout / 256;                       // channel pairs per board group
+  const int num_tiles = num_groups * n_pairs;
+  const int t_first = (int)(blockIdx.x >> 1), t_step = (int)(gridDim.x >> 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }   // 4 epilogue warps x 2 CTAs
+    if (kSeTail) { mbar_init(se_bar(0), 128); mbar_init(se_bar(1), 128); }   // the 128 threads of a group (+ the peer's bytes)
+    fence_barrier_init();
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&mx.full);
+  }
+  if (warp == 1) {  // both CTAs of the pair allocate together: all 512 columns (two 256-column accumulators) in each
+    tmem_alloc_2cta(holder, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything is signalled at them
+  tc_fence_after();
+  const uint32_t tmem_base = *holder_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): the warp runs the loop uniformly, one elected lane issues =====
+    const bool issuer = elect_one_sync();
+    int stage = 0; uint32_t phase = 0;
+    for (int t = t_first; t < num_tiles; t += t_step) {
+      const int grp = t / n_pairs, ct = (t % n_pairs) * 2 + (int)crank;
+      const int b0 = grp * kBoards;
+      int tap = 0, cc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int sx = tap % 3 - 1, sy = tap / 3 - 1, c0 = cc * kBlockK;
+        mbar_wait(empty_bar(stage), phase ^ 1u);          // this CTA's copy of the stage has been consumed by the pair's MMAs
+        const uint32_t a_dst = smem_base + stage * kStageBytes2;
+        const uint32_t b_dst = a_dst + kABytes;
+        if (issuer) {
+          if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), kTxBytes2);
+          tma_load_2d_2cta(a_dst, &map_w, full_bar(stage), kb * kBlockK, ct * kTileM);
+          if (crank == 0) {
+            tma_load_4d_2cta(b_dst, &mx.full, full_bar(stage), c0, sx, sy, b0);                       // board 0: columns 0..80
+            tma_load_4d_2cta(b_dst + 81 * 128, &mx.rows5, full_bar(stage), c0, sx, sy, b0 + 1);       // board 1 rows 0..4: 81..125
+            tma_load_4d_2cta(b_dst + 126 * 128, &mx.x2, full_bar(stage), c0, sx, 5 + sy, b0 + 1);     // row 5, x = 0..1: 126..127
+          } else {
+            tma_load_4d_2cta(b_dst, &mx.x7, full_bar(stage), c0, 2 + sx, 5 + sy, b0 + 1);             // row 5, x = 2..8: 128..134
+            tma_load_4d_2cta(b_dst + 7 * 128, &mx.rows3, full_bar(stage), c0, sx, 6 + sy, b0 + 1);    // rows 6..8: 135..161
+            tma_load_4d_2cta(b_dst + 34 * 128, &mx.full, full_bar(stage), c0, sx, sy, b0 + 2);        // board 2: 162..242
+          }
+        }
+        if (++cc == kb_per_tap) { cc = 0; ++tap; }
+        if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one elected lane of the leader CTA's warp 1 for the pair (uniform loop) =====
+    if (crank == 0) {
+      const bool issuer = elect_one_sync();
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int t = t_first; t < num_tiles; t += t_step, ++it) {
+        const int buf = it & 1;
+        const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), tphase ^ 1u);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kTileN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);      // both CTAs' boxes of this stage have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * kStageBytes2;
+          const uint64_t adesc = smem_desc_k128(a_addr);
+          const uint64_t bdesc = smem_desc_k128(a_addr + kABytes);
+          if (issuer) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16_2cta(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdescF16M256, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta_mc(empty_bar(stage), (uint16_t)3);   // frees the stage in both CTAs when these MMAs retire
+            if (kb == num_kb - 1) umma_commit_2cta_mc(tfull_bar(buf), (uint16_t)3);
+          }
+          __syncwarp();
+          if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): thread = output channel of this CTA's half; group g takes tiles it = g, g + 2, ... =====
+    const int lane_grp = warp & 3;        // TMEM lanes 32*lane_grp .. +31 are the ones this warp may read
+    const int g = (warp - 2) >> 2;        // epilogue group 0 / 1 = accumulator buffer
+    SeTailRegs se_regs;
+    if (kSeTail) se_tail_load(epi, (int)crank * kTileM + lane_grp * 32 + lane, lane_grp, lane, se_regs);
+    int it = g;
+    for (int t = t_first + g * t_step; t < num_tiles; t += 2 * t_step, it += 2) {
+      const int grp = t / n_pairs, ct = (t % n_pairs) * 2 + (int)crank;
+      const int buf = g;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      const int c = ct * kTileM + lane_grp * 32 + lane;
+      const int b0 = grp * kBoards;
+      const int nb_valid = min(kBoards, B - b0);
+      mbar_wait(tfull_bar(buf), tphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * kTileN);
+      if (kSeTail) {
+        if (nb_valid == kBoards)
+          se_tail_tile<true>(epi, se_regs, se_sm, se_sm_addr, se_bar(g), crank, g, tphase, taddr, c, lane_grp, lane, b0, nb_valid, out);
+        else
+          se_tail_tile<false>(epi, se_regs, se_sm, se_sm_addr, se_bar(g), crank, g, tphase, taddr, c, lane_grp, lane, b0, nb_valid, out);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tempty_bar(buf));
+      } else {
+        ConvEpiThread<bf16, kBoards, F> et(epi, c, Cout, B);
+        epilogue_tile<F>(epi, et, taddr, b0, nb_valid, Cout, out);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tempty_bar(buf));
+        et.finish(nb_valid);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still read this CTA's operands / signal its barriers until it is done too
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
   }
 }
 
@@ -461,6 +861,43 @@ int make_act_map(CUtensorMap* m, const void* x, int B, int C, int boards_per_box
   return KB_OK;
 }
 
+int make_act_box_map(CUtensorMap* m, const void* x, int B, int C, int bx, int by, int bb) {
+  EncodeTiledFn enc = get_encode_fn();
+  KB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)C, 9, 9, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * 9, (cuuint64_t)C * 2 * 81};
+  const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bb};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KB_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation box %dx%dx%d) failed: %d", bx, by, bb, (int)r);
+  return KB_OK;
+}
+
+template <int F, bool kSeTail = false>
+int launch_pair(const CUtensorMap& mw, const PairMaps& mx, bf16* out, int B, int Cin, int Cout, int groups,
+                const ConvEpi& epi, int grid, cudaStream_t st) {
+  constexpr int smem = PairCfg<kSeTail>::kSmemBytes;
+  static bool attr_set = false;  // per instantiation; idempotent
+  if (!attr_set) {
+    KB_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc2_kernel<F, kSeTail>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributePriority;
+  at[1].val.priority = conv_priority();
+  cfg.attrs = at; cfg.numAttrs = conv_priority() != 0 ? 2 : 1;
+  KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<F, kSeTail>, mw, mx, out, B, Cin, Cout, groups, epi));
+  kb_count_launch();
+  return KB_OK;
+}
+
 template <int F>
 int launch_fwd(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& mx2, const CUtensorMap& mx1, bf16* out, int B,
                int Cin, int Cout, int num_tiles, const ConvEpi& epi, int grid, bool cluster, cudaStream_t st) {
@@ -489,14 +926,69 @@ int launch_fwd(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& 
 
 }  // namespace
 
+int kbk_conv3x3_se_tail_supported(int Cin, int Cout, int S, int dtype) {
+  return dtype == KB_BF16 && Cout == kSeC && S == kSeS && Cin % kBlockK == 0 && Cin >= kBlockK;
+}
+
 int kbk_conv3x3_tc_supported(int Cin, int Cout, int dtype) {
   return dtype == KB_BF16 && Cin % kBlockK == 0 && Cout % kTileM == 0 && Cin >= kBlockK;
 }
 
-int kbk_conv3x3_tc(const void* in, const void* w, void* out, int B, int Cin, int Cout, const ConvEpi& epi, int num_sms,
-                   cudaStream_t st) {
+// mode: 0 = automatic (CTA-pair kernel whenever Cout is a multiple of 256; KB_CONV_2CTA=0 disables), 1 = single-CTA
+// kernel, 2 = CTA-pair kernel (error if the shape does not allow it)
+int kbk_conv3x3_tc_mode(const void* in, const void* w, void* out, int B, int Cin, int Cout, const ConvEpi& epi, int num_sms,
+                        int mode, cudaStream_t st) {
   KB_CHECK_ARG(kbk_conv3x3_tc_supported(Cin, Cout, KB_BF16), "conv3x3_tc: unsupported shape Cin=%d Cout=%d", Cin, Cout);
   if (B == 0) return KB_OK;
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* e = getenv("KB_CONV_2CTA"); pair_env = (e && e[0] == '0') ? 0 : 1; }
+  const bool pair_ok = Cout % 256 == 0;
+  KB_CHECK_ARG(mode != 2 || pair_ok, "conv3x3_tc: the CTA-pair kernel needs Cout %% 256 == 0 (got %d)", Cout);
+  if (mode == 2 || (mode == 0 && pair_env && pair_ok)) {
+    CUtensorMap mw;
+    PairMaps pm;
+    if (int r = make_weight_map(&mw, w, Cout, 9 * Cin)) return r;
+    if (int r = make_act_box_map(&pm.full, in, B, Cin, 9, 9, 1)) return r;
+    if (int r = make_act_box_map(&pm.rows5, in, B, Cin, 9, 5, 1)) return r;
+    if (int r = make_act_box_map(&pm.x2, in, B, Cin, 2, 1, 1)) return r;
+    if (int r = make_act_box_map(&pm.x7, in, B, Cin, 7, 1, 1)) return r;
+    if (int r = make_act_box_map(&pm.rows3, in, B, Cin, 9, 3, 1)) return r;
+    const int groups = kb_ceil_div(B, kBoards);
+    const int tiles = groups * (Cout / 256);
+    if (num_sms <= 0) num_sms = 148;
+    const int grid = 2 * (tiles < num_sms / 2 ? tiles : num_sms / 2);
+    bf16* o = (bf16*)out;
+    if (epi.res != nullptr) {   // fused evaluation tail
+      KB_CHECK_ARG(Cout == kSeC && epi.scale && epi.shift && epi.se_w1 && epi.se_b1 && epi.se_w2 && epi.se_b2 && epi.pool,
+                   "conv3x3_tc: the fused SE tail needs Cout == 256, folded BatchNorm and all four SE tensors");
+      return launch_pair<0, true>(mw, pm, o, B, Cin, Cout, groups, epi, grid, st);
+    }
+    const int f = conv_epi_features(epi);
+#define KB_PAIR(FF) return launch_pair<FF>(mw, pm, o, B, Cin, Cout, groups, epi, grid, st)
+    switch (f) {
+      case 0: KB_PAIR(0);
+      case kEpiSum | kEpiSumSq: KB_PAIR(kEpiSum | kEpiSumSq);
+      case kEpiSum | kEpiSumSq | kEpiBoard: KB_PAIR(kEpiSum | kEpiSumSq | kEpiBoard);
+      case kEpiAffine | kEpiRelu | kEpiGbias: KB_PAIR(kEpiAffine | kEpiRelu | kEpiGbias);
+      case kEpiAffine | kEpiRelu: KB_PAIR(kEpiAffine | kEpiRelu);
+      case kEpiAffine: KB_PAIR(kEpiAffine);
+      case kEpiAffine | kEpiRelu | kEpiPool: KB_PAIR(kEpiAffine | kEpiRelu | kEpiPool);
+      case kEpiAffine | kEpiBoard: KB_PAIR(kEpiAffine | kEpiBoard);
+      default: break;   // rarely used feature sets stay on the single-CTA kernel
+    }
+#undef KB_PAIR
+    KB_CHECK_ARG(mode != 2, "conv3x3_tc: epilogue feature set %d is not instantiated for the CTA-pair kernel", f);
+  }
+  return kbk_conv3x3_tc_single(in, w, out, B, Cin, Cout, epi, num_sms, st);
+}
+
+int kbk_conv3x3_tc(const void* in, const void* w, void* out, int B, int Cin, int Cout, const ConvEpi& epi, int num_sms,
+                   cudaStream_t st) {
+  return kbk_conv3x3_tc_mode(in, w, out, B, Cin, Cout, epi, num_sms, 0, st);
+}
+
+int kbk_conv3x3_tc_single(const void* in, const void* w, void* out, int B, int Cin, int Cout, const ConvEpi& epi, int num_sms,
+                          cudaStream_t st) {
   CUtensorMap mw, mx, mx2, mx1;
   if (int r = make_weight_map(&mw, w, Cout, 9 * Cin)) return r;
   if (int r = make_act_map(&mx, in, B, Cin, kBoards)) return r;

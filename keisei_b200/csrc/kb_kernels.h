@@ -30,6 +30,11 @@ int kbk_pack_batched(const PackJob* jobs, int n_jobs, cudaStream_t st);
 
 // ---- conv_tc.cu (tcgen05 / TMEM / TMA, bf16) ----
 int kbk_conv3x3_tc_supported(int Cin, int Cout, int dtype);
+int kbk_conv3x3_se_tail_supported(int Cin, int Cout, int S, int dtype);   // fused evaluation tail in the CTA-pair kernel
+int kbk_conv3x3_tc_mode(const void* in, const void* w, void* out, int B, int Cin, int Cout, const ConvEpi& epi,
+                        int num_sms, int mode, cudaStream_t st);
+int kbk_conv3x3_tc_single(const void* in, const void* w, void* out, int B, int Cin, int Cout, const ConvEpi& epi,
+                          int num_sms, cudaStream_t st);
 int kbk_conv3x3_tc(const void* in, const void* w, void* out, int B, int Cin, int Cout, const ConvEpi& epi,
                    int num_sms, cudaStream_t st);
 long long kbk_conv3x3_wgrad_tc_ws_bytes(int Cin, int Cout, int num_sms);

@@ -355,6 +355,10 @@ extern "C" int kb_seresnet_forward_sync(const kb_seresnet_desc* d, const void* c
   static int no_se_apply = -1;
   if (no_se_apply < 0) { const char* e = getenv("KB_NO_SE_APPLY"); no_se_apply = (e && e[0] == '1') ? 1 : 0; }
   const bool fuse_se = ltc && !no_se_apply && kbk_se_apply_supported(C, m.S);
+  // evaluation: the whole block tail (SE MLP, scale / shift, residual, ReLU, pool statistics) rides in conv2's epilogue
+  static int fused_tail_env = -1;
+  if (fused_tail_env < 0) { const char* e = getenv("KB_FUSED_TAIL"); fused_tail_env = (e && e[0] == '0') ? 0 : 1; }
+  const bool fuse_tail = !training && ltc && fused_tail_env && B >= 3 && kbk_conv3x3_se_tail_supported(C, C, m.S, dtype);
   bool pool_bf_ready = false;  // the producing apply kernel also writes the bf16 copy of the pool statistics
   // ---- residual tower ----
   for (int i = 0; i < m.nb; ++i) {
@@ -391,6 +395,18 @@ extern "C" int kb_seresnet_forward_sync(const kb_seresnet_desc* d, const void* c
       ConvEpi e = epi_base();
       e.scale = wp.bn_a(l1); e.shift = wp.bn_b(l1); e.relu = 1; e.gbias = w.g;
       KB_TRY(conv3x3(m, x_cur, wp.wf(i, 0), w.ey1, C, C, e, use_tc, num_sms, st));
+      if (fuse_tail) {
+        void* xo = (x_cur == w.ea) ? w.eb : w.ea;
+        float* pn = (pool_cur == w.epool_a) ? w.epool_b : w.epool_a;
+        ConvEpi e2 = epi_base();
+        e2.scale = wp.bn_a(l2); e2.shift = wp.bn_b(l2); e2.res = x_cur;
+        e2.se_w1 = P(pi_blk(i, 10)); e2.se_b1 = P(pi_blk(i, 11)); e2.se_w2 = P(pi_blk(i, 12)); e2.se_b2 = P(pi_blk(i, 13));
+        e2.pool = pn; e2.pool_bf = w.pool_bf;
+        KB_TRY(kbk_conv3x3_tc_mode(w.ey1, wp.wf(i, 1), xo, B, C, C, e2, num_sms, 2, st));
+        pool_bf_ready = true;
+        x_cur = xo; pool_cur = pn;
+        continue;
+      }
       ConvEpi e2 = epi_base();
       e2.scale = wp.bn_a(l2); e2.shift = wp.bn_b(l2); e2.board_sum = bw.bmean2; e2.board_scale = 1.f / 81.f;
       e2.board_bf = (ltc && !fuse_se) ? w.sein_bf : nullptr;

@@ -43,9 +43,9 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-__global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* buf, int n, PeerPtrs pp, int rank, int world,
-                                                                unsigned long long seq, int n_slots, long long slot_doubles,
-                                                                unsigned long long timeout_ns, unsigned long long* status) {
+__device__ __forceinline__ void peer_exchange(double* buf, int n, const PeerPtrs& pp, int rank, int world,
+                                              unsigned long long seq, int n_slots, long long slot_doubles,
+                                              unsigned long long timeout_ns, unsigned long long* status) {
   __shared__ int timed_out;
   const int slot = (int)(seq % (unsigned long long)n_slots);
   const size_t row = ((size_t)slot * world + rank) * (size_t)slot_doubles;
@@ -84,6 +84,21 @@ __global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* buf, in
     for (int r = 0; r < world; ++r) s += __ldcg(mine + (size_t)r * slot_doubles + i);
     buf[i] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : s;
   }
+}
+
+__global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* buf, int n, PeerPtrs pp, int rank, int world,
+                                                                unsigned long long seq, int n_slots, long long slot_doubles,
+                                                                unsigned long long timeout_ns, unsigned long long* status) {
+  peer_exchange(buf, n, pp, rank, world, seq, n_slots, slot_doubles, timeout_ns, status);
+}
+
+// Single-GPU emulation for tests: ONE cooperative launch whose block r plays rank r on that rank's data and buffers.
+// (Ranks emulated as separate launches that wait on one another are not guaranteed to run at the same time.)
+struct EmuArgs { double* buf[kMaxWorld]; PeerPtrs pp[kMaxWorld]; unsigned long long* status[kMaxWorld]; };
+__global__ void __launch_bounds__(256) peer_allreduce_emulate_kernel(EmuArgs a, int n, int world, unsigned long long seq, int n_slots,
+                                                                    long long slot_doubles, unsigned long long timeout_ns) {
+  const int r = blockIdx.x;
+  peer_exchange(a.buf[r], n, a.pp[r], r, world, seq, n_slots, slot_doubles, timeout_ns, a.status[r]);
 }
 
 }  // namespace
@@ -162,6 +177,36 @@ extern "C" int kb_peer_allreduce_f64(void* buf, long long n, const kb_peer_ctx* 
   peer_allreduce_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((double*)buf, (int)n, pp, ctx->rank, ctx->world, seq, ctx->n_slots,
                                                                 ctx->slot_doubles, timeout_ns, ctx->status);
   KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+extern "C" int kb_peer_allreduce_emulate(void* const* bufs, long long n, kb_peer_ctx* const* ctxs, int world, kb_stream_t stream) {
+  KB_CHECK_ARG(bufs && ctxs && world >= 1 && world <= kMaxWorld, "kb_peer_allreduce_emulate: bad arguments");
+  EmuArgs a; memset(&a, 0, sizeof(a));
+  const kb_peer_ctx* c0 = ctxs[0];
+  KB_CHECK_ARG(c0 && n >= 1 && n <= c0->slot_doubles && c0->n_slots >= 2, "kb_peer_allreduce_emulate: bad context / size");
+  const size_t data_doubles = (size_t)c0->n_slots * world * (size_t)c0->slot_doubles;
+  for (int r = 0; r < world; ++r) {
+    const kb_peer_ctx* c = ctxs[r];
+    KB_CHECK_ARG(c && c->world == world && c->rank == r && c->seq == c0->seq && c->n_slots == c0->n_slots && c->slot_doubles == c0->slot_doubles,
+                 "kb_peer_allreduce_emulate: context %d does not describe rank %d of %d", r, r, world);
+    a.buf[r] = (double*)bufs[r];
+    a.status[r] = c->status;
+    for (int q = 0; q < world; ++q) {
+      KB_CHECK_ARG(c->peers[q] != nullptr, "kb_peer_allreduce_emulate: peer %d of rank %d is not mapped", q, r);
+      a.pp[r].data[q] = (double*)c->peers[q];
+      a.pp[r].flags[q] = (unsigned long long*)((double*)c->peers[q] + data_doubles);
+    }
+  }
+  int nn = (int)n, w = world, slots = c0->n_slots;
+  unsigned long long seq = c0->seq;
+  long long sd = c0->slot_doubles;
+  unsigned long long timeout_ns = (unsigned long long)(c0->timeout_ms > 0 ? c0->timeout_ms : 120000) * 1000000ull;
+  void* args[] = {&a, &nn, &w, &seq, &slots, &sd, &timeout_ns};
+  KB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)peer_allreduce_emulate_kernel, dim3((unsigned)world), dim3(256), args, 0,
+                                            (cudaStream_t)stream));
+  kb_count_launch();
+  for (int r = 0; r < world; ++r) ctxs[r]->seq += 1ull;
   return KB_OK;
 }
 

@@ -41,6 +41,7 @@ _lib.register_signature("kb_seresnet_backward_sync", c_int, [_P, _P, _P, c_int, 
                                                               _P, _P, _P, c_int, c_int, _P, _P, c_int, _P])
 _lib.register_signature("kb_conv3x3_forward", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P,
                                                        _P, _P, _P, c_int, _P])
+_lib.register_signature("kb_conv3x3_se_tail", c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, _P])
 _lib.register_signature("kb_conv3x3_wgrad", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_longlong, c_int, _P])
 _lib.register_signature("kb_conv3x3_wgrad_ws_bytes", c_longlong, [c_int, c_int, c_int])
 _lib.register_signature("kb_pack_conv_weight", c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P])
@@ -405,6 +406,27 @@ def conv3x3(x: torch.Tensor, wf: torch.Tensor, backend: int = 0, scale=None, shi
             _lib.ptr(pool), sm_count(dev), _lib.stream_ptr(dev))
     _lib.check(rc, "kb_conv3x3_forward")
     return out, sums, bm, pool
+
+
+@torch.no_grad()
+def conv3x3_se_tail(x: torch.Tensor, wf: torch.Tensor, scale, shift, res: torch.Tensor, w1, b1, w2, b2):
+    """Evaluation-mode conv2 + block tail in ONE kernel (csrc/conv_tc.cu, CTA-pair kernel with the fused SE epilogue).
+    x, res (B,81,C) bf16; wf (256,9,C) bf16; scale/shift (256,) folded BatchNorm; SE weights fp32.
+    Returns (out (B,81,256) bf16, pool (B,768) fp32, pool_bf16 (B,768))."""
+    B, _, Cin = x.shape
+    Cout, S = wf.shape[0], w1.shape[0]
+    dev = x.device
+    out = torch.empty((B, 81, Cout), dtype=torch.bfloat16, device=dev)
+    pool = torch.empty((B, 3 * Cout), dtype=torch.float32, device=dev)
+    pool_bf = torch.empty((B, 3 * Cout), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().kb_conv3x3_se_tail(
+            x.contiguous().data_ptr(), wf.contiguous().data_ptr(), out.data_ptr(), B, Cin, Cout, scale.contiguous().data_ptr(),
+            shift.contiguous().data_ptr(), res.contiguous().data_ptr(), w1.contiguous().data_ptr(), b1.contiguous().data_ptr(),
+            w2.contiguous().data_ptr(), b2.contiguous().data_ptr(), S, pool.data_ptr(), pool_bf.data_ptr(), sm_count(dev),
+            _lib.stream_ptr(dev))
+    _lib.check(rc, "kb_conv3x3_se_tail")
+    return out, pool, pool_bf
 
 
 @torch.no_grad()

@@ -192,10 +192,12 @@ class SEResNetModel(KataGoBaseModel):
         self.graph_max_batch: int = int(os.environ.get("KB_GRAPH_MAX_BATCH", "4096"))
         self.graph_replayed_kernels: int = 0  # library kernels launched through graph replays (kb_launch_count sees captures only)
         self.bn_sync = None                  # distributed.BatchNormSync: global-batch BatchNorm statistics (SyncBatchNorm)
-        # graph-replayed rollout batches of at least this many boards run as two half batches on two captured branches:
-        # boards are independent in eval mode, so one half's HBM-bound block tails execute under the other half's
-        # tensor-bound convolutions (0 disables; KB_ROLLOUT_SPLIT_MIN overrides)
-        self.rollout_split_min: int = int(os.environ.get("KB_ROLLOUT_SPLIT_MIN", "2048"))
+        # graph-replayed rollout batches of at least this many boards can run as two half batches on two captured
+        # branches (boards are independent in eval mode): one half's HBM-bound block tails then execute under the other
+        # half's tensor-bound convolutions. Off by default (0) since the block tail is fused into conv2's epilogue for the
+        # 256-channel network (csrc/conv_tc.cu, fused SE tail) and no separate tail kernels are left to overlap; it still
+        # pays when KB_FUSED_TAIL=0 or for widths the fused tail does not cover (KB_ROLLOUT_SPLIT_MIN overrides)
+        self.rollout_split_min: int = int(os.environ.get("KB_ROLLOUT_SPLIT_MIN", "0"))
         self.rollout_split_ways: int = int(os.environ.get("KB_ROLLOUT_SPLIT_WAYS", "2"))   # number of parallel branches
 
     # ---- kernel plumbing ---------------------------------------------------------------------

@@ -116,3 +116,82 @@ def test_linear_tc(M, K, N):
     assert rel(yf.cpu().numpy(), want.numpy()) < 2e-3
     assert rel(yb[:, :N].float().cpu().numpy(), want.numpy()) < 1e-2
     assert torch.all(yb[:, N:] == 0)  # K padding of the consumer layer is valid
+
+
+@pytest.mark.parametrize("B,Cin,Cout", [(3, 64, 256), (4, 256, 256), (5, 256, 256), (7, 128, 256), (301, 256, 256), (50, 256, 512)])
+def test_conv3x3_cta_pair_kernel_plain_and_ragged(B, Cin, Cout):
+    """cta_group::2 kernel (backend 3): M = 256 UMMAs over a CTA pair, the 256 pixel columns split at column 128 (inside
+    board 1) into five TMA box shapes. Every board count modulo 3 and the partial last group are exercised."""
+    x, w, want = _case(B, Cin, Cout, 1000 + B + Cin)
+    wf = model_ops.pack_conv_weight(w.float().to(DEV), torch.bfloat16)
+    out, *_ = model_ops.conv3x3(nhwc(x).to(DEV), wf, backend=3)
+    torch.cuda.synchronize()
+    got = nchw(out.float().cpu())
+    assert rel(got.numpy(), want.numpy()) < 1e-2
+    for b in range(min(B, 6)):                                   # per board: a wrong box placement breaks single boards
+        assert rel(got[b].numpy(), want[b].numpy()) < 1e-2, b
+    assert rel(got[-1].numpy(), want[-1].numpy()) < 1e-2
+    assert rel(got[:, :, 5, :].numpy(), want[:, :, 5, :].numpy()) < 1e-2   # the row the column split runs through
+    # bit-identical to the single-CTA kernel: same operands, same K order, fp32 accumulation in the same sequence
+    out1, *_ = model_ops.conv3x3(nhwc(x).to(DEV), wf, backend=2)
+    assert torch.equal(out, out1)
+
+
+def test_conv3x3_cta_pair_kernel_fused_epilogues_match_single_cta():
+    B, Cin, Cout = 11, 256, 256
+    x, w, _ = _case(B, Cin, Cout, 77)
+    g = torch.Generator().manual_seed(78)
+    sc, sh = (torch.rand(Cout, generator=g) + 0.5).to(DEV), torch.randn(Cout, generator=g).to(DEV)
+    gb = torch.randn(B, Cout, generator=g).to(DEV)
+    wf = model_ops.pack_conv_weight(w.float().to(DEV), torch.bfloat16)
+    xin = nhwc(x).to(DEV)
+    for kw in (dict(want_sums=True), dict(want_sums=True, want_board_mean=True),
+               dict(scale=sc, shift=sh, relu=True, gbias=gb), dict(scale=sc, shift=sh, relu=True, want_pool=True),
+               dict(scale=sc, shift=sh, want_board_mean=True), dict(scale=sc, shift=sh, relu=True), dict(scale=sc, shift=sh)):
+        o1, s1, b1, p1 = model_ops.conv3x3(xin, wf, backend=2, **kw)
+        o2, s2, b2, p2 = model_ops.conv3x3(xin, wf, backend=3, **kw)
+        assert torch.equal(o1, o2), kw.keys()
+        if s1 is not None:
+            assert rel(s2.cpu().numpy(), s1.cpu().numpy()) < 1e-6     # double atomics: order differs in the last bits
+        if b1 is not None:
+            assert torch.equal(b1, b2)
+        if p1 is not None:
+            assert torch.equal(p1, p2)
+
+
+@pytest.mark.parametrize("B,Cin", [(3, 256), (4, 256), (8, 64), (301, 256)])
+def test_conv3x3_fused_se_tail_epilogue_vs_float64(B, Cin):
+    """Evaluation-mode conv2 with the whole block tail in the epilogue of the CTA-pair kernel (reference
+    se_resnet.py:79-98): folded BatchNorm, SE squeeze across the pair (DSMEM), SE MLP, scale / shift, residual, ReLU,
+    global-pool statistics — against float64 on the same bf16 inputs."""
+    C, S = 256, 16
+    g = torch.Generator().manual_seed(500 + B)
+    x = torch.randn(B, Cin, 9, 9, generator=g).bfloat16()
+    res = torch.randn(B, C, 9, 9, generator=g).bfloat16()
+    w = (torch.randn(C, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).bfloat16()
+    sc, sh = torch.rand(C, generator=g) + 0.5, 0.3 * torch.randn(C, generator=g)
+    w1, b1 = torch.randn(S, C, generator=g) / C ** 0.5, 0.1 * torch.randn(S, generator=g)
+    w2, b2 = torch.randn(2 * C, S, generator=g) / S ** 0.5, 0.1 * torch.randn(2 * C, generator=g)
+    v = F.conv2d(x.double(), w.double(), padding=1) * sc.double()[None, :, None, None] + sh.double()[None, :, None, None]
+    se = torch.relu(v.mean(dim=(2, 3)) @ w1.double().T + b1.double()) @ w2.double().T + b2.double()
+    want = torch.relu(v * torch.sigmoid(se[:, :C])[:, :, None, None] + se[:, C:, None, None] + res.double())
+    wf = model_ops.pack_conv_weight(w.float().to(DEV), torch.bfloat16)
+    n0 = model_ops._lib.launch_count()
+    out, pool, pool_bf = model_ops.conv3x3_se_tail(nhwc(x).to(DEV), wf, sc.to(DEV), sh.to(DEV), nhwc(res).to(DEV), w1.to(DEV),
+                                                   b1.to(DEV), w2.to(DEV), b2.to(DEV))
+    torch.cuda.synchronize()
+    assert model_ops._lib.launch_count() == n0 + 1           # ONE kernel
+    got = nchw(out.float().cpu())
+    assert rel(got.numpy(), want.numpy()) < 1e-2
+    for b in (0, 1, 2, B - 1):
+        assert rel(got[b].numpy(), want[b].numpy()) < 1e-2, b
+    # pool statistics are those of the STORED (bf16) block output, like the unfused kernels
+    stored = out.float().cpu().reshape(B, 81, C).double()
+    want_pool = torch.cat([stored.mean(1), stored.amax(1), stored.std(1, correction=0)], dim=1)
+    assert rel(pool.cpu().numpy(), want_pool.numpy()) < 1e-4
+    assert rel(pool_bf.float().cpu().numpy(), want_pool.numpy()) < 1e-2
+    # boards are independent: a sub-batch starting anywhere gives bit-identical rows
+    if B >= 8:
+        o2, p2, _ = model_ops.conv3x3_se_tail(nhwc(x)[4:8].contiguous().to(DEV), wf, sc.to(DEV), sh.to(DEV), nhwc(res)[4:8].contiguous().to(DEV),
+                                              w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV))
+        assert torch.equal(o2, out[4:8]) and torch.equal(p2, pool[4:8])

@@ -69,42 +69,37 @@ def _peer_handles(world: int, slot_doubles: int):
 
 
 def test_peer_memory_allreduce_kernel_three_ranks_many_rounds():
-    """kb_peer_allreduce_hook: sums in rank order, bit-identical on every rank, slots reused over many exchanges."""
+    """The NVLink peer-memory exchange kernel (csrc/peer_sync.cu): sums in rank order, bit-identical on every rank, slots
+    reused over many exchanges. The three ranks run as ONE cooperative launch (block r = rank r on its own data and
+    buffers): separate launches that spin on one another are not guaranteed to be co-resident on a single GPU."""
+    import ctypes
+    from keisei_b200 import _lib
     W, n = 3, 512
     bufs, handles = _peer_handles(W, n)
     g = torch.Generator().manual_seed(0)
     rounds = [[torch.randn(n - 7 * k, generator=g, dtype=torch.float64) for _ in range(W)] for k in range(11)]
-    got: list = [[] for _ in range(W)]
-    errors: list = []
-
-    def rank_main(r: int) -> None:
-        try:
-            torch.cuda.set_device(0)
-            with torch.cuda.stream(torch.cuda.Stream(DEV)):
-                for k in range(len(rounds)):
-                    t = rounds[k][r].to(DEV)
-                    handles[r].all_reduce_(t)
-                    got[r].append(t.cpu())
-        except BaseException as e:  # noqa: BLE001
-            errors.append(e)
-
-    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(W)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join(120)
-    assert not errors, errors
+    ctx_ptrs = (ctypes.c_void_p * W)(*[ctypes.addressof(h.ctx) for h in handles])
+    lib = _lib.load()
     for k, parts in enumerate(rounds):
+        dev_parts = [q.to(DEV) for q in parts]
+        ptrs = (ctypes.c_void_p * W)(*[t.data_ptr() for t in dev_parts])
+        _lib.check(lib.kb_peer_allreduce_emulate(ptrs, dev_parts[0].numel(), ctx_ptrs, W, torch.cuda.current_stream().cuda_stream),
+                   "kb_peer_allreduce_emulate")
+        torch.cuda.synchronize()
         want = parts[0].clone()
         for q in parts[1:]:
             want += q                      # rank order
         for r in range(W):
-            assert torch.equal(got[r][k], want), (k, r)
+            assert torch.equal(dev_parts[r].cpu(), want), (k, r)
+            handles[r].check()             # no exchange timed out
     assert all(h.ctx.seq == len(rounds) for h in handles)
     del bufs
 
 
-@pytest.mark.parametrize("kind", ["python_hook", "peer_memory"])
+# The exchange here is the host-synchronised Python hook (each "rank" thread drains its stream before the statistics are
+# summed), so no kernel ever waits for another launch. The peer-memory exchange inside the full schedule is asserted on
+# REAL multi-process runs in tests/test_multi_gpu.py (2 GPUs) and its kernel in the cooperative-launch test above.
+@pytest.mark.parametrize("kind", ["python_hook"])
 @pytest.mark.parametrize("amp", [False, True])
 def test_two_ranks_with_sync_bn_match_full_batch(amp, kind):
     torch.manual_seed(3)
