@@ -47,29 +47,47 @@ int kb_advantage_normalize(float* adv, long long n, float eps, kb_stream_t strea
 /* ---- rollout policy: keisei/training/katago_ppo.py:589-613 (also katago_loop.py:345-357, 407-418;
  *      match_utils.py:211-224): legal-count guard, mask -> softmax -> sample -> log_prob, scalar
  *      value P(W)-P(L) with optional score blend (value_adapter.py:79-96) ----
- * logits: (B, A) with row stride `row_stride` elements; mask: (B, A) uint8 contiguous.
+ * logits: (B, A) with row stride `row_stride` elements. mask + mask_kind + mask_pitch (all three policy entry points):
+ *   KB_MASK_BYTES (0): (B, A) uint8 / bool, `mask_pitch` bytes per row (the reference's buffer layout, katago_ppo.py:160);
+ *   KB_MASK_BITS  (1): bit-packed, `mask_pitch` 32-bit words per row, action i = bit (i & 31) of word i >> 5 (1,408 B instead
+ *                      of 11,259 B per row: the device-resident rollout buffer, kb_pack_mask_bits);
+ *   KB_MASK_NONE  (2): every action legal, mask may be NULL (supervised policy cross-entropy, sl/trainer.py:147-149).
  * logprob_mode 0 = float32 Categorical semantics, 1 = bfloat16-autocast semantics (eps = 2^-7).
  * forced_actions (optional, (B,) int64): report the log-prob of these instead of sampling.
  * flags[0] += rows with zero legal actions; legal_count (B,) int32. */
-int kb_policy_sample(const void* logits, int logits_dtype, long long row_stride, const uint8_t* mask,
+#define KB_MASK_BYTES 0
+#define KB_MASK_BITS 1
+#define KB_MASK_NONE 2
+int kb_policy_sample(const void* logits, int logits_dtype, long long row_stride, const void* mask,
                      const float* value_logits, const float* score_lead, float alpha, int B, int A,
                      unsigned long long seed, unsigned long long offset, int logprob_mode,
                      const long long* forced_actions, long long* actions, float* logp, float* values,
-                     int* legal_count, int* flags, kb_stream_t stream);
+                     int* legal_count, int* flags, int mask_kind, long long mask_pitch, kb_stream_t stream);
+/* (rows, A) uint8 / bool -> (rows, words) bit-packed legal masks (words * 32 >= A; padding bits are 0) */
+int kb_pack_mask_bits(const void* mask_bytes, void* bits, long long rows, int A, int words, kb_stream_t stream);
+/* One launch gathers a shuffled minibatch from the device-resident rollout storage (katago_ppo.py:829-841 does eight
+ * index-gathers): observations (rows of `obs_floats` fp32, even), bit-packed masks (`words` per row) and the per-sample
+ * scalars of rows idx[0..n_out) out of n_src stored samples. */
+int kb_gather_minibatch(const float* obs, const void* mask_bits, const long long* actions, const float* old_lp,
+                        const float* adv, const long long* cats, const float* score, const float* returns,
+                        const long long* idx, long long n_src, int n_out, int obs_floats, int words, float* o_obs,
+                        void* o_bits, long long* o_actions, float* o_old_lp, float* o_adv, long long* o_cats,
+                        float* o_score, float* o_returns, kb_stream_t stream);
 
 /* ---- update losses: keisei/training/katago_ppo.py:858-888 (NaN / zero-legal guards, masked
  *      log_softmax, gather, entropy) and :33-43 ppo_clip_loss ----
  * out2 = [policy_loss, entropy]; dlogp (B,) = d policy_loss / d new_logp; flags[0] zero-legal rows,
  * flags[1] rows with NaN raw logits. */
-int kb_ppo_policy_fwd(const void* logits, int logits_dtype, long long row_stride, const uint8_t* mask,
+int kb_ppo_policy_fwd(const void* logits, int logits_dtype, long long row_stride, const void* mask,
                       const long long* actions, const float* old_logp, const float* adv, int B, int A,
                       float clip_eps, float* new_logp, float* row_entropy, float* row_lse, float* dlogp,
-                      float* out2, int* flags, kb_stream_t stream);
+                      float* out2, int* flags, int mask_kind, long long mask_pitch, kb_stream_t stream);
 /* dlogits = g_policy[0] * d policy_loss + g_entropy[0] * d entropy, written once (zeros on illegal) */
-int kb_ppo_policy_bwd(const void* logits, int logits_dtype, long long row_stride, const uint8_t* mask,
+int kb_ppo_policy_bwd(const void* logits, int logits_dtype, long long row_stride, const void* mask,
                       const long long* actions, int B, int A, const float* row_lse,
                       const float* row_entropy, const float* dlogp, const float* g_policy,
-                      const float* g_entropy, void* dlogits, long long d_row_stride, kb_stream_t stream);
+                      const float* g_entropy, void* dlogits, long long d_row_stride, int mask_kind, long long mask_pitch,
+                      kb_stream_t stream);
 /* keisei/training/katago_ppo.py:46-57 wdl_cross_entropy_loss (ignore_index=-1, all-ignored -> 0),
  * :910-912 score MSE; value_adapter.py:98-126. out3 = [value_loss, score_loss, n_valid] */
 int kb_value_losses_fwd(const float* value_logits, const long long* cats, const float* score_pred,

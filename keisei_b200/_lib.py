@@ -29,11 +29,13 @@ _SIGS: dict[str, tuple[object, list[object]]] = {
     "kb_gae_scan": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_double, c_double, c_int, _P]),
     "kb_advantage_normalize": (c_int, [_P, c_longlong, c_float, _P]),
     "kb_policy_sample": (c_int, [_P, c_int, c_longlong, _P, _P, _P, c_float, c_int, c_int, c_ulonglong,
-                                 c_ulonglong, c_int, _P, _P, _P, _P, _P, _P, _P]),
+                                 c_ulonglong, c_int, _P, _P, _P, _P, _P, _P, c_int, c_longlong, _P]),
     "kb_ppo_policy_fwd": (c_int, [_P, c_int, c_longlong, _P, _P, _P, _P, c_int, c_int, c_float,
-                                  _P, _P, _P, _P, _P, _P, _P]),
+                                  _P, _P, _P, _P, _P, _P, c_int, c_longlong, _P]),
     "kb_ppo_policy_bwd": (c_int, [_P, c_int, c_longlong, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
-                                  c_longlong, _P]),
+                                  c_longlong, c_int, c_longlong, _P]),
+    "kb_pack_mask_bits": (c_int, [_P, _P, c_longlong, c_int, c_int, _P]),
+    "kb_gather_minibatch": (c_int, [_P] * 9 + [c_longlong, c_int, c_int, c_int] + [_P] * 8 + [_P]),
     "kb_value_losses_fwd": (c_int, [_P, _P, _P, _P, c_int, _P, _P]),
     "kb_value_losses_bwd": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "kb_peer_buffer_bytes": (c_longlong, [c_int, c_int, c_longlong]),

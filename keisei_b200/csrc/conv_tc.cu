@@ -693,43 +693,48 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
 
+  // single-issuer loops run warp-uniformly, one elected lane issues (see tc_ptx.cuh: elect_one_sync)
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int b = b_begin; b < b_end; ++b) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
+    const bool issuer = elect_one_sync();
+    const int sx = tap % 3 - 1, sy = tap / 3 - 1;
+    int stage = 0; uint32_t phase = 0;
+    for (int b = b_begin; b < b_end; ++b) {
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t a_dst = smem_base + stage * kWgStageBytes;
+      if (issuer) {
         mbar_arrive_expect_tx(full_bar(stage), (uint32_t)((kWgAGroups + b_groups) * kWgBoxBytes));
-        const uint32_t a_dst = smem_base + stage * kWgStageBytes;
 #pragma unroll
         for (int g = 0; g < kWgAGroups; ++g)
           tma_load_4d(a_dst + g * kWgGroupBytes, &map_dy, full_bar(stage), half * kTileM + g * 64, 0, 0, b);
         for (int g = 0; g < b_groups; ++g)
-          tma_load_4d(a_dst + (kWgAGroups + g) * kWgGroupBytes, &map_x, full_bar(stage), g * 64, tap % 3 - 1, tap / 3 - 1, b);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+          tma_load_4d(a_dst + (kWgAGroups + g) * kWgGroupBytes, &map_x, full_bar(stage), g * 64, sx, sy, b);
       }
+      if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // M = 128, N = Cin, A and B MN-major (bits 15, 16), fp32 accumulate, bf16 inputs
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(Cin >> 3) << 17) |
-                             ((uint32_t)(kTileM >> 4) << 24);
-      int stage = 0; uint32_t phase = 0;
-      for (int i = 0; i < nboards; ++i) {
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_base + stage * kWgStageBytes;
-        const uint64_t adesc = smem_desc_mn128(a_addr);
-        const uint64_t bdesc = smem_desc_mn128(a_addr + kWgAGroups * kWgGroupBytes);
+    const bool issuer = elect_one_sync();
+    // M = 128, N = Cin, A and B MN-major (bits 15, 16), fp32 accumulate, bf16 inputs
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(Cin >> 3) << 17) |
+                           ((uint32_t)(kTileM >> 4) << 24);
+    int stage = 0; uint32_t phase = 0;
+    for (int i = 0; i < nboards; ++i) {
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      const uint32_t a_addr = smem_base + stage * kWgStageBytes;
+      const uint64_t adesc = smem_desc_mn128(a_addr);
+      const uint64_t bdesc = smem_desc_mn128(a_addr + kWgAGroups * kWgGroupBytes);
+      if (issuer) {
 #pragma unroll
         for (int k = 0; k < kWgRows / 16; ++k) {
           // 16 pixel rows = 2048 bytes further down every group: +128 in the (addr >> 4) field
           umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (i | k) != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(stage));
-        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(done_bar);
+      __syncwarp();
+      if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
     }
+    if (issuer) umma_commit(done_bar);
   } else {
     const int lane_grp = warp & 3;
     float* dst = ws + ((size_t)blockIdx.x * Cin) * kTileM + lane_grp * 32 + lane;  // ws[cta][ci][co_local]

@@ -79,44 +79,48 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
 
+  // single-issuer loops run warp-uniformly, one elected lane issues (see tc_ptx.cuh: elect_one_sync)
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int ct = t % n_ct, mt = t / n_ct;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+    const bool issuer = elect_one_sync();
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int ct = t % n_ct, mt = t / n_ct;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t a_dst = smem_base + stage * kStageBytes;
+        if (issuer) {
           mbar_arrive_expect_tx(full_bar(stage), kABytes + kBBytes);
-          const uint32_t a_dst = smem_base + stage * kStageBytes;
           tma_load_2d(a_dst, &map_w, full_bar(stage), kb * kBlockK, ct * kTileM);
           tma_load_2d(a_dst + kABytes, &map_x, full_bar(stage), kb * kBlockK, mt * kTileN);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(tempty_bar(buf), tphase ^ 1u);
+    const bool issuer = elect_one_sync();
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(buf), tphase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kTileN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kTileN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * kStageBytes;
-          const uint64_t adesc = smem_desc_k128(a_addr);
-          const uint64_t bdesc = smem_desc_k128(a_addr + kABytes);
+        const uint32_t a_addr = smem_base + stage * kStageBytes;
+        const uint64_t adesc = smem_desc_k128(a_addr);
+        const uint64_t bdesc = smem_desc_k128(a_addr + kABytes);
+        if (issuer) {
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
             umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(stage));
           if (kb == num_kb - 1) umma_commit(tfull_bar(buf));
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {

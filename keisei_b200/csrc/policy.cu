@@ -35,27 +35,66 @@ template <> struct Vec4<bf16> {
   static constexpr int kAlign = 8;
 };
 
+// Legal-mask row in one of three storage kinds (include/keisei_b200.h: KB_MASK_*):
+//   0 bytes  — the reference's (B, A) bool tensor, one byte per action (katago_ppo.py:160)
+//   1 bits   — bit-packed, `pitch` 32-bit words per row, action i = bit (i & 31) of word (i >> 5): 1,408 B instead of
+//              11,259 B per row (device-resident buffer)
+//   2 none   — every action legal (supervised-learning policy cross-entropy, sl/trainer.py:147-149)
+template <int MK>
+struct MaskRow {
+  const uint8_t* bytes;
+  const uint32_t* words;
+  __device__ __forceinline__ MaskRow(const void* mask, long long pitch, int row) {
+    bytes = MK == 0 ? (const uint8_t*)mask + (size_t)row * (size_t)pitch : nullptr;
+    words = MK == 1 ? (const uint32_t*)mask + (size_t)row * (size_t)pitch : nullptr;
+  }
+  __device__ __forceinline__ bool get(int i) const {
+    if (MK == 2) return true;
+    if (MK == 0) return bytes[i] != 0;
+    return ((__ldg(words + (i >> 5)) >> (i & 31)) & 1u) != 0;
+  }
+  // 4 consecutive actions starting at i (i % 4 == 0) as a 4-bit set
+  __device__ __forceinline__ uint32_t get4(int i) const {
+    if (MK == 2) return 0xFu;
+    if (MK == 1) return (__ldg(words + (i >> 5)) >> (i & 31)) & 0xFu;
+    return (bytes[i] != 0 ? 1u : 0u) | (bytes[i + 1] != 0 ? 2u : 0u) | (bytes[i + 2] != 0 ? 4u : 0u) | (bytes[i + 3] != 0 ? 8u : 0u);
+  }
+};
+
 // Stage one row: s_row[i] = legal ? logit : -inf. Returns per-thread (legal count, any NaN in raw logits).
-template <typename T>
-__device__ __forceinline__ void stage_row(const T* __restrict__ lrow, const uint8_t* __restrict__ mrow,
+// Four 4-logit groups per thread are loaded before any is consumed (memory-level parallelism: the kernel is HBM-bound).
+template <typename T, int MK>
+__device__ __forceinline__ void stage_row(const T* __restrict__ lrow, const MaskRow<MK>& mrow,
                                           int A, float* s_row, int& legal, int& has_nan) {
   legal = 0; has_nan = 0;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(lrow) % Vec4<T>::kAlign) == 0);
   const int A4 = vec_ok ? (A & ~3) : 0;
-  for (int i = threadIdx.x * 4; i < A4; i += kThreads * 4) {
-    float v[4];
-    Vec4<T>::load(lrow + i, v);
+  constexpr int kUn = 4;
+  for (int base = threadIdx.x * 4; base < A4; base += kThreads * 4 * kUn) {
+    float v[kUn][4];
+    uint32_t mk[kUn];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const bool ok = mrow[i + j] != 0;
-      has_nan |= (v[j] != v[j]);
-      legal += ok;
-      s_row[i + j] = ok ? v[j] : -INFINITY;
+    for (int u = 0; u < kUn; ++u) {
+      const int i = base + u * kThreads * 4;
+      if (i < A4) { Vec4<T>::load(lrow + i, v[u]); mk[u] = mrow.get4(i); }
+    }
+#pragma unroll
+    for (int u = 0; u < kUn; ++u) {
+      const int i = base + u * kThreads * 4;
+      if (i < A4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = (mk[u] >> j) & 1u;
+          has_nan |= (v[u][j] != v[u][j]);
+          legal += ok;
+          s_row[i + j] = ok ? v[u][j] : -INFINITY;
+        }
+      }
     }
   }
   for (int i = A4 + threadIdx.x; i < A; i += kThreads) {
     const float v = kb_to_float<T>(lrow[i]);
-    const bool ok = mrow[i] != 0;
+    const bool ok = mrow.get(i);
     has_nan |= (v != v);
     legal += ok;
     s_row[i] = ok ? v : -INFINITY;
@@ -67,9 +106,9 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // ---------------------------------------------------------------------------------------------
 // Rollout: sample + log-prob + scalar value
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int MK>
 __global__ void __launch_bounds__(kThreads) policy_sample_kernel(
-    const T* __restrict__ logits, long long row_stride, const uint8_t* __restrict__ mask,
+    const T* __restrict__ logits, long long row_stride, const void* __restrict__ mask, long long mask_pitch,
     const float* __restrict__ value_logits, const float* __restrict__ score_lead, float alpha,
     int A, unsigned long long seed, unsigned long long offset, int logprob_mode,
     const long long* __restrict__ forced_actions,
@@ -81,9 +120,9 @@ __global__ void __launch_bounds__(kThreads) policy_sample_kernel(
   __shared__ int s_besti[kThreads / 32];
   const int row = blockIdx.x;
   const T* lrow = logits + (size_t)row * row_stride;
-  const uint8_t* mrow = mask + (size_t)row * A;
+  const MaskRow<MK> mrow(mask, mask_pitch, row);
   int legal, has_nan;
-  stage_row<T>(lrow, mrow, A, s_row, legal, has_nan);
+  stage_row<T, MK>(lrow, mrow, A, s_row, legal, has_nan);
   __syncthreads();
   const int n_legal = (int)(kb_block_sum((float)legal, scratch) + 0.5f);
   if (threadIdx.x == 0) {
@@ -154,7 +193,7 @@ __global__ void __launch_bounds__(kThreads) policy_sample_kernel(
   }
   if (a == 0x7fffffff) {  // every legal logit was -inf/NaN: fall back to the first legal index
     int first = 0x7fffffff;
-    for (int i = threadIdx.x; i < A; i += kThreads) if (mrow[i] != 0) { first = min(first, i); }
+    for (int i = threadIdx.x; i < A; i += kThreads) if (mrow.get(i)) { first = min(first, i); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
     __syncthreads();
@@ -187,18 +226,18 @@ __global__ void __launch_bounds__(kThreads) policy_sample_kernel(
 // ---------------------------------------------------------------------------------------------
 // Update: forward (per row) + reduction + backward
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int MK>
 __global__ void __launch_bounds__(kThreads) ppo_policy_fwd_kernel(
-    const T* __restrict__ logits, long long row_stride, const uint8_t* __restrict__ mask,
+    const T* __restrict__ logits, long long row_stride, const void* __restrict__ mask, long long mask_pitch,
     const long long* __restrict__ actions, int A, float* __restrict__ new_logp,
     float* __restrict__ row_entropy, float* __restrict__ row_lse, int* __restrict__ flags) {
   extern __shared__ float s_row[];
   __shared__ float scratch[32];
   const int row = blockIdx.x;
   const T* lrow = logits + (size_t)row * row_stride;
-  const uint8_t* mrow = mask + (size_t)row * A;
+  const MaskRow<MK> mrow(mask, mask_pitch, row);
   int legal, has_nan;
-  stage_row<T>(lrow, mrow, A, s_row, legal, has_nan);
+  stage_row<T, MK>(lrow, mrow, A, s_row, legal, has_nan);
   __syncthreads();
   float m = -INFINITY;
   for (int i = threadIdx.x; i < A; i += kThreads) m = fmaxf(m, s_row[i]);
@@ -260,16 +299,16 @@ __global__ void __launch_bounds__(1024) ppo_policy_reduce_kernel(
 }
 
 // dlogits[i] = legal ? gP*dlogp[row]*(onehot - p_i) + gH/B * (-p_i*(logp_i + H_row)) : 0
-template <typename T>
+template <typename T, int MK>
 __global__ void __launch_bounds__(kThreads) ppo_policy_bwd_kernel(
-    const T* __restrict__ logits, long long row_stride, const uint8_t* __restrict__ mask,
+    const T* __restrict__ logits, long long row_stride, const void* __restrict__ mask, long long mask_pitch,
     const long long* __restrict__ actions, int A, int B, const float* __restrict__ row_lse,
     const float* __restrict__ row_entropy, const float* __restrict__ dlogp,
     const float* __restrict__ g_policy, const float* __restrict__ g_entropy,
     T* __restrict__ dlogits, long long d_row_stride) {
   const int row = blockIdx.x;
   const T* lrow = logits + (size_t)row * row_stride;
-  const uint8_t* mrow = mask + (size_t)row * A;
+  const MaskRow<MK> mrow(mask, mask_pitch, row);
   T* drow = dlogits + (size_t)row * d_row_stride;
   const float lse = row_lse[row], H = row_entropy[row];
   const float gl = g_policy[0] * dlogp[row];
@@ -277,7 +316,7 @@ __global__ void __launch_bounds__(kThreads) ppo_policy_bwd_kernel(
   const int a = (int)actions[row];
   for (int i = threadIdx.x; i < A; i += kThreads) {
     float d = 0.f;
-    if (mrow[i] != 0) {
+    if (mrow.get(i)) {
       const float lp = kb_to_float<T>(lrow[i]) - lse;
       const float p = __expf(lp);
       d = gl * ((i == a ? 1.f : 0.f) - p);
@@ -343,6 +382,45 @@ __global__ void __launch_bounds__(256) value_losses_bwd_kernel(
   dscore[i] = g_score[0] * 2.f * (score_pred[i] - score_tgt[i]) / (float)B;
 }
 
+// (rows, A) bool -> (rows, words) bit-packed: a warp reads 32 consecutive bytes, one ballot makes the word
+__global__ void __launch_bounds__(256) pack_mask_bits_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ bits,
+                                                             long long rows, int A, int words) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows * words) return;
+  const long long row = warp / words;
+  const int w = (int)(warp - row * words);
+  const int i = w * 32 + lane;
+  const bool on = i < A && mask[(size_t)row * A + i] != 0;
+  const uint32_t word = __ballot_sync(0xffffffffu, on);
+  if (lane == 0) bits[warp] = word;
+}
+
+// One launch gathers a shuffled minibatch out of the device-resident rollout storage (reference katago_ppo.py:829-841:
+// eight index-gathers per minibatch): observations (row = obs_floats fp32), bit-packed masks and the per-sample scalars.
+struct GatherArgs {
+  const float* obs; const uint32_t* bits; const long long* actions; const float* old_lp; const float* adv;
+  const long long* cats; const float* score; const float* returns; const long long* idx;
+  float* o_obs; uint32_t* o_bits; long long* o_actions; float* o_old_lp; float* o_adv; long long* o_cats; float* o_score;
+  float* o_returns;
+  int obs_floats, words; long long n_src;
+};
+__global__ void __launch_bounds__(256) gather_minibatch_kernel(GatherArgs a) {
+  const long long r = blockIdx.x;
+  long long src = a.idx[r];
+  if (src < 0 || src >= a.n_src) src = 0;   // validated on the host side of the op; never out of bounds here
+  const float2* so = reinterpret_cast<const float2*>(a.obs + (size_t)src * a.obs_floats);   // rows are 8-byte aligned (even float count)
+  float2* dob = reinterpret_cast<float2*>(a.o_obs + (size_t)r * a.obs_floats);
+  const int n2 = a.obs_floats >> 1;
+  for (int i = threadIdx.x; i < n2; i += 256) dob[i] = __ldg(so + i);
+  if ((a.obs_floats & 1) && threadIdx.x == 0) a.o_obs[(size_t)r * a.obs_floats + a.obs_floats - 1] = a.obs[(size_t)src * a.obs_floats + a.obs_floats - 1];
+  for (int i = threadIdx.x; i < a.words; i += 256) a.o_bits[(size_t)r * a.words + i] = __ldg(a.bits + (size_t)src * a.words + i);
+  if (threadIdx.x == 0) {
+    a.o_actions[r] = a.actions[src]; a.o_old_lp[r] = a.old_lp[src]; a.o_adv[r] = a.adv[src]; a.o_cats[r] = a.cats[src];
+    a.o_score[r] = a.score[src]; a.o_returns[r] = a.returns[src];
+  }
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) {
@@ -354,52 +432,78 @@ int set_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+#define KB_TRY_RC(expr) do { int r__ = (expr); if (r__ != KB_OK) return r__; } while (0)
+#define KB_MASK_DISPATCH(KERNEL, T, ...)                                                     \
+  do {                                                                                       \
+    if (mask_kind == 0) KERNEL<T, 0> __VA_ARGS__;                                            \
+    else if (mask_kind == 1) KERNEL<T, 1> __VA_ARGS__;                                       \
+    else KERNEL<T, 2> __VA_ARGS__;                                                           \
+  } while (0)
+
+static int check_mask(const void* mask, int mask_kind, long long mask_pitch, int A, const char* who) {
+  KB_CHECK_ARG(mask_kind >= 0 && mask_kind <= 2, "%s: mask_kind must be 0 (bytes), 1 (bits) or 2 (none)", who);
+  KB_CHECK_ARG(mask_kind == 2 || mask != nullptr, "%s: null mask", who);
+  KB_CHECK_ARG(mask_kind != 0 || mask_pitch >= A, "%s: byte mask pitch %lld < %d", who, mask_pitch, A);
+  KB_CHECK_ARG(mask_kind != 1 || mask_pitch * 32 >= A, "%s: bit mask pitch %lld words < %d bits", who, mask_pitch, A);
+  return KB_OK;
+}
+
 extern "C" int kb_policy_sample(const void* logits, int logits_dtype, long long row_stride,
-                                const uint8_t* mask, const float* value_logits, const float* score_lead,
+                                const void* mask, const float* value_logits, const float* score_lead,
                                 float alpha, int B, int A, unsigned long long seed,
                                 unsigned long long offset, int logprob_mode,
                                 const long long* forced_actions, long long* actions,
                                 float* logp, float* values, int* legal_count, int* flags,
-                                cudaStream_t stream) {
+                                int mask_kind, long long mask_pitch, cudaStream_t stream) {
   KB_CHECK_ARG(B >= 0 && A > 0 && row_stride >= A, "kb_policy_sample: bad shape B=%d A=%d stride=%lld", B, A, row_stride);
   KB_CHECK_ARG(logits_dtype == KB_F32 || logits_dtype == KB_BF16, "kb_policy_sample: bad dtype %d", logits_dtype);
   if (B == 0) return KB_OK;
-  KB_CHECK_ARG(logits && mask && actions && logp && legal_count && flags, "kb_policy_sample: null pointer");
+  KB_TRY_RC(check_mask(mask, mask_kind, mask_pitch, A, "kb_policy_sample"));
+  KB_CHECK_ARG(logits && actions && logp && legal_count && flags, "kb_policy_sample: null pointer");
   KB_CHECK_ARG(values == nullptr || value_logits != nullptr, "kb_policy_sample: values requested without value_logits");
   const size_t smem = (size_t)A * sizeof(float);
   KB_CHECK_ARG(smem <= 200 * 1024, "kb_policy_sample: action space %d too large for one CTA", A);
   if (logits_dtype == KB_F32) {
-    if (int r = set_smem(policy_sample_kernel<float>, smem)) return r;
-    policy_sample_kernel<float><<<B, kThreads, smem, stream>>>((const float*)logits, row_stride, mask, value_logits,
-        score_lead, alpha, A, seed, offset, logprob_mode, forced_actions, actions, logp, values, legal_count, flags);
+    if (int r = set_smem(policy_sample_kernel<float, 0>, smem)) return r;
+    if (int r = set_smem(policy_sample_kernel<float, 1>, smem)) return r;
+    if (int r = set_smem(policy_sample_kernel<float, 2>, smem)) return r;
+    KB_MASK_DISPATCH(policy_sample_kernel, float, <<<B, kThreads, smem, stream>>>((const float*)logits, row_stride, mask, mask_pitch,
+        value_logits, score_lead, alpha, A, seed, offset, logprob_mode, forced_actions, actions, logp, values, legal_count, flags));
   } else {
-    if (int r = set_smem(policy_sample_kernel<bf16>, smem)) return r;
-    policy_sample_kernel<bf16><<<B, kThreads, smem, stream>>>((const bf16*)logits, row_stride, mask, value_logits,
-        score_lead, alpha, A, seed, offset, logprob_mode, forced_actions, actions, logp, values, legal_count, flags);
+    if (int r = set_smem(policy_sample_kernel<bf16, 0>, smem)) return r;
+    if (int r = set_smem(policy_sample_kernel<bf16, 1>, smem)) return r;
+    if (int r = set_smem(policy_sample_kernel<bf16, 2>, smem)) return r;
+    KB_MASK_DISPATCH(policy_sample_kernel, bf16, <<<B, kThreads, smem, stream>>>((const bf16*)logits, row_stride, mask, mask_pitch,
+        value_logits, score_lead, alpha, A, seed, offset, logprob_mode, forced_actions, actions, logp, values, legal_count, flags));
   }
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }
 
 extern "C" int kb_ppo_policy_fwd(const void* logits, int logits_dtype, long long row_stride,
-                                 const uint8_t* mask, const long long* actions,
+                                 const void* mask, const long long* actions,
                                  const float* old_logp, const float* adv, int B, int A, float clip_eps,
                                  float* new_logp, float* row_entropy, float* row_lse, float* dlogp,
-                                 float* out2, int* flags, cudaStream_t stream) {
+                                 float* out2, int* flags, int mask_kind, long long mask_pitch, cudaStream_t stream) {
   KB_CHECK_ARG(B > 0 && A > 0 && row_stride >= A, "kb_ppo_policy_fwd: bad shape B=%d A=%d stride=%lld", B, A, row_stride);
   KB_CHECK_ARG(logits_dtype == KB_F32 || logits_dtype == KB_BF16, "kb_ppo_policy_fwd: bad dtype %d", logits_dtype);
-  KB_CHECK_ARG(logits && mask && actions && old_logp && adv && new_logp && row_entropy && row_lse && dlogp && out2 && flags,
+  KB_TRY_RC(check_mask(mask, mask_kind, mask_pitch, A, "kb_ppo_policy_fwd"));
+  KB_CHECK_ARG(logits && actions && old_logp && adv && new_logp && row_entropy && row_lse && dlogp && out2 && flags,
                "kb_ppo_policy_fwd: null pointer");
   const size_t smem = (size_t)A * sizeof(float);
   KB_CHECK_ARG(smem <= 200 * 1024, "kb_ppo_policy_fwd: action space %d too large for one CTA", A);
   if (logits_dtype == KB_F32) {
-    if (int r = set_smem(ppo_policy_fwd_kernel<float>, smem)) return r;
-    ppo_policy_fwd_kernel<float><<<B, kThreads, smem, stream>>>((const float*)logits, row_stride, mask, actions, A,
-                                                                  new_logp, row_entropy, row_lse, flags);
+    if (int r = set_smem(ppo_policy_fwd_kernel<float, 0>, smem)) return r;
+    if (int r = set_smem(ppo_policy_fwd_kernel<float, 1>, smem)) return r;
+    if (int r = set_smem(ppo_policy_fwd_kernel<float, 2>, smem)) return r;
+    KB_MASK_DISPATCH(ppo_policy_fwd_kernel, float, <<<B, kThreads, smem, stream>>>((const float*)logits, row_stride, mask, mask_pitch,
+        actions, A, new_logp, row_entropy, row_lse, flags));
   } else {
-    if (int r = set_smem(ppo_policy_fwd_kernel<bf16>, smem)) return r;
-    ppo_policy_fwd_kernel<bf16><<<B, kThreads, smem, stream>>>((const bf16*)logits, row_stride, mask, actions, A,
-                                                                 new_logp, row_entropy, row_lse, flags);
+    if (int r = set_smem(ppo_policy_fwd_kernel<bf16, 0>, smem)) return r;
+    if (int r = set_smem(ppo_policy_fwd_kernel<bf16, 1>, smem)) return r;
+    if (int r = set_smem(ppo_policy_fwd_kernel<bf16, 2>, smem)) return r;
+    KB_MASK_DISPATCH(ppo_policy_fwd_kernel, bf16, <<<B, kThreads, smem, stream>>>((const bf16*)logits, row_stride, mask, mask_pitch,
+        actions, A, new_logp, row_entropy, row_lse, flags));
   }
   KB_CUDA_LAUNCH_CHECK();
   ppo_policy_reduce_kernel<<<1, 1024, 0, stream>>>(new_logp, old_logp, adv, row_entropy, B, clip_eps, out2, dlogp);
@@ -408,20 +512,49 @@ extern "C" int kb_ppo_policy_fwd(const void* logits, int logits_dtype, long long
 }
 
 extern "C" int kb_ppo_policy_bwd(const void* logits, int logits_dtype, long long row_stride,
-                                 const uint8_t* mask, const long long* actions, int B, int A,
+                                 const void* mask, const long long* actions, int B, int A,
                                  const float* row_lse, const float* row_entropy, const float* dlogp,
                                  const float* g_policy, const float* g_entropy, void* dlogits,
-                                 long long d_row_stride, cudaStream_t stream) {
+                                 long long d_row_stride, int mask_kind, long long mask_pitch, cudaStream_t stream) {
   KB_CHECK_ARG(B > 0 && A > 0 && row_stride >= A && d_row_stride >= A, "kb_ppo_policy_bwd: bad shape");
   KB_CHECK_ARG(logits_dtype == KB_F32 || logits_dtype == KB_BF16, "kb_ppo_policy_bwd: bad dtype %d", logits_dtype);
-  KB_CHECK_ARG(logits && mask && actions && row_lse && row_entropy && dlogp && g_policy && g_entropy && dlogits,
+  KB_TRY_RC(check_mask(mask, mask_kind, mask_pitch, A, "kb_ppo_policy_bwd"));
+  KB_CHECK_ARG(logits && actions && row_lse && row_entropy && dlogp && g_policy && g_entropy && dlogits,
                "kb_ppo_policy_bwd: null pointer");
   if (logits_dtype == KB_F32)
-    ppo_policy_bwd_kernel<float><<<B, kThreads, 0, stream>>>((const float*)logits, row_stride, mask, actions, A, B, row_lse,
-        row_entropy, dlogp, g_policy, g_entropy, (float*)dlogits, d_row_stride);
+    KB_MASK_DISPATCH(ppo_policy_bwd_kernel, float, <<<B, kThreads, 0, stream>>>((const float*)logits, row_stride, mask, mask_pitch, actions,
+        A, B, row_lse, row_entropy, dlogp, g_policy, g_entropy, (float*)dlogits, d_row_stride));
   else
-    ppo_policy_bwd_kernel<bf16><<<B, kThreads, 0, stream>>>((const bf16*)logits, row_stride, mask, actions, A, B, row_lse,
-        row_entropy, dlogp, g_policy, g_entropy, (bf16*)dlogits, d_row_stride);
+    KB_MASK_DISPATCH(ppo_policy_bwd_kernel, bf16, <<<B, kThreads, 0, stream>>>((const bf16*)logits, row_stride, mask, mask_pitch, actions,
+        A, B, row_lse, row_entropy, dlogp, g_policy, g_entropy, (bf16*)dlogits, d_row_stride));
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+extern "C" int kb_pack_mask_bits(const void* mask_bytes, void* bits, long long rows, int A, int words, cudaStream_t stream) {
+  KB_CHECK_ARG(rows >= 0 && A > 0 && words * 32 >= A, "kb_pack_mask_bits: bad shape rows=%lld A=%d words=%d", rows, A, words);
+  if (rows == 0) return KB_OK;
+  KB_CHECK_ARG(mask_bytes && bits, "kb_pack_mask_bits: null pointer");
+  const long long threads = rows * words * 32;
+  pack_mask_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>((const uint8_t*)mask_bytes, (uint32_t*)bits, rows, A, words);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+extern "C" int kb_gather_minibatch(const float* obs, const void* mask_bits, const long long* actions, const float* old_lp,
+                                   const float* adv, const long long* cats, const float* score, const float* returns,
+                                   const long long* idx, long long n_src, int n_out, int obs_floats, int words, float* o_obs,
+                                   void* o_bits, long long* o_actions, float* o_old_lp, float* o_adv, long long* o_cats,
+                                   float* o_score, float* o_returns, cudaStream_t stream) {
+  KB_CHECK_ARG(n_out >= 0 && n_src > 0 && obs_floats > 0 && obs_floats % 2 == 0 && words > 0, "kb_gather_minibatch: bad shape");
+  if (n_out == 0) return KB_OK;
+  KB_CHECK_ARG(obs && mask_bits && actions && old_lp && adv && cats && score && returns && idx && o_obs && o_bits && o_actions &&
+               o_old_lp && o_adv && o_cats && o_score && o_returns, "kb_gather_minibatch: null pointer");
+  GatherArgs a;
+  a.obs = obs; a.bits = (const uint32_t*)mask_bits; a.actions = actions; a.old_lp = old_lp; a.adv = adv; a.cats = cats; a.score = score;
+  a.returns = returns; a.idx = idx; a.o_obs = o_obs; a.o_bits = (uint32_t*)o_bits; a.o_actions = o_actions; a.o_old_lp = o_old_lp;
+  a.o_adv = o_adv; a.o_cats = o_cats; a.o_score = o_score; a.o_returns = o_returns; a.obs_floats = obs_floats; a.words = words; a.n_src = n_src;
+  gather_minibatch_kernel<<<(unsigned)n_out, 256, 0, stream>>>(a);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

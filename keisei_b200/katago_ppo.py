@@ -125,6 +125,52 @@ class KataGoPPOParams:
             raise ValueError(f"grad_clip must be > 0, got {self.grad_clip}")
 
 
+class _DeviceFlat(dict):
+    """`flatten()` result of a device-resident buffer: everything the reference's dict has, with `legal_masks` (the
+    (T*N, A) bool tensor) unpacked from the stored bit-packed rows only if somebody asks for it — `update()` consumes
+    `legal_masks_packed` directly and never does."""
+
+    def __init__(self, base: dict, bits: torch.Tensor, num_actions: int) -> None:
+        super().__init__(base)
+        self._bits, self._num_actions = bits, num_actions
+        dict.__setitem__(self, "legal_masks_packed", bits)
+
+    def __missing__(self, key):
+        if key == "legal_masks":
+            value = policy_ops.unpack_mask_bits(self._bits, self._num_actions)
+            dict.__setitem__(self, key, value)
+            return value
+        raise KeyError(key)
+
+    def __contains__(self, key) -> bool:
+        return key == "legal_masks" or dict.__contains__(self, key)
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+    def _materialise(self) -> None:
+        self["legal_masks"]   # noqa: B018  (side effect: unpack + cache)
+
+    def keys(self):
+        self._materialise()
+        return dict.keys(self)
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+    def values(self):
+        self._materialise()
+        return dict.values(self)
+
+    def __iter__(self):
+        self._materialise()
+        return dict.__iter__(self)
+
+
 class KataGoRolloutBuffer:
     """Rollout storage with the reference's interface and guards (katago_ppo.py:128-388): `add`, `flatten`, `clear`,
     `size`, `fill_alternating_perspective_overrides`.
@@ -133,7 +179,9 @@ class KataGoRolloutBuffer:
     `update()` ships observations + masks back (225 MB for T=128 x N=64). `device="cuda:k"` keeps the same storage in
     HBM: `add` is device-to-device, the guards run as one fused flag reduction with a single
     host read per step, `flatten()` returns device views and `update()` performs no host<->device copy of the
-    per-sample data at all."""
+    per-sample data at all. The legal masks of a CUDA buffer are stored BIT-PACKED (1,408 B instead of 11,259 B per
+    sample; `kb_pack_mask_bits` in `add`): `flatten()["legal_masks_packed"]` is what the update's gather and loss kernels
+    read, `flatten()["legal_masks"]` unpacks the reference's bool layout on demand."""
 
     _FIELDS = ("observations", "actions", "log_probs", "values", "rewards", "dones", "terminated", "legal_masks",
                "value_categories", "score_targets")
@@ -161,7 +209,8 @@ class KataGoRolloutBuffer:
             "rewards": torch.empty(cap, device=dev),
             "dones": torch.empty(cap, dtype=torch.bool, device=dev),
             "terminated": torch.empty(cap, dtype=torch.bool, device=dev),
-            "legal_masks": torch.empty(cap, self.action_space, dtype=torch.bool, device=dev),
+            "legal_masks": (torch.empty(cap, policy_ops.mask_words(self.action_space), dtype=torch.int32, device=dev)
+                            if dev.type == "cuda" else torch.empty(cap, self.action_space, dtype=torch.bool, device=dev)),
             "value_categories": torch.empty(cap, dtype=torch.long, device=dev),
             "score_targets": torch.empty(cap, device=dev),
         }
@@ -240,6 +289,10 @@ class KataGoRolloutBuffer:
         self._ensure_capacity(n)
         sl = slice(self._write_offset, self._write_offset + n)
         st = self._storage
+        if dev.type == "cuda":
+            if tuple(mask_c.shape) != (n, self.action_space):
+                raise ValueError(f"legal_masks shape {tuple(mask_c.shape)} != {(n, self.action_space)}")
+            mask_c = policy_ops.pack_mask_bits(mask_c)   # stored bit-packed in HBM
         for key, val in zip(self._FIELDS, (obs_c, act_c, lp_c, val_c, rew_c, done_c, term_c, mask_c, cats_c, score_c)):
             st[key][sl] = val
         if env_ids is not None:
@@ -278,16 +331,18 @@ class KataGoRolloutBuffer:
             raise ValueError("Cannot flatten an empty buffer. Call add() at least once before flatten().")
         off = self._write_offset
         st = self._storage
-        out = {
-            "observations": st["observations"][:off].reshape(-1, *self.obs_shape),
-            "legal_masks": st["legal_masks"][:off].reshape(-1, self.action_space),
-        }
+        packed = self.device.type == "cuda"
+        out = {"observations": st["observations"][:off].reshape(-1, *self.obs_shape)}
+        if not packed:
+            out["legal_masks"] = st["legal_masks"][:off].reshape(-1, self.action_space)
         for key in ("actions", "log_probs", "values", "rewards", "dones", "terminated", "value_categories", "score_targets"):
             out[key] = st[key][:off].reshape(-1)
         if self._has_env_ids and "env_ids" in st:
             out["env_ids"] = st["env_ids"][:off].reshape(-1)
         if self._has_next_value_override and "next_value_override" in st:
             out["next_value_override"] = st["next_value_override"][:off].reshape(-1)
+        if packed:
+            return _DeviceFlat(out, st["legal_masks"][:off], self.action_space)
         return out
 
 
@@ -490,7 +545,8 @@ class KataGoPPOAlgorithm:
             return adv.reshape(-1)
         nv_cpu = nv.cpu()
         # ragged buffers (split-merge rollouts): the index bookkeeping below is host-side, on the small 1-D fields only
-        data = {k: (v.cpu() if v.is_cuda and k not in ("observations", "legal_masks") else v) for k, v in data.items()}
+        data = {k: (v.cpu() if v.is_cuda and k not in ("observations", "legal_masks", "legal_masks_packed") else v)
+                for k, v in dict.items(data)}   # dict.items: a device buffer's lazy `legal_masks` is not materialised
         if "env_ids" in data:
             env_ids = data["env_ids"]
             order = torch.argsort(env_ids, stable=True)
@@ -676,13 +732,15 @@ class KataGoPPOAlgorithm:
         p = self.params
 
         if device.type == "cuda" and data["observations"].device == device:
-            side = None   # device-resident buffer (KataGoRolloutBuffer(device=...)): nothing to ship
-            gpu_obs, gpu_masks = data["observations"], data["legal_masks"]
+            side = None   # device-resident buffer (KataGoRolloutBuffer(device=...)): nothing to ship, masks already bit-packed
+            gpu_obs = data["observations"]
+            gpu_masks = data["legal_masks_packed"] if dict.__contains__(data, "legal_masks_packed") else data["legal_masks"]
         elif device.type == "cuda":
             side = torch.cuda.Stream(device)
             with torch.cuda.stream(side):
                 gpu_obs = data["observations"].pin_memory().to(device, non_blocking=True)
                 gpu_masks = data["legal_masks"].pin_memory().to(device, non_blocking=True)
+                gpu_masks = policy_ops.pack_mask_bits(gpu_masks)   # 8x fewer mask bytes for every gather and loss kernel below
         else:
             side = None
             gpu_obs, gpu_masks = data["observations"], data["legal_masks"]
@@ -708,12 +766,19 @@ class KataGoPPOAlgorithm:
         acc = {k: zero() for k in ("policy_loss", "value_loss", "score_loss", "entropy", "gradient_norm")}
         n_updates = 0
         last_value_logits = last_cats = None
+        # one gather kernel per minibatch (observations, bit-packed masks, six scalars) instead of eight index ops
+        fused_gather = (device.type == "cuda" and gpu_masks.dtype == torch.int32 and gpu_obs.dtype == torch.float32
+                        and gpu_obs.is_contiguous() and gpu_obs[0].numel() % 2 == 0)
         for _ in range(p.epochs_per_batch):
             perm = torch.randperm(total, device=device)
             for start in range(0, total, batch_size):
                 idx = perm[start:start + batch_size]
-                obs_b = gpu_obs[idx]
-                mb = (gpu_masks[idx], g_actions[idx], g_old[idx], adv[idx], g_cats[idx], g_score[idx], returns[idx])
+                if fused_gather:
+                    obs_b, *mb = policy_ops.gather_minibatch(gpu_obs, gpu_masks, g_actions, g_old, adv, g_cats, g_score, returns, idx)
+                    mb = tuple(mb)
+                else:
+                    obs_b = gpu_obs[idx]
+                    mb = (gpu_masks[idx], g_actions[idx], g_old[idx], adv[idx], g_cats[idx], g_score[idx], returns[idx])
                 tok = self._events(device, "update_forward_backward_ms")
                 if km is not None:
                     pl, vl, sl, ent, v_logits = self._step_fused(km, obs_b, mb, value_adapter)

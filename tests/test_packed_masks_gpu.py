@@ -1,0 +1,173 @@
+"""Bit-packed legal masks (1,408 B instead of 11,259 B per sample) through the rollout buffer, the
+sampler, the PPO loss kernels and the fused minibatch gather; the no-mask mode used by the supervised loss
+(reference sl/trainer.py:147-158). Integer / index work: bit-exact against the byte-mask kernels and torch indexing."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from keisei_b200 import _lib, policy_ops, sl
+from keisei_b200.katago_ppo import KataGoPPOAlgorithm, KataGoPPOParams, KataGoRolloutBuffer
+from keisei_b200.model_registry import build_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+A = 11259
+TINY = dict(num_blocks=1, channels=32, se_reduction=4, global_pool_channels=8, policy_channels=8, value_fc_size=8, score_fc_size=8)
+
+
+def _rows(B, seed, dtype=torch.bfloat16, density=0.01):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    logits = torch.randn(B, 11264, device=DEV, generator=g).to(dtype)[:, :A]
+    mask = torch.rand(B, A, device=DEV, generator=g) < density
+    acts = torch.randint(0, A, (B,), device=DEV, generator=g)
+    mask[torch.arange(B, device=DEV), acts] = True
+    return logits, mask, acts
+
+
+@pytest.mark.parametrize("A_", [11259, 64, 33, 1])
+def test_pack_unpack_roundtrip_and_bit_order(A_):
+    g = torch.Generator(device=DEV).manual_seed(A_)
+    mask = torch.rand(37, A_, device=DEV, generator=g) < 0.3
+    bits = policy_ops.pack_mask_bits(mask)
+    assert bits.dtype == torch.int32 and bits.shape == (37, (A_ + 31) // 32)
+    assert torch.equal(policy_ops.unpack_mask_bits(bits, A_), mask)
+    # action i = bit (i & 31) of word (i >> 5); padding bits are zero
+    m = mask.cpu().numpy()
+    want = np.zeros((37, (A_ + 31) // 32), dtype=np.uint32)
+    for i in range(A_):
+        want[:, i >> 5] |= (m[:, i].astype(np.uint32) << np.uint32(i & 31))
+    np.testing.assert_array_equal(bits.cpu().numpy().view(np.uint32), want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_loss_and_sampler_kernels_packed_equals_bytes(dtype):
+    B = 70
+    logits, mask, acts = _rows(B, 3, dtype)
+    mask[5] = False; mask[5, 77] = True                      # single legal action
+    bits = policy_ops.pack_mask_bits(mask)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    old, adv = -3 * torch.rand(B, device=DEV, generator=g), torch.randn(B, device=DEV, generator=g)
+    outs = {}
+    for name, mk in (("bytes", mask), ("bits", bits)):
+        lg = logits.detach().clone().requires_grad_(True)
+        out2, new_lp, row_ent, row_lse, dlogp, flags = policy_ops.ppo_policy_loss(lg, mk, acts, old, adv, 0.2)
+        (out2[0] - 0.01 * out2[1]).backward()
+        outs[name] = (out2.detach(), new_lp.detach(), row_ent.detach(), row_lse.detach(), lg.grad.clone(), flags)
+    for a, b in zip(outs["bytes"], outs["bits"]):
+        assert torch.equal(a, b)
+    assert bool((outs["bits"][4][~mask] == 0).all())
+    vl = torch.randn(B, 3, device=DEV)
+    for forced in (None, acts):
+        r0 = policy_ops.policy_sample(logits, mask, vl, seed=11, offset=5, forced_actions=forced)
+        r1 = policy_ops.policy_sample(logits, bits, vl, seed=11, offset=5, forced_actions=forced)
+        for a, b in zip(r0, r1):
+            assert torch.equal(a, b)
+        assert mask[torch.arange(B, device=DEV), r1[0]].all()
+    # zero-legal row is flagged identically
+    bad = mask.clone(); bad[9] = False
+    f0 = policy_ops.policy_sample(logits, bad, vl, seed=1, offset=1)[4]
+    f1 = policy_ops.policy_sample(logits, policy_ops.pack_mask_bits(bad), vl, seed=1, offset=1)[4]
+    assert int(f0[0]) == 1 and torch.equal(f0, f1)
+
+
+def test_no_mask_mode_is_plain_log_softmax_and_sl_losses_match_torch():
+    B = 33
+    g = torch.Generator().manual_seed(7)
+    logits = torch.randn(B, A, generator=g)
+    value = torch.randn(B, 3, generator=g); score = torch.randn(B, 1, generator=g)
+    pt, vt, st = torch.randint(0, A, (B,), generator=g), torch.randint(0, 3, (B,), generator=g), torch.randn(B, generator=g)
+    ref_in = [t.clone().requires_grad_(True) for t in (logits, value, score)]
+    want = 1.0 * F.cross_entropy(ref_in[0], pt) + 1.5 * F.cross_entropy(ref_in[1], vt) + 0.02 * F.mse_loss(ref_in[2].squeeze(-1), st)
+    want.backward()
+    got_in = [t.to(DEV).requires_grad_(True) for t in (logits, value, score)]
+    n0 = _lib.launch_count()
+    loss, pl, vl, sc = sl.sl_losses(got_in[0], got_in[1], got_in[2], pt.to(DEV), vt.to(DEV), st.to(DEV))
+    assert _lib.launch_count() > n0
+    assert abs(loss.item() - want.item()) <= 1e-5 * abs(want.item())
+    assert abs(pl.item() - F.cross_entropy(logits, pt).item()) <= 1e-5 * pl.item()
+    loss.backward()
+    for a, b in zip(got_in, ref_in):
+        assert torch.allclose(a.grad.cpu(), b.grad, rtol=1e-4, atol=1e-7)
+    # all-ones byte mask == no mask, bit for bit
+    ones = torch.ones(B, A, dtype=torch.bool, device=DEV)
+    z = torch.zeros(B, device=DEV)
+    r0 = policy_ops.ppo_policy_loss(got_in[0].detach(), None, pt.to(DEV), z, z, 0.0)
+    r1 = policy_ops.ppo_policy_loss(got_in[0].detach(), ones, pt.to(DEV), z, z, 0.0)
+    assert torch.equal(r0[1], r1[1]) and torch.equal(r0[3], r1[3])
+
+
+def test_sl_step_on_kernel_model_bf16_vs_oracle():
+    from oracle import keisei_oracle as O
+    torch.manual_seed(0)
+    cfg = dict(num_blocks=2, channels=128, se_reduction=8, global_pool_channels=32, policy_channels=16, value_fc_size=32, score_fc_size=32)
+    m = build_model("se_resnet", dict(cfg))
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    B = 24
+    g = torch.Generator().manual_seed(1)
+    batch = {"observation": torch.randn(B, 50, 9, 9, generator=g), "policy_target": torch.randint(0, A, (B,), generator=g),
+             "value_target": torch.randint(0, 3, (B,), generator=g), "score_target": torch.randn(B, generator=g).clamp(-1.5, 1.5)}
+    with torch.no_grad():
+        wp, wv, ws = O.seresnet_forward(sd, batch["observation"], 2, training=True)
+    want = (F.cross_entropy(wp.reshape(B, -1), batch["policy_target"]).item(), F.cross_entropy(wv, batch["value_target"]).item(),
+            F.mse_loss(ws.squeeze(-1), batch["score_target"]).item())
+    m = m.to(DEV)
+    step = sl.SLStep(m, torch.optim.Adam(m.parameters(), 1e-3), use_amp=True)
+    before = [p.detach().clone() for p in m.parameters()]
+    out = step(batch)
+    for got, w, k in zip((out["policy_loss"], out["value_loss"], out["score_loss"]), want, ("policy", "value", "score")):
+        assert abs(got.item() - w) <= 2e-2 * max(abs(w), 1e-3), (k, got.item(), w)
+    assert any(not torch.equal(a, b) for a, b in zip(before, m.parameters()))
+
+
+def test_gather_minibatch_equals_index_ops():
+    N, M = 300, 128
+    g = torch.Generator(device=DEV).manual_seed(9)
+    obs = torch.randn(N, 50, 9, 9, device=DEV, generator=g)
+    bits = policy_ops.pack_mask_bits(torch.rand(N, A, device=DEV, generator=g) < 0.02)
+    acts, cats = torch.randint(0, A, (N,), device=DEV, generator=g), torch.randint(-1, 3, (N,), device=DEV, generator=g)
+    f = [torch.randn(N, device=DEV, generator=g) for _ in range(4)]
+    idx = torch.randperm(N, device=DEV, generator=g)[:M]
+    n0 = _lib.launch_count()
+    got = policy_ops.gather_minibatch(obs, bits, acts, f[0], f[1], cats, f[2], f[3], idx)
+    assert _lib.launch_count() == n0 + 1
+    want = (obs[idx], bits[idx], acts[idx], f[0][idx], f[1][idx], cats[idx], f[2][idx], f[3][idx])
+    for a, b in zip(got, want):
+        assert a.dtype == b.dtype and torch.equal(a, b)
+
+
+def test_device_buffer_stores_packed_masks_and_update_matches_host_buffer():
+    N, T = 6, 5
+    torch.manual_seed(0)
+    host, devb = KataGoRolloutBuffer(N, (50, 9, 9), A), KataGoRolloutBuffer(N, (50, 9, 9), A, device=DEV)
+    g = torch.Generator().manual_seed(2)
+    masks = []
+    for t in range(T):
+        obs = torch.randn(N, 50, 9, 9, generator=g)
+        mask = torch.rand(N, A, generator=g) < 0.01
+        a = torch.randint(0, A, (N,), generator=g); mask[torch.arange(N), a] = True
+        masks.append(mask)
+        term = torch.rand(N, generator=g) < 0.2
+        fields = [obs, a, -2 * torch.rand(N, generator=g), 0.3 * torch.randn(N, generator=g), term.float(), term, term, mask,
+                  torch.where(term, torch.randint(0, 3, (N,), generator=g), torch.full((N,), -1)), torch.randn(N, generator=g).clamp(-1, 1)]
+        host.add(*fields)
+        devb.add(*[x.to(DEV) for x in fields])
+    assert devb._storage["legal_masks"].dtype == torch.int32 and devb._storage["legal_masks"].shape[1] == 352
+    flat = devb.flatten()
+    assert dict.__contains__(flat, "legal_masks_packed") and not dict.__contains__(flat, "legal_masks")
+    assert "legal_masks" in flat                                   # advertised, unpacked lazily
+    assert torch.equal(flat["legal_masks"].cpu(), torch.cat(masks))
+    assert set(host.flatten().keys()) | {"legal_masks_packed"} == set(flat.keys())
+    # same seeds -> same shuffles -> identical update through the packed / gathered path
+    res = []
+    for buf in (host, devb):
+        torch.manual_seed(5)
+        m = build_model("se_resnet", dict(TINY)).to(DEV)
+        algo = KataGoPPOAlgorithm(KataGoPPOParams(batch_size=16, epochs_per_batch=2), m)
+        torch.manual_seed(6)
+        metrics = algo.update(buf, torch.zeros(N, device=DEV))
+        res.append((metrics, [p.detach().clone() for p in m.parameters()]))
+    for k in ("policy_loss", "value_loss", "score_loss", "entropy"):
+        assert res[0][0][k] == pytest.approx(res[1][0][k], rel=1e-6, abs=1e-8), k
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
