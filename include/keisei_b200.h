@@ -96,6 +96,22 @@ int kb_value_losses_bwd(const float* value_logits, const long long* cats, const 
                         const float* score_tgt, int B, const float* out3, const float* g_value,
                         const float* g_score, float* dvalue_logits, float* dscore, kb_stream_t stream);
 
+/* ---- optimiser tail: keisei/training/katago_ppo.py:926-933 (GradScaler.unscale_, clip_grad_norm_, Adam.step) as two
+ *      passes over the flat fp32 gradient the backward produces (csrc/optim.cu) ----
+ * out2 (device, 2 doubles) = [sum of squares of flat_grad, 1.0 if any element is non-finite]; zeroed by the call. */
+int kb_flat_grad_stats(const float* flat_grad, long long n, double* out2, int num_sms, kb_stream_t stream);
+/* One launch over every parameter: g = flat_grad * inv_scale / grad_div, clipped to max_norm by the global 2-norm taken
+ * from `stats`, then torch.optim.Adam's update (no weight decay / amsgrad) in place on PyTorch's own parameter and moment
+ * tensors (DEVICE arrays of pointers p/m/v, [n_tensors]); `steps` (device, [n_tensors] floats) are the optimizer's `step`
+ * scalars, incremented unless the gradient was non-finite, in which case nothing is touched (GradScaler skip).
+ * Chunking: chunk c covers elements [chunk_start[c], chunk_start[c] + chunk) of tensor chunk_tensor[c]; g_off[t] is the
+ * tensor's offset in the flat gradient. grad_norm_out / found_inf_out: device floats. */
+int kb_adam_step_flat(const float* flat_grad, void* const* p_ptrs, void* const* m_ptrs, void* const* v_ptrs, float* steps,
+                      const long long* g_off, const long long* sizes, const int* chunk_tensor, const long long* chunk_start,
+                      int n_tensors, int n_chunks, int chunk, const double* stats, const float* inv_scale, float grad_div,
+                      float max_norm, float lr, float beta1, float beta2, float eps, float* grad_norm_out,
+                      float* found_inf_out, kb_stream_t stream);
+
 /* ---- SE-ResNet: keisei/training/models/se_resnet.py:132-159 SEResNetModel._forward_impl,
  *      :68-90 GlobalPoolBiasBlock.forward, :93-98 _global_pool, and their autograd ----
  * params / buffers / grads are HOST arrays of device pointers in the reference's registration

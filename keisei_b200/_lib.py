@@ -34,6 +34,8 @@ _SIGS: dict[str, tuple[object, list[object]]] = {
                                   _P, _P, _P, _P, _P, _P, c_int, c_longlong, _P]),
     "kb_ppo_policy_bwd": (c_int, [_P, c_int, c_longlong, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
                                   c_longlong, c_int, c_longlong, _P]),
+    "kb_flat_grad_stats": (c_int, [_P, c_longlong, _P, c_int, _P]),
+    "kb_adam_step_flat": (c_int, [_P] * 9 + [c_int, c_int, c_int, _P, _P] + [c_float] * 6 + [_P, _P, _P]),
     "kb_pack_mask_bits": (c_int, [_P, _P, c_longlong, c_int, c_int, _P]),
     "kb_gather_minibatch": (c_int, [_P] * 9 + [c_longlong, c_int, c_int, c_int] + [_P] * 8 + [_P]),
     "kb_value_losses_fwd": (c_int, [_P, _P, _P, _P, c_int, _P, _P]),

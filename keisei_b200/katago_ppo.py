@@ -382,6 +382,7 @@ class KataGoPPOAlgorithm:
         self.strict_guards = True      # check NaN / zero-legal flags every minibatch (1 host sync, reference: 2)
         self._sample_seed: int | None = None
         self._flat_grad: torch.Tensor | None = None   # flat gradient of the last fused step (consumed by _optimizer_tail)
+        self.fused_optimizer_tail = True   # norm + clip + Adam as two launches over the flat gradient (keisei_b200/optim.py)
 
     # ---- small helpers ---------------------------------------------------------------------------
     def get_entropy_coeff(self, epoch: int) -> float:
@@ -662,11 +663,12 @@ class KataGoPPOAlgorithm:
     def _optimizer_tail(self) -> torch.Tensor:
         """unscale -> clip -> optimiser step -> scaler update (reference katago_ppo.py:926-933), returns the gradient norm.
 
-        After a fused step all gradients are views of ONE flat fp32 buffer, so the GradScaler's inf check / unscale and
-        `clip_grad_norm_` run as a handful of kernels on that buffer instead of foreach passes over 576 tensors — the
-        same arithmetic (a 2-norm of per-tensor 2-norms IS the 2-norm of the concatenation), but ~0.3 ms instead of
-        ~2.6 ms of host time per step, which is 8 % of a 1024-sample-per-GPU step. Everything else (and any step whose
-        gradients did not come from `_step_fused`) goes through the stock PyTorch calls."""
+        After a fused step all gradients are views of ONE flat fp32 buffer, so the GradScaler's inf check / unscale,
+        `clip_grad_norm_` and — for a plain `torch.optim.Adam` — the Adam update itself run as TWO launches on that buffer
+        (`FlatAdamTail`: one read of the gradient, one pass over p / g / m / v) instead of ~50 foreach / multi-tensor
+        launches over 576 tensors; the optimizer's `state_dict()` is unchanged. Any other optimizer keeps the stock
+        `scaler.step()`, and any step whose gradients did not come from `_step_fused` goes through the stock PyTorch
+        calls end to end."""
         p = self.params
         flat = getattr(self, "_flat_grad", None)
         self._flat_grad = None
@@ -683,9 +685,16 @@ class KataGoPPOAlgorithm:
             self.scaler.step(self.optimizer)
             self.scaler.update()
             return grad_norm
+        from .optim import FlatAdamTail
+        tail = getattr(self, "_flat_adam", None)
+        if tail is None:
+            tail = self._flat_adam = FlatAdamTail()
+        fused_adam = self.fused_optimizer_tail and FlatAdamTail.supports(self.optimizer, params, flat)
+        inv_scale = None
+        st = None
         if self.scaler.is_enabled():
             # GradScaler.unscale_ on the flat buffer; the scaler's bookkeeping is filled in exactly as unscale_ does, so
-            # scaler.step() passes found_inf to the fused Adam and scaler.update() adapts the scale as usual
+            # scaler.update() adapts the scale as usual (and scaler.step() sees found_inf on the stock path)
             from torch.amp.grad_scaler import OptState
             st = self.scaler._per_optimizer_states[id(self.optimizer)]
             if st["stage"] is OptState.UNSCALED:
@@ -694,6 +703,19 @@ class KataGoPPOAlgorithm:
             if scale is None:
                 raise RuntimeError("GradScaler has no scale yet: scaler.scale(loss) must run before the optimiser tail")
             inv_scale = scale.double().reciprocal().float()
+        if fused_adam:
+            # two launches: one read of the gradient (norm + non-finite flag), one pass over (p, g, m, v) that unscales,
+            # clips and applies Adam in place on PyTorch's own parameter / state tensors (csrc/optim.cu)
+            grad_norm, found_inf = tail.step(flat, self.optimizer, params, p.grad_clip, inv_scale, 1.0,
+                                             model_ops.sm_count(flat.device))
+            if st is not None:
+                from torch.amp.grad_scaler import OptState
+                st["found_inf_per_device"] = {flat.device: found_inf.reshape(1)}
+                st["stage"] = OptState.STEPPED
+                self.scaler.update()
+            return grad_norm
+        if st is not None:
+            from torch.amp.grad_scaler import OptState
             found_inf = torch.zeros((), dtype=torch.float32, device=flat.device)
             torch._amp_foreach_non_finite_check_and_unscale_([flat], found_inf, inv_scale)
             st["found_inf_per_device"] = {flat.device: found_inf}

@@ -29,6 +29,12 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+def _f(x: torch.Tensor) -> torch.Tensor:
+    """The reference's `.float()` (bf16 / fp16 autocast outputs -> fp32 for the loss math); float64 inputs — the
+    rounding-free yardstick some tests compute — stay float64."""
+    return x if x.dtype == torch.float64 else x.float()
+
+
 SPATIAL_MOVE_TYPES = 139  # reference models/katago_base.py:41
 ACTION_SPACE = 81 * 139   # reference models/katago_base.py:43
 
@@ -165,7 +171,7 @@ def scalar_ppo_losses(policy_logits, value, legal_mask, actions, old_log_probs, 
     ratio = (new_logp - old_log_probs).exp()
     policy_loss = -torch.min(ratio * advantages, ratio.clamp(1 - clip_epsilon, 1 + clip_epsilon) * advantages).mean()
     entropy = -(logp_all.exp() * logp_all.masked_fill(~legal_mask, 0.0)).sum(dim=-1).mean()
-    value_loss = F.mse_loss(value.float().squeeze(-1), returns)
+    value_loss = F.mse_loss(_f(value).squeeze(-1), returns)
     loss = policy_loss + value_loss_coeff * value_loss - entropy_coeff * entropy
     return {"loss": loss, "policy_loss": policy_loss, "value_loss": value_loss, "entropy": entropy,
             "new_log_probs": new_logp}
@@ -176,7 +182,7 @@ def scalar_ppo_losses(policy_logits, value, legal_mask, actions, old_log_probs, 
 # ---------------------------------------------------------------------------------------------
 def masked_log_softmax(flat_logits, legal_mask):
     """katago_ppo.py:873-874."""
-    return F.log_softmax(flat_logits.float().masked_fill(~legal_mask, float("-inf")), dim=-1)
+    return F.log_softmax(_f(flat_logits).masked_fill(~legal_mask, float("-inf")), dim=-1)
 
 
 def ppo_losses(policy_logits, value_logits, score_lead, legal_mask, actions, old_log_probs, advantages,
@@ -194,10 +200,10 @@ def ppo_losses(policy_logits, value_logits, score_lead, legal_mask, actions, old
     probs = logp_all.exp()
     entropy = -(probs * logp_all.masked_fill(~legal_mask, 0.0)).sum(dim=-1).mean()  # :886-888
     if (value_cats >= 0).any():                                                # :51-57
-        value_loss = F.cross_entropy(value_logits.float(), value_cats, ignore_index=-1)
+        value_loss = F.cross_entropy(_f(value_logits), value_cats, ignore_index=-1)
     else:
-        value_loss = value_logits.float().sum() * 0.0
-    score_loss = F.mse_loss(score_lead.float().squeeze(-1), score_targets)     # :910-912
+        value_loss = _f(value_logits).sum() * 0.0
+    score_loss = F.mse_loss(_f(score_lead).squeeze(-1), score_targets)     # :910-912
     loss = lambda_policy * policy_loss + lambda_value * value_loss + lambda_score * score_loss \
         - entropy_coeff * entropy                                              # :914-924
     return {"loss": loss, "policy_loss": policy_loss, "value_loss": value_loss,
@@ -206,11 +212,11 @@ def ppo_losses(policy_logits, value_logits, score_lead, legal_mask, actions, old
 
 def scalar_value(value_logits, score_lead=None, alpha=0.0):
     """katago_ppo.py:533-541 and value_adapter.py:79-96."""
-    p = F.softmax(value_logits.float(), dim=-1)
+    p = F.softmax(_f(value_logits), dim=-1)
     v = p[:, 0] - p[:, 2]
     if alpha == 0.0 or score_lead is None:
         return v
-    return (1 - alpha) * v + alpha * score_lead.float().squeeze(-1).clamp(-1, 1)
+    return (1 - alpha) * v + alpha * _f(score_lead).squeeze(-1).clamp(-1, 1)
 
 
 def rollout_log_prob(flat_logits, legal_mask, actions):

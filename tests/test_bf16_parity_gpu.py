@@ -66,11 +66,14 @@ def make_batch(B, seed):
     return obs, mask, acts, old, adv, cats, score_t
 
 
-def oracle_step(model, batch, num_blocks):
+def oracle_step(model, batch, num_blocks, dtype=torch.float32):
     """Training-mode forward + KataGo-PPO loss + backward of the oracle on the model's weights.
-    Returns (policy, value, score, losses dict, {name: grad})."""
+    Returns (policy, value, score, losses dict, {name: grad}). dtype=float64 gives the rounding-free yardstick."""
     obs, mask, acts, old, adv, cats, score_t = batch
     sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    if dtype != torch.float32:
+        sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+        obs, old, adv, score_t = obs.to(dtype), old.to(dtype), adv.to(dtype), score_t.to(dtype)
     for k, v in sd.items():
         if v.is_floating_point() and "running" not in k:
             v.requires_grad_(True)
@@ -223,12 +226,16 @@ def test_fp32_40x256_training_forward_and_gradients_vs_cpu_oracle(big_model_cpu)
     assert abs(loss.item() - want["loss"]) <= 1e-4 * max(abs(want["loss"]), 1e-3)
     loss.backward()
     grads = dict((n, p.grad.cpu().numpy()) for n, p in m.named_parameters())
-    # fp32 on both sides; what differs is the summation order of 81 convolutions' worth of dot products and of the batch
-    # statistics (B = 4: only 324 elements per channel, so 1/std amplifies every rounding difference 82 times over).
-    # Measured 1.0e-4 .. 2.6e-4 relative L2 over the tower (it varies from box to box with the atomics' order): bar 5e-4,
-    # with direction and norm pinned much tighter below.
+    # Gradients: fp32 on both sides, so what differs is summation order (81 convolutions, 82 batch-statistics layers over
+    # only B*81 = 324 elements per channel). The yardstick is the SAME oracle in float64: the kernels must be as close to
+    # it as the reference's own fp32 arithmetic is (within a factor 4, floor 1e-4) — measured 1e-4 .. 5e-4 for both.
+    _, _, _, _, exact_g = oracle_step(big_model_cpu, batch, 40, dtype=torch.float64)
+    report = {}
     for name in BIG_TENSORS:
-        assert rel_l2(grads[name], want_g[name].numpy()) < 5e-4, (name, rel_l2(grads[name], want_g[name].numpy()))
+        exact = exact_g[name].numpy()
+        report[name] = (rel_l2(grads[name], exact), rel_l2(want_g[name].numpy(), exact))
+    bad = {k: v for k, v in report.items() if not v[0] < max(4 * v[1], 1e-4)}
+    assert not bad, report
     bad = check_grads(list(grads.items()), want_g, cos_min=0.9999, lo=0.999, hi=1.001)
     assert not bad, bad
 

@@ -150,3 +150,78 @@ def test_device_resident_buffer_guards():
     assert buf.size == 0
     buf.add(**ok)
     assert buf.size == 1 and buf.flatten()["observations"].is_cuda
+
+
+def _two_trainers(use_amp):
+    torch.manual_seed(0)
+    cfg = dict(num_blocks=2, channels=64, se_reduction=8, global_pool_channels=16, policy_channels=8, value_fc_size=16, score_fc_size=16)
+    a = build_model("se_resnet", dict(cfg)).to(DEV)
+    b = build_model("se_resnet", dict(cfg)).to(DEV)
+    b.load_state_dict(a.state_dict())
+    ta = KataGoPPOAlgorithm(KataGoPPOParams(batch_size=12, epochs_per_batch=1, use_amp=use_amp), a)
+    tb = KataGoPPOAlgorithm(KataGoPPOParams(batch_size=12, epochs_per_batch=1, use_amp=use_amp), b)
+    tb.fused_optimizer_tail = False          # stock path: foreach unscale + norm + PyTorch's fused Adam
+    return a, b, ta, tb
+
+
+@pytest.mark.parametrize("use_amp", [False, True])
+def test_fused_optimizer_tail_matches_torch_adam_and_keeps_state_dict(use_amp):
+    """global-norm + clip + Adam in two launches (csrc/optim.cu) against the stock sequence
+    (reference katago_ppo.py:926-933) over several steps, and the optimizer state stays a plain torch.optim.Adam state."""
+    a, b, ta, tb = _two_trainers(use_amp)
+    N, T, A = 6, 4, 11259
+    for rep in range(3):
+        for algo in (ta, tb):
+            buf = KataGoRolloutBuffer(N, (50, 9, 9), A)
+            _fill(buf, N, T, A, 40 + rep)
+            torch.manual_seed(100 + rep)
+            algo.update(buf, torch.zeros(N, device=DEV))
+    tol = dict(rtol=2e-2, atol=2e-3) if use_amp else dict(rtol=1e-4, atol=1e-6)   # bf16: side-stream atomics reorder the gradient's last bits
+    for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.allclose(p, q, **tol), n
+    sa, sb = ta.optimizer.state_dict(), tb.optimizer.state_dict()
+    assert sa["param_groups"] == sb["param_groups"] and sa["state"].keys() == sb["state"].keys()
+    for k in sa["state"]:
+        assert set(sa["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 3.0
+        assert torch.allclose(sa["state"][k]["exp_avg"], sb["state"][k]["exp_avg"], **tol)
+    # the state is interchangeable: a fresh torch Adam loads it (checkpoint.py:123 restores positionally) ...
+    fresh = torch.optim.Adam(a.parameters(), lr=ta.params.learning_rate, fused=True)
+    fresh.load_state_dict(sa)
+    # ... and the trainer keeps going on a replaced optimizer (katago_loop.py:1859 swaps `.optimizer` at seat rotation)
+    ta.optimizer = fresh
+    buf = KataGoRolloutBuffer(N, (50, 9, 9), A)
+    _fill(buf, N, T, A, 77)
+    before = [p.detach().clone() for p in a.parameters()]
+    m = ta.update(buf, torch.zeros(N, device=DEV))
+    assert all(np.isfinite(v) for v in m.values())
+    assert any(not torch.equal(x, y) for x, y in zip(before, a.parameters()))
+    assert float(fresh.state_dict()["state"][0]["step"]) == 4.0
+
+
+def test_fused_optimizer_tail_skips_non_finite_gradients():
+    """GradScaler semantics in the fused tail: a non-finite gradient leaves parameters, moments and step untouched and
+    halves the loss scale."""
+    a, _, ta, _ = _two_trainers(True)
+    N, T, A = 6, 2, 11259
+    buf = KataGoRolloutBuffer(N, (50, 9, 9), A)
+    _fill(buf, N, T, A, 5)
+    ta.update(buf, torch.zeros(N, device=DEV))              # one good step: state exists
+    scale0 = ta.scaler.get_scale()
+    before = [p.detach().clone() for p in a.parameters()]
+    step0 = float(ta.optimizer.state_dict()["state"][0]["step"])
+    km = ta._kernel_model(torch.device(DEV))
+    g = torch.Generator().manual_seed(1)
+    obs = torch.randn(12, 50, 9, 9, generator=g).to(DEV)
+    mask = torch.ones(12, A, dtype=torch.bool, device=DEV)
+    z = torch.zeros(12, device=DEV)
+    mb = (mask, torch.zeros(12, dtype=torch.long, device=DEV), z, z + 1, torch.zeros(12, dtype=torch.long, device=DEV), z, z)
+    a.train()
+    ta._step_fused(km, obs, mb, None)
+    ta._flat_grad[123] = float("inf")
+    ta._optimizer_tail()
+    torch.cuda.synchronize()
+    for x, y in zip(before, a.parameters()):
+        assert torch.equal(x, y)
+    assert float(ta.optimizer.state_dict()["state"][0]["step"]) == step0
+    assert ta.scaler.get_scale() == scale0 * 0.5
