@@ -63,7 +63,9 @@ def test_loss_and_sampler_kernels_packed_equals_bytes(dtype):
         r1 = policy_ops.policy_sample(logits, bits, vl, seed=11, offset=5, forced_actions=forced)
         for a, b in zip(r0, r1):
             assert torch.equal(a, b)
-        assert mask[torch.arange(B, device=DEV), r1[0]].all()
+        if forced is None:
+            assert mask[torch.arange(B, device=DEV), r1[0]].all()
+            assert int(r1[0][5]) == 77                             # the row with a single legal action
     # zero-legal row is flagged identically
     bad = mask.clone(); bad[9] = False
     f0 = policy_ops.policy_sample(logits, bad, vl, seed=1, offset=1)[4]
