@@ -447,21 +447,31 @@ def run_ours(args) -> None:
 
 
 class RolloutIngest:
-    """End-to-end rollout step from HOST buffers through the public `select_actions` call: pinned host observations +
-    legal masks -> device (H2D inside the timed region), action selection, D2H of actions / log-probs / values."""
+    """End-to-end rollout step from HOST buffers through the public API: `keisei_b200.ingest.PinnedIngest` (pinned,
+    double-buffered host -> device transfer of observations + legal masks, inside the timed region) -> `select_actions`
+    -> device -> host read of actions / log-probs / values. The transfer of step k+1 is submitted before the forward of
+    step k, as a caller with the next observations in hand would."""
 
     def __init__(self, algo, obs_cpu, mask_cpu, device) -> None:
+        from keisei_b200.ingest import PinnedIngest
         self.algo, self.device = algo, device
-        self.h_obs, self.h_mask = obs_cpu.pin_memory(), mask_cpu.pin_memory()
         n = obs_cpu.shape[0]
+        # two distinct host batches in page-locked memory (the contract's "pinned host memory")
+        self.src = [(obs_cpu.pin_memory(), mask_cpu.pin_memory()), (obs_cpu.flip(0).contiguous().pin_memory(), mask_cpu.flip(0).contiguous().pin_memory())]
+        self.ingest = PinnedIngest(device, n, tuple(obs_cpu.shape[1:]), mask_cpu.shape[1], depth=2, pack_masks=True)
         self.h_out = [torch.empty(n, dtype=torch.int64).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n).pin_memory()]
-        self.h2d_bytes = self.h_obs.numel() * 4 + self.h_mask.numel()
+        self.h2d_bytes = obs_cpu.numel() * 4 + mask_cpu.numel()
         self.d2h_bytes = n * 16
+        self.k = 0
+        self.slot = self.ingest.submit(*self.src[0])
 
     def step(self) -> None:
-        d_obs = self.h_obs.to(self.device, non_blocking=True)
-        d_mask = self.h_mask.to(self.device, non_blocking=True)
+        cur = self.slot
+        self.k += 1
+        self.slot = self.ingest.submit(*self.src[self.k & 1])      # next step's observations: staged + H2D while this step computes
+        d_obs, d_mask = self.ingest.get(cur)
         a, lp, v = self.algo.select_actions(d_obs, d_mask)
+        self.ingest.release(cur)
         self.h_out[0].copy_(a, non_blocking=True); self.h_out[1].copy_(lp, non_blocking=True); self.h_out[2].copy_(v, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
 

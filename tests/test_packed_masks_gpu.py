@@ -173,3 +173,36 @@ def test_device_buffer_stores_packed_masks_and_update_matches_host_buffer():
         assert res[0][0][k] == pytest.approx(res[1][0][k], rel=1e-6, abs=1e-8), k
     for a, b in zip(res[0][1], res[1][1]):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+
+
+def test_pinned_ingest_double_buffer_delivers_each_step_intact():
+    """keisei_b200.ingest.PinnedIngest (reference katago_loop.py:1529-1530): pinned, double-buffered
+    host -> device transfer with optional bit-packing; slots are reused safely and `select_actions` consumes them."""
+    from keisei_b200.ingest import PinnedIngest
+    N = 40
+    ing = PinnedIngest(DEV, N, (50, 9, 9), A, depth=2, pack_masks=True)
+    g = torch.Generator().manual_seed(0)
+    steps = []
+    for k in range(5):
+        n = N if k != 3 else 17                                    # a ragged step (fewer live envs)
+        obs = torch.randn(n, 50, 9, 9, generator=g)
+        mask = torch.rand(n, A, generator=g) < 0.01
+        mask[:, k] = True
+        steps.append((obs.numpy() if k % 2 else obs, mask.numpy() if k % 2 else mask, obs, mask))
+    torch.manual_seed(0)
+    m = build_model("se_resnet", dict(TINY)).to(DEV)
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(), m)
+    slot = ing.submit(steps[0][0], steps[0][1])
+    for k in range(5):
+        cur = slot
+        if k + 1 < 5:
+            slot = ing.submit(steps[k + 1][0], steps[k + 1][1])   # next step in flight while this one is consumed
+        d_obs, d_bits = ing.get(cur)
+        assert d_bits.dtype == torch.int32 and d_obs.is_cuda
+        assert torch.equal(d_obs.cpu(), steps[k][2])
+        assert torch.equal(policy_ops.unpack_mask_bits(d_bits, A).cpu(), steps[k][3])
+        a, lp, v = algo.select_actions(d_obs, d_bits)
+        ing.release(cur)
+        assert steps[k][3][torch.arange(d_obs.shape[0]), a.cpu()].all()
+    with pytest.raises(ValueError, match="unexpected shapes"):
+        ing.submit(torch.zeros(3, 46, 9, 9), torch.zeros(3, A, dtype=torch.bool))
