@@ -183,6 +183,14 @@ int kb_peer_allreduce_f64(void* buf, long long n, const kb_peer_ctx* ctx, unsign
 int kb_peer_allreduce_emulate(void* const* bufs, long long n, kb_peer_ctx* const* ctxs, int world, kb_stream_t stream);
 /* a kb_allreduce_hook: user = kb_peer_ctx* */
 int kb_peer_allreduce_hook(void* user, void* buf, long long n_doubles, kb_stream_t stream);
+/* Gradient-bucket hook of the backward schedules (replaces DDP's bucketed overlap, katago_loop.py:498-504). When set (per
+ * host thread; NULL clears), kb_seresnet_backward[_sync] calls it right after the kernels producing the gradients of
+ * parameters [first_param, first_param + n_params) have been enqueued: once for the heads (bucket = num_blocks), then for
+ * every residual block from the last (bucket = num_blocks - 1) down to 0. The stem (parameters 0..2) finishes with the
+ * call itself. `main_stream` / `side_stream` are the two streams those kernels were enqueued on (record an event on
+ * both). A non-zero return aborts the backward with an error. */
+typedef int (*kb_bucket_hook)(void* user, int bucket, int first_param, int n_params, kb_stream_t main_stream, kb_stream_t side_stream);
+int kb_seresnet_set_bucket_hook(kb_bucket_hook hook, void* user);
 /* grads: float32 buffers shaped like params, PRE-ZEROED by the caller */
 int kb_seresnet_backward(const kb_seresnet_desc* d, const void* const* params, const void* wpack, int B,
                          int dtype, void* workspace, long long ws_bytes, const void* dpolicy,
@@ -209,6 +217,14 @@ int kb_resnet_forward(const kb_resnet_desc* d, const void* const* params, void* 
                       const void* wpack, const float* obs, int B, int training, int dtype, void* workspace,
                       long long ws_bytes, void* policy_out, long long policy_pitch, float* value_out, int use_tc,
                       int num_sms, kb_stream_t stream);
+/* Gradient-bucket hook of the backward schedules (replaces DDP's bucketed overlap, katago_loop.py:498-504). When set (per
+ * host thread; NULL clears), kb_seresnet_backward[_sync] calls it right after the kernels producing the gradients of
+ * parameters [first_param, first_param + n_params) have been enqueued: once for the heads (bucket = num_blocks), then for
+ * every residual block from the last (bucket = num_blocks - 1) down to 0. The stem (parameters 0..2) finishes with the
+ * call itself. `main_stream` / `side_stream` are the two streams those kernels were enqueued on (record an event on
+ * both). A non-zero return aborts the backward with an error. */
+typedef int (*kb_bucket_hook)(void* user, int bucket, int first_param, int n_params, kb_stream_t main_stream, kb_stream_t side_stream);
+int kb_seresnet_set_bucket_hook(kb_bucket_hook hook, void* user);
 /* grads: float32 buffers shaped like params, PRE-ZEROED by the caller */
 int kb_resnet_backward(const kb_resnet_desc* d, const void* const* params, const void* wpack, int B, int dtype,
                        void* workspace, long long ws_bytes, const void* dpolicy, long long policy_pitch,

@@ -195,6 +195,13 @@ int wgrad3x3(const Dims& m, const void* x, const void* dy, float* dw, int Cin, i
 // tcgen05 Linear path: bf16 activations, every K a multiple of 64 after padding the small hidden sizes
 bool lin_tc(const Dims& m, int use_tc) { return use_tc && m.dtype == KB_BF16 && m.C % 64 == 0 && m.B >= 1; }
 
+// Gradient-bucket hook of the backward schedule (data-parallel overlap, reference katago_loop.py:498-504: DDP overlaps
+// its 25 MB gradient buckets with the backward): called on the host, per thread, right after the kernels that produce a
+// contiguous run of parameter gradients have been enqueued — the heads first, then every residual block from the last
+// to the first. The callee records events on the two streams and launches its collective behind them.
+thread_local kb_bucket_hook g_bucket_hook = nullptr;
+thread_local void* g_bucket_user = nullptr;
+
 int check_desc(const kb_seresnet_desc* d) {
   KB_CHECK_ARG(d != nullptr, "null model descriptor");
   KB_CHECK_ARG(d->num_blocks >= 0 && d->num_blocks <= 1024, "num_blocks out of range");
@@ -205,6 +212,12 @@ int check_desc(const kb_seresnet_desc* d) {
 }
 
 }  // namespace
+
+extern "C" int kb_seresnet_set_bucket_hook(kb_bucket_hook hook, void* user) {
+  g_bucket_hook = hook;
+  g_bucket_user = user;
+  return KB_OK;
+}
 
 extern "C" long long kb_seresnet_num_params(const kb_seresnet_desc* d) { return d ? 16 + 14LL * d->num_blocks : -1; }
 extern "C" long long kb_seresnet_num_buffers(const kb_seresnet_desc* d) { return d ? 6 + 6LL * d->num_blocks : -1; }
@@ -597,6 +610,13 @@ extern "C" int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* 
   }
   cudaStream_t wst = overlap ? side.s : st;
   auto ev = [&](int blk, int k) { return side.ev[4 * blk + k]; };
+  auto bucket_ready = [&](int bucket, int first_param, int n_params) -> int {
+    if (g_bucket_hook == nullptr) return KB_OK;
+    const int hr = g_bucket_hook(g_bucket_user, bucket, first_param, n_params, (kb_stream_t)st, (kb_stream_t)wst);
+    if (hr != 0) { kb_set_error("gradient bucket hook failed (rc=%d)", hr); return KB_ERR_INVALID; }
+    return KB_OK;
+  };
+  KB_TRY(bucket_ready(m.nb, pi_head(m, 0), 13));   // policy / value / score head gradients are complete
   // dL/dx_last = policy path + global-pool backward
   void *cur = w.d0, *t1 = w.d1, *t2 = w.d2, *t3 = w.d3;
   {
@@ -696,6 +716,7 @@ extern "C" int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* 
     if (overlap && i + 1 < m.nb) KB_CUDA_CHECK(cudaStreamWaitEvent(st, ev(i + 1, 3), 0));
     KB_TRY(kbk_block_bwd_dx(pd, st));
     void* nc = t3; t3 = t2; t2 = t1; t1 = cur; cur = nc;
+    KB_TRY(bucket_ready(i, pi_blk(i, 0), 14));     // all 14 gradients of block i are enqueued (weight gradients on `wst`)
   }
   if (overlap) {  // join: the stem's weight gradient reuses the partial-tile workspace, and the caller sees one stream
     KB_CUDA_CHECK(cudaEventRecord(side.ev[4 * m.nb], wst));

@@ -4,7 +4,10 @@ DistributedDataParallel + SyncBatchNorm wrap (katago_loop.py:494-508).
 One process per GPU (torchrun env: RANK / LOCAL_RANK / WORLD_SIZE), NCCL over NVLink 5 / NVSwitch
 for CUDA, gloo for CPU tests. The PPO update's only exchange step is the gradient average: the
 keisei_b200 backward emits every parameter gradient in ONE flat fp32 buffer (213.7 MB for the
-40x256 model), so the exchange is a single `all_reduce` — no bucketing, NVLS-eligible. Rollout
+40x256 model); its residual blocks are contiguous runs of that buffer, finished from the last block to
+the first, so the exchange is a handful of ~25 MB `all_reduce` calls on a communication stream, each
+launched as soon as the backward schedule has enqueued its bucket's kernels (`kb_bucket_hook`) —
+DDP's bucketed overlap without DDP. Rollout
 inference shards by process with no collective. Per-rank semantics are the reference's:
 `batch_size`, GAE and advantage normalisation are per rank; gradients are averaged; parameters are
 broadcast from rank 0 at construction.
@@ -280,12 +283,23 @@ class GradSync:
     of `bucket_bytes`, reduced, and copied back.
     """
 
-    def __init__(self, process_group=None, bucket_bytes: int = 256 << 20) -> None:
+    def __init__(self, process_group=None, bucket_bytes: int = 25 << 20, overlap: bool = True) -> None:
         if not dist.is_initialized():
             raise RuntimeError("GradSync needs an initialised process group (setup_distributed)")
         self.group = process_group
         self.world_size = dist.get_world_size(process_group)
-        self.bucket_bytes = bucket_bytes
+        self.bucket_bytes = bucket_bytes     # DDP's default bucket size (reference katago_loop.py:498-504 keeps it)
+        # fused CUDA path: all-reduce each bucket on a communication stream as soon as the backward schedule has enqueued
+        # the kernels that produce it (kb_bucket_hook), so only the last bucket (the stem) is exposed
+        self.overlap = overlap
+        self.last_overlap_buckets = 0
+        self._comm_streams: dict = {}
+
+    def comm_stream(self, device: torch.device) -> "torch.cuda.Stream":
+        s = self._comm_streams.get(device)
+        if s is None:
+            s = self._comm_streams[device] = torch.cuda.Stream(device)
+        return s
 
     @torch.no_grad()
     def broadcast_parameters(self, module: torch.nn.Module, src: int = 0) -> None:

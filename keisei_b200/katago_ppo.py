@@ -648,10 +648,15 @@ class KataGoPPOAlgorithm:
         self.optimizer.zero_grad(set_to_none=True)
         self.scaler.scale(loss).backward()
         with torch.no_grad():
+            gs = self.grad_sync
+            overlapped = gs is not None and int(gs.world_size) > 1 and getattr(gs, "overlap", False)
             flat = model_ops.seresnet_backward_raw(tables, wpack, ws, policy_buf.grad, value.grad, score.grad, code,
-                                                   bool(km.use_tensor_cores), km._grad_sizes, km.bn_sync)
-            if self.grad_sync is not None:
-                self.grad_sync.all_reduce_flat(flat)
+                                                   bool(km.use_tensor_cores), km._grad_sizes, km.bn_sync,
+                                                   grad_sync=gs if overlapped else None)
+            if overlapped:
+                flat.div_(gs.world_size)     # the buckets came back summed over the ranks
+            elif gs is not None:
+                gs.all_reduce_flat(flat)
             self._flat_grad = flat   # every p.grad below is a view of it: the optimiser tail works on this one buffer
             off = 0
             for prm in params:

@@ -53,6 +53,8 @@ _lib.register_signature("kb_linear_tc", c_int, [_P, c_longlong, c_int, _P, c_int
 _lib.register_signature("kb_se_block_tail", c_int, [_P] * 13 + [c_int] + [_P] * 3 + [c_int, c_int, c_int, c_int, _P])
 _lib.register_signature("kb_se_block_tail_variant", c_int, [_P] * 13 + [c_int] + [_P] * 3 + [c_int, c_int, c_int, c_int, c_int, _P])
 
+_lib.register_signature("kb_seresnet_set_bucket_hook", c_int, [_P, _P])
+
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 _DT_INV = {0: torch.float32, 1: torch.bfloat16}
 _sm_count_cache: dict[int, int] = {}
@@ -109,6 +111,91 @@ class _NativeHook:
 
     def check(self) -> None:
         return None   # the kernels are only enqueued here; a lost peer is reported by sync.check() after the step's host read
+
+
+_BUCKET_HOOK_T = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p)
+
+
+class _BucketHook:
+    """Overlapped, bucketed gradient all-reduce (reference katago_loop.py:498-504: DDP's 25 MB buckets). The backward
+    schedule calls back as each run of parameter gradients has been enqueued (heads, then blocks last to first); blocks are
+    contiguous in the flat gradient, so consecutive callbacks extend one contiguous range, which is all-reduced on a
+    communication stream — behind events recorded on the schedule's two streams — as soon as it reaches `bucket_bytes`.
+    `finish()` reduces what is left (the stem and the last partial bucket) and joins everything back into the caller's
+    stream. Exceptions cannot cross the C frame: they are parked and re-raised by `finish()`."""
+
+    def __init__(self, flat: torch.Tensor, offsets: list[int], grad_sync) -> None:
+        import torch.distributed as dist
+        self.flat, self.offsets, self.sync, self.dist = flat, offsets, grad_sync, dist
+        self.dev = flat.device
+        self.comm = grad_sync.comm_stream(self.dev)
+        self.works: list = []
+        self.error: BaseException | None = None
+        self.lo = self.hi = None            # pending contiguous range [lo, hi) of flat elements
+        self.fired: list[tuple[int, int]] = []   # ranges already handed to a collective
+        self.bucket_elems = max(1, int(grad_sync.bucket_bytes) // 4)
+        self.launched = 0
+
+        def cb(_user, _bucket, first_param, n_params, main_stream, side_stream):
+            try:
+                lo, hi = self.offsets[first_param], self.offsets[first_param + n_params]
+                if self.lo is None:
+                    self.lo, self.hi = lo, hi
+                elif hi == self.lo:
+                    self.lo = lo
+                elif lo == self.hi:
+                    self.hi = hi
+                else:                       # not contiguous with the pending range: flush it first
+                    self._fire(main_stream, side_stream)
+                    self.lo, self.hi = lo, hi
+                if self.hi - self.lo >= self.bucket_elems:
+                    self._fire(main_stream, side_stream)
+                return 0
+            except BaseException as e:  # noqa: BLE001
+                self.error = e
+                return 1
+
+        self.fn = _BUCKET_HOOK_T(cb)
+        self.ptr = ctypes.cast(self.fn, c_void_p)
+
+    def _fire(self, main_stream, side_stream) -> None:
+        if self.lo is None or self.hi <= self.lo:
+            return
+        ev_main, ev_side = torch.cuda.Event(), torch.cuda.Event()
+        ev_main.record(torch.cuda.ExternalStream(main_stream, device=self.dev))
+        self.comm.wait_event(ev_main)
+        if side_stream and side_stream != main_stream:
+            ev_side.record(torch.cuda.ExternalStream(side_stream, device=self.dev))
+            self.comm.wait_event(ev_side)
+        with torch.cuda.stream(self.comm):
+            self.works.append(self.dist.all_reduce(self.flat[self.lo:self.hi], op=self.dist.ReduceOp.SUM, group=self.sync.group,
+                                                   async_op=True))
+        self.launched += 1
+        self.fired.append((self.lo, self.hi))
+        self.lo = self.hi = None
+
+    def finish(self) -> None:
+        """After the C call returned: reduce every range not yet handed to a collective and join the caller's stream."""
+        if self.error is not None:
+            raise self.error
+        cur = torch.cuda.current_stream(self.dev)
+        # the flat buffer is [stem | blocks 0..nb-1 | heads]; callbacks came heads first, then blocks in descending order:
+        # what is still missing is the pending range and whatever no callback covered (the stem) — the gaps of `fired`
+        if self.lo is not None:
+            self._fire(cur.cuda_stream, 0)
+        gaps, pos = [], 0
+        for lo, hi in sorted(self.fired):
+            if lo > pos:
+                gaps.append((pos, lo))
+            pos = max(pos, hi)
+        if pos < self.flat.numel():
+            gaps.append((pos, self.flat.numel()))
+        for lo, hi in gaps:
+            self.lo, self.hi = lo, hi
+            self._fire(cur.cuda_stream, 0)
+        for w in self.works:
+            w.wait()                      # the caller's current stream waits for the collective
+        self.works.clear()
 
 
 def _sync_args(ws: torch.Tensor, sync):
@@ -235,8 +322,10 @@ def seresnet_forward_raw(obs: torch.Tensor, tables: PointerTables, wpack: torch.
 @torch.no_grad()
 def seresnet_backward_raw(tables: PointerTables, wpack: torch.Tensor, ws: torch.Tensor, dpolicy: torch.Tensor,
                           dvalue: torch.Tensor, dscore: torch.Tensor, dtype_code: int, use_tc: bool,
-                          sizes: List[int] | None = None, bn_sync=None) -> torch.Tensor:
-    """The C backward without the dispatcher. Returns the flat fp32 gradient (parameter-table order)."""
+                          sizes: List[int] | None = None, bn_sync=None, grad_sync=None) -> torch.Tensor:
+    """The C backward without the dispatcher. Returns the flat fp32 gradient (parameter-table order). With `grad_sync`
+    (a `distributed.GradSync` of more than one rank, overlap enabled) the gradient comes back all-reduced (SUMMED over
+    the ranks; the caller divides): buckets are reduced on a communication stream while the backward is still running."""
     d = tables.desc
     dev = ws.device
     B = dvalue.shape[0]
@@ -254,14 +343,30 @@ def seresnet_backward_raw(tables: PointerTables, wpack: torch.Tensor, ws: torch.
         gt[i] = base + 4 * off
         off += n
     hook, hook_ptr, hook_user, world = _sync_args(ws, bn_sync)
+    bucket = None
+    if grad_sync is not None and int(grad_sync.world_size) > 1 and getattr(grad_sync, "overlap", False):
+        offsets = [0]
+        for n in sizes:
+            offsets.append(offsets[-1] + n)
+        bucket = _BucketHook(flat, offsets, grad_sync)
+    lib = _lib.load()
     with torch.cuda.device(dev):
-        rc = _lib.load().kb_seresnet_backward_sync(
-            ctypes.byref(d), tables.pt, wpack.data_ptr(), B, dtype_code, ws.data_ptr(), ws.numel(), dpol.data_ptr(),
-            dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), hook_ptr, hook_user, world,
-            _lib.stream_ptr(dev))
+        if bucket is not None:
+            lib.kb_seresnet_set_bucket_hook(bucket.ptr, None)
+        try:
+            rc = lib.kb_seresnet_backward_sync(
+                ctypes.byref(d), tables.pt, wpack.data_ptr(), B, dtype_code, ws.data_ptr(), ws.numel(), dpol.data_ptr(),
+                dpol.stride(0), dv.data_ptr(), ds.data_ptr(), gt, 1 if use_tc else 0, sm_count(dev), hook_ptr, hook_user, world,
+                _lib.stream_ptr(dev))
+        finally:
+            if bucket is not None:
+                lib.kb_seresnet_set_bucket_hook(None, None)
     if hook is not None:
         hook.check()
     _lib.check(rc, "kb_seresnet_backward")
+    if bucket is not None:
+        bucket.finish()
+        grad_sync.last_overlap_buckets = bucket.launched
     return flat
 
 

@@ -52,7 +52,7 @@ def main() -> None:
             for p in model.parameters():
                 p.add_(0.05 * torch.randn_like(p))
     algo = KataGoPPOAlgorithm(KataGoPPOParams(use_amp=(mode == "bf16"), batch_size=bl), model)
-    algo.grad_sync = GradSync()
+    algo.grad_sync = GradSync(bucket_bytes=1 << 20)     # small buckets: several overlapped all-reduces even on this small model
     algo.grad_sync.broadcast_parameters(model)
     sync = PeerBatchNormSync() if kind == "peer" else BatchNormSync()
     model.convert_sync_batchnorm(sync)
@@ -60,6 +60,7 @@ def main() -> None:
     obs, mask, acts, old, adv, cats, score_t = batch
     model.train()
     pl, vl, sl, ent, _ = algo._step_fused(model, obs, (mask, acts, old, adv, cats, score_t, adv), None)
+    assert algo.grad_sync.last_overlap_buckets >= 3, algo.grad_sync.last_overlap_buckets   # bucketed, overlapped exchange ran
     scale = float(algo.scaler.get_scale()) if algo.scaler.is_enabled() else 1.0
     flat = (algo._flat_grad / scale).clone()
     algo._optimizer_tail()
