@@ -158,14 +158,18 @@ class _BucketHook:
         self.fn = _BUCKET_HOOK_T(cb)
         self.ptr = ctypes.cast(self.fn, c_void_p)
 
+    def _stream(self, handle):
+        """cudaStream_t handle from the C side -> torch stream (NULL is the legacy default stream)."""
+        return torch.cuda.ExternalStream(int(handle), device=self.dev) if handle else torch.cuda.default_stream(self.dev)
+
     def _fire(self, main_stream, side_stream) -> None:
         if self.lo is None or self.hi <= self.lo:
             return
         ev_main, ev_side = torch.cuda.Event(), torch.cuda.Event()
-        ev_main.record(torch.cuda.ExternalStream(main_stream, device=self.dev))
+        ev_main.record(self._stream(main_stream))
         self.comm.wait_event(ev_main)
         if side_stream and side_stream != main_stream:
-            ev_side.record(torch.cuda.ExternalStream(side_stream, device=self.dev))
+            ev_side.record(self._stream(side_stream))
             self.comm.wait_event(ev_side)
         with torch.cuda.stream(self.comm):
             self.works.append(self.dist.all_reduce(self.flat[self.lo:self.hi], op=self.dist.ReduceOp.SUM, group=self.sync.group,
@@ -363,6 +367,8 @@ def seresnet_backward_raw(tables: PointerTables, wpack: torch.Tensor, ws: torch.
                 lib.kb_seresnet_set_bucket_hook(None, None)
     if hook is not None:
         hook.check()
+    if bucket is not None and bucket.error is not None:
+        raise bucket.error
     _lib.check(rc, "kb_seresnet_backward")
     if bucket is not None:
         bucket.finish()
