@@ -273,11 +273,10 @@ def conv_roofline(device, reps: int = 20) -> dict:
     flops = CONV_FLOP_PER_POS * B
     achieved = flops / (ms * 1e-3) / 1e12
     peak = pk["bf16_tflops"]
-    return {"kernel": "conv3x3_tc 256->256 B=4096", "bound": "tensor", "achieved": round(achieved, 1), "peak": peak,
+    return {"kernel": "conv3x3_tc2 (cta_group::2) 256->256 B=4096", "bound": "tensor", "achieved": round(achieved, 1), "peak": peak,
             "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture under profiles/
-            "traffic": CONV_TRAFFIC_BYTES, "ms": round(ms, 4), "peak_src": f"{pk['source']} burst",
-            "frac_sustained": round(achieved / pk["bf16_tflops_sustained"], 4)}
+            "traffic": CONV_TRAFFIC_BYTES, "ms": round(ms, 4), "peak_src": f"{pk['source']} burst"}
 
 
 def hbm_kernels(device) -> dict:
@@ -421,7 +420,7 @@ def run_ours(args) -> None:
             line["cpu_baseline"] = cpu_baseline()
             c1 = cpu_config1()
             detail["cpu_config1"] = c1
-            line["cpu_config1_4x64_b256_fwdbwd"] = {"value": round(c1["value"], 1), "unit": "samples/s", "cores": c1["cores"]}
+            line["cpu_config1"] = {"value": round(c1["value"], 1), "unit": "samples/s", "cores": c1["cores"]}   # 4x64 b256 PPO fwd+bwd
             line["cpu_baseline"]["value"] = round(line["cpu_baseline"]["value"], 2)
             if upd is not None:
                 cu = cpu_update_baseline()

@@ -979,6 +979,7 @@ int kbk_conv3x3_tc_mode(const void* in, const void* w, void* out, int B, int Cin
       case kEpiAffine: KB_PAIR(kEpiAffine);
       case kEpiAffine | kEpiRelu | kEpiPool: KB_PAIR(kEpiAffine | kEpiRelu | kEpiPool);
       case kEpiAffine | kEpiBoard: KB_PAIR(kEpiAffine | kEpiBoard);
+      case kEpiMask | kEpiSum | kEpiDot | kEpiBoard: KB_PAIR(kEpiMask | kEpiSum | kEpiDot | kEpiBoard);
       default: break;   // rarely used feature sets stay on the single-CTA kernel
     }
 #undef KB_PAIR

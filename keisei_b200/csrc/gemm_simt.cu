@@ -57,15 +57,17 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
 // bf16 / AMP path only, where the reference itself computes these Linear layers in bf16 under autocast (TF32 keeps 3
 // more mantissa bits); the fp32 path keeps exact fp32 FMAs. These GEMMs are far too small for a tcgen05 pipeline to
 // pay off (K or N of 32..768) but large enough (M = 8192 boards) to be CUDA-core bound as SIMT.
+// (bx, by, bz) = (N tile, M tile, K slice) of this CTA: blockIdx for a plain launch, decoded from a linear tile index in
+// a grouped launch
 template <int BM, bool TF32>
-__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g, int k_per_slice, int a_vec, int b_vec) {
+__device__ __forceinline__ void gemm_body(const GemmArgs& g, int k_per_slice, int a_vec, int b_vec, int bx, int by, int bz) {
   constexpr int TM = BM / 16;  // rows per thread (4 or 2)
   constexpr int PAD = TF32 ? 8 : 4;  // +8: the (k = lane%4, m = lane/4) fragment reads hit 32 distinct banks
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int k_begin = blockIdx.z * k_per_slice;
+  const int m0 = by * BM, n0 = bx * BN;
+  const int k_begin = bz * k_per_slice;
   const int k_end = min(g.K, k_begin + k_per_slice);
   float acc[TM][4];
 #pragma unroll
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g, int k_per_slice, 
     long long crow;
     if (g.c_group_rows > 0) crow = ((long long)gm / g.c_group_rows) * g.c_group_pitch + ((long long)gm % g.c_group_rows) * g.ldc;
     else crow = (long long)gm * g.ldc;
-    if (g.bias && blockIdx.z == 0) v += g.bias[gn];
+    if (g.bias && bz == 0) v += g.bias[gn];
     if (g.splitk > 1) {
       atomicAdd(((float*)g.C) + crow + gn, v);
     } else {
@@ -204,13 +206,20 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g, int k_per_slice, 
   }
 }
 
+template <int BM, bool TF32>
+__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g, int k_per_slice, int a_vec, int b_vec) {
+  gemm_body<BM, TF32>(g, k_per_slice, a_vec, b_vec, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
 // out[n] += sum_m X[m][n]; block (32, 8)
-__global__ void colsum_kernel(const void* __restrict__ X, int dtype, long long ldx, int group_rows, long long group_pitch,
-                              int M, int N, int rows_per_block, float* out) {
+struct ColsumArgs { const void* X; int dtype; long long ldx; int group_rows; long long group_pitch; int M, N, rows_per_block; float* out; };
+
+__device__ __forceinline__ void colsum_body(const void* __restrict__ X, int dtype, long long ldx, int group_rows, long long group_pitch,
+                                            int M, int N, int rows_per_block, float* out, int bx, int by) {
   __shared__ float sh[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int n = blockIdx.y * 32 + cx;
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  const int n = by * 32 + cx;
+  const int r0 = bx * rows_per_block, r1 = min(M, r0 + rows_per_block);
   float s = 0.f;
   if (n < N)
     for (int r = r0 + ry; r < r1; r += 8) {
@@ -227,6 +236,49 @@ __global__ void colsum_kernel(const void* __restrict__ X, int dtype, long long l
     atomicAdd(&out[n], a);
   }
 }
+
+__global__ void colsum_kernel(const void* __restrict__ X, int dtype, long long ldx, int group_rows, long long group_pitch,
+                              int M, int N, int rows_per_block, float* out) {
+  colsum_body(X, dtype, ldx, group_rows, group_pitch, M, N, rows_per_block, out, blockIdx.x, blockIdx.y);
+}
+
+// Several independent small GEMMs and column sums as ONE launch (grouped): the Linear-layer backward of a block is four
+// latency-bound GEMMs of a few dozen tiles each plus two bias-gradient column sums — issued one after the other they cost
+// a launch latency apiece and never fill the GPU; grouped, the independent ones run side by side. Tiles are numbered
+// linearly over the problems; every CTA decodes its problem and its (N tile, M tile, K slice).
+constexpr int kMaxGroupGemms = 4, kMaxGroupColsums = 4;
+struct GemmGroup {
+  GemmArgs g[kMaxGroupGemms];
+  int kps[kMaxGroupGemms], a_vec[kMaxGroupGemms], b_vec[kMaxGroupGemms], nx[kMaxGroupGemms], ny[kMaxGroupGemms];
+  int first[kMaxGroupGemms + 1];                 // first linear tile of each GEMM; first[n] = start of the column sums
+  int n;
+  ColsumArgs cs[kMaxGroupColsums];
+  int cs_first[kMaxGroupColsums + 1], cs_nx[kMaxGroupColsums];
+  int ncs;
+};
+
+template <bool TF32>
+__global__ void __launch_bounds__(256) gemm_group_kernel(const __grid_constant__ GemmGroup G) {
+  const int t = blockIdx.x;
+  if (t < G.first[G.n]) {
+    int p = 0;
+    while (p + 1 < G.n && t >= G.first[p + 1]) ++p;
+    const int local = t - G.first[p];
+    const int bx = local % G.nx[p], by = (local / G.nx[p]) % G.ny[p], bz = local / (G.nx[p] * G.ny[p]);
+    gemm_body<64, TF32>(G.g[p], G.kps[p], G.a_vec[p], G.b_vec[p], bx, by, bz);
+    return;
+  }
+  const int u = t - G.first[G.n];
+  int q = 0;
+  while (q + 1 < G.ncs && u >= G.cs_first[q + 1]) ++q;
+  const int local = u - G.cs_first[q];
+  const ColsumArgs& c = G.cs[q];
+  colsum_body(c.X, c.dtype, c.ldx, c.group_rows, c.group_pitch, c.M, c.N, c.rows_per_block, c.out, local % G.cs_nx[q], local / G.cs_nx[q]);
+}
+
+// deferral: while a group is open on this host thread, kbk_gemm / kbk_colsum append to it instead of launching
+struct PendingGroup { GemmGroup grp; bool open; int tf32; };
+thread_local PendingGroup g_pending = {{}, false, 0};
 
 // can every 4-element group of this operand be fetched with one aligned vector load?
 bool vec4_ok(const void* p, int dtype, long long ld, int group_rows, long long group_pitch) {
@@ -253,6 +305,15 @@ int kbk_gemm(const GemmArgs& g, cudaStream_t st) {
   // K offset of every slice is a multiple of 16, so alignment reduces to base/ld divisibility
   const int a_vec = vec4_ok(g.A, g.a_dtype, g.lda, g.a_group_rows, g.a_group_pitch) ? 1 : 0;
   const int b_vec = vec4_ok(g.B, g.b_dtype, g.ldb, 0, 0) ? 1 : 0;
+  if (g_pending.open && g_pending.grp.n < kMaxGroupGemms && (g_pending.grp.n + g_pending.grp.ncs == 0 || g_pending.tf32 == (g.tf32 ? 1 : 0))) {
+    GemmGroup& G = g_pending.grp;
+    const int p = G.n++;
+    g_pending.tf32 = g.tf32 ? 1 : 0;
+    G.g[p] = a; G.kps[p] = kps; G.a_vec[p] = a_vec; G.b_vec[p] = b_vec;
+    G.nx[p] = kb_ceil_div(g.N, BN); G.ny[p] = kb_ceil_div(g.M, 64);
+    G.first[p + 1] = G.first[p] + G.nx[p] * G.ny[p] * splitk;
+    return KB_OK;
+  }
   const long long tiles64 = (long long)kb_ceil_div(g.N, BN) * kb_ceil_div(g.M, 64) * splitk;
   if (g.tf32) {
     gemm_kernel<64, true><<<dim3(kb_ceil_div(g.N, BN), kb_ceil_div(g.M, 64), splitk), 256, 0, st>>>(a, kps, a_vec, b_vec);
@@ -269,7 +330,45 @@ int kbk_colsum(const void* X, int dtype, long long ldx, int group_rows, long lon
                cudaStream_t st) {
   if (M == 0) return KB_OK;
   const int rpb = 1024;
+  if (g_pending.open && g_pending.grp.ncs < kMaxGroupColsums) {
+    GemmGroup& G = g_pending.grp;
+    const int q = G.ncs++;
+    G.cs[q] = ColsumArgs{X, dtype, ldx, group_rows, group_pitch, M, N, rpb, out};
+    G.cs_nx[q] = kb_ceil_div(M, rpb);
+    G.cs_first[q + 1] = G.cs_first[q] + G.cs_nx[q] * kb_ceil_div(N, 32);
+    return KB_OK;
+  }
   colsum_kernel<<<dim3(kb_ceil_div(M, rpb), kb_ceil_div(N, 32)), 256, 0, st>>>(X, dtype, ldx, group_rows, group_pitch, M, N, rpb, out);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
+}
+
+// ---- grouped launches (see GemmGroup) ----
+int kbk_gemm_group_begin() {
+  KB_CHECK_ARG(!g_pending.open, "gemm group: already open on this thread");
+  memset(&g_pending.grp, 0, sizeof(g_pending.grp));
+  g_pending.open = true;
+  g_pending.tf32 = 0;
+  return KB_OK;
+}
+
+// launches what has been collected (one kernel) and keeps the group open for the next batch of independent problems
+int kbk_gemm_group_flush(cudaStream_t st) {
+  KB_CHECK_ARG(g_pending.open, "gemm group: not open");
+  GemmGroup& G = g_pending.grp;
+  const int tiles = G.first[G.n] + G.cs_first[G.ncs];
+  if (tiles > 0) {
+    if (g_pending.tf32) gemm_group_kernel<true><<<(unsigned)tiles, 256, 0, st>>>(G);
+    else gemm_group_kernel<false><<<(unsigned)tiles, 256, 0, st>>>(G);
+    KB_CUDA_LAUNCH_CHECK();
+  }
+  memset(&G, 0, sizeof(G));
+  return KB_OK;
+}
+
+int kbk_gemm_group_end(cudaStream_t st) {
+  if (!g_pending.open) return KB_OK;
+  const int r = kbk_gemm_group_flush(st);
+  g_pending.open = false;
+  return r;
 }

@@ -67,6 +67,11 @@ struct GemmArgs {
   int tf32;                                                // inner product as TF32 tensor-core MMAs (bf16 / AMP path only)
 };
 int kbk_gemm(const GemmArgs& g, cudaStream_t st);
+// Grouped launches: between begin and end (per host thread) kbk_gemm / kbk_colsum calls are COLLECTED (up to 4 + 4) and
+// run as one kernel at the next flush / end — for problems that are independent of one another.
+int kbk_gemm_group_begin();
+int kbk_gemm_group_flush(cudaStream_t st);
+int kbk_gemm_group_end(cudaStream_t st);
 // out[n] += sum_m X[m][n]  (X may be board-pitched like GemmArgs.A)
 int kbk_colsum(const void* X, int dtype, long long ldx, int group_rows, long long group_pitch, int M, int N,
                float* out, cudaStream_t st);

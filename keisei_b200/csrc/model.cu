@@ -684,11 +684,18 @@ extern "C" int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* 
       if (overlap && !wg_first) KB_TRY(conv2_wgrad());
     }
     KB_TRY(bn_bwd_fin(pi_blk(i, 1), l1, G(pi_blk(i, 1)), G(pi_blk(i, 2)), C));
-    // global-pool-bias MLP backward -> gradient wrt the pool statistics of the block input
-    KB_TRY(linear_bwd_w(w.dg, KB_F32, C, bw.gh, KB_F32, m.G, B, C, m.G, G(pi_blk(i, 8)), G(pi_blk(i, 9)), st));
-    KB_TRY(linear_bwd_x(w.dg, KB_F32, C, B, C, P(pi_blk(i, 8)), m.G, w.dgh, KB_F32, m.G, bw.gh, m.G, 0, st));
-    KB_TRY(linear_bwd_w(w.dgh, KB_F32, m.G, pool_in, KB_F32, 3 * C, B, m.G, 3 * C, G(pi_blk(i, 6)), G(pi_blk(i, 7)), st));
-    KB_TRY(linear_bwd_x(w.dgh, KB_F32, m.G, B, m.G, P(pi_blk(i, 6)), 3 * C, w.dpool, KB_F32, 3 * C, nullptr, 0, 0, st));
+    // global-pool-bias MLP backward -> gradient wrt the pool statistics of the block input: four small GEMMs and two
+    // bias column sums as TWO grouped launches (the members of a group are independent of one another)
+    {
+      GemmGroupScope grp(st);
+      KB_TRY(grp.status());
+      KB_TRY(linear_bwd_w(w.dg, KB_F32, C, bw.gh, KB_F32, m.G, B, C, m.G, G(pi_blk(i, 8)), G(pi_blk(i, 9)), st));
+      KB_TRY(linear_bwd_x(w.dg, KB_F32, C, B, C, P(pi_blk(i, 8)), m.G, w.dgh, KB_F32, m.G, bw.gh, m.G, 0, st));
+      KB_TRY(grp.flush());   // dgh is complete before anything reads it
+      KB_TRY(linear_bwd_w(w.dgh, KB_F32, m.G, pool_in, KB_F32, 3 * C, B, m.G, 3 * C, G(pi_blk(i, 6)), G(pi_blk(i, 7)), st));
+      KB_TRY(linear_bwd_x(w.dgh, KB_F32, m.G, B, m.G, P(pi_blk(i, 6)), 3 * C, w.dpool, KB_F32, 3 * C, nullptr, 0, 0, st));
+      KB_TRY(grp.close());
+    }
     // pass C: dz1 in place; conv1 weight + data gradients
     KB_TRY(kbk_bn_bwd_apply(t2, bw.z1, k1, k2, k3, m.M, C, dtype, st));
     auto conv1_wgrad = [&]() -> int {  // side stream: released at this point of the main stream

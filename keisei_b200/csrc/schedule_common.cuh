@@ -70,6 +70,17 @@ inline int linear_bwd_w(const void* dy, int dy_dtype, long long ldy, const void*
   return KB_OK;
 }
 
+// RAII wrapper of the grouped-launch deferral (kb_kernels.h): problems issued inside are collected and launched together
+// by flush() / close(); an early return through KB_TRY still ends the group (without leaving it open on the thread).
+struct GemmGroupScope {
+  cudaStream_t st; int rc; bool open;
+  explicit GemmGroupScope(cudaStream_t s) : st(s), rc(kbk_gemm_group_begin()), open(rc == KB_OK) {}
+  int status() const { return rc; }
+  int flush() { return kbk_gemm_group_flush(st); }
+  int close() { open = false; return kbk_gemm_group_end(st); }
+  ~GemmGroupScope() { if (open) kbk_gemm_group_end(st); }
+};
+
 #define KB_TRY(expr) do { int r__ = (expr); if (r__ != KB_OK) return r__; } while (0)
 
 // Side stream for the backward schedules: the weight-gradient convolutions (tensor-bound, 45 registers, no dependants
