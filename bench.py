@@ -37,7 +37,7 @@ ROLLOUT_B = 4096                                        # BASELINE.json configs[
 UPDATE_GLOBAL_B = 8192                                  # BASELINE.json configs[2]
 A = 11259
 WORKLOAD = "SE-ResNet 40x256 rollout, 4096 boards/GPU"
-CONV_TRAFFIC_BYTES = 306.0e6                            # ncu dram read+write per launch (profiles/, refreshed per round)
+CONV_TRAFFIC_BYTES = 303.8e6                            # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/ncu_r2_conv_pair.txt)
 CONV_FLOP_PER_POS = 2 * 81 * 256 * 2304                 # one 256->256 3x3 conv, SURVEY.md 8(d): 95.55 MFLOP
 FWD_FLOP_PER_POS = 18.66e6 + 80 * 95.55e6               # trunk convs only: 7.663 GFLOP
 

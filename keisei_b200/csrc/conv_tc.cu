@@ -475,7 +475,7 @@ constexpr uint32_t kIdescF16M256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32
 struct PairMaps { CUtensorMap full, rows5, x2, x7, rows3; };
 
 template <int F, bool kSeTail>
-__global__ void __launch_bounds__(kThreads2, 1)
+__global__ void __launch_bounds__(kThreads2, 1)   // 10 warps are allocated as 12 (groups of 4): 168 registers per thread at most
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ PairMaps mx,
                    bf16* __restrict__ out, int B, int Cin, int Cout, int num_groups, ConvEpi epi) {
   constexpr int kStages2 = PairCfg<kSeTail>::kStages;
