@@ -593,6 +593,17 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       const int c = ct * kTileM + lane_grp * 32 + lane;
       const int b0 = grp * kBoards;
       const int nb_valid = min(kBoards, B - b0);
+      if (kSeTail) {
+        // L2 prefetch of the whole residual tile of this warp (243 rows x 64 bytes = its 32 channels), 8 requests per
+        // lane, issued BEFORE waiting for the tile's MMAs: when pass 2 asks for them the register prefetches find their
+        // lines in L2 instead of waiting on HBM (ncu: the residual use was the fused epilogue's top stall)
+        const char* wbase = reinterpret_cast<const char*>(epi.res) + (((size_t)b0 * 81) * kSeC + (size_t)(c - lane)) * 2;
+#pragma unroll
+        for (int k = 0; k < (kBoards * 81 + 31) / 32; ++k) {
+          const int col = k * 32 + lane;
+          if (col < kBoards * 81 && col / 81 < nb_valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + (size_t)col * kSeC * 2));
+        }
+      }
       mbar_wait(tfull_bar(buf), tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * kTileN);
