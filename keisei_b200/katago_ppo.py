@@ -653,8 +653,9 @@ class KataGoPPOAlgorithm:
             flat = model_ops.seresnet_backward_raw(tables, wpack, ws, policy_buf.grad, value.grad, score.grad, code,
                                                    bool(km.use_tensor_cores), km._grad_sizes, km.bn_sync,
                                                    grad_sync=gs if overlapped else None)
+            self._grad_div = 1.0
             if overlapped:
-                flat.div_(gs.world_size)     # the buckets came back summed over the ranks
+                self._grad_div = float(gs.world_size)   # the buckets came back SUMMED over the ranks: divided in the optimiser tail
             elif gs is not None:
                 gs.all_reduce_flat(flat)
             self._flat_grad = flat   # every p.grad below is a view of it: the optimiser tail works on this one buffer
@@ -677,6 +678,8 @@ class KataGoPPOAlgorithm:
         p = self.params
         flat = getattr(self, "_flat_grad", None)
         self._flat_grad = None
+        grad_div = getattr(self, "_grad_div", 1.0)
+        self._grad_div = 1.0
         base = self._base()
         if hasattr(base, "invalidate_packed_weights"):
             base.invalidate_packed_weights()   # the fused optimiser does not bump Tensor._version: re-pack explicitly
@@ -684,17 +687,20 @@ class KataGoPPOAlgorithm:
         usable = (flat is not None and params is not None and len(params) > 0 and params[0].grad is not None
                   and params[0].grad.data_ptr() == flat.data_ptr()
                   and sum(q.numel() for q in params) == flat.numel())
+        from .optim import FlatAdamTail
+        fused_adam = usable and self.fused_optimizer_tail and FlatAdamTail.supports(self.optimizer, params, flat)
+        if flat is not None and grad_div != 1.0 and not fused_adam:
+            flat.div_(grad_div)     # the stock paths below expect the rank-averaged gradient
+            grad_div = 1.0
         if not usable:
             self.scaler.unscale_(self.optimizer)
             grad_norm = torch.nn.utils.clip_grad_norm_(self.model.parameters(), p.grad_clip)
             self.scaler.step(self.optimizer)
             self.scaler.update()
             return grad_norm
-        from .optim import FlatAdamTail
         tail = getattr(self, "_flat_adam", None)
         if tail is None:
             tail = self._flat_adam = FlatAdamTail()
-        fused_adam = self.fused_optimizer_tail and FlatAdamTail.supports(self.optimizer, params, flat)
         inv_scale = None
         st = None
         if self.scaler.is_enabled():
@@ -711,7 +717,7 @@ class KataGoPPOAlgorithm:
         if fused_adam:
             # two launches: one read of the gradient (norm + non-finite flag), one pass over (p, g, m, v) that unscales,
             # clips and applies Adam in place on PyTorch's own parameter / state tensors (csrc/optim.cu)
-            grad_norm, found_inf = tail.step(flat, self.optimizer, params, p.grad_clip, inv_scale, 1.0,
+            grad_norm, found_inf = tail.step(flat, self.optimizer, params, p.grad_clip, inv_scale, grad_div,
                                              model_ops.sm_count(flat.device))
             if st is not None:
                 from torch.amp.grad_scaler import OptState

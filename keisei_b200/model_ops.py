@@ -159,8 +159,14 @@ class _BucketHook:
         self.ptr = ctypes.cast(self.fn, c_void_p)
 
     def _stream(self, handle):
-        """cudaStream_t handle from the C side -> torch stream (NULL is the legacy default stream)."""
-        return torch.cuda.ExternalStream(int(handle), device=self.dev) if handle else torch.cuda.default_stream(self.dev)
+        """cudaStream_t handle from the C side -> torch stream (NULL is the legacy default stream); wrappers are cached."""
+        if not handle:
+            return torch.cuda.default_stream(self.dev)
+        cache = self.sync.__dict__.setdefault("_ext_streams", {})
+        s = cache.get((self.dev, int(handle)))
+        if s is None:
+            s = cache[(self.dev, int(handle))] = torch.cuda.ExternalStream(int(handle), device=self.dev)
+        return s
 
     def _fire(self, main_stream, side_stream) -> None:
         if self.lo is None or self.hi <= self.lo:

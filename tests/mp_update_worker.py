@@ -62,7 +62,7 @@ def main() -> None:
     pl, vl, sl, ent, _ = algo._step_fused(model, obs, (mask, acts, old, adv, cats, score_t, adv), None)
     assert algo.grad_sync.last_overlap_buckets >= 3, algo.grad_sync.last_overlap_buckets   # bucketed, overlapped exchange ran
     scale = float(algo.scaler.get_scale()) if algo.scaler.is_enabled() else 1.0
-    flat = (algo._flat_grad / scale).clone()
+    flat = (algo._flat_grad / scale / getattr(algo, "_grad_div", 1.0)).clone()   # overlapped buckets come back summed over the ranks
     algo._optimizer_tail()
     torch.cuda.synchronize(dev)
     # identical state on every rank, bit for bit
