@@ -66,6 +66,10 @@ struct GemmArgs {
   int splitk;                                              // >1: fp32 atomicAdd into C (C pre-zeroed / accumulating)
   int tf32;                                                // inner product as TF32 tensor-core MMAs (bf16 / AMP path only)
 };
+// gpool_mlp_tc.cu: the whole global-pool-bias MLP (Linear 3C->128, ReLU, Linear 128->256) as one tcgen05 kernel
+int kbk_gpool_mlp_tc_supported(int C, int G);
+int kbk_gpool_mlp_tc(const void* x_bf16, int B, int K, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
+                     float* gh_out, float* g_out, int num_sms, cudaStream_t st);
 int kbk_gemm(const GemmArgs& g, cudaStream_t st);
 // Grouped launches: between begin and end (per host thread) kbk_gemm / kbk_colsum calls are COLLECTED (up to 4 + 4) and
 // run as one kernel at the next flush / end — for problems that are independent of one another.

@@ -372,13 +372,21 @@ extern "C" int kb_seresnet_forward_sync(const kb_seresnet_desc* d, const void* c
   static int fused_tail_env = -1;
   if (fused_tail_env < 0) { const char* e = getenv("KB_FUSED_TAIL"); fused_tail_env = (e && e[0] == '0') ? 0 : 1; }
   const bool fuse_tail = !training && ltc && fused_tail_env && B >= 3 && kbk_conv3x3_se_tail_supported(C, C, m.S, dtype);
+  static int fused_gfc_env = -1;
+  if (fused_gfc_env < 0) { const char* e = getenv("KB_FUSED_GFC"); fused_gfc_env = (e && e[0] == '0') ? 0 : 1; }
+  const bool fused_gfc = fused_gfc_env && kbk_gpool_mlp_tc_supported(C, m.G);
   bool pool_bf_ready = false;  // the producing apply kernel also writes the bf16 copy of the pool statistics
   // ---- residual tower ----
   for (int i = 0; i < m.nb; ++i) {
     BlockWs& bw = training ? blks[i] : blks[0];
     const int l1 = 1 + 2 * i, l2 = 2 + 2 * i;
     // global-pool bias from the block INPUT: g = W2 relu(W1 pool + b1) + b2   (se_resnet.py:73-78)
-    if (ltc) {
+    if (ltc && fused_gfc) {
+      // both Linear layers in one tcgen05 kernel, the hidden layer never leaves the SM (gpool_mlp_tc.cu)
+      if (!pool_bf_ready) KB_TRY(kbk_cast_rows_bf16(pool_cur, w.pool_bf, B, 3 * C, 3 * C, st));
+      KB_TRY(kbk_gpool_mlp_tc(w.pool_bf, B, 3 * C, wp.lin_blk(i, wp.o_g1), P(pi_blk(i, 7)), wp.lin_blk(i, wp.o_g2), P(pi_blk(i, 9)),
+                              training ? bw.gh : nullptr, w.g, num_sms, st));
+    } else if (ltc) {
       if (!pool_bf_ready) KB_TRY(kbk_cast_rows_bf16(pool_cur, w.pool_bf, B, 3 * C, 3 * C, st));
       KB_TRY(kbk_linear_tc(w.pool_bf, B, 3 * C, wp.lin_blk(i, wp.o_g1), m.G, wp.Gp, nullptr, P(pi_blk(i, 7)), 1, bw.gh, m.G,
                            w.gh_bf, wp.Gk, wp.Gk, 0, 0, num_sms, st));
