@@ -311,9 +311,19 @@ def hbm_kernels(device) -> dict:
     B = ROLLOUT_B
     sets = rows(B)
     vl = torch.randn(B, 3, device=device)
-    ms = timeit(lambda i: policy_ops.policy_sample(sets[i & 1][0][:, :A], sets[i & 1][1], vl))
+    # rollout sampling: (i) the dense one-CTA-per-row kernel on byte masks (whole row staged: SURVEY 8(d) algorithmic bytes
+    # = bf16 logits + byte mask), (ii) what select_actions runs since round 2: bit-packed masks + the warp-per-row kernel
+    # that gathers ONLY the legal logits (~80 of 11,259 here) — its traffic is the packed mask + one 32-byte sector per
+    # legal logit, which is what its fraction is computed on (on the dense bytes it would read > 1)
+    ms = timeit(lambda i: policy_ops.policy_sample(sets[i & 1][0][:, :A], sets[i & 1][1], vl, dense=True))
     bytes_row = A * 2 + policy_ops.mask_row_bytes(sets[0][1])
-    out["policy_sample"] = {"ms": round(ms, 4), "gbs": round(B * bytes_row / ms / 1e6, 1), "frac": round(B * bytes_row / ms / 1e6 / pk, 3)}
+    out["policy_sample_dense"] = {"ms": round(ms, 4), "gbs": round(B * bytes_row / ms / 1e6, 1), "frac": round(B * bytes_row / ms / 1e6 / pk, 3)}
+    bits = [policy_ops.pack_mask_bits(sets[k][1]) for k in range(2)]
+    legal = float(sets[0][1].sum(1).float().mean())
+    ms = timeit(lambda i: policy_ops.policy_sample(sets[i & 1][0][:, :A], bits[i & 1], vl))
+    sparse_row = policy_ops.mask_row_bytes(bits[0]) + 32 * legal
+    out["policy_sample"] = {"ms": round(ms, 4), "gbs": round(B * sparse_row / ms / 1e6, 1), "frac": round(B * sparse_row / ms / 1e6 / pk, 3),
+                            "legal_per_row": round(legal, 1), "bytes_per_row": round(sparse_row), "dense_bytes_per_row": A * 2 + bits[0].shape[1] * 4}
     B = UPDATE_GLOBAL_B
     sets = rows(B)
     old, adv = -3 * torch.rand(B, device=device), torch.randn(B, device=device)

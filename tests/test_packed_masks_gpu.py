@@ -206,3 +206,35 @@ def test_pinned_ingest_double_buffer_delivers_each_step_intact():
         assert steps[k][3][torch.arange(d_obs.shape[0]), a.cpu()].all()
     with pytest.raises(ValueError, match="unexpected shapes"):
         ing.submit(torch.zeros(3, 46, 9, 9), torch.zeros(3, A, dtype=torch.bool))
+
+
+@pytest.mark.parametrize("dtype,mode", [(torch.float32, 0), (torch.bfloat16, 1), (torch.bfloat16, 0)])
+@pytest.mark.parametrize("density", [0.007, 0.4])
+def test_sparse_warp_per_row_sampler_matches_the_dense_kernel(dtype, mode, density):
+    """Bit-packed masks are sampled by a warp-per-row kernel that gathers only the legal logits (csrc/policy.cu:
+    policy_sample_bits_kernel). Same Philox keys and tie-breaking as the dense one-CTA-per-row kernel: the drawn action,
+    the legal counts and the flags are identical; log-probs agree up to summation order."""
+    B = 333
+    logits, mask, acts = _rows(B, 21, dtype, density)
+    mask[7] = False                                               # zero legal actions
+    mask[8] = False; mask[8, 11258] = True                        # single legal action in the last (partial) mask word
+    logits = logits.clone(); logits[9][mask[9]] = float("-inf")   # every legal logit -inf: falls back to the first legal index
+    vl = torch.randn(B, 3, device=DEV)
+    sc = torch.randn(B, 1, device=DEV)
+    for forced in (None, acts):
+        d = policy_ops.policy_sample(logits, mask, vl, sc, 0.3, seed=5, offset=9, logprob_mode=mode, forced_actions=forced, dense=True)
+        s_ = policy_ops.policy_sample(logits, policy_ops.pack_mask_bits(mask), vl, sc, 0.3, seed=5, offset=9, logprob_mode=mode,
+                                      forced_actions=forced)
+        assert torch.equal(d[0], s_[0])                           # actions
+        assert torch.equal(d[3], s_[3]) and torch.equal(d[4], s_[4])   # legal counts, flags
+        assert torch.equal(d[2], s_[2])                           # scalar values
+        ok = torch.ones(B, dtype=torch.bool, device=DEV); ok[7] = False
+        if forced is None:
+            assert int(s_[0][8]) == 11258 and int(s_[0][9]) == int(mask[9].nonzero()[0])
+        diff = (d[1][ok] - s_[1][ok]).abs()
+        diff = diff[~diff.isnan()]
+        if mode == 0:
+            assert float(diff.max()) < 2e-5
+        else:   # bf16-rounded log-probs: a last-bit difference of the normaliser may flip one rounding
+            assert float((diff > 0).float().mean()) < 0.02 and float(diff.max()) <= 0.0625
+    assert bool(s_[1][7].isnan())
