@@ -501,18 +501,38 @@ __global__ void __launch_bounds__(256) value_losses_bwd_kernel(
   dscore[i] = g_score[0] * 2.f * (score_pred[i] - score_tgt[i]) / (float)B;
 }
 
-// (rows, A) bool -> (rows, words) bit-packed: a warp reads 32 consecutive bytes, one ballot makes the word
+// (rows, A) bool -> (rows, words) bit-packed. One CTA per row: the row's bytes are staged into shared memory with aligned
+// 4-byte loads of the covering range (rows of 11,259 bytes start at every alignment), then each thread assembles whole
+// 32-bit words from shared memory. HBM sees one coalesced read of the mask and one write of 1/8 of it.
 __global__ void __launch_bounds__(256) pack_mask_bits_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ bits,
-                                                             long long rows, int A, int words) {
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= rows * words) return;
-  const long long row = warp / words;
-  const int w = (int)(warp - row * words);
-  const int i = w * 32 + lane;
-  const bool on = i < A && mask[(size_t)row * A + i] != 0;
-  const uint32_t word = __ballot_sync(0xffffffffu, on);
-  if (lane == 0) bits[warp] = word;
+                                                             long long rows, int A, int words, long long total_bytes) {
+  extern __shared__ uint32_t s_words32[];
+  uint8_t* s_bytes = reinterpret_cast<uint8_t*>(s_words32);
+  const long long row = blockIdx.x;
+  const long long begin = row * A;                       // flat byte offset of the row
+  const long long a0 = begin & ~3ll;                     // aligned start of the covering range
+  const int lead = (int)(begin - a0);
+  const int n4 = (lead + A + 3) >> 2;                    // 4-byte words covering [begin, begin + A)
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(mask + a0);
+  const long long last4 = (total_bytes + 3) >> 2;        // the allocation is a whole number of... bytes: guard the tail
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    uint32_t v;
+    if ((a0 >> 2) + i + 1 <= (total_bytes >> 2)) v = __ldg(src + i);
+    else {                                               // last partial word of the whole tensor: byte loads
+      v = 0;
+      for (int b = 0; b < 4; ++b) { const long long o = a0 + 4ll * i + b; if (o < total_bytes) v |= (uint32_t)mask[o] << (8 * b); }
+    }
+    s_words32[i] = v;
+  }
+  (void)last4;
+  __syncthreads();
+  for (int w = threadIdx.x; w < words; w += 256) {
+    uint32_t word = 0;
+    const int base = lead + w * 32;
+    const int n = min(32, A - w * 32);
+    for (int k = 0; k < n; ++k) word |= (s_bytes[base + k] != 0 ? 1u : 0u) << k;
+    bits[row * words + w] = word;
+  }
 }
 
 // One launch gathers a shuffled minibatch out of the device-resident rollout storage (reference katago_ppo.py:829-841:
@@ -666,8 +686,10 @@ extern "C" int kb_pack_mask_bits(const void* mask_bytes, void* bits, long long r
   KB_CHECK_ARG(rows >= 0 && A > 0 && words * 32 >= A, "kb_pack_mask_bits: bad shape rows=%lld A=%d words=%d", rows, A, words);
   if (rows == 0) return KB_OK;
   KB_CHECK_ARG(mask_bytes && bits, "kb_pack_mask_bits: null pointer");
-  const long long threads = rows * words * 32;
-  pack_mask_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>((const uint8_t*)mask_bytes, (uint32_t*)bits, rows, A, words);
+  KB_CHECK_ARG(((uintptr_t)mask_bytes & 3) == 0, "kb_pack_mask_bits: the mask tensor must be 4-byte aligned");
+  const size_t smem = (size_t)((A + 3 + 3) / 4 + 1) * 4;
+  KB_CHECK_ARG(smem <= 48 * 1024, "kb_pack_mask_bits: action space %d too large", A);
+  pack_mask_bits_kernel<<<(unsigned)rows, 256, smem, stream>>>((const uint8_t*)mask_bytes, (uint32_t*)bits, rows, A, words, rows * (long long)A);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

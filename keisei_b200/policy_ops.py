@@ -248,7 +248,7 @@ _sample_calls = itertools.count()
 def policy_sample(logits: torch.Tensor, mask: torch.Tensor | None, value_logits: torch.Tensor | None = None,
                   score_lead: torch.Tensor | None = None, alpha: float = 0.0, *, seed: int | None = None,
                   offset: int | None = None, logprob_mode: int | None = None,
-                  forced_actions: torch.Tensor | None = None, dense: bool = False):
+                  forced_actions: torch.Tensor | None = None, dense: bool | None = None):
     """One launch: actions (int64), log_probs (fp32), scalar values (fp32 or None), legal_count, flags.
 
     Sampling is Gumbel-max over the legal entries with a Philox4x32-10 stream keyed by
@@ -256,12 +256,15 @@ def policy_sample(logits: torch.Tensor, mask: torch.Tensor | None, value_logits:
     logprob_mode 0 = fp32 Categorical semantics, 1 = bf16-autocast semantics (eps = 2^-7 clamp);
     default follows the logits dtype like the reference does.
     `forced_actions` (int64, (B,)) skips the draw and reports the log-prob of the given actions.
-    Bool / uint8 masks are bit-packed first (`pack_mask_bits`) and sampled by the warp-per-row kernel that touches only
-    the legal logits; `dense=True` keeps the byte mask and the one-CTA-per-row kernel that stages the whole row (same
-    draw, log-probs equal up to summation order).
+    Bit-packed masks go to the warp-per-row kernel that touches only the legal logits. Bool / uint8 masks: `dense=False`
+    packs them first (`pack_mask_bits`) for that kernel, `dense=True` keeps the byte mask and the one-CTA-per-row kernel
+    that stages the whole row (same draw, log-probs equal up to summation order); the default picks by batch — measured
+    on B200, pack + sparse is 100 us against 130 us at 4096 rows but 63 us against 43 us at 512 (tools/bench_sample.py).
     """
     B, A, stride = _check_logits(logits)
     dev = logits.device
+    if dense is None:
+        dense = B < 2048
     if mask is not None and mask.dtype != torch.int32 and not dense:
         if mask.shape != (B, A):
             raise ValueError(f"legal mask shape {tuple(mask.shape)} != {(B, A)}")
