@@ -231,17 +231,17 @@ __global__ void __launch_bounds__(kThreads) policy_sample_kernel(
 // re-reads hit L1). Same semantics and the same Philox keys as policy_sample_kernel: the drawn action is identical, the
 // log-prob differs by summation order only. No shared memory, no block barriers, 8 rows per 256-thread CTA.
 // ---------------------------------------------------------------------------------------------
+// Fallback walk (rows with more legal entries than the shared-memory list holds, or an action space wider than the
+// register-resident mask words): three bit-walks straight over the mask words, gathering from global memory each time.
 template <typename T>
-__global__ void __launch_bounds__(kThreads) policy_sample_bits_kernel(
+__device__ __noinline__ void sample_row_walk(
     const T* __restrict__ logits, long long row_stride, const uint32_t* __restrict__ mask, long long pitch,
-    const float* __restrict__ value_logits, const float* __restrict__ score_lead, float alpha, int B,
+    const float* __restrict__ value_logits, const float* __restrict__ score_lead, float alpha, int row,
     int A, unsigned long long seed, unsigned long long offset, int logprob_mode,
     const long long* __restrict__ forced_actions,
     long long* __restrict__ actions, float* __restrict__ logp_out, float* __restrict__ value_out,
     int* __restrict__ legal_count, int* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  if (row >= B) return;
   const T* lrow = logits + (size_t)row * row_stride;
   const uint32_t* words = mask + (size_t)row * pitch;
   const int nwords = (A + 31) >> 5;
@@ -335,6 +335,147 @@ __global__ void __launch_bounds__(kThreads) policy_sample_bits_kernel(
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float Q = bf16_round(q);
+    const float eps = 0.0078125f;
+    const float p = bf16_round(bf16_round(expf(la - m) * invS) / Q);
+    lp = bf16_round(logf(fminf(fmaxf(p, eps), 1.f - eps)));
+  }
+  if (lane == 0) { actions[row] = (long long)a; logp_out[row] = lp; }
+}
+
+__device__ __forceinline__ float scalar_value_of(const float* __restrict__ value_logits, const float* __restrict__ score_lead,
+                                                 float alpha, int row) {
+  const float a = value_logits[row * 3 + 0], b = value_logits[row * 3 + 1], c = value_logits[row * 3 + 2];
+  const float mm = fmaxf(a, fmaxf(b, c));
+  const float ea = expf(a - mm), eb = expf(b - mm), ec = expf(c - mm);
+  const float inv = 1.f / (ea + eb + ec);
+  float v = ea * inv - ec * inv;
+  if (alpha != 0.f && score_lead != nullptr) v = (1.f - alpha) * v + alpha * fminf(fmaxf(score_lead[row], -1.f), 1.f);
+  return v;
+}
+
+// The kernel proper. Each lane loads its 11 mask words at once (one round trip), the warp compacts the legal action
+// indices into a shared-memory list by a prefix sum over the popcounts, and the list is then processed 32 entries at a
+// time with four independent gathers in flight per lane — two dependent memory round trips per row instead of one per
+// legal action. The gathered logits stay in shared memory for the normaliser passes.
+constexpr int kListCap = 640;        // a shogi position has at most 593 legal moves; longer rows take the walk
+constexpr int kWordsPerLane = 11;    // 352 mask words (11,259 actions) held in registers
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) policy_sample_bits_kernel(
+    const T* __restrict__ logits, long long row_stride, const uint32_t* __restrict__ mask, long long pitch,
+    const float* __restrict__ value_logits, const float* __restrict__ score_lead, float alpha, int B,
+    int A, unsigned long long seed, unsigned long long offset, int logprob_mode,
+    const long long* __restrict__ forced_actions,
+    long long* __restrict__ actions, float* __restrict__ logp_out, float* __restrict__ value_out,
+    int* __restrict__ legal_count, int* __restrict__ flags) {
+  __shared__ uint16_t s_idx[kThreads / 32][kListCap];
+  __shared__ float s_val[kThreads / 32][kListCap];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = blockIdx.x * (kThreads / 32) + wid;
+  if (row >= B) return;
+  const int nwords = (A + 31) >> 5;
+  const T* lrow = logits + (size_t)row * row_stride;
+  const uint32_t* words = mask + (size_t)row * pitch;
+  uint32_t wd[kWordsPerLane];
+  int cnt = 0;
+  const bool wide = nwords > 32 * kWordsPerLane || A > 65535;
+  if (!wide) {
+#pragma unroll
+    for (int k = 0; k < kWordsPerLane; ++k) {
+      const int w = lane + 32 * k;
+      uint32_t bits = w < nwords ? __ldg(words + w) : 0u;
+      if (w == nwords - 1 && (A & 31) != 0) bits &= (1u << (A & 31)) - 1u;   // padding bits are never actions
+      wd[k] = bits;
+      cnt += __popc(bits);
+    }
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int legal = __shfl_sync(0xffffffffu, incl, 31);
+  if (wide || legal > kListCap) {   // warp-uniform
+    sample_row_walk<T>(logits, row_stride, mask, pitch, value_logits, score_lead, alpha, row, A, seed, offset, logprob_mode,
+                       forced_actions, actions, logp_out, value_out, legal_count, flags);
+    return;
+  }
+  if (lane == 0) {
+    legal_count[row] = legal;
+    if (legal == 0) atomicAdd(&flags[0], 1);
+    if (value_out != nullptr) value_out[row] = scalar_value_of(value_logits, score_lead, alpha, row);
+  }
+  if (legal == 0) {  // reference raises; keep outputs defined
+    if (lane == 0) { actions[row] = 0; logp_out[row] = __int_as_float(0x7fc00000); }
+    return;
+  }
+  // compaction: lane-major order (any fixed order gives the same arg-max; sums differ by rounding only)
+  int pos = incl - cnt, first = 0x7fffffff;
+#pragma unroll
+  for (int k = 0; k < kWordsPerLane; ++k) {
+    uint32_t bits = wd[k];
+    while (bits) {
+      const int i = (lane + 32 * k) * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      first = min(first, i);
+      s_idx[wid][pos++] = (uint16_t)i;
+    }
+  }
+  __syncwarp();
+  float m = -INFINITY, best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int j0 = 0; j0 < legal; j0 += 128) {
+    int idx[4];
+    float l[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 32 + lane;
+      idx[u] = j < legal ? (int)s_idx[wid][j] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) l[u] = idx[u] >= 0 ? kb_to_float<T>(lrow[idx[u]]) : -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (idx[u] < 0) continue;
+      s_val[wid][j0 + u * 32 + lane] = l[u];
+      if (l[u] == -INFINITY) continue;  // a legal -inf logit: probability exactly 0
+      m = fmaxf(m, l[u]);
+      const kb_philox4 r = kb_philox4x32_10(seed, (unsigned long long)row, (offset << 32) | (unsigned long long)(unsigned)idx[u]);
+      const float sc = l[u] - __logf(-__logf(kb_u32_to_unit(r.x)));
+      if (sc > best || (sc == best && idx[u] < besti)) { best = sc; besti = idx[u]; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  int a = besti;
+  if (forced_actions != nullptr) {
+    const long long fa = forced_actions[row];
+    a = (fa >= 0 && fa < A) ? (int)fa : 0;
+  }
+  if (a == 0x7fffffff) a = first;  // every legal logit was -inf / NaN: the first legal index
+  float s = 0.f;
+  for (int j = lane; j < legal; j += 32) s += __expf(s_val[wid][j] - m);
+  const float S = kb_warp_sum(s);
+  const bool a_legal = ((__ldg(words + (a >> 5)) >> (a & 31)) & 1u) != 0;
+  const float la = a_legal ? kb_to_float<T>(lrow[a]) : -INFINITY;
+  float lp;
+  if (logprob_mode == 0) {
+    const float eps = 1.1920928955078125e-07f;
+    const float p = expf(la - m) / S;
+    lp = logf(fminf(fmaxf(p, eps), 1.f - eps));
+  } else {
+    // bf16 reference semantics (see policy_sample_kernel): probabilities rounded to bf16 and renormalised in bf16
+    float q = 0.f;
+    const float invS = 1.f / S;
+    for (int j = lane; j < legal; j += 32) q += bf16_round(__expf(s_val[wid][j] - m) * invS);
+    const float Q = bf16_round(kb_warp_sum(q));
     const float eps = 0.0078125f;
     const float p = bf16_round(bf16_round(expf(la - m) * invS) / Q);
     lp = bf16_round(logf(fminf(fmaxf(p, eps), 1.f - eps)));
@@ -447,6 +588,169 @@ __global__ void __launch_bounds__(kThreads) ppo_policy_bwd_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
+// Update kernels over BIT-PACKED masks (the product path: the rollout buffer stores packed masks and hands them over).
+// Illegal actions contribute nothing to the softmax, so the forward is a pure streaming NaN scan of the raw logits (the
+// reference's guard, katago_ppo.py:860-862, looks at every logit) plus a walk over the ~1 % legal entries, and the
+// backward never reads an illegal logit: it writes zeros for them. No shared-memory row, 8 CTAs resident per SM.
+// ---------------------------------------------------------------------------------------------
+// NaN test on packed values without converting: |x| > inf  <=>  |x| + (all mantissa bits) carries into the sign position.
+template <typename T> __device__ __forceinline__ uint32_t nan_bits(uint32_t x);
+template <> __device__ __forceinline__ uint32_t nan_bits<bf16>(uint32_t x) { return ((x & 0x7fff7fffu) + 0x007f007fu) & 0x80008000u; }
+template <> __device__ __forceinline__ uint32_t nan_bits<float>(uint32_t x) { return ((x & 0x7fffffffu) + 0x007fffffu) & 0x80000000u; }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) ppo_policy_fwd_bits_kernel(
+    const T* __restrict__ logits, long long row_stride, const uint32_t* __restrict__ mask, long long pitch,
+    const long long* __restrict__ actions, int A, float* __restrict__ new_logp,
+    float* __restrict__ row_entropy, float* __restrict__ row_lse, int* __restrict__ flags) {
+  __shared__ float s_red[3][kThreads / 32];
+  const int row = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const T* lrow = logits + (size_t)row * row_stride;
+  const uint32_t* words = mask + (size_t)row * pitch;
+  const int nwords = (A + 31) >> 5;
+  auto word_at = [&](int w) -> uint32_t {
+    uint32_t bits = __ldg(words + w);
+    if (w == nwords - 1 && (A & 31) != 0) bits &= (1u << (A & 31)) - 1u;
+    return bits;
+  };
+  // the first two mask words of this thread are requested before the stream starts (352 words: every word of a shogi row)
+  const uint32_t w0 = threadIdx.x < nwords ? word_at(threadIdx.x) : 0u;
+  const uint32_t w1 = threadIdx.x + kThreads < nwords ? word_at(threadIdx.x + kThreads) : 0u;
+  // streaming NaN scan of the whole raw row
+  uint32_t nan_acc = 0;
+  constexpr int kPer = 16 / (int)sizeof(T);
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(lrow) & 15) == 0;
+  const int nvec = vec_ok ? A / kPer : 0;
+  const uint4* v4 = reinterpret_cast<const uint4*>(lrow);
+  constexpr int kUn = 6;
+  for (int j = threadIdx.x; j < nvec; j += kThreads * kUn) {
+    uint4 x[kUn];
+#pragma unroll
+    for (int u = 0; u < kUn; ++u) {
+      const int jj = j + u * kThreads;
+      x[u] = jj < nvec ? __ldg(v4 + jj) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kUn; ++u) nan_acc |= nan_bits<T>(x[u].x) | nan_bits<T>(x[u].y) | nan_bits<T>(x[u].z) | nan_bits<T>(x[u].w);
+  }
+  for (int i = nvec * kPer + threadIdx.x; i < A; i += kThreads) {
+    const float v = kb_to_float<T>(lrow[i]);
+    nan_acc |= (v != v) ? 1u : 0u;
+  }
+  // walk 1 over the legal entries: count and max
+  float m = -INFINITY;
+  int legal = 0;
+  for (int w = threadIdx.x, k = 0; w < nwords; w += kThreads, ++k) {
+    uint32_t bits = k == 0 ? w0 : (k == 1 ? w1 : word_at(w));
+    legal += __popc(bits);
+    while (bits) {
+      const int i = w * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      m = fmaxf(m, kb_to_float<T>(lrow[i]));
+    }
+  }
+  m = kb_warp_max(m);
+  const float lg = kb_warp_sum((float)legal);
+  const uint32_t nn = __any_sync(0xffffffffu, nan_acc != 0) ? 1u : 0u;
+  if (lane == 0) { s_red[0][wid] = m; s_red[1][wid] = lg; s_red[2][wid] = (float)nn; }
+  __syncthreads();
+  float lgs = 0.f, nns = 0.f;
+  m = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) { m = fmaxf(m, s_red[0][w]); lgs += s_red[1][w]; nns += s_red[2][w]; }
+  const int n_legal = (int)(lgs + 0.5f);
+  if (threadIdx.x == 0) {
+    if (n_legal == 0) atomicAdd(&flags[0], 1);
+    if (nns != 0.f) atomicAdd(&flags[1], 1);
+  }
+  if (n_legal == 0) {
+    if (threadIdx.x == 0) { new_logp[row] = 0.f; row_entropy[row] = 0.f; row_lse[row] = 0.f; }
+    return;
+  }
+  // walk 2: S = sum exp(l-m), U = sum exp(l-m)*(l-m) over the legal entries (the gathers hit L1 / L2: just streamed)
+  float s = 0.f, u = 0.f;
+  for (int w = threadIdx.x, k = 0; w < nwords; w += kThreads, ++k) {
+    uint32_t bits = k == 0 ? w0 : (k == 1 ? w1 : word_at(w));
+    while (bits) {
+      const int i = w * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      const float d = kb_to_float<T>(lrow[i]) - m;
+      if (d > -INFINITY) { const float e = __expf(d); s += e; u += e * d; }
+    }
+  }
+  s = kb_warp_sum(s);
+  u = kb_warp_sum(u);
+  __syncthreads();   // s_red reuse
+  if (lane == 0) { s_red[0][wid] = s; s_red[1][wid] = u; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float S = 0.f, U = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) { S += s_red[0][w]; U += s_red[1][w]; }
+    const float logS = logf(S);
+    const long long a = actions[row];
+    float la = -INFINITY;
+    if (a >= 0 && a < A && ((word_at((int)(a >> 5)) >> (a & 31)) & 1u)) la = kb_to_float<T>(lrow[a]);
+    new_logp[row] = (la - m) - logS;
+    row_entropy[row] = logS - U / S;  // -sum p*logp over legal
+    row_lse[row] = m + logS;
+  }
+}
+
+// Same formula as ppo_policy_bwd_kernel, organised around what is sparse: the gradient row is first written as 16-byte
+// zero vectors that depend on no load (the write stream — all of the kernel's real traffic — starts at once), then, after
+// one barrier, each thread walks the set bits of ITS mask words (352 words over 256 threads, ~80 set bits per row) and
+// stores those few gradients over the zeros. Illegal logits are never read.
+// Needs 16-byte aligned gradient rows (d_row_stride a multiple of 16 / sizeof(T)); the host falls back otherwise.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) ppo_policy_bwd_bits_kernel(
+    const T* __restrict__ logits, long long row_stride, const uint32_t* __restrict__ mask, long long pitch,
+    const long long* __restrict__ actions, int A, int B, const float* __restrict__ row_lse,
+    const float* __restrict__ row_entropy, const float* __restrict__ dlogp,
+    const float* __restrict__ g_policy, const float* __restrict__ g_entropy,
+    T* __restrict__ dlogits, long long d_row_stride) {
+  constexpr int kPer = 16 / (int)sizeof(T);
+  const int row = blockIdx.x;
+  const T* lrow = logits + (size_t)row * row_stride;
+  const uint32_t* words = mask + (size_t)row * pitch;
+  T* dscalar = dlogits + (size_t)row * d_row_stride;
+  uint4* drow = reinterpret_cast<uint4*>(dscalar);
+  const int nvec = (int)(d_row_stride / kPer);
+  const int nwords = (A + 31) >> 5;
+  auto word_at = [&](int w) -> uint32_t {
+    uint32_t bits = __ldg(words + w);
+    if (w == nwords - 1 && (A & 31) != 0) bits &= (1u << (A & 31)) - 1u;
+    return bits;
+  };
+  const uint32_t w0 = threadIdx.x < nwords ? word_at(threadIdx.x) : 0u;
+  const uint32_t w1 = threadIdx.x + kThreads < nwords ? word_at(threadIdx.x + kThreads) : 0u;
+  const float lse = row_lse[row], H = row_entropy[row];
+  const float gl = g_policy[0] * dlogp[row];
+  const float gh = g_entropy[0] / (float)B;
+  const int a = (int)actions[row];
+#pragma unroll 6
+  for (int j = threadIdx.x; j < nvec; j += kThreads) drow[j] = make_uint4(0, 0, 0, 0);
+  // the first legal logit of both words is requested before the barrier
+  const float l0 = w0 != 0 ? kb_to_float<T>(lrow[threadIdx.x * 32 + __ffs(w0) - 1]) : 0.f;
+  const float l1 = w1 != 0 ? kb_to_float<T>(lrow[(threadIdx.x + kThreads) * 32 + __ffs(w1) - 1]) : 0.f;
+  __syncthreads();   // orders the zero vectors of the whole CTA before the scalar stores below (same addresses)
+  for (int w = threadIdx.x, k = 0; w < nwords; w += kThreads, ++k) {
+    uint32_t bits = k == 0 ? w0 : (k == 1 ? w1 : word_at(w));
+    bool first = k < 2;
+    while (bits) {
+      const int i = w * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      const float lp = (first ? (k == 0 ? l0 : l1) : kb_to_float<T>(lrow[i])) - lse;
+      first = false;
+      const float p = __expf(lp);
+      float dd = gl * ((i == a ? 1.f : 0.f) - p);
+      if (p > 0.f) dd -= gh * p * (lp + H);
+      dscalar[i] = kb_from_float<T>(dd);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // W/D/L cross-entropy (ignore_index = -1, mean over valid rows) + score MSE. Single CTA.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) value_losses_fwd_kernel(
@@ -501,37 +805,64 @@ __global__ void __launch_bounds__(256) value_losses_bwd_kernel(
   dscore[i] = g_score[0] * 2.f * (score_pred[i] - score_tgt[i]) / (float)B;
 }
 
-// (rows, A) bool -> (rows, words) bit-packed. One CTA per row: the row's bytes are staged into shared memory with aligned
-// 4-byte loads of the covering range (rows of 11,259 bytes start at every alignment), then each thread assembles whole
-// 32-bit words from shared memory. HBM sees one coalesced read of the mask and one write of 1/8 of it.
+// (rows, A) bool -> (rows, words) bit-packed. The mask is one flat byte array; a lane takes SIXTEEN consecutive bytes of a
+// row: rows of 11,259 bytes start at every alignment, so it loads the two aligned 16-byte vectors the bytes straddle (the
+// second one is the next lane's first: an L1 hit) and funnel-shifts them into place. Each 4-byte word becomes a nibble
+// without branches (non-zero-byte detect + one multiply), a lane makes half an output word and a lane pair one word.
+// No shared memory, no barriers, every load coalesced, eight 16-byte loads in flight per lane.
+constexpr int kPackIters = 4;                          // a warp covers 32 * 4 sixteen-byte pieces = 64 output words
+__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t v) {   // bit k = (byte k of v != 0)
+  const uint32_t y = (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
+  return (y * 0x00204081u) >> 28;                      // bits 7, 15, 23, 31 -> 28, 29, 30, 31
+}
 __global__ void __launch_bounds__(256) pack_mask_bits_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ bits,
-                                                             long long rows, int A, int words, long long total_bytes) {
-  extern __shared__ uint32_t s_words32[];
-  uint8_t* s_bytes = reinterpret_cast<uint8_t*>(s_words32);
-  const long long row = blockIdx.x;
-  const long long begin = row * A;                       // flat byte offset of the row
-  const long long a0 = begin & ~3ll;                     // aligned start of the covering range
-  const int lead = (int)(begin - a0);
-  const int n4 = (lead + A + 3) >> 2;                    // 4-byte words covering [begin, begin + A)
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(mask + a0);
-  const long long last4 = (total_bytes + 3) >> 2;        // the allocation is a whole number of... bytes: guard the tail
-  for (int i = threadIdx.x; i < n4; i += 256) {
-    uint32_t v;
-    if ((a0 >> 2) + i + 1 <= (total_bytes >> 2)) v = __ldg(src + i);
-    else {                                               // last partial word of the whole tensor: byte loads
-      v = 0;
-      for (int b = 0; b < 4; ++b) { const long long o = a0 + 4ll * i + b; if (o < total_bytes) v |= (uint32_t)mask[o] << (8 * b); }
-    }
-    s_words32[i] = v;
+                                                             long long rows, int A, int words, int chunks, int base_off) {
+  // `mask` is the tensor's address rounded DOWN to 16 bytes and base_off the bytes in between (a row-sliced mask starts
+  // anywhere); the bytes before / after the tensor inside its first / last vector are read but never used
+  const int lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long row = gw / chunks;
+  if (row >= rows) return;
+  const int chunk = (int)(gw - row * chunks);
+  const long long total_bytes = base_off + rows * (long long)A;
+  const long long begin = base_off + row * (long long)A;   // flat byte offset of the row
+  const int ws = (int)(begin & 15) >> 2, bs = (int)(begin & 3) * 8;
+  const uint4* V = reinterpret_cast<const uint4*>(mask);
+  const long long full_vecs = total_bytes >> 4;        // aligned vectors lying wholly inside the tensor
+  auto load_vec = [&](long long g) -> uint4 {
+    if (g < full_vecs) return __ldg(V + g);
+    uint32_t w[4] = {0, 0, 0, 0};                      // the tensor's last partial vector: byte loads
+    for (int b = 0; b < 16; ++b) { const long long o = 16 * g + b; if (o < total_bytes) w[b >> 2] |= (uint32_t)mask[o] << (8 * (b & 3)); }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  };
+  const int npieces = words * 2;
+  uint4 lo[kPackIters], hi[kPackIters];
+#pragma unroll
+  for (int it = 0; it < kPackIters; ++it) {
+    const int c = (chunk * kPackIters + it) * 32 + lane;
+    const bool live = c < npieces && 16 * c < A;
+    const long long g = (begin + 16ll * c) >> 4;
+    lo[it] = live ? load_vec(g) : make_uint4(0, 0, 0, 0);
+    hi[it] = (live && (begin & 15) != 0) ? load_vec(g + 1) : make_uint4(0, 0, 0, 0);
   }
-  (void)last4;
-  __syncthreads();
-  for (int w = threadIdx.x; w < words; w += 256) {
-    uint32_t word = 0;
-    const int base = lead + w * 32;
-    const int n = min(32, A - w * 32);
-    for (int k = 0; k < n; ++k) word |= (s_bytes[base + k] != 0 ? 1u : 0u) << k;
-    bits[row * words + w] = word;
+#pragma unroll
+  for (int it = 0; it < kPackIters; ++it) {
+    const int c = (chunk * kPackIters + it) * 32 + lane;
+    const uint32_t w8[8] = {lo[it].x, lo[it].y, lo[it].z, lo[it].w, hi[it].x, hi[it].y, hi[it].z, hi[it].w};
+    uint32_t o0, o1, o2, o3;
+#define KB_PACK_CASE(WS)                                                                                   \
+    case WS: o0 = __funnelshift_r(w8[WS], w8[WS + 1], bs); o1 = __funnelshift_r(w8[WS + 1], w8[WS + 2], bs);  \
+             o2 = __funnelshift_r(w8[WS + 2], w8[WS + 3], bs); o3 = __funnelshift_r(w8[WS + 3], w8[WS + 4], bs); break;
+    switch (ws) {                                      // warp-uniform: one row per warp
+      KB_PACK_CASE(0) KB_PACK_CASE(1) KB_PACK_CASE(2)
+      default: KB_PACK_CASE(3)
+    }
+#undef KB_PACK_CASE
+    uint32_t half = nonzero_nibble(o0) | (nonzero_nibble(o1) << 4) | (nonzero_nibble(o2) << 8) | (nonzero_nibble(o3) << 12);
+    const int left = A - 16 * c;                       // bytes past A belong to the next row
+    if (left < 16) half &= left > 0 ? (1u << left) - 1u : 0u;
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, half, 1);
+    if ((lane & 1) == 0 && c < npieces) bits[row * words + (c >> 1)] = half | (other << 16);
   }
 }
 
@@ -643,7 +974,14 @@ extern "C" int kb_ppo_policy_fwd(const void* logits, int logits_dtype, long long
                "kb_ppo_policy_fwd: null pointer");
   const size_t smem = (size_t)A * sizeof(float);
   KB_CHECK_ARG(smem <= 200 * 1024, "kb_ppo_policy_fwd: action space %d too large for one CTA", A);
-  if (logits_dtype == KB_F32) {
+  if (mask_kind == 1) {   // bit-packed masks: streaming NaN scan + walk over the legal entries, no shared-memory row
+    if (logits_dtype == KB_F32)
+      ppo_policy_fwd_bits_kernel<float><<<B, kThreads, 0, stream>>>((const float*)logits, row_stride, (const uint32_t*)mask, mask_pitch,
+          actions, A, new_logp, row_entropy, row_lse, flags);
+    else
+      ppo_policy_fwd_bits_kernel<bf16><<<B, kThreads, 0, stream>>>((const bf16*)logits, row_stride, (const uint32_t*)mask, mask_pitch,
+          actions, A, new_logp, row_entropy, row_lse, flags);
+  } else if (logits_dtype == KB_F32) {
     if (int r = set_smem(ppo_policy_fwd_kernel<float, 0>, smem)) return r;
     if (int r = set_smem(ppo_policy_fwd_kernel<float, 1>, smem)) return r;
     if (int r = set_smem(ppo_policy_fwd_kernel<float, 2>, smem)) return r;
@@ -672,7 +1010,15 @@ extern "C" int kb_ppo_policy_bwd(const void* logits, int logits_dtype, long long
   KB_TRY_RC(check_mask(mask, mask_kind, mask_pitch, A, "kb_ppo_policy_bwd"));
   KB_CHECK_ARG(logits && actions && row_lse && row_entropy && dlogp && g_policy && g_entropy && dlogits,
                "kb_ppo_policy_bwd: null pointer");
-  if (logits_dtype == KB_F32)
+  const long long per16 = logits_dtype == KB_F32 ? 4 : 8;
+  if (mask_kind == 1 && d_row_stride % per16 == 0 && ((uintptr_t)dlogits & 15) == 0) {
+    if (logits_dtype == KB_F32)
+      ppo_policy_bwd_bits_kernel<float><<<B, kThreads, 0, stream>>>((const float*)logits, row_stride, (const uint32_t*)mask, mask_pitch,
+          actions, A, B, row_lse, row_entropy, dlogp, g_policy, g_entropy, (float*)dlogits, d_row_stride);
+    else
+      ppo_policy_bwd_bits_kernel<bf16><<<B, kThreads, 0, stream>>>((const bf16*)logits, row_stride, (const uint32_t*)mask, mask_pitch,
+          actions, A, B, row_lse, row_entropy, dlogp, g_policy, g_entropy, (bf16*)dlogits, d_row_stride);
+  } else if (logits_dtype == KB_F32)
     KB_MASK_DISPATCH(ppo_policy_bwd_kernel, float, <<<B, kThreads, 0, stream>>>((const float*)logits, row_stride, mask, mask_pitch, actions,
         A, B, row_lse, row_entropy, dlogp, g_policy, g_entropy, (float*)dlogits, d_row_stride));
   else
@@ -686,10 +1032,11 @@ extern "C" int kb_pack_mask_bits(const void* mask_bytes, void* bits, long long r
   KB_CHECK_ARG(rows >= 0 && A > 0 && words * 32 >= A, "kb_pack_mask_bits: bad shape rows=%lld A=%d words=%d", rows, A, words);
   if (rows == 0) return KB_OK;
   KB_CHECK_ARG(mask_bytes && bits, "kb_pack_mask_bits: null pointer");
-  KB_CHECK_ARG(((uintptr_t)mask_bytes & 3) == 0, "kb_pack_mask_bits: the mask tensor must be 4-byte aligned");
-  const size_t smem = (size_t)((A + 3 + 3) / 4 + 1) * 4;
-  KB_CHECK_ARG(smem <= 48 * 1024, "kb_pack_mask_bits: action space %d too large", A);
-  pack_mask_bits_kernel<<<(unsigned)rows, 256, smem, stream>>>((const uint8_t*)mask_bytes, (uint32_t*)bits, rows, A, words, rows * (long long)A);
+  const int base_off = (int)((uintptr_t)mask_bytes & 15);
+  const int chunks = (words * 2 + 32 * kPackIters - 1) / (32 * kPackIters);
+  const long long warps = rows * chunks;
+  pack_mask_bits_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>((const uint8_t*)mask_bytes - base_off, (uint32_t*)bits, rows, A, words,
+                                                                        chunks, base_off);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

@@ -585,6 +585,10 @@ class KataGoPPOAlgorithm:
         (reference katago_ppo.py:858-888, :33-43) — one fused kernel on CUDA."""
         p = self.params
         if flat_logits.is_cuda:
+            if masks is not None and masks.dtype != torch.int32:
+                # byte masks handed in directly (the device-resident buffer already stores packed rows): pack once, the
+                # forward and backward kernels over packed masks read 8x less mask and skip every illegal logit
+                masks = policy_ops.pack_mask_bits(masks)
             out2, _, _, _, _, flags = policy_ops.ppo_policy_loss(flat_logits, masks, actions, old_lp, adv, p.clip_epsilon)
             return out2[0], out2[1], flags
         if flat_logits.isnan().any():

@@ -258,13 +258,11 @@ def policy_sample(logits: torch.Tensor, mask: torch.Tensor | None, value_logits:
     `forced_actions` (int64, (B,)) skips the draw and reports the log-prob of the given actions.
     Bit-packed masks go to the warp-per-row kernel that touches only the legal logits. Bool / uint8 masks: `dense=False`
     packs them first (`pack_mask_bits`) for that kernel, `dense=True` keeps the byte mask and the one-CTA-per-row kernel
-    that stages the whole row (same draw, log-probs equal up to summation order); the default picks by batch — measured
-    on B200, pack + sparse is 100 us against 130 us at 4096 rows but 63 us against 43 us at 512 (tools/bench_sample.py).
+    that stages the whole row (same draw, log-probs equal up to summation order); the default is to pack
+    (tools/bench_sample.py has the timings of both).
     """
     B, A, stride = _check_logits(logits)
     dev = logits.device
-    if dense is None:
-        dense = B < 2048
     if mask is not None and mask.dtype != torch.int32 and not dense:
         if mask.shape != (B, A):
             raise ValueError(f"legal mask shape {tuple(mask.shape)} != {(B, A)}")

@@ -41,10 +41,19 @@ def test_pack_unpack_roundtrip_and_bit_order(A_):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_loss_and_sampler_kernels_packed_equals_bytes(dtype):
+@pytest.mark.parametrize("padded", [True, False])
+def test_loss_and_sampler_kernels_packed_equals_bytes(dtype, padded):
+    """Bit-packed masks run their own kernels (streaming NaN scan + walk over the legal entries; write-only backward):
+    same integers (flags, zero gradient on illegal entries), floats equal to the byte-mask kernels up to summation order.
+    `padded=False` gives rows that are not 16-byte aligned: the scalar tails and the generic backward."""
     B = 70
     logits, mask, acts = _rows(B, 3, dtype)
+    if not padded:
+        logits = logits.contiguous()
     mask[5] = False; mask[5, 77] = True                      # single legal action
+    mask[6] = False; mask[6, 11258] = True; mask[6, 0] = True   # first and last action of the row
+    acts[6] = 11258
+    acts[7] = int((~mask[7]).nonzero()[0])                   # an ILLEGAL action: log-prob -inf in both
     bits = policy_ops.pack_mask_bits(mask)
     g = torch.Generator(device=DEV).manual_seed(4)
     old, adv = -3 * torch.rand(B, device=DEV, generator=g), torch.randn(B, device=DEV, generator=g)
@@ -52,25 +61,63 @@ def test_loss_and_sampler_kernels_packed_equals_bytes(dtype):
     for name, mk in (("bytes", mask), ("bits", bits)):
         lg = logits.detach().clone().requires_grad_(True)
         out2, new_lp, row_ent, row_lse, dlogp, flags = policy_ops.ppo_policy_loss(lg, mk, acts, old, adv, 0.2)
-        (out2[0] - 0.01 * out2[1]).backward()
-        outs[name] = (out2.detach(), new_lp.detach(), row_ent.detach(), row_lse.detach(), lg.grad.clone(), flags)
-    for a, b in zip(outs["bytes"], outs["bits"]):
-        assert torch.equal(a, b)
-    assert bool((outs["bits"][4][~mask] == 0).all())
+        ok = torch.ones(B, dtype=torch.bool, device=DEV); ok[7] = False
+        (new_lp[ok].sum() * 0.01 + row_ent.sum() * 0.002).backward()
+        outs[name] = (new_lp.detach(), row_ent.detach(), row_lse.detach(), lg.grad.clone(), flags)
+    by, bi = outs["bytes"], outs["bits"]
+    assert torch.equal(by[4], bi[4]) and int(bi[4][0]) == 0 and int(bi[4][1]) == 0
+    assert bool(torch.isneginf(bi[0][7])) and bool(torch.isneginf(by[0][7]))
+    ok = torch.ones(B, dtype=torch.bool, device=DEV); ok[7] = False
+    for k in (0, 1, 2):
+        assert torch.allclose(by[k][ok], bi[k][ok], rtol=2e-6, atol=2e-6), k
+    assert bool((bi[3][~mask] == 0).all())
+    gd = (by[3].float() - bi[3].float()).abs()
+    tol = 1e-7 if dtype == torch.float32 else 4e-3 * by[3].float().abs().max()      # one bf16 ulp of the largest entry
+    assert float(gd.max()) <= float(tol), float(gd.max())
     vl = torch.randn(B, 3, device=DEV)
     for forced in (None, acts):
-        r0 = policy_ops.policy_sample(logits, mask, vl, seed=11, offset=5, forced_actions=forced)
+        r0 = policy_ops.policy_sample(logits, mask, vl, seed=11, offset=5, forced_actions=forced, dense=True)
         r1 = policy_ops.policy_sample(logits, bits, vl, seed=11, offset=5, forced_actions=forced)
-        for a, b in zip(r0, r1):
-            assert torch.equal(a, b)
+        r2 = policy_ops.policy_sample(logits, mask, vl, seed=11, offset=5, forced_actions=forced, dense=False)
+        for k in (0, 2, 3, 4):
+            assert torch.equal(r0[k], r1[k]), k
+        for a, b in zip(r1, r2):                                   # packing on the fly == pre-packed
+            assert torch.equal(a, b) or bool((a.isnan() == b.isnan()).all() and torch.equal(a.nan_to_num(), b.nan_to_num()))
+        fin = ~torch.isinf(r0[1]) & ~torch.isnan(r0[1])
+        assert float((r0[1][fin] - r1[1][fin]).abs().max()) <= (2e-5 if dtype == torch.float32 else 0.0625)
         if forced is None:
             assert mask[torch.arange(B, device=DEV), r1[0]].all()
             assert int(r1[0][5]) == 77                             # the row with a single legal action
     # zero-legal row is flagged identically
     bad = mask.clone(); bad[9] = False
-    f0 = policy_ops.policy_sample(logits, bad, vl, seed=1, offset=1)[4]
+    f0 = policy_ops.policy_sample(logits, bad, vl, seed=1, offset=1, dense=True)[4]
     f1 = policy_ops.policy_sample(logits, policy_ops.pack_mask_bits(bad), vl, seed=1, offset=1)[4]
     assert int(f0[0]) == 1 and torch.equal(f0, f1)
+    outb = policy_ops.ppo_policy_loss(logits, policy_ops.pack_mask_bits(bad), acts, old, adv, 0.2)
+    assert int(outb[5][0]) == 1 and float(outb[1][9]) == 0.0 and float(outb[2][9]) == 0.0
+    # NaN in an ILLEGAL raw logit is still reported (the reference checks the raw model output, katago_ppo.py:860-862)
+    poisoned = logits.clone()
+    poisoned[11, int((~mask[11]).nonzero()[3])] = float("nan")
+    poisoned[12, A - 1] = float("nan")                             # in the scalar tail of the row
+    for mk in (mask, bits):
+        assert int(policy_ops.ppo_policy_loss(poisoned, mk, acts, old, adv, 0.2)[5][1]) == 2
+
+
+@pytest.mark.parametrize("rows", [1, 3, 64])
+def test_pack_rows_at_every_alignment_and_tensor_tail(rows):
+    """Rows of 11,259 bytes start at every byte alignment; the last row ends at the tensor's last byte (no over-read that
+    changes the result): compare with a host-side numpy packbits."""
+    g = torch.Generator(device=DEV).manual_seed(rows)
+    mask = (torch.rand(rows, A, device=DEV, generator=g) < 0.5)
+    mask[-1, -5:] = True
+    as_u8 = (mask.to(torch.uint8) * 255)                           # any non-zero byte is a set bit
+    want = np.packbits(np.pad(mask.cpu().numpy(), ((0, 0), (0, 352 * 32 - A))), axis=1, bitorder="little").view(np.uint32)
+    for m in (mask, as_u8):
+        got = policy_ops.pack_mask_bits(m).cpu().numpy().view(np.uint32)
+        np.testing.assert_array_equal(got, want)
+    if rows > 1:                                                   # a row slice starts at an arbitrary byte address
+        got = policy_ops.pack_mask_bits(mask[1:]).cpu().numpy().view(np.uint32)
+        np.testing.assert_array_equal(got, want[1:])
 
 
 def test_no_mask_mode_is_plain_log_softmax_and_sl_losses_match_torch():
