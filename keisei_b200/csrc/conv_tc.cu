@@ -638,29 +638,38 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 // dW[co][ci][tap] = sum_{board, pixel} dY[board][pixel][co] * X[board][pixel + shift(tap)][ci]
 //
 // GEMM view per CTA: one (tap, 128-channel half of Cout) unit and one slice of the boards.
-//   D[co (128 TMEM lanes), ci (N = Cin columns)] += A[co, k] * B[ci, k],  k = pixels of one board.
+//   D[co (128 TMEM lanes), ci (N = Cin columns)] += A[co, k] * B[ci, k],  k = pixels.
 // Both operands are "MN-major": in NHWC memory the channel index is contiguous for a fixed pixel k.
-// TMA lands each board as 64-channel groups of [81 pixel rows x 128 B] (swizzle 128B); rows 81..95
-// of every group are zeroed once and never written, so K is padded 81 -> 96 = 6 x UMMA_K for free.
+// K is a multiple of UMMA_K = 16 but a board has 81 pixels. Rather than padding every board to 96 rows (15.6 % of the
+// tensor work multiplying zeros), a board stage holds pixels 0..79 (two TMA boxes per 64-channel group: 9 x 8 rows and the
+// first 8 pixels of the last row; 80 rows x 128 B, swizzle 128B, both landing on 1024-byte boundaries) = 5 UMMA_K steps,
+// and the 81st pixel (8, 8) of SIXTEEN consecutive boards arrives as one extra box (1 x 1 x 16 boards = 16 rows) = one
+// more step per 16 boards: 81 steps per 16 boards... per board 5 + 1/16, no zero work. The "extras" item travels through
+// the same stage ring as the boards. Slices are multiples of 16 boards; boards past B are zero-filled by TMA.
 // The tap shift is the TMA box origin on X (zero fill at the board edge), exactly as in the forward.
 // Partial tiles go to a workspace with coalesced stores; wgrad_reduce_kernel sums the board slices
 // and scatters into the PyTorch (Cout, Cin, 3, 3) fp32 gradient.
 constexpr int kWgStages = 3;
-constexpr int kWgRows = 96;                          // 81 pixels padded to a multiple of UMMA_K
-constexpr int kWgGroupBytes = kWgRows * 128;         // one 64-channel group of one board: 12 KB
-constexpr int kWgBoxBytes = 81 * 128;                // bytes TMA writes per group
+constexpr int kWgRows = 80;                          // pixels 0..79 of one board
+constexpr int kWgGroupBytes = kWgRows * 128;         // one 64-channel group of one board: 10 KB (a multiple of 1024)
+constexpr int kWgMainBytes = 72 * 128;               // box 9 x 8
+constexpr int kWgRowBytes = 8 * 128;                 // box 8 x 1, lands at row 72
+constexpr int kWgExtraBoards = 16;                   // boards whose last pixel shares one UMMA_K step
+constexpr int kWgExtraBytes = kWgExtraBoards * 128;
 constexpr int kWgAGroups = 2;                        // 128 output channels
 constexpr int kWgMaxBGroups = 4;                     // up to 256 input channels
-constexpr int kWgStageBytes = (kWgAGroups + kWgMaxBGroups) * kWgGroupBytes;  // 72 KB
+constexpr int kWgStageBytes = (kWgAGroups + kWgMaxBGroups) * kWgGroupBytes;  // 60 KB
 constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 1024 + 256;
 
 // MN-major operand, SWIZZLE_128B: 64-element groups LBO apart, 8-row (k) groups SBO = 1024 B apart
+struct WgMaps { CUtensorMap main, row, extra; };     // boxes (64c, 9, 8, 1), (64c, 8, 1, 1), (64c, 1, 1, 16)
+
 __device__ __forceinline__ uint64_t smem_desc_mn128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(kWgGroupBytes >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+conv3x3_wgrad_tc_kernel(const __grid_constant__ WgMaps map_dy, const __grid_constant__ WgMaps map_x,
                         float* __restrict__ ws, int B, int Cin, int Cout, int units, int boards_per_slice) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -681,24 +690,18 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
   const int b_end = min(B, b_begin + boards_per_slice);
   const int nboards = b_end - b_begin;
 
-  // zero the whole operand area once: the K-padding rows (81..95 of every group) must read as 0
-  {
-    uint4* p = reinterpret_cast<uint4*>(smem_gen);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < kWgStages * kWgStageBytes / 16; i += kThreads) p[i] = z;
-  }
+  const int nblocks = (nboards + kWgExtraBoards - 1) / kWgExtraBoards;   // items: per block its boards, then one extras item
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(done_bar, 1);
     fence_barrier_init();
-    tma_prefetch_desc(&map_dy);
-    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy.main); tma_prefetch_desc(&map_dy.row); tma_prefetch_desc(&map_dy.extra);
+    tma_prefetch_desc(&map_x.main); tma_prefetch_desc(&map_x.row); tma_prefetch_desc(&map_x.extra);
   }
   if (warp == 1) {
     tmem_alloc(holder, 256);
     tmem_relinquish();
   }
-  fence_proxy_async();  // generic-proxy zero fill -> visible to the async proxy (TMA / UMMA)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -709,18 +712,36 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     const bool issuer = elect_one_sync();
     const int sx = tap % 3 - 1, sy = tap / 3 - 1;
     int stage = 0; uint32_t phase = 0;
-    for (int b = b_begin; b < b_end; ++b) {
-      mbar_wait(empty_bar(stage), phase ^ 1u);
-      const uint32_t a_dst = smem_base + stage * kWgStageBytes;
-      if (issuer) {
-        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)((kWgAGroups + b_groups) * kWgBoxBytes));
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const int b0 = b_begin + blk * kWgExtraBoards;
+      const int nb = min(kWgExtraBoards, b_end - b0);
+      for (int i = 0; i <= nb; ++i) {               // i == nb: the extras item of this block
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t a_dst = smem_base + stage * kWgStageBytes;
+        if (issuer) {
+          if (i < nb) {
+            const int b = b0 + i;
+            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)((kWgAGroups + b_groups) * kWgGroupBytes));
 #pragma unroll
-        for (int g = 0; g < kWgAGroups; ++g)
-          tma_load_4d(a_dst + g * kWgGroupBytes, &map_dy, full_bar(stage), half * kTileM + g * 64, 0, 0, b);
-        for (int g = 0; g < b_groups; ++g)
-          tma_load_4d(a_dst + (kWgAGroups + g) * kWgGroupBytes, &map_x, full_bar(stage), g * 64, sx, sy, b);
+            for (int g = 0; g < kWgAGroups; ++g) {
+              tma_load_4d(a_dst + g * kWgGroupBytes, &map_dy.main, full_bar(stage), half * kTileM + g * 64, 0, 0, b);
+              tma_load_4d(a_dst + g * kWgGroupBytes + kWgMainBytes, &map_dy.row, full_bar(stage), half * kTileM + g * 64, 0, 8, b);
+            }
+            for (int g = 0; g < b_groups; ++g) {
+              tma_load_4d(a_dst + (kWgAGroups + g) * kWgGroupBytes, &map_x.main, full_bar(stage), g * 64, sx, sy, b);
+              tma_load_4d(a_dst + (kWgAGroups + g) * kWgGroupBytes + kWgMainBytes, &map_x.row, full_bar(stage), g * 64, sx, sy + 8, b);
+            }
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)((kWgAGroups + b_groups) * kWgExtraBytes));
+#pragma unroll
+            for (int g = 0; g < kWgAGroups; ++g)
+              tma_load_4d(a_dst + g * kWgGroupBytes, &map_dy.extra, full_bar(stage), half * kTileM + g * 64, 8, 8, b0);
+            for (int g = 0; g < b_groups; ++g)
+              tma_load_4d(a_dst + (kWgAGroups + g) * kWgGroupBytes, &map_x.extra, full_bar(stage), g * 64, sx + 8, sy + 8, b0);
+          }
+        }
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
       }
-      if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     const bool issuer = elect_one_sync();
@@ -728,22 +749,27 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(Cin >> 3) << 17) |
                            ((uint32_t)(kTileM >> 4) << 24);
     int stage = 0; uint32_t phase = 0;
-    for (int i = 0; i < nboards; ++i) {
-      mbar_wait(full_bar(stage), phase);
-      tc_fence_after();
-      const uint32_t a_addr = smem_base + stage * kWgStageBytes;
-      const uint64_t adesc = smem_desc_mn128(a_addr);
-      const uint64_t bdesc = smem_desc_mn128(a_addr + kWgAGroups * kWgGroupBytes);
-      if (issuer) {
-#pragma unroll
-        for (int k = 0; k < kWgRows / 16; ++k) {
-          // 16 pixel rows = 2048 bytes further down every group: +128 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (i | k) != 0 ? 1u : 0u);
+    uint32_t accumulate = 0;
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const int nb = min(kWgExtraBoards, nboards - blk * kWgExtraBoards);
+      for (int i = 0; i <= nb; ++i) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + stage * kWgStageBytes;
+        const uint64_t adesc = smem_desc_mn128(a_addr);
+        const uint64_t bdesc = smem_desc_mn128(a_addr + kWgAGroups * kWgGroupBytes);
+        if (issuer) {
+          const int ksteps = i < nb ? kWgRows / 16 : 1;     // a board: 80 pixels; the extras item: 16 last pixels
+          for (int k = 0; k < ksteps; ++k) {
+            // 16 pixel rows = 2048 bytes further down every group: +128 in the (addr >> 4) field
+            umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, accumulate);
+            accumulate = 1u;
+          }
+          umma_commit(empty_bar(stage));
         }
-        umma_commit(empty_bar(stage));
+        __syncwarp();
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
     }
     if (issuer) umma_commit(done_bar);
   } else {
@@ -769,6 +795,153 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------- weight-gradient kernel, CTA pair (cta_group::2)
+// The single-CTA kernel above moves 6 operand groups (60 KB) per board into every SM for 5 UMMA_K steps: ~81 B/clk per
+// SM, which is what the L2 -> shared-memory path delivers (measured: cutting the tensor work by 15.6 % bought 3.5 %).
+// A CTA pair computes the whole 256 x Cin gradient tile of one tap with M = 256 UMMAs: each CTA loads only ITS 128 output
+// channels of dY and ITS half of the input channels of X (4 groups, 40 KB per board), the tensor cores of both SMs read
+// the B halves from both shared memories. Cluster = (tap, board slice); rank = Cout half = the workspace block the
+// reduce kernel expects. Same item stream (boards of 80 pixels + one extras item per 16 boards), 5-stage ring.
+constexpr int kWg2Stages = 5;
+constexpr int kWg2Groups = 4;                                   // per CTA: 2 of dY + up to 2 of X
+constexpr int kWg2StageBytes = kWg2Groups * kWgGroupBytes;      // 40 KB
+constexpr int kWg2SmemBytes = kWg2Stages * kWg2StageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_wgrad_tc2_kernel(const __grid_constant__ WgMaps map_dy, const __grid_constant__ WgMaps map_x,
+                         float* __restrict__ ws, int B, int Cin, int boards_per_slice) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + kWg2Stages * kWg2StageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kWg2Stages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kWg2Stages);
+  const uint32_t holder = bar_base + 8u * (2 * kWg2Stages + 1);
+  volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kWg2Stages * kWg2StageBytes + 8 * (2 * kWg2Stages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int cl = (int)(blockIdx.x >> 1);                 // cluster index = slice * 9 + tap
+  const int tap = cl % 9, slice = cl / 9;
+  const int bg = Cin / 128;                              // X groups per CTA (its half of the input channels)
+  const int b_begin = slice * boards_per_slice;
+  const int b_end = min(B, b_begin + boards_per_slice);
+  const int nboards = b_end - b_begin;
+  const int nblocks = (nboards + kWgExtraBoards - 1) / kWgExtraBoards;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWg2Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_dy.main); tma_prefetch_desc(&map_dy.row); tma_prefetch_desc(&map_dy.extra);
+    tma_prefetch_desc(&map_x.main); tma_prefetch_desc(&map_x.row); tma_prefetch_desc(&map_x.extra);
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(holder, 256);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything is signalled at them
+  tc_fence_after();
+  const uint32_t tmem_base = *holder_ptr;
+
+  if (warp == 0) {
+    // TMA producer (both CTAs): data lands in the issuing CTA, the bytes are credited to the leader's full barrier
+    const bool issuer = elect_one_sync();
+    const int sx = tap % 3 - 1, sy = tap / 3 - 1;
+    const int co0 = (int)crank * kTileM, ci0 = (int)crank * bg * 64;
+    int stage = 0; uint32_t phase = 0;
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const int b0 = b_begin + blk * kWgExtraBoards;
+      const int nb = min(kWgExtraBoards, b_end - b0);
+      for (int i = 0; i <= nb; ++i) {               // i == nb: the extras item of this block
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t a_dst = smem_base + stage * kWg2StageBytes;
+        if (issuer) {
+          if (i < nb) {
+            const int b = b0 + i;
+            if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(2 * (kWgAGroups + bg) * kWgGroupBytes));
+#pragma unroll
+            for (int g = 0; g < kWgAGroups; ++g) {
+              tma_load_4d_2cta(a_dst + g * kWgGroupBytes, &map_dy.main, full_bar(stage), co0 + g * 64, 0, 0, b);
+              tma_load_4d_2cta(a_dst + g * kWgGroupBytes + kWgMainBytes, &map_dy.row, full_bar(stage), co0 + g * 64, 0, 8, b);
+            }
+            for (int g = 0; g < bg; ++g) {
+              tma_load_4d_2cta(a_dst + (kWgAGroups + g) * kWgGroupBytes, &map_x.main, full_bar(stage), ci0 + g * 64, sx, sy, b);
+              tma_load_4d_2cta(a_dst + (kWgAGroups + g) * kWgGroupBytes + kWgMainBytes, &map_x.row, full_bar(stage), ci0 + g * 64, sx, sy + 8, b);
+            }
+          } else {
+            if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(2 * (kWgAGroups + bg) * kWgExtraBytes));
+#pragma unroll
+            for (int g = 0; g < kWgAGroups; ++g)
+              tma_load_4d_2cta(a_dst + g * kWgGroupBytes, &map_dy.extra, full_bar(stage), co0 + g * 64, 8, 8, b0);
+            for (int g = 0; g < bg; ++g)
+              tma_load_4d_2cta(a_dst + (kWgAGroups + g) * kWgGroupBytes, &map_x.extra, full_bar(stage), ci0 + g * 64, sx + 8, sy + 8, b0);
+          }
+        }
+        if (++stage == kWg2Stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (crank == 0) {   // one elected lane of the leader issues the pair's MMAs
+      const bool issuer = elect_one_sync();
+      // M = 256 over the pair, N = Cin, A and B MN-major (bits 15, 16), fp32 accumulate, bf16 inputs
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(Cin >> 3) << 17) |
+                             ((uint32_t)(256 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      for (int blk = 0; blk < nblocks; ++blk) {
+        const int nb = min(kWgExtraBoards, nboards - blk * kWgExtraBoards);
+        for (int i = 0; i <= nb; ++i) {
+          mbar_wait(full_bar(stage), phase);        // both CTAs' boxes of this item have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * kWg2StageBytes;
+          const uint64_t adesc = smem_desc_mn128(a_addr);
+          const uint64_t bdesc = smem_desc_mn128(a_addr + kWgAGroups * kWgGroupBytes);
+          if (issuer) {
+            const int ksteps = i < nb ? kWgRows / 16 : 1;
+            for (int k = 0; k < ksteps; ++k) {
+              umma_bf16_2cta(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, accumulate);
+              accumulate = 1u;
+            }
+            umma_commit_2cta_mc(empty_bar(stage), (uint16_t)3);   // frees the stage in both CTAs
+          }
+          __syncwarp();
+          if (++stage == kWg2Stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (issuer) umma_commit_2cta_mc(done_bar, (uint16_t)3);
+    }
+  } else {
+    const int lane_grp = warp & 3;
+    // ws[slice * 18 + tap * 2 + half][ci][co_local]: the layout wgrad_reduce_kernel sums
+    float* dst = ws + ((size_t)(slice * 18 + tap * 2 + (int)crank) * Cin) * kTileM + lane_grp * 32 + lane;
+    if (nboards > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+      for (int ch = 0; ch < Cin / 16; ++ch) {
+        uint32_t r[16];
+        tmem_ld16(taddr + ch * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dst[(size_t)(ch * 16 + i) * kTileM] = __uint_as_float(r[i]);
+      }
+    } else {
+      for (int ci = 0; ci < Cin; ++ci) dst[(size_t)ci * kTileM] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still read this CTA's operands / signal its barriers until it is done too
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 256);
   }
 }
 
@@ -1058,20 +1231,46 @@ int kbk_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int Ci
   int slices = num_sms / units;
   if (slices < 1) slices = 1;
   if (slices > B) slices = B;
-  const int bps = kb_ceil_div(B, slices);
+  // whole 16-board blocks per slice: the 81st pixels of a block share one TMA box and one UMMA_K step
+  const int bps = kb_ceil_div(kb_ceil_div(B, slices), kWgExtraBoards) * kWgExtraBoards;
   slices = kb_ceil_div(B, bps);
   KB_CHECK_ARG(ws != nullptr && ws_bytes >= (long long)slices * units * Cin * kTileM * (long long)sizeof(float),
                "conv3x3_wgrad_tc: workspace too small");
-  CUtensorMap mdy, mx;
-  if (int r = make_act_map(&mdy, dy, B, Cout, 1)) return r;
-  if (int r = make_act_map(&mx, x, B, Cin, 1)) return r;
-  static bool attr_set = false;
-  if (!attr_set) {
-    KB_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
-    attr_set = true;
+  WgMaps mdy, mx;
+  if (int r = make_act_box_map(&mdy.main, dy, B, Cout, 9, 8, 1)) return r;
+  if (int r = make_act_box_map(&mdy.row, dy, B, Cout, 8, 1, 1)) return r;
+  if (int r = make_act_box_map(&mdy.extra, dy, B, Cout, 1, 1, kWgExtraBoards)) return r;
+  if (int r = make_act_box_map(&mx.main, x, B, Cin, 9, 8, 1)) return r;
+  if (int r = make_act_box_map(&mx.row, x, B, Cin, 8, 1, 1)) return r;
+  if (int r = make_act_box_map(&mx.extra, x, B, Cin, 1, 1, kWgExtraBoards)) return r;
+  static const bool pair_off = [] { const char* e = getenv("KB_WGRAD_2CTA"); return e && e[0] == '0'; }();
+  if (!pair_off && Cout == 256 && (Cin == 128 || Cin == 256)) {
+    // CTA-pair kernel: cluster = (tap, slice), the two ranks are the two Cout halves -> the same 18 workspace blocks per slice
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      KB_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWg2SmemBytes));
+      attr2_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(units * slices)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kWg2SmemBytes; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributePriority;
+    at[1].val.priority = conv_priority();
+    cfg.attrs = at; cfg.numAttrs = conv_priority() != 0 ? 2 : 1;
+    KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv3x3_wgrad_tc2_kernel, mdy, mx, ws, B, Cin, bps));
+    kb_count_launch();
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      KB_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+      attr_set = true;
+    }
+    launch_prio(conv3x3_wgrad_tc_kernel, units * slices, kThreads, kWgSmemBytes, st, mdy, mx, ws, B, Cin, Cout, units, bps);
+    KB_CUDA_LAUNCH_CHECK();
   }
-  launch_prio(conv3x3_wgrad_tc_kernel, units * slices, kThreads, kWgSmemBytes, st, mdy, mx, ws, B, Cin, Cout, units, bps);
-  KB_CUDA_LAUNCH_CHECK();
   wgrad_reduce_kernel<<<dim3(kb_ceil_div(Cout, 32), kb_ceil_div(Cin_true, kRedCi)), 256, 0, st>>>(ws, dw, Cin, Cout, Cin_true, units, slices);
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;

@@ -85,7 +85,8 @@ def test_linearity_at_full_size():
     assert rel(o1[1000:1003].float().cpu().numpy(), o3.float().cpu().numpy()) < 1e-2
 
 
-@pytest.mark.parametrize("B,Cin,Cout,ct", [(3, 64, 128, None), (8, 64, 256, 50), (5, 256, 256, None), (130, 256, 256, None), (29, 128, 256, None)])
+@pytest.mark.parametrize("B,Cin,Cout,ct", [(3, 64, 128, None), (8, 64, 256, 50), (5, 256, 256, None), (130, 256, 256, None), (29, 128, 256, None),
+                                           (1, 64, 128, None), (16, 256, 256, None), (33, 128, 128, None), (300, 256, 256, None)])
 def test_conv3x3_wgrad_tc(B, Cin, Cout, ct):
     g = torch.Generator().manual_seed(100 + B)
     x = torch.randn(B, Cin, 9, 9, generator=g).bfloat16()
