@@ -176,15 +176,26 @@ def test_fused_optimizer_tail_matches_torch_adam_and_keeps_state_dict(use_amp):
             _fill(buf, N, T, A, 40 + rep)
             torch.manual_seed(100 + rep)
             algo.update(buf, torch.zeros(N, device=DEV))
-    tol = dict(rtol=2e-2, atol=2e-3) if use_amp else dict(rtol=1e-4, atol=1e-6)   # bf16: side-stream atomics reorder the gradient's last bits
+    # Two independent trajectories: the gradients of two runs differ in their last bits (3.5e-8 relative: atomics in the
+    # weight-gradient / BatchNorm sums, tools/grad_nondeterminism.py), and Adam divides by sqrt(v) + eps — an element whose gradient is
+    # below eps = 1e-8 moves by lr * g / eps, so last-bit noise there becomes a step of order lr, after which every
+    # gradient of the two runs differs at the 1e-3 level. The trajectories are therefore compared loosely (an algorithmic
+    # error in the tail — bias correction, eps placement, clip coefficient — is an O(1) relative error); the tight check
+    # of the tail's arithmetic is test_fused_optimizer_tail_equals_stock_tail_on_identical_gradients below.
+    tol = dict(rtol=2e-2, atol=2e-3) if use_amp else dict(rtol=5e-3, atol=2e-5)
+    lr, steps = ta.params.learning_rate, 6
     for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
-        assert torch.allclose(p, q, **tol), n
+        d = (p - q).abs()
+        bad = d > tol["atol"] + tol["rtol"] * q.abs()
+        assert float(bad.float().mean()) <= 0.02 and float(d.max()) <= 2.2 * steps * lr, (n, float(bad.float().mean()), float(d.max()))
     sa, sb = ta.optimizer.state_dict(), tb.optimizer.state_dict()
     assert sa["param_groups"] == sb["param_groups"] and sa["state"].keys() == sb["state"].keys()
     for k in sa["state"]:
         assert set(sa["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
         assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 6.0   # 2 minibatches x 3 updates
-        assert torch.allclose(sa["state"][k]["exp_avg"], sb["state"][k]["exp_avg"], **tol)
+    ea = torch.cat([sa["state"][k]["exp_avg"].flatten() for k in sa["state"]])
+    eb = torch.cat([sb["state"][k]["exp_avg"].flatten() for k in sb["state"]])
+    assert float((ea - eb).norm()) <= (0.25 if use_amp else 5e-3) * float(eb.norm()), float((ea - eb).norm() / eb.norm())
     # the state is interchangeable: a fresh torch Adam loads it (checkpoint.py:123 restores positionally) ...
     fresh = torch.optim.Adam(a.parameters(), lr=ta.params.learning_rate, fused=True)
     fresh.load_state_dict(sa)
@@ -197,6 +208,37 @@ def test_fused_optimizer_tail_matches_torch_adam_and_keeps_state_dict(use_amp):
     assert all(np.isfinite(v) for v in m.values())
     assert any(not torch.equal(x, y) for x, y in zip(before, a.parameters()))
     assert float(fresh.state_dict()["state"][0]["step"]) == 8.0
+
+
+@pytest.mark.parametrize("use_amp", [False, True])
+def test_fused_optimizer_tail_equals_stock_tail_on_identical_gradients(use_amp):
+    """The tail's arithmetic in isolation: both trainers are handed the SAME flat gradient every step (the second trainer's
+    buffer is overwritten with the first one's), so unscale + global-norm clip + Adam of csrc/optim.cu must reproduce
+    GradScaler.unscale_ + clip_grad_norm_ + torch.optim.Adam(fused) to fp32 rounding, step after step."""
+    a, b, ta, tb = _two_trainers(use_amp)
+    dev = torch.device(DEV)
+    N, A = 12, 11259
+    g = torch.Generator().manual_seed(9)
+    for step in range(5):
+        obs = torch.randn(N, 50, 9, 9, generator=g).to(DEV)
+        mask = torch.rand(N, A, generator=g) < 0.01
+        acts = torch.randint(0, A, (N,), generator=g); mask[torch.arange(N), acts] = True
+        mb = (mask.to(DEV), acts.to(DEV), (-2 * torch.rand(N, generator=g)).to(DEV), torch.randn(N, generator=g).to(DEV),
+              torch.randint(0, 3, (N,), generator=g).to(DEV), torch.randn(N, generator=g).clamp(-1, 1).to(DEV),
+              torch.randn(N, generator=g).to(DEV))
+        for model, algo in ((a, ta), (b, tb)):
+            model.train()
+            algo._step_fused(algo._kernel_model(dev), obs, mb, None)
+        tb._flat_grad.copy_(ta._flat_grad)
+        ta._optimizer_tail(); tb._optimizer_tail()
+        for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+            assert torch.allclose(p, q, rtol=2e-6, atol=1e-8), (step, n, float((p - q).abs().max()))
+    sa, sb = ta.optimizer.state_dict(), tb.optimizer.state_dict()
+    for k in sa["state"]:
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 5.0
+        for key in ("exp_avg", "exp_avg_sq"):
+            x, y = sa["state"][k][key], sb["state"][k][key]   # torch: lerp_ / addcmul_; here: fused multiply-adds
+            assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max()) + 1e-30, (k, key, float((x - y).abs().max()))
 
 
 def test_fused_optimizer_tail_skips_non_finite_gradients():
