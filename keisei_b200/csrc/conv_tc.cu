@@ -472,7 +472,34 @@ template <bool kSeTail> struct PairCfg {
 constexpr uint32_t kTxBytes2 = 2u * kABytes + 128u * 128u + 115u * 128u;   // both CTAs' boxes (OOB-filled elements count)
 constexpr uint32_t kIdescF16M256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
-struct PairMaps { CUtensorMap full, rows5, x2, x7, rows3; };
+// Two-board ("narrow") tiles, N = 176: CTA 0 holds board 0 and the first 7 pixels of board 1 (88 columns), CTA 1 the
+// other 74 pixels (2 of row 0 + rows 1-8) and 14 columns nobody reads.
+constexpr int kNarrowN = 176;
+constexpr uint32_t kTxBytes2Narrow = 2u * kABytes + 88u * 128u + 74u * 128u;
+constexpr uint32_t kIdescF16M256Narrow = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNarrowN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+struct PairMaps { CUtensorMap full, rows5, x2, x7, rows3, rows8; };
+
+// Tile schedule of the pair kernel. The boards are dealt to the CTA pairs as contiguous, near-equal ranges (the pairs are
+// persistent: the kernel ends with the slowest one), and a range is cut into three-board tiles plus zero, one or two
+// two-board tiles (N = 176 instead of 256: 0.69 of the MMA time), so a range of 7 boards costs 256 + 176 + 176 columns
+// instead of three full tiles. 512 boards on 74 pairs: 608 columns for the slowest pair instead of 768; 4096 boards: 4784
+// instead of 4864. All three warp roles walk the same sequence.
+struct PairSched {
+  int b, end, cp, n_pairs;
+  __device__ __forceinline__ PairSched(int B, int n_pairs_) : cp(0), n_pairs(n_pairs_) {
+    const int P = (int)(gridDim.x >> 1), p = (int)(blockIdx.x >> 1);
+    const int base = B / P, rem = B % P;
+    b = p * base + min(p, rem);
+    end = b + base + (p < rem ? 1 : 0);
+  }
+  __device__ __forceinline__ bool done() const { return b >= end; }
+  __device__ __forceinline__ int boards() const {          // boards of the tile starting at b: 3, or 2 / 1 at the tail
+    const int left = end - b;
+    return (left == 1 || left == 2 || left == 4) ? min(left, 2) : 3;
+  }
+  __device__ __forceinline__ void next() { if (++cp == n_pairs) { cp = 0; b += boards(); } }
+};
 
 template <int F, bool kSeTail>
 __global__ void __launch_bounds__(kThreads2, 1)   // 10 warps are allocated as 12 (groups of 4): 168 registers per thread at most
@@ -497,9 +524,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   const int kb_per_tap = Cin / kBlockK;
   const int num_kb = 9 * kb_per_tap;
   const uint32_t crank = cluster_ctarank();
-  const int n_pairs = Cout / 256;                       // channel pairs per board group
-  const int num_tiles = num_groups * n_pairs;
-  const int t_first = (int)(blockIdx.x >> 1), t_step = (int)(gridDim.x >> 1);
+  const int n_pairs = Cout / 256;                       // channel pairs per board tile
+  (void)num_groups;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -523,9 +549,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     // ===== TMA producer (both CTAs): the warp runs the loop uniformly, one elected lane issues =====
     const bool issuer = elect_one_sync();
     int stage = 0; uint32_t phase = 0;
-    for (int t = t_first; t < num_tiles; t += t_step) {
-      const int grp = t / n_pairs, ct = (t % n_pairs) * 2 + (int)crank;
-      const int b0 = grp * kBoards;
+    for (PairSched ts(B, n_pairs); !ts.done(); ts.next()) {
+      const int ct = ts.cp * 2 + (int)crank;
+      const int b0 = ts.b;
+      const bool wide = ts.boards() == kBoards;
       int tap = 0, cc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int sx = tap % 3 - 1, sy = tap / 3 - 1, c0 = cc * kBlockK;
@@ -533,9 +560,17 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         const uint32_t a_dst = smem_base + stage * kStageBytes2;
         const uint32_t b_dst = a_dst + kABytes;
         if (issuer) {
-          if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), kTxBytes2);
+          if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), wide ? kTxBytes2 : kTxBytes2Narrow);
           tma_load_2d_2cta(a_dst, &map_w, full_bar(stage), kb * kBlockK, ct * kTileM);
-          if (crank == 0) {
+          if (!wide) {
+            if (crank == 0) {
+              tma_load_4d_2cta(b_dst, &mx.full, full_bar(stage), c0, sx, sy, b0);                     // board 0: columns 0..80
+              tma_load_4d_2cta(b_dst + 81 * 128, &mx.x7, full_bar(stage), c0, sx, sy, b0 + 1);        // board 1, row 0, x = 0..6: 81..87
+            } else {
+              tma_load_4d_2cta(b_dst, &mx.x2, full_bar(stage), c0, 7 + sx, sy, b0 + 1);               // row 0, x = 7..8: 88..89
+              tma_load_4d_2cta(b_dst + 2 * 128, &mx.rows8, full_bar(stage), c0, sx, 1 + sy, b0 + 1);  // rows 1..8: 90..161
+            }
+          } else if (crank == 0) {
             tma_load_4d_2cta(b_dst, &mx.full, full_bar(stage), c0, sx, sy, b0);                       // board 0: columns 0..80
             tma_load_4d_2cta(b_dst + 81 * 128, &mx.rows5, full_bar(stage), c0, sx, sy, b0 + 1);       // board 1 rows 0..4: 81..125
             tma_load_4d_2cta(b_dst + 126 * 128, &mx.x2, full_bar(stage), c0, sx, 5 + sy, b0 + 1);     // row 5, x = 0..1: 126..127
@@ -555,7 +590,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       const bool issuer = elect_one_sync();
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int t = t_first; t < num_tiles; t += t_step, ++it) {
+      for (PairSched ts(B, n_pairs); !ts.done(); ts.next(), ++it) {
+        const uint32_t idesc = ts.boards() == kBoards ? kIdescF16M256 : kIdescF16M256Narrow;
         const int buf = it & 1;
         const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(buf), tphase ^ 1u);  // both CTAs' epilogues have drained this accumulator
@@ -570,7 +606,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           if (issuer) {
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16_2cta(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdescF16M256, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_2cta(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit_2cta_mc(empty_bar(stage), (uint16_t)3);   // frees the stage in both CTAs when these MMAs retire
             if (kb == num_kb - 1) umma_commit_2cta_mc(tfull_bar(buf), (uint16_t)3);
           }
@@ -585,14 +621,15 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     const int g = (warp - 2) >> 2;        // epilogue group 0 / 1 = accumulator buffer
     SeTailRegs se_regs;
     if (kSeTail) se_tail_load(epi, (int)crank * kTileM + lane_grp * 32 + lane, lane_grp, lane, se_regs);
-    int it = g;
-    for (int t = t_first + g * t_step; t < num_tiles; t += 2 * t_step, it += 2) {
-      const int grp = t / n_pairs, ct = (t % n_pairs) * 2 + (int)crank;
+    int it = 0;
+    for (PairSched ts(B, n_pairs); !ts.done(); ts.next(), ++it) {
+      if ((it & 1) != g) continue;
+      const int ct = ts.cp * 2 + (int)crank;
       const int buf = g;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
       const int c = ct * kTileM + lane_grp * 32 + lane;
-      const int b0 = grp * kBoards;
-      const int nb_valid = min(kBoards, B - b0);
+      const int b0 = ts.b;
+      const int nb_valid = ts.boards();
       if (kSeTail) {
         // L2 prefetch of the whole residual tile of this warp (243 rows x 64 bytes = its 32 channels), 8 requests per
         // lane, issued BEFORE waiting for the tile's MMAs: when pass 2 asks for them the register prefetches find their
@@ -1142,10 +1179,11 @@ int kbk_conv3x3_tc_mode(const void* in, const void* w, void* out, int B, int Cin
     if (int r = make_act_box_map(&pm.x2, in, B, Cin, 2, 1, 1)) return r;
     if (int r = make_act_box_map(&pm.x7, in, B, Cin, 7, 1, 1)) return r;
     if (int r = make_act_box_map(&pm.rows3, in, B, Cin, 9, 3, 1)) return r;
+    if (int r = make_act_box_map(&pm.rows8, in, B, Cin, 9, 8, 1)) return r;
     const int groups = kb_ceil_div(B, kBoards);
-    const int tiles = groups * (Cout / 256);
     if (num_sms <= 0) num_sms = 148;
-    const int grid = 2 * (tiles < num_sms / 2 ? tiles : num_sms / 2);
+    // one contiguous board range per CTA pair (PairSched); with fewer boards than pairs every pair gets one board
+    const int grid = 2 * (B < num_sms / 2 ? B : num_sms / 2);
     bf16* o = (bf16*)out;
     if (epi.res != nullptr) {   // fused evaluation tail
       KB_CHECK_ARG(Cout == kSeC && epi.scale && epi.shift && epi.se_w1 && epi.se_b1 && epi.se_w2 && epi.se_b2 && epi.pool,
