@@ -145,6 +145,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   if (kCl) cluster_sync_all();  // peer barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer: the warp runs the loop uniformly, one elected lane issues =====
@@ -544,6 +546,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   cluster_sync_all();  // the peer's barriers are initialised before anything is signalled at them
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): the warp runs the loop uniformly, one elected lane issues =====
@@ -743,6 +747,8 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ WgMaps map_dy, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
 
   // single-issuer loops run warp-uniformly, one elected lane issues (see tc_ptx.cuh: elect_one_sync)
   if (warp == 0) {
@@ -886,6 +892,8 @@ conv3x3_wgrad_tc2_kernel(const __grid_constant__ WgMaps map_dy, const __grid_con
   cluster_sync_all();  // the peer's barriers are initialised before anything is signalled at them
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // TMA producer (both CTAs): data lands in the issuing CTA, the bytes are credited to the leader's full barrier
@@ -1037,10 +1045,11 @@ cudaError_t launch_prio(void (*kernel)(KArgs...), int grid, int block, size_t sm
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributePriority;
-  attr[0].val.priority = conv_priority();
-  cfg.attrs = attr; cfg.numAttrs = conv_priority() != 0 ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (conv_priority() != 0) { attr[n].id = cudaLaunchAttributePriority; attr[n].val.priority = conv_priority(); ++n; }
+  if (kb_pdl_enabled()) { attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+  cfg.attrs = attr; cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -1113,12 +1122,13 @@ int launch_pair(const CUtensorMap& mw, const PairMaps& mx, bf16* out, int B, int
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributePriority;
-  at[1].val.priority = conv_priority();
-  cfg.attrs = at; cfg.numAttrs = conv_priority() != 0 ? 2 : 1;
+  cudaLaunchAttribute at[3];
+  int n = 0;
+  at[n].id = cudaLaunchAttributeClusterDimension;
+  at[n].val.clusterDim.x = 2; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1; ++n;
+  if (conv_priority() != 0) { at[n].id = cudaLaunchAttributePriority; at[n].val.priority = conv_priority(); ++n; }
+  if (kb_pdl_enabled()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+  cfg.attrs = at; cfg.numAttrs = n;
   KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<F, kSeTail>, mw, mx, out, B, Cin, Cout, groups, epi));
   kb_count_launch();
   return KB_OK;
@@ -1292,12 +1302,13 @@ int kbk_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int Ci
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(units * slices)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kWg2SmemBytes; cfg.stream = st;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributePriority;
-    at[1].val.priority = conv_priority();
-    cfg.attrs = at; cfg.numAttrs = conv_priority() != 0 ? 2 : 1;
+    cudaLaunchAttribute at[3];
+    int n = 0;
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = 2; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1; ++n;
+    if (conv_priority() != 0) { at[n].id = cudaLaunchAttributePriority; at[n].val.priority = conv_priority(); ++n; }
+    if (kb_pdl_enabled()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+    cfg.attrs = at; cfg.numAttrs = n;
     KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv3x3_wgrad_tc2_kernel, mdy, mx, ws, B, Cin, bps));
     kb_count_launch();
   } else {

@@ -78,6 +78,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
 
   // single-issuer loops run warp-uniformly, one elected lane issues (see tc_ptx.cuh: elect_one_sync)
   if (warp == 0) {
@@ -295,7 +297,7 @@ int kbk_linear_tc(const void* x, long long M, int Kp, const void* w, int N, int 
     KB_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  linear_tc_kernel<<<grid_tiles < num_sms ? grid_tiles : num_sms, kThreads, kSmemBytes, st>>>(mw, mx, g, num_tiles);
+  KB_CUDA_CHECK(kb_launch_pdl(linear_tc_kernel, grid_tiles < num_sms ? grid_tiles : num_sms, kThreads, kSmemBytes, st, mw, mx, g, num_tiles));
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

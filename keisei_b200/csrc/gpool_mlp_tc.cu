@@ -79,6 +79,8 @@ gpool_mlp_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + kRows;   // D1: columns 0..127, D2: 128..383
 
   if (warp == 0) {
@@ -265,7 +267,7 @@ int kbk_gpool_mlp_tc(const void* x_bf16, int B, int K, const void* w1, const flo
     KB_CUDA_CHECK(cudaFuncSetAttribute(gpool_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  gpool_mlp_tc_kernel<<<num_tiles < num_sms ? num_tiles : num_sms, kThreads, kSmemBytes, st>>>(mw1, mx, mw2, g, num_tiles);
+  KB_CUDA_CHECK(kb_launch_pdl(gpool_mlp_tc_kernel, num_tiles < num_sms ? num_tiles : num_sms, kThreads, kSmemBytes, st, mw1, mx, mw2, g, num_tiles));
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

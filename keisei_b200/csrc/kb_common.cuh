@@ -145,4 +145,27 @@ __device__ __forceinline__ kb_philox4 kb_philox4x32_10(uint64_t seed, uint64_t c
 // representable in fp32 (with 24 bits the top value rounds to exactly 1.0 and -log(-log(u)) becomes +inf)
 __device__ __forceinline__ float kb_u32_to_unit(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
+
+// Programmatic dependent launch for the kernels that call tcptx::pdl_wait(): OFF by default, KB_PDL=1 switches it on.
+// Measured on the graph-replayed rollout (same box, alternating runs): 27.2-27.4 ms with, 26.8-27.1 ms without at 4096
+// boards; 5.9-6.6 vs 5.6-5.7 ms at 512 — the persistent one-CTA-per-SM kernels leave no room for a dependent grid's CTAs
+// until their own exit, and the early CTAs then sit in griddepcontrol.wait on SMs the tail of the previous grid shares.
+inline bool kb_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KB_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0;
+}
+// <<<grid, block, smem, stream>>> with the programmatic-serialization attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t kb_launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = kb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 #endif  // __CUDACC__

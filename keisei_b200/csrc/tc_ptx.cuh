@@ -86,6 +86,15 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// Programmatic dependent launch (launch attribute programmaticStreamSerialization on THIS kernel): the grid may start
+// while the previous kernel of the stream is still draining; everything before pdl_wait() (barrier init, TMEM allocation,
+// descriptor prefetch, cluster sync) overlaps that tail and the launch latency, pdl_wait() returns once the previous grid
+// has completed and its memory is visible. The trigger for OUR dependents is issued after the wait: when every CTA has
+// passed it the whole grid is resident, so a dependent grid can only take SMs this grid's CTAs have left (no starvation).
+// Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
