@@ -439,11 +439,15 @@ class KataGoPPOAlgorithm:
         `forward_model` in train mode."""
         device = next(self.model.parameters()).device
         model = self.forward_model
-        model.eval()
+        # the kernel path takes the mode as an argument: no eval() / train() walk over ~600 submodules per step (1.5 ms of
+        # Python with the GPU idle); every other path gets the reference's eval() ... train() bracket
+        fast = isinstance(model, SEResNetModel) and obs.is_cuda
+        if not fast:
+            model.eval()
         try:
             tok = self._events(device, "select_actions_forward_ms")
             # small batches replay a captured CUDA graph of the network (launch-bound otherwise)
-            output = model.rollout_forward(obs) if isinstance(model, SEResNetModel) else model(obs)
+            output = model.rollout_forward(obs, eval_mode=True) if isinstance(model, SEResNetModel) else model(obs)
             self._events_end(tok)
             B = obs.shape[0]
             if device.type == "cuda":
@@ -475,7 +479,8 @@ class KataGoPPOAlgorithm:
                 values = self.scalar_value(output.value_logits)
             return actions, log_probs, values
         finally:
-            self.forward_model.train()
+            if not fast or not self.forward_model.training:
+                self.forward_model.train()
 
     @torch.no_grad()
     def select_actions_many(self, batches, models=None, value_adapter: Any | None = None):
@@ -493,12 +498,9 @@ class KataGoPPOAlgorithm:
         grouped = device.type == "cuda" and all(isinstance(m, SEResNetModel) for m in models)
         if not grouped:
             return [self.select_actions(o, k, value_adapter) for o, k in batches]
-        was_training = [m.training for m in models]
-        for m in models:
-            m.eval()
         try:
             from .models import rollout_forward_many
-            outs = rollout_forward_many([(m, o) for m, (o, _) in zip(models, batches)])
+            outs = rollout_forward_many([(m, o) for m, (o, _) in zip(models, batches)], eval_mode=True)
             alpha = float(getattr(value_adapter, "score_blend_alpha", 0.0)) if value_adapter is not None else 0.0
             fused_value = value_adapter is None or hasattr(value_adapter, "score_blend_alpha")
             results, checks = [], []
@@ -519,9 +521,8 @@ class KataGoPPOAlgorithm:
                                            f"all-False legal mask would produce NaN")
             return results
         finally:
-            for m, t in zip(models, was_training):
-                m.train(t)
-            self.forward_model.train()
+            if not self.forward_model.training:
+                self.forward_model.train()
 
     # ---- advantages ------------------------------------------------------------------------------
     def _advantages(self, data, T: int, N: int, next_values: torch.Tensor, device: torch.device) -> torch.Tensor:

@@ -292,10 +292,12 @@ class PointerTables:
 
 @torch.no_grad()
 def seresnet_forward_raw(obs: torch.Tensor, tables: PointerTables, wpack: torch.Tensor, training: bool, dtype_code: int,
-                         use_tc: bool, bn_sync=None, out=None):
+                         use_tc: bool, bn_sync=None, out=None, num_sms: int | None = None):
     """The C call without the torch.library dispatcher (no-grad callers: rollout, the fused trainer step).
     Returns (policy_buf, value_logits, score_lead, workspace, new_stats). `out` = (policy_buf, value, score) row
-    slices of caller-owned buffers to write into (the two-stream rollout runs half batches side by side)."""
+    slices of caller-owned buffers to write into (the two-stream rollout runs half batches side by side).
+    `num_sms`: the SM budget the persistent kernels size their grids for (default: the whole device); the grouped
+    multi-model rollout gives every branch its share so that the branches are co-resident."""
     if not obs.is_cuda:
         raise _lib.KeiseiB200Error("keisei_b200 seresnet_forward needs CUDA tensors")
     d = tables.desc
@@ -321,7 +323,8 @@ def seresnet_forward_raw(obs: torch.Tensor, tables: PointerTables, wpack: torch.
         rc = _lib.load().kb_seresnet_forward_sync(
             ctypes.byref(d), tables.pt, tables.bt, new_stats.data_ptr() if training else None, wpack.data_ptr(),
             obs_c.data_ptr(), B, 1 if training else 0, dtype_code, ws.data_ptr(), ws.numel(), policy.data_ptr(),
-            POLICY_PITCH, value.data_ptr(), score.data_ptr(), 1 if use_tc else 0, sm_count(dev), hook_ptr, hook_user, world,
+            POLICY_PITCH, value.data_ptr(), score.data_ptr(), 1 if use_tc else 0,
+            sm_count(dev) if num_sms is None else max(2, min(int(num_sms), sm_count(dev))), hook_ptr, hook_user, world,
             _lib.stream_ptr(dev))
     if hook is not None:
         hook.check()

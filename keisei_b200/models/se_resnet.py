@@ -299,7 +299,17 @@ class SEResNetModel(KataGoBaseModel):
 
     # ---- CUDA-graph replay for small rollout batches ---------------------------------------------
     @torch.no_grad()
-    def rollout_forward(self, obs: torch.Tensor) -> KataGoOutput:
+    def _eval_forward_impl(self, obs: torch.Tensor) -> KataGoOutput:
+        """`_forward_impl` in evaluation mode whatever the module's current mode (restored afterwards)."""
+        if not self.training:
+            return self._forward_impl(obs)
+        self.eval()
+        try:
+            return self._forward_impl(obs)
+        finally:
+            self.train()
+
+    def rollout_forward(self, obs: torch.Tensor, eval_mode: bool = False) -> KataGoOutput:
         """Eval-mode no-grad forward for action selection (reference katago_ppo.py:575-580 / katago_loop.py:337-344,
         404-406: per-step inference on 64..512 boards, several sub-batches per step in league play).
 
@@ -309,10 +319,14 @@ class SEResNetModel(KataGoBaseModel):
         varying sub-batch sizes share a few graphs; a bucket is captured the second time it is seen. The returned
         tensors are views of the graph's static output buffers — owned by the calling thread, valid until its next
         `rollout_forward` in the same bucket (`select_actions` consumes them immediately). Larger batches, CPU tensors
-        and training mode go through the ordinary `forward`."""
-        if (self.training or not obs.is_cuda or obs.shape[0] > self.graph_max_batch or not self.kernel_supported()
+        and training mode go through the ordinary `forward`.
+
+        `eval_mode=True`: evaluate in inference mode WITHOUT touching the module's `training` flags — the kernels take the
+        mode as an argument, and `model.eval()` + `model.train()` walk ~600 submodules in Python (0.72 + 0.76 ms measured,
+        with the GPU idle: a quarter of a 512-board step). `select_actions` uses it."""
+        if ((self.training and not eval_mode) or not obs.is_cuda or obs.shape[0] > self.graph_max_batch or not self.kernel_supported()
                 or obs.ndim != 4 or tuple(obs.shape[1:]) != (self.params.obs_channels, 9, 9) or obs.shape[0] < 1):
-            return self._forward_impl(obs)
+            return self._eval_forward_impl(obs) if eval_mode else self._forward_impl(obs)
         tables = self._ptr_tables()
         dtype = self._act_dtype(obs.device)
         code = 0 if dtype == torch.float32 else 1
@@ -326,7 +340,7 @@ class SEResNetModel(KataGoBaseModel):
             ent = None
         if ent is None:
             if not self._graphs.should_capture(key):
-                return self._forward_impl(obs)
+                return self._eval_forward_impl(obs) if eval_mode else self._forward_impl(obs)
             static_obs = torch.zeros((Bb, self.params.obs_channels, 9, 9), dtype=torch.float32, device=obs.device)
             static_obs[:B].copy_(obs)
             with _capture_lock:
@@ -353,12 +367,12 @@ class SEResNetModel(KataGoBaseModel):
         policy = policy_buf[:, :model_ops.POLICY_A].view(B, 9, 9, self.SPATIAL_MOVE_TYPES)
         return KataGoOutput(policy_logits=policy, value_logits=value, score_lead=score)
 
-    def _captured_forward(self, obs: torch.Tensor, tables, wpack: torch.Tensor, code: int):
+    def _captured_forward(self, obs: torch.Tensor, tables, wpack: torch.Tensor, code: int, num_sms: int | None = None):
         """Body of the rollout graph: one C call, or two half-batch calls on two branches of the capture."""
         B = obs.shape[0]
         use_tc = bool(self.use_tensor_cores)
-        if self.rollout_split_min <= 0 or B < self.rollout_split_min:
-            return model_ops.seresnet_forward_raw(obs, tables, wpack, False, code, use_tc)
+        if num_sms is not None or self.rollout_split_min <= 0 or B < self.rollout_split_min:
+            return model_ops.seresnet_forward_raw(obs, tables, wpack, False, code, use_tc, num_sms=num_sms)
         # split on 3-board tile boundaries; every part but the last gets a whole number of conv rounds (74 board groups x
         # 2 channel halves = one CTA per SM), so only the last part pays a partial round
         groups = (B + 2) // 3
@@ -433,7 +447,25 @@ class SEResNetModel(KataGoBaseModel):
 
 # ---- grouped rollout: several (model, sub-batch) pairs as parallel branches of ONE CUDA graph -------------------------
 @torch.no_grad()
-def rollout_forward_many(pairs: "list[tuple[SEResNetModel, torch.Tensor]]") -> "list[KataGoOutput]":
+def _sm_shares(batches: "list[int]", sms: int) -> "list[int]":
+    """SM budget of every branch of a grouped rollout graph, proportional to its boards, in whole CTA pairs (>= 1 pair each).
+    The convolutions are persistent one-CTA-per-SM kernels: sized for the whole device, the branches of a graph would take
+    turns; sized for their share they run side by side, each CTA pair with about as many boards as if the sub-batches had
+    been one batch."""
+    pairs_total = max(len(batches), int(sms // 2 * float(os.environ.get("KB_GROUP_SM_FRACTION", "1.0"))))
+    total = max(1, sum(batches))
+    shares = [max(1, (pairs_total * b) // total) for b in batches]
+    spare = pairs_total - sum(shares)
+    order = sorted(range(len(batches)), key=lambda i: -(batches[i] / shares[i]))   # most boards per pair first
+    k = 0
+    while spare > 0 and order:
+        shares[order[k % len(order)]] += 1
+        spare -= 1
+        k += 1
+    return [2 * s for s in shares]
+
+
+def rollout_forward_many(pairs: "list[tuple[SEResNetModel, torch.Tensor]]", eval_mode: bool = False) -> "list[KataGoOutput]":
     """Eval-mode forward of several independent (model, observations) pairs — the learner and its K league opponents
     on their sub-batches (reference katago_loop.py:284-431 `split_merge_step`, match_utils.py:124-293 `play_batch`: one
     sequential forward per model per step, 64..256 boards each). At these sizes a forward is a chain of ~290 kernels of
@@ -444,14 +476,15 @@ def rollout_forward_many(pairs: "list[tuple[SEResNetModel, torch.Tensor]]") -> "
     first falls back to one `rollout_forward` per pair). Results are bit-identical to `model.rollout_forward(obs)` per
     pair. Returned tensors are views of static buffers owned by the calling thread (valid until its next call with the
     same bucket signature). The cache lives on the first model of the group. Falls back to one `rollout_forward` per
-    pair for CPU tensors, training-mode models or unsupported shapes."""
+    pair for CPU tensors, training-mode models or unsupported shapes. `eval_mode=True`: inference whatever the modules'
+    `training` flags say, without toggling them (see `rollout_forward`)."""
     if not pairs:
         return []
-    ok = all(isinstance(m, SEResNetModel) and not m.training and o.is_cuda and m.kernel_supported() and o.ndim == 4
+    ok = all(isinstance(m, SEResNetModel) and (eval_mode or not m.training) and o.is_cuda and m.kernel_supported() and o.ndim == 4
              and tuple(o.shape[1:]) == (m.params.obs_channels, 9, 9) and 0 < o.shape[0] <= max(m.graph_max_batch, 0)
              for m, o in pairs) and len({o.device for _, o in pairs}) == 1
     if not ok or len(pairs) == 1:
-        return [m.rollout_forward(o) for m, o in pairs]
+        return [m.rollout_forward(o, eval_mode) if isinstance(m, SEResNetModel) else m.rollout_forward(o) for m, o in pairs]
     dev = pairs[0][1].device
     prep = []
     for m, o in pairs:
@@ -466,7 +499,7 @@ def rollout_forward_many(pairs: "list[tuple[SEResNetModel, torch.Tensor]]") -> "
     ent = cache.lookup(key)
     if ent is None:
         if not cache.should_capture(key):
-            return [m.rollout_forward(o) for m, o in pairs]
+            return [m.rollout_forward(o, eval_mode) for m, o in pairs]
         statics = []
         for _, o, *_rest in prep:
             so = torch.zeros((rollout_bucket(o.shape[0]),) + tuple(o.shape[1:]), dtype=torch.float32, device=dev)
@@ -489,12 +522,13 @@ def rollout_forward_many(pairs: "list[tuple[SEResNetModel, torch.Tensor]]") -> "
                 branches = [torch.cuda.Stream(dev) for _ in prep[1:]]
                 for br in branches:
                     br.wait_stream(cap)
+                shares = _sm_shares([so.shape[0] for so in statics], model_ops.sm_count(dev))
                 for i, ((m, _, tables, wpack, code), so) in enumerate(zip(prep, statics)):
                     if i == 0:
-                        outs.append(m._captured_forward(so, tables, wpack, code))
+                        outs.append(m._captured_forward(so, tables, wpack, code, num_sms=shares[i]))
                     else:
                         with torch.cuda.stream(branches[i - 1]):
-                            outs.append(m._captured_forward(so, tables, wpack, code))
+                            outs.append(m._captured_forward(so, tables, wpack, code, num_sms=shares[i]))
                 for br in branches:
                     cap.wait_stream(br)
             n_kernels = model_ops._lib.launch_count() - n0
