@@ -552,11 +552,19 @@ def bench_update(args, algo, model, device, rank, world) -> tuple[dict, dict]:
         # timed both ways: NCCL all-reduce per layer, and this library's one-kernel exchange over NVLink peer memory.
         from keisei_b200.distributed import PeerBatchNormSync
         gs = algo.grad_sync
-        algo.grad_sync = None
-        ms_no_ar = timed(step, steps, warm, device, world)          # no gradient exchange at all (weights diverge: timing only)
-        algo.grad_sync = gs
+        # step without any gradient exchange (weights diverge: timing only) against the step with the overlapped bucketed
+        # exchange, INTERLEAVED (A B A B): the two legs differ by ~1 ms on a power-capped chip whose step time drifts by
+        # more than that between legs timed minutes apart (tools/exp_allreduce_overlap.py)
+        t_no, t_gs = [], []
+        for rnd in range(2):
+            algo.grad_sync = None
+            t_no.append(timed(step, steps, warm if rnd == 0 else 1, device, world))
+            algo.grad_sync = gs
+            if rnd == 0:
+                gs.broadcast_parameters(model)
+            t_gs.append(timed(step, steps, 1, device, world))
+        ms_no_ar, ms_local_bn = sum(t_no) / len(t_no), sum(t_gs) / len(t_gs)
         gs.broadcast_parameters(model)
-        ms_local_bn = timed(step, steps, warm, device, world)
         flat = torch.zeros(sum(p.numel() for p in model.parameters()), device=device)
         allreduce_ms = timed(lambda: dist.all_reduce(flat), 10, 3, device, world)   # the 213.7 MB flat gradient, alone
         del flat
