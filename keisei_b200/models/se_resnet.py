@@ -340,7 +340,11 @@ class SEResNetModel(KataGoBaseModel):
             ent = None
         if ent is None:
             if not self._graphs.should_capture(key):
-                return self._eval_forward_impl(obs) if eval_mode else self._forward_impl(obs)
+                # first sighting of this bucket: the same C call the graph would replay, launched directly
+                policy_buf, value, score, _ws, _ = self._captured_forward(obs, tables, wpack, code)
+                self.last_policy_buffer = policy_buf
+                policy = policy_buf[:, :model_ops.POLICY_A].view(B, 9, 9, self.SPATIAL_MOVE_TYPES)
+                return KataGoOutput(policy_logits=policy, value_logits=value, score_lead=score)
             static_obs = torch.zeros((Bb, self.params.obs_channels, 9, 9), dtype=torch.float32, device=obs.device)
             static_obs[:B].copy_(obs)
             with _capture_lock:

@@ -188,3 +188,42 @@ def test_graph_buffers_are_per_thread():
     assert torch.equal(other["out"], want_b)
     assert torch.equal(mine.value_logits, want_a)        # untouched by the other thread's replay
     assert len(m._graphs) == 2
+
+
+def test_select_actions_never_flips_the_training_flags_on_the_kernel_path(monkeypatch):
+    """`select_actions` evaluates in inference mode by passing the mode to the kernels (`rollout_forward(eval_mode=True)`),
+    not by walking the module tree twice per step; the model is in train mode afterwards like in the reference
+    (katago_ppo.py:575-617), and the result is what an eval-mode forward gives — also for the grouped league step."""
+    torch.manual_seed(3)
+    m = SEResNetModel(SEResNetParams(**CFG)).to(DEV)
+    algo = KataGoPPOAlgorithm(KataGoPPOParams(use_amp=True), m)
+    A = 11259
+    obs = torch.randn(12, 50, 9, 9, device=DEV)
+    mask = torch.rand(12, A, device=DEV) < 0.01
+    mask[:, 5] = True
+    m.eval()
+    with torch.no_grad():
+        want = m.rollout_forward(obs).policy_logits.clone()
+    m.train()
+    calls = {"eval": 0, "train": 0}
+    real_eval, real_train = m.eval, m.train
+    monkeypatch.setattr(m, "eval", lambda: (calls.__setitem__("eval", calls["eval"] + 1), real_eval())[1])
+    monkeypatch.setattr(m, "train", lambda mode=True: (calls.__setitem__("train", calls["train"] + 1), real_train(mode))[1])
+    for _ in range(3):   # plain launch, capture, replay
+        a, lp, v = algo.select_actions(obs, mask)
+        assert m.training and mask[torch.arange(12, device=DEV), a].all()
+        assert torch.equal(m.last_policy_buffer[:, :A].reshape(want.shape), want)
+    res = algo.select_actions_many([(obs[:8], mask[:8]), (obs[8:], mask[8:])])
+    assert m.training and len(res) == 2
+    assert calls == {"eval": 0, "train": 0}
+    # a model that was left in eval mode comes back in train mode (the reference's `finally: train()`)
+    real_eval()                                   # (Module.eval() is train(False): counted by the patched train)
+    calls["train"] = 0
+    algo.select_actions(obs, mask)
+    assert m.training and calls["eval"] == 0 and calls["train"] == 1
+    # training-mode `rollout_forward` without eval_mode is still the ordinary training forward (batch statistics)
+    monkeypatch.undo()
+    m.train()
+    with torch.no_grad():
+        tr = m.rollout_forward(obs).policy_logits
+    assert not torch.equal(tr, want)

@@ -249,3 +249,17 @@ def test_model_deepcopy_pickle_and_weight_cache_invalidation():
     m._wpack_key = ("stale",)
     m.invalidate_packed_weights()
     assert m._wpack_key is None
+
+
+def test_sm_shares_of_a_grouped_rollout_graph():
+    """Every branch of the grouped league graph gets whole CTA pairs in proportion to its boards, at least one pair, and
+    together they use the device once (keisei_b200/models/se_resnet.py: _sm_shares)."""
+    from keisei_b200.models.se_resnet import _sm_shares
+    assert _sm_shares([512], 148) == [148]
+    sh = _sm_shares([256, 64, 64, 64, 64], 148)
+    assert sum(sh) == 148 and all(x % 2 == 0 and x >= 2 for x in sh) and sh[0] == 74 and max(sh[1:]) - min(sh[1:]) <= 2
+    assert _sm_shares([64, 64], 148) == [74, 74]
+    sh = _sm_shares([3000, 8, 8], 148)
+    assert sum(sh) <= 150 and sh[1] == sh[2] == 2
+    sh = _sm_shares([8] * 100, 148)           # more branches than CTA pairs: one pair each, the graph serialises the rest
+    assert sh == [2] * 100
