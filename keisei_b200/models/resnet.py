@@ -135,7 +135,20 @@ class ResNetModel(BaseModel):
         torch._foreach_copy_(dst, src)
         torch._foreach_add_(nbt, 1)
 
-    def _forward_cuda(self, obs: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    def eval_forward(self, obs: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """Inference-mode forward on CUDA whatever the modules' `training` flags say, without flipping them (the kernels
+        take the mode as an argument; `model.eval()` ... `model.train()` per rollout step is pure Python overhead).
+        Anything the kernels do not cover gets the ordinary eval() ... train() bracket."""
+        if obs.is_cuda and obs.ndim == 4 and self.kernel_supported():
+            return self._forward_cuda(obs, training=False)
+        was = self.training
+        self.eval()
+        try:
+            return self.forward(obs)
+        finally:
+            self.train(was)
+
+    def _forward_cuda(self, obs: torch.Tensor, training: bool | None = None) -> tuple[torch.Tensor, torch.Tensor]:
         if not self.kernel_supported():
             raise KeiseiB200Error(f"ResNetParams {self.params} not supported by the CUDA kernels "
                                   "(hidden_size must be a multiple of 4, <= 1024)")
@@ -143,7 +156,7 @@ class ResNetModel(BaseModel):
         params, buffers = tables.params, tables.buffers
         dtype = self._act_dtype(obs.device)
         code = 0 if dtype == torch.float32 else 1
-        training = self.training
+        training = self.training if training is None else training
         wpack = self._packed(params, buffers, dtype)
         if torch.is_grad_enabled() and training:
             policy_buf, value, _ws, new_stats = resnet_ops.resnet_forward(

@@ -60,11 +60,13 @@ class PPOAlgorithm(KataGoPPOAlgorithm):
         scalar value = value.squeeze(-1) (value_adapter.py:46-47). Leaves the model in train mode."""
         device = next(self.model.parameters()).device
         model = self.forward_model
-        model.eval()
+        fast = isinstance(model, ResNetModel) and obs.is_cuda   # mode passed to the kernels: no eval() / train() walks
+        if not fast:
+            model.eval()
         try:
             tok = self._events(device, "select_actions_forward_ms")
             with autocast(device_type=device.type, dtype=torch.bfloat16, enabled=self.params.use_amp):
-                logits, value = model(obs)
+                logits, value = model.eval_forward(obs) if fast else model(obs)
             self._events_end(tok)
             values = self._scalar_adapter.scalar_value_from_output(value).float()
             if device.type == "cuda":
@@ -84,7 +86,8 @@ class PPOAlgorithm(KataGoPPOAlgorithm):
             actions = dist.sample()
             return actions, dist.log_prob(actions), values
         finally:
-            self.forward_model.train()
+            if not fast or not self.forward_model.training:
+                self.forward_model.train()
 
     # ---- one optimisation step -----------------------------------------------------------------------
     def _losses(self, flat_logits, value, _score, mb, value_adapter):
