@@ -134,11 +134,16 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& g, int k_per_slice, in
     else *reinterpret_cast<float4*>(&Bs[b_r][b_c]) = v;
   };
 
+  // register prefetch TWO K steps ahead: these problems are small (a few tiles, 8-64 K steps), so a CTA's time is the
+  // chain of its K steps and each step exposes one global-load latency divided by the prefetch depth
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 ra = load_a(k_begin), rb = load_b(k_begin);
+  float4 ra1 = k_begin + BK < k_end ? load_a(k_begin + BK) : zero4, rb1 = k_begin + BK < k_end ? load_b(k_begin + BK) : zero4;
   for (int k0 = k_begin; k0 < k_end; k0 += BK) {
     store_a(ra); store_b(rb);
     __syncthreads();
-    if (k0 + BK < k_end) { ra = load_a(k0 + BK); rb = load_b(k0 + BK); }  // prefetch while computing
+    ra = ra1; rb = rb1;
+    if (k0 + 2 * BK < k_end) { ra1 = load_a(k0 + 2 * BK); rb1 = load_b(k0 + 2 * BK); }
     if constexpr (TF32) {
       // warp (wm, wn) of a 4 x 2 grid owns rows 16*wm..+15 and columns 32*wn..+31 (four m16n8 tiles)
       const int lane = tid & 31, wid = tid >> 5, wm = wid & 3, wn = wid >> 2, gq = lane >> 2, tq = lane & 3;
