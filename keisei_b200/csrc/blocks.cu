@@ -850,6 +850,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_vec_kernel(T* __restrict__ d
 // =================================================================================================
 constexpr int kColPix = 3;
 inline bool col_ok(int C) { return C % kVW == 0 && C / kVW <= 256 && 256 % (C / kVW) == 0; }
+// Small launches (at most two CTAs per SM: up to ~1200 boards at 256 channels — the reference's 256-sample minibatches, the
+// per-GPU share of an 8-GPU update) are latency-bound: a thread walks its 81 pixels in 27 dependent round trips of 3
+// pixels (21-26 us whatever the batch). They run the 9-pixel instantiation: 9 round trips, one CTA per SM's worth of
+// registers, which is all such a launch can use anyway.
+inline bool col_small(int B, int C) { return kb_ceil_div(B, 256 / (C / kVW)) <= 2 * 148; }
 inline int col_grid(int B, int C) {
   const int bpc = 256 / (C / kVW);
   const int want = kb_ceil_div(B, bpc);
@@ -862,8 +867,8 @@ __device__ __forceinline__ void stf4(float* p, const float (&v)[kVW]) {
 }
 
 // pass B: dz2 = k1 * (du * sigmoid(scale) + dse_in / 81) - k2 * z2 - k3     (du already masked by the block's ReLU)
-template <typename T>
-__global__ void __launch_bounds__(256, 3) block_bwd_dz2_col_kernel(PassBArgs g) {
+template <typename T, int kColPix>
+__global__ void __launch_bounds__(256, kColPix == 3 ? 3 : 1) block_bwd_dz2_col_kernel(PassBArgs g) {
   const int C = g.C, TPB = C / kVW, BPC = 256 / TPB;
   const int slot = threadIdx.x / TPB, c0 = (threadIdx.x % TPB) * kVW;
   float k1[kVW], k2[kVW], k3[kVW];
@@ -894,8 +899,8 @@ __global__ void __launch_bounds__(256, 3) block_bwd_dz2_col_kernel(PassBArgs g) 
 
 // pass D, in-tower configuration (see PassDArgs): dx = [x > 0] * (dxc + du' + pool backward), plus the board sums
 // of dx and dx * z_next for the producing block.
-template <typename T, bool ZN>
-__global__ void __launch_bounds__(256, 3) block_bwd_dx_col_kernel(PassDArgs g) {
+template <typename T, bool ZN, int kColPix>
+__global__ void __launch_bounds__(256, kColPix == 3 ? 3 : 1) block_bwd_dx_col_kernel(PassDArgs g) {
   const int C = g.C, TPB = C / kVW, BPC = 256 / TPB;
   const int slot = threadIdx.x / TPB, c0 = (threadIdx.x % TPB) * kVW;
   for (int b = blockIdx.x * BPC + slot; b < g.B; b += gridDim.x * BPC) {
@@ -950,8 +955,8 @@ __global__ void __launch_bounds__(256, 3) block_bwd_dx_col_kernel(PassDArgs g) {
 
 // mask_bwd_stats, column form: d <- d * [z*ma + mb > 0] in place; board_sum[b][c] = sum_p d (unmasked);
 // sums += per-channel sums of the masked gradient and of masked gradient * z (double atomics, once per CTA).
-template <typename T>
-__global__ void __launch_bounds__(256, 3) mask_bwd_stats_col_kernel(T* d, const T* __restrict__ z, int B, int C,
+template <typename T, int kColPix>
+__global__ void __launch_bounds__(256, kColPix == 3 ? 3 : 1) mask_bwd_stats_col_kernel(T* d, const T* __restrict__ z, int B, int C,
                                                                  const float* __restrict__ ma, const float* __restrict__ mb,
                                                                  float* __restrict__ board_sum, double* sums) {
   __shared__ float red[2][256 * kVW];
@@ -1263,8 +1268,10 @@ int kbk_block_bwd_dz2(const PassBArgs& a, cudaStream_t st) {
   static int col = -1;
   if (col < 0) { const char* e = getenv("KB_COL_KERNELS"); col = (e && e[0] == '0') ? 0 : 1; }
   if (col && col_ok(a.C) && a.xp == nullptr) {
-    if (a.dtype == KB_F32) { block_bwd_dz2_col_kernel<float><<<col_grid(a.B, a.C), 256, 0, st>>>(a); }
-    else { block_bwd_dz2_col_kernel<bf16><<<col_grid(a.B, a.C), 256, 0, st>>>(a); }
+    const bool small = col_small(a.B, a.C);
+    if (a.dtype == KB_F32) { block_bwd_dz2_col_kernel<float, 3><<<col_grid(a.B, a.C), 256, 0, st>>>(a); }
+    else if (small) { block_bwd_dz2_col_kernel<bf16, 9><<<col_grid(a.B, a.C), 256, 0, st>>>(a); }
+    else { block_bwd_dz2_col_kernel<bf16, 3><<<col_grid(a.B, a.C), 256, 0, st>>>(a); }
     KB_CUDA_LAUNCH_CHECK();
     return KB_OK;
   }
@@ -1314,12 +1321,15 @@ int kbk_block_bwd_dx(const PassDArgs& a, cudaStream_t st) {
   if (col < 0) { const char* e = getenv("KB_COL_KERNELS"); col = (e && e[0] == '0') ? 0 : 1; }
   if (col && col_ok(a.C) && a.dxc && a.dxp && !a.xp && a.dpool && a.ties && a.mask_out) {
     const int grid = col_grid(a.B, a.C);
+    const bool small = col_small(a.B, a.C);
     if (a.z_next) {
-      if (a.dtype == KB_F32) { block_bwd_dx_col_kernel<float, true><<<grid, 256, 0, st>>>(a); }
-      else { block_bwd_dx_col_kernel<bf16, true><<<grid, 256, 0, st>>>(a); }
+      if (a.dtype == KB_F32) { block_bwd_dx_col_kernel<float, true, 3><<<grid, 256, 0, st>>>(a); }
+      else if (small) { block_bwd_dx_col_kernel<bf16, true, 9><<<grid, 256, 0, st>>>(a); }
+      else { block_bwd_dx_col_kernel<bf16, true, 3><<<grid, 256, 0, st>>>(a); }
     } else {
-      if (a.dtype == KB_F32) { block_bwd_dx_col_kernel<float, false><<<grid, 256, 0, st>>>(a); }
-      else { block_bwd_dx_col_kernel<bf16, false><<<grid, 256, 0, st>>>(a); }
+      if (a.dtype == KB_F32) { block_bwd_dx_col_kernel<float, false, 3><<<grid, 256, 0, st>>>(a); }
+      else if (small) { block_bwd_dx_col_kernel<bf16, false, 9><<<grid, 256, 0, st>>>(a); }
+      else { block_bwd_dx_col_kernel<bf16, false, 3><<<grid, 256, 0, st>>>(a); }
     }
     KB_CUDA_LAUNCH_CHECK();
     return KB_OK;
@@ -1389,8 +1399,9 @@ int kbk_mask_bwd_stats(void* d_inout, const void* z, const float* ma, const floa
   if (col < 0) { const char* e = getenv("KB_COL_KERNELS"); col = (e && e[0] == '0') ? 0 : 1; }
   if (col && col_ok(C)) {
     const int grid = col_grid(B, C);
-    if (dtype == KB_F32) { mask_bwd_stats_col_kernel<float><<<grid, 256, 0, st>>>((float*)d_inout, (const float*)z, B, C, ma, mb, board_sum, sums); }
-    else { mask_bwd_stats_col_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)d_inout, (const bf16*)z, B, C, ma, mb, board_sum, sums); }
+    if (dtype == KB_F32) { mask_bwd_stats_col_kernel<float, 3><<<grid, 256, 0, st>>>((float*)d_inout, (const float*)z, B, C, ma, mb, board_sum, sums); }
+    else if (col_small(B, C)) { mask_bwd_stats_col_kernel<bf16, 9><<<grid, 256, 0, st>>>((bf16*)d_inout, (const bf16*)z, B, C, ma, mb, board_sum, sums); }
+    else { mask_bwd_stats_col_kernel<bf16, 3><<<grid, 256, 0, st>>>((bf16*)d_inout, (const bf16*)z, B, C, ma, mb, board_sum, sums); }
     KB_CUDA_LAUNCH_CHECK();
     return KB_OK;
   }

@@ -98,8 +98,8 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 constexpr int kPix = 3;  // 81 = 27 x 3
 
-template <bool TIES>
-__global__ void __launch_bounds__(256, 3) se_apply_col_kernel(SeApplyArgs g) {
+template <bool TIES, int kPix>
+__global__ void __launch_bounds__(256, kPix == 3 ? 3 : 1) se_apply_col_kernel(SeApplyArgs g) {
   const int C = g.C, TPB = C / 4, BPC = 256 / TPB;
   const int slot = threadIdx.x / TPB, c0 = (threadIdx.x % TPB) * 4;
   float a_[4] = {1.f, 1.f, 1.f, 1.f}, b_[4] = {0.f, 0.f, 0.f, 0.f};
@@ -236,8 +236,10 @@ int kbk_se_apply_col(const SeApplyArgs& a, int num_sms, cudaStream_t st) {
   const int bpc = 256 / (a.C / 4);
   int grid = kb_ceil_div(a.B, bpc);
   if (grid > num_sms * 8) grid = num_sms * 8;
-  if (a.ties) se_apply_col_kernel<true><<<grid, 256, 0, st>>>(a);
-  else { kb_prefer_max_smem_carveout(se_apply_col_kernel<false>); se_apply_col_kernel<false><<<grid, 256, 0, st>>>(a); }
+  // small launches are latency-bound on the 27 dependent 3-pixel round trips of a thread: 9 pixels per trip (blocks.cu: col_small)
+  const bool small = kb_ceil_div(a.B, bpc) <= 2 * num_sms;
+  if (a.ties) { if (small) se_apply_col_kernel<true, 9><<<grid, 256, 0, st>>>(a); else se_apply_col_kernel<true, 3><<<grid, 256, 0, st>>>(a); }
+  else { kb_prefer_max_smem_carveout(se_apply_col_kernel<false, 3>); se_apply_col_kernel<false, 3><<<grid, 256, 0, st>>>(a); }
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }
