@@ -955,7 +955,9 @@ __global__ void __launch_bounds__(256, kColPix == 3 ? 3 : 1) block_bwd_dx_col_ke
 
 // mask_bwd_stats, column form: d <- d * [z*ma + mb > 0] in place; board_sum[b][c] = sum_p d (unmasked);
 // sums += per-channel sums of the masked gradient and of masked gradient * z (double atomics, once per CTA).
-template <typename T, int kColPix>
+// kStore = false: the masked gradient is not written back (two tensor passes instead of three); the consumer,
+// bn_bwd_apply_flat_kernel<T, true>, recomputes the same mask from z.
+template <typename T, int kColPix, bool kStore = true>
 __global__ void __launch_bounds__(256, kColPix == 3 ? 3 : 1) mask_bwd_stats_col_kernel(T* d, const T* __restrict__ z, int B, int C,
                                                                  const float* __restrict__ ma, const float* __restrict__ mb,
                                                                  float* __restrict__ board_sum, double* sums) {
@@ -986,7 +988,7 @@ __global__ void __launch_bounds__(256, kColPix == 3 ? 3 : 1) mask_bwd_stats_col_
           s0[i] += dd[j][i];
           dd[j][i] = fmaf(zz[j][i], fa[i], fb[i]) > 0.f ? dd[j][i] : 0.f;
         }
-        V8<T>::store(d + base + (size_t)(p + j) * C, dd[j]);
+        if (kStore) V8<T>::store(d + base + (size_t)(p + j) * C, dd[j]);
         V8<T>::round(dd[j]);
 #pragma unroll
         for (int i = 0; i < kVW; ++i) { s1[i] += dd[j][i]; s2[i] = fmaf(dd[j][i], zz[j][i], s2[i]); }
@@ -1045,17 +1047,21 @@ __global__ void __launch_bounds__(256, 4) apply_flat_kernel(ApplyArgs g, unsigne
 
 // dz = k1[c]*dzh - k2[c]*z - k3[c] in place, flat (same shape as apply_flat_kernel: coefficients in registers, four
 // branch-free vector pairs in flight per thread, consecutive CTAs on consecutive 2 KB segments).
-template <typename T>
+// kMask: d holds the UNMASKED gradient of relu(z*ma + mb); the ReLU mask is recomputed here from z (same expression as
+// mask_bwd_stats_col_kernel, which then does not have to write the masked tensor back).
+template <typename T, bool kMask = false>
 __global__ void __launch_bounds__(256, 4) bn_bwd_apply_flat_kernel(T* d, const T* __restrict__ z, const float* __restrict__ k1,
                                                                   const float* __restrict__ k2, const float* __restrict__ k3,
-                                                                  unsigned rows, int C) {
+                                                                  unsigned rows, int C, const float* __restrict__ ma = nullptr,
+                                                                  const float* __restrict__ mb = nullptr) {
   constexpr int U = 4;
   const int cpv = C / kVW;
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned rs = (gridDim.x * blockDim.x) / cpv;
   const int c0 = (int)(tid % cpv) * kVW;
-  float a[kVW], b[kVW], e[kVW];
+  float a[kVW], b[kVW], e[kVW], fa[kVW], fb[kVW];
   ldf8(k1 + c0, a); ldf8(k2 + c0, b); ldf8(k3 + c0, e);
+  if (kMask) { ldf8(ma + c0, fa); ldf8(mb + c0, fb); }
   for (unsigned row = tid / cpv; row < rows; row += U * rs) {
     float v[U][kVW], zz[U][kVW];
 #pragma unroll
@@ -1069,7 +1075,10 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_flat_kernel(T* d, const T
       const unsigned ru = row + u * rs;
       if (ru < rows) {
 #pragma unroll
-        for (int j = 0; j < kVW; ++j) v[u][j] = a[j] * v[u][j] - b[j] * zz[u][j] - e[j];
+        for (int j = 0; j < kVW; ++j) {
+          const float dv = (!kMask || fmaf(zz[u][j], fa[j], fb[j]) > 0.f) ? v[u][j] : 0.f;
+          v[u][j] = a[j] * dv - b[j] * zz[u][j] - e[j];
+        }
         V8<T>::store(d + (size_t)ru * C + c0, v[u]);
       }
     }
@@ -1315,6 +1324,21 @@ int kbk_bn_bwd_apply(void* d, const void* z, const float* k1, const float* k2, c
   return KB_OK;
 }
 
+// dz = k1 * (d * [z*ma + mb > 0]) - k2*z - k3 in place: BatchNorm backward of relu(bn(z)) with the ReLU mask recomputed from z
+int kbk_bn_bwd_apply_masked_supported(long long rows, int C) { return col_ok(C) && rows < (1LL << 31) ? 1 : 0; }
+
+int kbk_bn_bwd_apply_masked(void* d, const void* z, const float* k1, const float* k2, const float* k3, const float* ma,
+                            const float* mb, long long rows, int C, int dtype, cudaStream_t st) {
+  KB_CHECK_ARG(kbk_bn_bwd_apply_masked_supported(rows, C), "bn_bwd_apply_masked: unsupported shape");
+  KB_CHECK_ARG(ma != nullptr && mb != nullptr, "bn_bwd_apply_masked: mask coefficients missing");
+  if (rows == 0) return KB_OK;
+  const int grid = flat_grid(rows, C / kVW);
+  if (dtype == KB_F32) { bn_bwd_apply_flat_kernel<float, true><<<grid, 256, 0, st>>>((float*)d, (const float*)z, k1, k2, k3, (unsigned)rows, C, ma, mb); }
+  else { bn_bwd_apply_flat_kernel<bf16, true><<<grid, 256, 0, st>>>((bf16*)d, (const bf16*)z, k1, k2, k3, (unsigned)rows, C, ma, mb); }
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
 int kbk_block_bwd_dx(const PassDArgs& a, cudaStream_t st) {
   KB_CHECK_ARG(a.C <= 1024, "block_bwd_dx: C too large");
   static int col = -1;
@@ -1409,6 +1433,26 @@ int kbk_mask_bwd_stats(void* d_inout, const void* z, const float* ma, const floa
     mask_bwd_stats_vec_kernel<float><<<kb_ceil_div(B, kStatsBoardsPerCta), 256, 0, st>>>((float*)d_inout, (const float*)z, B, C, ma, mb, board_sum, sums);
   else
     mask_bwd_stats_vec_kernel<bf16><<<kb_ceil_div(B, kStatsBoardsPerCta), 256, 0, st>>>((bf16*)d_inout, (const bf16*)z, B, C, ma, mb, board_sum, sums);
+  KB_CUDA_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+// Statistics only: `d` is left unmasked (see kbk_bn_bwd_apply_masked). Column kernels only.
+int kbk_mask_bwd_stats_ro_supported(int C) {
+  static int col = -1;
+  if (col < 0) { const char* e = getenv("KB_COL_KERNELS"); col = (e && e[0] == '0') ? 0 : 1; }
+  return col && col_ok(C) ? 1 : 0;
+}
+
+int kbk_mask_bwd_stats_ro(const void* d, const void* z, const float* ma, const float* mb, float* board_sum, int B, int C,
+                          int dtype, double* sums, cudaStream_t st) {
+  KB_CHECK_ARG(kbk_mask_bwd_stats_ro_supported(C), "mask_bwd_stats_ro: unsupported channel count %d", C);
+  if (B == 0) return KB_OK;
+  KB_CHECK_ARG(ma != nullptr && mb != nullptr, "mask_bwd_stats_ro: mask coefficients missing");
+  const int grid = col_grid(B, C);
+  if (dtype == KB_F32) { mask_bwd_stats_col_kernel<float, 3, false><<<grid, 256, 0, st>>>((float*)d, (const float*)z, B, C, ma, mb, board_sum, sums); }
+  else if (col_small(B, C)) { mask_bwd_stats_col_kernel<bf16, 9, false><<<grid, 256, 0, st>>>((bf16*)d, (const bf16*)z, B, C, ma, mb, board_sum, sums); }
+  else { mask_bwd_stats_col_kernel<bf16, 3, false><<<grid, 256, 0, st>>>((bf16*)d, (const bf16*)z, B, C, ma, mb, board_sum, sums); }
   KB_CUDA_LAUNCH_CHECK();
   return KB_OK;
 }

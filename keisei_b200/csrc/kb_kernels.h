@@ -175,6 +175,14 @@ int kbk_relu_bwd_stats(const void* dy, const void* y, const void* z, void* dzh, 
 int kbk_mask_bwd_stats_supported(int C);
 int kbk_mask_bwd_stats(void* d_inout, const void* z, const float* ma, const float* mb, float* board_sum, int B, int C,
                        int dtype, double* sums, cudaStream_t st);
+// Two-pass variant of the pair above (one tensor pass less per residual block): the statistics kernel leaves `d`
+// unmasked and the BatchNorm-backward apply recomputes the mask from z: dz = k1 * (d * [z*ma+mb > 0]) - k2*z - k3.
+int kbk_mask_bwd_stats_ro_supported(int C);
+int kbk_mask_bwd_stats_ro(const void* d, const void* z, const float* ma, const float* mb, float* board_sum, int B, int C,
+                          int dtype, double* sums, cudaStream_t st);
+int kbk_bn_bwd_apply_masked_supported(long long rows, int C);
+int kbk_bn_bwd_apply_masked(void* d_inout, const void* z, const float* k1, const float* k2, const float* k3, const float* ma,
+                            const float* mb, long long rows, int C, int dtype, cudaStream_t st);
 // fp32 [M][C] variant for the policy head (mask by act > 0)
 int kbk_relu_bwd_stats_f32(float* d_inout, const float* act, const float* z, long long M, int C, double* sums,
                            cudaStream_t st);

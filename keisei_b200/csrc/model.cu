@@ -679,11 +679,21 @@ extern "C" int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* 
     const bool tc_conv = use_tc && B >= 3 && kbk_conv3x3_tc_supported(C, C, dtype);
     static int fused_env = -1;
     if (fused_env < 0) { const char* fe = getenv("KB_FUSED_DGRAD"); fused_env = (fe && fe[0] == '1') ? 1 : 0; }
+    // The ReLU mask is a function of z1 alone (a1 = relu(bn1(z1)) + gbias), so the statistics pass does not write the
+    // masked gradient back: the dz1 pass below recomputes the mask (KB_MASK_RECOMPUTE=0 restores the three-pass form).
+    static int mask_recompute_env = -1;
+    if (mask_recompute_env < 0) { const char* me = getenv("KB_MASK_RECOMPUTE"); mask_recompute_env = (me && me[0] == '0') ? 0 : 1; }
+    bool mask_pending = false;
     if (tc_conv && kbk_mask_bwd_stats_supported(C) && !fused_env) {
       ConvEpi e = epi_base();
       KB_TRY(conv3x3(m, t1, wp.wd(i, 1), t2, C, C, e, use_tc, num_sms, st));
       if (overlap && !wg_first) KB_TRY(conv2_wgrad());
-      KB_TRY(kbk_mask_bwd_stats(t2, bw.z1, w.bn_a(l1), w.bn_b(l1), w.dg, B, C, dtype, w.dsums, st));
+      if (mask_recompute_env && kbk_mask_bwd_stats_ro_supported(C) && kbk_bn_bwd_apply_masked_supported(m.M, C)) {
+        KB_TRY(kbk_mask_bwd_stats_ro(t2, bw.z1, w.bn_a(l1), w.bn_b(l1), w.dg, B, C, dtype, w.dsums, st));
+        mask_pending = true;
+      } else {
+        KB_TRY(kbk_mask_bwd_stats(t2, bw.z1, w.bn_a(l1), w.bn_b(l1), w.dg, B, C, dtype, w.dsums, st));
+      }
     } else {
       ConvEpi e = epi_base();
       e.mask_src = bw.z1; e.mask_a = w.bn_a(l1); e.mask_b = w.bn_b(l1);
@@ -705,7 +715,8 @@ extern "C" int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* 
       KB_TRY(grp.close());
     }
     // pass C: dz1 in place; conv1 weight + data gradients
-    KB_TRY(kbk_bn_bwd_apply(t2, bw.z1, k1, k2, k3, m.M, C, dtype, st));
+    if (mask_pending) KB_TRY(kbk_bn_bwd_apply_masked(t2, bw.z1, k1, k2, k3, w.bn_a(l1), w.bn_b(l1), m.M, C, dtype, st));
+    else KB_TRY(kbk_bn_bwd_apply(t2, bw.z1, k1, k2, k3, m.M, C, dtype, st));
     auto conv1_wgrad = [&]() -> int {  // side stream: released at this point of the main stream
       KB_CUDA_CHECK(cudaEventRecord(ev(i, 1), st));
       KB_CUDA_CHECK(cudaStreamWaitEvent(wst, ev(i, 1), 0));

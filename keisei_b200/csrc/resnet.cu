@@ -363,11 +363,17 @@ extern "C" int kb_resnet_backward(const kb_resnet_desc* d, const void* const* pa
     KB_TRY(conv3x3(m, t1, wp.wd(i, 1), t2, C, C, e, use_tc, num_sms, st));
     // ReLU mask of a1, BN1 backward -> dz1
     // a1 = relu(bn1(z1)): the mask is a function of z1 and the BN1 affine, so a1 is not re-read (3 passes instead of 4)
-    if (kbk_mask_bwd_stats_supported(C)) KB_TRY(kbk_mask_bwd_stats(t2, bw.z1, w.bn_a(l1), w.bn_b(l1), nullptr, B, C, dtype, w.dsums, st));
+    // ... and the masked gradient is not written back either: the dz1 pass recomputes the mask (2 + 3 passes)
+    static int mask_recompute_env = -1;
+    if (mask_recompute_env < 0) { const char* me = getenv("KB_MASK_RECOMPUTE"); mask_recompute_env = (me && me[0] == '0') ? 0 : 1; }
+    const bool mask_pending = mask_recompute_env && kbk_mask_bwd_stats_ro_supported(C) && kbk_bn_bwd_apply_masked_supported(m.M, C);
+    if (mask_pending) KB_TRY(kbk_mask_bwd_stats_ro(t2, bw.z1, w.bn_a(l1), w.bn_b(l1), nullptr, B, C, dtype, w.dsums, st));
+    else if (kbk_mask_bwd_stats_supported(C)) KB_TRY(kbk_mask_bwd_stats(t2, bw.z1, w.bn_a(l1), w.bn_b(l1), nullptr, B, C, dtype, w.dsums, st));
     else KB_TRY(kbk_relu_bwd_stats(t2, bw.a1, bw.z1, t2, m.M, C, dtype, w.dsums, st));
     KB_TRY(kbk_bn_bwd_finalize(w.dsums, count, P(pi_blk(i, 1)), w.bn_mean(l1), w.bn_invstd(l1), k1, k2, k3, G(pi_blk(i, 1)),
                                G(pi_blk(i, 2)), C, st));
-    KB_TRY(kbk_bn_bwd_apply(t2, bw.z1, k1, k2, k3, m.M, C, dtype, st));
+    if (mask_pending) KB_TRY(kbk_bn_bwd_apply_masked(t2, bw.z1, k1, k2, k3, w.bn_a(l1), w.bn_b(l1), m.M, C, dtype, st));
+    else KB_TRY(kbk_bn_bwd_apply(t2, bw.z1, k1, k2, k3, m.M, C, dtype, st));
     if (overlap) { KB_CUDA_CHECK(cudaEventRecord(ev(i, 1), st)); KB_CUDA_CHECK(cudaStreamWaitEvent(wst, ev(i, 1), 0)); }
     KB_TRY(wgrad3x3(m, x_in, t2, G(pi_blk(i, 0)), C, C, C, use_tc, num_sms, w.wg_ws, w.wg_ws_bytes, wst));
     if (overlap) {

@@ -14,7 +14,10 @@ What is swapped (and nothing else):
     dataclass (`katago_loop.py:538-541` isinstance check) — the trainer only reads its fields;
   * `keisei.training.gae.compute_gae{,_padded,_gpu,_padded_gpu}` -> the kernel-backed functions of `keisei_b200.gae`
     (same signatures); `update()` resolves them through that module's attributes at call time, so a test or caller that
-    patches `keisei.training.gae.compute_gae_padded` is still seen (reference tests/test_split_merge_gae_opt.py:336-372).
+    patches `keisei.training.gae.compute_gae_padded` is still seen (reference tests/test_split_merge_gae_opt.py:336-372);
+  * `keisei.training.katago_loop.split_merge_step` (when that module is importable: it pulls in the reference's whole
+    loop) -> `keisei_b200.split_merge.split_merge_step`: same signature and result type, host-side partition, grouped
+    CUDA-graph forwards for the learner + opponents (reference katago_loop.py:284-431, called at :1179-1198).
 """
 from __future__ import annotations
 
@@ -24,6 +27,7 @@ from typing import Any
 
 from . import gae as kb_gae
 from . import katago_ppo as kb_ppo
+from . import split_merge as kb_split_merge
 from .models.resnet import ResNetModel, ResNetParams
 from .models.se_resnet import SEResNetModel, SEResNetParams
 
@@ -56,7 +60,7 @@ def installed() -> bool:
     return bool(_PATCHED or _REGISTRY_PATCHED)
 
 
-def install_into_reference(resnet: bool = True) -> None:
+def install_into_reference(resnet: bool = True, split_merge: bool = True) -> None:
     """Idempotent. Needs an importable `keisei` (the reference); raises ImportError otherwise."""
     if installed():
         return
@@ -89,6 +93,18 @@ def install_into_reference(resnet: bool = True) -> None:
         if getattr(ref_ppo, n, None) is _PATCHED[-1][2]:        # katago_ppo.py:15 binds compute_gae_gpu by name
             _PATCHED.append((ref_ppo, n, getattr(ref_ppo, n)))
             setattr(ref_ppo, n, getattr(kb_gae, n))
+    if split_merge:
+        try:
+            import keisei.training.katago_loop as ref_loop     # noqa: PLC0415 — needs the loop's own dependencies
+        except ImportError:
+            ref_loop = None
+        if ref_loop is not None and hasattr(ref_loop, "split_merge_step"):
+            _PATCHED.append((ref_loop, "split_merge_step", ref_loop.split_merge_step))
+            ref_loop.split_merge_step = kb_split_merge.split_merge_step
+            for n in _TRAINER_NAMES:                            # the loop module was imported just now: same swap as above
+                if getattr(ref_loop, n, None) is originals[n]:
+                    _PATCHED.append((ref_loop, n, originals[n]))
+                    setattr(ref_loop, n, replacements[n])
 
 
 def uninstall_from_reference() -> None:

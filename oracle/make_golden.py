@@ -342,6 +342,50 @@ def golden_buffer():
     print("buffer.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB raw")
 
 
+def golden_split_merge():
+    """The reference's `split_merge_step` (katago_loop.py:284-431) on CPU with three real tiny models: cohort mode with a
+    per-env learner side and a blending value adapter, and legacy single-opponent mode. The sampled actions depend on
+    torch's CPU generator (seeded right before each call)."""
+    from keisei.training.katago_loop import split_merge_step
+    from keisei.training.model_registry import build_model
+    from keisei.training.value_adapter import get_value_adapter
+    N, A = 12, 11259
+    out = {}
+    models = []
+    for k in range(3):
+        torch.manual_seed(10 + k)
+        m = build_model("se_resnet", dict(TINY))
+        m.train()
+        with torch.no_grad():
+            m(torch.randn(16, 50, 9, 9))      # non-trivial BatchNorm running statistics
+        m.eval()
+        models.append(m)
+        for name, v in m.state_dict().items():
+            out[f"sd{k}/{name}"] = _np(v)
+    g = torch.Generator().manual_seed(21)
+    obs = torch.randn(N, 50, 9, 9, generator=g)
+    mask = torch.rand(N, A, generator=g) < 0.01
+    mask[torch.arange(N), torch.randint(0, A, (N,), generator=g)] = True
+    players = torch.randint(0, 2, (N,), generator=g).numpy().astype(np.uint8)
+    side = torch.randint(0, 2, (N,), generator=g).numpy().astype(np.uint8)
+    opp_ids = torch.randint(0, 2, (N,), generator=g).numpy().astype(np.int64)
+    out.update(obs=_np(obs), mask=_np(mask), players=players, side=side, opp_ids=opp_ids)
+    ad = get_value_adapter("multi_head", 1.5, 0.02, 0.3)
+    torch.manual_seed(123)
+    r = split_merge_step(obs=obs, legal_masks=mask, current_players=players, learner_model=models[0],
+                         opponent_models={0: models[1], 1: models[2], 7: models[1]}, env_opponent_ids=opp_ids, learner_side=side,
+                         value_adapter=ad)
+    for f in ("actions", "learner_mask", "opponent_mask", "learner_log_probs", "learner_values", "learner_indices"):
+        out[f"cohort/{f}"] = _np(getattr(r, f))
+    torch.manual_seed(321)
+    r = split_merge_step(obs=obs, legal_masks=mask, current_players=players, learner_model=models[0], opponent_model=models[2],
+                         learner_side=1)
+    for f in ("actions", "learner_mask", "opponent_mask", "learner_log_probs", "learner_values", "learner_indices"):
+        out[f"legacy/{f}"] = _np(getattr(r, f))
+    np.savez_compressed(OUT / "split_merge.npz", **out)
+    print("split_merge.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB raw")
+
+
 if __name__ == "__main__":
     if not REF.exists():
         sys.exit("needs /root/reference (build container only)")
@@ -354,3 +398,4 @@ if __name__ == "__main__":
     golden_update()
     golden_resnet()
     golden_buffer()
+    golden_split_merge()

@@ -17,7 +17,7 @@ ROOT = Path(__file__).resolve().parent.parent
 REF = Path(os.environ.get("KEISEI_REFERENCE", "/root/reference"))
 FILES = ["test_katago_ppo.py", "test_se_resnet.py", "test_value_adapter.py", "test_pytorch_training_gaps.py", "test_amp.py",
          "test_split_merge_gae_opt.py", "test_gae.py", "test_gae_batched.py", "test_registries.py", "test_model_variants.py",
-         "test_pytorch_amp_pipeline.py", "test_katago_loop.py"]
+         "test_pytorch_amp_pipeline.py", "test_katago_loop.py", "test_split_merge.py", "test_katago_loop_integration.py"]
 NEEDS_CUDA = ["tests/test_amp.py::TestGradScalerCheckpoint::test_scaler_state_round_trip",
               "tests/test_pytorch_amp_pipeline.py::TestGradScalerCheckpointRoundTrip::test_scaler_state_survives_save_load"]
 
@@ -42,7 +42,7 @@ def test_reference_hot_path_tests_pass_on_top_of_the_shim(tmp_path):
     tail = p.stdout[-4000:]
     m = re.search(r"(\d+) passed", tail)
     assert p.returncode == 0 and m, tail + p.stderr[-2000:]
-    assert int(m.group(1)) >= 275 and "failed" not in tail.splitlines()[-1], tail
+    assert int(m.group(1)) >= 336 and "failed" not in tail.splitlines()[-1], tail
 
 
 def test_shim_swaps_and_restores_every_seam():
@@ -52,12 +52,14 @@ import keisei.training.katago_loop as loop, keisei.training.katago_ppo as ref_pp
 import keisei.training.model_registry as ref_reg
 from keisei.training.models.se_resnet import SEResNetModel as RefModel, SEResNetParams as RefParams
 from keisei.training.models.katago_base import KataGoBaseModel as RefBase
-import keisei_b200.dropin as dropin, keisei_b200.katago_ppo as kb_ppo, keisei_b200.gae as kb_gae
+import keisei_b200.dropin as dropin, keisei_b200.katago_ppo as kb_ppo, keisei_b200.gae as kb_gae, keisei_b200.split_merge as kb_sm
 from keisei_b200.models import SEResNetModel
 orig = (loop.KataGoPPOAlgorithm, loop.KataGoRolloutBuffer, ref_gae.compute_gae_padded, ref_reg._REGISTRY["se_resnet"])
+orig_sm = loop.split_merge_step
 dropin.install_into_reference(); dropin.install_into_reference()   # idempotent
 assert loop.KataGoPPOAlgorithm is kb_ppo.KataGoPPOAlgorithm and ref_ppo.KataGoRolloutBuffer is kb_ppo.KataGoRolloutBuffer
 assert ref_gae.compute_gae_padded is kb_gae.compute_gae_padded and ref_ppo.compute_gae_gpu is kb_gae.compute_gae_gpu
+assert loop.split_merge_step is kb_sm.split_merge_step and kb_sm._result_type() is loop.SplitMergeResult
 m = ref_reg.build_model("se_resnet", dict(num_blocks=1, channels=16, se_reduction=4, global_pool_channels=8, policy_channels=8, value_fc_size=8, score_fc_size=8))
 assert isinstance(m, SEResNetModel) and isinstance(m, RefModel) and isinstance(m, RefBase) and isinstance(m.params, RefParams)
 assert type(m).__name__ == "SEResNetModel"
@@ -69,6 +71,7 @@ ref_gae.compute_gae_padded = spy
 assert kb_ppo._gae_fn("compute_gae_padded") is spy
 ref_gae.compute_gae_padded = kb_gae.compute_gae_padded
 dropin.uninstall_from_reference()
+assert loop.split_merge_step is orig_sm
 assert (loop.KataGoPPOAlgorithm, loop.KataGoRolloutBuffer, ref_gae.compute_gae_padded, ref_reg._REGISTRY["se_resnet"]) == orig
 assert kb_ppo._gae_fn("compute_gae_padded") is kb_gae.compute_gae_padded   # pristine reference function: ours is used
 print("ok")
