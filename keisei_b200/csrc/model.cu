@@ -614,10 +614,21 @@ extern "C" int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* 
   if (overlap) {
     int dev = 0;
     KB_CUDA_CHECK(cudaGetDevice(&dev));
-    KB_TRY(side.ensure(dev, 4 * m.nb + 1));
+    KB_TRY(side.ensure(dev, 6 * m.nb + 1));
   }
   cudaStream_t wst = overlap ? side.s : st;
-  auto ev = [&](int blk, int k) { return side.ev[4 * blk + k]; };
+  // The global-pool-bias MLP backward of a block (two grouped launches of small TF32 GEMMs, 2 x 68 us at 8192 samples and
+  // 2 x 25 us at 1024: latency- / L2-bound) has one consumer on the main chain, the block's dx pass (dpool), so it CAN run
+  // on a second side stream under the HBM-bound dz1 pass and the conv1 data gradient: events [4] dg ready (main ->
+  // gst), [5] MLP backward done (gst -> main, before the dx pass). Measured on B200 (same box, interleaved): SLOWER —
+  // 197.5 / 199.3 ms against 192.7 / 193.9 ms per 8192-sample step, 29.6 / 29.8 against 29.0 / 29.1 ms at 1024 samples —
+  // the co-running kernels take more from the dz1 pass and the convolutions than the GEMMs' own time. Off unless
+  // KB_BWD_MLP_SIDE=1.
+  static int mlp_side_env = -1;
+  if (mlp_side_env < 0) { const char* e = getenv("KB_BWD_MLP_SIDE"); mlp_side_env = (e && e[0] == '1') ? 1 : 0; }
+  const bool mlp_side = overlap && mlp_side_env;
+  cudaStream_t gst = mlp_side ? side.s2 : st;
+  auto ev = [&](int blk, int k) { return side.ev[6 * blk + k]; };
   auto bucket_ready = [&](int bucket, int first_param, int n_params) -> int {
     if (g_bucket_hook == nullptr) return KB_OK;
     const int hr = g_bucket_hook(g_bucket_user, bucket, first_param, n_params, (kb_stream_t)st, (kb_stream_t)wst);
@@ -705,14 +716,16 @@ extern "C" int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* 
     // global-pool-bias MLP backward -> gradient wrt the pool statistics of the block input: four small GEMMs and two
     // bias column sums as TWO grouped launches (the members of a group are independent of one another)
     {
-      GemmGroupScope grp(st);
+      if (mlp_side) { KB_CUDA_CHECK(cudaEventRecord(ev(i, 4), st)); KB_CUDA_CHECK(cudaStreamWaitEvent(gst, ev(i, 4), 0)); }
+      GemmGroupScope grp(gst);
       KB_TRY(grp.status());
-      KB_TRY(linear_bwd_w(w.dg, KB_F32, C, bw.gh, KB_F32, m.G, B, C, m.G, G(pi_blk(i, 8)), G(pi_blk(i, 9)), st));
-      KB_TRY(linear_bwd_x(w.dg, KB_F32, C, B, C, P(pi_blk(i, 8)), m.G, w.dgh, KB_F32, m.G, bw.gh, m.G, 0, st));
+      KB_TRY(linear_bwd_w(w.dg, KB_F32, C, bw.gh, KB_F32, m.G, B, C, m.G, G(pi_blk(i, 8)), G(pi_blk(i, 9)), gst));
+      KB_TRY(linear_bwd_x(w.dg, KB_F32, C, B, C, P(pi_blk(i, 8)), m.G, w.dgh, KB_F32, m.G, bw.gh, m.G, 0, gst));
       KB_TRY(grp.flush());   // dgh is complete before anything reads it
-      KB_TRY(linear_bwd_w(w.dgh, KB_F32, m.G, pool_in, KB_F32, 3 * C, B, m.G, 3 * C, G(pi_blk(i, 6)), G(pi_blk(i, 7)), st));
-      KB_TRY(linear_bwd_x(w.dgh, KB_F32, m.G, B, m.G, P(pi_blk(i, 6)), 3 * C, w.dpool, KB_F32, 3 * C, nullptr, 0, 0, st));
+      KB_TRY(linear_bwd_w(w.dgh, KB_F32, m.G, pool_in, KB_F32, 3 * C, B, m.G, 3 * C, G(pi_blk(i, 6)), G(pi_blk(i, 7)), gst));
+      KB_TRY(linear_bwd_x(w.dgh, KB_F32, m.G, B, m.G, P(pi_blk(i, 6)), 3 * C, w.dpool, KB_F32, 3 * C, nullptr, 0, 0, gst));
       KB_TRY(grp.close());
+      if (mlp_side) KB_CUDA_CHECK(cudaEventRecord(ev(i, 5), gst));
     }
     // pass C: dz1 in place; conv1 weight + data gradients
     if (mask_pending) KB_TRY(kbk_bn_bwd_apply_masked(t2, bw.z1, k1, k2, k3, w.bn_a(l1), w.bn_b(l1), m.M, C, dtype, st));
@@ -740,13 +753,14 @@ extern "C" int kb_seresnet_backward_sync(const kb_seresnet_desc* d, const void* 
     pd.mask_out = 1;  // hand du (masked by the producer's ReLU) to block i-1 / the stem
     if (i > 0) { pd.z_next = blks[i - 1].z2; pd.s_du = w.s_du; pd.s_duz = w.s_duz; }
     if (overlap && i + 1 < m.nb) KB_CUDA_CHECK(cudaStreamWaitEvent(st, ev(i + 1, 3), 0));
+    if (mlp_side) KB_CUDA_CHECK(cudaStreamWaitEvent(st, ev(i, 5), 0));   // dpool (and the MLP's four gradients) are complete
     KB_TRY(kbk_block_bwd_dx(pd, st));
     void* nc = t3; t3 = t2; t2 = t1; t1 = cur; cur = nc;
     KB_TRY(bucket_ready(i, pi_blk(i, 0), 14));     // all 14 gradients of block i are enqueued (weight gradients on `wst`)
   }
   if (overlap) {  // join: the stem's weight gradient reuses the partial-tile workspace, and the caller sees one stream
-    KB_CUDA_CHECK(cudaEventRecord(side.ev[4 * m.nb], wst));
-    KB_CUDA_CHECK(cudaStreamWaitEvent(st, side.ev[4 * m.nb], 0));
+    KB_CUDA_CHECK(cudaEventRecord(side.ev[6 * m.nb], wst));
+    KB_CUDA_CHECK(cudaStreamWaitEvent(st, side.ev[6 * m.nb], 0));
   }
 
   // ---- stem ----

@@ -91,16 +91,18 @@ struct GemmGroupScope {
 // stream-ordered semantics. KB_BWD_OVERLAP=0 disables it; it is also off while the caller's stream is being captured.
 struct SideStream {
   cudaStream_t s = nullptr;
+  cudaStream_t s2 = nullptr;   // second side stream: the small global-pool-MLP backward GEMMs (model.cu), off the main chain
   cudaEvent_t* ev = nullptr;
   int n_ev = 0, device = -1;
   ~SideStream() {
     for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
     free(ev);
     if (s) cudaStreamDestroy(s);
+    if (s2) cudaStreamDestroy(s2);
   }
   int ensure(int device_id, int events) {
     if (s == nullptr || device != device_id) {
-      if (s) { for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]); free(ev); ev = nullptr; n_ev = 0; cudaStreamDestroy(s); s = nullptr; }
+      if (s) { for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]); free(ev); ev = nullptr; n_ev = 0; cudaStreamDestroy(s); s = nullptr; if (s2) { cudaStreamDestroy(s2); s2 = nullptr; } }
       int lo = 0, hi = 0;
       KB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       // Lowest priority (= the default stream's): measured on B200, a high-priority side stream does not help — the
@@ -110,6 +112,7 @@ struct SideStream {
       static int prio_hi = -1;
       if (prio_hi < 0) { const char* e = getenv("KB_SIDE_PRIO"); prio_hi = (e && e[0] == 'h') ? 1 : 0; }
       KB_CUDA_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi ? hi : lo));
+      KB_CUDA_CHECK(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, lo));
       device = device_id;
     }
     if (events > n_ev) {
