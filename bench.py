@@ -699,7 +699,31 @@ def bench_league(algo, device, rank, world) -> dict:
         for _ in range(128):
             algo.select_actions_many(subs)
     ms_grouped = timed(grouped128, 2, 3, device, world)
-    return {"metric": "league rollout positions/s (512 envs per GPU, 128 consecutive steps)", "value": world * Bl * 128 / (ms * 1e-3),
+    # the whole split-merge environment step through the reference's own entry point (katago_loop.py:284-431, swapped in
+    # by dropin.install_into_reference): host-side partition, gather, grouped forwards, sampling, merged scatter, and the
+    # actions read back on the host as the loop does for vecenv.step(); fixed 256 + 4 x 64 partition, then a fresh random
+    # partition every step (sub-batch sizes vary -> bucketed graphs)
+    import numpy as np
+    from keisei_b200.split_merge import split_merge_step
+    base = algo.forward_model
+    opponents = {k: base for k in range(4)}
+    players_fixed = np.concatenate([np.zeros(256, np.uint8), np.ones(256, np.uint8)])
+    ids_fixed = np.concatenate([np.zeros(256, np.int64), np.repeat(np.arange(4), 64)])
+    rng = np.random.default_rng(5 + rank)
+    randoms = [(rng.integers(0, 2, Bl).astype(np.uint8), rng.integers(0, 4, Bl).astype(np.int64)) for _ in range(16)]
+    def sm128(parts_of):
+        def run():
+            for i in range(128):
+                players, ids = parts_of(i)
+                r = split_merge_step(obs, mask, players, base, opponent_models=opponents, env_opponent_ids=ids, learner_side=0)
+                r.actions.cpu()
+        return run
+    ms_sm = timed(sm128(lambda i: (players_fixed, ids_fixed)), 2, 3, device, world)
+    ms_sm_rand = timed(sm128(lambda i: randoms[i % 16]), 2, 3, device, world)
+    sm = {"what": "split_merge_step (partition + gather + grouped forwards + sampling + scatter + actions D2H) per 512-env step",
+          "fixed_256_4x64": world * Bl * 128 / (ms_sm * 1e-3), "random_partition_each_step": world * Bl * 128 / (ms_sm_rand * 1e-3),
+          "unit": "positions/s", "ms_per_128_steps": [ms_sm, ms_sm_rand]}
+    return {"split_merge_step": sm, "metric": "league rollout positions/s (512 envs per GPU, 128 consecutive steps)", "value": world * Bl * 128 / (ms * 1e-3),
             "unit": "positions/s", "ms_per_128_steps": ms, "envs_per_gpu": Bl, "scaling": "weak",
             "split_variant": {"value": world * Bl * 128 / (ms_split * 1e-3), "unit": "positions/s", "ms_per_128_steps": ms_split,
                               "sub_batches": "256 learner + 4 x 64 opponents (same weights: synthetic)",
