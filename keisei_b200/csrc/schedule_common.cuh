@@ -61,7 +61,8 @@ inline int linear_bwd_w(const void* dy, int dy_dtype, long long ldy, const void*
   g.C = dW; g.c_dtype = KB_F32; g.ldc = K;
   g.M = N; g.N = K; g.K = M;
   const int tiles = kb_ceil_div(N, 64) * kb_ceil_div(K, 64);
-  int sk = kb_ceil_div(148 * 5, tiles);  // ~5 resident CTAs per SM: the K loop is a 1-deep prefetch, latency is hidden by occupancy
+  static const int ctas_per_sm = [] { const char* e = getenv("KB_WGEMM_CTAS"); const int v = e ? atoi(e) : 5; return v < 1 ? 1 : v; }();
+  int sk = kb_ceil_div(148 * ctas_per_sm, tiles);  // ~5 resident CTAs per SM: the K loop is a 1-deep prefetch, latency is hidden by occupancy
   const int max_sk = kb_ceil_div(M, 64);
   if (sk > max_sk) sk = max_sk;
   g.splitk = sk < 2 ? 2 : sk;  // always the atomic epilogue: dW accumulates into the pre-zeroed gradient
