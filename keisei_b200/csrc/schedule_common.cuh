@@ -61,8 +61,11 @@ inline int linear_bwd_w(const void* dy, int dy_dtype, long long ldy, const void*
   g.C = dW; g.c_dtype = KB_F32; g.ldc = K;
   g.M = N; g.N = K; g.K = M;
   const int tiles = kb_ceil_div(N, 64) * kb_ceil_div(K, 64);
-  static const int ctas_per_sm = [] { const char* e = getenv("KB_WGEMM_CTAS"); const int v = e ? atoi(e) : 5; return v < 1 ? 1 : v; }();
-  int sk = kb_ceil_div(148 * ctas_per_sm, tiles);  // ~5 resident CTAs per SM: the K loop is a 1-deep prefetch, latency is hidden by occupancy
+  static const int ctas_per_sm = [] { const char* e = getenv("KB_WGEMM_CTAS"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+  // K slices for ~2 CTAs per SM. Measured on B200 with the lean main loop (same box, interleaved; KB_WGEMM_CTAS): 8192-sample
+  // step 196.0 / 197.6 ms at 5 per SM, 194.7 / 195.4 ms at 2, 196.6 / 195.8 ms at 3; 1024 samples 28.0 / 28.1 / 27.7 ms —
+  // fewer, longer slices mean fewer atomic partial tiles (a 128 x 768 gradient was being written 31 times).
+  int sk = kb_ceil_div(148 * ctas_per_sm, tiles);
   const int max_sk = kb_ceil_div(M, 64);
   if (sk > max_sk) sk = max_sk;
   g.splitk = sk < 2 ? 2 : sk;  // always the atomic epilogue: dW accumulates into the pre-zeroed gradient
